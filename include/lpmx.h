@@ -1,0 +1,253 @@
+/* lpmx.h -- C ABI of the B200-native direct-sum engine for LPM's spherical particle solvers.
+ *
+ * This is the drop-in boundary.  pbosler/lpm has no FFI layer: its de-facto
+ * operator interface is the Kokkos functor constructors and the time-stepper entry points, all of
+ * which take Kokkos Views by value.  Every function below names the reference interface it stands
+ * in for (file:line under /root/reference/src).  A maintainer's binding passes `view.data()`,
+ * the extents and the layout of the View (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; no C++/torch types; every function returns an int
+ *     (LPMX_OK == 0, negative = error) and never throws.  lpmx_last_error_string() gives detail.
+ *   - Real = double, Index = int, mask = unsigned char (Kokkos View<bool*>), as in
+ *     LpmConfig.h.in:31-32 and lpm_kokkos_defs.hpp:31-39.
+ *   - every array argument may be a DEVICE pointer (Kokkos CUDA build: used in place, no copy)
+ *     or a HOST pointer (Kokkos OpenMP/Serial build: staged through pinned memory; the copies are
+ *     part of the call).  The library detects which with cudaPointerGetAttributes.
+ *   - `layout` describes Real*[3] Views: LPMX_LAYOUT_RIGHT is x[i*3+k] (Kokkos LayoutRight, the
+ *     host default), LPMX_LAYOUT_LEFT is x[k*ld+i] (Kokkos LayoutLeft, the CUDA default,
+ *     lpm_geometry.hpp:261-263).  `ld` is the leading dimension (>= n) for LAYOUT_LEFT and is
+ *     ignored for LAYOUT_RIGHT.
+ *   - calls are asynchronous on the handle's stream when all pointers are device pointers;
+ *     lpmx_sync() waits.  Calls with host pointers return after results are in the host buffers.
+ *   - there is NO CPU fallback: without a CUDA device lpmx_create fails with LPMX_ERR_NO_DEVICE.
+ *     Only the mesh generator (host code in the reference too) works without a GPU.
+ */
+#ifndef LPMX_H
+#define LPMX_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPMX_VERSION_MAJOR 0
+#define LPMX_VERSION_MINOR 1
+
+/* error codes */
+#define LPMX_OK 0
+#define LPMX_ERR_INVALID (-1)     /* bad argument (null pointer, negative size, unknown enum) */
+#define LPMX_ERR_CUDA (-2)        /* a CUDA runtime call or kernel failed */
+#define LPMX_ERR_NOMEM (-3)       /* host or device allocation failed */
+#define LPMX_ERR_NO_DEVICE (-4)   /* no usable CUDA device: the engine has no CPU fallback */
+#define LPMX_ERR_COMM (-5)        /* NCCL / multi-GPU exchange failed */
+#define LPMX_ERR_UNSUPPORTED (-6) /* recognised but out-of-scope request */
+#define LPMX_ERR_STATE (-7)       /* call sequence error (e.g. advance before set_state) */
+
+/* layouts of Real*[3] views */
+#define LPMX_LAYOUT_RIGHT 0 /* x[i*3+k]  */
+#define LPMX_LAYOUT_LEFT 1  /* x[k*ld+i] */
+
+/* mesh seeds (reference: src/mesh/lpm_mesh_seed.hpp:111-147) */
+#define LPMX_SEED_ICOS_TRI_SPHERE 0
+#define LPMX_SEED_CUBED_SPHERE 1
+
+typedef struct lpmx_handle_s* lpmx_handle_t;
+typedef struct lpmx_mesh_s* lpmx_mesh_t;
+typedef struct lpmx_bve_solver_s* lpmx_bve_solver_t;
+typedef struct lpmx_ic2d_solver_s* lpmx_ic2d_solver_t;
+
+const char* lpmx_version_string(void);
+const char* lpmx_error_name(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * Mesh generator (HOST; deterministic; no GPU needed).
+ * Replaces PolyMesh2d<Seed>::tree_init (src/mesh/lpm_polymesh2d_impl.hpp:25-42) with
+ * MeshSeed<Seed> (src/mesh/lpm_mesh_seed.cpp:10-18,20-206), FaceDivider<..>::divide
+ * (src/mesh/lpm_faces_impl.hpp:284-431 tri, :433-574 quad) and Edges::divide
+ * (src/mesh/lpm_edges.cpp:58-96) for uniform refinement of the two spherical seeds.
+ * ------------------------------------------------------------------------------------------ */
+
+/* MeshSeed<Seed>::set_max_allocations (src/mesh/lpm_mesh_seed.cpp:266-279) */
+int lpmx_mesh_max_allocations(int seed, int depth, int* n_verts, int* n_edges, int* n_faces);
+
+/* Build the tree mesh of `depth` uniform refinements on a sphere of `radius`. */
+int lpmx_mesh_create(int seed, int depth, double radius, lpmx_mesh_t* mesh);
+int lpmx_mesh_destroy(lpmx_mesh_t mesh);
+
+/* counts after refinement: vertices.nh(), edges.nh(), faces.nh(), faces.n_leaves_host(),
+ * edges.n_leaves_host(), vertices per face (3 or 4) */
+int lpmx_mesh_sizes(lpmx_mesh_t mesh, int* n_verts, int* n_edges, int* n_faces, int* n_face_leaves,
+                    int* n_edge_leaves, int* n_face_verts);
+
+/* array ids for lpmx_mesh_array: element type and extent in the comment */
+#define LPMX_MESH_VERT_XYZ 0       /* double[n_verts][3]  vertices.phys_crds (LayoutRight)        */
+#define LPMX_MESH_VERT_LAG_XYZ 1   /* double[n_verts][3]  vertices.lag_crds                      */
+#define LPMX_MESH_VERT_CRD_INDS 2  /* int[n_verts]        vertices.crd_inds                      */
+#define LPMX_MESH_EDGE_ORIGS 3     /* int[n_edges]        edges.origs                            */
+#define LPMX_MESH_EDGE_DESTS 4     /* int[n_edges]        edges.dests                            */
+#define LPMX_MESH_EDGE_LEFTS 5     /* int[n_edges]        edges.lefts                            */
+#define LPMX_MESH_EDGE_RIGHTS 6    /* int[n_edges]        edges.rights                           */
+#define LPMX_MESH_EDGE_PARENTS 7   /* int[n_edges]        edges.parent                           */
+#define LPMX_MESH_EDGE_KIDS 8      /* int[n_edges][2]     edges.kids                             */
+#define LPMX_MESH_FACE_XYZ 9       /* double[n_faces][3]  faces.phys_crds                        */
+#define LPMX_MESH_FACE_LAG_XYZ 10  /* double[n_faces][3]  faces.lag_crds                         */
+#define LPMX_MESH_FACE_AREA 11     /* double[n_faces]     faces.area  (0 for divided faces)      */
+#define LPMX_MESH_FACE_MASK 12     /* uchar[n_faces]      faces.mask  (1 for divided faces)      */
+#define LPMX_MESH_FACE_VERTS 13    /* int[n_faces][nfv]   faces.verts                            */
+#define LPMX_MESH_FACE_EDGES 14    /* int[n_faces][nfv]   faces.edges                            */
+#define LPMX_MESH_FACE_CRD_INDS 15 /* int[n_faces]        faces.crd_inds                         */
+#define LPMX_MESH_FACE_PARENT 16   /* int[n_faces]        faces.parent                           */
+#define LPMX_MESH_FACE_KIDS 17     /* int[n_faces][4]     faces.kids                             */
+#define LPMX_MESH_FACE_LEVEL 18    /* int[n_faces]        faces.level (root level defined as 1)  */
+#define LPMX_MESH_FACE_LEAF_IDX 19 /* int[n_faces]        faces.leaf_idx (exclusive scan)        */
+
+/* Returns a pointer (owned by the mesh, valid until lpmx_mesh_destroy) to the array and its
+ * element count; *is_real = 1 for double arrays, 0 for int arrays, 2 for unsigned char. */
+int lpmx_mesh_array(lpmx_mesh_t mesh, int array_id, const void** data, long* count, int* is_real);
+
+/* ------------------------------------------------------------------------------------------
+ * Engine handle: one per process and GPU.
+ * ------------------------------------------------------------------------------------------ */
+int lpmx_create(lpmx_handle_t* h, int device_id);
+int lpmx_destroy(lpmx_handle_t h);
+int lpmx_sync(lpmx_handle_t h);
+const char* lpmx_last_error_string(lpmx_handle_t h);
+/* cudaStream_t the handle launches on (as void*), for callers that time with CUDA events */
+int lpmx_stream(lpmx_handle_t h, void** cuda_stream);
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches claim) */
+int lpmx_launch_count(lpmx_handle_t h, long* n_launches);
+
+/* Target sharding over the GPUs of one box (the reference has no multi-device path; DESIGN.md
+ * section 6).  The concatenated target list (vertices then faces) is split into `world`
+ * contiguous index ranges; this handle evaluates range `rank`.  Default: rank 0 of 1. */
+int lpmx_set_partition(lpmx_handle_t h, int rank, int world);
+/* NCCL bootstrap: rank 0 calls lpmx_comm_unique_id, the host program ships the 128 bytes to
+ * all ranks (torch.distributed / MPI / a file), then every rank calls lpmx_comm_init. */
+int lpmx_comm_unique_id(void* id128);
+int lpmx_comm_init(lpmx_handle_t h, const void* id128, int rank, int world);
+
+/* Measured FP64 FMA throughput of this GPU in TFLOP/s (dependent-free DFMA loop on all SMs);
+ * the roofline denominator that MEASURED_PEAKS.json lacks. */
+int lpmx_fp64_peak_tflops(lpmx_handle_t h, double* tflops, double* ms);
+
+/* ------------------------------------------------------------------------------------------
+ * Stateless direct sums (operator level).
+ *
+ * Common arguments: n_tgt targets with coordinates tgt_xyz (layout/ld as above); n_src sources
+ * src_xyz with vorticity src_vort[n_src], panel area src_area[n_src], mask src_mask[n_src]
+ * (non-zero = divided panel, skipped as a source).  `collocated` != 0 means targets ARE the
+ * sources (tgt_xyz is ignored and may be NULL, n_tgt must equal n_src) and the j == i term is
+ * skipped by index.  Outputs use the same layout/ld as their target coordinates.
+ * ------------------------------------------------------------------------------------------ */
+
+/* BVEVertexVelocity (collocated=0, src/lpm_bve_sphere_kernels.hpp:179-211) and BVEFaceVelocity
+ * (collocated=1, :365-394) with VelocityReduceDistinct/Collocated (:53-82, :249-274) and
+ * biot_savart (src/lpm_sphere_functions.hpp:44-57).  out_vel: Real*[3]. */
+int lpmx_bve_velocity(lpmx_handle_t h, const double* tgt_xyz, int tgt_layout, long tgt_ld, int n_tgt,
+                      const double* src_xyz, int src_layout, long src_ld, const double* src_vort,
+                      const double* src_area, const unsigned char* src_mask, int n_src,
+                      int collocated, double* out_vel);
+
+/* BVEVertexStreamFn (:141-170) / BVEFaceStreamFn (:329-356) with StreamReduce* (:20-48,:218-242)
+ * and greens_fn (src/lpm_sphere_functions.hpp:21-29).  out_psi: Real[n_tgt]. */
+int lpmx_bve_streamfn(lpmx_handle_t h, const double* tgt_xyz, int tgt_layout, long tgt_ld, int n_tgt,
+                      const double* src_xyz, int src_layout, long src_ld, const double* src_vort,
+                      const double* src_area, const unsigned char* src_mask, int n_src,
+                      int collocated, double* out_psi);
+
+/* Incompressible2DPassiveSums<SphereGeometry> (collocated_targets=0,
+ * src/lpm_incompressible2d_kernels.hpp:144-193) and Incompressible2DActiveSums (collocated
+ * targets, :201-246; the self term is skipped only when |eps| < DBL_EPSILON, :235), with
+ * kernel_vals (:35-47) and Incompressible2DReducer (:92-136).  out_psi may be NULL (velocity
+ * only). */
+int lpmx_ic2d_sums(lpmx_handle_t h, const double* tgt_xyz, int tgt_layout, long tgt_ld, int n_tgt,
+                   const double* src_xyz, int src_layout, long src_ld, const double* src_vort,
+                   const double* src_area, const unsigned char* src_mask, int n_src, double eps,
+                   int targets_are_sources, double* out_vel, double* out_psi);
+
+/* SphereVertexSums (targets_are_sources=0, src/lpm_swe_kernels.hpp:723-780) and SphereFaceSums
+ * (:877-930) with SphereSweDirectSumReducer (:578-619) and sphere_swe_velocity_sums (:334-362).
+ * out_vel (Real*[3]) is written only if do_velocity != 0; out_ddot[n_tgt] always.
+ * out_grad (optional, may be NULL): the 9 accumulated gradient sums per target, row-major
+ * [n_tgt][9] regardless of layout (a debugging/validation aid; the reference does not expose
+ * them). */
+int lpmx_swe_sphere_sums(lpmx_handle_t h, const double* tgt_xyz, int tgt_layout, long tgt_ld,
+                         int n_tgt, const double* src_xyz, int src_layout, long src_ld,
+                         const double* src_vort, const double* src_div, const double* src_area,
+                         const unsigned char* src_mask, int n_src, double eps,
+                         int targets_are_sources, int do_velocity, double* out_vel,
+                         double* out_ddot, double* out_grad);
+
+/* ------------------------------------------------------------------------------------------
+ * Time steppers (stepper level).
+ * ------------------------------------------------------------------------------------------ */
+
+/* BVERK4::advance_timestep(vx, vzeta, vvel, fx, fzeta, fvel, fa, fm) (src/lpm_bve_rk4.hpp:47-49,
+ * src/lpm_bve_rk4_impl.hpp:63-167), repeated n_steps times, IN PLACE on the caller's views.
+ * On entry vvel/fvel must hold the velocity of the current state (as after
+ * BVESphere::init_velocity, src/lpm_bve_sphere_impl.hpp:181-207); on exit they hold the
+ * velocity of the new state.  Replicates the reference's face-vorticity update as coded
+ * (facevort4 in the facevort3 slot, :155-157). */
+int lpmx_bve_rk4_step(lpmx_handle_t h, double dt, double Omega, int n_verts, double* vert_xyz,
+                      double* vert_vort, double* vert_vel, int n_faces, double* face_xyz,
+                      double* face_vort, double* face_vel, const double* face_area,
+                      const unsigned char* face_mask, int layout, long vert_ld, long face_ld,
+                      int n_steps);
+
+/* Persistent-state variant: state lives in HBM across calls (what BVERK4 + BVESphere's device
+ * views do in the reference); set/get move it.  All arrays as in lpmx_bve_rk4_step. */
+int lpmx_bve_solver_create(lpmx_handle_t h, int n_verts, int n_faces, lpmx_bve_solver_t* s);
+int lpmx_bve_solver_destroy(lpmx_bve_solver_t s);
+int lpmx_bve_solver_set_state(lpmx_bve_solver_t s, const double* vert_xyz, const double* vert_vort,
+                              const double* vert_vel, const double* face_xyz,
+                              const double* face_vort, const double* face_vel,
+                              const double* face_area, const unsigned char* face_mask, int layout,
+                              long vert_ld, long face_ld);
+/* any output pointer may be NULL */
+int lpmx_bve_solver_get_state(lpmx_bve_solver_t s, double* vert_xyz, double* vert_vort,
+                              double* vert_vel, double* face_xyz, double* face_vort,
+                              double* face_vel, int layout, long vert_ld, long face_ld);
+/* BVESphere::init_velocity (src/lpm_bve_sphere_impl.hpp:181-207) on the resident state */
+int lpmx_bve_solver_init_velocity(lpmx_bve_solver_t s);
+/* BVESphere::init_stream_fn (:209-231): psi at vertices then faces, into out arrays (host or
+ * device, either may be NULL) */
+int lpmx_bve_solver_stream_fn(lpmx_bve_solver_t s, double* vert_psi, double* face_psi);
+int lpmx_bve_solver_advance(lpmx_bve_solver_t s, double dt, double Omega, int n_steps);
+/* pair interactions evaluated by one velocity evaluation of this solver on this rank
+ * ((n_v + n_f) * n_leaf - n_leaf over all ranks) */
+int lpmx_bve_solver_interactions_per_eval(lpmx_bve_solver_t s, double* local, double* global);
+
+/* Incompressible2DRK2::advance_timestep_impl (src/lpm_incompressible2d_rk2_impl.hpp:75-172)
+ * for SphereGeometry, n_steps times, in place.  passive = vertices, active = faces.
+ * Omega is CoriolisSphere::Omega (src/lpm_coriolis.hpp:154-195).  On entry the velocities must
+ * hold the current state's velocity (Incompressible2D::init_direct_sums,
+ * src/lpm_incompressible2d_impl.hpp:235-254); on exit velocity and stream function are those
+ * of the new state. */
+int lpmx_ic2d_rk2_step(lpmx_handle_t h, double dt, double Omega, double eps, int n_passive,
+                       double* passive_xyz, double* passive_vort, double* passive_vel,
+                       double* passive_psi, int n_active, double* active_xyz, double* active_vort,
+                       double* active_vel, double* active_psi, const double* active_area,
+                       const unsigned char* active_mask, int layout, long passive_ld,
+                       long active_ld, int n_steps);
+
+int lpmx_ic2d_solver_create(lpmx_handle_t h, int n_passive, int n_active, double eps,
+                            lpmx_ic2d_solver_t* s);
+int lpmx_ic2d_solver_destroy(lpmx_ic2d_solver_t s);
+int lpmx_ic2d_solver_set_state(lpmx_ic2d_solver_t s, const double* passive_xyz,
+                               const double* passive_vort, const double* passive_vel,
+                               const double* active_xyz, const double* active_vort,
+                               const double* active_vel, const double* active_area,
+                               const unsigned char* active_mask, int layout, long passive_ld,
+                               long active_ld);
+int lpmx_ic2d_solver_get_state(lpmx_ic2d_solver_t s, double* passive_xyz, double* passive_vort,
+                               double* passive_vel, double* passive_psi, double* active_xyz,
+                               double* active_vort, double* active_vel, double* active_psi,
+                               int layout, long passive_ld, long active_ld);
+/* Incompressible2D::init_direct_sums on the resident state */
+int lpmx_ic2d_solver_init_direct_sums(lpmx_ic2d_solver_t s);
+int lpmx_ic2d_solver_advance(lpmx_ic2d_solver_t s, double dt, double Omega, int n_steps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPMX_H */

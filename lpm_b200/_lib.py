@@ -1,0 +1,107 @@
+"""ctypes loader for liblpmx.so (the C ABI declared in include/lpmx.h).
+
+The product path FAILS LOUDLY when the CUDA library is missing or no B200 is present: there is no
+CPU fallback anywhere in this package (the mesh generator is host code in the reference too and is
+the only part usable without a GPU).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblpmx.so")
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+c_ubyte_p = ctypes.POINTER(ctypes.c_ubyte)
+c_long_p = ctypes.POINTER(ctypes.c_long)
+vp = ctypes.c_void_p
+
+OK = 0
+ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_NO_DEVICE, ERR_COMM, ERR_UNSUPPORTED, ERR_STATE = -1, -2, -3, -4, -5, -6, -7
+LAYOUT_RIGHT, LAYOUT_LEFT = 0, 1
+SEED_ICOS_TRI_SPHERE, SEED_CUBED_SPHERE = 0, 1
+
+
+class LpmxError(RuntimeError):
+    def __init__(self, code, where, detail=""):
+        self.code = code
+        super().__init__(f"{where}: {error_name(code)} ({code}) {detail}")
+
+
+_lib = None
+
+
+def lib():
+    """Load liblpmx.so; raises if it has not been built (python -m lpm_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `python -m lpm_b200.build` "
+                "(lpm_b200 has no CPU or pure-Python fallback)")
+        L = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+        _declare(L)
+        _lib = L
+    return _lib
+
+
+def error_name(code):
+    return lib().lpmx_error_name(code).decode()
+
+
+def _declare(L):
+    d, i, l = ctypes.c_double, ctypes.c_int, ctypes.c_long
+    L.lpmx_version_string.restype = ctypes.c_char_p
+    L.lpmx_error_name.restype = ctypes.c_char_p
+    L.lpmx_error_name.argtypes = [i]
+    L.lpmx_last_error_string.restype = ctypes.c_char_p
+    L.lpmx_last_error_string.argtypes = [vp]
+    sig = {
+        "lpmx_mesh_max_allocations": [i, i, c_int_p, c_int_p, c_int_p],
+        "lpmx_mesh_create": [i, i, d, ctypes.POINTER(vp)],
+        "lpmx_mesh_destroy": [vp],
+        "lpmx_mesh_sizes": [vp, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p],
+        "lpmx_mesh_array": [vp, i, ctypes.POINTER(vp), c_long_p, c_int_p],
+        "lpmx_create": [ctypes.POINTER(vp), i],
+        "lpmx_destroy": [vp],
+        "lpmx_sync": [vp],
+        "lpmx_stream": [vp, ctypes.POINTER(vp)],
+        "lpmx_launch_count": [vp, c_long_p],
+        "lpmx_set_partition": [vp, i, i],
+        "lpmx_comm_unique_id": [vp],
+        "lpmx_comm_init": [vp, vp, i, i],
+        "lpmx_fp64_peak_tflops": [vp, c_double_p, c_double_p],
+        "lpmx_bve_velocity": [vp, vp, i, l, i, vp, i, l, vp, vp, vp, i, i, vp],
+        "lpmx_bve_streamfn": [vp, vp, i, l, i, vp, i, l, vp, vp, vp, i, i, vp],
+        "lpmx_ic2d_sums": [vp, vp, i, l, i, vp, i, l, vp, vp, vp, i, d, i, vp, vp],
+        "lpmx_swe_sphere_sums": [vp, vp, i, l, i, vp, i, l, vp, vp, vp, vp, i, d, i, i, vp, vp, vp],
+        "lpmx_bve_rk4_step": [vp, d, d, i, vp, vp, vp, i, vp, vp, vp, vp, vp, i, l, l, i],
+        "lpmx_bve_solver_create": [vp, i, i, ctypes.POINTER(vp)],
+        "lpmx_bve_solver_destroy": [vp],
+        "lpmx_bve_solver_set_state": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, l, l],
+        "lpmx_bve_solver_get_state": [vp, vp, vp, vp, vp, vp, vp, i, l, l],
+        "lpmx_bve_solver_init_velocity": [vp],
+        "lpmx_bve_solver_stream_fn": [vp, vp, vp],
+        "lpmx_bve_solver_advance": [vp, d, d, i],
+        "lpmx_bve_solver_interactions_per_eval": [vp, c_double_p, c_double_p],
+        "lpmx_ic2d_rk2_step": [vp, d, d, d, i, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, i, l, l, i],
+        "lpmx_ic2d_solver_create": [vp, i, i, d, ctypes.POINTER(vp)],
+        "lpmx_ic2d_solver_destroy": [vp],
+        "lpmx_ic2d_solver_set_state": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, l, l],
+        "lpmx_ic2d_solver_get_state": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, l, l],
+        "lpmx_ic2d_solver_init_direct_sums": [vp],
+        "lpmx_ic2d_solver_advance": [vp, d, d, i],
+    }
+    for name, args in sig.items():
+        f = getattr(L, name)
+        f.argtypes = args
+        f.restype = i
+
+
+def declared_symbols():
+    """Every function include/lpmx.h declares (parsed from the header)."""
+    import re
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "lpmx.h")
+    text = open(hdr).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lpmx_[a-z0-9_]+)\s*\(", text)))

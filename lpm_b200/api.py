@@ -1,0 +1,394 @@
+"""Host-side mirror of the reference's operator / stepper interface over the C ABI.
+
+The reference is C++ (its API surface is mirrored in C++ under include/lpm/); this module is the
+thin Python binding the parity tests and bench.py drive.  Names follow the reference:
+PolyMesh2d / MeshSeed (src/mesh/lpm_polymesh2d.hpp), BVEVertexVelocity ... (src/lpm_bve_sphere_kernels.hpp),
+BVERK4 (src/lpm_bve_rk4.hpp), Incompressible2DRK2 (src/lpm_incompressible2d_rk2.hpp),
+SphereVertexSums / SphereFaceSums (src/lpm_swe_kernels.hpp).
+
+Arrays may be numpy arrays (host: staged inside the call) or torch CUDA tensors (device: used in
+place).  Everything is float64 / int32 / uint8 as in the reference (Real / Index / bool).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import LAYOUT_LEFT, LAYOUT_RIGHT, SEED_CUBED_SPHERE, SEED_ICOS_TRI_SPHERE, LpmxError  # noqa: F401
+
+_MESH_ARRAYS = {
+    "vert_xyz": (0, 3), "vert_lag_xyz": (1, 3), "vert_crd_inds": (2, 1),
+    "edge_origs": (3, 1), "edge_dests": (4, 1), "edge_lefts": (5, 1), "edge_rights": (6, 1),
+    "edge_parents": (7, 1), "edge_kids": (8, 2),
+    "face_xyz": (9, 3), "face_lag_xyz": (10, 3), "face_area": (11, 1), "face_mask": (12, 1),
+    "face_verts": (13, -1), "face_edges": (14, -1), "face_crd_inds": (15, 1), "face_parent": (16, 1),
+    "face_kids": (17, 4), "face_level": (18, 1), "face_leaf_idx": (19, 1),
+}
+
+SEEDS = {"icos": SEED_ICOS_TRI_SPHERE, "icostri_sphere": SEED_ICOS_TRI_SPHERE,
+         "cubed": SEED_CUBED_SPHERE, "cubed_sphere": SEED_CUBED_SPHERE}
+
+
+def _seed_id(seed):
+    if isinstance(seed, str):
+        return SEEDS[seed]
+    return int(seed)
+
+
+def max_allocations(seed, depth):
+    """MeshSeed<Seed>::set_max_allocations (src/mesh/lpm_mesh_seed.cpp:266-279)."""
+    L = _lib.lib()
+    nv, ne, nf = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = L.lpmx_mesh_max_allocations(_seed_id(seed), depth, nv, ne, nf)
+    if rc:
+        raise LpmxError(rc, "lpmx_mesh_max_allocations")
+    return nv.value, ne.value, nf.value
+
+
+class PolyMesh2d:
+    """Uniform tree mesh on the sphere: PolyMesh2d<Seed>::tree_init (host; no GPU needed)."""
+
+    def __init__(self, seed, depth, radius=1.0):
+        L = _lib.lib()
+        self.seed = _seed_id(seed)
+        self.depth = depth
+        m = ctypes.c_void_p()
+        rc = L.lpmx_mesh_create(self.seed, depth, float(radius), ctypes.byref(m))
+        if rc:
+            raise LpmxError(rc, "lpmx_mesh_create")
+        try:
+            s = [ctypes.c_int() for _ in range(6)]
+            L.lpmx_mesh_sizes(m, *s)
+            (self.n_verts, self.n_edges, self.n_faces, self.n_face_leaves, self.n_edge_leaves,
+             self.n_face_verts) = [x.value for x in s]
+            for name, (aid, width) in _MESH_ARRAYS.items():
+                p, n, kind = ctypes.c_void_p(), ctypes.c_long(), ctypes.c_int()
+                rc = L.lpmx_mesh_array(m, aid, ctypes.byref(p), ctypes.byref(n), ctypes.byref(kind))
+                if rc:
+                    raise LpmxError(rc, "lpmx_mesh_array")
+                ctype = {0: ctypes.c_int, 1: ctypes.c_double, 2: ctypes.c_ubyte}[kind.value]
+                if n.value == 0:
+                    arr = np.zeros(0, dtype=np.dtype(ctype))
+                else:
+                    arr = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctype)), shape=(n.value,)).copy()
+                w = self.n_face_verts if width == -1 else width
+                if w > 1:
+                    arr = arr.reshape(-1, w)
+                setattr(self, name, arr)
+        finally:
+            L.lpmx_mesh_destroy(m)
+
+    # names used by the reference's examples
+    def n_vertices_host(self):
+        return self.n_verts
+
+    def n_faces_host(self):
+        return self.n_faces
+
+    def appx_mesh_size(self):
+        """Faces::appx_mesh_size (src/mesh/lpm_faces_impl.hpp:214-227)."""
+        return float(np.sqrt(self.face_area[self.face_mask == 0].sum() / self.n_face_leaves))
+
+
+def _ptr(a):
+    """void* of a numpy array / torch tensor / None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return ctypes.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        return ctypes.c_void_p(a.data_ptr())
+    raise TypeError(f"unsupported array type {type(a)}")
+
+
+def _f64(a):
+    if a is None or hasattr(a, "data_ptr"):
+        return a
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _u8(a):
+    if a is None or hasattr(a, "data_ptr"):
+        return a
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _empty_like_vec(ref, n, layout, ld):
+    if hasattr(ref, "data_ptr"):
+        import torch
+        shape = (n, 3) if layout == LAYOUT_RIGHT else (3, ld)
+        return torch.empty(shape, dtype=torch.float64, device=ref.device)
+    return np.empty((n, 3) if layout == LAYOUT_RIGHT else (3, ld), dtype=np.float64)
+
+
+def _empty_like_scalar(ref, n):
+    if hasattr(ref, "data_ptr"):
+        import torch
+        return torch.empty(n, dtype=torch.float64, device=ref.device)
+    return np.empty(n, dtype=np.float64)
+
+
+class Engine:
+    """One engine handle per process and GPU (lpmx_create)."""
+
+    def __init__(self, device_id=0):
+        self._L = _lib.lib()
+        h = ctypes.c_void_p()
+        rc = self._L.lpmx_create(ctypes.byref(h), device_id)
+        if rc:
+            raise LpmxError(rc, "lpmx_create", "(no CUDA device: this engine has no CPU fallback)")
+        self._h = h
+        self.device_id = device_id
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.lpmx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, where):
+        if rc:
+            raise LpmxError(rc, where, self._L.lpmx_last_error_string(self._h).decode())
+
+    def sync(self):
+        self._check(self._L.lpmx_sync(self._h), "lpmx_sync")
+
+    def stream(self):
+        s = ctypes.c_void_p()
+        self._check(self._L.lpmx_stream(self._h, ctypes.byref(s)), "lpmx_stream")
+        return s.value
+
+    def launch_count(self):
+        n = ctypes.c_long()
+        self._check(self._L.lpmx_launch_count(self._h, ctypes.byref(n)), "lpmx_launch_count")
+        return n.value
+
+    def fp64_peak_tflops(self):
+        t, ms = ctypes.c_double(), ctypes.c_double()
+        self._check(self._L.lpmx_fp64_peak_tflops(self._h, ctypes.byref(t), ctypes.byref(ms)), "lpmx_fp64_peak_tflops")
+        return t.value
+
+    def set_partition(self, rank, world):
+        self._check(self._L.lpmx_set_partition(self._h, rank, world), "lpmx_set_partition")
+
+    @staticmethod
+    def comm_unique_id():
+        buf = ctypes.create_string_buffer(128)
+        rc = _lib.lib().lpmx_comm_unique_id(buf)
+        if rc:
+            raise LpmxError(rc, "lpmx_comm_unique_id")
+        return bytes(buf.raw)
+
+    def comm_init(self, unique_id, rank, world):
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._L.lpmx_comm_init(self._h, buf, rank, world), "lpmx_comm_init")
+
+    # ---- operator level -----------------------------------------------------------------
+    @staticmethod
+    def _vec_args(x, layout, ld):
+        """(array, n, ld) for a Real*[3] view."""
+        if x is None:
+            return None, 0, 0
+        if layout == LAYOUT_RIGHT:
+            return x, int(x.shape[0]), 0
+        return x, None, int(ld if ld else x.shape[1])
+
+    def _sums_common(self, tgt_xyz, src_xyz, layout, n_tgt, n_src, tgt_ld, src_ld):
+        src_xyz = _f64(src_xyz)
+        tgt_xyz = _f64(tgt_xyz)
+        if layout == LAYOUT_RIGHT:
+            n_src = src_xyz.shape[0] if n_src is None else n_src
+            if tgt_xyz is not None:
+                n_tgt = tgt_xyz.shape[0] if n_tgt is None else n_tgt
+        else:
+            src_ld = src_ld or src_xyz.shape[1]
+            n_src = src_xyz.shape[1] if n_src is None else n_src
+            if tgt_xyz is not None:
+                tgt_ld = tgt_ld or tgt_xyz.shape[1]
+                n_tgt = tgt_xyz.shape[1] if n_tgt is None else n_tgt
+        if tgt_xyz is None:
+            n_tgt, tgt_ld = n_src, src_ld
+        return tgt_xyz, src_xyz, int(n_tgt), int(n_src), int(tgt_ld or 0), int(src_ld or 0)
+
+    def bve_velocity(self, tgt_xyz, src_xyz, src_vort, src_area, src_mask, collocated=False, layout=LAYOUT_RIGHT,
+                     out=None, n_tgt=None, n_src=None, tgt_ld=0, src_ld=0):
+        """BVEVertexVelocity (collocated=False) / BVEFaceVelocity (collocated=True, tgt_xyz=None)."""
+        tgt_xyz, src_xyz, n_tgt, n_src, tgt_ld, src_ld = self._sums_common(
+            None if collocated else tgt_xyz, src_xyz, layout, n_tgt, n_src, tgt_ld, src_ld)
+        src_vort, src_area, src_mask = _f64(src_vort), _f64(src_area), _u8(src_mask)
+        if out is None:
+            out = _empty_like_vec(src_xyz, n_tgt, layout, tgt_ld)
+        self._check(self._L.lpmx_bve_velocity(self._h, _ptr(tgt_xyz), layout, tgt_ld, n_tgt, _ptr(src_xyz), layout,
+                                              src_ld, _ptr(src_vort), _ptr(src_area), _ptr(src_mask), n_src,
+                                              int(bool(collocated)), _ptr(out)), "lpmx_bve_velocity")
+        return out
+
+    def bve_streamfn(self, tgt_xyz, src_xyz, src_vort, src_area, src_mask, collocated=False, layout=LAYOUT_RIGHT,
+                     out=None, n_tgt=None, n_src=None, tgt_ld=0, src_ld=0):
+        """BVEVertexStreamFn / BVEFaceStreamFn."""
+        tgt_xyz, src_xyz, n_tgt, n_src, tgt_ld, src_ld = self._sums_common(
+            None if collocated else tgt_xyz, src_xyz, layout, n_tgt, n_src, tgt_ld, src_ld)
+        src_vort, src_area, src_mask = _f64(src_vort), _f64(src_area), _u8(src_mask)
+        if out is None:
+            out = _empty_like_scalar(src_xyz, n_tgt)
+        self._check(self._L.lpmx_bve_streamfn(self._h, _ptr(tgt_xyz), layout, tgt_ld, n_tgt, _ptr(src_xyz), layout,
+                                              src_ld, _ptr(src_vort), _ptr(src_area), _ptr(src_mask), n_src,
+                                              int(bool(collocated)), _ptr(out)), "lpmx_bve_streamfn")
+        return out
+
+    def ic2d_sums(self, tgt_xyz, src_xyz, src_vort, src_area, src_mask, eps=0.0, targets_are_sources=False,
+                  with_psi=True, layout=LAYOUT_RIGHT, n_tgt=None, n_src=None, tgt_ld=0, src_ld=0):
+        """Incompressible2DPassiveSums (targets_are_sources=False) / ActiveSums (True)."""
+        tgt_xyz, src_xyz, n_tgt, n_src, tgt_ld, src_ld = self._sums_common(
+            None if targets_are_sources else tgt_xyz, src_xyz, layout, n_tgt, n_src, tgt_ld, src_ld)
+        src_vort, src_area, src_mask = _f64(src_vort), _f64(src_area), _u8(src_mask)
+        vel = _empty_like_vec(src_xyz, n_tgt, layout, tgt_ld)
+        psi = _empty_like_scalar(src_xyz, n_tgt) if with_psi else None
+        self._check(self._L.lpmx_ic2d_sums(self._h, _ptr(tgt_xyz), layout, tgt_ld, n_tgt, _ptr(src_xyz), layout, src_ld,
+                                           _ptr(src_vort), _ptr(src_area), _ptr(src_mask), n_src, float(eps),
+                                           int(bool(targets_are_sources)), _ptr(vel), _ptr(psi)), "lpmx_ic2d_sums")
+        return vel, psi
+
+    def swe_sphere_sums(self, tgt_xyz, src_xyz, src_vort, src_div, src_area, src_mask, eps=0.0,
+                        targets_are_sources=False, do_velocity=True, want_grad=False, layout=LAYOUT_RIGHT,
+                        n_tgt=None, n_src=None, tgt_ld=0, src_ld=0):
+        """SphereVertexSums (targets_are_sources=False) / SphereFaceSums (True)."""
+        tgt_xyz, src_xyz, n_tgt, n_src, tgt_ld, src_ld = self._sums_common(
+            None if targets_are_sources else tgt_xyz, src_xyz, layout, n_tgt, n_src, tgt_ld, src_ld)
+        src_vort, src_div, src_area, src_mask = _f64(src_vort), _f64(src_div), _f64(src_area), _u8(src_mask)
+        vel = _empty_like_vec(src_xyz, n_tgt, layout, tgt_ld) if do_velocity else None
+        ddot = _empty_like_scalar(src_xyz, n_tgt)
+        grad = None
+        if want_grad:
+            grad = _empty_like_scalar(src_xyz, 9 * n_tgt)
+        self._check(self._L.lpmx_swe_sphere_sums(self._h, _ptr(tgt_xyz), layout, tgt_ld, n_tgt, _ptr(src_xyz), layout,
+                                                 src_ld, _ptr(src_vort), _ptr(src_div), _ptr(src_area), _ptr(src_mask),
+                                                 n_src, float(eps), int(bool(targets_are_sources)),
+                                                 int(bool(do_velocity)), _ptr(vel), _ptr(ddot), _ptr(grad)),
+                    "lpmx_swe_sphere_sums")
+        if want_grad:
+            grad = grad.reshape(n_tgt, 9)
+        return vel, ddot, grad
+
+    # ---- stepper level, in place on caller arrays ----------------------------------------
+    def bve_rk4_step(self, dt, Omega, vert_xyz, vert_vort, vert_vel, face_xyz, face_vort, face_vel, face_area,
+                     face_mask, n_steps=1, layout=LAYOUT_RIGHT):
+        """BVERK4::advance_timestep, n_steps times, in place (arrays must be C-contiguous float64)."""
+        nv = vert_xyz.shape[0] if layout == LAYOUT_RIGHT else vert_xyz.shape[1]
+        nf = face_xyz.shape[0] if layout == LAYOUT_RIGHT else face_xyz.shape[1]
+        self._check(self._L.lpmx_bve_rk4_step(self._h, float(dt), float(Omega), nv, _ptr(vert_xyz), _ptr(vert_vort),
+                                              _ptr(vert_vel), nf, _ptr(face_xyz), _ptr(face_vort), _ptr(face_vel),
+                                              _ptr(face_area), _ptr(face_mask), layout, nv, nf, n_steps),
+                    "lpmx_bve_rk4_step")
+
+    def ic2d_rk2_step(self, dt, Omega, eps, passive_xyz, passive_vort, passive_vel, passive_psi, active_xyz,
+                      active_vort, active_vel, active_psi, active_area, active_mask, n_steps=1, layout=LAYOUT_RIGHT):
+        """Incompressible2DRK2::advance_timestep_impl, n_steps times, in place."""
+        np_ = passive_xyz.shape[0] if layout == LAYOUT_RIGHT else passive_xyz.shape[1]
+        na = active_xyz.shape[0] if layout == LAYOUT_RIGHT else active_xyz.shape[1]
+        self._check(self._L.lpmx_ic2d_rk2_step(self._h, float(dt), float(Omega), float(eps), np_, _ptr(passive_xyz),
+                                               _ptr(passive_vort), _ptr(passive_vel), _ptr(passive_psi), na,
+                                               _ptr(active_xyz), _ptr(active_vort), _ptr(active_vel), _ptr(active_psi),
+                                               _ptr(active_area), _ptr(active_mask), layout, np_, na, n_steps),
+                    "lpmx_ic2d_rk2_step")
+
+
+class BVESolver:
+    """Device-resident BVESphere state + BVERK4 (lpmx_bve_solver_*)."""
+
+    def __init__(self, engine, n_verts, n_faces):
+        self.e = engine
+        self.nv, self.nf = n_verts, n_faces
+        s = ctypes.c_void_p()
+        engine._check(engine._L.lpmx_bve_solver_create(engine._h, n_verts, n_faces, ctypes.byref(s)),
+                      "lpmx_bve_solver_create")
+        self._s = s
+
+    def close(self):
+        if getattr(self, "_s", None) and getattr(self.e, "_h", None):
+            self.e._L.lpmx_bve_solver_destroy(self._s)
+        self._s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_state(self, vert_xyz, vert_vort, vert_vel, face_xyz, face_vort, face_vel, face_area, face_mask,
+                  layout=LAYOUT_RIGHT):
+        self.e._check(self.e._L.lpmx_bve_solver_set_state(
+            self._s, _ptr(vert_xyz), _ptr(vert_vort), _ptr(vert_vel), _ptr(face_xyz), _ptr(face_vort), _ptr(face_vel),
+            _ptr(face_area), _ptr(face_mask), layout, self.nv, self.nf), "lpmx_bve_solver_set_state")
+
+    def get_state(self, vert_xyz=None, vert_vort=None, vert_vel=None, face_xyz=None, face_vort=None, face_vel=None,
+                  layout=LAYOUT_RIGHT):
+        self.e._check(self.e._L.lpmx_bve_solver_get_state(
+            self._s, _ptr(vert_xyz), _ptr(vert_vort), _ptr(vert_vel), _ptr(face_xyz), _ptr(face_vort), _ptr(face_vel),
+            layout, self.nv, self.nf), "lpmx_bve_solver_get_state")
+
+    def init_velocity(self):
+        self.e._check(self.e._L.lpmx_bve_solver_init_velocity(self._s), "lpmx_bve_solver_init_velocity")
+
+    def stream_fn(self, vert_psi, face_psi):
+        self.e._check(self.e._L.lpmx_bve_solver_stream_fn(self._s, _ptr(vert_psi), _ptr(face_psi)),
+                      "lpmx_bve_solver_stream_fn")
+
+    def advance(self, dt, Omega, n_steps=1):
+        self.e._check(self.e._L.lpmx_bve_solver_advance(self._s, float(dt), float(Omega), n_steps),
+                      "lpmx_bve_solver_advance")
+
+    def interactions_per_eval(self):
+        a, b = ctypes.c_double(), ctypes.c_double()
+        self.e._check(self.e._L.lpmx_bve_solver_interactions_per_eval(self._s, ctypes.byref(a), ctypes.byref(b)),
+                      "lpmx_bve_solver_interactions_per_eval")
+        return a.value, b.value
+
+
+class IC2DSolver:
+    """Device-resident Incompressible2D state + Incompressible2DRK2 (lpmx_ic2d_solver_*)."""
+
+    def __init__(self, engine, n_passive, n_active, eps=0.0):
+        self.e = engine
+        self.np_, self.na = n_passive, n_active
+        s = ctypes.c_void_p()
+        engine._check(engine._L.lpmx_ic2d_solver_create(engine._h, n_passive, n_active, float(eps), ctypes.byref(s)),
+                      "lpmx_ic2d_solver_create")
+        self._s = s
+
+    def close(self):
+        if getattr(self, "_s", None) and getattr(self.e, "_h", None):
+            self.e._L.lpmx_ic2d_solver_destroy(self._s)
+        self._s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_state(self, passive_xyz, passive_vort, passive_vel, active_xyz, active_vort, active_vel, active_area,
+                  active_mask, layout=LAYOUT_RIGHT):
+        self.e._check(self.e._L.lpmx_ic2d_solver_set_state(
+            self._s, _ptr(passive_xyz), _ptr(passive_vort), _ptr(passive_vel), _ptr(active_xyz), _ptr(active_vort),
+            _ptr(active_vel), _ptr(active_area), _ptr(active_mask), layout, self.np_, self.na),
+            "lpmx_ic2d_solver_set_state")
+
+    def get_state(self, passive_xyz=None, passive_vort=None, passive_vel=None, passive_psi=None, active_xyz=None,
+                  active_vort=None, active_vel=None, active_psi=None, layout=LAYOUT_RIGHT):
+        self.e._check(self.e._L.lpmx_ic2d_solver_get_state(
+            self._s, _ptr(passive_xyz), _ptr(passive_vort), _ptr(passive_vel), _ptr(passive_psi), _ptr(active_xyz),
+            _ptr(active_vort), _ptr(active_vel), _ptr(active_psi), layout, self.np_, self.na),
+            "lpmx_ic2d_solver_get_state")
+
+    def init_direct_sums(self):
+        self.e._check(self.e._L.lpmx_ic2d_solver_init_direct_sums(self._s), "lpmx_ic2d_solver_init_direct_sums")
+
+    def advance(self, dt, Omega, n_steps=1):
+        self.e._check(self.e._L.lpmx_ic2d_solver_advance(self._s, float(dt), float(Omega), n_steps),
+                      "lpmx_ic2d_solver_advance")

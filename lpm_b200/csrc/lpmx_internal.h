@@ -1,0 +1,141 @@
+// lpmx_internal.h -- shared declarations of the engine's translation units (not installed).
+#ifndef LPMX_INTERNAL_H
+#define LPMX_INTERNAL_H
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/lpmx.h"
+
+namespace lpmx {
+
+// ------------------------------------------------------------------------------------------------
+// Pair-sum kernel configuration
+// ------------------------------------------------------------------------------------------------
+constexpr int kStages = 4;          // TMA ring depth
+constexpr int kChunk = 256;         // sources per TMA stage
+constexpr int kComputeWarps = 8;    // compute warps per CTA (+1 producer warp)
+constexpr int kCtaThreads = (kComputeWarps + 1) * 32;
+constexpr int kLanesPerCta = kComputeWarps * 32;
+
+enum PairKind : int {
+  kVel = 0,     // moment  M = sum Gamma y / d                    (BVE + IC2D velocity)
+  kVelPsi = 1,  // M and   P = sum Gamma log d                    (IC2D velocity + stream function)
+  kPsi = 2,     // P only                                         (BVE stream function)
+  kSwe = 3,     // Mz, Ms, G[9]                                   (spherical SWE 12-tuple)
+};
+constexpr int kind_nacc(int k) { return k == kVel ? 3 : k == kVelPsi ? 4 : k == kPsi ? 1 : 15; }
+constexpr int kind_rec(int k) { return k == kSwe ? 6 : 4; }  // doubles per packed source record
+
+// strided accessor for Real*[3] views: element (i,k) at p[i*si + k*sk]
+struct Vec3View {
+  double* p;
+  long si, sk;
+  __host__ __device__ double& operator()(long i, int k) const { return p[i * si + k * sk]; }
+};
+inline Vec3View make_view(const double* p, int layout, long ld) {
+  Vec3View v;
+  v.p = const_cast<double*>(p);
+  if (layout == LPMX_LAYOUT_LEFT) {
+    v.si = 1;
+    v.sk = ld;
+  } else {
+    v.si = 3;
+    v.sk = 1;
+  }
+  return v;
+}
+
+// Work decomposition of one pair-sum launch (stream-K over target blocks x source chunks).
+struct SumPlan {
+  int kind;
+  int T;            // targets per thread
+  int tb;           // targets per CTA block = T * kLanesPerCta
+  int n_tgt;        // targets evaluated by this launch
+  int n_tb;         // target blocks
+  int n_src_pad;    // packed sources incl. zero padding (multiple of kChunk)
+  int n_sc;         // source chunks
+  int grid;         // persistent CTAs
+  int max_slots;    // partial-sum slots per target block
+  long n_tgt_pad;   // n_tb * tb
+  size_t smem_bytes;
+};
+
+// grow-only device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace lpmx
+
+struct lpmx_handle_s {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  std::string err;
+  long launches = 0;
+  int rank = 0, world = 1;
+  void* nccl_comm = nullptr;  // ncclComm_t when lpmx_comm_init succeeded
+  void* nccl_lib = nullptr;   // dlopen handle
+  std::map<std::string, lpmx::DevBuf> bufs;  // named scratch buffers
+  std::map<std::string, lpmx::DevBuf> pinned;  // named pinned host staging buffers
+  // cached one-shot solvers for the in-place stepper entry points
+  lpmx_bve_solver_t cached_bve = nullptr;
+  lpmx_ic2d_solver_t cached_ic2d = nullptr;
+};
+
+namespace lpmx {
+
+int set_error(lpmx_handle_t h, int code, const char* fmt, ...);
+int check_cuda(lpmx_handle_t h, cudaError_t e, const char* what);
+#define LPMX_CUDA(h, call)                                          \
+  do {                                                              \
+    int _rc = ::lpmx::check_cuda((h), (call), #call);               \
+    if (_rc != LPMX_OK) return _rc;                                 \
+  } while (0)
+#define LPMX_TRY(call)               \
+  do {                               \
+    int _rc = (call);                \
+    if (_rc != LPMX_OK) return _rc;  \
+  } while (0)
+
+// scratch management
+int dev_buffer(lpmx_handle_t h, const char* name, size_t bytes, void** out);
+int pinned_buffer(lpmx_handle_t h, const char* name, size_t bytes, void** out);
+bool is_device_pointer(const void* p);
+
+// Staged argument: if `user` is a host pointer, a device copy is made (inputs) or reserved
+// (outputs) in a named scratch buffer; if it is a device pointer it is used in place.
+int stage_in(lpmx_handle_t h, const char* name, const void* user, size_t bytes, const void** dev);
+int stage_out_begin(lpmx_handle_t h, const char* name, void* user, size_t bytes, void** dev);
+int stage_out_end(lpmx_handle_t h, void* user, const void* dev, size_t bytes);
+
+// ---- pair-sum engine (lpmx_kernels.cu) ----
+int make_plan(lpmx_handle_t h, int kind, int n_tgt, int n_src, SumPlan* plan);
+size_t plan_partials_bytes(const SumPlan& p);
+// tgt: target coordinates of the n_tgt targets of this launch (view indexed from 0);
+// self_idx: compact source index of each target's own particle or -1 (may be nullptr);
+// packed: n_src_pad records of kind_rec(kind) doubles; partials: plan_partials_bytes.
+int launch_pair_sum(lpmx_handle_t h, const SumPlan& plan, Vec3View tgt, const int* self_idx, const double* packed,
+                    double kappa, double* partials);
+
+// exclusive scan of !mask -> leaf_idx, returns number of unmasked sources (host sync)
+int scan_leaves(lpmx_handle_t h, const unsigned char* mask_dev, int n, int* leaf_idx_dev, int* n_leaves);
+int round_up_chunk(int n);
+int fp64_probe(lpmx_handle_t h, double* tflops, double* ms_out);
+
+// In-place allgatherv of doubles on the handle's stream: rank r owns elements
+// [offsets[r], offsets[r+1]) of `base`; after the call every rank holds all of them.
+// No-op for world == 1.  (lpmx_core.cu; NCCL broadcasts grouped into one launch.)
+int comm_allgatherv(lpmx_handle_t h, double* base, const long* offsets);
+
+}  // namespace lpmx
+
+#endif

@@ -1,0 +1,812 @@
+// lpmx_steppers.cu -- device-resident time steppers: BVERK4 and Incompressible2DRK2 on the sphere.
+//
+// Reference (as coded, quirks included -- SURVEY.md 8(a)):
+//   BVERK4::advance_timestep            src/lpm_bve_rk4_impl.hpp:63-167  (38 launches per step)
+//   BVERK4Update                        src/lpm_bve_rk4_impl.hpp:12-53
+//   BVEVorticityTendency                src/lpm_bve_sphere_kernels.hpp:399-413
+//   Incompressible2DRK2::advance_timestep_impl   src/lpm_incompressible2d_rk2_impl.hpp:75-172
+//   Incompressible2DTendencies          src/lpm_incompressible2d_kernels.hpp:257-278
+//
+// Here a step is (pair-sum kernel + one fused O(N) stage kernel) per velocity evaluation: the stage
+// kernel adds the partial moments, applies u = x cross M, forms the stage increments, the next
+// stage's input state AND its packed source records (ping-pong buffers), so the reference's
+// KokkosBlas scal/update calls and tendency/update functors never run as separate passes.
+// Targets (vertices then faces) are stored structure-of-arrays; with world > 1 each rank
+// evaluates a contiguous range of that list and the packed source records of its leaves are
+// exchanged after every stage (in-place allgatherv over NCCL).
+#include <cfloat>
+#include <cmath>
+#include <new>
+
+#include "lpmx_finalize.cuh"
+#include "lpmx_internal.h"
+
+using namespace lpmx;
+
+namespace lpmx {
+
+// state common to both steppers: SoA arrays over the concatenated target list
+struct SolverState {
+  lpmx_handle_t h = nullptr;
+  int nv = 0, nf = 0, nt = 0, n_leaf = 0;
+  int t0 = 0, t1 = 0;  // this rank's targets
+  bool has_state = false;
+  void* slab = nullptr;
+  double *X = nullptr, *U = nullptr, *Xw = nullptr, *Z = nullptr, *Zw = nullptr, *Psi = nullptr;
+  double* K[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};  // K[s][0]=x incr (3*nt), [1]=zeta incr
+  double* area = nullptr;
+  unsigned char* mask = nullptr;
+  int* leaf_idx = nullptr;
+  int* self_idx = nullptr;
+  double* packed[2] = {nullptr, nullptr};
+  int cur = 0;
+  int n_src_pad = 0;
+  double* partials = nullptr;
+  size_t partials_bytes = 0;
+  std::vector<long> tgt_off;     // world+1 target offsets
+  std::vector<long> packed_off;  // world+1 offsets into packed (in doubles)
+  Vec3View view(double* base) const {
+    Vec3View v;
+    v.p = base;
+    v.si = 1;
+    v.sk = nt;
+    return v;
+  }
+  Vec3View local_view(double* base) const {
+    Vec3View v = view(base);
+    v.p = base + t0;
+    return v;
+  }
+};
+
+static int solver_alloc(SolverState* s, lpmx_handle_t h, int nv, int nf, int n_k) {
+  if (!h || nv < 0 || nf < 0) return LPMX_ERR_INVALID;
+  LPMX_CUDA(h, cudaSetDevice(h->device));
+  s->h = h;
+  s->nv = nv;
+  s->nf = nf;
+  s->nt = nv + nf;
+  const long nt = s->nt;
+  s->n_src_pad = round_up_chunk(nf);  // upper bound: every face a leaf
+  // one slab: X U Xw (3nt each) Z Zw Psi (nt each) K (n_k * 4nt) area packed[2] | ints | mask
+  size_t dbl = 9 * nt + 3 * nt + (size_t)n_k * 4 * nt + nf + 2 * 4 * (size_t)(s->n_src_pad + kChunk);
+  size_t bytes = dbl * sizeof(double) + sizeof(int) * (size_t)(nf + 1 + nt + 1) + (size_t)nf + 64;
+  LPMX_CUDA(h, cudaMalloc(&s->slab, bytes));
+  LPMX_CUDA(h, cudaMemsetAsync(s->slab, 0, bytes, h->stream));  // Kokkos views start at zero
+  double* p = (double*)s->slab;
+  s->X = p, p += 3 * nt;
+  s->U = p, p += 3 * nt;
+  s->Xw = p, p += 3 * nt;
+  s->Z = p, p += nt;
+  s->Zw = p, p += nt;
+  s->Psi = p, p += nt;
+  for (int k = 0; k < n_k; ++k) {
+    s->K[k][0] = p, p += 3 * nt;
+    s->K[k][1] = p, p += nt;
+  }
+  s->area = p, p += nf;
+  s->packed[0] = p, p += 4 * (size_t)(s->n_src_pad + kChunk);
+  s->packed[1] = p, p += 4 * (size_t)(s->n_src_pad + kChunk);
+  int* ip = (int*)p;
+  s->leaf_idx = ip, ip += nf + 1;
+  s->self_idx = ip, ip += nt + 1;
+  s->mask = (unsigned char*)ip;
+  s->t0 = (int)(((long)h->rank * nt) / h->world);
+  s->t1 = (int)(((long)(h->rank + 1) * nt) / h->world);
+  return LPMX_OK;
+}
+
+static void solver_free(SolverState* s) {
+  if (s->slab) {
+    cudaSetDevice(s->h->device);
+    cudaStreamSynchronize(s->h->stream);
+    cudaFree(s->slab);
+    s->slab = nullptr;
+  }
+}
+
+// user views -> SoA state; also self index of every target
+__global__ void import_state_kernel(int nv, int nf, Vec3View vx, const double* vz, Vec3View vu, Vec3View fx,
+                                    const double* fz, Vec3View fu, double* X, double* Z, double* U) {
+  const long nt = (long)nv + nf;
+  const long g = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (g >= nt) return;
+  const bool vert = g < nv;
+  const long i = vert ? g : g - nv;
+  const Vec3View& x = vert ? vx : fx;
+  const Vec3View& u = vert ? vu : fu;
+  const double* z = vert ? vz : fz;
+  for (int k = 0; k < 3; ++k) {
+    X[k * nt + g] = x(i, k);
+    U[k * nt + g] = u.p ? u(i, k) : 0.0;
+  }
+  Z[g] = z[i];
+}
+
+__global__ void export_state_kernel(int nv, int nf, Vec3View vx, double* vz, Vec3View vu, double* vpsi, Vec3View fx,
+                                    double* fz, Vec3View fu, double* fpsi, const double* X, const double* Z,
+                                    const double* U, const double* Psi) {
+  const long nt = (long)nv + nf;
+  const long g = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (g >= nt) return;
+  const bool vert = g < nv;
+  const long i = vert ? g : g - nv;
+  const Vec3View& x = vert ? vx : fx;
+  const Vec3View& u = vert ? vu : fu;
+  double* z = vert ? vz : fz;
+  double* psi = vert ? vpsi : fpsi;
+  for (int k = 0; k < 3; ++k) {
+    if (x.p) x(i, k) = X[k * nt + g];
+    if (u.p) u(i, k) = U[k * nt + g];
+  }
+  if (z) z[i] = Z[g];
+  if (psi) psi[i] = Psi[g];
+}
+
+__global__ void self_idx_kernel(int nv, int nf, const unsigned char* mask, const int* leaf_idx, int skip_self,
+                                int* self_idx) {
+  const long g = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (g >= (long)nv + nf) return;
+  int v = -1;
+  if (g >= nv && skip_self) {
+    const long f = g - nv;
+    if (!mask[f]) v = leaf_idx[f];
+  }
+  self_idx[g] = v;
+}
+
+// write the packed record of face-target g (if it is a leaf)
+__device__ __forceinline__ void pack_target(long g, int nv, const unsigned char* mask, const int* leaf_idx,
+                                            const double* area, const double* x, double zeta, double* packed) {
+  if (g < nv || !packed) return;
+  const long f = g - nv;
+  if (mask[f]) return;
+  double* rec = packed + 4 * (size_t)leaf_idx[f];
+  rec[0] = x[0];
+  rec[1] = x[1];
+  rec[2] = x[2];
+  rec[3] = gamma_of(zeta, area[f]);
+}
+
+// pack the current state (X, Z) [or work state] of this rank's targets
+__global__ void pack_state_kernel(int t0, int n_local, int nv, long nt, const double* X, const double* Z,
+                                  const unsigned char* mask, const int* leaf_idx, const double* area, double* packed) {
+  const long li = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (li >= n_local) return;
+  const long g = t0 + li;
+  const double x[3] = {X[g], X[nt + g], X[2 * nt + g]};
+  pack_target(g, nv, mask, leaf_idx, area, x, Z[g], packed);
+}
+
+struct StageArgs {
+  PartView pv;
+  int t0, n_local, nv;
+  long nt;
+  int stage;  // which evaluation just finished (1-based); 0 = prologue from U
+  int more;   // another step follows (fuse its stage 1)
+  double dt, Omega;
+  double *X, *U, *Xw, *Z, *Zw, *Psi;
+  double *K1x, *K1z, *K2x, *K2z, *K3x, *K3z;
+  const double* area;
+  const unsigned char* mask;
+  const int* leaf_idx;
+  double* packed_next;
+};
+
+// ---- BVE RK4 -------------------------------------------------------------------------------
+// stage 0 (prologue) and the tail of stage 4 both do "stage 1 from the current velocity":
+//   x1 = dt*u, zeta1 = -2 Omega u_z dt, work = state + 0.5 * increment   (:85-98)
+__device__ __forceinline__ void bve_stage1(const StageArgs& a, long g, const double* u, double* xw, double* zw) {
+  const long nt = a.nt;
+  const double z1 = -2.0 * a.Omega * u[2] * a.dt;
+  a.K1z[g] = z1;
+  for (int k = 0; k < 3; ++k) {
+    const double x1 = a.dt * u[k];
+    a.K1x[k * nt + g] = x1;
+    xw[k] = a.X[k * nt + g] + 0.5 * x1;
+    a.Xw[k * nt + g] = xw[k];
+  }
+  *zw = a.Z[g] + 0.5 * z1;
+  a.Zw[g] = *zw;
+}
+
+__global__ void bve_rk4_stage_kernel(const StageArgs a) {
+  const long li = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (li >= a.n_local) return;
+  const long g = a.t0 + li;
+  const long nt = a.nt;
+  double u[3], xw[3], zw;
+  if (a.stage == 0) {
+    for (int k = 0; k < 3; ++k) u[k] = a.U[k * nt + g];
+    bve_stage1(a, g, u, xw, &zw);
+    pack_target(g, a.nv, a.mask, a.leaf_idx, a.area, xw, zw, a.packed_next);
+    return;
+  }
+  double M[3];
+  reduce_slots<3>(a.pv, li, M);
+  const double x[3] = {a.Xw[g], a.Xw[nt + g], a.Xw[2 * nt + g]};
+  cross3(u, x, M);
+  const double zk = -2.0 * a.Omega * u[2] * a.dt;  // BVEVorticityTendency
+  if (a.stage == 1 || a.stage == 2) {
+    double* Kx = a.stage == 1 ? a.K2x : a.K3x;
+    double* Kz = a.stage == 1 ? a.K2z : a.K3z;
+    const double c = a.stage == 1 ? 0.5 : 1.0;  // stage-3 input uses 0.5*x2, stage-4 input 1.0*x3 (:114-137)
+    Kz[g] = zk;
+    for (int k = 0; k < 3; ++k) {
+      const double xk = a.dt * u[k];
+      Kx[k * nt + g] = xk;
+      xw[k] = a.X[k * nt + g] + c * xk;
+      a.Xw[k * nt + g] = xw[k];
+    }
+    zw = a.Z[g] + c * zk;
+    a.Zw[g] = zw;
+  } else if (a.stage == 3) {
+    // BVERK4Update (:12-53).  Faces get zeta4 in the zeta3 slot (:155-157, reference quirk A-i).
+    const double sixth = 1.0 / 6.0, third = 1.0 / 3.0;
+    for (int k = 0; k < 3; ++k) {
+      const double x4 = a.dt * u[k];
+      const double xn =
+          a.X[k * nt + g] + (sixth * (a.K1x[k * nt + g] + x4) + third * (a.K2x[k * nt + g] + a.K3x[k * nt + g]));
+      a.X[k * nt + g] = xn;
+      a.Xw[k * nt + g] = xn;
+      xw[k] = xn;
+    }
+    const double z3 = (g >= a.nv) ? zk : a.K3z[g];
+    zw = a.Z[g] + (sixth * (a.K1z[g] + zk) + third * (a.K2z[g] + z3));
+    a.Z[g] = zw;
+    a.Zw[g] = zw;
+  } else {  // stage 4: velocity of the new state (:159-164)
+    for (int k = 0; k < 3; ++k) a.U[k * nt + g] = u[k];
+    if (!a.more) return;
+    bve_stage1(a, g, u, xw, &zw);
+  }
+  pack_target(g, a.nv, a.mask, a.leaf_idx, a.area, xw, zw, a.packed_next);
+}
+
+// ---- IC2D RK2 --------------------------------------------------------------------------------
+// stage 1 from the current velocity (:77-110): x1 = dt*u, zeta1 = -2 Omega u_z (no dt),
+// work = x + dt*u, zeta + dt*zeta1
+__device__ __forceinline__ void ic2d_stage1(const StageArgs& a, long g, const double* u, double* xw, double* zw) {
+  const long nt = a.nt;
+  const double z1 = -(2.0 * a.Omega * u[2]);
+  a.K1z[g] = z1;
+  for (int k = 0; k < 3; ++k) {
+    a.K1x[k * nt + g] = a.dt * u[k];
+    xw[k] = a.X[k * nt + g] + a.dt * u[k];
+    a.Xw[k * nt + g] = xw[k];
+  }
+  *zw = a.Z[g] + a.dt * z1;
+  a.Zw[g] = *zw;
+}
+
+template <bool WITH_PSI>
+__global__ void ic2d_rk2_stage_kernel(const StageArgs a) {
+  const long li = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (li >= a.n_local) return;
+  const long g = a.t0 + li;
+  const long nt = a.nt;
+  double u[3], xw[3], zw;
+  if (a.stage == 0) {
+    for (int k = 0; k < 3; ++k) u[k] = a.U[k * nt + g];
+    ic2d_stage1(a, g, u, xw, &zw);
+    pack_target(g, a.nv, a.mask, a.leaf_idx, a.area, xw, zw, a.packed_next);
+    return;
+  }
+  constexpr int NACC = WITH_PSI ? 4 : 3;
+  double M[NACC];
+  reduce_slots<NACC>(a.pv, li, M);
+  const double x[3] = {a.Xw[g], a.Xw[nt + g], a.Xw[2 * nt + g]};
+  cross3(u, x, M);
+  if (a.stage == 1) {
+    // (:127-155) x2 = dt*u, zeta2 = -2 Omega u_z ; zeta += .5dt*z1 + .5dt*z2 ; x += .5*x1 + .5*x2
+    const double z2 = -(2.0 * a.Omega * u[2]);
+    const double hdt = 0.5 * a.dt;
+    for (int k = 0; k < 3; ++k) {
+      const double x2 = a.dt * u[k];
+      const double xn = a.X[k * nt + g] + (0.5 * a.K1x[k * nt + g] + 0.5 * x2);
+      a.X[k * nt + g] = xn;
+      a.Xw[k * nt + g] = xn;
+      xw[k] = xn;
+      a.U[k * nt + g] = u[k];  // the reference overwrites the velocity view at this point too
+    }
+    zw = a.Z[g] + (hdt * a.K1z[g] + hdt * z2);
+    a.Z[g] = zw;
+    a.Zw[g] = zw;
+  } else {  // stage 2: velocity and stream function of the new state (:157-170)
+    for (int k = 0; k < 3; ++k) a.U[k * nt + g] = u[k];
+    if (WITH_PSI) a.Psi[g] = M[NACC - 1];
+    if (!a.more) return;
+    ic2d_stage1(a, g, u, xw, &zw);
+  }
+  pack_target(g, a.nv, a.mask, a.leaf_idx, a.area, xw, zw, a.packed_next);
+}
+
+// psi-only finalize on the resident state (BVESphere::init_stream_fn)
+__global__ void psi_out_kernel(PartView pv, int t0, int n_local, double* Psi) {
+  const long li = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (li >= n_local) return;
+  double p[1];
+  reduce_slots<1>(pv, li, p);
+  Psi[t0 + li] = p[0];
+}
+
+static int ensure_partials(SolverState* s, const SumPlan& plan) {
+  const size_t need = plan_partials_bytes(plan) + 256;
+  void* p = nullptr;
+  LPMX_TRY(dev_buffer(s->h, "solver_partials", need, &p));
+  s->partials = (double*)p;
+  s->partials_bytes = need;
+  return LPMX_OK;
+}
+
+static int exchange_packed(SolverState* s, double* packed) {
+  if (s->h->world == 1) return LPMX_OK;
+  return comm_allgatherv(s->h, packed, s->packed_off.data());
+}
+
+// gather full-length SoA rows (n_rows rows of length nt) so every rank holds every target
+static int exchange_rows(SolverState* s, double* base, int n_rows) {
+  if (s->h->world == 1) return LPMX_OK;
+  std::vector<long> off(s->h->world + 1);
+  for (int r = 0; r < n_rows; ++r) {
+    for (int q = 0; q <= s->h->world; ++q) off[q] = s->tgt_off[q];
+    LPMX_TRY(comm_allgatherv(s->h, base + (long)r * s->nt, off.data()));
+  }
+  return LPMX_OK;
+}
+
+static int solver_set_state(SolverState* s, const double* vx, const double* vz, const double* vu, const double* fx,
+                            const double* fz, const double* fu, const double* fa, const unsigned char* fm, int layout,
+                            long vld, long fld, int skip_self) {
+  lpmx_handle_t h = s->h;
+  if (layout != LPMX_LAYOUT_LEFT && layout != LPMX_LAYOUT_RIGHT) return set_error(h, LPMX_ERR_INVALID, "unknown layout");
+  if ((s->nv > 0 && (!vx || !vz)) || (s->nf > 0 && (!fx || !fz || !fa || !fm)))
+    return set_error(h, LPMX_ERR_INVALID, "null state array");
+  if (layout == LPMX_LAYOUT_LEFT && (vld < s->nv || fld < s->nf))
+    return set_error(h, LPMX_ERR_INVALID, "leading dimension smaller than extent");
+  LPMX_CUDA(h, cudaSetDevice(h->device));
+  auto vb = [&](long ld, int n) {
+    return (layout == LPMX_LAYOUT_LEFT ? (size_t)(2 * ld + n) : (size_t)3 * n) * sizeof(double);
+  };
+  const void *dvx, *dvz, *dvu, *dfx, *dfz, *dfu, *dfa, *dfm;
+  LPMX_TRY(stage_in(h, "st_vx", vx, vb(vld, s->nv), &dvx));
+  LPMX_TRY(stage_in(h, "st_vz", vz, sizeof(double) * s->nv, &dvz));
+  LPMX_TRY(stage_in(h, "st_vu", vu, vb(vld, s->nv), &dvu));
+  LPMX_TRY(stage_in(h, "st_fx", fx, vb(fld, s->nf), &dfx));
+  LPMX_TRY(stage_in(h, "st_fz", fz, sizeof(double) * s->nf, &dfz));
+  LPMX_TRY(stage_in(h, "st_fu", fu, vb(fld, s->nf), &dfu));
+  LPMX_TRY(stage_in(h, "st_fa", fa, sizeof(double) * s->nf, &dfa));
+  LPMX_TRY(stage_in(h, "st_fm", fm, (size_t)s->nf, &dfm));
+  if (s->nf > 0) {
+    LPMX_CUDA(h, cudaMemcpyAsync(s->area, dfa, sizeof(double) * s->nf, cudaMemcpyDeviceToDevice, h->stream));
+    LPMX_CUDA(h, cudaMemcpyAsync(s->mask, dfm, (size_t)s->nf, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  const int threads = 256;
+  const int blocks = (s->nt + threads - 1) / threads;
+  if (s->nt > 0) {
+    import_state_kernel<<<blocks, threads, 0, h->stream>>>(
+        s->nv, s->nf, make_view((const double*)dvx, layout, vld), (const double*)dvz,
+        make_view((const double*)dvu, layout, vld), make_view((const double*)dfx, layout, fld), (const double*)dfz,
+        make_view((const double*)dfu, layout, fld), s->X, s->Z, s->U);
+    ++h->launches;
+    LPMX_CUDA(h, cudaGetLastError());
+  }
+  LPMX_TRY(scan_leaves(h, s->mask, s->nf, s->leaf_idx, &s->n_leaf));
+  if (s->nt > 0) {
+    self_idx_kernel<<<blocks, threads, 0, h->stream>>>(s->nv, s->nf, s->mask, s->leaf_idx, skip_self, s->self_idx);
+    ++h->launches;
+    LPMX_CUDA(h, cudaGetLastError());
+  }
+  s->n_src_pad = round_up_chunk(s->n_leaf);
+  // zero both packed buffers once: the padding records must stay {0,0,0,0}
+  const size_t pk_bytes = sizeof(double) * 4 * (size_t)(round_up_chunk(s->nf) + kChunk);
+  LPMX_CUDA(h, cudaMemsetAsync(s->packed[0], 0, pk_bytes, h->stream));
+  LPMX_CUDA(h, cudaMemsetAsync(s->packed[1], 0, pk_bytes, h->stream));
+  // shard offsets (targets, and each rank's leaf range in the packed array)
+  const int W = h->world;
+  s->tgt_off.assign(W + 1, 0);
+  s->packed_off.assign(W + 1, 0);
+  std::vector<int> leaf_host;
+  if (W > 1 && s->nf > 0) {
+    leaf_host.resize(s->nf);
+    LPMX_CUDA(h, cudaMemcpyAsync(leaf_host.data(), s->leaf_idx, sizeof(int) * s->nf, cudaMemcpyDeviceToHost, h->stream));
+    LPMX_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  for (int r = 0; r <= W; ++r) {
+    const long t = ((long)r * s->nt) / W;
+    s->tgt_off[r] = t;
+    long f = t - s->nv;
+    if (f < 0) f = 0;
+    long l = (f >= s->nf) ? s->n_leaf : (W > 1 ? leaf_host[f] : 0);
+    if (r == W) l = s->n_leaf;
+    s->packed_off[r] = 4 * l;
+  }
+  s->t0 = (int)s->tgt_off[h->rank];
+  s->t1 = (int)s->tgt_off[h->rank + 1];
+  s->has_state = true;
+  if (!is_device_pointer(vx) || !is_device_pointer(fx)) LPMX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return LPMX_OK;
+}
+
+static int solver_get_state(SolverState* s, double* vx, double* vz, double* vu, double* vpsi, double* fx, double* fz,
+                            double* fu, double* fpsi, int layout, long vld, long fld) {
+  lpmx_handle_t h = s->h;
+  if (!s->has_state) return set_error(h, LPMX_ERR_STATE, "get_state before set_state");
+  if (layout != LPMX_LAYOUT_LEFT && layout != LPMX_LAYOUT_RIGHT) return set_error(h, LPMX_ERR_INVALID, "unknown layout");
+  LPMX_CUDA(h, cudaSetDevice(h->device));
+  // every rank returns the full state
+  LPMX_TRY(exchange_rows(s, s->X, 3));
+  LPMX_TRY(exchange_rows(s, s->U, 3));
+  LPMX_TRY(exchange_rows(s, s->Z, 1));
+  if (vpsi || fpsi) LPMX_TRY(exchange_rows(s, s->Psi, 1));
+  auto vb = [&](long ld, int n) {
+    return (layout == LPMX_LAYOUT_LEFT ? (size_t)(2 * ld + n) : (size_t)3 * n) * sizeof(double);
+  };
+  void *dvx = nullptr, *dvz = nullptr, *dvu = nullptr, *dvp = nullptr, *dfx = nullptr, *dfz = nullptr, *dfu = nullptr,
+       *dfp = nullptr;
+  if (vx) LPMX_TRY(stage_out_begin(h, "go_vx", vx, vb(vld, s->nv), &dvx));
+  if (vz) LPMX_TRY(stage_out_begin(h, "go_vz", vz, sizeof(double) * s->nv, &dvz));
+  if (vu) LPMX_TRY(stage_out_begin(h, "go_vu", vu, vb(vld, s->nv), &dvu));
+  if (vpsi) LPMX_TRY(stage_out_begin(h, "go_vp", vpsi, sizeof(double) * s->nv, &dvp));
+  if (fx) LPMX_TRY(stage_out_begin(h, "go_fx", fx, vb(fld, s->nf), &dfx));
+  if (fz) LPMX_TRY(stage_out_begin(h, "go_fz", fz, sizeof(double) * s->nf, &dfz));
+  if (fu) LPMX_TRY(stage_out_begin(h, "go_fu", fu, vb(fld, s->nf), &dfu));
+  if (fpsi) LPMX_TRY(stage_out_begin(h, "go_fp", fpsi, sizeof(double) * s->nf, &dfp));
+  if (s->nt > 0) {
+    const int threads = 256;
+    const int blocks = (s->nt + threads - 1) / threads;
+    export_state_kernel<<<blocks, threads, 0, h->stream>>>(
+        s->nv, s->nf, make_view((double*)dvx, layout, vld), (double*)dvz, make_view((double*)dvu, layout, vld),
+        (double*)dvp, make_view((double*)dfx, layout, fld), (double*)dfz, make_view((double*)dfu, layout, fld),
+        (double*)dfp, s->X, s->Z, s->U, s->Psi);
+    ++h->launches;
+    LPMX_CUDA(h, cudaGetLastError());
+  }
+  bool any_host = false;
+  auto out = [&](void* user, void* dev, size_t bytes) -> int {
+    if (user && user != dev) any_host = true;
+    return stage_out_end(h, user, dev, bytes);
+  };
+  LPMX_TRY(out(vx, dvx, vb(vld, s->nv)));
+  LPMX_TRY(out(vz, dvz, sizeof(double) * s->nv));
+  LPMX_TRY(out(vu, dvu, vb(vld, s->nv)));
+  LPMX_TRY(out(vpsi, dvp, sizeof(double) * s->nv));
+  LPMX_TRY(out(fx, dfx, vb(fld, s->nf)));
+  LPMX_TRY(out(fz, dfz, sizeof(double) * s->nf));
+  LPMX_TRY(out(fu, dfu, vb(fld, s->nf)));
+  LPMX_TRY(out(fpsi, dfp, sizeof(double) * s->nf));
+  if (any_host) LPMX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return LPMX_OK;
+}
+
+static StageArgs stage_args(SolverState* s, const SumPlan* plan, int stage, int more, double dt, double Omega,
+                            double* packed_next) {
+  StageArgs a;
+  if (plan)
+    a.pv = part_view(*plan, s->partials);
+  else
+    a.pv = PartView{nullptr, 0, 0, 0, 1, 1};
+  a.t0 = s->t0;
+  a.n_local = s->t1 - s->t0;
+  a.nv = s->nv;
+  a.nt = s->nt;
+  a.stage = stage;
+  a.more = more;
+  a.dt = dt;
+  a.Omega = Omega;
+  a.X = s->X, a.U = s->U, a.Xw = s->Xw, a.Z = s->Z, a.Zw = s->Zw, a.Psi = s->Psi;
+  a.K1x = s->K[0][0], a.K1z = s->K[0][1];
+  a.K2x = s->K[1][0], a.K2z = s->K[1][1];
+  a.K3x = s->K[2][0], a.K3z = s->K[2][1];
+  a.area = s->area;
+  a.mask = s->mask;
+  a.leaf_idx = s->leaf_idx;
+  a.packed_next = packed_next;
+  return a;
+}
+
+// pack (X,Z) of the resident state into packed[cur] and exchange
+static int pack_resident(SolverState* s) {
+  lpmx_handle_t h = s->h;
+  const int n_local = s->t1 - s->t0;
+  if (n_local > 0) {
+    const int threads = 256, blocks = (n_local + threads - 1) / threads;
+    pack_state_kernel<<<blocks, threads, 0, h->stream>>>(s->t0, n_local, s->nv, s->nt, s->X, s->Z, s->mask, s->leaf_idx,
+                                                         s->area, s->packed[s->cur]);
+    ++h->launches;
+    LPMX_CUDA(h, cudaGetLastError());
+  }
+  return exchange_packed(s, s->packed[s->cur]);
+}
+
+}  // namespace lpmx
+
+struct lpmx_bve_solver_s {
+  SolverState st;
+  SumPlan plan_vel, plan_psi;
+};
+struct lpmx_ic2d_solver_s {
+  SolverState st;
+  SumPlan plan_vel, plan_velpsi;
+  double eps = 0;
+};
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------------
+// BVE
+// ------------------------------------------------------------------------------------------------
+int lpmx_bve_solver_create(lpmx_handle_t h, int n_verts, int n_faces, lpmx_bve_solver_t* out) {
+  if (!h || !out) return LPMX_ERR_INVALID;
+  lpmx_bve_solver_s* s = new (std::nothrow) lpmx_bve_solver_s;
+  if (!s) return LPMX_ERR_NOMEM;
+  const int rc = solver_alloc(&s->st, h, n_verts, n_faces, 3);
+  if (rc != LPMX_OK) {
+    delete s;
+    return rc;
+  }
+  *out = s;
+  return LPMX_OK;
+}
+
+int lpmx_bve_solver_destroy(lpmx_bve_solver_t s) {
+  if (!s) return LPMX_OK;
+  if (s->st.h && s->st.h->cached_bve == s) s->st.h->cached_bve = nullptr;
+  solver_free(&s->st);
+  delete s;
+  return LPMX_OK;
+}
+
+int lpmx_bve_solver_set_state(lpmx_bve_solver_t s, const double* vx, const double* vz, const double* vu,
+                              const double* fx, const double* fz, const double* fu, const double* fa,
+                              const unsigned char* fm, int layout, long vld, long fld) {
+  if (!s) return LPMX_ERR_INVALID;
+  LPMX_TRY(solver_set_state(&s->st, vx, vz, vu, fx, fz, fu, fa, fm, layout, vld, fld, /*skip_self=*/1));
+  LPMX_TRY(make_plan(s->st.h, kVel, s->st.t1 - s->st.t0, s->st.n_leaf, &s->plan_vel));
+  LPMX_TRY(make_plan(s->st.h, kPsi, s->st.t1 - s->st.t0, s->st.n_leaf, &s->plan_psi));
+  return LPMX_OK;
+}
+
+int lpmx_bve_solver_get_state(lpmx_bve_solver_t s, double* vx, double* vz, double* vu, double* fx, double* fz,
+                              double* fu, int layout, long vld, long fld) {
+  if (!s) return LPMX_ERR_INVALID;
+  return solver_get_state(&s->st, vx, vz, vu, nullptr, fx, fz, fu, nullptr, layout, vld, fld);
+}
+
+int lpmx_bve_solver_interactions_per_eval(lpmx_bve_solver_t s, double* local, double* global) {
+  if (!s || !s->st.has_state) return LPMX_ERR_INVALID;
+  const SolverState& st = s->st;
+  // every target against every leaf, minus the self pair of each leaf face target
+  const double nl = (double)st.n_leaf;
+  if (global) *global = (double)st.nt * nl - nl;
+  if (local) {
+    // leaves among this rank's face targets
+    const long l0 = st.packed_off[st.h->rank] / 4, l1 = st.packed_off[st.h->rank + 1] / 4;
+    *local = (double)(st.t1 - st.t0) * nl - (double)(st.h->world > 1 ? (l1 - l0) : st.n_leaf);
+  }
+  return LPMX_OK;
+}
+
+static int bve_eval(lpmx_bve_solver_s* s, int stage, int more, double dt, double Omega) {
+  SolverState& st = s->st;
+  lpmx_handle_t h = st.h;
+  const int n_local = st.t1 - st.t0;
+  LPMX_TRY(ensure_partials(&st, s->plan_vel));
+  LPMX_TRY(launch_pair_sum(h, s->plan_vel, st.local_view(st.Xw), st.self_idx + st.t0, st.packed[st.cur], 1.0, st.partials));
+  const bool writes_next = !(stage == 4 && !more);
+  double* next = writes_next ? st.packed[st.cur ^ 1] : nullptr;
+  if (n_local > 0) {
+    const StageArgs a = stage_args(&st, &s->plan_vel, stage, more, dt, Omega, next);
+    const int threads = 128, blocks = (n_local + threads - 1) / threads;
+    bve_rk4_stage_kernel<<<blocks, threads, 0, h->stream>>>(a);
+    ++h->launches;
+    LPMX_CUDA(h, cudaGetLastError());
+  }
+  if (writes_next) {
+    LPMX_TRY(exchange_packed(&st, next));
+    st.cur ^= 1;
+  }
+  return LPMX_OK;
+}
+
+int lpmx_bve_solver_init_velocity(lpmx_bve_solver_t s) {
+  if (!s) return LPMX_ERR_INVALID;
+  SolverState& st = s->st;
+  if (!st.has_state) return set_error(st.h, LPMX_ERR_STATE, "init_velocity before set_state");
+  LPMX_CUDA(st.h, cudaSetDevice(st.h->device));
+  // work state := state
+  LPMX_CUDA(st.h, cudaMemcpyAsync(st.Xw, st.X, sizeof(double) * 3 * (size_t)st.nt, cudaMemcpyDeviceToDevice, st.h->stream));
+  LPMX_CUDA(st.h, cudaMemcpyAsync(st.Zw, st.Z, sizeof(double) * (size_t)st.nt, cudaMemcpyDeviceToDevice, st.h->stream));
+  LPMX_TRY(pack_resident(&st));
+  return bve_eval(s, 4, 0, 0.0, 0.0);
+}
+
+int lpmx_bve_solver_stream_fn(lpmx_bve_solver_t s, double* vert_psi, double* face_psi) {
+  if (!s) return LPMX_ERR_INVALID;
+  SolverState& st = s->st;
+  lpmx_handle_t h = st.h;
+  if (!st.has_state) return set_error(h, LPMX_ERR_STATE, "stream_fn before set_state");
+  LPMX_CUDA(h, cudaSetDevice(h->device));
+  LPMX_TRY(pack_resident(&st));
+  LPMX_TRY(ensure_partials(&st, s->plan_psi));
+  LPMX_TRY(launch_pair_sum(h, s->plan_psi, st.local_view(st.X), st.self_idx + st.t0, st.packed[st.cur], 1.0, st.partials));
+  const int n_local = st.t1 - st.t0;
+  if (n_local > 0) {
+    const int threads = 128, blocks = (n_local + threads - 1) / threads;
+    psi_out_kernel<<<blocks, threads, 0, h->stream>>>(part_view(s->plan_psi, st.partials), st.t0, n_local, st.Psi);
+    ++h->launches;
+    LPMX_CUDA(h, cudaGetLastError());
+  }
+  return solver_get_state(&st, nullptr, nullptr, nullptr, vert_psi, nullptr, nullptr, nullptr, face_psi,
+                          LPMX_LAYOUT_RIGHT, 0, 0);
+}
+
+int lpmx_bve_solver_advance(lpmx_bve_solver_t s, double dt, double Omega, int n_steps) {
+  if (!s) return LPMX_ERR_INVALID;
+  SolverState& st = s->st;
+  lpmx_handle_t h = st.h;
+  if (!st.has_state) return set_error(h, LPMX_ERR_STATE, "advance before set_state");
+  if (n_steps < 0) return set_error(h, LPMX_ERR_INVALID, "negative step count");
+  if (n_steps == 0 || st.nt == 0) return LPMX_OK;
+  LPMX_CUDA(h, cudaSetDevice(h->device));
+  const int n_local = st.t1 - st.t0;
+  // prologue: stage 1 of the first step from the resident velocity
+  if (n_local > 0) {
+    const StageArgs a = stage_args(&st, nullptr, 0, 1, dt, Omega, st.packed[st.cur]);
+    const int threads = 128, blocks = (n_local + threads - 1) / threads;
+    bve_rk4_stage_kernel<<<blocks, threads, 0, h->stream>>>(a);
+    ++h->launches;
+    LPMX_CUDA(h, cudaGetLastError());
+  }
+  LPMX_TRY(exchange_packed(&st, st.packed[st.cur]));
+  for (int step = 0; step < n_steps; ++step) {
+    const int more = step + 1 < n_steps;
+    for (int stage = 1; stage <= 4; ++stage) LPMX_TRY(bve_eval(s, stage, more, dt, Omega));
+  }
+  return LPMX_OK;
+}
+
+int lpmx_bve_rk4_step(lpmx_handle_t h, double dt, double Omega, int n_verts, double* vx, double* vz, double* vu,
+                      int n_faces, double* fx, double* fz, double* fu, const double* fa, const unsigned char* fm,
+                      int layout, long vld, long fld, int n_steps) {
+  if (!h) return LPMX_ERR_INVALID;
+  if ((n_verts > 0 && !vu) || (n_faces > 0 && !fu)) return set_error(h, LPMX_ERR_INVALID, "null velocity array");
+  lpmx_bve_solver_t s = h->cached_bve;
+  if (!s || s->st.nv != n_verts || s->st.nf != n_faces) {
+    if (s) lpmx_bve_solver_destroy(s);
+    h->cached_bve = nullptr;
+    LPMX_TRY(lpmx_bve_solver_create(h, n_verts, n_faces, &s));
+    h->cached_bve = s;
+  }
+  LPMX_TRY(lpmx_bve_solver_set_state(s, vx, vz, vu, fx, fz, fu, fa, fm, layout, vld, fld));
+  LPMX_TRY(lpmx_bve_solver_advance(s, dt, Omega, n_steps));
+  return lpmx_bve_solver_get_state(s, vx, vz, vu, fx, fz, fu, layout, vld, fld);
+}
+
+// ------------------------------------------------------------------------------------------------
+// IC2D
+// ------------------------------------------------------------------------------------------------
+int lpmx_ic2d_solver_create(lpmx_handle_t h, int n_passive, int n_active, double eps, lpmx_ic2d_solver_t* out) {
+  if (!h || !out) return LPMX_ERR_INVALID;
+  lpmx_ic2d_solver_s* s = new (std::nothrow) lpmx_ic2d_solver_s;
+  if (!s) return LPMX_ERR_NOMEM;
+  s->eps = eps;
+  const int rc = solver_alloc(&s->st, h, n_passive, n_active, 1);
+  if (rc != LPMX_OK) {
+    delete s;
+    return rc;
+  }
+  *out = s;
+  return LPMX_OK;
+}
+
+int lpmx_ic2d_solver_destroy(lpmx_ic2d_solver_t s) {
+  if (!s) return LPMX_OK;
+  if (s->st.h && s->st.h->cached_ic2d == s) s->st.h->cached_ic2d = nullptr;
+  solver_free(&s->st);
+  delete s;
+  return LPMX_OK;
+}
+
+int lpmx_ic2d_solver_set_state(lpmx_ic2d_solver_t s, const double* px, const double* pz, const double* pu,
+                               const double* ax, const double* az, const double* au, const double* aa,
+                               const unsigned char* am, int layout, long pld, long ald) {
+  if (!s) return LPMX_ERR_INVALID;
+  // Incompressible2DActiveSums skips the self term only when |eps| < DBL_EPSILON (:235)
+  const int skip = std::fabs(s->eps) < DBL_EPSILON;
+  LPMX_TRY(solver_set_state(&s->st, px, pz, pu, ax, az, au, aa, am, layout, pld, ald, skip));
+  LPMX_TRY(make_plan(s->st.h, kVel, s->st.t1 - s->st.t0, s->st.n_leaf, &s->plan_vel));
+  LPMX_TRY(make_plan(s->st.h, kVelPsi, s->st.t1 - s->st.t0, s->st.n_leaf, &s->plan_velpsi));
+  return LPMX_OK;
+}
+
+int lpmx_ic2d_solver_get_state(lpmx_ic2d_solver_t s, double* px, double* pz, double* pu, double* ppsi, double* ax,
+                               double* az, double* au, double* apsi, int layout, long pld, long ald) {
+  if (!s) return LPMX_ERR_INVALID;
+  return solver_get_state(&s->st, px, pz, pu, ppsi, ax, az, au, apsi, layout, pld, ald);
+}
+
+// one evaluation: stage 1 = predictor (velocity only; its psi is overwritten by the corrector in
+// the reference, quirk B-i), stage 2 = velocity + stream function at the new state
+static int ic2d_eval(lpmx_ic2d_solver_s* s, int stage, int more, double dt, double Omega) {
+  SolverState& st = s->st;
+  lpmx_handle_t h = st.h;
+  const int n_local = st.t1 - st.t0;
+  const bool with_psi = (stage == 2);
+  const SumPlan& plan = with_psi ? s->plan_velpsi : s->plan_vel;
+  const double kappa = 1.0 + s->eps * s->eps;
+  LPMX_TRY(ensure_partials(&st, plan));
+  LPMX_TRY(launch_pair_sum(h, plan, st.local_view(st.Xw), st.self_idx + st.t0, st.packed[st.cur], kappa, st.partials));
+  const bool writes_next = !(stage == 2 && !more);
+  double* next = writes_next ? st.packed[st.cur ^ 1] : nullptr;
+  if (n_local > 0) {
+    const StageArgs a = stage_args(&st, &plan, stage, more, dt, Omega, next);
+    const int threads = 128, blocks = (n_local + threads - 1) / threads;
+    if (with_psi)
+      ic2d_rk2_stage_kernel<true><<<blocks, threads, 0, h->stream>>>(a);
+    else
+      ic2d_rk2_stage_kernel<false><<<blocks, threads, 0, h->stream>>>(a);
+    ++h->launches;
+    LPMX_CUDA(h, cudaGetLastError());
+  }
+  if (writes_next) {
+    LPMX_TRY(exchange_packed(&st, next));
+    st.cur ^= 1;
+  }
+  return LPMX_OK;
+}
+
+int lpmx_ic2d_solver_init_direct_sums(lpmx_ic2d_solver_t s) {
+  if (!s) return LPMX_ERR_INVALID;
+  SolverState& st = s->st;
+  if (!st.has_state) return set_error(st.h, LPMX_ERR_STATE, "init_direct_sums before set_state");
+  LPMX_CUDA(st.h, cudaSetDevice(st.h->device));
+  LPMX_CUDA(st.h, cudaMemcpyAsync(st.Xw, st.X, sizeof(double) * 3 * (size_t)st.nt, cudaMemcpyDeviceToDevice, st.h->stream));
+  LPMX_CUDA(st.h, cudaMemcpyAsync(st.Zw, st.Z, sizeof(double) * (size_t)st.nt, cudaMemcpyDeviceToDevice, st.h->stream));
+  LPMX_TRY(pack_resident(&st));
+  return ic2d_eval(s, 2, 0, 0.0, 0.0);
+}
+
+int lpmx_ic2d_solver_advance(lpmx_ic2d_solver_t s, double dt, double Omega, int n_steps) {
+  if (!s) return LPMX_ERR_INVALID;
+  SolverState& st = s->st;
+  lpmx_handle_t h = st.h;
+  if (!st.has_state) return set_error(h, LPMX_ERR_STATE, "advance before set_state");
+  if (n_steps < 0) return set_error(h, LPMX_ERR_INVALID, "negative step count");
+  if (n_steps == 0 || st.nt == 0) return LPMX_OK;
+  LPMX_CUDA(h, cudaSetDevice(h->device));
+  const int n_local = st.t1 - st.t0;
+  if (n_local > 0) {
+    const StageArgs a = stage_args(&st, nullptr, 0, 1, dt, Omega, st.packed[st.cur]);
+    const int threads = 128, blocks = (n_local + threads - 1) / threads;
+    ic2d_rk2_stage_kernel<false><<<blocks, threads, 0, h->stream>>>(a);
+    ++h->launches;
+    LPMX_CUDA(h, cudaGetLastError());
+  }
+  LPMX_TRY(exchange_packed(&st, st.packed[st.cur]));
+  for (int step = 0; step < n_steps; ++step) {
+    const int more = step + 1 < n_steps;
+    LPMX_TRY(ic2d_eval(s, 1, more, dt, Omega));
+    LPMX_TRY(ic2d_eval(s, 2, more, dt, Omega));
+  }
+  return LPMX_OK;
+}
+
+int lpmx_ic2d_rk2_step(lpmx_handle_t h, double dt, double Omega, double eps, int n_passive, double* px, double* pz,
+                       double* pu, double* ppsi, int n_active, double* ax, double* az, double* au, double* apsi,
+                       const double* aa, const unsigned char* am, int layout, long pld, long ald, int n_steps) {
+  if (!h) return LPMX_ERR_INVALID;
+  if ((n_passive > 0 && !pu) || (n_active > 0 && !au)) return set_error(h, LPMX_ERR_INVALID, "null velocity array");
+  lpmx_ic2d_solver_t s = h->cached_ic2d;
+  if (!s || s->st.nv != n_passive || s->st.nf != n_active || s->eps != eps) {
+    if (s) lpmx_ic2d_solver_destroy(s);
+    h->cached_ic2d = nullptr;
+    LPMX_TRY(lpmx_ic2d_solver_create(h, n_passive, n_active, eps, &s));
+    h->cached_ic2d = s;
+  }
+  LPMX_TRY(lpmx_ic2d_solver_set_state(s, px, pz, pu, ax, az, au, aa, am, layout, pld, ald));
+  LPMX_TRY(lpmx_ic2d_solver_advance(s, dt, Omega, n_steps));
+  return lpmx_ic2d_solver_get_state(s, px, pz, pu, ppsi, ax, az, au, apsi, layout, pld, ald);
+}
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+"""ctypes binding of the CPU oracle (oracle/lpm_oracle.c).  TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(_HERE, "_build", "liblpm_oracle.so")
+REF_LIB = os.path.join(_HERE, "_ref", "liblpm_ref.so")
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_up = ctypes.POINTER(ctypes.c_ubyte)
+
+
+def build(ref=False):
+    targets = ["all"] + (["ref"] if ref else [])
+    subprocess.run(["make", "-C", _HERE] + targets, check=True, capture_output=True)
+
+
+def _load(path):
+    if not os.path.exists(path):
+        if path == LIB:
+            build()
+        else:
+            raise FileNotFoundError(path)
+    return ctypes.CDLL(path)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = _load(LIB)
+        _lib.oracle_num_threads.restype = ctypes.c_int
+    return _lib
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _m(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a, a.ctypes.data_as(_up)
+
+
+def num_threads():
+    return lib().oracle_num_threads()
+
+
+def bve_velocity(tgt_xyz, src_xyz, vort, area, mask, collocated=False, long_double=False, L=None):
+    L = L or lib()
+    src_xyz, vort, area = _d(src_xyz), _d(vort), _d(area)
+    mask, mp = _m(mask)
+    tx = src_xyz if collocated else _d(tgt_xyz)
+    out = np.zeros((tx.shape[0], 3))
+    f = L.oracle_bve_velocity_ld if long_double else L.oracle_bve_velocity
+    f(ctypes.c_int(tx.shape[0]), _p(tx), ctypes.c_int(src_xyz.shape[0]), _p(src_xyz), _p(vort), _p(area), mp,
+      ctypes.c_int(int(collocated)), _p(out))
+    return out
+
+
+def bve_streamfn(tgt_xyz, src_xyz, vort, area, mask, collocated=False, L=None):
+    L = L or lib()
+    src_xyz, vort, area = _d(src_xyz), _d(vort), _d(area)
+    mask, mp = _m(mask)
+    tx = src_xyz if collocated else _d(tgt_xyz)
+    out = np.zeros(tx.shape[0])
+    L.oracle_bve_streamfn(ctypes.c_int(tx.shape[0]), _p(tx), ctypes.c_int(src_xyz.shape[0]), _p(src_xyz), _p(vort),
+                          _p(area), mp, ctypes.c_int(int(collocated)), _p(out))
+    return out
+
+
+def bve_rk4_step(dt, Omega, vx, vz, vu, fx, fz, fu, fa, fm, n_steps=1, L=None):
+    """In place on float64 C-contiguous arrays."""
+    L = L or lib()
+    fm, mp = _m(fm)
+    for a in (vx, vz, vu, fx, fz, fu):
+        assert a.dtype == np.float64 and a.flags.c_contiguous
+    fa = _d(fa)
+    L.oracle_bve_rk4_step(ctypes.c_double(dt), ctypes.c_double(Omega), ctypes.c_int(vx.shape[0]), _p(vx), _p(vz),
+                          _p(vu), ctypes.c_int(fx.shape[0]), _p(fx), _p(fz), _p(fu), _p(fa), mp,
+                          ctypes.c_int(n_steps))
+
+
+def ic2d_sums(tgt_xyz, src_xyz, vort, area, mask, eps=0.0, targets_are_sources=False, with_psi=True, L=None):
+    L = L or lib()
+    src_xyz, vort, area = _d(src_xyz), _d(vort), _d(area)
+    mask, mp = _m(mask)
+    tx = src_xyz if targets_are_sources else _d(tgt_xyz)
+    vel = np.zeros((tx.shape[0], 3))
+    psi = np.zeros(tx.shape[0]) if with_psi else None
+    L.oracle_ic2d_sums(ctypes.c_int(tx.shape[0]), _p(tx), ctypes.c_int(src_xyz.shape[0]), _p(src_xyz), _p(vort),
+                       _p(area), mp, ctypes.c_double(eps), ctypes.c_int(int(targets_are_sources)), _p(vel), _p(psi))
+    return vel, psi
+
+
+def ic2d_rk2_step(dt, Omega, eps, px, pz, pu, ppsi, ax, az, au, apsi, aa, am, n_steps=1, L=None):
+    L = L or lib()
+    am, mp = _m(am)
+    for a in (px, pz, pu, ppsi, ax, az, au, apsi):
+        assert a.dtype == np.float64 and a.flags.c_contiguous
+    aa = _d(aa)
+    L.oracle_ic2d_rk2_step(ctypes.c_double(dt), ctypes.c_double(Omega), ctypes.c_double(eps),
+                           ctypes.c_int(px.shape[0]), _p(px), _p(pz), _p(pu), _p(ppsi), ctypes.c_int(ax.shape[0]),
+                           _p(ax), _p(az), _p(au), _p(apsi), _p(aa), mp, ctypes.c_int(n_steps))
+
+
+def swe_pair(x, y, eps=0.0, L=None):
+    """kzeta, ksigma (unit strength: vort*area = 1), grad_kzeta, grad_ksigma for one pair."""
+    L = L or lib()
+    x, y = _d(x), _d(y)
+    kz, ks, gkz, gks = np.zeros(3), np.zeros(3), np.zeros(9), np.zeros(9)
+    L.oracle_kzeta_sphere(_p(kz), _p(x), _p(y), ctypes.c_double(1.0), ctypes.c_double(1.0), ctypes.c_double(eps))
+    L.oracle_ksigma_sphere(_p(ks), _p(x), _p(y), ctypes.c_double(1.0), ctypes.c_double(1.0), ctypes.c_double(eps))
+    L.oracle_grad_kzeta(_p(gkz), _p(x), _p(y), ctypes.c_double(eps))
+    L.oracle_grad_ksigma(_p(gks), _p(x), _p(y), ctypes.c_double(eps))
+    return kz, ks, gkz, gks
+
+
+def swe_sphere_sums(tgt_xyz, src_xyz, vort, div, area, mask, eps=0.0, targets_are_sources=False, do_velocity=True,
+                    L=None):
+    L = L or lib()
+    src_xyz, vort, div, area = _d(src_xyz), _d(vort), _d(div), _d(area)
+    mask, mp = _m(mask)
+    tx = src_xyz if targets_are_sources else _d(tgt_xyz)
+    n = tx.shape[0]
+    vel, ddot, grad = np.zeros((n, 3)), np.zeros(n), np.zeros((n, 9))
+    L.oracle_swe_sphere_sums(ctypes.c_int(n), _p(tx), ctypes.c_int(src_xyz.shape[0]), _p(src_xyz), _p(vort), _p(div),
+                             _p(area), mp, ctypes.c_double(eps), ctypes.c_int(int(targets_are_sources)),
+                             ctypes.c_int(int(do_velocity)), _p(vel), _p(ddot), _p(grad))
+    return vel, ddot, grad

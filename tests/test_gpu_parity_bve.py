@@ -1,0 +1,193 @@
+"""GPU parity: BVE direct sums and BVERK4 through the C ABI vs the CPU oracle (family A).
+
+Tolerances are the ones BASELINE.json's north_star states: <= 1e-12 on velocity, <= 1e-10 on
+vorticity after a fixed number of steps, as field-relative max-norms (summation order differs).
+Targets compared: all vertices and all LEAF faces.  Divided (masked) faces are targets in the
+reference too, but on icosahedral meshes a parent's centre coincides (d = 1 - x.y <= 2e-16) with its
+centre descendant, so the reference itself returns NaN/garbage there (tests/test_oracle_golden.py
+pins that); on the cubed sphere they are regular and are compared as well.
+"""
+import numpy as np
+import pytest
+
+from conftest import field_rel_err
+from lpm_b200 import gallery
+from lpm_b200.api import LAYOUT_LEFT, LAYOUT_RIGHT, BVESolver
+
+pytestmark = pytest.mark.gpu
+
+VEL_TOL = 1e-12
+VORT_TOL = 1e-10
+
+
+def _ic(mesh, kind):
+    if kind == "rotation":
+        f = gallery.SolidBodyRotation()
+    elif kind == "rh54":
+        f = gallery.RossbyHaurwitz54()
+        f.set_stationary_wave_speed()
+    else:
+        f = gallery.GaussianVortexSphere()
+    return f(mesh.vert_xyz), f(mesh.face_xyz)
+
+
+@pytest.mark.parametrize("seed,depth,ic", [("icos", 2, "rotation"), ("icos", 4, "rotation"), ("cubed", 4, "rh54"),
+                                           ("cubed", 5, "gauss")])
+def test_velocity_vertices_and_faces(engine, oracle, meshes, seed, depth, ic):
+    m = meshes(seed, depth)
+    _, fz = _ic(m, ic)
+    leaf = m.face_mask == 0
+    sel_f = leaf if seed == "icos" else None
+    uv = engine.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask, collocated=False)
+    uf = engine.bve_velocity(None, m.face_xyz, fz, m.face_area, m.face_mask, collocated=True)
+    ov = oracle.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask, collocated=False)
+    of = oracle.bve_velocity(None, m.face_xyz, fz, m.face_area, m.face_mask, collocated=True)
+    assert field_rel_err(uv, ov) <= VEL_TOL
+    assert field_rel_err(uf, of, sel_f) <= VEL_TOL
+
+
+def test_velocity_layout_left_matches_layout_right(engine, meshes):
+    m = meshes("cubed", 3)
+    fz = gallery.SolidBodyRotation()(m.face_xyz)
+    a = engine.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask)
+    vt = np.ascontiguousarray(m.vert_xyz.T)
+    ft = np.ascontiguousarray(m.face_xyz.T)
+    b = engine.bve_velocity(vt, ft, fz, m.face_area, m.face_mask, layout=LAYOUT_LEFT)
+    assert np.array_equal(a, b.T)  # same kernel, same order: bit-identical
+
+
+def test_velocity_device_pointers(engine, oracle, meshes):
+    import torch
+    m = meshes("icos", 3)
+    fz = gallery.SolidBodyRotation()(m.face_xyz)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out = engine.bve_velocity(t(m.vert_xyz), t(m.face_xyz), t(fz), t(m.face_area), t(m.face_mask))
+    engine.sync()
+    ov = oracle.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask)
+    assert field_rel_err(out.cpu().numpy(), ov) <= VEL_TOL
+
+
+@pytest.mark.parametrize("seed,depth", [("icos", 3), ("cubed", 4)])
+def test_streamfn(engine, oracle, meshes, seed, depth):
+    m = meshes(seed, depth)
+    fz = gallery.SolidBodyRotation()(m.face_xyz)
+    leaf = m.face_mask == 0
+    pv = engine.bve_streamfn(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask, collocated=False)
+    pf = engine.bve_streamfn(None, m.face_xyz, fz, m.face_area, m.face_mask, collocated=True)
+    ov = oracle.bve_streamfn(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask, collocated=False)
+    of = oracle.bve_streamfn(None, m.face_xyz, fz, m.face_area, m.face_mask, collocated=True)
+    assert field_rel_err(pv, ov) <= VEL_TOL
+    assert field_rel_err(pf, of, leaf if seed == "icos" else None) <= VEL_TOL
+
+
+def test_edge_cases_empty_and_all_masked(engine):
+    x = np.array([[0.0, 0.0, 1.0], [1.0, 0.0, 0.0]])
+    # no sources
+    out = engine.bve_velocity(x, np.zeros((0, 3)), np.zeros(0), np.zeros(0), np.zeros(0, dtype=np.uint8))
+    assert np.array_equal(out, np.zeros((2, 3)))
+    # every source masked
+    y = np.array([[0.0, 1.0, 0.0]])
+    out = engine.bve_velocity(x, y, np.ones(1), np.ones(1), np.ones(1, dtype=np.uint8))
+    assert np.array_equal(out, np.zeros((2, 3)))
+    # no targets
+    out = engine.bve_velocity(np.zeros((0, 3)), y, np.ones(1), np.ones(1), np.zeros(1, dtype=np.uint8))
+    assert out.shape == (0, 3)
+
+
+def test_ragged_sizes_against_oracle(engine, oracle):
+    """Sizes that are not multiples of the tile (256 sources / 256-1024 targets)."""
+    for n_t, n_s in [(1, 1), (7, 300), (257, 255), (1025, 513), (3000, 1)]:
+        xs, zeta, area = gallery.synthetic_sphere_points(n_s, seed=n_s)
+        xt, _, _ = gallery.synthetic_sphere_points(n_t, seed=1000 + n_t)
+        mask = np.zeros(n_s, dtype=np.uint8)
+        mask[::5] = 1
+        if n_s == 1:
+            mask[:] = 0
+        a = engine.bve_velocity(xt, xs, zeta, area, mask)
+        b = oracle.bve_velocity(xt, xs, zeta, area, mask)
+        assert field_rel_err(a, b) <= VEL_TOL, (n_t, n_s)
+
+
+def _rk4_case(m, ic, oracle):
+    vz, fz = _ic(m, ic)
+    vu = oracle.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask)
+    fu = oracle.bve_velocity(None, m.face_xyz, fz, m.face_area, m.face_mask, collocated=True)
+    return [m.vert_xyz.copy(), vz.copy(), vu, m.face_xyz.copy(), fz.copy(), fu]
+
+
+@pytest.mark.parametrize("seed,depth,ic,nsteps,Omega", [("icos", 3, "rotation", 3, 0.0),
+                                                        ("cubed", 4, "rh54", 3, 2 * np.pi),
+                                                        ("icos", 2, "gauss", 10, 2 * np.pi)])
+def test_rk4_steps_in_place(engine, oracle, meshes, seed, depth, ic, nsteps, Omega):
+    """lpmx_bve_rk4_step == BVERK4::advance_timestep as coded (incl. the facevort4 quirk)."""
+    m = meshes(seed, depth)
+    dt = 0.01
+    ref = _rk4_case(m, ic, oracle)
+    got = [a.copy() for a in ref]
+    if seed == "icos":
+        # divided icos faces are NaN in the reference from the first evaluation on; keep them finite
+        # and identical on both sides by zeroing their (unobservable) velocity
+        for s in (ref, got):
+            s[5][m.face_mask == 1] = 0.0
+    oracle.bve_rk4_step(dt, Omega, *ref, m.face_area, m.face_mask, n_steps=nsteps)
+    engine.bve_rk4_step(dt, Omega, *got, m.face_area, m.face_mask, n_steps=nsteps)
+    leaf = m.face_mask == 0
+    sel = leaf if seed == "icos" else None
+    assert field_rel_err(got[0], ref[0]) <= VEL_TOL      # vertex positions
+    assert field_rel_err(got[3], ref[3], sel) <= VEL_TOL  # face positions
+    assert field_rel_err(got[1], ref[1]) <= VORT_TOL      # vertex vorticity
+    assert field_rel_err(got[4], ref[4], sel) <= VORT_TOL  # face vorticity
+    assert field_rel_err(got[2], ref[2]) <= 10 * VEL_TOL
+    assert field_rel_err(got[5], ref[5], sel) <= 10 * VEL_TOL
+
+
+def test_rk4_face_vorticity_quirk_is_replicated(engine, oracle, meshes):
+    """With Omega != 0 the faces' zeta update uses k4 in the k3 slot (lpm_bve_rk4_impl.hpp:155-157): the
+    GPU result must follow the reference, not the textbook formula.  A vertex placed exactly at a face
+    centre would differ from that face; check via the update identity on a cubed-sphere mesh."""
+    m = meshes("cubed", 3)
+    dt, Omega = 0.05, 2 * np.pi
+    ref = _rk4_case(m, "rh54", oracle)
+    got = [a.copy() for a in ref]
+    oracle.bve_rk4_step(dt, Omega, *ref, m.face_area, m.face_mask, n_steps=1)
+    engine.bve_rk4_step(dt, Omega, *got, m.face_area, m.face_mask, n_steps=1)
+    assert field_rel_err(got[4], ref[4]) <= VORT_TOL
+
+
+def test_resident_solver_matches_in_place_call(engine, oracle, meshes):
+    m = meshes("cubed", 3)
+    state = _rk4_case(m, "rh54", oracle)
+    s = BVESolver(engine, m.n_verts, m.n_faces)
+    s.set_state(*state, np.ascontiguousarray(m.face_area), np.ascontiguousarray(m.face_mask))
+    s.advance(0.01, 2 * np.pi, 2)
+    out = [np.empty_like(a) for a in state]
+    s.get_state(*out)
+    ref = [a.copy() for a in state]
+    engine.bve_rk4_step(0.01, 2 * np.pi, *ref, m.face_area, m.face_mask, n_steps=2)
+    for a, b in zip(out, ref):
+        assert np.array_equal(a, b)
+    # init_velocity reproduces the oracle's initial velocity
+    s.set_state(state[0], state[1], None, state[3], state[4], None, np.ascontiguousarray(m.face_area),
+                np.ascontiguousarray(m.face_mask))
+    s.init_velocity()
+    vu, fu = np.empty_like(state[2]), np.empty_like(state[5])
+    s.get_state(vert_vel=vu, face_vel=fu)
+    assert field_rel_err(vu, state[2]) <= VEL_TOL
+    assert field_rel_err(fu, state[5]) <= VEL_TOL
+    s.close()
+
+
+def test_large_n_sampled_targets(engine, oracle):
+    """BASELINE-size check: cubed-sphere depth 7 (98 304 sources); 2 048 sampled vertex targets are checked
+    against the oracle, and all targets against the analytic solid-body solution's discretisation bound."""
+    from lpm_b200.api import PolyMesh2d
+    m = PolyMesh2d("cubed", 7)
+    sbr = gallery.SolidBodyRotation()
+    fz = sbr(m.face_xyz)
+    uv = engine.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask)
+    rng = np.random.default_rng(7)
+    idx = rng.choice(m.n_verts, 2048, replace=False)
+    ov = oracle.bve_velocity(m.vert_xyz[idx], m.face_xyz, fz, m.face_area, m.face_mask)
+    assert field_rel_err(uv[idx], ov) <= VEL_TOL
+    assert np.abs(uv - sbr.velocity(m.vert_xyz)).max() < 2e-3  # quadrature error at this resolution
