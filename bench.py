@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- the contract benchmark of the direct-sum hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--stepper bve_rk4|ic2d_rk2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...        # the reference's CPU path on the host cores
+
+A "step" is one time step of the stepper over the whole particle set: BVERK4::advance_timestep = 4 velocity
+evaluations (default; BASELINE.json's metric names the RK4 step), or Incompressible2DRK2 = 2 evaluations.
+metric = FP64 particle-pair interactions per second (one interaction = one (target,
+unmasked source, j != i) kernel evaluation; I_eval = (n_v + n_f) n_leaf - n_leaf).
+
+One JSON line on stdout (rank 0).  value: device-resident stepping (state in HBM, CUDA events on the
+engine's stream, L2 flushed between steps).  e2e: the same step through the in-place C-ABI entry point
+lpmx_bve_rk4_step with PINNED HOST buffers, i.e. H2D of the state + step + D2H of the result in the timed
+region.  roofline: the pair-sum kernel alone (CUDA events around each launch) in algorithmic FP64 flops
+(24 per BVE interaction) against the FP64 FMA peak measured live by a DFMA probe (MEASURED_PEAKS.json has no
+FP64 entry).  cpu_baseline: the reference's CPU path timed on the host cores on a bounded target sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOPS_PER_INTERACTION = {"bve_rk4": 24.0, "ic2d_rk2": 27.5}  # ic2d: one 24-flop velocity eval + one 31-flop (u,psi) eval
+EVALS_PER_STEP = {"bve_rk4": 4, "ic2d_rk2": 2}
+
+WORKLOADS = {
+    # name: (seed, depth, vorticity, description)
+    "rh54_cubed7": ("cubed", 7, "rh54", "examples/sphere_rh54: Rossby-Haurwitz 54 on cubedSphereSeed depth 7 "
+                                        "(98306 vertices + 131070 faces, 98304 leaf sources)"),
+    "rotation_icos4": ("icos", 4, "rotation", "examples/bve_rotation: solid-body rotation on icosTriSphereSeed depth 4"),
+    "gauss_icos8": ("icos", 8, "gauss", "examples/sphere_gaussian_vortex on icosTriSphereSeed depth 8 (1.97M particles)"),
+    "gauss_icos9": ("icos", 9, "gauss", "examples/sphere_gaussian_vortex on icosTriSphereSeed depth 9 (7.86M particles)"),
+    "rh54_cubed6": ("cubed", 6, "rh54", "Rossby-Haurwitz 54 on cubedSphereSeed depth 6"),
+    "rh54_cubed5": ("cubed", 5, "rh54", "Rossby-Haurwitz 54 on cubedSphereSeed depth 5 (CPU-sized)"),
+}
+
+
+def build_case(workload):
+    from lpm_b200 import gallery
+    from lpm_b200.api import PolyMesh2d
+    seed, depth, vort, desc = WORKLOADS[workload]
+    m = PolyMesh2d(seed, depth)
+    if vort == "rh54":
+        f = gallery.RossbyHaurwitz54()
+        f.set_stationary_wave_speed()  # u0 = Omega/14, Omega = 2 pi (examples/sphere_rh54.cpp:108-111)
+    elif vort == "rotation":
+        f = gallery.SolidBodyRotation()
+    else:
+        f = gallery.GaussianVortexSphere()
+    return m, f(m.vert_xyz), f(m.face_xyz), desc
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append((float(parts[0]), float(parts[1]), float(parts[2])))
+                    for n, v in zip(names, parts[3:7]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(self.reasons), "samples": 0}
+        sm = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1],
+                "power_w_max": max(s[2] for s in self.samples), "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_reference_lib():
+    """The reference's own functors compiled in place (oracle/_ref) when present, else the restatement."""
+    import ctypes
+    from oracle import oracle
+    if os.path.exists(oracle.REF_LIB):
+        try:
+            L = ctypes.CDLL(oracle.REF_LIB)
+            L.oracle_num_threads.restype = ctypes.c_int
+            return oracle, L, "reference"
+        except OSError:
+            pass
+    return oracle, oracle.lib(), "port"
+
+
+def time_cpu_sample(m, fz, n_sample, reps=1):
+    """Velocity evaluation of the first n_sample vertex targets against all faces with the reference CPU path
+    (OpenMP over targets, sequential j, per-pair divide).  Returns (interactions/s, seconds, kind, threads)."""
+    oracle, L, kind = cpu_reference_lib()
+    n_sample = min(n_sample, m.n_verts)
+    tx = np.ascontiguousarray(m.vert_xyz[:n_sample])
+    if not getattr(time_cpu_sample, "_warm", False):
+        # the first few parallel regions of a process run several times slower (thread-pool start-up)
+        w = np.ascontiguousarray(m.vert_xyz[:max(64, min(n_sample // 16, 2048))])
+        for _ in range(4):
+            oracle.bve_velocity(w, m.face_xyz, fz, m.face_area, m.face_mask, collocated=False, L=L)
+        time_cpu_sample._warm = True
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        oracle.bve_velocity(tx, m.face_xyz, fz, m.face_area, m.face_mask, collocated=False, L=L)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    inter = float(n_sample) * m.n_face_leaves
+    return inter / best, best, kind, L.oracle_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the same step, on the host cores, each step a
+    bounded sample (a slice of the targets, all sources) of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    m, vz, fz, desc = build_case(args.workload)
+    evals = EVALS_PER_STEP[args.stepper]
+    n_sample = args.cpu_sample
+    for _ in range(max(args.warmup, 0)):
+        time_cpu_sample(m, fz, max(n_sample // 8, 64))
+    rates, secs = [], []
+    kind, threads = "port", 1
+    for _ in range(args.steps):
+        r, s, kind, threads = time_cpu_sample(m, fz, n_sample)
+        rates.append(r)
+        secs.append(s)
+    value = float(np.mean(rates))
+    i_eval = float(m.n_verts + m.n_faces) * m.n_face_leaves - m.n_face_leaves
+    sample = (f"{min(n_sample, m.n_verts)} vertex targets x all {m.n_faces} faces ({m.n_face_leaves} leaf sources) per "
+              f"step, one velocity evaluation; full-step time extrapolated linearly in targets")
+    line = {
+        "impl": "reference", "metric": "fp64_pair_interactions_per_s", "value": value, "unit": "interactions/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": evals * i_eval / value * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc, "stepper": args.stepper,
+                   "evals_per_step": evals, "interactions_per_eval": i_eval, "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rh54_cubed7", choices=sorted(WORKLOADS))
+    ap.add_argument("--stepper", default="bve_rk4", choices=["bve_rk4", "ic2d_rk2"])
+    ap.add_argument("--dt", type=float, default=0.01)
+    ap.add_argument("--cpu-sample", type=int, default=65536, help="vertex targets in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    from lpm_b200.api import BVESolver, Engine, IC2DSolver
+    from lpm_b200.dist import env_rank_world, init_engine_comm
+
+    rank, world, local_rank = env_rank_world()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = Engine(local_rank)
+    init_engine_comm(eng, rank, world)
+    stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
+
+    m, vz, fz, desc = build_case(args.workload)
+    nv, nf, nleaf = m.n_verts, m.n_faces, m.n_face_leaves
+    evals = EVALS_PER_STEP[args.stepper]
+    i_eval = float(nv + nf) * nleaf - nleaf
+    Omega = 2 * np.pi
+    area = np.ascontiguousarray(m.face_area)
+    mask = np.ascontiguousarray(m.face_mask)
+
+    if args.stepper == "bve_rk4":
+        solver = BVESolver(eng, nv, nf)
+        solver.set_state(m.vert_xyz, vz, None, m.face_xyz, fz, None, area, mask)
+        solver.init_velocity()
+    else:
+        solver = IC2DSolver(eng, nv, nf, eps=0.0)
+        solver.set_state(m.vert_xyz, vz, None, m.face_xyz, fz, None, area, mask)
+        solver.init_direct_sums()
+    eng.sync()
+    fp64_peak = eng.fp64_peak_tflops()
+
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for _ in range(args.warmup):
+        solver.advance(args.dt, Omega, 1)
+    eng.sync()
+
+    # ---- timed: K device-resident steps, L2 flushed between steps, events on the engine's stream ----
+    sampler = ClockSampler(local_rank)
+    launches0 = eng.launch_count()
+    eng.profile_enable(True)
+    eng.profile_read()
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    evs = []
+    for _ in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush_buf.fill_(1)  # untimed L2 flush
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            solver.advance(args.dt, Omega, 1)
+            e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(sum(step_ms))
+    n_k, k_ms, k_pairs = eng.profile_read()
+    eng.profile_enable(False)
+    launches = eng.launch_count() - launches0
+    if dist is not None:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = evals * i_eval / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (rank-local): algorithmic flops / CUDA-event launch time ----
+    flops_per = 24.0  # BVE velocity pair; the IC2D (u,psi) evaluation counts 31
+    local_inter = evals * args.steps * (float(solver_local_targets(nv + nf, rank, world)) * nleaf)
+    if args.stepper == "ic2d_rk2":
+        flops_per = FLOPS_PER_INTERACTION["ic2d_rk2"]
+    achieved_tf = local_inter * flops_per / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else None
+    roofline = {
+        "bound": "fp64", "kernel": "lpmx::pair_sum_kernel", "achieved": achieved_tf, "peak": fp64_peak,
+        "unit": "TFLOP/s", "frac": (achieved_tf / fp64_peak) if achieved_tf else None,
+        "peak_source": "measured live: lpmx_fp64_peak_tflops DFMA probe (MEASURED_PEAKS.json has no FP64 entry; "
+                       "nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2)",
+        "flops_per_interaction": flops_per, "launches": n_k, "avg_launch_ms": (k_ms / n_k) if n_k else None,
+        "kernel_share_of_step": (k_ms / (sum(step_ms))) if step_ms else None,
+        "fp64_pipe_instr_per_interaction": 9,
+        "traffic": None,
+    }
+    prof = os.path.join(ROOT, "profiles", "r1_pair_sum_dram.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e: in-place C-ABI call on pinned host buffers (H2D + step + D2H inside the timed region) ----
+    e2e = None
+    if rank == 0 and world == 1:
+        def pin(a):
+            t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            return t
+        if args.stepper == "bve_rk4":
+            st_np = [m.vert_xyz.copy(), vz.copy(), np.zeros((nv, 3)), m.face_xyz.copy(), fz.copy(), np.zeros((nf, 3))]
+            solver.get_state(*st_np)
+            host = [pin(a) for a in st_np]
+            h_area, h_mask = pin(area), pin(mask)
+            args_np = [t.numpy() for t in host]
+
+            def one():
+                eng.bve_rk4_step(args.dt, Omega, *args_np, h_area.numpy(), h_mask.numpy(), n_steps=1)
+            h2d = sum(t.numel() * 8 for t in host) + area.nbytes + mask.nbytes
+            d2h = sum(t.numel() * 8 for t in host)
+        else:
+            st_np = [m.vert_xyz.copy(), vz.copy(), np.zeros((nv, 3)), np.zeros(nv), m.face_xyz.copy(), fz.copy(),
+                     np.zeros((nf, 3)), np.zeros(nf)]
+            solver.get_state(*st_np)
+            host = [pin(a) for a in st_np]
+            h_area, h_mask = pin(area), pin(mask)
+            args_np = [t.numpy() for t in host]
+
+            def one():
+                eng.ic2d_rk2_step(args.dt, Omega, 0.0, *args_np, h_area.numpy(), h_mask.numpy(), n_steps=1)
+            h2d = sum(t.numel() * 8 for t in host) - 8 * (nv + nf) + area.nbytes + mask.nbytes
+            d2h = sum(t.numel() * 8 for t in host)
+        one()  # warm-up: allocates the cached solver and the staging buffers
+        torch.cuda.synchronize()
+        t_calls = 0.0
+        for _ in range(args.steps):
+            flush_buf.fill_(1)  # L2 flush between calls, outside the timed call
+            torch.cuda.synchronize()
+            c0 = time.perf_counter()
+            one()  # returns when the results are back in the host buffers
+            t_calls += time.perf_counter() - c0
+        e2e = {"value": evals * i_eval * args.steps / t_calls, "unit": "interactions/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": t_calls / args.steps * 1e3,
+               "api": "lpmx_bve_rk4_step" if args.stepper == "bve_rk4" else "lpmx_ic2d_rk2_step",
+               "host_buffers": "pinned"}
+
+    # ---- CPU baseline on the host cores (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, secs, kind, threads = time_cpu_sample(m, fz, args.cpu_sample)
+        cpu = {"value": rate, "unit": "interactions/s", "cores": threads, "kind": kind,
+               "sample": f"{min(args.cpu_sample, nv)} vertex targets x all {nf} faces ({nleaf} leaf sources), one "
+                         f"velocity evaluation, {secs:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "fp64_pair_interactions_per_s", "value": value, "unit": "interactions/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc, "stepper": args.stepper,
+                       "evals_per_step": evals, "n_verts": nv, "n_faces": nf, "n_leaf_sources": nleaf,
+                       "interactions_per_eval": i_eval, "dt": args.dt, "Omega": Omega,
+                       "parallelism": f"targets sharded over {world} GPU(s), per-stage allgather of leaf source records",
+                       "l2": "flushed between timed steps (256 MiB write)"},
+            "rk_step_ms": ms_per_step, "step_ms_each": step_ms, "wall_s_timed_region": t_wall,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def solver_local_targets(nt, rank, world):
+    return ((rank + 1) * nt) // world - (rank * nt) // world
+
+
+if __name__ == "__main__":
+    sys.exit(main())

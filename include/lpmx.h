@@ -117,6 +117,12 @@ int lpmx_stream(lpmx_handle_t h, void** cuda_stream);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches claim) */
 int lpmx_launch_count(lpmx_handle_t h, long* n_launches);
 
+/* Kernel timing for roofline reports: when enabled, every pair-sum launch is bracketed by CUDA events on
+ * the handle's stream.  lpmx_profile_read synchronises the stream, returns the number of pair-sum launches
+ * and their summed device time (ms) and pair visits since the last read, then resets the counters. */
+int lpmx_profile_enable(lpmx_handle_t h, int enable);
+int lpmx_profile_read(lpmx_handle_t h, long* n_launches, double* total_ms, double* pair_visits);
+
 /* Target sharding over the GPUs of one box (the reference has no multi-device path; DESIGN.md
  * section 6).  The concatenated target list (vertices then faces) is split into `world`
  * contiguous index ranges; this handle evaluates range `rank`.  Default: rank 0 of 1. */

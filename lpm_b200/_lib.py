@@ -67,6 +67,8 @@ def _declare(L):
         "lpmx_sync": [vp],
         "lpmx_stream": [vp, ctypes.POINTER(vp)],
         "lpmx_launch_count": [vp, c_long_p],
+        "lpmx_profile_enable": [vp, i],
+        "lpmx_profile_read": [vp, c_long_p, c_double_p, c_double_p],
         "lpmx_set_partition": [vp, i, i],
         "lpmx_comm_unique_id": [vp],
         "lpmx_comm_init": [vp, vp, i, i],

@@ -173,6 +173,16 @@ class Engine:
         self._check(self._L.lpmx_fp64_peak_tflops(self._h, ctypes.byref(t), ctypes.byref(ms)), "lpmx_fp64_peak_tflops")
         return t.value
 
+    def profile_enable(self, enable=True):
+        self._check(self._L.lpmx_profile_enable(self._h, int(bool(enable))), "lpmx_profile_enable")
+
+    def profile_read(self):
+        """(pair-sum launches, their summed device ms, pair visits incl. zero padding) since the last read."""
+        n, ms, pv = ctypes.c_long(), ctypes.c_double(), ctypes.c_double()
+        self._check(self._L.lpmx_profile_read(self._h, ctypes.byref(n), ctypes.byref(ms), ctypes.byref(pv)),
+                    "lpmx_profile_read")
+        return n.value, ms.value, pv.value
+
     def set_partition(self, rank, world):
         self._check(self._L.lpmx_set_partition(self._h, rank, world), "lpmx_set_partition")
 

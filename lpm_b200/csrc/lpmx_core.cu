@@ -183,6 +183,10 @@ int lpmx_destroy(lpmx_handle_t h) {
     if (kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : h->pinned)
     if (kv.second.p) cudaFreeHost(kv.second.p);
+  for (auto& ev : h->prof_events) {
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
   if (h->nccl_comm && h->nccl_lib) {
     typedef int (*destroy_t)(void*);
     destroy_t f = (destroy_t)dlsym(h->nccl_lib, "ncclCommDestroy");
@@ -211,6 +215,29 @@ int lpmx_stream(lpmx_handle_t h, void** s) {
 int lpmx_launch_count(lpmx_handle_t h, long* n) {
   if (!h || !n) return LPMX_ERR_INVALID;
   *n = h->launches;
+  return LPMX_OK;
+}
+
+int lpmx_profile_enable(lpmx_handle_t h, int enable) {
+  if (!h) return LPMX_ERR_INVALID;
+  h->profile = enable != 0;
+  return LPMX_OK;
+}
+
+int lpmx_profile_read(lpmx_handle_t h, long* n_launches, double* total_ms, double* pair_visits) {
+  if (!h) return LPMX_ERR_INVALID;
+  LPMX_CUDA(h, cudaStreamSynchronize(h->stream));
+  double ms = 0;
+  for (size_t i = 0; i < h->prof_used; ++i) {
+    float t = 0;
+    LPMX_CUDA(h, cudaEventElapsedTime(&t, h->prof_events[i].first, h->prof_events[i].second));
+    ms += t;
+  }
+  if (n_launches) *n_launches = (long)h->prof_used;
+  if (total_ms) *total_ms = ms;
+  if (pair_visits) *pair_visits = h->prof_pairs;
+  h->prof_used = 0;
+  h->prof_pairs = 0;
   return LPMX_OK;
 }
 

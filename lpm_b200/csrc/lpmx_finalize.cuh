@@ -10,6 +10,15 @@ namespace lpmx {
 #define LPMX_PI 3.1415926535897932384626433832795027975
 __device__ __forceinline__ double gamma_of(double strength, double area) { return (-strength * area) / (4.0 * LPMX_PI); }
 
+// the 64-byte source record of the BVE / IC2D kinds
+__device__ __forceinline__ void write_bve_record(double* rec, const double* y, double gam) {
+  double2* r2 = reinterpret_cast<double2*>(rec);
+  r2[0] = make_double2(y[0], y[1]);
+  r2[1] = make_double2(y[2], gam * y[0]);
+  r2[2] = make_double2(gam * y[1], gam * y[2]);
+  r2[3] = make_double2(gam, 0.0);
+}
+
 // Where the pair-sum kernel left its partial sums for a launch (mirrors SumPlan).
 struct PartView {
   const double* part;

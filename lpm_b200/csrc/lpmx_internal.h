@@ -19,9 +19,6 @@ namespace lpmx {
 // ------------------------------------------------------------------------------------------------
 constexpr int kStages = 4;          // TMA ring depth
 constexpr int kChunk = 256;         // sources per TMA stage
-constexpr int kComputeWarps = 8;    // compute warps per CTA (+1 producer warp)
-constexpr int kCtaThreads = (kComputeWarps + 1) * 32;
-constexpr int kLanesPerCta = kComputeWarps * 32;
 
 enum PairKind : int {
   kVel = 0,     // moment  M = sum Gamma y / d                    (BVE + IC2D velocity)
@@ -30,7 +27,11 @@ enum PairKind : int {
   kSwe = 3,     // Mz, Ms, G[9]                                   (spherical SWE 12-tuple)
 };
 constexpr int kind_nacc(int k) { return k == kVel ? 3 : k == kVelPsi ? 4 : k == kPsi ? 1 : 15; }
-constexpr int kind_rec(int k) { return k == kSwe ? 6 : 4; }  // doubles per packed source record
+// doubles per packed source record:
+//   BVE / IC2D kinds  {y0, y1, y2, G*y0, G*y1, G*y2, G, 0}   (G = -zeta*A/(4 pi); 64 bytes)
+//   SWE               {y0, y1, y2, Gz, Gs, 0}                 (48 bytes)
+constexpr int kBveRec = 8;
+constexpr int kind_rec(int k) { return k == kSwe ? 6 : kBveRec; }
 
 // strided accessor for Real*[3] views: element (i,k) at p[i*si + k*sk]
 struct Vec3View {
@@ -54,8 +55,9 @@ inline Vec3View make_view(const double* p, int layout, long ld) {
 // Work decomposition of one pair-sum launch (stream-K over target blocks x source chunks).
 struct SumPlan {
   int kind;
+  int shape;        // index of the kernel instance (lpmx_kernels.cu: kShapes)
   int T;            // targets per thread
-  int tb;           // targets per CTA block = T * kLanesPerCta
+  int tb;           // targets per CTA block = T * compute lanes per CTA
   int n_tgt;        // targets evaluated by this launch
   int n_tb;         // target blocks
   int n_src_pad;    // packed sources incl. zero padding (multiple of kChunk)
@@ -86,6 +88,11 @@ struct lpmx_handle_s {
   void* nccl_lib = nullptr;   // dlopen handle
   std::map<std::string, lpmx::DevBuf> bufs;  // named scratch buffers
   std::map<std::string, lpmx::DevBuf> pinned;  // named pinned host staging buffers
+  // optional per-launch timing of the pair-sum kernel (lpmx_profile_enable)
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  size_t prof_used = 0;
+  double prof_pairs = 0;
   // cached one-shot solvers for the in-place stepper entry points
   lpmx_bve_solver_t cached_bve = nullptr;
   lpmx_ic2d_solver_t cached_ic2d = nullptr;

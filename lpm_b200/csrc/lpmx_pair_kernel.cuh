@@ -1,0 +1,330 @@
+// lpmx_pair_kernel.cuh -- device code of the O(N^2) pair-sum kernel family (sm_100a).
+// Included by lpmx_kernels.cu (the product instances) and tools/tune_pair_sum.cu (the tuning
+// harness that times alternative shapes on the GPU box).  See lpmx_kernels.cu for the design notes.
+#ifndef LPMX_PAIR_KERNEL_CUH
+#define LPMX_PAIR_KERNEL_CUH
+
+#include "lpmx_internal.h"
+
+namespace lpmx {
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk TMA
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (TMA, SASS UBLKCP); bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// 20-bit reciprocal seed (MUFU.RCP64H)
+__device__ __forceinline__ double rcp_seed(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel arguments
+// ------------------------------------------------------------------------------------------------
+struct SumArgs {
+  Vec3View tgt;
+  const int* self_idx;
+  const double* packed;
+  double* part;
+  int n_tgt;
+  int n_tb;
+  int n_sc;
+  long n_tgt_pad;
+  double kappa;  // 1 + eps^2
+};
+
+__host__ __device__ __forceinline__ int cta_of_item(long item, int grid, long n_items) {
+  return (int)(((item + 1) * (long)grid - 1) / n_items);
+}
+
+// Per-kind pair bodies.  x = target, (y, g..) = source record, acc = this target's accumulators.
+// CHECK: compare the source's global compact index with the target's own (self) index.
+template <int KIND, bool CHECK>
+struct Pair;
+
+// BVE / IC2D record: s = {y0, y1, y2, G*y0, G*y1, G*y2, G, 0}.
+// Velocity moment: 9 FP64-pipe instructions per pair -- 3 (d), 3 (r = 1/d from the MUFU seed), 3 (M += r * G*y).
+template <bool CHECK>
+struct Pair<kVel, CHECK> {
+  static constexpr int NLOAD = 6;  // doubles of the record this kind reads
+  __device__ __forceinline__ static void apply(const double* x, const double* /*kx*/, double kappa, const double* s,
+                                               int j, int self, double* acc) {
+    const double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
+    const double r0 = rcp_seed(d);
+    const double e = fma(-d, r0, 1.0);
+    const double p = fma(e, e, e);
+    double r = fma(r0, p, r0);
+    if (CHECK) r = (j == self) ? 0.0 : r;
+    acc[0] = fma(r, s[3], acc[0]);
+    acc[1] = fma(r, s[4], acc[1]);
+    acc[2] = fma(r, s[5], acc[2]);
+  }
+};
+
+template <bool CHECK>
+struct Pair<kVelPsi, CHECK> {
+  static constexpr int NLOAD = 8;
+  __device__ __forceinline__ static void apply(const double* x, const double*, double kappa, const double* s, int j,
+                                               int self, double* acc) {
+    double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
+    double gam = s[6];
+    if (CHECK) {
+      const bool me = (j == self);
+      d = me ? 1.0 : d;
+      gam = me ? 0.0 : gam;
+    }
+    const double r0 = rcp_seed(d);
+    const double e = fma(-d, r0, 1.0);
+    const double p = fma(e, e, e);
+    double r = fma(r0, p, r0);
+    if (CHECK) r = (j == self) ? 0.0 : r;
+    acc[0] = fma(r, s[3], acc[0]);
+    acc[1] = fma(r, s[4], acc[1]);
+    acc[2] = fma(r, s[5], acc[2]);
+    acc[3] = fma(gam, log(d), acc[3]);
+  }
+};
+
+template <bool CHECK>
+struct Pair<kPsi, CHECK> {
+  static constexpr int NLOAD = 8;
+  __device__ __forceinline__ static void apply(const double* x, const double*, double kappa, const double* s, int j,
+                                               int self, double* acc) {
+    double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
+    double gam = s[6];
+    if (CHECK) {
+      const bool me = (j == self);
+      d = me ? 1.0 : d;
+      gam = me ? 0.0 : gam;
+    }
+    acc[0] = fma(gam, log(d), acc[0]);
+  }
+};
+
+// kSwe accumulators: [0..2] Mz = sum Gz y/d, [3..5] Ms = sum Gs y/d, [6..14] G (row-major):
+//   G_ab += (Gz/d^2) c_a q_b - (Gs/d^2) q_a p_b,  c = x cross y, q = kappa x - y, p = y - (x.y) x
+// The 1/d parts of the coded gradient polynomials ([y]x / d and (x.y) P / d) are linear in y and
+// are rebuilt from Mz and Ms in the finalize kernel.
+template <bool CHECK>
+struct Pair<kSwe, CHECK> {
+  static constexpr int NLOAD = 6;
+  __device__ __forceinline__ static void apply(const double* x, const double* kx, double kappa, const double* s,
+                                               int j, int self, double* acc) {
+    double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
+    double gz = s[3], gs = s[4];
+    if (CHECK) {
+      const bool me = (j == self);
+      d = me ? 1.0 : d;
+      gz = me ? 0.0 : gz;
+      gs = me ? 0.0 : gs;
+    }
+    const double xy = kappa - d;
+    const double r0 = rcp_seed(d);
+    const double e = fma(-d, r0, 1.0);
+    const double pp = fma(e, e, e);
+    const double r = fma(r0, pp, r0);
+    const double wz = gz * r, ws = gs * r;
+    acc[0] = fma(wz, s[0], acc[0]);
+    acc[1] = fma(wz, s[1], acc[1]);
+    acc[2] = fma(wz, s[2], acc[2]);
+    acc[3] = fma(ws, s[0], acc[3]);
+    acc[4] = fma(ws, s[1], acc[4]);
+    acc[5] = fma(ws, s[2], acc[5]);
+    const double wz2 = wz * r, ws2 = ws * r;
+    double c[3], q[3], p[3];
+    c[0] = fma(x[1], s[2], -(x[2] * s[1]));
+    c[1] = fma(x[2], s[0], -(x[0] * s[2]));
+    c[2] = fma(x[0], s[1], -(x[1] * s[0]));
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      q[b] = kx[b] - s[b];
+      p[b] = fma(-xy, x[b], s[b]);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double cz = wz2 * c[a];
+      const double qs = ws2 * q[a];
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        acc[6 + 3 * a + b] = fma(cz, q[b], acc[6 + 3 * a + b]);
+        acc[6 + 3 * a + b] = fma(-qs, p[b], acc[6 + 3 * a + b]);
+      }
+    }
+  }
+};
+
+template <int KIND, int T, int UNROLL, bool CHECK>
+__device__ __forceinline__ void chunk_loop(const double (*x)[3], const double (*kx)[3], double kappa,
+                                           const double* __restrict__ sp, int j0, const int* self,
+                                           double (*acc)[kind_nacc(KIND)]) {
+  constexpr int REC = kind_rec(KIND);
+#pragma unroll UNROLL
+  for (int j = 0; j < kChunk; ++j) {
+    constexpr int NLOAD = Pair<KIND, CHECK>::NLOAD;
+    double s[NLOAD];
+    const double2* s2 = reinterpret_cast<const double2*>(sp + (size_t)j * REC);
+#pragma unroll
+    for (int v = 0; v < NLOAD / 2; ++v) {
+      const double2 t = s2[v];
+      s[2 * v] = t.x;
+      s[2 * v + 1] = t.y;
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) Pair<KIND, CHECK>::apply(x[t], kx[t], kappa, s, j0 + j, self[t], acc[t]);
+  }
+}
+
+// Compile-time shape of one kernel instance.
+//   KIND    pair body (PairKind)          T      targets per thread (register blocking)
+//   NW      compute warps per CTA (+1 producer warp)     MINB   CTAs per SM the register budget allows
+//   UNROLL  unroll factor of the source loop
+template <int KIND_, int T_, int NW_, int MINB_, int UNROLL_>
+struct PairCfg {
+  static constexpr int KIND = KIND_, T = T_, NW = NW_, MINB = MINB_, UNROLL = UNROLL_;
+  static constexpr int THREADS = (NW_ + 1) * 32;
+  static constexpr int LANES = NW_ * 32;
+  static constexpr int TB = T_ * NW_ * 32;
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, C::MINB) pair_sum_kernel(const SumArgs a) {
+  constexpr int KIND = C::KIND;
+  constexpr int T = C::T;
+  constexpr int kComputeWarps = C::NW;
+  constexpr int kLanesPerCta = C::LANES;
+  constexpr int REC = kind_rec(KIND);
+  constexpr int NACC = kind_nacc(KIND);
+  constexpr uint32_t kStageBytes = kChunk * REC * sizeof(double);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stage = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kStageBytes);
+  uint64_t* empty = full + kStages;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, kComputeWarps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const long n_items = (long)a.n_tb * a.n_sc;
+  const int grid = gridDim.x;
+  const long it0 = ((long)blockIdx.x * n_items) / grid;
+  const long it1 = ((long)(blockIdx.x + 1) * n_items) / grid;
+
+  if (warp == kComputeWarps) {
+    // ---- producer warp: one lane streams source chunks through the ring ----
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      int sc = (int)(it0 % a.n_sc);
+      for (long it = it0; it < it1; ++it) {
+        mbar_wait(empty + s, ph ^ 1u);
+        mbar_arrive_expect_tx(full + s, kStageBytes);
+        tma_load_1d(stage + (size_t)s * kChunk * REC, a.packed + (size_t)sc * kChunk * REC, kStageBytes, full + s);
+        if (++sc == a.n_sc) sc = 0;
+        if (++s == kStages) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+    return;
+  }
+
+  // ---- compute warps ----
+  const int tid = threadIdx.x;  // 0 .. kLanesPerCta-1
+  constexpr int TB = C::TB;
+  int s = 0;
+  uint32_t ph = 0;
+  long it = it0;
+  while (it < it1) {
+    const int tb = (int)(it / a.n_sc);
+    int sc = (int)(it - (long)tb * a.n_sc);
+    const long it_end = min(it1, (long)(tb + 1) * a.n_sc);
+
+    double x[T][3], kx[T][3], acc[T][NACC];
+    int self[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const long tg = (long)tb * TB + t * kLanesPerCta + tid;
+      const bool valid = tg < a.n_tgt;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        x[t][k] = valid ? a.tgt(tg, k) : 0.0;
+        kx[t][k] = a.kappa * x[t][k];
+      }
+      self[t] = (valid && a.self_idx) ? a.self_idx[tg] : -1;
+#pragma unroll
+      for (int q = 0; q < NACC; ++q) acc[t][q] = 0.0;
+    }
+
+    for (; it < it_end; ++it, ++sc) {
+      mbar_wait(full + s, ph);
+      const double* sp = stage + (size_t)s * kChunk * REC;
+      const int j0 = sc * kChunk;
+      bool hit = false;
+#pragma unroll
+      for (int t = 0; t < T; ++t) hit |= (unsigned)(self[t] - j0) < (unsigned)kChunk;
+      if (__any_sync(0xffffffffu, hit))
+        chunk_loop<KIND, T, C::UNROLL, true>(x, kx, a.kappa, sp, j0, self, acc);
+      else
+        chunk_loop<KIND, T, C::UNROLL, false>(x, kx, a.kappa, sp, j0, self, acc);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);
+      if (++s == kStages) {
+        s = 0;
+        ph ^= 1u;
+      }
+    }
+
+    // flush this CTA's contribution to target block tb into its slot
+    const int slot = blockIdx.x - cta_of_item((long)tb * a.n_sc, grid, n_items);
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const long tg = (long)tb * TB + t * kLanesPerCta + tid;
+#pragma unroll
+      for (int q = 0; q < NACC; ++q) a.part[((long)slot * NACC + q) * a.n_tgt_pad + tg] = acc[t][q];
+    }
+  }
+}
+
+
+}  // namespace lpmx
+#endif

@@ -69,8 +69,8 @@ static int solver_alloc(SolverState* s, lpmx_handle_t h, int nv, int nf, int n_k
   const long nt = s->nt;
   s->n_src_pad = round_up_chunk(nf);  // upper bound: every face a leaf
   // one slab: X U Xw (3nt each) Z Zw Psi (nt each) K (n_k * 4nt) area packed[2] | ints | mask
-  size_t dbl = 9 * nt + 3 * nt + (size_t)n_k * 4 * nt + nf + 2 * 4 * (size_t)(s->n_src_pad + kChunk);
-  size_t bytes = dbl * sizeof(double) + sizeof(int) * (size_t)(nf + 1 + nt + 1) + (size_t)nf + 64;
+  size_t dbl = 9 * nt + 3 * nt + (size_t)n_k * 4 * nt + nf + 2 * kBveRec * (size_t)(s->n_src_pad + kChunk);
+  size_t bytes = dbl * sizeof(double) + sizeof(int) * (size_t)(nf + 1 + nt + 1) + (size_t)nf + 64 + 256;
   LPMX_CUDA(h, cudaMalloc(&s->slab, bytes));
   LPMX_CUDA(h, cudaMemsetAsync(s->slab, 0, bytes, h->stream));  // Kokkos views start at zero
   double* p = (double*)s->slab;
@@ -85,8 +85,9 @@ static int solver_alloc(SolverState* s, lpmx_handle_t h, int nv, int nf, int n_k
     s->K[k][1] = p, p += nt;
   }
   s->area = p, p += nf;
-  s->packed[0] = p, p += 4 * (size_t)(s->n_src_pad + kChunk);
-  s->packed[1] = p, p += 4 * (size_t)(s->n_src_pad + kChunk);
+  p = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(p) + 127) & ~(uintptr_t)127);  // TMA source alignment
+  s->packed[0] = p, p += kBveRec * (size_t)(s->n_src_pad + kChunk);
+  s->packed[1] = p, p += kBveRec * (size_t)(s->n_src_pad + kChunk);
   int* ip = (int*)p;
   s->leaf_idx = ip, ip += nf + 1;
   s->self_idx = ip, ip += nt + 1;
@@ -161,11 +162,7 @@ __device__ __forceinline__ void pack_target(long g, int nv, const unsigned char*
   if (g < nv || !packed) return;
   const long f = g - nv;
   if (mask[f]) return;
-  double* rec = packed + 4 * (size_t)leaf_idx[f];
-  rec[0] = x[0];
-  rec[1] = x[1];
-  rec[2] = x[2];
-  rec[3] = gamma_of(zeta, area[f]);
+  write_bve_record(packed + kBveRec * (size_t)leaf_idx[f], x, gamma_of(zeta, area[f]));
 }
 
 // pack the current state (X, Z) [or work state] of this rank's targets
@@ -399,7 +396,7 @@ static int solver_set_state(SolverState* s, const double* vx, const double* vz, 
   }
   s->n_src_pad = round_up_chunk(s->n_leaf);
   // zero both packed buffers once: the padding records must stay {0,0,0,0}
-  const size_t pk_bytes = sizeof(double) * 4 * (size_t)(round_up_chunk(s->nf) + kChunk);
+  const size_t pk_bytes = sizeof(double) * kBveRec * (size_t)(round_up_chunk(s->nf) + kChunk);
   LPMX_CUDA(h, cudaMemsetAsync(s->packed[0], 0, pk_bytes, h->stream));
   LPMX_CUDA(h, cudaMemsetAsync(s->packed[1], 0, pk_bytes, h->stream));
   // shard offsets (targets, and each rank's leaf range in the packed array)
@@ -419,7 +416,7 @@ static int solver_set_state(SolverState* s, const double* vx, const double* vz, 
     if (f < 0) f = 0;
     long l = (f >= s->nf) ? s->n_leaf : (W > 1 ? leaf_host[f] : 0);
     if (r == W) l = s->n_leaf;
-    s->packed_off[r] = 4 * l;
+    s->packed_off[r] = kBveRec * l;
   }
   s->t0 = (int)s->tgt_off[h->rank];
   s->t1 = (int)s->tgt_off[h->rank + 1];
@@ -581,7 +578,7 @@ int lpmx_bve_solver_interactions_per_eval(lpmx_bve_solver_t s, double* local, do
   if (global) *global = (double)st.nt * nl - nl;
   if (local) {
     // leaves among this rank's face targets
-    const long l0 = st.packed_off[st.h->rank] / 4, l1 = st.packed_off[st.h->rank + 1] / 4;
+    const long l0 = st.packed_off[st.h->rank] / kBveRec, l1 = st.packed_off[st.h->rank + 1] / kBveRec;
     *local = (double)(st.t1 - st.t0) * nl - (double)(st.h->world > 1 ? (l1 - l0) : st.n_leaf);
   }
   return LPMX_OK;

@@ -23,13 +23,16 @@ __global__ void pack_sources_kernel(Vec3View sx, const double* __restrict__ vort
     const bool leaf = mask[i] == 0;
     if (leaf) {
       double* rec = packed + (size_t)leaf_idx[i] * REC;
-      rec[0] = sx(i, 0);
-      rec[1] = sx(i, 1);
-      rec[2] = sx(i, 2);
-      rec[3] = gamma_of(vort[i], area[i]);
+      const double y[3] = {sx(i, 0), sx(i, 1), sx(i, 2)};
       if (REC == 6) {
+        rec[0] = y[0];
+        rec[1] = y[1];
+        rec[2] = y[2];
+        rec[3] = gamma_of(vort[i], area[i]);
         rec[4] = gamma_of(div[i], area[i]);
         rec[5] = 0.0;
+      } else {
+        write_bve_record(rec, y, gamma_of(vort[i], area[i]));
       }
     }
     if (self_idx) self_idx[i] = (skip_self && leaf) ? leaf_idx[i] : -1;
@@ -182,8 +185,8 @@ static int run_sum(lpmx_handle_t h, const SumCall& c) {
     const int threads = 256;
     int blocks = (std::max(c.n_src, plan.n_src_pad - n_leaf) + threads - 1) / threads;
     if (blocks < 1) blocks = 1;
-    if (rec == 4)
-      pack_sources_kernel<4><<<blocks, threads, 0, h->stream>>>(sxv, (const double*)d_vort, nullptr, (const double*)d_area,
+    if (rec == kBveRec)
+      pack_sources_kernel<kBveRec><<<blocks, threads, 0, h->stream>>>(sxv, (const double*)d_vort, nullptr, (const double*)d_area,
                                                                 (const unsigned char*)d_mask, (const int*)d_leaf,
                                                                 c.n_src, n_leaf, plan.n_src_pad, (double*)d_packed,
                                                                 (int*)d_self, c.skip_self);

@@ -113,3 +113,17 @@ def synthetic_sphere_points(n, seed=20261017):
     zeta = rh(x)
     area = np.full(n, 4 * PI / n)
     return x, zeta, area
+
+
+def fibonacci_sphere_points(n):
+    """Quasi-uniform synthetic particle set for the N-sweep: Fibonacci (golden-angle) lattice, smooth
+    RH54 vorticity, equal areas 4pi/N.  Deterministic, no RNG; nearest-neighbour spacing ~ sqrt(4pi/N),
+    so the 1 - x.y kernel stays as well conditioned as on LPM's own meshes."""
+    i = np.arange(n, dtype=np.float64)
+    z = 1.0 - (2.0 * i + 1.0) / n
+    r = np.sqrt(np.maximum(0.0, 1.0 - z * z))
+    phi = i * (PI * (3.0 - np.sqrt(5.0)))
+    x = np.stack([r * np.cos(phi), r * np.sin(phi), z], axis=1)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    rh = RossbyHaurwitz54(u0=2 * PI / 14)
+    return x, rh(x), np.full(n, 4 * PI / n)

@@ -1,0 +1,144 @@
+// ref_driver.cpp -- C entry points around the REFERENCE's own direct-sum functors, compiled in place from
+// /root/reference/src (never copied) against oracle/kokkos_shim.  Output: oracle/_ref/liblpm_ref.so.
+// TEST INFRASTRUCTURE: used by tests/test_ref_build.py to pin oracle/lpm_oracle.c (same C signatures, so
+// either library can sit behind oracle/oracle.py), and optionally as the timed CPU baseline
+// (bench.py --impl reference, cpu_baseline.kind == "reference").
+//
+// Reference code exercised (all as shipped):
+//   lpm_sphere_functions.hpp   greens_fn, biot_savart
+//   lpm_bve_sphere_kernels.hpp BVEVertexVelocity, BVEFaceVelocity, BVEVertexStreamFn, BVEFaceStreamFn,
+//                              BVEVorticityTendency
+//   lpm_incompressible2d_kernels.hpp  Incompressible2DPassiveSums / ActiveSums <SphereGeometry>
+//   lpm_swe_kernels.hpp        kzeta_sphere, ksigma_sphere, grad_kzeta, grad_ksigma, SphereVertexSums,
+//                              SphereFaceSums
+#include <cstdint>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "lpm_coriolis.hpp"  // lpm_incompressible2d_kernels.hpp relies on its includer for this
+#include "lpm_bve_sphere_kernels.hpp"
+#include "lpm_incompressible2d_kernels.hpp"
+#include "lpm_swe_kernels.hpp"
+
+using namespace Lpm;
+using crd = SphereGeometry::crd_view_type;
+using vec = SphereGeometry::vec_view_type;
+
+namespace {
+struct Mask {
+  std::unique_ptr<bool[]> b;
+  mask_view_type v;
+  Mask(const uint8_t* m, int n) : b(new bool[n > 0 ? n : 1]) {
+    for (int i = 0; i < n; ++i) b[i] = m[i] != 0;
+    v = mask_view_type(b.get(), n);
+  }
+};
+inline crd wrap3(const double* p, int n) { return crd(const_cast<double*>(p), n); }
+inline scalar_view_type wrap1(const double* p, int n) { return scalar_view_type(const_cast<double*>(p), n); }
+}  // namespace
+
+extern "C" {
+
+int oracle_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+void oracle_bve_velocity(int n_tgt, const double* tx, int n_src, const double* sx, const double* zeta,
+                         const double* area, const uint8_t* mask, int collocated, double* vel) {
+  Mask fm(mask, n_src);
+  crd fx = wrap3(sx, n_src);
+  scalar_view_type fz = wrap1(zeta, n_src), fa = wrap1(area, n_src);
+  vec u = wrap3(vel, n_tgt);
+  if (collocated) {
+    Kokkos::parallel_for("ref face velocity", Kokkos::TeamPolicy<>(n_src, Kokkos::AUTO()),
+                         BVEFaceVelocity(u, fx, fz, fa, fm.v, n_src));
+  } else {
+    crd vx = wrap3(tx, n_tgt);
+    Kokkos::parallel_for("ref vertex velocity", Kokkos::TeamPolicy<>(n_tgt, Kokkos::AUTO()),
+                         BVEVertexVelocity(u, vx, fx, fz, fa, fm.v, n_src));
+  }
+}
+
+void oracle_bve_streamfn(int n_tgt, const double* tx, int n_src, const double* sx, const double* zeta,
+                         const double* area, const uint8_t* mask, int collocated, double* psi) {
+  Mask fm(mask, n_src);
+  crd fx = wrap3(sx, n_src);
+  scalar_view_type fz = wrap1(zeta, n_src), fa = wrap1(area, n_src);
+  scalar_view_type p = wrap1(psi, n_tgt);
+  if (collocated) {
+    Kokkos::parallel_for(Kokkos::TeamPolicy<>(n_src, Kokkos::AUTO()), BVEFaceStreamFn(p, fx, fz, fa, fm.v, n_src));
+  } else {
+    crd vx = wrap3(tx, n_tgt);
+    Kokkos::parallel_for(Kokkos::TeamPolicy<>(n_tgt, Kokkos::AUTO()), BVEVertexStreamFn(p, vx, fx, fz, fa, fm.v, n_src));
+  }
+}
+
+void oracle_ic2d_sums(int n_tgt, const double* tx, int n_src, const double* sx, const double* zeta,
+                      const double* area, const uint8_t* mask, double eps, int targets_are_sources, double* vel,
+                      double* psi) {
+  Mask am(mask, n_src);
+  crd ay = wrap3(sx, n_src);
+  scalar_view_type az = wrap1(zeta, n_src), aa = wrap1(area, n_src);
+  vec u = wrap3(vel, n_tgt);
+  std::vector<double> scratch;
+  if (!psi) {
+    scratch.resize(n_tgt > 0 ? n_tgt : 1);
+    psi = scratch.data();
+  }
+  scalar_view_type p = wrap1(psi, n_tgt);
+  if (targets_are_sources) {
+    Kokkos::parallel_for(Kokkos::TeamPolicy<>(n_src, Kokkos::AUTO()),
+                         Incompressible2DActiveSums<SphereGeometry>(u, p, ay, az, aa, am.v, eps, n_src));
+  } else {
+    crd px = wrap3(tx, n_tgt);
+    Kokkos::parallel_for(Kokkos::TeamPolicy<>(n_tgt, Kokkos::AUTO()),
+                         Incompressible2DPassiveSums<SphereGeometry>(u, p, px, ay, az, aa, am.v, eps, n_src));
+  }
+}
+
+void oracle_kzeta_sphere(double* u, const double* x, const double* y, double vort, double area, double eps) {
+  kzeta_sphere(u, x, y, vort, area, eps);
+}
+void oracle_ksigma_sphere(double* u, const double* x, const double* y, double div, double area, double eps) {
+  ksigma_sphere(u, x, y, div, area, eps);
+}
+void oracle_grad_kzeta(double* g, const double* x, const double* y, double eps) { grad_kzeta(g, x, y, eps); }
+void oracle_grad_ksigma(double* g, const double* x, const double* y, double eps) { grad_ksigma(g, x, y, eps); }
+
+// SphereVertexSums / SphereFaceSums.  The reference leaves velz/vels uninitialised inside
+// sphere_swe_velocity_sums (undefined behaviour, SURVEY.md quirk C-i), so the VELOCITY part of this entry
+// point is whatever the compiler made of that; ddot / gradient sums are well defined.  grad9 is not
+// exposed by the reference functors and is left untouched here.
+void oracle_swe_sphere_sums(int n_tgt, const double* tx, int n_src, const double* sx, const double* zeta,
+                            const double* sigma, const double* area, const uint8_t* mask, double eps,
+                            int targets_are_sources, int do_velocity, double* vel, double* ddot, double* grad9) {
+  (void)grad9;
+  Mask fm(mask, n_src);
+  crd fy = wrap3(sx, n_src);
+  scalar_view_type fz = wrap1(zeta, n_src), fs = wrap1(sigma, n_src), fa = wrap1(area, n_src);
+  vec u = wrap3(vel, n_tgt);
+  scalar_view_type dd = wrap1(ddot, n_tgt);
+  if (targets_are_sources) {
+    Kokkos::parallel_for(Kokkos::TeamPolicy<>(n_src, Kokkos::AUTO()),
+                         SphereFaceSums(u, dd, fy, fz, fs, fa, fm.v, eps, n_src, do_velocity != 0));
+  } else {
+    crd vx = wrap3(tx, n_tgt);
+    Kokkos::parallel_for(Kokkos::TeamPolicy<>(n_tgt, Kokkos::AUTO()),
+                         SphereVertexSums(u, dd, vx, fy, fz, fs, fa, fm.v, eps, n_src, do_velocity != 0));
+  }
+}
+
+// BVEVorticityTendency over n particles (O(N); used to pin the oracle's stage algebra)
+void ref_bve_vorticity_tendency(int n, double* dzeta, const double* vel, double dt, double Omega) {
+  scalar_view_type dz = wrap1(dzeta, n);
+  vec u = wrap3(vel, n);
+  Kokkos::parallel_for(n, BVEVorticityTendency(dz, u, dt, Omega));
+}
+
+}  // extern "C"

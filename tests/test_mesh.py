@@ -1,0 +1,95 @@
+"""CPU: the host mesh generator (input generator of every config) against
+  * golden fixtures produced by an independent pure-Python restatement run on the reference's own seed files
+    (oracle/mesh_oracle.py, tests/golden/make_mesh_golden.py): EVERY array bit-exact;
+  * the reference's own mesh tests: allocation counts (tests/lpm_polymesh_tests.cpp:76-123), total area 4 pi;
+  * structural invariants of the quad-tree."""
+import os
+
+import numpy as np
+import pytest
+
+from lpm_b200.api import PolyMesh2d, max_allocations
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = [("icos", 0), ("icos", 1), ("icos", 2), ("icos", 3), ("cubed", 0), ("cubed", 1), ("cubed", 2), ("cubed", 3),
+         ("cubed", 4)]
+INT_ARRAYS = ["edge_origs", "edge_dests", "edge_lefts", "edge_rights", "edge_parents", "edge_kids", "face_verts",
+              "face_edges", "face_parent", "face_kids", "face_level", "face_leaf_idx", "face_mask"]
+REAL_ARRAYS = ["vert_xyz", "vert_lag_xyz", "face_xyz", "face_lag_xyz", "face_area"]
+
+
+@pytest.mark.parametrize("seed,depth", CASES)
+def test_mesh_matches_golden_bit_exact(seed, depth):
+    g = np.load(os.path.join(GOLDEN, f"mesh_{seed}_{depth}.npz"))
+    m = PolyMesh2d(seed, depth)
+    for k in INT_ARRAYS:
+        assert np.array_equal(g[k], getattr(m, k)), k
+    for k in REAL_ARRAYS:  # same libm, no FMA contraction on either side: bitwise equality
+        assert np.array_equal(g[k].view(np.int64), getattr(m, k).view(np.int64)), k
+
+
+def test_embedded_seed_tables_equal_reference_dat_files():
+    t = np.load(os.path.join(GOLDEN, "seed_tables.npz"))
+    for seed, nv in (("icos", 12), ("cubed", 8)):
+        m = PolyMesh2d(seed, 0)
+        assert np.array_equal(t[f"{seed}_crds"][:nv], m.vert_xyz)
+        assert np.array_equal(t[f"{seed}_crds"][nv:], m.face_xyz)
+        assert np.array_equal(t[f"{seed}_edges"][:, 0], m.edge_origs)
+        assert np.array_equal(t[f"{seed}_edges"][:, 1], m.edge_dests)
+        assert np.array_equal(t[f"{seed}_edges"][:, 2], m.edge_lefts)
+        assert np.array_equal(t[f"{seed}_edges"][:, 3], m.edge_rights)
+        assert np.array_equal(t[f"{seed}_face_verts"], m.face_verts)
+        assert np.array_equal(t[f"{seed}_face_edges"], m.face_edges)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/mesh_seeds"), reason="reference not mounted")
+def test_live_python_restatement_from_reference_seed_files():
+    from oracle import mesh_oracle
+    for seed, depth in (("icos", 2), ("cubed", 3)):
+        ref = mesh_oracle.TreeMesh(seed, depth).arrays()
+        m = PolyMesh2d(seed, depth)
+        for k, v in ref.items():
+            assert np.array_equal(v, getattr(m, k)), k
+
+
+@pytest.mark.parametrize("seed,depth", [("icos", 3), ("cubed", 3), ("icos", 5), ("cubed", 6)])
+def test_counts_equal_max_allocations_and_area_is_4pi(seed, depth):
+    """tests/lpm_polymesh_tests.cpp:76-123: nh == nmax for all three element kinds; area = 4 pi."""
+    m = PolyMesh2d(seed, depth)
+    assert (m.n_verts, m.n_edges, m.n_faces) == max_allocations(seed, depth)
+    area = 0.0
+    for a in m.face_area:  # sequential, as surface_area_host does
+        area += a
+    assert abs(area - 4 * np.pi) < 31e-14
+    assert m.n_face_leaves == (20 if seed == "icos" else 6) * 4 ** depth
+
+
+@pytest.mark.parametrize("seed,depth", [("icos", 4), ("cubed", 5)])
+def test_tree_invariants(seed, depth):
+    m = PolyMesh2d(seed, depth)
+    leaf = m.face_mask == 0
+    # mask <=> divided <=> area 0; leaves have positive area and level depth+1 (root level 1)
+    assert np.array_equal(~leaf, m.face_kids[:, 0] > 0)
+    assert (m.face_area[~leaf] == 0).all() and (m.face_area[leaf] > 0).all()
+    assert (m.face_level[leaf] == depth + 1).all()
+    # leaf_idx is the exclusive scan of leaf flags
+    assert np.array_equal(m.face_leaf_idx, np.concatenate([[0], np.cumsum(leaf)[:-1]]).astype(np.int32))
+    # kids point back to their parent
+    for k in range(4):
+        kids = m.face_kids[~leaf, k]
+        assert np.array_equal(m.face_parent[kids], np.nonzero(~leaf)[0])
+    # every leaf edge separates two leaf faces that list it
+    eleaf = m.edge_kids[:, 0] <= 0
+    for side in (m.edge_lefts, m.edge_rights):
+        f = side[eleaf]
+        assert leaf[f].all()
+        assert (m.face_edges[f] == np.nonzero(eleaf)[0][:, None]).any(axis=1).all()
+    # Euler characteristic of the leaf mesh: V - E + F = 2
+    assert m.n_verts - eleaf.sum() + leaf.sum() == 2
+    # all particles on the unit sphere
+    assert np.abs(np.linalg.norm(m.vert_xyz, axis=1) - 1).max() < 4e-16
+    assert np.abs(np.linalg.norm(m.face_xyz, axis=1) - 1).max() < 4e-16
+    # face vertices are counter-clockwise seen from outside
+    v = m.vert_xyz[m.face_verts[leaf]]
+    n = np.cross(v[:, 1] - v[:, 0], v[:, 2] - v[:, 1])
+    assert ((n * m.face_xyz[leaf]).sum(axis=1) > 0).all()
