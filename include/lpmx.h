@@ -55,6 +55,7 @@ typedef struct lpmx_handle_s* lpmx_handle_t;
 typedef struct lpmx_mesh_s* lpmx_mesh_t;
 typedef struct lpmx_bve_solver_s* lpmx_bve_solver_t;
 typedef struct lpmx_ic2d_solver_s* lpmx_ic2d_solver_t;
+typedef struct lpmx_swe_solver_s* lpmx_swe_solver_t;
 
 const char* lpmx_version_string(void);
 const char* lpmx_error_name(int code);
@@ -252,6 +253,60 @@ int lpmx_ic2d_solver_get_state(lpmx_ic2d_solver_t s, double* passive_xyz, double
 /* Incompressible2D::init_direct_sums on the resident state */
 int lpmx_ic2d_solver_init_direct_sums(lpmx_ic2d_solver_t s);
 int lpmx_ic2d_solver_advance(lpmx_ic2d_solver_t s, double dt, double Omega, int n_steps);
+
+/* ------------------------------------------------------------------------------------------
+ * Spherical shallow water: SWE<Seed> fields + SWERK2 (src/lpm_swe.hpp:29-88, src/lpm_swe_rk2.hpp:15-39).
+ * ------------------------------------------------------------------------------------------ */
+
+/* The SWE<Seed> fields the stepper reads and writes.  passive = vertices, active = faces.  Array lengths are
+ * n_passive / n_active; xyz and vel are Real*[3] in the call's layout.  (Reference names: mesh.vertices.phys_crds,
+ * rel_vort_passive, div_passive, depth_passive, surf_passive, bottom_passive, velocity_passive,
+ * double_dot_passive, surf_lap_passive; mesh.faces.phys_crds, rel_vort_active, div_active, mesh.faces.area,
+ * mass_active, depth_active, surf_active, bottom_active, velocity_active, double_dot_active, surf_lap_active,
+ * mesh.faces.mask.) */
+typedef struct lpmx_swe_passive_s {
+  double *xyz, *vort, *div, *depth, *surf, *bottom, *vel, *ddot, *laps;
+} lpmx_swe_passive_t;
+typedef struct lpmx_swe_active_s {
+  double *xyz, *vort, *div, *area, *mass, *depth, *surf, *bottom, *vel, *ddot, *laps;
+  const unsigned char* mask;
+} lpmx_swe_active_t;
+
+/* Surface-Laplacian provider.  SWERK2 evaluates the Laplacian of the surface height with Compadre GMLS on a
+ * host kd-tree (src/lpm_swe_rk2_impl.hpp:134-154 for the predictor state = stage 1, :233-252 for the new state =
+ * stage 2); that third-party step is outside this library and is supplied by the caller.  All pointers are DEVICE
+ * pointers; xyz arrays are LPMX_LAYOUT_LEFT with leading dimension xyz_ld.  The provider must fill passive_laps
+ * and active_laps, ordering its work on `cuda_stream` (or synchronising that stream before host access), and
+ * return 0.  A NULL provider leaves the Laplacian arrays as they are (see lpmx_swe_solver_set_laplacian). */
+typedef int (*lpmx_swe_laplacian_fn)(void* user, int stage, void* cuda_stream, int n_passive,
+                                     const double* passive_xyz, const double* passive_surf, double* passive_laps,
+                                     int n_active, const double* active_xyz, const double* active_surf,
+                                     const unsigned char* active_mask, double* active_laps, long xyz_ld);
+
+/* SWERK2<Seed, ZeroFunctor>::advance_timestep_impl (src/lpm_swe_rk2_impl.hpp:80-258) for SphereGeometry, n_steps
+ * times, IN PLACE on the caller's arrays (host or device pointers).  On entry vel, ddot and laps must belong to
+ * the current state (SWE::init_direct_sums, src/lpm_swe_impl.hpp:401-445, and the SWERK2 constructor's Laplacian,
+ * rk2_impl.hpp:56-77); every field of both structs is required except surf/bottom/depth(active)/laps/div, which
+ * default to zero when NULL.  `eps` is the kernel smoothing parameter (never initialised by the reference on
+ * the sphere, SURVEY.md quirk C-iii: pass it explicitly).  Bottom topography is ZeroFunctor. */
+int lpmx_swe_rk2_step(lpmx_handle_t h, double dt, double Omega, double g, double eps, int n_passive,
+                      const lpmx_swe_passive_t* passive, int n_active, const lpmx_swe_active_t* active, int layout,
+                      long passive_ld, long active_ld, lpmx_swe_laplacian_fn laplacian, void* user, int n_steps);
+
+/* Persistent-state variant */
+int lpmx_swe_solver_create(lpmx_handle_t h, int n_passive, int n_active, double eps, lpmx_swe_solver_t* s);
+int lpmx_swe_solver_destroy(lpmx_swe_solver_t s);
+int lpmx_swe_solver_set_state(lpmx_swe_solver_t s, const lpmx_swe_passive_t* passive, const lpmx_swe_active_t* active,
+                              int layout, long passive_ld, long active_ld);
+/* any pointer inside the structs may be NULL (= not wanted) */
+int lpmx_swe_solver_get_state(lpmx_swe_solver_t s, const lpmx_swe_passive_t* passive, const lpmx_swe_active_t* active,
+                              int layout, long passive_ld, long active_ld);
+/* overwrite the resident surface-Laplacian arrays (host or device pointers; either may be NULL) */
+int lpmx_swe_solver_set_laplacian(lpmx_swe_solver_t s, const double* passive_laps, const double* active_laps);
+/* SWE::init_direct_sums(do_velocity) on the resident state (physical == Lagrangian coordinates at t = 0) */
+int lpmx_swe_solver_init_direct_sums(lpmx_swe_solver_t s, int do_velocity);
+int lpmx_swe_solver_advance(lpmx_swe_solver_t s, double dt, double Omega, double g, lpmx_swe_laplacian_fn laplacian,
+                            void* user, int n_steps);
 
 #ifdef __cplusplus
 }

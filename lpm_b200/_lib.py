@@ -22,6 +22,23 @@ LAYOUT_RIGHT, LAYOUT_LEFT = 0, 1
 SEED_ICOS_TRI_SPHERE, SEED_CUBED_SPHERE = 0, 1
 
 
+class SwePassive(ctypes.Structure):
+    """lpmx_swe_passive_t"""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("xyz", "vort", "div", "depth", "surf", "bottom", "vel", "ddot", "laps")]
+
+
+class SweActive(ctypes.Structure):
+    """lpmx_swe_active_t"""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("xyz", "vort", "div", "area", "mass", "depth", "surf", "bottom", "vel",
+                                               "ddot", "laps", "mask")]
+
+
+# lpmx_swe_laplacian_fn
+SWE_LAPLACIAN_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long)
+
+
 class LpmxError(RuntimeError):
     def __init__(self, code, where, detail=""):
         self.code = code
@@ -93,6 +110,15 @@ def _declare(L):
         "lpmx_ic2d_solver_get_state": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, l, l],
         "lpmx_ic2d_solver_init_direct_sums": [vp],
         "lpmx_ic2d_solver_advance": [vp, d, d, i],
+        "lpmx_swe_rk2_step": [vp, d, d, d, d, i, ctypes.POINTER(SwePassive), i, ctypes.POINTER(SweActive), i, l, l,
+                              SWE_LAPLACIAN_FN, vp, i],
+        "lpmx_swe_solver_create": [vp, i, i, d, ctypes.POINTER(vp)],
+        "lpmx_swe_solver_destroy": [vp],
+        "lpmx_swe_solver_set_state": [vp, ctypes.POINTER(SwePassive), ctypes.POINTER(SweActive), i, l, l],
+        "lpmx_swe_solver_get_state": [vp, ctypes.POINTER(SwePassive), ctypes.POINTER(SweActive), i, l, l],
+        "lpmx_swe_solver_set_laplacian": [vp, vp, vp],
+        "lpmx_swe_solver_init_direct_sums": [vp, i],
+        "lpmx_swe_solver_advance": [vp, d, d, d, SWE_LAPLACIAN_FN, vp, i],
     }
     for name, args in sig.items():
         f = getattr(L, name)

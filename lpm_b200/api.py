@@ -402,3 +402,96 @@ class IC2DSolver:
     def advance(self, dt, Omega, n_steps=1):
         self.e._check(self.e._L.lpmx_ic2d_solver_advance(self._s, float(dt), float(Omega), n_steps),
                       "lpmx_ic2d_solver_advance")
+
+
+PASSIVE_FIELDS = ("xyz", "vort", "div", "depth", "surf", "bottom", "vel", "ddot", "laps")
+ACTIVE_FIELDS = ("xyz", "vort", "div", "area", "mass", "depth", "surf", "bottom", "vel", "ddot", "laps")
+
+
+def _swe_structs(passive, active, mask):
+    """dicts of arrays (missing / None = NULL) -> (lpmx_swe_passive_t, lpmx_swe_active_t, keep-alive list)."""
+    P, A = _lib.SwePassive(), _lib.SweActive()
+    for k in PASSIVE_FIELDS:
+        a = passive.get(k)
+        setattr(P, k, None if a is None else _ptr(a))
+    for k in ACTIVE_FIELDS:
+        a = active.get(k)
+        setattr(A, k, None if a is None else _ptr(a))
+    A.mask = None if mask is None else _ptr(mask)
+    return P, A
+
+
+def _laplacian_cb(fn):
+    """Wrap a Python callable fn(stage, stream, n_passive, passive_xyz_ptr, passive_surf_ptr, passive_laps_ptr,
+    n_active, active_xyz_ptr, active_surf_ptr, active_mask_ptr, active_laps_ptr, xyz_ld) -> None (device pointers
+    as ints) into an lpmx_swe_laplacian_fn; None -> NULL provider."""
+    if fn is None:
+        return ctypes.cast(None, _lib.SWE_LAPLACIAN_FN)
+
+    def cb(user, stage, stream, n_p, pxyz, psurf, plaps, n_a, axyz, asurf, amask, alaps, ld):
+        try:
+            fn(stage, stream, n_p, pxyz, psurf, plaps, n_a, axyz, asurf, amask, alaps, ld)
+            return 0
+        except Exception:  # a Python exception must not unwind through C
+            import traceback
+            traceback.print_exc()
+            return 1
+    return _lib.SWE_LAPLACIAN_FN(cb)
+
+
+def swe_rk2_step(engine, dt, Omega, g, eps, passive, active, mask, laplacian=None, n_steps=1, layout=LAYOUT_RIGHT):
+    """SWERK2::advance_timestep_impl, n_steps times, in place on the arrays in the dicts `passive` / `active`
+    (keys PASSIVE_FIELDS / ACTIVE_FIELDS; float64, C-contiguous) -- lpmx_swe_rk2_step."""
+    nv = passive["xyz"].shape[0] if layout == LAYOUT_RIGHT else passive["xyz"].shape[1]
+    nf = active["xyz"].shape[0] if layout == LAYOUT_RIGHT else active["xyz"].shape[1]
+    P, A = _swe_structs(passive, active, mask)
+    cb = _laplacian_cb(laplacian)
+    engine._check(engine._L.lpmx_swe_rk2_step(engine._h, float(dt), float(Omega), float(g), float(eps), nv,
+                                              ctypes.byref(P), nf, ctypes.byref(A), layout, nv, nf, cb, None, n_steps),
+                  "lpmx_swe_rk2_step")
+
+
+class SWESolver:
+    """Device-resident SWE<Seed> fields + SWERK2 (lpmx_swe_solver_*)."""
+
+    def __init__(self, engine, n_passive, n_active, eps=0.0):
+        self.e = engine
+        self.np_, self.na = n_passive, n_active
+        s = ctypes.c_void_p()
+        engine._check(engine._L.lpmx_swe_solver_create(engine._h, n_passive, n_active, float(eps), ctypes.byref(s)),
+                      "lpmx_swe_solver_create")
+        self._s = s
+
+    def close(self):
+        if getattr(self, "_s", None) and getattr(self.e, "_h", None):
+            self.e._L.lpmx_swe_solver_destroy(self._s)
+        self._s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_state(self, passive, active, mask, layout=LAYOUT_RIGHT):
+        P, A = _swe_structs(passive, active, mask)
+        self.e._check(self.e._L.lpmx_swe_solver_set_state(self._s, ctypes.byref(P), ctypes.byref(A), layout, self.np_,
+                                                          self.na), "lpmx_swe_solver_set_state")
+
+    def get_state(self, passive, active, layout=LAYOUT_RIGHT):
+        P, A = _swe_structs(passive, active, None)
+        self.e._check(self.e._L.lpmx_swe_solver_get_state(self._s, ctypes.byref(P), ctypes.byref(A), layout, self.np_,
+                                                          self.na), "lpmx_swe_solver_get_state")
+
+    def set_laplacian(self, passive_laps, active_laps):
+        self.e._check(self.e._L.lpmx_swe_solver_set_laplacian(self._s, _ptr(passive_laps), _ptr(active_laps)),
+                      "lpmx_swe_solver_set_laplacian")
+
+    def init_direct_sums(self, do_velocity=True):
+        self.e._check(self.e._L.lpmx_swe_solver_init_direct_sums(self._s, int(bool(do_velocity))),
+                      "lpmx_swe_solver_init_direct_sums")
+
+    def advance(self, dt, Omega, g, laplacian=None, n_steps=1):
+        cb = _laplacian_cb(laplacian)
+        self.e._check(self.e._L.lpmx_swe_solver_advance(self._s, float(dt), float(Omega), float(g), cb, None, n_steps),
+                      "lpmx_swe_solver_advance")

@@ -172,6 +172,7 @@ int lpmx_create(lpmx_handle_t* out, int device_id) {
 
 int lpmx_bve_solver_destroy(lpmx_bve_solver_t s);
 int lpmx_ic2d_solver_destroy(lpmx_ic2d_solver_t s);
+int lpmx_swe_solver_destroy(lpmx_swe_solver_t s);
 
 int lpmx_destroy(lpmx_handle_t h) {
   if (!h) return LPMX_OK;
@@ -179,6 +180,7 @@ int lpmx_destroy(lpmx_handle_t h) {
   cudaStreamSynchronize(h->stream);
   if (h->cached_bve) lpmx_bve_solver_destroy(h->cached_bve);
   if (h->cached_ic2d) lpmx_ic2d_solver_destroy(h->cached_ic2d);
+  if (h->cached_swe) lpmx_swe_solver_destroy(h->cached_swe);
   for (auto& kv : h->bufs)
     if (kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : h->pinned)

@@ -64,5 +64,31 @@ __device__ __forceinline__ void cross3(double* c, const double* a, const double*
   c[2] = a[0] * b[1] - a[1] * b[0];
 }
 
+// SWE finalize (SphereVertexSums::operator(), lpm_swe_kernels.hpp:756-779 on the factored accumulators of
+// Pair<kSwe>): u = x cross Mz + P_x Ms ;  G_total = G + [Mz]x - (x.Ms) P_x ;  ddot = sum_ab G_ab G_ba.
+// acc[0..2] = Mz, acc[3..5] = Ms, acc[6..14] = G (row-major).  g9 receives G_total.
+__device__ __forceinline__ double swe_finalize(const double* acc, const double* x, double* u, double* g9) {
+  const double* mz = acc;
+  const double* ms = acc + 3;
+  const double xms = x[0] * ms[0] + x[1] * ms[1] + x[2] * ms[2];
+  cross3(u, x, mz);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) u[k] = u[k] + (ms[k] - xms * x[k]);
+  const double mzx[9] = {0, -mz[2], mz[1], mz[2], 0, -mz[0], -mz[1], mz[0], 0};
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const double P = (a == b ? 1.0 : 0.0) - x[a] * x[b];
+      g9[3 * a + b] = acc[6 + 3 * a + b] + mzx[3 * a + b] - xms * P;
+    }
+  double dd = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) dd += g9[3 * a + b] * g9[3 * b + a];
+  return dd;
+}
+
 }  // namespace lpmx
 #endif

@@ -96,6 +96,7 @@ struct lpmx_handle_s {
   // cached one-shot solvers for the in-place stepper entry points
   lpmx_bve_solver_t cached_bve = nullptr;
   lpmx_ic2d_solver_t cached_ic2d = nullptr;
+  lpmx_swe_solver_t cached_swe = nullptr;
 };
 
 namespace lpmx {

@@ -6,6 +6,10 @@
 
 #include "lpmx_internal.h"
 
+#ifndef LPMX_SEED_LO
+#define LPMX_SEED_LO 0
+#endif
+
 namespace lpmx {
 
 // ------------------------------------------------------------------------------------------------
@@ -49,6 +53,22 @@ __device__ __forceinline__ double rcp_seed(double d) {
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
   return r;
 }
+// Same seed, but the low word is taken from `dead` (a value the caller no longer needs) instead of being
+// zeroed: MUFU.RCP64H writes only the high word, so ptxas can drop the MOV that zeroes the low one by placing
+// the seed in `dead`'s register pair.  The low word perturbs the seed by < 2^-20 relative, which the cubic
+// Newton step absorbs (|e| < 2^-19 -> |e|^3 < 2^-57).
+__device__ __forceinline__ double rcp_seed_lo(double d, double dead) {
+  double r;
+  asm("{\n"
+      ".reg .f64 t;\n"
+      ".reg .b32 lo, hi, glo, ghi;\n"
+      "rcp.approx.ftz.f64 t, %1;\n"
+      "mov.b64 {lo, hi}, t;\n"
+      "mov.b64 {glo, ghi}, %2;\n"
+      "mov.b64 %0, {glo, hi};\n"
+      "}" : "=d"(r) : "d"(d), "d"(dead));
+  return r;
+}
 
 // ------------------------------------------------------------------------------------------------
 // kernel arguments
@@ -79,13 +99,20 @@ struct Pair;
 template <bool CHECK>
 struct Pair<kVel, CHECK> {
   static constexpr int NLOAD = 6;  // doubles of the record this kind reads
+  // `car` carries a dead value (the previous pair's r of this accumulator slot) whose register pair hosts the
+  // next reciprocal seed (see rcp_seed_lo).
   __device__ __forceinline__ static void apply(const double* x, const double* /*kx*/, double kappa, const double* s,
-                                               int j, int self, double* acc) {
+                                               int j, int self, double* acc, double& car) {
     const double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
+#if LPMX_SEED_LO
+    const double r0 = rcp_seed_lo(d, car);
+#else
     const double r0 = rcp_seed(d);
+#endif
     const double e = fma(-d, r0, 1.0);
     const double p = fma(e, e, e);
     double r = fma(r0, p, r0);
+    car = r;
     if (CHECK) r = (j == self) ? 0.0 : r;
     acc[0] = fma(r, s[3], acc[0]);
     acc[1] = fma(r, s[4], acc[1]);
@@ -97,7 +124,7 @@ template <bool CHECK>
 struct Pair<kVelPsi, CHECK> {
   static constexpr int NLOAD = 8;
   __device__ __forceinline__ static void apply(const double* x, const double*, double kappa, const double* s, int j,
-                                               int self, double* acc) {
+                                               int self, double* acc, double& /*car*/) {
     double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
     double gam = s[6];
     if (CHECK) {
@@ -121,7 +148,7 @@ template <bool CHECK>
 struct Pair<kPsi, CHECK> {
   static constexpr int NLOAD = 8;
   __device__ __forceinline__ static void apply(const double* x, const double*, double kappa, const double* s, int j,
-                                               int self, double* acc) {
+                                               int self, double* acc, double& /*car*/) {
     double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
     double gam = s[6];
     if (CHECK) {
@@ -141,7 +168,7 @@ template <bool CHECK>
 struct Pair<kSwe, CHECK> {
   static constexpr int NLOAD = 6;
   __device__ __forceinline__ static void apply(const double* x, const double* kx, double kappa, const double* s,
-                                               int j, int self, double* acc) {
+                                               int j, int self, double* acc, double& /*car*/) {
     double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
     double gz = s[3], gs = s[4];
     if (CHECK) {
@@ -190,19 +217,29 @@ __device__ __forceinline__ void chunk_loop(const double (*x)[3], const double (*
                                            const double* __restrict__ sp, int j0, const int* self,
                                            double (*acc)[kind_nacc(KIND)]) {
   constexpr int REC = kind_rec(KIND);
-#pragma unroll UNROLL
-  for (int j = 0; j < kChunk; ++j) {
-    constexpr int NLOAD = Pair<KIND, CHECK>::NLOAD;
-    double s[NLOAD];
-    const double2* s2 = reinterpret_cast<const double2*>(sp + (size_t)j * REC);
+  static_assert(kChunk % UNROLL == 0, "source-loop unroll must divide the chunk");
+  double car[UNROLL][T];
 #pragma unroll
-    for (int v = 0; v < NLOAD / 2; ++v) {
-      const double2 t = s2[v];
-      s[2 * v] = t.x;
-      s[2 * v + 1] = t.y;
+  for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+    for (int t = 0; t < T; ++t) car[u][t] = 0.0;
+#pragma unroll 1
+  for (int jj = 0; jj < kChunk; jj += UNROLL) {
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int j = jj + u;
+      constexpr int NLOAD = Pair<KIND, CHECK>::NLOAD;
+      double s[NLOAD];
+      const double2* s2 = reinterpret_cast<const double2*>(sp + (size_t)j * REC);
+#pragma unroll
+      for (int v = 0; v < NLOAD / 2; ++v) {
+        const double2 t = s2[v];
+        s[2 * v] = t.x;
+        s[2 * v + 1] = t.y;
+      }
+#pragma unroll
+      for (int t = 0; t < T; ++t) Pair<KIND, CHECK>::apply(x[t], kx[t], kappa, s, j0 + j, self[t], acc[t], car[u][t]);
     }
-#pragma unroll
-    for (int t = 0; t < T; ++t) Pair<KIND, CHECK>::apply(x[t], kx[t], kappa, s, j0 + j, self[t], acc[t]);
   }
 }
 

@@ -79,24 +79,10 @@ __global__ void fin_swe_kernel(PartView pv, int n_tgt, Vec3View tx, int do_veloc
   double acc[15];
   reduce_slots<15>(pv, i, acc);
   const double x[3] = {tx(i, 0), tx(i, 1), tx(i, 2)};
-  const double* mz = acc;
-  const double* ms = acc + 3;
-  const double xms = x[0] * ms[0] + x[1] * ms[1] + x[2] * ms[2];
-  if (do_velocity && out_vel.p) {
-    double u[3];
-    cross3(u, x, mz);
-    for (int k = 0; k < 3; ++k) out_vel(i, k) = u[k] + (ms[k] - xms * x[k]);
-  }
-  double g[9];
-  const double mzx[9] = {0, -mz[2], mz[1], mz[2], 0, -mz[0], -mz[1], mz[0], 0};
-  for (int a = 0; a < 3; ++a)
-    for (int b = 0; b < 3; ++b) {
-      const double P = (a == b ? 1.0 : 0.0) - x[a] * x[b];
-      g[3 * a + b] = acc[6 + 3 * a + b] + mzx[3 * a + b] - xms * P;
-    }
-  double dd = 0;
-  for (int a = 0; a < 3; ++a)
-    for (int b = 0; b < 3; ++b) dd += g[3 * a + b] * g[3 * b + a];
+  double u[3], g[9];
+  const double dd = swe_finalize(acc, x, u, g);
+  if (do_velocity && out_vel.p)
+    for (int k = 0; k < 3; ++k) out_vel(i, k) = u[k];
   out_ddot[i] = dd;
   if (out_grad)
     for (int k = 0; k < 9; ++k) out_grad[9L * i + k] = g[k];

@@ -400,3 +400,120 @@ void oracle_swe_sphere_sums(int n_tgt, const double* tx, int n_src, const double
       for (int k = 0; k < 9; ++k) grad9[9L * i + k] = s[3 + k];
   }
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Family C stepper: SWERK2 on the sphere (direct sums + O(N) algebra; the GMLS surface Laplacian
+ * is an external input, supplied through `laps_fn`)
+ * ------------------------------------------------------------------------------------------- */
+
+/* CoriolisSphere (lpm_coriolis.hpp:154-195) */
+static inline double cor_f(double Omega, const double* x) { return 2 * Omega * x[2]; }
+static inline double cor_dfdt(double Omega, const double* u) { return 2 * Omega * u[2]; }
+static inline double cor_grad_f_cross_u(double Omega, const double* x, const double* u) {
+  return -2 * Omega * (-u[0] * x[1] + u[1] * x[0]);
+}
+
+/* SWEVorticityDivergenceHeightTendencies<SphereGeometry> (lpm_swe_kernels.hpp:941-999) when
+ * is_area == 0 (third output dh = -sigma*h*dt, third input h = depth) and
+ * SWEVorticityDivergenceAreaTendencies<SphereGeometry> (:1010-1069) when is_area != 0 (third
+ * output darea = sigma*area*dt, third input = area). */
+void oracle_swe_tendencies(int n, int is_area, double* dzeta, double* dsigma, double* dthird, const double* x,
+                           const double* u, const double* zeta, const double* sigma, const double* third,
+                           const double* ddot, const double* laps, double Omega, double g, double dt) {
+  for (int i = 0; i < n; ++i) {
+    const double* xi = x + 3 * i;
+    const double* ui = u + 3 * i;
+    const double f = cor_f(Omega, xi);
+    dzeta[i] = (-cor_dfdt(Omega, ui) - (zeta[i] + f) * sigma[i]) * dt;
+    dsigma[i] = (f * zeta[i] + cor_grad_f_cross_u(Omega, xi, ui) - ddot[i] - g * laps[i] - dot3(ui, ui)) * dt;
+    dthird[i] = is_area ? (sigma[i] * third[i]) * dt : (-sigma[i] * third[i]) * dt;
+  }
+}
+
+/* SetSurfaceFromDepth<SphereGeometry, ZeroFunctor> (:1079-1100): b = topo(x) = 0, s = h + b.
+ * (The constructor never copies `topo`, quirk C-v: the functor is default-constructed.) */
+void oracle_swe_set_surface_from_depth(int n, double* s, double* b, const double* h) {
+  for (int i = 0; i < n; ++i) {
+    b[i] = 0.0;
+    s[i] = h[i] + b[i];
+  }
+}
+
+/* SetDepthAndSurfaceFromMassAndArea<SphereGeometry, ZeroFunctor> (:1110-1140): unmasked faces only */
+void oracle_swe_set_depth_surface_from_mass_area(int n, double* h, double* s, double* b, const double* m,
+                                                 const double* area, const uint8_t* mask) {
+  for (int i = 0; i < n; ++i) {
+    if (!mask[i]) {
+      h[i] = m[i] / area[i];
+      b[i] = 0.0;
+      s[i] = b[i] + h[i];
+    }
+  }
+}
+
+/* The surface-Laplacian provider: fills plaps[np] and alaps[na] for the particle positions and surface
+ * heights it is given.  stage 1 = predictor state (lpm_swe_rk2_impl.hpp:134-154), stage 2 = new state
+ * (:233-252).  NULL = leave the arrays as they are. */
+typedef void (*oracle_laps_fn)(void* user, int stage, int np, const double* px, const double* psurf, double* plaps,
+                               int na, const double* ax, const double* asurf, const uint8_t* amask, double* alaps);
+
+/* SWERK2<Seed, ZeroFunctor>::advance_timestep_impl (lpm_swe_rk2_impl.hpp:80-258) for SphereGeometry,
+ * n_steps times, in place.  p* = passive (vertices), a* = active (faces).  On entry velocity, double dot and
+ * surface Laplacian must belong to the current state (SWE::init_direct_sums + the SWERK2 constructor,
+ * :56-77). */
+void oracle_swe_rk2_step(double dt, double Omega, double g, double eps, int np, double* px, double* pz, double* ps,
+                         double* ph, double* psurf, double* pbot, double* pu, double* pdd, double* plaps, int na,
+                         double* ax, double* az, double* as, double* aarea, double* amass, double* ah, double* asurf,
+                         double* abot, double* au, double* add, double* alaps, const uint8_t* am,
+                         oracle_laps_fn laps_fn, void* user, int n_steps) {
+  double* w = (double*)calloc((size_t)18 * (np + na), sizeof(double));
+  double *px1 = w, *px2 = px1 + 3L * np, *pxw = px2 + 3L * np;
+  double *pz1 = pxw + 3L * np, *pz2 = pz1 + np, *pzw = pz2 + np;
+  double *ps1 = pzw + np, *ps2 = ps1 + np, *psw = ps2 + np;
+  double *ph1 = psw + np, *ph2 = ph1 + np, *phw = ph2 + np;
+  double *ax1 = phw + np, *ax2 = ax1 + 3L * na, *axw = ax2 + 3L * na;
+  double *az1 = axw + 3L * na, *az2 = az1 + na, *azw = az2 + na;
+  double *as1 = azw + na, *as2 = as1 + na, *asw = as2 + na;
+  double *aa1 = asw + na, *aa2 = aa1 + na, *aaw = aa2 + na;
+  for (int s = 0; s < n_steps; ++s) {
+    /* stage 1 (:85-104) */
+    blas_scal(3L * np, px1, dt, pu);
+    blas_scal(3L * na, ax1, dt, au);
+    oracle_swe_tendencies(np, 0, pz1, ps1, ph1, px, pu, pz, ps, ph, pdd, plaps, Omega, g, dt);
+    oracle_swe_tendencies(na, 1, az1, as1, aa1, ax, au, az, as, aarea, add, alaps, Omega, g, dt);
+    /* predictor state (:108-123) */
+    blas_update(3L * np, 1, px, 1, px1, 0, pxw);
+    blas_update(np, 1, pz, 1, pz1, 0, pzw);
+    blas_update(np, 1, ps, 1, ps1, 0, psw);
+    blas_update(3L * na, 1, ax, 1, ax1, 0, axw);
+    blas_update(na, 1, az, 1, az1, 0, azw);
+    blas_update(na, 1, as, 1, as1, 0, asw);
+    blas_update(np, 1, ph, 1, ph1, 0, phw);
+    blas_update(na, 1, aarea, 1, aa1, 0, aaw);
+    oracle_swe_set_surface_from_depth(np, psurf, pbot, phw);                              /* :124-127 */
+    oracle_swe_set_depth_surface_from_mass_area(na, ah, asurf, abot, amass, aaw, am);     /* :128-132 */
+    if (laps_fn) laps_fn(user, 1, np, pxw, psurf, plaps, na, axw, asurf, am, alaps);      /* :134-154 */
+    oracle_swe_sphere_sums(np, pxw, na, axw, azw, asw, aaw, am, eps, 0, 1, pu, pdd, NULL); /* :157-168 */
+    oracle_swe_sphere_sums(na, NULL, na, axw, azw, asw, aaw, am, eps, 1, 1, au, add, NULL);
+    /* stage 2 tendencies at the predictor state (:170-185) */
+    oracle_swe_tendencies(np, 0, pz2, ps2, ph2, pxw, pu, pzw, psw, phw, pdd, plaps, Omega, g, dt);
+    oracle_swe_tendencies(na, 1, az2, as2, aa2, axw, au, azw, asw, aaw, add, alaps, Omega, g, dt);
+    blas_scal(3L * np, px2, dt, pu); /* :187-188 */
+    blas_scal(3L * na, ax2, dt, au);
+    /* Heun combine (:190-205) */
+    blas_update(3L * np, 0.5, px1, 0.5, px2, 1, px);
+    blas_update(np, 0.5, pz1, 0.5, pz2, 1, pz);
+    blas_update(np, 0.5, ps1, 0.5, ps2, 1, ps);
+    blas_update(np, 0.5, ph1, 0.5, ph2, 1, ph);
+    blas_update(3L * na, 0.5, ax1, 0.5, ax2, 1, ax);
+    blas_update(na, 0.5, az1, 0.5, az2, 1, az);
+    blas_update(na, 0.5, as1, 0.5, as2, 1, as);
+    blas_update(na, 0.5, aa1, 0.5, aa2, 1, aarea);
+    oracle_swe_set_surface_from_depth(np, psurf, pbot, ph);                               /* :207-211 */
+    oracle_swe_set_depth_surface_from_mass_area(na, ah, asurf, abot, amass, aarea, am);   /* :212-216 */
+    oracle_swe_sphere_sums(np, px, na, ax, az, as, aarea, am, eps, 0, 1, pu, pdd, NULL);  /* :218-231 */
+    oracle_swe_sphere_sums(na, NULL, na, ax, az, as, aarea, am, eps, 1, 1, au, add, NULL);
+    if (laps_fn) laps_fn(user, 2, np, px, psurf, plaps, na, ax, asurf, am, alaps);        /* :233-252 */
+  }
+  free(w);
+}

@@ -138,3 +138,59 @@ def swe_sphere_sums(tgt_xyz, src_xyz, vort, div, area, mask, eps=0.0, targets_ar
                              _p(area), mp, ctypes.c_double(eps), ctypes.c_int(int(targets_are_sources)),
                              ctypes.c_int(int(do_velocity)), _p(vel), _p(ddot), _p(grad))
     return vel, ddot, grad
+
+
+# ---- SWE RK2 (family C stepper) ---------------------------------------------------------------------
+LAPS_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _dp, _dp, _dp, ctypes.c_int, _dp, _dp,
+                           _up, _dp)
+
+
+def swe_tendencies(is_area, x, u, zeta, sigma, third, ddot, laps, Omega, g, dt, L=None):
+    """SWEVorticityDivergence{Height,Area}Tendencies<SphereGeometry>: returns (dzeta, dsigma, dh | darea)."""
+    L = L or lib()
+    x, u, zeta, sigma, third, ddot, laps = map(_d, (x, u, zeta, sigma, third, ddot, laps))
+    n = x.shape[0]
+    dz, ds, d3 = np.zeros(n), np.zeros(n), np.zeros(n)
+    L.oracle_swe_tendencies(ctypes.c_int(n), ctypes.c_int(int(is_area)), _p(dz), _p(ds), _p(d3), _p(x), _p(u),
+                            _p(zeta), _p(sigma), _p(third), _p(ddot), _p(laps), ctypes.c_double(Omega),
+                            ctypes.c_double(g), ctypes.c_double(dt))
+    return dz, ds, d3
+
+
+class SWEState:
+    """The SWE<Seed> fields the stepper touches, as float64 C-contiguous numpy arrays (src/lpm_swe.hpp:29-88)."""
+    PASSIVE = ("xyz", "vort", "div", "depth", "surf", "bottom", "vel", "ddot", "laps")
+    ACTIVE = ("xyz", "vort", "div", "area", "mass", "depth", "surf", "bottom", "vel", "ddot", "laps")
+
+    def __init__(self, passive, active, mask):
+        self.p = {k: np.ascontiguousarray(passive[k], dtype=np.float64).copy() for k in self.PASSIVE}
+        self.a = {k: np.ascontiguousarray(active[k], dtype=np.float64).copy() for k in self.ACTIVE}
+        self.mask = np.ascontiguousarray(mask, dtype=np.uint8).copy()
+
+    def copy(self):
+        return SWEState(self.p, self.a, self.mask)
+
+
+def swe_rk2_step(dt, Omega, g, eps, st, laps_fn=None, n_steps=1, L=None):
+    """SWERK2::advance_timestep_impl on the sphere, in place on `st` (SWEState).  laps_fn(stage, px, psurf, ax,
+    asurf, amask) -> (plaps, alaps) stands in for the GMLS Laplacian; None leaves st.*['laps'] unchanged."""
+    L = L or lib()
+    p, a = st.p, st.a
+    np_, na = p["xyz"].shape[0], a["xyz"].shape[0]
+
+    def cb(user, stage, n_p, px, psurf, plaps, n_a, ax, asurf, amask, alaps):
+        pxv = np.ctypeslib.as_array(px, shape=(n_p, 3))
+        axv = np.ctypeslib.as_array(ax, shape=(n_a, 3))
+        pl, al = laps_fn(stage, pxv, np.ctypeslib.as_array(psurf, shape=(n_p,)), axv,
+                         np.ctypeslib.as_array(asurf, shape=(n_a,)), np.ctypeslib.as_array(amask, shape=(n_a,)))
+        np.ctypeslib.as_array(plaps, shape=(n_p,))[:] = pl
+        np.ctypeslib.as_array(alaps, shape=(n_a,))[:] = al
+
+    fn = LAPS_FN(cb) if laps_fn is not None else ctypes.cast(None, LAPS_FN)
+    L.oracle_swe_rk2_step(ctypes.c_double(dt), ctypes.c_double(Omega), ctypes.c_double(g), ctypes.c_double(eps),
+                          ctypes.c_int(np_), _p(p["xyz"]), _p(p["vort"]), _p(p["div"]), _p(p["depth"]), _p(p["surf"]),
+                          _p(p["bottom"]), _p(p["vel"]), _p(p["ddot"]), _p(p["laps"]), ctypes.c_int(na),
+                          _p(a["xyz"]), _p(a["vort"]), _p(a["div"]), _p(a["area"]), _p(a["mass"]), _p(a["depth"]),
+                          _p(a["surf"]), _p(a["bottom"]), _p(a["vel"]), _p(a["ddot"]), _p(a["laps"]),
+                          st.mask.ctypes.data_as(_up), fn, None, ctypes.c_int(n_steps))
+    return st

@@ -21,6 +21,7 @@
 #include "lpm_bve_sphere_kernels.hpp"
 #include "lpm_incompressible2d_kernels.hpp"
 #include "lpm_swe_kernels.hpp"
+#include "lpm_surface_gallery.hpp"
 
 using namespace Lpm;
 using crd = SphereGeometry::crd_view_type;
@@ -132,6 +133,41 @@ void oracle_swe_sphere_sums(int n_tgt, const double* tx, int n_src, const double
     Kokkos::parallel_for(Kokkos::TeamPolicy<>(n_tgt, Kokkos::AUTO()),
                          SphereVertexSums(u, dd, vx, fy, fz, fs, fa, fm.v, eps, n_src, do_velocity != 0));
   }
+}
+
+// SWEVorticityDivergenceHeightTendencies / ...AreaTendencies <SphereGeometry>, CoriolisSphere(Omega)
+void oracle_swe_tendencies(int n, int is_area, double* dzeta, double* dsigma, double* dthird, const double* x,
+                           const double* u, const double* zeta, const double* sigma, const double* third,
+                           const double* ddot, const double* laps, double Omega, double g, double dt) {
+  scalar_view_type dz = wrap1(dzeta, n), ds = wrap1(dsigma, n), d3 = wrap1(dthird, n);
+  crd xv = wrap3(x, n);
+  vec uv = wrap3(u, n);
+  CoriolisSphere cor(Omega);
+  if (is_area) {
+    Kokkos::parallel_for(n, SWEVorticityDivergenceAreaTendencies<SphereGeometry>(
+                                dz, ds, d3, xv, uv, wrap1(zeta, n), wrap1(sigma, n), wrap1(third, n), wrap1(ddot, n),
+                                wrap1(laps, n), cor, g, dt));
+  } else {
+    Kokkos::parallel_for(n, SWEVorticityDivergenceHeightTendencies<SphereGeometry>(
+                                dz, ds, d3, xv, uv, wrap1(zeta, n), wrap1(sigma, n), wrap1(third, n), wrap1(ddot, n),
+                                wrap1(laps, n), cor, g, dt));
+  }
+}
+
+// SetSurfaceFromDepth<SphereGeometry, ZeroFunctor>; x is not needed by ZeroFunctor but the functor reads it
+void ref_swe_set_surface_from_depth(int n, double* s, double* b, const double* x, const double* h) {
+  scalar_view_type sv = wrap1(s, n), bv = wrap1(b, n);
+  Kokkos::parallel_for(n, SetSurfaceFromDepth<SphereGeometry, ZeroFunctor>(sv, bv, wrap3(x, n), wrap1(h, n),
+                                                                            ZeroFunctor()));
+}
+
+// SetDepthAndSurfaceFromMassAndArea<SphereGeometry, ZeroFunctor>
+void ref_swe_set_depth_surface_from_mass_area(int n, double* h, double* s, double* b, const double* x,
+                                              const double* m, const double* area, const uint8_t* mask) {
+  Mask fm(mask, n);
+  scalar_view_type hv = wrap1(h, n), sv = wrap1(s, n), bv = wrap1(b, n);
+  Kokkos::parallel_for(n, SetDepthAndSurfaceFromMassAndArea<SphereGeometry, ZeroFunctor>(
+                              hv, sv, bv, wrap3(x, n), wrap1(m, n), wrap1(area, n), fm.v, ZeroFunctor()));
 }
 
 // BVEVorticityTendency over n particles (O(N); used to pin the oracle's stage algebra)

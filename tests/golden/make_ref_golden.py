@@ -45,6 +45,20 @@ if __name__ == "__main__":
             _, dd, _ = O.swe_sphere_sums(None, m.face_xyz, fz, sig, m.face_area, m.face_mask, eps=eps,
                                          targets_are_sources=True, L=R)
             out[k + e + "swe_ddot_faces"] = dd
+    # O(N) SWE functors (tendencies) on seeded random particle data
+    rng = np.random.default_rng(20261018)
+    n = 257
+    x = rng.standard_normal((n, 3))
+    x /= np.linalg.norm(x, axis=1)[:, None]
+    x *= 1 + 1e-3 * rng.standard_normal((n, 1))
+    tin = {"x": x, "u": rng.standard_normal((n, 3)), "zeta": rng.standard_normal(n), "sigma": rng.standard_normal(n),
+           "third": 1 + rng.random(n), "ddot": rng.standard_normal(n), "laps": rng.standard_normal(n)}
+    for k2, v in tin.items():
+        out["tend_in_" + k2] = v
+    for is_area in (0, 1):
+        dz, ds, d3 = O.swe_tendencies(is_area, tin["x"], tin["u"], tin["zeta"], tin["sigma"], tin["third"], tin["ddot"],
+                                      tin["laps"], Omega=2 * np.pi, g=1.5, dt=0.0125, L=R)
+        out[f"tend_out_{is_area}"] = np.stack([dz, ds, d3])
     # pair-level values of the reference functions on random pairs, on and off the unit sphere
     rng = np.random.default_rng(20261017)
     xs, ys, epss, vals = [], [], [], []

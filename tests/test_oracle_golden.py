@@ -134,6 +134,51 @@ def test_sums_match_live_reference_build(oracle):
     _compare(_sum_cases(oracle), _sum_cases(oracle, L=R))
 
 
+def _tend_case(o, g, L=None):
+    out = []
+    for is_area in (0, 1):
+        out.append(np.stack(o.swe_tendencies(is_area, g["tend_in_x"], g["tend_in_u"], g["tend_in_zeta"],
+                                             g["tend_in_sigma"], g["tend_in_third"], g["tend_in_ddot"],
+                                             g["tend_in_laps"], Omega=2 * np.pi, g=1.5, dt=0.0125, L=L)))
+    return out
+
+
+def test_swe_tendencies_match_golden_reference_outputs(oracle):
+    """SWEVorticityDivergence{Height,Area}Tendencies (lpm_swe_kernels.hpp:941-1069) as compiled from the reference."""
+    g = np.load(os.path.join(GOLDEN, "ref_sums.npz"))
+    got = _tend_case(oracle, g)
+    for is_area in (0, 1):
+        ref = g[f"tend_out_{is_area}"]
+        assert np.abs(got[is_area] - ref).max() <= 4e-15 * np.abs(ref).max()  # FMA contraction may differ by an ulp
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "liblpm_ref.so")),
+                    reason="oracle/_ref not built (needs /root/reference)")
+def test_swe_surface_setters_match_live_reference_build(oracle):
+    """SetSurfaceFromDepth / SetDepthAndSurfaceFromMassAndArea with ZeroFunctor (lpm_swe_kernels.hpp:1079-1140)."""
+    R = ctypes.CDLL(oracle.REF_LIB)
+    Lo = oracle.lib()
+    rng = np.random.default_rng(5)
+    n = 100
+    dp = ctypes.POINTER(ctypes.c_double)
+    x = rng.standard_normal((n, 3))
+    h, m, area = 1 + rng.random(n), 1 + rng.random(n), 0.1 + rng.random(n)
+    mask = (rng.random(n) < 0.3).astype(np.uint8)
+    P = lambda a: a.ctypes.data_as(dp)  # noqa: E731
+    s1, b1, s2, b2 = (np.full(n, 7.0) for _ in range(4))
+    R.ref_swe_set_surface_from_depth(n, P(s1), P(b1), P(x), P(h))
+    Lo.oracle_swe_set_surface_from_depth(n, P(s2), P(b2), P(h))
+    assert np.array_equal(s1, s2) and np.array_equal(b1, b2)
+    out1 = [np.full(n, 7.0) for _ in range(3)]
+    out2 = [np.full(n, 7.0) for _ in range(3)]
+    mp = mask.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte))
+    R.ref_swe_set_depth_surface_from_mass_area(n, *map(P, out1), P(x), P(m), P(area), mp)
+    Lo.oracle_swe_set_depth_surface_from_mass_area(n, *map(P, out2), P(m), P(area), mp)
+    for a, b in zip(out1, out2):
+        assert np.array_equal(a, b)
+    assert (out1[0][mask == 1] == 7.0).all()  # divided faces are left untouched
+
+
 def test_solid_body_rotation_analytic(oracle):
     """examples/bve_rotation.cpp:147-167: zeta = 2 Omega z  ->  u = Omega(-y, x, 0), psi = Omega z; the direct
     sums converge to it at first order in the mesh size."""

@@ -299,6 +299,7 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(d_tgt, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_src, pk.data(), pk.size() * sizeof(double), cudaMemcpyHostToDevice));
 
+#define RUNK(K, T, NW, MINB, UNR) run<PairCfg<K, T, NW, MINB, UNR>>(#K " T" #T " NW" #NW " B" #MINB " U" #UNR)
 #define RUN(T, NW, MINB, UNR) run<PairCfg<kVel, T, NW, MINB, UNR>>("vel T" #T " NW" #NW " B" #MINB " U" #UNR)
   if (argc > 3) goto probes;
   RUN(4, 8, 2, 2);
@@ -326,7 +327,6 @@ int main(int argc, char** argv) {
   RUN(6, 16, 1, 1);
   RUN(8, 8, 1, 1);
   RUN(8, 4, 2, 1);
-#define RUNK(K, T, NW, MINB, UNR) run<PairCfg<K, T, NW, MINB, UNR>>(#K " T" #T " NW" #NW " B" #MINB " U" #UNR)
   if (argc <= 3) {
     RUNK(kVelPsi, 2, 8, 1, 2);
     RUNK(kVelPsi, 2, 8, 2, 2);
@@ -338,17 +338,30 @@ int main(int argc, char** argv) {
     RUNK(kPsi, 4, 16, 1, 2);
   }
 probes:
-  RUN(8, 4, 1, 1);
-  RUN(8, 4, 1, 2);
-  RUN(10, 4, 1, 1);
-  RUN(12, 4, 1, 1);
-  RUN(12, 4, 1, 2);
-  RUN(16, 4, 1, 1);
-  RUN(6, 4, 1, 2);
+  printf("LPMX_SEED_LO=%d\n", LPMX_SEED_LO);
   RUN(6, 8, 1, 2);
   RUN(6, 8, 1, 4);
-  RUN(5, 8, 1, 2);
+  RUN(6, 12, 1, 2);
+  RUN(6, 12, 1, 4);
   RUN(7, 8, 1, 2);
+  RUN(8, 8, 1, 2);
+  RUN(8, 8, 1, 4);
+  RUN(8, 4, 1, 2);
+  RUN(8, 4, 2, 2);
+  RUN(5, 8, 1, 2);
+  RUN(5, 12, 1, 2);
+  RUN(4, 12, 1, 2);
+  RUN(4, 16, 1, 2);
+  RUN(4, 8, 2, 2);
+  RUN(3, 8, 3, 2);
+  RUNK(kVelPsi, 2, 16, 1, 2);
+  RUNK(kVelPsi, 4, 8, 1, 2);
+  RUNK(kPsi, 4, 16, 1, 2);
+  RUNK(kSwe, 2, 8, 1, 2);
+  RUNK(kSwe, 2, 12, 1, 2);
+  RUNK(kSwe, 1, 16, 1, 2);
+  RUNK(kSwe, 3, 8, 1, 1);
+  if (argc > 4) return 0;
   {
     std::vector<double> cs(kConstSources * 6);
     for (int j = 0; j < kConstSources; ++j) {
