@@ -1,0 +1,213 @@
+// lpm/lpm_polymesh2d.hpp -- MeshSeed<Seed>, PolyMeshParameters<Seed> and PolyMesh2d<Seed> for the two spherical
+// seeds, backed by the C ABI's host mesh generator (lpmx_mesh_*).
+//   MeshSeed / IcosTriSphereSeed / CubedSphereSeed     src/mesh/lpm_mesh_seed.hpp:111-147,150-230
+//   MeshSeed::set_max_allocations                      src/mesh/lpm_mesh_seed.cpp:266-279
+//   PolyMeshParameters                                 src/mesh/lpm_polymesh2d.hpp:32-72
+//   PolyMesh2d::tree_init / n_*_host / appx_mesh_size  src/mesh/lpm_polymesh2d.hpp:152-159,861; _impl.hpp:25-42
+//   Vertices / Edges / Faces public views              src/mesh/lpm_vertices.hpp, lpm_edges.hpp, lpm_faces.hpp
+// Uniform refinement only: AMR (divide_flagged_faces), point location and remeshing are outside the hot path and
+// refuse with LPM_REQUIRE.
+#ifndef LPM_SHIM_POLYMESH2D_HPP
+#define LPM_SHIM_POLYMESH2D_HPP
+
+#include "lpm_coords.hpp"
+
+namespace Lpm {
+
+struct TriFace {
+  static constexpr Int nverts = 3;
+};
+struct QuadFace {
+  static constexpr Int nverts = 4;
+};
+
+struct CubedSphereSeed {
+  static constexpr Int nverts = 8, nfaces = 6, nedges = 12, nfaceverts = 4, vertex_degree = 4;
+  static constexpr int lpmx_id = LPMX_SEED_CUBED_SPHERE;
+  typedef SphereGeometry geo;
+  typedef QuadFace faceKind;
+  static std::string filename() { return "cubedSphereSeed.dat"; }
+  static std::string id_string() { return "cubed_sphere"; }
+};
+
+struct IcosTriSphereSeed {
+  static constexpr Int nverts = 12, nfaces = 20, nedges = 30, nfaceverts = 3, vertex_degree = 6;
+  static constexpr int lpmx_id = LPMX_SEED_ICOS_TRI_SPHERE;
+  typedef SphereGeometry geo;
+  typedef TriFace faceKind;
+  static std::string filename() { return "icosTriSphereSeed.dat"; }
+  static std::string id_string() { return "icostri_sphere"; }
+};
+
+template <typename SeedType>
+struct MeshSeed {
+  Real radius;
+  explicit MeshSeed(const Real r = 1) : radius(r) {}
+  static std::string id_string() { return SeedType::id_string(); }
+  /// memory needed for a uniform tree of depth lev (src/mesh/lpm_mesh_seed.cpp:266-279)
+  void set_max_allocations(Index& nboundary, Index& nedges, Index& nfaces, const Int lev) const {
+    LPM_REQUIRE(lpmx_mesh_max_allocations(SeedType::lpmx_id, lev, &nboundary, &nedges, &nfaces) == LPMX_OK);
+  }
+};
+
+template <typename SeedType>
+struct PolyMeshParameters {
+  Index nmaxverts, nmaxedges, nmaxfaces;
+  Int init_depth, amr_buffer, amr_limit;
+  MeshSeed<SeedType> seed;
+  PolyMeshParameters(const Int depth, const Real r = 1, const Int amr_buff = 0, const Int amr_lim = 0)
+      : init_depth(depth), amr_buffer(amr_buff), amr_limit(amr_lim), seed(r) {
+    seed.set_max_allocations(nmaxverts, nmaxedges, nmaxfaces, depth + amr_buff);
+  }
+};
+
+template <typename Geo>
+struct Vertices {
+  Coords<Geo> phys_crds, lag_crds;
+  index_view_type crd_inds;
+  Index nh() const { return n_; }
+  Index n_ = 0;
+};
+
+struct Edges {
+  index_view_type origs, dests, lefts, rights, parent;
+  View2<Index, 2> kids;
+  Index nh() const { return n_; }
+  Index n_leaves_host() const { return n_leaves_; }
+  Index n_ = 0, n_leaves_ = 0;
+};
+
+template <typename FaceKind, typename Geo>
+struct Faces {
+  Coords<Geo> phys_crds, lag_crds;
+  scalar_view_type area;
+  mask_view_type mask;              ///< non-zero = divided panel (not a leaf)
+  View2<Index, FaceKind::nverts> verts, edges;
+  View2<Index, 4> kids;
+  index_view_type crd_inds, parent, level, leaf_idx;
+  Index nh() const { return n_; }
+  Index n_leaves_host() const { return n_leaves_; }
+  /// sqrt(mean leaf area) (src/mesh/lpm_faces_impl.hpp:213-226)
+  Real appx_mesh_size() const {
+    Real s = 0;
+    for (Index i = 0; i < n_; ++i)
+      if (!mask(i)) s += area(i);
+    return std::sqrt(s / n_leaves_);
+  }
+  Real surface_area_host() const {
+    Real s = 0;
+    for (Index i = 0; i < n_; ++i) s += area(i);
+    return s;
+  }
+  Index n_ = 0, n_leaves_ = 0;
+};
+
+template <typename SeedType>
+class PolyMesh2d {
+ public:
+  typedef SeedType seed_type;
+  typedef typename SeedType::geo Geo;
+  typedef typename SeedType::faceKind FaceType;
+
+  Vertices<Geo> vertices;
+  Edges edges;
+  Faces<FaceType, Geo> faces;
+  Real radius = 1;
+  Int base_tree_depth = 0;
+
+  /// allocates; tree_init() fills (reference: PolyMesh2d(nmaxverts, nmaxedges, nmaxfaces))
+  PolyMesh2d(const Index nmaxverts, const Index nmaxedges, const Index nmaxfaces)
+      : nmaxverts_(nmaxverts), nmaxedges_(nmaxedges), nmaxfaces_(nmaxfaces) {}
+
+  /// allocates and builds the uniform tree (reference: PolyMesh2d(const PolyMeshParameters&), lpm_polymesh2d.hpp:152-159)
+  explicit PolyMesh2d(const PolyMeshParameters<SeedType>& params)
+      : nmaxverts_(params.nmaxverts), nmaxedges_(params.nmaxedges), nmaxfaces_(params.nmaxfaces) {
+    tree_init(params.init_depth, params.seed);
+  }
+  virtual ~PolyMesh2d() = default;
+
+  /// PolyMesh2d::tree_init (src/mesh/lpm_polymesh2d_impl.hpp:25-42) via lpmx_mesh_create
+  void tree_init(const Int initDepth, const MeshSeed<SeedType>& seed) {
+    lpmx_mesh_t m = nullptr;
+    LPM_REQUIRE_MSG(lpmx_mesh_create(SeedType::lpmx_id, initDepth, seed.radius, &m) == LPMX_OK, "lpmx_mesh_create");
+    int nv, ne, nf, nfl, nel, nfv;
+    lpmx_mesh_sizes(m, &nv, &ne, &nf, &nfl, &nel, &nfv);
+    LPM_REQUIRE_MSG(nv <= nmaxverts_ && ne <= nmaxedges_ && nf <= nmaxfaces_, "mesh exceeds the allocated sizes");
+    radius = seed.radius;
+    base_tree_depth = initDepth;
+    vertices.n_ = nv, edges.n_ = ne, edges.n_leaves_ = nel, faces.n_ = nf, faces.n_leaves_ = nfl;
+    vertices.phys_crds = Coords<Geo>(nv), vertices.lag_crds = Coords<Geo>(nv);
+    faces.phys_crds = Coords<Geo>(nf), faces.lag_crds = Coords<Geo>(nf);
+    vertices.phys_crds.set_nh(nv), vertices.lag_crds.set_nh(nv), faces.phys_crds.set_nh(nf), faces.lag_crds.set_nh(nf);
+    vertices.crd_inds = index_view_type("vert_crd_inds", nv);
+    edges.origs = index_view_type("origs", ne), edges.dests = index_view_type("dests", ne);
+    edges.lefts = index_view_type("lefts", ne), edges.rights = index_view_type("rights", ne);
+    edges.parent = index_view_type("edge_parent", ne), edges.kids = View2<Index, 2>("edge_kids", ne);
+    faces.area = scalar_view_type("area", nf), faces.mask = mask_view_type("mask", nf);
+    faces.verts = View2<Index, FaceType::nverts>("face_verts", nf), faces.edges = View2<Index, FaceType::nverts>("face_edges", nf);
+    faces.kids = View2<Index, 4>("face_kids", nf);
+    faces.crd_inds = index_view_type("face_crd_inds", nf), faces.parent = index_view_type("face_parent", nf);
+    faces.level = index_view_type("face_level", nf), faces.leaf_idx = index_view_type("leaf_idx", nf);
+    fetch(m, LPMX_MESH_VERT_XYZ, vertices.phys_crds.view.data());
+    fetch(m, LPMX_MESH_VERT_LAG_XYZ, vertices.lag_crds.view.data());
+    fetch(m, LPMX_MESH_VERT_CRD_INDS, vertices.crd_inds.data());
+    fetch(m, LPMX_MESH_EDGE_ORIGS, edges.origs.data());
+    fetch(m, LPMX_MESH_EDGE_DESTS, edges.dests.data());
+    fetch(m, LPMX_MESH_EDGE_LEFTS, edges.lefts.data());
+    fetch(m, LPMX_MESH_EDGE_RIGHTS, edges.rights.data());
+    fetch(m, LPMX_MESH_EDGE_PARENTS, edges.parent.data());
+    fetch(m, LPMX_MESH_EDGE_KIDS, edges.kids.data());
+    fetch(m, LPMX_MESH_FACE_XYZ, faces.phys_crds.view.data());
+    fetch(m, LPMX_MESH_FACE_LAG_XYZ, faces.lag_crds.view.data());
+    fetch(m, LPMX_MESH_FACE_AREA, faces.area.data());
+    fetch(m, LPMX_MESH_FACE_MASK, faces.mask.data());
+    fetch(m, LPMX_MESH_FACE_VERTS, faces.verts.data());
+    fetch(m, LPMX_MESH_FACE_EDGES, faces.edges.data());
+    fetch(m, LPMX_MESH_FACE_CRD_INDS, faces.crd_inds.data());
+    fetch(m, LPMX_MESH_FACE_PARENT, faces.parent.data());
+    fetch(m, LPMX_MESH_FACE_KIDS, faces.kids.data());
+    fetch(m, LPMX_MESH_FACE_LEVEL, faces.level.data());
+    fetch(m, LPMX_MESH_FACE_LEAF_IDX, faces.leaf_idx.data());
+    lpmx_mesh_destroy(m);
+  }
+
+  Index n_vertices_host() const { return vertices.nh(); }
+  Index n_edges_host() const { return edges.nh(); }
+  Index n_faces_host() const { return faces.nh(); }
+  Real appx_mesh_size() const { return faces.appx_mesh_size(); }
+  Real surface_area_host() const { return faces.surface_area_host(); }
+  virtual void update_device() const {}
+  virtual void update_host() const {}
+
+  template <typename Flags, typename LoggerType>
+  void divide_flagged_faces(const Flags&, LoggerType&) {
+    LPM_REQUIRE_MSG(false, "adaptive refinement is outside the direct-sum hot path (SURVEY.md section 2, row 19)");
+  }
+
+  virtual std::string info_string(const std::string& label = "", const int tab_level = 0, const bool = false) const {
+    std::ostringstream ss;
+    const std::string tabs(tab_level, '\t');
+    ss << tabs << "PolyMesh2d<" << SeedType::id_string() << "> " << label << ": depth " << base_tree_depth << ", "
+       << n_vertices_host() << " vertices, " << n_edges_host() << " edges (" << edges.n_leaves_host() << " leaves), "
+       << n_faces_host() << " faces (" << faces.n_leaves_host() << " leaves); surface area " << surface_area_host()
+       << ", appx mesh size " << appx_mesh_size() << "\n";
+    return ss.str();
+  }
+
+ protected:
+  Index nmaxverts_, nmaxedges_, nmaxfaces_;
+
+ private:
+  template <typename T>
+  static void fetch(lpmx_mesh_t m, const int id, T* dst) {
+    const void* src = nullptr;
+    long n = 0;
+    int kind = 0;
+    LPM_REQUIRE(lpmx_mesh_array(m, id, &src, &n, &kind) == LPMX_OK);
+    const T* s = static_cast<const T*>(src);
+    for (long i = 0; i < n; ++i) dst[i] = s[i];
+  }
+};
+
+}  // namespace Lpm
+#endif

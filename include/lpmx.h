@@ -124,6 +124,12 @@ int lpmx_launch_count(lpmx_handle_t h, long* n_launches);
 int lpmx_profile_enable(lpmx_handle_t h, int enable);
 int lpmx_profile_read(lpmx_handle_t h, long* n_launches, double* total_ms, double* pair_visits);
 
+/* Synchronous copy of `bytes` bytes between any two of {host, device} buffers, ordered after the work queued on
+ * the handle's stream (what Kokkos::deep_copy is to the reference's update_host/update_device,
+ * src/mesh/lpm_faces.hpp:151-165).  Lets host-only callers (the C++ shim's Laplacian trampoline) move data without
+ * the CUDA headers. */
+int lpmx_copy(lpmx_handle_t h, void* dst, const void* src, long bytes);
+
 /* Target sharding over the GPUs of one box (the reference has no multi-device path; DESIGN.md
  * section 6).  The concatenated target list (vertices then faces) is split into `world`
  * contiguous index ranges; this handle evaluates range `rank`.  Default: rank 0 of 1. */

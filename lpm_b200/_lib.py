@@ -84,6 +84,7 @@ def _declare(L):
         "lpmx_sync": [vp],
         "lpmx_stream": [vp, ctypes.POINTER(vp)],
         "lpmx_launch_count": [vp, c_long_p],
+        "lpmx_copy": [vp, vp, vp, l],
         "lpmx_profile_enable": [vp, i],
         "lpmx_profile_read": [vp, c_long_p, c_double_p, c_double_p],
         "lpmx_set_partition": [vp, i, i],

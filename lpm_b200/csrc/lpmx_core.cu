@@ -220,6 +220,15 @@ int lpmx_launch_count(lpmx_handle_t h, long* n) {
   return LPMX_OK;
 }
 
+int lpmx_copy(lpmx_handle_t h, void* dst, const void* src, long bytes) {
+  if (!h || bytes < 0 || (bytes > 0 && (!dst || !src))) return h ? set_error(h, LPMX_ERR_INVALID, "bad copy arguments") : LPMX_ERR_INVALID;
+  if (bytes == 0) return LPMX_OK;
+  LPMX_CUDA(h, cudaSetDevice(h->device));
+  LPMX_CUDA(h, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, h->stream));
+  LPMX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return LPMX_OK;
+}
+
 int lpmx_profile_enable(lpmx_handle_t h, int enable) {
   if (!h) return LPMX_ERR_INVALID;
   h->profile = enable != 0;

@@ -81,7 +81,9 @@ class RossbyHaurwitz54:
 class SphereTestCase2:
     """Williamson test case 2 (examples/sphere_swe_tc2.cpp:231-251, lpm_vorticity_gallery.hpp:264-278,
     lpm_surface_gallery.hpp:120-134): u = u0(-y, x, 0), zeta = 2 u0 z, sigma = 0,
-    surface s = h0 + (u0^2/2 + Omega u0) cos^2(lat) / g (:239)."""
+    initial surface AS CODED in SphereTestCase2InitialSurface: s = h0 + Omega u0 cos^2(lat) / g (no u0^2/2 term,
+    lpm_surface_gallery.hpp:126-131); the example's exact surface is h0 + (u0^2/2 + Omega u0) cos^2(lat) / g
+    (examples/sphere_swe_tc2.cpp:239)."""
 
     def __init__(self, u0=2 * PI / 12, h0=10.0, g=1.0, Omega=2 * PI):
         self.u0, self.h0, self.g, self.Omega = u0, h0, g, Omega
@@ -100,7 +102,14 @@ class SphereTestCase2:
         return -2 * self.u0 ** 2 * xyz[:, 2] ** 2
 
     def surface(self, xyz):
+        return self.h0 + self.Omega * self.u0 * (1 - xyz[:, 2] ** 2) / self.g
+
+    def surface_exact(self, xyz):
         return self.h0 + (0.5 * self.u0 ** 2 + self.Omega * self.u0) * (1 - xyz[:, 2] ** 2) / self.g
+
+    def surface_laplacian_exact(self, xyz):
+        """slap_exact (examples/sphere_swe_tc2.cpp:243-244): (u0^2 + 2 Omega u0)(2 sin^2 - cos^2)/g"""
+        return (self.u0 ** 2 + 2 * self.Omega * self.u0) * (3 * xyz[:, 2] ** 2 - 1) / self.g
 
 
 def synthetic_sphere_points(n, seed=20261017):

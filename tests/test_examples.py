@@ -1,0 +1,82 @@
+"""The C++ API shim (include/lpm/*.hpp: the reference's class names over the C ABI) and the four config drivers in
+examples/ (bve_rotation, sphere_rh54, sphere_gaussian_vortex, sphere_swe_tc2).  CPU: they build with the host compiler
+alone and refuse to run without a GPU.  GPU: they run the reference's smoke configurations
+(examples/CMakeLists.txt:143-167: `bve_rotation -d 3 -dt 0.01 -tf 0.03`) and pass their own acceptance checks."""
+import json
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "examples", "_build")
+EXAMPLES = ["bve_rotation", "sphere_rh54", "sphere_gaussian_vortex", "sphere_swe_tc2"]
+
+
+@pytest.fixture(scope="module")
+def built():
+    from lpm_b200 import build
+    build.build()
+    subprocess.run(["make", "-C", os.path.join(ROOT, "examples")], check=True, capture_output=True)
+    return BUILD
+
+
+def test_examples_build_with_the_host_compiler(built):
+    for name in EXAMPLES:
+        assert os.access(os.path.join(built, name), os.X_OK), name
+
+
+def test_examples_refuse_to_run_without_a_gpu(built):
+    from conftest import HAVE_GPU
+    if HAVE_GPU:
+        pytest.skip("a GPU is present")
+    p = subprocess.run([os.path.join(built, "bve_rotation"), "-d", "2"], capture_output=True, text=True)
+    assert p.returncode == 2
+    assert "LPMX_ERR_NO_DEVICE" in p.stderr and "no CPU fallback" in p.stderr
+
+
+def _run(built, name, *args):
+    p = subprocess.run([os.path.join(built, name), *args], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    line = [ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1]
+    return json.loads(line), p.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", ["cubed", "icos"])
+def test_bve_rotation_ctest_case(built, seed):
+    out, log = _run(built, "bve_rotation", "-s", seed, "-d", "3", "-dt", "0.01", "-tf", "0.03")
+    assert out["steps"] == 3 and out["gpu_launches"] > 0
+    assert out["vel_l2"] < 0.1 and out["pos_l2"] < 1e-2  # first-order quadrature at depth 3
+    assert "tfinal (velocity)" in log
+
+
+@pytest.mark.gpu
+def test_bve_rotation_converges_with_depth(built):
+    e3, _ = _run(built, "bve_rotation", "-d", "3", "-dt", "0.01", "-tf", "0.01")
+    e5, _ = _run(built, "bve_rotation", "-d", "5", "-dt", "0.005", "-tf", "0.01")  # same Courant number
+    assert e5["vel_l2"] < 0.5 * e3["vel_l2"]
+
+
+@pytest.mark.gpu
+def test_bve_rotation_refuses_courant_number_above_one(built):
+    """examples/bve_rotation.cpp:111-114: LPM_REQUIRE(cr < 1)."""
+    p = subprocess.run([os.path.join(built, "bve_rotation"), "-d", "5", "-dt", "0.01", "-tf", "0.02"],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 3 and "exceeds 1" in p.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["sphere_rh54", "sphere_gaussian_vortex"])
+def test_ic2d_examples(built, name):
+    out, log = _run(built, name, "-d", "4", "-tf", "0.05", "-n", "5")
+    assert out["steps"] == 5 and abs(out["t"] - 0.05) < 1e-12 and out["gpu_launches"] > 0
+    assert out["ke_drift"] < 1e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", ["cubed", "icos"])
+def test_swe_tc2_example(built, seed):
+    out, log = _run(built, "sphere_swe_tc2", "-s", seed, "-d", "3", "-tf", "0.02", "-n", "4")
+    assert out["steps"] == 4 and out["gpu_launches"] > 0
+    assert out["depth_l2"] < 1e-3
