@@ -186,7 +186,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="rh54_cubed7", choices=sorted(WORKLOADS))
     ap.add_argument("--stepper", default="bve_rk4", choices=["bve_rk4", "ic2d_rk2"])
-    ap.add_argument("--dt", type=float, default=0.01)
+    ap.add_argument("--dt", type=float, default=None,
+                    help="time step; default 0.025 * h / h(cubed-4): the reference's sphere_rh54 default (tfinal 0.025, "
+                         "1 step, depth 4; examples/sphere_rh54.cpp:442-452) at constant Courant number")
     ap.add_argument("--cpu-sample", type=int, default=65536, help="vertex targets in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -207,6 +209,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # keep stdout to the one JSON line: NCCL's version / debug lines go to a file unless the user chose one
+        import tempfile
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(tempfile.gettempdir(), "lpmx_nccl.%h.%p.log"))
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = Engine(local_rank)
@@ -215,6 +220,8 @@ def main():
 
     m, vz, fz, desc = build_case(args.workload)
     nv, nf, nleaf = m.n_verts, m.n_faces, m.n_face_leaves
+    if args.dt is None:
+        args.dt = 0.025 * m.appx_mesh_size() / 0.09045016  # Courant number of the reference default (~0.4)
     evals = EVALS_PER_STEP[args.stepper]
     i_eval = float(nv + nf) * nleaf - nleaf
     Omega = 2 * np.pi
@@ -277,6 +284,20 @@ def main():
     ms_per_step = total_ms / args.steps
     value = evals * i_eval / (ms_per_step * 1e-3)
 
+    # ---- sanity of the advanced state (a blown-up run would still time the same): finite, still on the sphere ----
+    chk = [np.zeros((nv, 3)), np.zeros(nv), np.zeros((nv, 3)), np.zeros((nf, 3)), np.zeros(nf), np.zeros((nf, 3))]
+    if args.stepper == "bve_rk4":
+        solver.get_state(*chk)
+    else:
+        solver.get_state(chk[0], chk[1], chk[2], None, chk[3], chk[4], chk[5], None)
+    leafsel = mask == 0
+    state_check = {
+        "finite": bool(np.isfinite(chk[0]).all() and np.isfinite(chk[3][leafsel]).all() and np.isfinite(chk[5][leafsel]).all()),
+        "max_abs_radius_minus_1": float(np.abs(np.linalg.norm(chk[3][leafsel], axis=1) - 1).max()),
+        "max_speed": float(np.linalg.norm(chk[5][leafsel], axis=1).max()),
+        "steps_advanced": args.warmup + args.steps,
+    }
+
     # ---- roofline of the dominant kernel (rank-local): algorithmic flops / CUDA-event launch time ----
     flops_per = 24.0  # BVE velocity pair; the IC2D (u,psi) evaluation counts 31
     local_inter = evals * args.steps * (float(solver_local_targets(nv + nf, rank, world)) * nleaf)
@@ -302,7 +323,7 @@ def main():
 
     # ---- e2e: in-place C-ABI call on pinned host buffers (H2D + step + D2H inside the timed region) ----
     e2e = None
-    if rank == 0 and world == 1:
+    if True:  # every rank passes the full state; the engine shards the targets and gathers the result
         def pin(a):
             t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
             return t
@@ -334,10 +355,14 @@ def main():
         t_calls = 0.0
         for _ in range(args.steps):
             flush_buf.fill_(1)  # L2 flush between calls, outside the timed call
-            torch.cuda.synchronize()
+            barrier()
             c0 = time.perf_counter()
             one()  # returns when the results are back in the host buffers
             t_calls += time.perf_counter() - c0
+        if dist is not None:
+            t = torch.tensor([t_calls], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_calls = float(t.item())
         e2e = {"value": evals * i_eval * args.steps / t_calls, "unit": "interactions/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": t_calls / args.steps * 1e3,
@@ -363,6 +388,7 @@ def main():
                        "parallelism": f"targets sharded over {world} GPU(s), per-stage allgather of leaf source records",
                        "l2": "flushed between timed steps (256 MiB write)"},
             "rk_step_ms": ms_per_step, "step_ms_each": step_ms, "wall_s_timed_region": t_wall,
+            "state_check": state_check,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -261,6 +261,26 @@ int lpmx_ic2d_solver_init_direct_sums(lpmx_ic2d_solver_t s);
 int lpmx_ic2d_solver_advance(lpmx_ic2d_solver_t s, double dt, double Omega, int n_steps);
 
 /* ------------------------------------------------------------------------------------------
+ * Per-step diagnostics of the callers (the O(N) tail of every example's time loop).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Incompressible2D::total_vorticity / total_kinetic_energy / total_enstrophy
+ * (src/lpm_incompressible2d_impl.hpp:91-137): sums over the unmasked active particles of zeta A, |u|^2 A / 2,
+ * zeta^2 A / 2.  Host or device pointers; any output may be NULL. */
+int lpmx_ic2d_totals(lpmx_handle_t h, int n_active, const double* active_vort, const double* active_vel, int layout,
+                     long active_ld, const double* active_area, const unsigned char* active_mask,
+                     double* total_vorticity, double* total_kinetic_energy, double* total_enstrophy);
+/* the same on the resident state of a solver (no transfer of the fields) */
+int lpmx_ic2d_solver_totals(lpmx_ic2d_solver_t s, double* total_vorticity, double* total_kinetic_energy,
+                            double* total_enstrophy);
+
+/* ErrNorms(err, exact, weight) (src/lpm_error.hpp:81-131, ReduceErrorFtor src/lpm_error_impl.hpp:59-108):
+ * l1 = sum |e| w / sum |x| w, l2 = sqrt(sum e^2 w / sum x^2 w), linf = max |e| / max |x|; ndim = 1 for scalar
+ * views, 3 for Real*[3] views (|.| = Euclidean magnitude of a row; layout/ld as everywhere). */
+int lpmx_err_norms(lpmx_handle_t h, int n, int ndim, const double* err, const double* exact, int layout, long ld,
+                   const double* weight, double* l1, double* l2, double* linf);
+
+/* ------------------------------------------------------------------------------------------
  * Spherical shallow water: SWE<Seed> fields + SWERK2 (src/lpm_swe.hpp:29-88, src/lpm_swe_rk2.hpp:15-39).
  * ------------------------------------------------------------------------------------------ */
 

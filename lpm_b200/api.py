@@ -285,6 +285,26 @@ class Engine:
             grad = grad.reshape(n_tgt, 9)
         return vel, ddot, grad
 
+    # ---- diagnostics ---------------------------------------------------------------------
+    def ic2d_totals(self, active_vort, active_vel, active_area, active_mask, layout=LAYOUT_RIGHT):
+        """(total_vorticity, total_kinetic_energy, total_enstrophy) -- Incompressible2D::total_*."""
+        n = active_vel.shape[0] if layout == LAYOUT_RIGHT else active_vel.shape[1]
+        v, k, e = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        self._check(self._L.lpmx_ic2d_totals(self._h, n, _ptr(_f64(active_vort)), _ptr(_f64(active_vel)), layout, n,
+                                             _ptr(_f64(active_area)), _ptr(_u8(active_mask)), ctypes.byref(v),
+                                             ctypes.byref(k), ctypes.byref(e)), "lpmx_ic2d_totals")
+        return v.value, k.value, e.value
+
+    def err_norms(self, err, exact, weight, layout=LAYOUT_RIGHT):
+        """ErrNorms(err, exact, weight) -> (l1, l2, linf)."""
+        err, exact, weight = _f64(err), _f64(exact), _f64(weight)
+        ndim = 1 if err.ndim == 1 else 3
+        n = err.shape[0] if (ndim == 1 or layout == LAYOUT_RIGHT) else err.shape[1]
+        a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        self._check(self._L.lpmx_err_norms(self._h, n, ndim, _ptr(err), _ptr(exact), layout, n, _ptr(weight),
+                                           ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "lpmx_err_norms")
+        return a.value, b.value, c.value
+
     # ---- stepper level, in place on caller arrays ----------------------------------------
     def bve_rk4_step(self, dt, Omega, vert_xyz, vert_vort, vert_vel, face_xyz, face_vort, face_vel, face_area,
                      face_mask, n_steps=1, layout=LAYOUT_RIGHT):
@@ -398,6 +418,13 @@ class IC2DSolver:
 
     def init_direct_sums(self):
         self.e._check(self.e._L.lpmx_ic2d_solver_init_direct_sums(self._s), "lpmx_ic2d_solver_init_direct_sums")
+
+    def totals(self):
+        """(total_vorticity, total_kinetic_energy, total_enstrophy) of the resident state."""
+        v, k, e = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        self.e._check(self.e._L.lpmx_ic2d_solver_totals(self._s, ctypes.byref(v), ctypes.byref(k), ctypes.byref(e)),
+                      "lpmx_ic2d_solver_totals")
+        return v.value, k.value, e.value
 
     def advance(self, dt, Omega, n_steps=1):
         self.e._check(self.e._L.lpmx_ic2d_solver_advance(self._s, float(dt), float(Omega), n_steps),

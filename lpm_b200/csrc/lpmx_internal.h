@@ -139,6 +139,10 @@ int scan_leaves(lpmx_handle_t h, const unsigned char* mask_dev, int n, int* leaf
 int round_up_chunk(int n);
 int fp64_probe(lpmx_handle_t h, double* tflops, double* ms_out);
 
+// leaf totals [sum zeta A, sum zeta^2 A, sum |u|^2 A] of n faces -> host (lpmx_diagnostics.cu; synchronises the stream)
+int ic2d_totals_device(lpmx_handle_t h, int n, const double* zeta, Vec3View u, const double* area, const unsigned char* mask,
+                       double* out3_host);
+
 // In-place allgatherv of doubles on the handle's stream: rank r owns elements
 // [offsets[r], offsets[r+1]) of `base`; after the call every rank holds all of them.
 // No-op for world == 1.  (lpmx_core.cu; NCCL broadcasts grouped into one launch.)

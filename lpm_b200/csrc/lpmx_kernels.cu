@@ -61,15 +61,16 @@ static int launch_cfg(lpmx_handle_t h, const SumPlan& p, const SumArgs& a) {
 #define LPMX_SHAPE(K, T, NW, MINB, UNR) \
   { K, T, NW, MINB, &launch_cfg<PairCfg<K, T, NW, MINB, UNR>> }
 // Per kind: preferred (largest target block) first; smaller blocks keep all SMs busy on small meshes.
-// Shapes were picked with tools/tune_pair_sum.cu on a B200 (profiles/tune_r1.txt): the FP64 pipe sustains
+// Shapes were picked with tools/tune_pair_sum.cu on a B200 (profiles/r1b_tune_shapes.txt, profiles/r1f_tune_psi.txt): the FP64 pipe sustains
 // one DFMA per 2 cycles per SM sub-partition only while an instruction reads <= 2 distinct 64-bit register
 // operands (3 distinct: 3 cycles), so the winner is the shape with the most operand reuse across the T
 // targets of a thread that still leaves 8 warps per SM to cover MUFU/LDS latency.
 static const Shape kShapes[] = {
     LPMX_SHAPE(kVel, 6, 8, 1, 2),     LPMX_SHAPE(kVel, 4, 8, 2, 2),    LPMX_SHAPE(kVel, 2, 8, 2, 2),
     LPMX_SHAPE(kVel, 1, 8, 2, 2),
-    LPMX_SHAPE(kVelPsi, 2, 16, 1, 2), LPMX_SHAPE(kVelPsi, 2, 8, 2, 2), LPMX_SHAPE(kVelPsi, 1, 8, 2, 2),
-    LPMX_SHAPE(kPsi, 4, 16, 1, 2),    LPMX_SHAPE(kPsi, 2, 8, 2, 2),    LPMX_SHAPE(kPsi, 1, 8, 2, 2),
+    LPMX_SHAPE(kVelPsi, 4, 8, 1, 2),  LPMX_SHAPE(kVelPsi, 2, 8, 2, 2), LPMX_SHAPE(kVelPsi, 1, 8, 2, 2),
+    LPMX_SHAPE(kPsi, 8, 8, 1, 2),     LPMX_SHAPE(kPsi, 4, 8, 2, 2),    LPMX_SHAPE(kPsi, 2, 8, 2, 2),
+    LPMX_SHAPE(kPsi, 1, 8, 2, 2),
     LPMX_SHAPE(kSwe, 2, 8, 1, 2),     LPMX_SHAPE(kSwe, 1, 8, 1, 2),
 };
 constexpr int kNumShapes = sizeof(kShapes) / sizeof(kShapes[0]);
@@ -115,7 +116,7 @@ int make_plan(lpmx_handle_t h, int kind, int n_tgt, int n_src, SumPlan* p) {
     }
   }
   p->max_slots = ms;
-  p->smem_bytes = (size_t)kStages * kChunk * kind_rec(kind) * sizeof(double) + 2 * kStages * sizeof(uint64_t);
+  p->smem_bytes = pair_smem_bytes(kind);
   return LPMX_OK;
 }
 

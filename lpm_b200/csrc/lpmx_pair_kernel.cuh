@@ -71,6 +71,39 @@ __device__ __forceinline__ double rcp_seed_lo(double d, double dead) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// log(d) for the stream-function kinds.  d = kappa - x.y is a positive normal double (0 < d <= ~2), so the
+// general-purpose libdevice log (special cases, denormals, ~45 FP64-pipe instructions) is replaced by a
+// table-driven one: d = 2^k m, m in [1,2); c_i ~ 1/m from the top 7 mantissa bits, t = m c_i - 1 (one FMA,
+// |t| <= 2^-8), log d = k ln2 - log c_i + log1p(t), log1p by a degree-7 Taylor polynomial (|t|^8/8 < 2^-67).
+// 11 FP64-pipe instructions; absolute error < 3e-16 on (0, 4), checked in tests/test_gpu_parity_bve.py;
+// non-finite for d <= 0 like std::log.
+// The 2 KB table {c_i, -log c_i} sits in shared memory behind the source ring (divergent LDS.128).
+// ------------------------------------------------------------------------------------------------
+__device__ const double2 kLogTable[128] = {
+#include "log_table.inc"
+};
+
+__host__ __device__ constexpr bool kind_has_log(int k) { return k == kVelPsi || k == kPsi; }
+
+__device__ __forceinline__ double fast_log(double d, const double2* __restrict__ tbl) {
+  const int hi = __double2hiint(d);
+  const int k = (hi >> 20) - 1023;
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(d));
+  const double2 cl = tbl[(hi >> 13) & 127];
+  const double t = fma(m, cl.x, -1.0);
+  double q = fma(t, 1.0 / 7.0, -1.0 / 6.0);
+  q = fma(q, t, 0.2);
+  q = fma(q, t, -0.25);
+  q = fma(q, t, 1.0 / 3.0);
+  q = fma(q, t, -0.5);
+  const double l1p = fma(q, t * t, t);
+  // d <= 0 (a target sitting exactly on a source, e.g. a divided icosahedral panel on its child at eps = 0):
+  // the reference's std::log returns -inf / NaN there; stay non-finite (integer compare + select, off the FP64 pipe)
+  const double kd = hi > 0 ? (double)k : __longlong_as_double(0x7ff8000000000000LL);
+  return fma(kd, 0.693147180559945309417232121458, cl.y) + l1p;
+}
+
+// ------------------------------------------------------------------------------------------------
 // kernel arguments
 // ------------------------------------------------------------------------------------------------
 struct SumArgs {
@@ -84,6 +117,12 @@ struct SumArgs {
   long n_tgt_pad;
   double kappa;  // 1 + eps^2
 };
+
+// dynamic shared memory of one CTA: source ring + full/empty barriers (+ the log table)
+__host__ __device__ constexpr size_t pair_smem_bytes(int kind) {
+  return (size_t)kStages * kChunk * kind_rec(kind) * sizeof(double) + 2 * kStages * sizeof(uint64_t) +
+         (kind_has_log(kind) ? 128 * sizeof(double2) : 0);
+}
 
 __host__ __device__ __forceinline__ int cta_of_item(long item, int grid, long n_items) {
   return (int)(((item + 1) * (long)grid - 1) / n_items);
@@ -102,7 +141,7 @@ struct Pair<kVel, CHECK> {
   // `car` carries a dead value (the previous pair's r of this accumulator slot) whose register pair hosts the
   // next reciprocal seed (see rcp_seed_lo).
   __device__ __forceinline__ static void apply(const double* x, const double* /*kx*/, double kappa, const double* s,
-                                               int j, int self, double* acc, double& car) {
+                                               int j, int self, double* acc, double& car, const double2* /*tbl*/) {
     const double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
 #if LPMX_SEED_LO
     const double r0 = rcp_seed_lo(d, car);
@@ -124,7 +163,7 @@ template <bool CHECK>
 struct Pair<kVelPsi, CHECK> {
   static constexpr int NLOAD = 8;
   __device__ __forceinline__ static void apply(const double* x, const double*, double kappa, const double* s, int j,
-                                               int self, double* acc, double& /*car*/) {
+                                               int self, double* acc, double& /*car*/, const double2* tbl) {
     double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
     double gam = s[6];
     if (CHECK) {
@@ -140,7 +179,7 @@ struct Pair<kVelPsi, CHECK> {
     acc[0] = fma(r, s[3], acc[0]);
     acc[1] = fma(r, s[4], acc[1]);
     acc[2] = fma(r, s[5], acc[2]);
-    acc[3] = fma(gam, log(d), acc[3]);
+    acc[3] = fma(gam, fast_log(d, tbl), acc[3]);
   }
 };
 
@@ -148,7 +187,7 @@ template <bool CHECK>
 struct Pair<kPsi, CHECK> {
   static constexpr int NLOAD = 8;
   __device__ __forceinline__ static void apply(const double* x, const double*, double kappa, const double* s, int j,
-                                               int self, double* acc, double& /*car*/) {
+                                               int self, double* acc, double& /*car*/, const double2* tbl) {
     double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
     double gam = s[6];
     if (CHECK) {
@@ -156,7 +195,7 @@ struct Pair<kPsi, CHECK> {
       d = me ? 1.0 : d;
       gam = me ? 0.0 : gam;
     }
-    acc[0] = fma(gam, log(d), acc[0]);
+    acc[0] = fma(gam, fast_log(d, tbl), acc[0]);
   }
 };
 
@@ -168,7 +207,7 @@ template <bool CHECK>
 struct Pair<kSwe, CHECK> {
   static constexpr int NLOAD = 6;
   __device__ __forceinline__ static void apply(const double* x, const double* kx, double kappa, const double* s,
-                                               int j, int self, double* acc, double& /*car*/) {
+                                               int j, int self, double* acc, double& /*car*/, const double2* /*tbl*/) {
     double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
     double gz = s[3], gs = s[4];
     if (CHECK) {
@@ -215,7 +254,7 @@ struct Pair<kSwe, CHECK> {
 template <int KIND, int T, int UNROLL, bool CHECK>
 __device__ __forceinline__ void chunk_loop(const double (*x)[3], const double (*kx)[3], double kappa,
                                            const double* __restrict__ sp, int j0, const int* self,
-                                           double (*acc)[kind_nacc(KIND)]) {
+                                           double (*acc)[kind_nacc(KIND)], const double2* tbl) {
   constexpr int REC = kind_rec(KIND);
   static_assert(kChunk % UNROLL == 0, "source-loop unroll must divide the chunk");
   double car[UNROLL][T];
@@ -238,7 +277,7 @@ __device__ __forceinline__ void chunk_loop(const double (*x)[3], const double (*
         s[2 * v + 1] = t.y;
       }
 #pragma unroll
-      for (int t = 0; t < T; ++t) Pair<KIND, CHECK>::apply(x[t], kx[t], kappa, s, j0 + j, self[t], acc[t], car[u][t]);
+      for (int t = 0; t < T; ++t) Pair<KIND, CHECK>::apply(x[t], kx[t], kappa, s, j0 + j, self[t], acc[t], car[u][t], tbl);
     }
   }
 }
@@ -268,6 +307,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) pair_sum_kernel(const Sum
   double* stage = reinterpret_cast<double*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kStageBytes);
   uint64_t* empty = full + kStages;
+  double2* tbl = reinterpret_cast<double2*>(empty + kStages);  // 16-byte aligned: 2 * kStages * 8 bytes after the ring
+  if (kind_has_log(KIND))
+    for (int i = threadIdx.x; i < 128; i += C::THREADS) tbl[i] = kLogTable[i];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -340,9 +382,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) pair_sum_kernel(const Sum
 #pragma unroll
       for (int t = 0; t < T; ++t) hit |= (unsigned)(self[t] - j0) < (unsigned)kChunk;
       if (__any_sync(0xffffffffu, hit))
-        chunk_loop<KIND, T, C::UNROLL, true>(x, kx, a.kappa, sp, j0, self, acc);
+        chunk_loop<KIND, T, C::UNROLL, true>(x, kx, a.kappa, sp, j0, self, acc, tbl);
       else
-        chunk_loop<KIND, T, C::UNROLL, false>(x, kx, a.kappa, sp, j0, self, acc);
+        chunk_loop<KIND, T, C::UNROLL, false>(x, kx, a.kappa, sp, j0, self, acc, tbl);
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);
       if (++s == kStages) {

@@ -789,6 +789,28 @@ int lpmx_ic2d_solver_advance(lpmx_ic2d_solver_t s, double dt, double Omega, int 
   return LPMX_OK;
 }
 
+int lpmx_ic2d_solver_totals(lpmx_ic2d_solver_t s, double* total_vorticity, double* total_kinetic_energy,
+                            double* total_enstrophy) {
+  if (!s) return LPMX_ERR_INVALID;
+  SolverState& st = s->st;
+  lpmx_handle_t h = st.h;
+  if (!st.has_state) return set_error(h, LPMX_ERR_STATE, "totals before set_state");
+  LPMX_CUDA(h, cudaSetDevice(h->device));
+  // every rank sums over all faces: gather the rows the other ranks own first
+  LPMX_TRY(exchange_rows(&st, st.U, 3));
+  LPMX_TRY(exchange_rows(&st, st.Z, 1));
+  double out[3] = {0, 0, 0};
+  if (st.nf > 0) {
+    Vec3View u = st.view(st.U);
+    u.p += st.nv;
+    LPMX_TRY(ic2d_totals_device(h, st.nf, st.Z + st.nv, u, st.area, st.mask, out));
+  }
+  if (total_vorticity) *total_vorticity = out[0];
+  if (total_enstrophy) *total_enstrophy = 0.5 * out[1];
+  if (total_kinetic_energy) *total_kinetic_energy = 0.5 * out[2];
+  return LPMX_OK;
+}
+
 int lpmx_ic2d_rk2_step(lpmx_handle_t h, double dt, double Omega, double eps, int n_passive, double* px, double* pz,
                        double* pu, double* ppsi, int n_active, double* ax, double* az, double* au, double* apsi,
                        const double* aa, const unsigned char* am, int layout, long pld, long ald, int n_steps) {

@@ -198,3 +198,59 @@ def test_large_n_sampled_targets(engine, oracle):
     ov = oracle.bve_velocity(m.vert_xyz[idx], m.face_xyz, fz, m.face_area, m.face_mask)
     assert field_rel_err(uv[idx], ov) <= VEL_TOL
     assert np.abs(uv - sbr.velocity(m.vert_xyz)).max() < 1e-2  # quadrature error O(h) at this resolution
+
+
+def test_fast_log_accuracy_over_the_kernel_range(engine):
+    """The stream-function kernels evaluate log(1 - x.y + eps^2) with a table-driven log (lpmx_pair_kernel.cuh:
+    fast_log).  One unit source at the pole and targets on the axis give psi_i = log(d_i) * (-1/(4 pi)) for
+    prescribed d_i across the whole range a mesh can produce (1e-14 .. 2, plus exact powers of two and table
+    boundaries): absolute error must stay at the level of a correctly rounded log."""
+    d = np.concatenate([np.logspace(-14, np.log10(2.0), 4001), 2.0 ** -np.arange(0, 40), 1 + np.arange(128) / 128,
+                        1 + (np.arange(128) + 0.999999) / 128, [1.0, 2.0, 0.5, 1 - 2 ** -53, 1 + 2 ** -52]])
+    tx = np.zeros((len(d), 3))
+    tx[:, 2] = 1.0 - d  # 1 - x.y = d exactly when 1 - d is representable; compare against log of the realised d
+    d_real = 1.0 - tx[:, 2]
+    y = np.array([[0.0, 0.0, 1.0]])
+    psi = engine.bve_streamfn(tx, y, np.array([1.0]), np.array([1.0]), np.zeros(1, dtype=np.uint8))
+    got = psi * (-4 * gallery.PI)
+    ref = np.log(d_real)
+    bad = np.abs(got - ref) > 4e-16 * np.maximum(1.0, np.abs(ref))
+    assert not bad.any(), (d_real[bad][:8], got[bad][:8], ref[bad][:8])
+    assert np.abs(got - ref).max() <= 4e-16 * np.maximum(1.0, np.abs(ref)).max()
+    assert (np.abs(got - ref) <= 4e-16 * np.maximum(1.0, np.abs(ref))).all()
+    # IC2D fused kernel uses the same log with eps > 0
+    eps = 0.05
+    u, p = engine.ic2d_sums(tx, y, np.array([1.0]), np.array([1.0]), np.zeros(1, dtype=np.uint8), eps=eps)
+    ref2 = -np.log(d_real + eps * eps) / (4 * gallery.PI)
+    # the kernel forms (1 + eps^2) - x.y: the argument itself carries ~1e-16 absolute rounding, i.e. 4e-14 relative at
+    # d ~ eps^2, so the comparison is limited by the inputs, not by the log
+    assert np.abs(p - ref2).max() <= 1e-14
+
+
+def test_full_size_rk4_step_properties(engine, oracle):
+    """BASELINE.json configs[1] size (cubed-sphere depth 7, 229 376 targets x 98 304 leaf sources): one BVERK4 step
+    of solid-body rotation at the reference's Courant number.  Size-independent properties: positions follow the
+    rigid rotation to discretisation accuracy, radii are preserved, vorticity is untouched (Omega = 0), and the
+    velocity left in the state equals the oracle's velocity at the advected positions on 1 024 sampled targets."""
+    from lpm_b200.api import PolyMesh2d
+    m = PolyMesh2d("cubed", 7)
+    sbr = gallery.SolidBodyRotation()
+    vz, fz = sbr(m.vert_xyz), sbr(m.face_xyz)
+    dt = 0.5 * m.appx_mesh_size() / sbr.OMEGA  # Courant number 0.5 (the example refuses > 1: bve_rotation.cpp:111-114)
+    s = BVESolver(engine, m.n_verts, m.n_faces)
+    s.set_state(m.vert_xyz, vz, None, m.face_xyz, fz, None, np.ascontiguousarray(m.face_area), np.ascontiguousarray(m.face_mask))
+    s.init_velocity()
+    s.advance(dt, 0.0, 1)
+    out = [np.empty((m.n_verts, 3)), np.empty(m.n_verts), np.empty((m.n_verts, 3)), np.empty((m.n_faces, 3)),
+           np.empty(m.n_faces), np.empty((m.n_faces, 3))]
+    s.get_state(*out)
+    s.close()
+    c, sn = np.cos(sbr.OMEGA * dt), np.sin(sbr.OMEGA * dt)
+    exact = np.stack([m.vert_xyz[:, 0] * c - m.vert_xyz[:, 1] * sn, m.vert_xyz[:, 1] * c + m.vert_xyz[:, 0] * sn, m.vert_xyz[:, 2]], 1)
+    assert np.abs(out[0] - exact).max() < 1e-4                      # O(h) velocity error x dt
+    assert np.abs(np.linalg.norm(out[0], axis=1) - 1).max() < 1e-6
+    assert np.array_equal(out[1], vz) and np.array_equal(out[4], fz)
+    rng = np.random.default_rng(11)
+    idx = rng.choice(m.n_verts, 1024, replace=False)
+    ov = oracle.bve_velocity(out[0][idx], out[3], out[4], m.face_area, m.face_mask)
+    assert field_rel_err(out[2][idx], ov) <= VEL_TOL

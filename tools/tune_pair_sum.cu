@@ -73,7 +73,7 @@ static void run(const char* label) {
   a.n_sc = n_sc;
   a.n_tgt_pad = n_tgt_pad;
   a.kappa = 1.0;
-  const size_t smem = (size_t)kStages * kChunk * kind_rec(C::KIND) * sizeof(double) + 2 * kStages * sizeof(uint64_t);
+  const size_t smem = pair_smem_bytes(C::KIND);
   auto kern = pair_sum_kernel<C>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaFuncAttributes fa;
@@ -355,8 +355,21 @@ probes:
   RUN(4, 8, 2, 2);
   RUN(3, 8, 3, 2);
   RUNK(kVelPsi, 2, 16, 1, 2);
+  RUNK(kVelPsi, 2, 8, 2, 2);
+  RUNK(kVelPsi, 3, 8, 1, 2);
+  RUNK(kVelPsi, 3, 12, 1, 2);
   RUNK(kVelPsi, 4, 8, 1, 2);
+  RUNK(kVelPsi, 4, 8, 1, 1);
+  RUNK(kVelPsi, 4, 12, 1, 2);
+  RUNK(kVelPsi, 6, 8, 1, 1);
+  RUNK(kVelPsi, 6, 8, 1, 2);
   RUNK(kPsi, 4, 16, 1, 2);
+  RUNK(kPsi, 4, 8, 1, 2);
+  RUNK(kPsi, 4, 8, 2, 2);
+  RUNK(kPsi, 6, 8, 1, 2);
+  RUNK(kPsi, 8, 8, 1, 2);
+  RUNK(kPsi, 8, 8, 1, 1);
+  RUNK(kPsi, 2, 8, 2, 2);
   RUNK(kSwe, 2, 8, 1, 2);
   RUNK(kSwe, 2, 12, 1, 2);
   RUNK(kSwe, 1, 16, 1, 2);
