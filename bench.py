@@ -31,8 +31,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-FLOPS_PER_INTERACTION = {"bve_rk4": 24.0, "ic2d_rk2": 27.5}  # ic2d: one 24-flop velocity eval + one 31-flop (u,psi) eval
-EVALS_PER_STEP = {"bve_rk4": 4, "ic2d_rk2": 2}
+# algorithmic flops per interaction; ic2d: one 24-flop velocity eval + one 31-flop (u, psi) eval per step
+FLOPS_PER_INTERACTION = {"bve_rk4": 24.0, "ic2d_rk2": 27.5, "swe_rk2": 124.0}
+EVALS_PER_STEP = {"bve_rk4": 4, "ic2d_rk2": 2, "swe_rk2": 2}
 
 WORKLOADS = {
     # name: (seed, depth, vorticity, description)
@@ -43,6 +44,9 @@ WORKLOADS = {
     "gauss_icos9": ("icos", 9, "gauss", "examples/sphere_gaussian_vortex on icosTriSphereSeed depth 9 (7.86M particles)"),
     "rh54_cubed6": ("cubed", 6, "rh54", "Rossby-Haurwitz 54 on cubedSphereSeed depth 6"),
     "rh54_cubed5": ("cubed", 5, "rh54", "Rossby-Haurwitz 54 on cubedSphereSeed depth 5 (CPU-sized)"),
+    "tc2_icos8": ("icos", 8, "tc2", "examples/sphere_swe_tc2 (Williamson test case 2) on icosTriSphereSeed depth 8"),
+    "tc2_cubed7": ("cubed", 7, "tc2", "examples/sphere_swe_tc2 (Williamson test case 2) on cubedSphereSeed depth 7"),
+    "tc2_cubed5": ("cubed", 5, "tc2", "Williamson test case 2 on cubedSphereSeed depth 5"),
 }
 
 
@@ -54,6 +58,8 @@ def build_case(workload):
     if vort == "rh54":
         f = gallery.RossbyHaurwitz54()
         f.set_stationary_wave_speed()  # u0 = Omega/14, Omega = 2 pi (examples/sphere_rh54.cpp:108-111)
+    elif vort == "tc2":
+        f = gallery.SphereTestCase2().vorticity
     elif vort == "rotation":
         f = gallery.SolidBodyRotation()
     else:
@@ -185,7 +191,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="rh54_cubed7", choices=sorted(WORKLOADS))
-    ap.add_argument("--stepper", default="bve_rk4", choices=["bve_rk4", "ic2d_rk2"])
+    ap.add_argument("--stepper", default="bve_rk4", choices=["bve_rk4", "ic2d_rk2", "swe_rk2"])
     ap.add_argument("--dt", type=float, default=None,
                     help="time step; default 0.025 * h / h(cubed-4): the reference's sphere_rh54 default (tfinal 0.025, "
                          "1 step, depth 4; examples/sphere_rh54.cpp:442-452) at constant Courant number")
@@ -198,7 +204,7 @@ def main():
         return run_reference(args)
 
     import torch
-    from lpm_b200.api import BVESolver, Engine, IC2DSolver
+    from lpm_b200.api import BVESolver, Engine, IC2DSolver, SWESolver
     from lpm_b200.dist import env_rank_world, init_engine_comm
 
     rank, world, local_rank = env_rank_world()
@@ -232,10 +238,31 @@ def main():
         solver = BVESolver(eng, nv, nf)
         solver.set_state(m.vert_xyz, vz, None, m.face_xyz, fz, None, area, mask)
         solver.init_velocity()
-    else:
+    elif args.stepper == "ic2d_rk2":
         solver = IC2DSolver(eng, nv, nf, eps=0.0)
         solver.set_state(m.vert_xyz, vz, None, m.face_xyz, fz, None, area, mask)
         solver.init_direct_sums()
+    else:
+        # SWE fields of examples/sphere_swe_tc2.cpp; the (out-of-path) GMLS Laplacian is replaced by the closed-form
+        # Laplacian of the TC2 surface, frozen at the initial particle positions
+        from lpm_b200 import gallery as _g
+        tc = _g.SphereTestCase2()
+        swe_p = {"xyz": m.vert_xyz, "vort": vz, "div": np.zeros(nv), "depth": tc.surface(m.vert_xyz),
+                 "surf": tc.surface(m.vert_xyz), "bottom": np.zeros(nv), "laps": tc.surface_laplacian_exact(m.vert_xyz)}
+        swe_a = {"xyz": m.face_xyz, "vort": fz, "div": np.zeros(nf), "area": area, "mass": tc.surface(m.face_xyz) * area,
+                 "depth": tc.surface(m.face_xyz), "surf": tc.surface(m.face_xyz), "bottom": np.zeros(nf),
+                 "laps": tc.surface_laplacian_exact(m.face_xyz)}
+        swe_p = {k: np.ascontiguousarray(v) for k, v in swe_p.items()}
+        swe_a = {k: np.ascontiguousarray(v) for k, v in swe_a.items()}
+        swe_solver = SWESolver(eng, nv, nf, eps=0.0)
+        swe_solver.set_state(swe_p, swe_a, mask)
+        swe_solver.init_direct_sums(True)
+        swe_g = tc.g
+
+        class _Adv:  # same advance(dt, Omega, n) surface as the other two solvers
+            def advance(self, dt, Omega, n):
+                swe_solver.advance(dt, Omega, swe_g, None, n)
+        solver = _Adv()
     eng.sync()
     fp64_peak = eng.fp64_peak_tflops()
 
@@ -288,8 +315,10 @@ def main():
     chk = [np.zeros((nv, 3)), np.zeros(nv), np.zeros((nv, 3)), np.zeros((nf, 3)), np.zeros(nf), np.zeros((nf, 3))]
     if args.stepper == "bve_rk4":
         solver.get_state(*chk)
-    else:
+    elif args.stepper == "ic2d_rk2":
         solver.get_state(chk[0], chk[1], chk[2], None, chk[3], chk[4], chk[5], None)
+    else:
+        swe_solver.get_state({"xyz": chk[0], "vort": chk[1], "vel": chk[2]}, {"xyz": chk[3], "vort": chk[4], "vel": chk[5]})
     leafsel = mask == 0
     state_check = {
         "finite": bool(np.isfinite(chk[0]).all() and np.isfinite(chk[3][leafsel]).all() and np.isfinite(chk[5][leafsel]).all()),
@@ -299,10 +328,8 @@ def main():
     }
 
     # ---- roofline of the dominant kernel (rank-local): algorithmic flops / CUDA-event launch time ----
-    flops_per = 24.0  # BVE velocity pair; the IC2D (u,psi) evaluation counts 31
     local_inter = evals * args.steps * (float(solver_local_targets(nv + nf, rank, world)) * nleaf)
-    if args.stepper == "ic2d_rk2":
-        flops_per = FLOPS_PER_INTERACTION["ic2d_rk2"]
+    flops_per = FLOPS_PER_INTERACTION[args.stepper]
     achieved_tf = local_inter * flops_per / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else None
     roofline = {
         "bound": "fp64", "kernel": "lpmx::pair_sum_kernel", "achieved": achieved_tf, "peak": fp64_peak,
@@ -311,7 +338,7 @@ def main():
                        "nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2)",
         "flops_per_interaction": flops_per, "launches": n_k, "avg_launch_ms": (k_ms / n_k) if n_k else None,
         "kernel_share_of_step": (k_ms / (sum(step_ms))) if step_ms else None,
-        "fp64_pipe_instr_per_interaction": 9,
+        "fp64_pipe_instr_per_interaction": {"bve_rk4": 9, "ic2d_rk2": 15.5, "swe_rk2": 53}[args.stepper],
         "traffic": None,
     }
     prof = os.path.join(ROOT, "profiles", "r1_pair_sum_dram.json")
@@ -338,6 +365,18 @@ def main():
                 eng.bve_rk4_step(args.dt, Omega, *args_np, h_area.numpy(), h_mask.numpy(), n_steps=1)
             h2d = sum(t.numel() * 8 for t in host) + area.nbytes + mask.nbytes
             d2h = sum(t.numel() * 8 for t in host)
+        elif args.stepper == "swe_rk2":
+            from lpm_b200.api import ACTIVE_FIELDS, PASSIVE_FIELDS, swe_rk2_step
+            hp = {k: pin(np.zeros((nv, 3)) if k in ("xyz", "vel") else np.zeros(nv)) for k in PASSIVE_FIELDS}
+            ha = {k: pin(np.zeros((nf, 3)) if k in ("xyz", "vel") else np.zeros(nf)) for k in ACTIVE_FIELDS}
+            h_mask = pin(mask)
+            hp_np, ha_np = {k: t.numpy() for k, t in hp.items()}, {k: t.numpy() for k, t in ha.items()}
+            swe_solver.get_state(hp_np, ha_np)
+
+            def one():
+                swe_rk2_step(eng, args.dt, Omega, swe_g, 0.0, hp_np, ha_np, h_mask.numpy(), None, n_steps=1)
+            h2d = sum(t.numel() * 8 for t in hp.values()) + sum(t.numel() * 8 for t in ha.values()) + mask.nbytes
+            d2h = h2d - mask.nbytes
         else:
             st_np = [m.vert_xyz.copy(), vz.copy(), np.zeros((nv, 3)), np.zeros(nv), m.face_xyz.copy(), fz.copy(),
                      np.zeros((nf, 3)), np.zeros(nf)]
@@ -366,7 +405,7 @@ def main():
         e2e = {"value": evals * i_eval * args.steps / t_calls, "unit": "interactions/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": t_calls / args.steps * 1e3,
-               "api": "lpmx_bve_rk4_step" if args.stepper == "bve_rk4" else "lpmx_ic2d_rk2_step",
+               "api": {"bve_rk4": "lpmx_bve_rk4_step", "ic2d_rk2": "lpmx_ic2d_rk2_step", "swe_rk2": "lpmx_swe_rk2_step"}[args.stepper],
                "host_buffers": "pinned"}
 
     # ---- CPU baseline on the host cores (rank 0, N = 1 only) ----

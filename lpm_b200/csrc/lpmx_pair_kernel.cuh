@@ -6,6 +6,9 @@
 
 #include "lpmx_internal.h"
 
+#ifndef LPMX_STAGE_MAJOR
+#define LPMX_STAGE_MAJOR 1
+#endif
 #ifndef LPMX_SEED_LO
 #define LPMX_SEED_LO 0
 #endif
@@ -251,6 +254,38 @@ struct Pair<kSwe, CHECK> {
   }
 };
 
+// kVel, stage-major over the T targets of a thread.  The FP64 pipe reads one 64-bit register operand per cycle, so a
+// DFMA with three fresh register operands occupies it for 3 cycles instead of 2 unless one of them comes from the
+// operand-reuse cache, which only holds the operand of the immediately preceding instruction.  Emitting each stage for
+// all T targets back to back makes the shared operand (the source's y_k or Gamma*y_k) the reused one
+// (tools/sass_reuse_stats.py, profiles/README.md).
+template <int T, bool CHECK>
+__device__ __forceinline__ void vel_source(const double (*x)[3], double kappa, const double* s, int j, const int* self,
+                                           double (*acc)[3]) {
+  double d[T], r[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) d[t] = fma(s[0], -x[t][0], kappa);
+#pragma unroll
+  for (int t = 0; t < T; ++t) d[t] = fma(s[1], -x[t][1], d[t]);
+#pragma unroll
+  for (int t = 0; t < T; ++t) d[t] = fma(s[2], -x[t][2], d[t]);
+#pragma unroll
+  for (int t = 0; t < T; ++t) r[t] = rcp_seed(d[t]);
+#pragma unroll
+  for (int t = 0; t < T; ++t) d[t] = fma(-d[t], r[t], 1.0);   // e
+#pragma unroll
+  for (int t = 0; t < T; ++t) d[t] = fma(d[t], d[t], d[t]);   // e + e^2
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    r[t] = fma(r[t], d[t], r[t]);
+    if (CHECK) r[t] = (j == self[t]) ? 0.0 : r[t];
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int t = 0; t < T; ++t) acc[t][k] = fma(s[3 + k], r[t], acc[t][k]);
+}
+
 template <int KIND, int T, int UNROLL, bool CHECK>
 __device__ __forceinline__ void chunk_loop(const double (*x)[3], const double (*kx)[3], double kappa,
                                            const double* __restrict__ sp, int j0, const int* self,
@@ -276,6 +311,12 @@ __device__ __forceinline__ void chunk_loop(const double (*x)[3], const double (*
         s[2 * v] = t.x;
         s[2 * v + 1] = t.y;
       }
+#if LPMX_STAGE_MAJOR
+      if constexpr (KIND == kVel) {
+        vel_source<T, CHECK>(x, kappa, s, j0 + j, self, acc);
+        continue;
+      }
+#endif
 #pragma unroll
       for (int t = 0; t < T; ++t) Pair<KIND, CHECK>::apply(x[t], kx[t], kappa, s, j0 + j, self[t], acc[t], car[u][t], tbl);
     }

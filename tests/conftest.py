@@ -67,4 +67,6 @@ def field_rel_err(a, b, sel=None):
         a, b = a[:, None], b[:, None]
     num = np.sqrt(((a - b) ** 2).sum(axis=1)).max()
     den = np.sqrt((b ** 2).sum(axis=1)).max()
+    if den == 0.0:
+        return 0.0 if num == 0.0 else np.inf
     return num / den

@@ -145,3 +145,49 @@ def test_swe_tc2_analytic(engine, meshes):
     # The double-dot sums are checked against the oracle (pinned to the reference's own code), not against
     # the example's closed form -2 u0^2 z^2: the reference only logs that error and never asserts it.
     assert np.isfinite(vdd).all()
+
+
+def test_ic2d_totals_and_err_norms_match_host_formulas(engine, meshes):
+    """lpmx_ic2d_totals / lpmx_ic2d_solver_totals (Incompressible2D::total_*, lpm_incompressible2d_impl.hpp:91-137)
+    and lpmx_err_norms (ErrNorms, lpm_error_impl.hpp:59-108) against their definitions in numpy."""
+    from lpm_b200.api import IC2DSolver
+    m = meshes("icos", 4)
+    f = gallery.RossbyHaurwitz54()
+    f.set_stationary_wave_speed()
+    fz = f(m.face_xyz)
+    leaf = m.face_mask == 0
+    rng = np.random.default_rng(3)
+    u = rng.standard_normal((m.n_faces, 3))
+    tv, ke, ens = engine.ic2d_totals(fz, u, m.face_area, m.face_mask)
+    a = m.face_area
+    assert abs(tv - (fz * a)[leaf].sum()) <= 1e-13 * np.abs(fz * a)[leaf].sum()
+    assert abs(ens - 0.5 * (fz ** 2 * a)[leaf].sum()) <= 1e-13 * ens
+    assert abs(ke - 0.5 * ((u ** 2).sum(axis=1) * a)[leaf].sum()) <= 1e-13 * ke
+    # scalar and vector error norms, both layouts
+    exact = rng.standard_normal(m.n_faces)
+    err = 1e-3 * rng.standard_normal(m.n_faces)
+    l1, l2, linf = engine.err_norms(err, exact, a)
+    assert np.isclose(l1, (np.abs(err) * a).sum() / (np.abs(exact) * a).sum(), rtol=1e-13)
+    assert np.isclose(l2, np.sqrt((err ** 2 * a).sum() / (exact ** 2 * a).sum()), rtol=1e-13)
+    assert linf == np.abs(err).max() / np.abs(exact).max()
+    ev, xv = 1e-3 * rng.standard_normal((m.n_faces, 3)), rng.standard_normal((m.n_faces, 3))
+    em, xm = np.linalg.norm(ev, axis=1), np.linalg.norm(xv, axis=1)
+    for layout, args in ((0, (ev, xv)), (1, (np.ascontiguousarray(ev.T), np.ascontiguousarray(xv.T)))):
+        l1, l2, linf = engine.err_norms(*args, a, layout=layout)
+        assert np.isclose(l1, (em * a).sum() / (xm * a).sum(), rtol=1e-13)
+        assert np.isclose(l2, np.sqrt((em ** 2 * a).sum() / (xm ** 2 * a).sum()), rtol=1e-13)
+        assert np.isclose(linf, em.max() / xm.max(), rtol=1e-15)
+    # resident solver: totals of the advected state without moving the fields
+    vz = f(m.vert_xyz)
+    s = IC2DSolver(engine, m.n_verts, m.n_faces, eps=0.0)
+    s.set_state(m.vert_xyz, vz, None, m.face_xyz, fz, None, np.ascontiguousarray(a), np.ascontiguousarray(m.face_mask))
+    s.init_direct_sums()
+    tv0, ke0, ens0 = s.totals()
+    s.advance(0.01, 2 * np.pi, 3)
+    tv1, ke1, ens1 = s.totals()
+    au, az = np.empty((m.n_faces, 3)), np.empty(m.n_faces)
+    s.get_state(active_vel=au, active_vort=az)
+    assert np.isclose(ke1, 0.5 * ((au ** 2).sum(axis=1) * a)[leaf].sum(), rtol=1e-13)
+    assert np.isclose(ens1, 0.5 * (az ** 2 * a)[leaf].sum(), rtol=1e-13)
+    assert abs(ke1 - ke0) / ke0 < 1e-2 and abs(ens1 - ens0) / ens0 < 1e-3  # near-conservation over 3 steps
+    s.close()

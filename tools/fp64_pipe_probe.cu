@@ -170,6 +170,20 @@ __global__ void __launch_bounds__(256) k_mix(double* out, double a, double b) {
   if (s == 123.456) out[0] = s;
 }
 
+// accuracy of the MUFU.RCP64H seed: max over d of |1 - d * rcp.approx.ftz.f64(d)|
+__global__ void k_rcp_acc(double* out, double lo, double ratio, int n) {
+  double worst = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double d = lo * pow(ratio, (double)i);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    const double e = fabs(fma(-d, r, 1.0));
+    worst = fmax(worst, e);
+  }
+  for (int o = 16; o > 0; o >>= 1) worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+  if ((threadIdx.x & 31) == 0) atomicMax((unsigned long long*)out, (unsigned long long)__double_as_longlong(worst));
+}
+
 template <class F>
 static double time_ms(F launch) {
   cudaEvent_t e0, e1;
@@ -193,6 +207,14 @@ int main() {
   const double clk = clk_khz * 1e3;
   printf("%s: %d SMs, %.0f MHz\n", p.name, sms, clk * 1e-6);
   double *out, *in; CK(cudaMalloc(&out, 64)); CK(cudaMalloc(&in, 4096)); CK(cudaMemset(in, 0, 4096));
+  {
+    CK(cudaMemset(out, 0, 8));
+    const int n = 1 << 24;
+    k_rcp_acc<<<sms * 4, 256>>>(out, 1e-12, pow(4e12, 1.0 / n), n);
+    double worst = 0;
+    CK(cudaMemcpy(&worst, out, 8, cudaMemcpyDeviceToHost));
+    printf("MUFU.RCP64H seed: max |1 - d*r0| over %d log-spaced d in [1e-12, 4] = %.3e = 2^%.2f\n", n, worst, log2(worst));
+  }
   for (int bps : {1, 2, 4}) {   // blocks of 256 threads per SM -> 2, 4, 8 warps per scheduler
     const int blocks = sms * bps; const double warps = (double)blocks * 8;
     auto rep = [&](const char* name, double ms, double dfma_per_thread_iter, double other) {
