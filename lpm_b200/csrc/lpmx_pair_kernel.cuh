@@ -6,13 +6,6 @@
 
 #include "lpmx_internal.h"
 
-#ifndef LPMX_STAGE_MAJOR
-#define LPMX_STAGE_MAJOR 1
-#endif
-#ifndef LPMX_SEED_LO
-#define LPMX_SEED_LO 0
-#endif
-
 namespace lpmx {
 
 // ------------------------------------------------------------------------------------------------
@@ -56,23 +49,6 @@ __device__ __forceinline__ double rcp_seed(double d) {
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
   return r;
 }
-// Same seed, but the low word is taken from `dead` (a value the caller no longer needs) instead of being
-// zeroed: MUFU.RCP64H writes only the high word, so ptxas can drop the MOV that zeroes the low one by placing
-// the seed in `dead`'s register pair.  The low word perturbs the seed by < 2^-20 relative, which the cubic
-// Newton step absorbs (|e| < 2^-19 -> |e|^3 < 2^-57).
-__device__ __forceinline__ double rcp_seed_lo(double d, double dead) {
-  double r;
-  asm("{\n"
-      ".reg .f64 t;\n"
-      ".reg .b32 lo, hi, glo, ghi;\n"
-      "rcp.approx.ftz.f64 t, %1;\n"
-      "mov.b64 {lo, hi}, t;\n"
-      "mov.b64 {glo, ghi}, %2;\n"
-      "mov.b64 %0, {glo, hi};\n"
-      "}" : "=d"(r) : "d"(d), "d"(dead));
-  return r;
-}
-
 // ------------------------------------------------------------------------------------------------
 // log(d) for the stream-function kinds.  d = kappa - x.y is a positive normal double (0 < d <= ~2), so the
 // general-purpose libdevice log (special cases, denormals, ~45 FP64-pipe instructions) is replaced by a
@@ -141,20 +117,13 @@ struct Pair;
 template <bool CHECK>
 struct Pair<kVel, CHECK> {
   static constexpr int NLOAD = 6;  // doubles of the record this kind reads
-  // `car` carries a dead value (the previous pair's r of this accumulator slot) whose register pair hosts the
-  // next reciprocal seed (see rcp_seed_lo).
   __device__ __forceinline__ static void apply(const double* x, const double* /*kx*/, double kappa, const double* s,
-                                               int j, int self, double* acc, double& car, const double2* /*tbl*/) {
+                                               int j, int self, double* acc, const double2* /*tbl*/) {
     const double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
-#if LPMX_SEED_LO
-    const double r0 = rcp_seed_lo(d, car);
-#else
     const double r0 = rcp_seed(d);
-#endif
     const double e = fma(-d, r0, 1.0);
     const double p = fma(e, e, e);
     double r = fma(r0, p, r0);
-    car = r;
     if (CHECK) r = (j == self) ? 0.0 : r;
     acc[0] = fma(r, s[3], acc[0]);
     acc[1] = fma(r, s[4], acc[1]);
@@ -166,7 +135,7 @@ template <bool CHECK>
 struct Pair<kVelPsi, CHECK> {
   static constexpr int NLOAD = 8;
   __device__ __forceinline__ static void apply(const double* x, const double*, double kappa, const double* s, int j,
-                                               int self, double* acc, double& /*car*/, const double2* tbl) {
+                                               int self, double* acc, const double2* tbl) {
     double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
     double gam = s[6];
     if (CHECK) {
@@ -190,7 +159,7 @@ template <bool CHECK>
 struct Pair<kPsi, CHECK> {
   static constexpr int NLOAD = 8;
   __device__ __forceinline__ static void apply(const double* x, const double*, double kappa, const double* s, int j,
-                                               int self, double* acc, double& /*car*/, const double2* tbl) {
+                                               int self, double* acc, const double2* tbl) {
     double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
     double gam = s[6];
     if (CHECK) {
@@ -210,7 +179,7 @@ template <bool CHECK>
 struct Pair<kSwe, CHECK> {
   static constexpr int NLOAD = 6;
   __device__ __forceinline__ static void apply(const double* x, const double* kx, double kappa, const double* s,
-                                               int j, int self, double* acc, double& /*car*/, const double2* /*tbl*/) {
+                                               int j, int self, double* acc, const double2* /*tbl*/) {
     double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
     double gz = s[3], gs = s[4];
     if (CHECK) {
@@ -254,49 +223,12 @@ struct Pair<kSwe, CHECK> {
   }
 };
 
-// kVel, stage-major over the T targets of a thread.  The FP64 pipe reads one 64-bit register operand per cycle, so a
-// DFMA with three fresh register operands occupies it for 3 cycles instead of 2 unless one of them comes from the
-// operand-reuse cache, which only holds the operand of the immediately preceding instruction.  Emitting each stage for
-// all T targets back to back makes the shared operand (the source's y_k or Gamma*y_k) the reused one
-// (tools/sass_reuse_stats.py, profiles/README.md).
-template <int T, bool CHECK>
-__device__ __forceinline__ void vel_source(const double (*x)[3], double kappa, const double* s, int j, const int* self,
-                                           double (*acc)[3]) {
-  double d[T], r[T];
-#pragma unroll
-  for (int t = 0; t < T; ++t) d[t] = fma(s[0], -x[t][0], kappa);
-#pragma unroll
-  for (int t = 0; t < T; ++t) d[t] = fma(s[1], -x[t][1], d[t]);
-#pragma unroll
-  for (int t = 0; t < T; ++t) d[t] = fma(s[2], -x[t][2], d[t]);
-#pragma unroll
-  for (int t = 0; t < T; ++t) r[t] = rcp_seed(d[t]);
-#pragma unroll
-  for (int t = 0; t < T; ++t) d[t] = fma(-d[t], r[t], 1.0);   // e
-#pragma unroll
-  for (int t = 0; t < T; ++t) d[t] = fma(d[t], d[t], d[t]);   // e + e^2
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    r[t] = fma(r[t], d[t], r[t]);
-    if (CHECK) r[t] = (j == self[t]) ? 0.0 : r[t];
-  }
-#pragma unroll
-  for (int k = 0; k < 3; ++k)
-#pragma unroll
-    for (int t = 0; t < T; ++t) acc[t][k] = fma(s[3 + k], r[t], acc[t][k]);
-}
-
 template <int KIND, int T, int UNROLL, bool CHECK>
 __device__ __forceinline__ void chunk_loop(const double (*x)[3], const double (*kx)[3], double kappa,
                                            const double* __restrict__ sp, int j0, const int* self,
                                            double (*acc)[kind_nacc(KIND)], const double2* tbl) {
   constexpr int REC = kind_rec(KIND);
   static_assert(kChunk % UNROLL == 0, "source-loop unroll must divide the chunk");
-  double car[UNROLL][T];
-#pragma unroll
-  for (int u = 0; u < UNROLL; ++u)
-#pragma unroll
-    for (int t = 0; t < T; ++t) car[u][t] = 0.0;
 #pragma unroll 1
   for (int jj = 0; jj < kChunk; jj += UNROLL) {
 #pragma unroll
@@ -311,14 +243,8 @@ __device__ __forceinline__ void chunk_loop(const double (*x)[3], const double (*
         s[2 * v] = t.x;
         s[2 * v + 1] = t.y;
       }
-#if LPMX_STAGE_MAJOR
-      if constexpr (KIND == kVel) {
-        vel_source<T, CHECK>(x, kappa, s, j0 + j, self, acc);
-        continue;
-      }
-#endif
 #pragma unroll
-      for (int t = 0; t < T; ++t) Pair<KIND, CHECK>::apply(x[t], kx[t], kappa, s, j0 + j, self[t], acc[t], car[u][t], tbl);
+      for (int t = 0; t < T; ++t) Pair<KIND, CHECK>::apply(x[t], kx[t], kappa, s, j0 + j, self[t], acc[t], tbl);
     }
   }
 }

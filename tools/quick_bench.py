@@ -19,11 +19,12 @@ for seed, depth in [("icos", 4), ("cubed", 6), ("cubed", 7), ("icos", 7), ("icos
     s.init_velocity(); e.sync()
     _, inter = s.interactions_per_eval()
     nsteps = 3 if depth < 8 else 1
-    s.advance(0.01, 2 * np.pi, 1); e.sync()
+    dt = 0.025 * m.appx_mesh_size() / 0.09045016
+    s.advance(dt, 2 * np.pi, 1); e.sync()
     with torch.cuda.stream(stream):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
-        s.advance(0.01, 2 * np.pi, nsteps)
+        s.advance(dt, 2 * np.pi, nsteps)
         b.record(stream)
     e.sync()
     ms = a.elapsed_time(b) / nsteps

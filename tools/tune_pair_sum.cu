@@ -338,7 +338,7 @@ int main(int argc, char** argv) {
     RUNK(kPsi, 4, 16, 1, 2);
   }
 probes:
-  printf("LPMX_SEED_LO=%d\n", LPMX_SEED_LO);
+
   RUN(6, 8, 1, 2);
   RUN(6, 8, 1, 4);
   RUN(6, 12, 1, 2);
