@@ -56,6 +56,7 @@ typedef struct lpmx_mesh_s* lpmx_mesh_t;
 typedef struct lpmx_bve_solver_s* lpmx_bve_solver_t;
 typedef struct lpmx_ic2d_solver_s* lpmx_ic2d_solver_t;
 typedef struct lpmx_swe_solver_s* lpmx_swe_solver_t;
+typedef struct lpmx_plane_solver_s* lpmx_plane_solver_t;
 
 const char* lpmx_version_string(void);
 const char* lpmx_error_name(int code);
@@ -333,6 +334,87 @@ int lpmx_swe_solver_set_laplacian(lpmx_swe_solver_t s, const double* passive_lap
 int lpmx_swe_solver_init_direct_sums(lpmx_swe_solver_t s, int do_velocity);
 int lpmx_swe_solver_advance(lpmx_swe_solver_t s, double dt, double Omega, double g, lpmx_swe_laplacian_fn laplacian,
                             void* user, int n_steps);
+
+/* ------------------------------------------------------------------------------------------
+ * Planar problems (PlaneGeometry): Real*[2] views.  LPMX_LAYOUT_RIGHT is x[i*2+k], LPMX_LAYOUT_LEFT is x[k*ld+i].
+ * Coriolis is CoriolisBetaPlane(f0, beta) (src/lpm_coriolis.hpp:93-148): f = f0 + beta y.
+ * ------------------------------------------------------------------------------------------ */
+
+/* bottom topography functors of src/lpm_surface_gallery.hpp usable in the plane */
+#define LPMX_TOPO_ZERO 0                     /* ZeroFunctor (:92-102) */
+#define LPMX_TOPO_PLANAR_GAUSSIAN_MOUNTAIN 1 /* PlanarGaussianMountain (:41-61): 0.8 exp(-5 |x|^2) */
+
+/* Incompressible2DPassiveSums<PlaneGeometry> (targets_are_sources=0, src/lpm_incompressible2d_kernels.hpp:144-193)
+ * and Incompressible2DActiveSums<PlaneGeometry> (:201-246; the self term is skipped only when |eps| < zero_tol),
+ * with Incompressible2DKernels<PlaneGeometry>::kernel_vals (:55-85).  out_vel: Real*[2] in the targets' layout;
+ * out_psi may be NULL. */
+int lpmx_ic2d_plane_sums(lpmx_handle_t h, const double* tgt_xy, int tgt_layout, long tgt_ld, int n_tgt,
+                         const double* src_xy, int src_layout, long src_ld, const double* src_vort,
+                         const double* src_area, const unsigned char* src_mask, int n_src, double eps,
+                         int targets_are_sources, double* out_vel, double* out_psi);
+
+/* Incompressible2DRK2<Seed>::advance_timestep_impl (src/lpm_incompressible2d_rk2_impl.hpp:75-172) for PlaneGeometry
+ * (examples/plane_colliding_dipoles.cpp:196), n_steps times, in place.  Arguments as lpmx_ic2d_rk2_step. */
+int lpmx_ic2d_plane_rk2_step(lpmx_handle_t h, double dt, double f0, double beta, double eps, int n_passive,
+                             double* passive_xy, double* passive_vort, double* passive_vel, double* passive_psi,
+                             int n_active, double* active_xy, double* active_vort, double* active_vel,
+                             double* active_psi, const double* active_area, const unsigned char* active_mask,
+                             int layout, long passive_ld, long active_ld, int n_steps);
+
+/* The planar SWE<Seed> fields (src/lpm_swe.hpp:29-88).  passive = vertices, active = faces; xy and vel are Real*[2].
+ * Reference names: mesh.vertices.phys_crds, rel_vort_passive, div_passive, depth_passive, surf_passive,
+ * bottom_passive, velocity_passive, double_dot_passive, du1dx1_passive .. du2dx2_passive, surf_lap_passive,
+ * stream_fn_passive, potential_passive; the active ones likewise plus mesh.faces.area, mass_active, mesh.faces.mask. */
+typedef struct lpmx_plane_swe_passive_s {
+  double *xy, *vort, *div, *depth, *surf, *bottom, *vel, *ddot, *du1dx1, *du1dx2, *du2dx1, *du2dx2, *laps, *psi, *phi;
+} lpmx_plane_swe_passive_t;
+typedef struct lpmx_plane_swe_active_s {
+  double *xy, *vort, *div, *area, *mass, *depth, *surf, *bottom, *vel, *ddot, *du1dx1, *du1dx2, *du2dx1, *du2dx2, *laps,
+      *psi, *phi;
+  const unsigned char* mask;
+} lpmx_plane_swe_active_t;
+
+/* The nine direct-sum outputs of PlanarSWEVertexSums / PlanarSWEFaceSums (any pointer may be NULL) */
+typedef struct lpmx_plane_swe_sums_s {
+  double *vel, *ddot, *du1dx1, *du1dx2, *du2dx1, *du2dx2, *laps, *psi, *phi;
+} lpmx_plane_swe_sums_t;
+
+/* PlanarSWEVertexSums (targets_are_sources=0, src/lpm_swe_kernels.hpp:626-716) and PlanarSWEFaceSums (:787-870;
+ * the self term is skipped unless eps > 0) with PlanarSwePseDirectSumReducer (:522-571), planar_swe_sums_rhs_pse
+ * (:393-445) and pse::BivariateOrder8::laplacian (src/lpm_pse.hpp:66-73).  tgt_surf/src_surf are the surface heights
+ * the PSE Laplacian differences.  out->vel is written only if do_velocity != 0. */
+int lpmx_swe_plane_sums(lpmx_handle_t h, const double* tgt_xy, int tgt_layout, long tgt_ld, const double* tgt_surf,
+                        int n_tgt, const double* src_xy, int src_layout, long src_ld, const double* src_vort,
+                        const double* src_div, const double* src_area, const unsigned char* src_mask,
+                        const double* src_surf, int n_src, double eps, double pse_eps, int targets_are_sources,
+                        int do_velocity, const lpmx_plane_swe_sums_t* out);
+
+/* SWERK4<Seed, Topo>::advance_timestep (src/lpm_swe_rk4.hpp:88-96, src/lpm_swe_rk4_impl.hpp:203-445) for
+ * PlaneGeometry (examples/plane_gravity_wave.cpp:171-176), n_steps times, IN PLACE on the caller's arrays (host or
+ * device pointers).  On entry vel, ddot and laps must belong to the current state (SWE::init_direct_sums,
+ * src/lpm_swe_impl.hpp:401-422).  Required: xy, vort, depth (passive) / area, mass, mask (active), vel, ddot, laps;
+ * the rest default to zero when NULL on input and are skipped on output.  As coded in the reference, the
+ * fourth-stage position increment is never assigned (x4 = 0), so positions advance with
+ * x += (x1 + 0)/6 + (x2 + x3)/3; this is replicated. */
+int lpmx_swe_plane_rk4_step(lpmx_handle_t h, double dt, double f0, double beta, double g, double eps, double pse_eps,
+                            int topo, int n_passive, const lpmx_plane_swe_passive_t* passive, int n_active,
+                            const lpmx_plane_swe_active_t* active, int layout, long passive_ld, long active_ld,
+                            int n_steps);
+
+/* Persistent-state variant (state resident in HBM across calls) */
+int lpmx_plane_swe_solver_create(lpmx_handle_t h, int n_passive, int n_active, double eps, double pse_eps, int topo,
+                                 lpmx_plane_solver_t* s);
+int lpmx_plane_swe_solver_destroy(lpmx_plane_solver_t s);
+int lpmx_plane_swe_solver_set_state(lpmx_plane_solver_t s, const lpmx_plane_swe_passive_t* passive,
+                                    const lpmx_plane_swe_active_t* active, int layout, long passive_ld, long active_ld);
+/* any pointer inside the structs may be NULL (= not wanted) */
+int lpmx_plane_swe_solver_get_state(lpmx_plane_solver_t s, const lpmx_plane_swe_passive_t* passive,
+                                    const lpmx_plane_swe_active_t* active, int layout, long passive_ld, long active_ld);
+/* SWE::init_direct_sums(do_velocity) on the resident state */
+int lpmx_plane_swe_solver_init_direct_sums(lpmx_plane_solver_t s, int do_velocity);
+int lpmx_plane_swe_solver_advance(lpmx_plane_solver_t s, double dt, double f0, double beta, double g, int n_steps);
+/* pair interactions evaluated by one direct-sum evaluation of this solver: local (this rank) and global */
+int lpmx_plane_swe_solver_interactions_per_eval(lpmx_plane_solver_t s, double* local, double* global);
 
 #ifdef __cplusplus
 }

@@ -33,6 +33,28 @@ class SweActive(ctypes.Structure):
                                                "ddot", "laps", "mask")]
 
 
+PLANE_PASSIVE_FIELDS = ("xy", "vort", "div", "depth", "surf", "bottom", "vel", "ddot", "du1dx1", "du1dx2", "du2dx1",
+                        "du2dx2", "laps", "psi", "phi")
+PLANE_ACTIVE_FIELDS = ("xy", "vort", "div", "area", "mass", "depth", "surf", "bottom", "vel", "ddot", "du1dx1", "du1dx2",
+                       "du2dx1", "du2dx2", "laps", "psi", "phi")
+PLANE_SUM_FIELDS = ("vel", "ddot", "du1dx1", "du1dx2", "du2dx1", "du2dx2", "laps", "psi", "phi")
+
+
+class PlaneSwePassive(ctypes.Structure):
+    """lpmx_plane_swe_passive_t"""
+    _fields_ = [(n, ctypes.c_void_p) for n in PLANE_PASSIVE_FIELDS]
+
+
+class PlaneSweActive(ctypes.Structure):
+    """lpmx_plane_swe_active_t"""
+    _fields_ = [(n, ctypes.c_void_p) for n in PLANE_ACTIVE_FIELDS + ("mask",)]
+
+
+class PlaneSweSums(ctypes.Structure):
+    """lpmx_plane_swe_sums_t"""
+    _fields_ = [(n, ctypes.c_void_p) for n in PLANE_SUM_FIELDS]
+
+
 # lpmx_swe_laplacian_fn
 SWE_LAPLACIAN_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
@@ -123,6 +145,19 @@ def _declare(L):
         "lpmx_swe_solver_set_laplacian": [vp, vp, vp],
         "lpmx_swe_solver_init_direct_sums": [vp, i],
         "lpmx_swe_solver_advance": [vp, d, d, d, SWE_LAPLACIAN_FN, vp, i],
+        "lpmx_ic2d_plane_sums": [vp, vp, i, l, i, vp, i, l, vp, vp, vp, i, d, i, vp, vp],
+        "lpmx_ic2d_plane_rk2_step": [vp, d, d, d, d, i, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, i, l, l, i],
+        "lpmx_swe_plane_sums": [vp, vp, i, l, vp, i, vp, i, l, vp, vp, vp, vp, vp, i, d, d, i, i,
+                                ctypes.POINTER(PlaneSweSums)],
+        "lpmx_swe_plane_rk4_step": [vp, d, d, d, d, d, d, i, i, ctypes.POINTER(PlaneSwePassive), i,
+                                    ctypes.POINTER(PlaneSweActive), i, l, l, i],
+        "lpmx_plane_swe_solver_create": [vp, i, i, d, d, i, ctypes.POINTER(vp)],
+        "lpmx_plane_swe_solver_destroy": [vp],
+        "lpmx_plane_swe_solver_set_state": [vp, ctypes.POINTER(PlaneSwePassive), ctypes.POINTER(PlaneSweActive), i, l, l],
+        "lpmx_plane_swe_solver_get_state": [vp, ctypes.POINTER(PlaneSwePassive), ctypes.POINTER(PlaneSweActive), i, l, l],
+        "lpmx_plane_swe_solver_init_direct_sums": [vp, i],
+        "lpmx_plane_swe_solver_advance": [vp, d, d, d, d, i],
+        "lpmx_plane_swe_solver_interactions_per_eval": [vp, c_double_p, c_double_p],
     }
     for name, args in sig.items():
         f = getattr(L, name)

@@ -522,3 +522,145 @@ class SWESolver:
         cb = _laplacian_cb(laplacian)
         self.e._check(self.e._L.lpmx_swe_solver_advance(self._s, float(dt), float(Omega), float(g), cb, None, n_steps),
                       "lpmx_swe_solver_advance")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Planar problems (PlaneGeometry): Real*[2] views
+# ---------------------------------------------------------------------------------------------------------
+TOPO_ZERO, TOPO_PLANAR_GAUSSIAN_MOUNTAIN = 0, 1
+PLANE_PASSIVE_FIELDS, PLANE_ACTIVE_FIELDS = _lib.PLANE_PASSIVE_FIELDS, _lib.PLANE_ACTIVE_FIELDS
+PLANE_SUM_FIELDS = _lib.PLANE_SUM_FIELDS
+
+
+def _n2(x, layout):
+    return int(x.shape[0] if layout == LAYOUT_RIGHT else x.shape[1])
+
+
+def _empty_vec2(ref, n, layout):
+    shape = (n, 2) if layout == LAYOUT_RIGHT else (2, n)
+    if hasattr(ref, "data_ptr"):
+        import torch
+        return torch.empty(shape, dtype=torch.float64, device=ref.device)
+    return np.empty(shape, dtype=np.float64)
+
+
+def ic2d_plane_sums(engine, tgt_xy, src_xy, src_vort, src_area, src_mask, eps=0.0, targets_are_sources=False,
+                    with_psi=True, layout=LAYOUT_RIGHT):
+    """Incompressible2DPassiveSums<PlaneGeometry> (targets_are_sources=False) / ActiveSums (True) -- lpmx_ic2d_plane_sums."""
+    src_xy, src_vort, src_area, src_mask = _f64(src_xy), _f64(src_vort), _f64(src_area), _u8(src_mask)
+    n_src = _n2(src_xy, layout)
+    tgt_xy = None if targets_are_sources else _f64(tgt_xy)
+    n_tgt = n_src if targets_are_sources else _n2(tgt_xy, layout)
+    vel = _empty_vec2(src_xy, n_tgt, layout)
+    psi = _empty_like_scalar(src_xy, n_tgt) if with_psi else None
+    engine._check(engine._L.lpmx_ic2d_plane_sums(engine._h, _ptr(tgt_xy), layout, n_tgt, n_tgt, _ptr(src_xy), layout, n_src,
+                                                 _ptr(src_vort), _ptr(src_area), _ptr(src_mask), n_src, float(eps),
+                                                 int(bool(targets_are_sources)), _ptr(vel), _ptr(psi)),
+                  "lpmx_ic2d_plane_sums")
+    return vel, psi
+
+
+def ic2d_plane_rk2_step(engine, dt, f0, beta, eps, passive_xy, passive_vort, passive_vel, passive_psi, active_xy,
+                        active_vort, active_vel, active_psi, active_area, active_mask, n_steps=1, layout=LAYOUT_RIGHT):
+    """Incompressible2DRK2::advance_timestep_impl in the plane, n_steps times, in place -- lpmx_ic2d_plane_rk2_step."""
+    np_, na = _n2(passive_xy, layout), _n2(active_xy, layout)
+    engine._check(engine._L.lpmx_ic2d_plane_rk2_step(engine._h, float(dt), float(f0), float(beta), float(eps), np_,
+                                                     _ptr(passive_xy), _ptr(passive_vort), _ptr(passive_vel),
+                                                     _ptr(passive_psi), na, _ptr(active_xy), _ptr(active_vort),
+                                                     _ptr(active_vel), _ptr(active_psi), _ptr(active_area),
+                                                     _ptr(active_mask), layout, np_, na, n_steps),
+                  "lpmx_ic2d_plane_rk2_step")
+
+
+def swe_plane_sums(engine, tgt_xy, tgt_surf, src_xy, src_vort, src_div, src_area, src_mask, src_surf, eps, pse_eps,
+                   targets_are_sources=False, do_velocity=True, layout=LAYOUT_RIGHT):
+    """PlanarSWEVertexSums / PlanarSWEFaceSums -- lpmx_swe_plane_sums.  Returns a dict keyed by PLANE_SUM_FIELDS."""
+    src_xy, src_vort, src_div, src_area, src_surf = map(_f64, (src_xy, src_vort, src_div, src_area, src_surf))
+    src_mask = _u8(src_mask)
+    n_src = _n2(src_xy, layout)
+    if targets_are_sources:
+        tgt_xy, tgt_surf, n_tgt = None, None, n_src
+    else:
+        tgt_xy, tgt_surf = _f64(tgt_xy), _f64(tgt_surf)
+        n_tgt = _n2(tgt_xy, layout)
+    out = {k: _empty_like_scalar(src_xy, n_tgt) for k in PLANE_SUM_FIELDS if k != "vel"}
+    out["vel"] = _empty_vec2(src_xy, n_tgt, layout) if do_velocity else None
+    S = _lib.PlaneSweSums()
+    for k in PLANE_SUM_FIELDS:
+        setattr(S, k, None if out[k] is None else _ptr(out[k]))
+    engine._check(engine._L.lpmx_swe_plane_sums(engine._h, _ptr(tgt_xy), layout, n_tgt, _ptr(tgt_surf), n_tgt, _ptr(src_xy),
+                                                layout, n_src, _ptr(src_vort), _ptr(src_div), _ptr(src_area),
+                                                _ptr(src_mask), _ptr(src_surf), n_src, float(eps), float(pse_eps),
+                                                int(bool(targets_are_sources)), int(bool(do_velocity)), ctypes.byref(S)),
+                  "lpmx_swe_plane_sums")
+    return out
+
+
+def _plane_swe_structs(passive, active, mask):
+    P, A = _lib.PlaneSwePassive(), _lib.PlaneSweActive()
+    for k in PLANE_PASSIVE_FIELDS:
+        a = passive.get(k)
+        setattr(P, k, None if a is None else _ptr(a))
+    for k in PLANE_ACTIVE_FIELDS:
+        a = active.get(k)
+        setattr(A, k, None if a is None else _ptr(a))
+    A.mask = None if mask is None else _ptr(mask)
+    return P, A
+
+
+def swe_plane_rk4_step(engine, dt, f0, beta, g, eps, pse_eps, topo, passive, active, mask, n_steps=1,
+                       layout=LAYOUT_RIGHT):
+    """SWERK4::advance_timestep in the plane, n_steps times, in place on the arrays in the dicts (keys
+    PLANE_PASSIVE_FIELDS / PLANE_ACTIVE_FIELDS; float64, C-contiguous) -- lpmx_swe_plane_rk4_step."""
+    nv, nf = _n2(passive["xy"], layout), _n2(active["xy"], layout)
+    P, A = _plane_swe_structs(passive, active, mask)
+    engine._check(engine._L.lpmx_swe_plane_rk4_step(engine._h, float(dt), float(f0), float(beta), float(g), float(eps),
+                                                    float(pse_eps), int(topo), nv, ctypes.byref(P), nf, ctypes.byref(A),
+                                                    layout, nv, nf, n_steps), "lpmx_swe_plane_rk4_step")
+
+
+class PlaneSWESolver:
+    """Device-resident planar SWE<Seed> fields + SWERK4 (lpmx_plane_swe_solver_*)."""
+
+    def __init__(self, engine, n_passive, n_active, eps, pse_eps, topo=TOPO_ZERO):
+        self.e = engine
+        self.np_, self.na = n_passive, n_active
+        s = ctypes.c_void_p()
+        engine._check(engine._L.lpmx_plane_swe_solver_create(engine._h, n_passive, n_active, float(eps), float(pse_eps),
+                                                             int(topo), ctypes.byref(s)), "lpmx_plane_swe_solver_create")
+        self._s = s
+
+    def close(self):
+        if getattr(self, "_s", None) and getattr(self.e, "_h", None):
+            self.e._L.lpmx_plane_swe_solver_destroy(self._s)
+        self._s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_state(self, passive, active, mask, layout=LAYOUT_RIGHT):
+        P, A = _plane_swe_structs(passive, active, mask)
+        self.e._check(self.e._L.lpmx_plane_swe_solver_set_state(self._s, ctypes.byref(P), ctypes.byref(A), layout,
+                                                                self.np_, self.na), "lpmx_plane_swe_solver_set_state")
+
+    def get_state(self, passive, active, layout=LAYOUT_RIGHT):
+        P, A = _plane_swe_structs(passive, active, None)
+        self.e._check(self.e._L.lpmx_plane_swe_solver_get_state(self._s, ctypes.byref(P), ctypes.byref(A), layout,
+                                                                self.np_, self.na), "lpmx_plane_swe_solver_get_state")
+
+    def init_direct_sums(self, do_velocity=True):
+        self.e._check(self.e._L.lpmx_plane_swe_solver_init_direct_sums(self._s, int(bool(do_velocity))),
+                      "lpmx_plane_swe_solver_init_direct_sums")
+
+    def advance(self, dt, f0, beta, g, n_steps=1):
+        self.e._check(self.e._L.lpmx_plane_swe_solver_advance(self._s, float(dt), float(f0), float(beta), float(g),
+                                                              n_steps), "lpmx_plane_swe_solver_advance")
+
+    def interactions_per_eval(self):
+        a, b = ctypes.c_double(), ctypes.c_double()
+        self.e._check(self.e._L.lpmx_plane_swe_solver_interactions_per_eval(self._s, ctypes.byref(a), ctypes.byref(b)),
+                      "lpmx_plane_swe_solver_interactions_per_eval")
+        return a.value, b.value

@@ -181,6 +181,7 @@ int lpmx_destroy(lpmx_handle_t h) {
   if (h->cached_bve) lpmx_bve_solver_destroy(h->cached_bve);
   if (h->cached_ic2d) lpmx_ic2d_solver_destroy(h->cached_ic2d);
   if (h->cached_swe) lpmx_swe_solver_destroy(h->cached_swe);
+  if (h->cached_plane) lpmx_plane_swe_solver_destroy(h->cached_plane);
   for (auto& kv : h->bufs)
     if (kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : h->pinned)

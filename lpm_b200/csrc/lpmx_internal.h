@@ -25,13 +25,22 @@ enum PairKind : int {
   kVelPsi = 1,  // M and   P = sum Gamma log d                    (IC2D velocity + stream function)
   kPsi = 2,     // P only                                         (BVE stream function)
   kSwe = 3,     // Mz, Ms, G[9]                                   (spherical SWE 12-tuple)
+  kPlaneVelPsi = 4,  // u0, u1, sum G log a                       (planar IC2D velocity + stream function)
+  kPlaneSwe = 5,     // u0, u1, du[4], lap, sum Gz log a, sum Gs log a   (planar SWE 9-tuple with the PSE Laplacian)
 };
-constexpr int kind_nacc(int k) { return k == kVel ? 3 : k == kVelPsi ? 4 : k == kPsi ? 1 : 15; }
+constexpr int kind_nacc(int k) {
+  return k == kVel ? 3 : k == kVelPsi ? 4 : k == kPsi ? 1 : k == kSwe ? 15 : k == kPlaneVelPsi ? 3 : 9;
+}
 // doubles per packed source record:
 //   BVE / IC2D kinds  {y0, y1, y2, G*y0, G*y1, G*y2, G, 0}   (G = -zeta*A/(4 pi); 64 bytes)
 //   SWE               {y0, y1, y2, Gz, Gs, 0}                 (48 bytes)
+//   planar IC2D       {y0, y1, G, 0}                          (G = zeta*A/(2 pi); 32 bytes)
+//   planar SWE        {y0, y1, Gz, Gs, s, A/(pi pse_eps^2)}   (Gz = zeta*A/(2 pi), Gs = sigma*A/(2 pi); 48 bytes)
 constexpr int kBveRec = 8;
-constexpr int kind_rec(int k) { return k == kSwe ? 6 : kBveRec; }
+constexpr int kPlaneIc2dRec = 4;
+constexpr int kPlaneSweRec = 6;
+constexpr int kind_rec(int k) { return k == kSwe ? 6 : k == kPlaneVelPsi ? kPlaneIc2dRec : k == kPlaneSwe ? kPlaneSweRec : kBveRec; }
+constexpr bool kind_is_plane(int k) { return k == kPlaneVelPsi || k == kPlaneSwe; }
 
 // strided accessor for Real*[3] views: element (i,k) at p[i*si + k*sk]
 struct Vec3View {
@@ -97,6 +106,7 @@ struct lpmx_handle_s {
   lpmx_bve_solver_t cached_bve = nullptr;
   lpmx_ic2d_solver_t cached_ic2d = nullptr;
   lpmx_swe_solver_t cached_swe = nullptr;
+  lpmx_plane_solver_t cached_plane = nullptr;
 };
 
 namespace lpmx {
@@ -131,8 +141,10 @@ size_t plan_partials_bytes(const SumPlan& p);
 // tgt: target coordinates of the n_tgt targets of this launch (view indexed from 0);
 // self_idx: compact source index of each target's own particle or -1 (may be nullptr);
 // packed: n_src_pad records of kind_rec(kind) doubles; partials: plan_partials_bytes.
+// kappa: 1 + eps^2 on the sphere, eps^2 in the plane; aux: 1 / pse_eps^2 for kPlaneSwe (unused otherwise).
+// Planar kinds read target rows (x0, x1, surface height) through the same 3-row view.
 int launch_pair_sum(lpmx_handle_t h, const SumPlan& plan, Vec3View tgt, const int* self_idx, const double* packed,
-                    double kappa, double* partials);
+                    double kappa, double* partials, double aux = 0.0);
 
 // exclusive scan of !mask -> leaf_idx, returns number of unmasked sources (host sync)
 int scan_leaves(lpmx_handle_t h, const unsigned char* mask_dev, int n, int* leaf_idx_dev, int* n_leaves);

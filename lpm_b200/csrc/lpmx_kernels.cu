@@ -72,6 +72,8 @@ static const Shape kShapes[] = {
     LPMX_SHAPE(kPsi, 8, 8, 1, 2),     LPMX_SHAPE(kPsi, 4, 8, 2, 2),    LPMX_SHAPE(kPsi, 2, 8, 2, 2),
     LPMX_SHAPE(kPsi, 1, 8, 2, 2),
     LPMX_SHAPE(kSwe, 2, 8, 1, 2),     LPMX_SHAPE(kSwe, 1, 8, 1, 2),
+    LPMX_SHAPE(kPlaneVelPsi, 4, 8, 1, 2), LPMX_SHAPE(kPlaneVelPsi, 2, 8, 2, 2), LPMX_SHAPE(kPlaneVelPsi, 1, 8, 2, 2),
+    LPMX_SHAPE(kPlaneSwe, 2, 8, 1, 2),    LPMX_SHAPE(kPlaneSwe, 1, 8, 2, 2),
 };
 constexpr int kNumShapes = sizeof(kShapes) / sizeof(kShapes[0]);
 
@@ -125,7 +127,7 @@ size_t plan_partials_bytes(const SumPlan& p) {
 }
 
 int launch_pair_sum(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* self_idx, const double* packed,
-                    double kappa, double* partials) {
+                    double kappa, double* partials, double aux) {
   if (p.n_tgt == 0) return LPMX_OK;
   if (p.n_sc == 0) {
     // no sources: every partial sum is zero
@@ -142,6 +144,7 @@ int launch_pair_sum(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* 
   a.n_sc = p.n_sc;
   a.n_tgt_pad = p.n_tgt_pad;
   a.kappa = kappa;
+  a.aux = aux;
   if (!h->profile) return kShapes[p.shape].launch(h, p, a);
   if (h->prof_used == h->prof_events.size()) {
     cudaEvent_t e0, e1;

@@ -62,7 +62,7 @@ __device__ const double2 kLogTable[128] = {
 #include "log_table.inc"
 };
 
-__host__ __device__ constexpr bool kind_has_log(int k) { return k == kVelPsi || k == kPsi; }
+__host__ __device__ constexpr bool kind_has_log(int k) { return k == kVelPsi || k == kPsi || k == kPlaneVelPsi || k == kPlaneSwe; }
 
 __device__ __forceinline__ double fast_log(double d, const double2* __restrict__ tbl) {
   const int hi = __double2hiint(d);
@@ -82,6 +82,33 @@ __device__ __forceinline__ double fast_log(double d, const double2* __restrict__
   return fma(kd, 0.693147180559945309417232121458, cl.y) + l1p;
 }
 
+// exp(-x) for x >= 0 (the PSE kernel, lpm_pse.hpp:66-73): k = rint(-x log2 e) by the magic-number add, r = -x - k ln2
+// in two FMAs (hi/lo split of ln2), |r| <= ln2/2, degree-12 Taylor polynomial (|r|^13/13! < 2e-16), scale by 2^k
+// with an integer add on the exponent field.  x is clamped to 700 (exp(-700) ~ 1e-304 stays normal; the PSE term
+// it multiplies is below any tolerance there).  17 FP64-pipe instructions; relative error < 4e-16.
+__device__ __forceinline__ double fast_exp_neg(double x) {
+  x = fmin(x, 700.0);
+  const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+  const double t = fma(x, -1.4426950408889634074, kMagic);
+  const int k = __double2loint(t);
+  const double kf = t - kMagic;
+  double r = fma(kf, -6.93147180369123816490e-01, -x);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  double p = fma(r, 1.0 / 479001600.0, 1.0 / 39916800.0);
+  p = fma(p, r, 1.0 / 3628800.0);
+  p = fma(p, r, 1.0 / 362880.0);
+  p = fma(p, r, 1.0 / 40320.0);
+  p = fma(p, r, 1.0 / 5040.0);
+  p = fma(p, r, 1.0 / 720.0);
+  p = fma(p, r, 1.0 / 120.0);
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernel arguments
 // ------------------------------------------------------------------------------------------------
@@ -94,7 +121,8 @@ struct SumArgs {
   int n_tb;
   int n_sc;
   long n_tgt_pad;
-  double kappa;  // 1 + eps^2
+  double kappa;  // 1 + eps^2 (sphere) / eps^2 (plane)
+  double aux;    // 1 / pse_eps^2 (kPlaneSwe)
 };
 
 // dynamic shared memory of one CTA: source ring + full/empty barriers (+ the log table)
@@ -117,7 +145,7 @@ struct Pair;
 template <bool CHECK>
 struct Pair<kVel, CHECK> {
   static constexpr int NLOAD = 6;  // doubles of the record this kind reads
-  __device__ __forceinline__ static void apply(const double* x, const double* /*kx*/, double kappa, const double* s,
+  __device__ __forceinline__ static void apply(const double* x, const double* /*kx*/, double kappa, double /*aux*/, const double* s,
                                                int j, int self, double* acc, const double2* /*tbl*/) {
     const double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
     const double r0 = rcp_seed(d);
@@ -134,7 +162,7 @@ struct Pair<kVel, CHECK> {
 template <bool CHECK>
 struct Pair<kVelPsi, CHECK> {
   static constexpr int NLOAD = 8;
-  __device__ __forceinline__ static void apply(const double* x, const double*, double kappa, const double* s, int j,
+  __device__ __forceinline__ static void apply(const double* x, const double*, double kappa, double, const double* s, int j,
                                                int self, double* acc, const double2* tbl) {
     double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
     double gam = s[6];
@@ -158,7 +186,7 @@ struct Pair<kVelPsi, CHECK> {
 template <bool CHECK>
 struct Pair<kPsi, CHECK> {
   static constexpr int NLOAD = 8;
-  __device__ __forceinline__ static void apply(const double* x, const double*, double kappa, const double* s, int j,
+  __device__ __forceinline__ static void apply(const double* x, const double*, double kappa, double, const double* s, int j,
                                                int self, double* acc, const double2* tbl) {
     double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
     double gam = s[6];
@@ -178,7 +206,7 @@ struct Pair<kPsi, CHECK> {
 template <bool CHECK>
 struct Pair<kSwe, CHECK> {
   static constexpr int NLOAD = 6;
-  __device__ __forceinline__ static void apply(const double* x, const double* kx, double kappa, const double* s,
+  __device__ __forceinline__ static void apply(const double* x, const double* kx, double kappa, double, const double* s,
                                                int j, int self, double* acc, const double2* /*tbl*/) {
     double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
     double gz = s[3], gs = s[4];
@@ -223,8 +251,94 @@ struct Pair<kSwe, CHECK> {
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// Planar kinds.  x = {x0, x1, surface height of the target}; kappa = eps^2.  The difference
+// x - y is formed per pair (pulling the target out of the sum would cancel digits for targets far from the origin).
+// ------------------------------------------------------------------------------------------------
+
+// Incompressible2DKernels<PlaneGeometry>::kernel_vals (lpm_incompressible2d_kernels.hpp:70-84) with the source
+// strength folded in: record {y0, y1, G, 0}, G = zeta A / (2 pi).  acc = {u0, u1, sum G log a}; psi = -acc[2] / 2.
+template <bool CHECK>
+struct Pair<kPlaneVelPsi, CHECK> {
+  static constexpr int NLOAD = 4;
+  __device__ __forceinline__ static void apply(const double* x, const double*, double kappa, double, const double* s,
+                                               int j, int self, double* acc, const double2* tbl) {
+    const double dx = x[0] - s[0], dy = x[1] - s[1];
+    double a = fma(dx, dx, fma(dy, dy, kappa));
+    double g = s[2];
+    if (CHECK) {
+      const bool me = (j == self);
+      a = me ? 1.0 : a;
+      g = me ? 0.0 : g;
+    }
+    const double r0 = rcp_seed(a);
+    const double e = fma(-a, r0, 1.0);
+    const double p = fma(e, e, e);
+    const double r = fma(r0, p, r0);
+    const double w = g * r;
+    acc[0] = fma(-dy, w, acc[0]);
+    acc[1] = fma(dx, w, acc[1]);
+    acc[2] = fma(g, fast_log(a, tbl), acc[2]);
+  }
+};
+
+// planar_swe_sums_rhs_pse (lpm_swe_kernels.hpp:393-445): record {y0, y1, Gz, Gs, s_j, Ap}, Gz = zeta A / (2 pi),
+// Gs = sigma A / (2 pi), Ap = A / (pi pse_eps^2).  With a = |x-y|^2 + eps^2, r = 1/a, wz = Gz r, ws = Gs r and
+// pA = 1 - 2 dx^2 r, pB = 2 dx dy r, pC = 1 - 2 dy^2 r the six velocity/gradient entries of the reference are
+//   u      = (-dy wz + dx ws,  dx wz + dy ws)
+//   du1dx1 =  wz pB + ws pA     du1dx2 = -wz pC - ws pB     du2dx1 = wz pA - ws pB     du2dx2 = -wz pB + ws pC
+// (same per-pair combinations as the reference, so no cancellation is introduced), and
+//   lap    = (s_j - s_i) Ap (40 (1 - q) + 10 q^2 - 2 q^3 / 3) exp(-q),  q = |x-y|^2 / pse_eps^2  (lpm_pse.hpp:66-73)
+//   psi, phi accumulate G log a; the finalize kernel applies the factor -1/2.
+// acc = {u0, u1, du1dx1, du1dx2, du2dx1, du2dx2, lap, sum Gz log a, sum Gs log a}.
+template <bool CHECK>
+struct Pair<kPlaneSwe, CHECK> {
+  static constexpr int NLOAD = 6;
+  __device__ __forceinline__ static void apply(const double* x, const double*, double kappa, double inv_pe2,
+                                               const double* s, int j, int self, double* acc, const double2* tbl) {
+    const double dx = x[0] - s[0], dy = x[1] - s[1];
+    const double a2 = dx * dx, c2 = dy * dy, b2 = dx * dy;
+    const double rsq = a2 + c2;
+    double a = rsq + kappa;
+    double gz = s[2], gs = s[3], ap = s[5];
+    if (CHECK) {
+      const bool me = (j == self);
+      a = me ? 1.0 : a;
+      gz = me ? 0.0 : gz;
+      gs = me ? 0.0 : gs;
+      ap = me ? 0.0 : ap;
+    }
+    const double r0 = rcp_seed(a);
+    const double e = fma(-a, r0, 1.0);
+    const double pp = fma(e, e, e);
+    const double r = fma(r0, pp, r0);
+    const double wz = gz * r, ws = gs * r;
+    acc[0] = fma(-dy, wz, acc[0]);
+    acc[0] = fma(dx, ws, acc[0]);
+    acc[1] = fma(dx, wz, acc[1]);
+    acc[1] = fma(dy, ws, acc[1]);
+    const double r2 = r + r;
+    const double pA = fma(-r2, a2, 1.0), pC = fma(-r2, c2, 1.0), pB = r2 * b2;
+    acc[2] = fma(wz, pB, acc[2]);
+    acc[2] = fma(ws, pA, acc[2]);
+    acc[3] = fma(-wz, pC, acc[3]);
+    acc[3] = fma(-ws, pB, acc[3]);
+    acc[4] = fma(wz, pA, acc[4]);
+    acc[4] = fma(-ws, pB, acc[4]);
+    acc[5] = fma(-wz, pB, acc[5]);
+    acc[5] = fma(ws, pC, acc[5]);
+    const double lg = fast_log(a, tbl);
+    acc[7] = fma(gz, lg, acc[7]);
+    acc[8] = fma(gs, lg, acc[8]);
+    const double q = rsq * inv_pe2;
+    const double pre = fma(q, fma(q, fma(q, -2.0 / 3.0, 10.0), -40.0), 40.0);
+    const double t = (s[4] - x[2]) * ap;
+    acc[6] = fma(t * pre, fast_exp_neg(q), acc[6]);
+  }
+};
+
 template <int KIND, int T, int UNROLL, bool CHECK>
-__device__ __forceinline__ void chunk_loop(const double (*x)[3], const double (*kx)[3], double kappa,
+__device__ __forceinline__ void chunk_loop(const double (*x)[3], const double (*kx)[3], double kappa, double aux,
                                            const double* __restrict__ sp, int j0, const int* self,
                                            double (*acc)[kind_nacc(KIND)], const double2* tbl) {
   constexpr int REC = kind_rec(KIND);
@@ -244,7 +358,7 @@ __device__ __forceinline__ void chunk_loop(const double (*x)[3], const double (*
         s[2 * v + 1] = t.y;
       }
 #pragma unroll
-      for (int t = 0; t < T; ++t) Pair<KIND, CHECK>::apply(x[t], kx[t], kappa, s, j0 + j, self[t], acc[t], tbl);
+      for (int t = 0; t < T; ++t) Pair<KIND, CHECK>::apply(x[t], kx[t], kappa, aux, s, j0 + j, self[t], acc[t], tbl);
     }
   }
 }
@@ -349,9 +463,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) pair_sum_kernel(const Sum
 #pragma unroll
       for (int t = 0; t < T; ++t) hit |= (unsigned)(self[t] - j0) < (unsigned)kChunk;
       if (__any_sync(0xffffffffu, hit))
-        chunk_loop<KIND, T, C::UNROLL, true>(x, kx, a.kappa, sp, j0, self, acc, tbl);
+        chunk_loop<KIND, T, C::UNROLL, true>(x, kx, a.kappa, a.aux, sp, j0, self, acc, tbl);
       else
-        chunk_loop<KIND, T, C::UNROLL, false>(x, kx, a.kappa, sp, j0, self, acc, tbl);
+        chunk_loop<KIND, T, C::UNROLL, false>(x, kx, a.kappa, a.aux, sp, j0, self, acc, tbl);
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);
       if (++s == kStages) {

@@ -177,4 +177,126 @@ void ref_bve_vorticity_tendency(int n, double* dzeta, const double* vel, double 
   Kokkos::parallel_for(n, BVEVorticityTendency(dz, u, dt, Omega));
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Planar paths: the reference's PlaneGeometry functors, as shipped.
+//   lpm_incompressible2d_kernels.hpp  Incompressible2DPassiveSums / ActiveSums / Tendencies <PlaneGeometry>
+//   lpm_swe_kernels.hpp               planar_swe_sums_rhs_pse, PlanarSWEVertexSums, PlanarSWEFaceSums,
+//                                     SWEVorticityDivergence{Height,Area}Tendencies<PlaneGeometry>,
+//                                     SetSurfaceFromDepth / SetDepthAndSurfaceFromMassAndArea <PlaneGeometry, Topo>
+//   lpm_surface_gallery.hpp           PlanarGaussianMountain, ZeroFunctor
+// ---------------------------------------------------------------------------------------------------------
+using crd2 = PlaneGeometry::crd_view_type;
+using vec2 = PlaneGeometry::vec_view_type;
+namespace {
+inline crd2 wrap2(const double* p, int n) { return crd2(const_cast<double*>(p), n); }
+}
+
+void oracle_ic2d_plane_sums(int n_tgt, const double* tx, int n_src, const double* sx, const double* zeta,
+                            const double* area, const uint8_t* mask, double eps, int targets_are_sources, double* vel,
+                            double* psi) {
+  Mask am(mask, n_src);
+  crd2 ay = wrap2(sx, n_src);
+  scalar_view_type az = wrap1(zeta, n_src), aa = wrap1(area, n_src);
+  vec2 u = wrap2(vel, n_tgt);
+  std::vector<double> scratch;
+  if (!psi) {
+    scratch.resize(n_tgt > 0 ? n_tgt : 1);
+    psi = scratch.data();
+  }
+  scalar_view_type p = wrap1(psi, n_tgt);
+  if (targets_are_sources) {
+    Kokkos::parallel_for(Kokkos::TeamPolicy<>(n_src, Kokkos::AUTO()),
+                         Incompressible2DActiveSums<PlaneGeometry>(u, p, ay, az, aa, am.v, eps, n_src));
+  } else {
+    crd2 px = wrap2(tx, n_tgt);
+    Kokkos::parallel_for(Kokkos::TeamPolicy<>(n_tgt, Kokkos::AUTO()),
+                         Incompressible2DPassiveSums<PlaneGeometry>(u, p, px, ay, az, aa, am.v, eps, n_src));
+  }
+}
+
+// Incompressible2DTendencies<PlaneGeometry> with CoriolisBetaPlane(f0, beta)
+void ref_ic2d_plane_tendency(int n, double* dzeta, const double* vel, double f0, double beta) {
+  CoriolisBetaPlane cor(f0, beta);
+  Kokkos::parallel_for(n, Incompressible2DTendencies<PlaneGeometry>(wrap1(dzeta, n), wrap2(vel, n), cor));
+}
+
+void oracle_planar_swe_sums_rhs_pse(double* result, const double* tgt_x, const double* src_y, double src_zeta,
+                                    double src_sigma, double src_area, double src_s, double tgt_s, double eps,
+                                    double pse_eps) {
+  const auto r = planar_swe_sums_rhs_pse(tgt_x, src_y, src_zeta, src_sigma, src_area, src_s, tgt_s, eps, pse_eps);
+  for (int k = 0; k < 9; ++k) result[k] = r[k];
+}
+
+void oracle_swe_plane_sums(int n_tgt, const double* tx, const double* tsurf, int n_src, const double* sx,
+                           const double* zeta, const double* sigma, const double* area, const uint8_t* mask,
+                           const double* ssurf, double eps, double pse_eps, int targets_are_sources, int do_velocity,
+                           double* vel, double* ddot, double* du1dx1, double* du1dx2, double* du2dx1, double* du2dx2,
+                           double* laps, double* psi, double* phi) {
+  Mask fm(mask, n_src);
+  std::vector<double> scratch((size_t)8 * (n_tgt > 0 ? n_tgt : 1));
+  double* outs[8] = {ddot, du1dx1, du1dx2, du2dx1, du2dx2, laps, psi, phi};
+  scalar_view_type ov[8];
+  for (int k = 0; k < 8; ++k) ov[k] = wrap1(outs[k] ? outs[k] : scratch.data() + (size_t)k * n_tgt, n_tgt);
+  vec2 u = wrap2(vel, n_tgt);
+  crd2 fy = wrap2(sx, n_src);
+  scalar_view_type fz = wrap1(zeta, n_src), fs = wrap1(sigma, n_src), fa = wrap1(area, n_src), fsf = wrap1(ssurf, n_src);
+  if (targets_are_sources) {
+    Kokkos::parallel_for(Kokkos::TeamPolicy<>(n_src, Kokkos::AUTO()),
+                         PlanarSWEFaceSums(u, ov[0], ov[1], ov[2], ov[3], ov[4], ov[5], ov[6], ov[7], fy, fz, fs, fa,
+                                           fm.v, fsf, eps, pse_eps, n_src, do_velocity != 0));
+  } else {
+    Kokkos::parallel_for(Kokkos::TeamPolicy<>(n_tgt, Kokkos::AUTO()),
+                         PlanarSWEVertexSums(u, ov[0], ov[1], ov[2], ov[3], ov[4], ov[5], ov[6], ov[7], wrap2(tx, n_tgt),
+                                             wrap1(tsurf, n_tgt), fy, fz, fs, fa, fm.v, fsf, eps, pse_eps, n_src,
+                                             do_velocity != 0));
+  }
+}
+
+void oracle_swe_plane_tendencies(int n, int is_area, double* dzeta, double* dsigma, double* dthird, const double* x,
+                                 const double* u, const double* zeta, const double* sigma, const double* third,
+                                 const double* ddot, const double* laps, double f0, double beta, double g, double dt) {
+  scalar_view_type dz = wrap1(dzeta, n), ds = wrap1(dsigma, n), d3 = wrap1(dthird, n);
+  crd2 xv = wrap2(x, n);
+  vec2 uv = wrap2(u, n);
+  CoriolisBetaPlane cor(f0, beta);
+  if (is_area) {
+    Kokkos::parallel_for(n, SWEVorticityDivergenceAreaTendencies<PlaneGeometry>(
+                                dz, ds, d3, xv, uv, wrap1(zeta, n), wrap1(sigma, n), wrap1(third, n), wrap1(ddot, n),
+                                wrap1(laps, n), cor, g, dt));
+  } else {
+    Kokkos::parallel_for(n, SWEVorticityDivergenceHeightTendencies<PlaneGeometry>(
+                                dz, ds, d3, xv, uv, wrap1(zeta, n), wrap1(sigma, n), wrap1(third, n), wrap1(ddot, n),
+                                wrap1(laps, n), cor, g, dt));
+  }
+}
+
+double oracle_plane_topography(int topo, const double* xy) {
+  crd2 x = wrap2(xy, 1);
+  const auto x0 = Kokkos::subview(x, 0, Kokkos::ALL);
+  return topo == 1 ? PlanarGaussianMountain()(x0) : ZeroFunctor()(x0);
+}
+
+void oracle_swe_plane_set_surface_from_depth(int n, double* s, double* b, const double* x, const double* h, int topo) {
+  scalar_view_type sv = wrap1(s, n), bv = wrap1(b, n);
+  if (topo == 1)
+    Kokkos::parallel_for(n, SetSurfaceFromDepth<PlaneGeometry, PlanarGaussianMountain>(sv, bv, wrap2(x, n), wrap1(h, n),
+                                                                                       PlanarGaussianMountain()));
+  else
+    Kokkos::parallel_for(n, SetSurfaceFromDepth<PlaneGeometry, ZeroFunctor>(sv, bv, wrap2(x, n), wrap1(h, n),
+                                                                            ZeroFunctor()));
+}
+
+void oracle_swe_plane_set_depth_surface_from_mass_area(int n, double* h, double* s, double* b, const double* x,
+                                                       const double* m, const double* area, const uint8_t* mask,
+                                                       int topo) {
+  Mask fm(mask, n);
+  scalar_view_type hv = wrap1(h, n), sv = wrap1(s, n), bv = wrap1(b, n);
+  if (topo == 1)
+    Kokkos::parallel_for(n, SetDepthAndSurfaceFromMassAndArea<PlaneGeometry, PlanarGaussianMountain>(
+                                hv, sv, bv, wrap2(x, n), wrap1(m, n), wrap1(area, n), fm.v, PlanarGaussianMountain()));
+  else
+    Kokkos::parallel_for(n, SetDepthAndSurfaceFromMassAndArea<PlaneGeometry, ZeroFunctor>(
+                                hv, sv, bv, wrap2(x, n), wrap1(m, n), wrap1(area, n), fm.v, ZeroFunctor()));
+}
+
 }  // extern "C"
