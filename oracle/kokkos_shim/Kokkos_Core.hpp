@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <limits>
 #include <string>
 #include <type_traits>
 #include <utility>
@@ -365,6 +366,20 @@ void parallel_reduce(const std::string&, I n, const F& f, V& result) {
 template <class I, class F, class V, typename std::enable_if<std::is_integral<I>::value, int>::type = 0>
 void parallel_reduce(I n, const F& f, V& result) {
   parallel_reduce(std::string(), n, f, result);
+}
+
+
+// reducer objects passed by value as the last argument (Kokkos::Max<Real>(result)): sequential, identity-initialised
+template <class T>
+struct Max {
+  T& ref;
+  explicit Max(T& r) : ref(r) {}
+};
+template <class I, class F, class T, typename std::enable_if<std::is_integral<I>::value, int>::type = 0>
+void parallel_reduce(I n, const F& f, Max<T> red) {
+  T acc = std::numeric_limits<T>::lowest();
+  for (long j = 0; j < (long)n; ++j) f((int)j, acc);
+  red.ref = acc;
 }
 
 inline void initialize(int&, char**) {}

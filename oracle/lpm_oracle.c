@@ -517,3 +517,123 @@ void oracle_swe_rk2_step(double dt, double Omega, double g, double eps, int np, 
   }
   free(w);
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * FTLE diagnostic: ComputeFTLE<SeedType>::operator() for quadrilateral faces,
+ * sphere (mesh/lpm_ftle.hpp:86-220) and plane (:222-319), and get_max_ftle (:327-338).
+ * As coded: the "Cauchy-Green tensor" is the ELEMENTWISE product F_ij * F_ji (:70-79), not F^T F; on the
+ * sphere the face's physical coordinates are normalised IN PLACE (:98, a write to phys_crds_faces); the
+ * result is log(lambda_1) with no division by 2t (:218).
+ * ------------------------------------------------------------------------------------------- */
+
+/* north_pole_rotation_matrix (util/lpm_math.hpp:199-217) */
+static void north_pole_rotation_matrix(double* r, const double* x) {
+  const double cosy = sqrt(x[1] * x[1] + x[2] * x[2]);
+  const double siny = x[0];
+  const int on_x_axis = fabs(cosy) < ORACLE_ZERO_TOL;
+  const double cosx = on_x_axis ? 1 : x[2] / cosy;
+  const double sinx = on_x_axis ? 0 : x[1] / cosy;
+  r[0] = cosy, r[1] = -sinx * siny, r[2] = -cosx * siny;
+  r[3] = 0, r[4] = cosx, r[5] = -sinx;
+  r[6] = siny, r[7] = cosy * sinx, r[8] = cosx * cosy;
+}
+
+/* apply_3by3 (util/lpm_math.hpp:244-253) */
+static void apply_3by3(double* out, const double* m, const double* x) {
+  for (int i = 0; i < 3; ++i) {
+    out[i] = 0;
+    for (int j = 0; j < 3; ++j) out[i] += m[3 * i + j] * x[j];
+  }
+}
+
+/* set_flow_map_gradient + cauchy_green_tensor + two_by_two_real_eigenvalues (mesh/lpm_ftle.hpp:54-79,
+ * util/lpm_math.hpp:119-141); returns log(lambda_1) */
+static double ftle_from_edges(const double* e0rev_phys, const double* e1_phys, const double* xdir, const double* ydir,
+                              double dx0, double dy0) {
+  double F[4], cg[4];
+  F[0] = (e1_phys[0] * xdir[0] + e1_phys[1] * xdir[1]) / dx0;
+  F[1] = (e0rev_phys[0] * xdir[0] + e0rev_phys[1] * xdir[1]) / dx0;
+  F[2] = (e1_phys[0] * ydir[0] + e1_phys[1] * ydir[1]) / dy0;
+  F[3] = (e0rev_phys[0] * ydir[0] + e0rev_phys[1] * ydir[1]) / dy0;
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) cg[2 * i + j] = F[2 * i + j] * F[2 * j + i];
+  const double det = cg[0] * cg[3] - cg[1] * cg[2];
+  const double half_trace = 0.5 * (cg[0] + cg[3]);
+  double sqrt_arg = half_trace * half_trace - det;
+  if (fabs(sqrt_arg) < ORACLE_ZERO_TOL) sqrt_arg = 0;
+  return log(half_trace + sqrt(sqrt_arg));
+}
+
+/* geom: 0 = sphere (ndim 3), 1 = plane (ndim 2).  face_verts is [n_faces][4] row-major.  ftle(i) is written for
+ * leaves only (masked entries are left untouched, as in the reference). */
+void oracle_ftle(int geom, int n_verts, const double* vert_phys, const double* vert_ref, int n_faces, double* face_phys,
+                 const double* face_ref, const int* face_verts, const uint8_t* mask, double* ftle) {
+  (void)n_verts;
+#pragma omp parallel for schedule(static)
+  for (int f = 0; f < n_faces; ++f) {
+    if (mask[f]) continue;
+    if (geom == 0) {
+      const double* fa = face_ref + 3 * f;
+      double* fx = face_phys + 3 * f;
+      const double s = 1.0 / sqrt(fx[0] * fx[0] + fx[1] * fx[1] + fx[2] * fx[2]); /* SphereGeometry::normalize */
+      for (int k = 0; k < 3; ++k) fx[k] *= s;
+      double rr[9], rp[9], vp[4][3], vr[4][3];
+      north_pole_rotation_matrix(rr, fa);
+      north_pole_rotation_matrix(rp, fx);
+      for (int i = 0; i < 4; ++i) {
+        const int v = face_verts[4 * f + i];
+        apply_3by3(vr[i], rr, vert_ref + 3 * v);
+        apply_3by3(vp[i], rp, vert_phys + 3 * v);
+      }
+      /* "shift so that vertex 1 is the origin" (:148-153) is an in-place loop over i = 0..3: i == 1 zeroes vertex 1,
+       * so vertices 2 and 3 are then shifted by 0 (edge 1 below is vertex 2's tangent-plane position).  As coded. */
+      for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 2; ++j) {
+          vp[i][j] -= vp[1][j];
+          vr[i][j] -= vr[1][j];
+        }
+      const double e1r[2] = {vr[2][0] - vr[1][0], vr[2][1] - vr[1][1]};
+      const double e1p[2] = {vp[2][0] - vp[1][0], vp[2][1] - vp[1][1]};
+      const double dx0 = sqrt(e1r[0] * e1r[0] + e1r[1] * e1r[1]);
+      double xdir[2], ydir[2];
+      double xr = sqrt(e1r[0] * e1r[0] + e1r[1] * e1r[1]);
+      xdir[0] = e1r[0] / xr, xdir[1] = e1r[1] / xr;
+      const double e0r[2] = {vr[0][0], vr[0][1]}, e0p[2] = {vp[0][0], vp[0][1]};
+      const double dxy = xdir[0] * e0r[0] + xdir[1] * e0r[1];
+      ydir[0] = e0r[0] - dxy * xdir[0], ydir[1] = e0r[1] - dxy * xdir[1];
+      const double dy0 = sqrt(ydir[0] * ydir[0] + ydir[1] * ydir[1]);
+      const double yr = sqrt(ydir[0] * ydir[0] + ydir[1] * ydir[1]);
+      ydir[0] /= yr, ydir[1] /= yr;
+      ftle[f] = ftle_from_edges(e0p, e1p, xdir, ydir, dx0, dy0);
+    } else {
+      double vp[4][2], vr[4][2];
+      for (int i = 0; i < 4; ++i) {
+        const int v = face_verts[4 * f + i];
+        for (int j = 0; j < 2; ++j) vp[i][j] = vert_phys[2 * v + j], vr[i][j] = vert_ref[2 * v + j];
+      }
+      for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 2; ++j) {
+          vp[i][j] -= vp[1][j];
+          vr[i][j] -= vr[1][j];
+        }
+      const double e1r[2] = {vr[2][0] - vr[1][0], vr[2][1] - vr[1][1]};
+      const double e1p[2] = {vp[2][0] - vp[1][0], vp[2][1] - vp[1][1]};
+      const double dx0 = sqrt(e1r[0] * e1r[0] + e1r[1] * e1r[1]);
+      const double xl = sqrt(e1r[0] * e1r[0] + e1r[1] * e1r[1]);
+      const double xdir[2] = {e1r[0] / xl, e1r[1] / xl};
+      const double e0p[2] = {vp[0][0], vp[0][1]}, e0r[2] = {vr[0][0], vr[0][1]};
+      const double dy0 = sqrt(e0r[0] * e0r[0] + e0r[1] * e0r[1]);
+      const double yl = sqrt(e0r[0] * e0r[0] + e0r[1] * e0r[1]);
+      const double ydir[2] = {e0r[0] / yl, e0r[1] / yl};
+      ftle[f] = ftle_from_edges(e0p, e1p, xdir, ydir, dx0, dy0);
+    }
+  }
+}
+
+/* get_max_ftle (mesh/lpm_ftle.hpp:327-338): Kokkos::Max identity = lowest double */
+double oracle_max_ftle(int n_faces, const double* ftle, const uint8_t* mask) {
+  double m = -1.7976931348623157e308;
+  for (int i = 0; i < n_faces; ++i)
+    if (!mask[i]) m = m > ftle[i] ? m : ftle[i];
+  return m;
+}

@@ -11,6 +11,7 @@
 //   lpm_incompressible2d_kernels.hpp  Incompressible2DPassiveSums / ActiveSums <SphereGeometry>
 //   lpm_swe_kernels.hpp        kzeta_sphere, ksigma_sphere, grad_kzeta, grad_ksigma, SphereVertexSums,
 //                              SphereFaceSums
+//   mesh/lpm_ftle.hpp          ComputeFTLE<CubedSphereSeed>, ComputeFTLE<QuadRectSeed>, get_max_ftle
 #include <cstdint>
 #include <vector>
 #ifdef _OPENMP
@@ -22,6 +23,7 @@
 #include "lpm_incompressible2d_kernels.hpp"
 #include "lpm_swe_kernels.hpp"
 #include "lpm_surface_gallery.hpp"
+#include "mesh/lpm_ftle.hpp"
 
 using namespace Lpm;
 using crd = SphereGeometry::crd_view_type;
@@ -297,6 +299,29 @@ void oracle_swe_plane_set_depth_surface_from_mass_area(int n, double* h, double*
   else
     Kokkos::parallel_for(n, SetDepthAndSurfaceFromMassAndArea<PlaneGeometry, ZeroFunctor>(
                                 hv, sv, bv, wrap2(x, n), wrap1(m, n), wrap1(area, n), fm.v, ZeroFunctor()));
+}
+
+// ComputeFTLE (mesh/lpm_ftle.hpp) as launched by examples/sphere_rh54.cpp:308-316 / plane_colliding_dipoles.cpp:269-277
+void oracle_ftle(int geom, int n_verts, const double* vert_phys, const double* vert_ref, int n_faces, double* face_phys,
+                 const double* face_ref, const int* face_verts, const uint8_t* mask, double* ftle) {
+  Mask fm(mask, n_faces);
+  Kokkos::View<Index* [4]> fv(const_cast<int*>(face_verts), n_faces);
+  if (geom == 0) {
+    Kokkos::parallel_for(n_faces, ComputeFTLE<CubedSphereSeed>(wrap1(ftle, n_faces), wrap3(vert_phys, n_verts),
+                                                               wrap3(vert_ref, n_verts), wrap3(face_phys, n_faces),
+                                                               wrap3(face_ref, n_faces), fv, fm.v, 0.0));
+  } else {
+    using crd2d = PlaneGeometry::crd_view_type;
+    auto w2 = [](const double* p, int n) { return crd2d(const_cast<double*>(p), n); };
+    Kokkos::parallel_for(n_faces, ComputeFTLE<QuadRectSeed>(wrap1(ftle, n_faces), w2(vert_phys, n_verts),
+                                                            w2(vert_ref, n_verts), w2(face_phys, n_faces),
+                                                            w2(face_ref, n_faces), fv, fm.v, 0.0));
+  }
+}
+
+double oracle_max_ftle(int n_faces, const double* ftle, const uint8_t* mask) {
+  Mask fm(mask, n_faces);
+  return get_max_ftle(wrap1(ftle, n_faces), fm.v, n_faces);
 }
 
 }  // extern "C"
