@@ -43,10 +43,22 @@ int run_ic2d(const char* example, const Options& opt, Vorticity& vorticity, cons
   const Real vort0 = sphere->total_vorticity(), ke0 = sphere->total_kinetic_energy(), ens0 = sphere->total_enstrophy();
   auto solver = std::make_unique<Incompressible2DRK2<seed_type>>(dt, *sphere);
   Timer loop;
+  Real max_ftle = 0;
   for (Int t_idx = 0; t_idx < nsteps; ++t_idx) {
     sphere->advance_timestep(*solver);
+    if constexpr (std::is_same<typename seed_type::faceKind, QuadFace>::value) {
+      // examples/sphere_rh54.cpp:308-318 (the reference's FTLE is a static_assert for triangular panels)
+      ComputeFTLE<seed_type> ftle(sphere->ftle.view, sphere->mesh.vertices.phys_crds.view, sphere->ref_crds_passive.view,
+                                  sphere->mesh.faces.phys_crds.view, sphere->ref_crds_active.view, sphere->mesh.faces.verts,
+                                  sphere->mesh.faces.mask, sphere->t - sphere->t_ref);
+      ftle.apply(sphere->mesh.n_faces_host());
+      max_ftle = get_max_ftle(sphere->ftle.view, sphere->mesh.faces.mask, sphere->mesh.n_faces_host());
+      if (max_ftle != ftle.max_ftle && !(std::isnan(max_ftle) || std::isnan(ftle.max_ftle)))
+        throw std::runtime_error("device and host max_ftle disagree");
+    }
     per_step(*sphere, vorticity);
   }
+  std::printf("max_ftle = %.12e\n", max_ftle);
   const double loop_s = loop.seconds();
   const Real vort1 = sphere->total_vorticity(), ke1 = sphere->total_kinetic_energy(), ens1 = sphere->total_enstrophy();
   const Index nv = sphere->mesh.n_vertices_host(), nf = sphere->mesh.n_faces_host(), nl = sphere->mesh.faces.n_leaves_host();

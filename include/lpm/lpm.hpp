@@ -6,6 +6,7 @@
 #include "lpm_coords.hpp"
 #include "lpm_coriolis.hpp"
 #include "lpm_error.hpp"
+#include "lpm_ftle.hpp"
 #include "lpm_gallery.hpp"
 #include "lpm_geometry.hpp"
 #include "lpm_incompressible2d.hpp"

@@ -1,7 +1,8 @@
 // lpm/lpm_incompressible2d.hpp -- Incompressible2D<Seed> and Incompressible2DRK2<Seed> on the sphere.
 //   Incompressible2D<Seed>             src/lpm_incompressible2d.hpp:17-108, src/lpm_incompressible2d_impl.hpp
 //   Incompressible2DRK2<Seed>          src/lpm_incompressible2d_rk2.hpp:15-63, _rk2_impl.hpp:75-172
-// Remeshing, AMR and FTLE are outside the direct-sum hot path and are not provided.
+// Remeshing and AMR are outside the direct-sum hot path and are not provided; the FTLE field is
+// filled by ComputeFTLE (lpm_ftle.hpp), as in the reference's drivers.
 #ifndef LPM_SHIM_INCOMPRESSIBLE2D_HPP
 #define LPM_SHIM_INCOMPRESSIBLE2D_HPP
 

@@ -281,6 +281,21 @@ int lpmx_ic2d_solver_totals(lpmx_ic2d_solver_t s, double* total_vorticity, doubl
 int lpmx_err_norms(lpmx_handle_t h, int n, int ndim, const double* err, const double* exact, int layout, long ld,
                    const double* weight, double* l1, double* l2, double* linf);
 
+/* ComputeFTLE<SeedType> for quadrilateral faces (src/mesh/lpm_ftle.hpp:15-319; launched once per step by
+ * examples/sphere_rh54.cpp:308-316, sphere_gaussian_vortex.cpp:252-260, plane_colliding_dipoles.cpp:269-277) and
+ * get_max_ftle (:327-338).  geom selects the SphereGeometry (Real*[3]) or PlaneGeometry (Real*[2]) branch;
+ * `layout`/`*_ld` describe the four coordinate views, `verts_layout` the Index*[4] view faces.verts
+ * (LPMX_LAYOUT_RIGHT: v[f*4+k], LPMX_LAYOUT_LEFT: v[k*n_faces+f]).  As in the reference: ftle(f) = log(lambda_1) of
+ * the elementwise product F_ij F_ji (no division by 2t); entries of divided faces (mask != 0) are not written; on
+ * the sphere face_phys(f,:) of every leaf is normalised IN PLACE (:98), so face_phys is an in/out argument there;
+ * triangular faces are a static_assert in the reference (:19-20) and are not offered.  Host or device pointers;
+ * max_ftle may be NULL. */
+#define LPMX_GEOM_SPHERE 0
+#define LPMX_GEOM_PLANE 1
+int lpmx_ftle(lpmx_handle_t h, int geom, int n_verts, const double* vert_phys, const double* vert_ref, int layout,
+              long vert_ld, int n_faces, double* face_phys, const double* face_ref, long face_ld, const int* face_verts,
+              int verts_layout, const unsigned char* face_mask, double* ftle, double* max_ftle);
+
 /* ------------------------------------------------------------------------------------------
  * Spherical shallow water: SWE<Seed> fields + SWERK2 (src/lpm_swe.hpp:29-88, src/lpm_swe_rk2.hpp:15-39).
  * ------------------------------------------------------------------------------------------ */

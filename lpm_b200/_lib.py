@@ -136,6 +136,7 @@ def _declare(L):
         "lpmx_ic2d_totals": [vp, i, vp, vp, i, l, vp, vp, c_double_p, c_double_p, c_double_p],
         "lpmx_ic2d_solver_totals": [vp, c_double_p, c_double_p, c_double_p],
         "lpmx_err_norms": [vp, i, i, vp, vp, i, l, vp, c_double_p, c_double_p, c_double_p],
+        "lpmx_ftle": [vp, i, i, vp, vp, i, l, i, vp, vp, l, vp, i, vp, vp, c_double_p],
         "lpmx_swe_rk2_step": [vp, d, d, d, d, i, ctypes.POINTER(SwePassive), i, ctypes.POINTER(SweActive), i, l, l,
                               SWE_LAPLACIAN_FN, vp, i],
         "lpmx_swe_solver_create": [vp, i, i, d, ctypes.POINTER(vp)],

@@ -305,6 +305,28 @@ class Engine:
                                            ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "lpmx_err_norms")
         return a.value, b.value, c.value
 
+    def ftle(self, geom, vert_phys, vert_ref, face_phys, face_ref, face_verts, face_mask, ftle=None,
+             layout=LAYOUT_RIGHT, verts_layout=LAYOUT_RIGHT):
+        """ComputeFTLE<Seed> + get_max_ftle (src/mesh/lpm_ftle.hpp) for quadrilateral faces; geom 0 = sphere, 1 = plane.
+        `face_phys` is normalised in place on the sphere, `ftle` (zeros if omitted) is written at the leaves only.
+        Returns (ftle, max_ftle)."""
+        vert_phys, vert_ref, face_ref = _f64(vert_phys), _f64(vert_ref), _f64(face_ref)
+        if isinstance(face_phys, np.ndarray) and (face_phys.dtype != np.float64 or not face_phys.flags.c_contiguous):
+            raise ValueError("face_phys is an in/out argument: pass a C-contiguous float64 array")
+        nd = 3 if geom == 0 else 2
+        nv = vert_ref.shape[0] if layout == LAYOUT_RIGHT else vert_ref.shape[1]
+        nf = face_ref.shape[0] if layout == LAYOUT_RIGHT else face_ref.shape[1]
+        assert (vert_ref.shape[1] if layout == LAYOUT_RIGHT else vert_ref.shape[0]) == nd
+        fv = face_verts if hasattr(face_verts, "data_ptr") else np.ascontiguousarray(face_verts, dtype=np.int32)
+        if ftle is None:
+            ftle = _empty_like_scalar(face_ref, nf)
+            ftle[...] = 0.0
+        mx = ctypes.c_double()
+        self._check(self._L.lpmx_ftle(self._h, geom, nv, _ptr(vert_phys), _ptr(vert_ref), layout, nv, nf, _ptr(face_phys),
+                                      _ptr(face_ref), nf, _ptr(fv), verts_layout, _ptr(_u8(face_mask)), _ptr(ftle),
+                                      ctypes.byref(mx)), "lpmx_ftle")
+        return ftle, mx.value
+
     # ---- stepper level, in place on caller arrays ----------------------------------------
     def bve_rk4_step(self, dt, Omega, vert_xyz, vert_vort, vert_vel, face_xyz, face_vort, face_vel, face_area,
                      face_mask, n_steps=1, layout=LAYOUT_RIGHT):

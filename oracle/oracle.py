@@ -194,3 +194,20 @@ def swe_rk2_step(dt, Omega, g, eps, st, laps_fn=None, n_steps=1, L=None):
                           _p(a["surf"]), _p(a["bottom"]), _p(a["vel"]), _p(a["ddot"]), _p(a["laps"]),
                           st.mask.ctypes.data_as(_up), fn, None, ctypes.c_int(n_steps))
     return st
+
+
+def ftle(geom, vert_phys, vert_ref, face_phys, face_ref, face_verts, mask, L=None):
+    """ComputeFTLE for quadrilateral faces (mesh/lpm_ftle.hpp); geom 0 = sphere, 1 = plane.  Returns (ftle with
+    zeros at masked faces, face_phys after the call -- the sphere branch normalises it in place, max_ftle)."""
+    L = L or lib()
+    vert_phys, vert_ref, face_ref = _d(vert_phys), _d(vert_ref), _d(face_ref)
+    face_phys = _d(face_phys).copy()
+    fv = np.ascontiguousarray(face_verts, dtype=np.int32)
+    mask, mp = _m(mask)
+    nf, nv = face_ref.shape[0], vert_ref.shape[0]
+    out = np.zeros(nf)
+    L.oracle_ftle(ctypes.c_int(geom), ctypes.c_int(nv), _p(vert_phys), _p(vert_ref), ctypes.c_int(nf), _p(face_phys),
+                  _p(face_ref), fv.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), mp, _p(out))
+    L.oracle_max_ftle.restype = ctypes.c_double
+    mx = L.oracle_max_ftle(ctypes.c_int(nf), _p(out), mp)
+    return out, face_phys, float(mx)
