@@ -43,7 +43,12 @@ int run(const Options& opt) {
     for (Index i = 0; i < nv; ++i) vlaps[i] = f(vx + 3 * i);
     for (Index i = 0; i < nf; ++i) flaps[i] = f(fx + 3 * i);
   };
-  auto solver = std::make_unique<SWERK2<seed_type, topography_type>>(dt, *sphere, topo, slap);
+  // examples/sphere_swe_tc2.cpp:136-139: GMLS of order 4 for the surface Laplacian (here on the device); -lap exact
+  // swaps in the closed form above
+  const gmls::Params gmls_params(opt.get_int("-gmls", 4), SphereGeometry::ndim);
+  auto solver = opt.get_str("-lap", "gmls") == "exact"
+                    ? std::make_unique<SWERK2<seed_type, topography_type>>(dt, *sphere, topo, slap)
+                    : std::make_unique<SWERK2<seed_type, topography_type>>(dt, *sphere, topo, gmls_params);
   std::printf("%s%s", solver->info_string().c_str(), sphere->info_string().c_str());
 
   const Index nv = sphere->mesh.n_vertices_host(), nf = sphere->mesh.n_faces_host(), nl = sphere->mesh.faces.n_leaves_host();

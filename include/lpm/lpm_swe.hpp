@@ -149,6 +149,39 @@ typedef std::function<void(int stage, Index nv, const Real* vx, const Real* vsur
                            const Real* fsurf, const unsigned char* fmask, Real* flaps)>
     SurfaceLaplacian;
 
+namespace gmls {
+/// gmls::Params (src/lpm_compadre.hpp:23-60): same members, same defaults; Compadre::GMLS::getNP(order, 2) spelled out
+struct Params {
+  Real eps_multiplier;
+  Int samples_order;
+  Int manifold_order;
+  Real samples_weight_pwr;
+  Real manifold_weight_pwr;
+  Int ambient_dim;
+  Int topo_dim;
+  Int min_neighbors;
+  Int amr_max;
+  Params() : Params(3) {}
+  Params(const Int order, const Int dim = 3)
+      : eps_multiplier(2.0), samples_order(order), manifold_order(order), samples_weight_pwr(2.0), manifold_weight_pwr(2.0),
+        ambient_dim(dim), topo_dim(2), min_neighbors((order + 1) * (order + 2) / 2), amr_max(0) {}
+  lpmx_gmls_params_t c_params() const {
+    return lpmx_gmls_params_t{eps_multiplier, samples_order, manifold_order, samples_weight_pwr, manifold_weight_pwr,
+                              ambient_dim,    topo_dim,      min_neighbors};
+  }
+  std::string info_string(const int tab_lev = 0) const {
+    std::ostringstream ss;
+    const std::string tab(tab_lev + 1, '\t');
+    ss << std::string(tab_lev, '\t') << "gmls::Params info:\n"
+       << tab << "eps_multiplier = " << eps_multiplier << "\n" << tab << "samples_order = " << samples_order << "\n"
+       << tab << "manifold_order = " << manifold_order << "\n" << tab << "samples_weight_pwr = " << samples_weight_pwr << "\n"
+       << tab << "manifold_weight_pwr = " << manifold_weight_pwr << "\n" << tab << "ambient_dim = " << ambient_dim << "\n"
+       << tab << "topo_dim = " << topo_dim << "\n" << tab << "min_neighbors = " << min_neighbors << "\n";
+    return ss.str();
+  }
+};
+}  // namespace gmls
+
 template <typename SeedType, typename TopoType = ZeroFunctor>
 class SWERK2 {
  public:
@@ -157,6 +190,38 @@ class SWERK2 {
   Int t_idx;
   Real eps;
   SurfaceLaplacian laplacian;
+  gmls::Params gmls_params;
+  bool use_gmls = false;
+
+  /// The reference's constructor (src/lpm_swe_rk2.hpp:31-32, rk2_impl.hpp:14-78): the surface Laplacian comes from GMLS
+  /// with these parameters -- here evaluated on the device (lpmx_gmls_swe_laplacian), not by Compadre on the host.
+  SWERK2(const Real dt, SWE<SeedType>& swe, const TopoType&, const gmls::Params& gmls_params)
+      : dt(dt), swe(swe), t_idx(0), eps(swe.eps), gmls_params(gmls_params), use_gmls(true) {
+    static_assert(std::is_same<TopoType, ZeroFunctor>::value, "the engine implements the flat-bottom (ZeroFunctor) topography");
+    provider_.handle = Engine::get();
+    provider_.params = gmls_params.c_params();
+    // Laplacian of the initial surface: gather -> GMLS -> scatter (rk2_impl.hpp:56-77)
+    auto& m = swe.mesh;
+    lpmx_handle_t h = Engine::get();
+    const Index nv = m.n_vertices_host(), nf = m.n_faces_host();
+    int n = 0;
+    Engine::check(lpmx_gather_mesh_data(h, 3, LPMX_LAYOUT_RIGHT, nv, m.vertices.phys_crds.view.data(), 0, nf,
+                                        m.faces.phys_crds.view.data(), 0, m.faces.mask.data(), nullptr, 0, &n),
+                  "GatherMeshData");
+    std::vector<Real> gx(3 * (size_t)n), gs(n), gl(n);
+    Engine::check(lpmx_gather_mesh_data(h, 3, LPMX_LAYOUT_RIGHT, nv, m.vertices.phys_crds.view.data(), 0, nf,
+                                        m.faces.phys_crds.view.data(), 0, m.faces.mask.data(), gx.data(), 0, &n),
+                  "GatherMeshData::gather_coordinates");
+    Engine::check(lpmx_gather_mesh_data(h, 1, LPMX_LAYOUT_RIGHT, nv, swe.surf_passive.view.data(), 0, nf,
+                                        swe.surf_active.view.data(), 0, m.faces.mask.data(), gs.data(), 0, &n),
+                  "GatherMeshData::gather_scalar_fields");
+    Engine::check(lpmx_gmls_sphere_laplacian(h, &provider_.params, n, gx.data(), LPMX_LAYOUT_RIGHT, 0, gs.data(), gl.data(),
+                                             nullptr, nullptr),
+                  "sphere_scalar_gmls");
+    Engine::check(lpmx_scatter_mesh_data(h, 1, LPMX_LAYOUT_RIGHT, gl.data(), 0, nv, swe.surf_lap_passive.view.data(), 0, nf,
+                                         swe.surf_lap_active.view.data(), 0, m.faces.mask.data()),
+                  "ScatterMeshData::scatter_fields");
+  }
 
   SWERK2(const Real dt, SWE<SeedType>& swe, const TopoType&, const SurfaceLaplacian& lap)
       : dt(dt), swe(swe), t_idx(0), eps(swe.eps), laplacian(lap) {
@@ -181,7 +246,9 @@ class SWERK2 {
                         swe.surf_active.view.data(), swe.bottom_active.view.data(), swe.velocity_active.view.data(),
                         swe.double_dot_active.view.data(), swe.surf_lap_active.view.data(), m.faces.mask.data()};
     Engine::check(lpmx_swe_rk2_step(Engine::get(), dt, swe.coriolis.Omega, swe.g, eps, m.n_vertices_host(), &P, m.n_faces_host(),
-                                    &A, LPMX_LAYOUT_RIGHT, 0, 0, laplacian ? &SWERK2::trampoline : nullptr, this, 1),
+                                    &A, LPMX_LAYOUT_RIGHT, 0, 0,
+                                    use_gmls ? &lpmx_gmls_swe_laplacian : (laplacian ? &SWERK2::trampoline : nullptr),
+                                    use_gmls ? (void*)&provider_ : (void*)this, 1),
                   "SWERK2::advance_timestep_impl");
     ++t_idx;
   }
@@ -195,6 +262,7 @@ class SWERK2 {
  private:
   std::vector<Real> hx_, hs_, hl_;
   std::vector<unsigned char> hm_;
+  lpmx_gmls_provider_t provider_{};
 
   // lpmx_swe_laplacian_fn: device SoA -> host LayoutRight -> provider -> device
   static int trampoline(void* user, int stage, void* /*stream*/, int nv, const double* vx, const double* vsurf, double* vlaps,

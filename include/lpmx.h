@@ -351,6 +351,60 @@ int lpmx_swe_solver_advance(lpmx_swe_solver_t s, double dt, double Omega, double
                             void* user, int n_steps);
 
 /* ------------------------------------------------------------------------------------------
+ * The steps either side of the spherical SWE direct sums, kept on the device: the reference
+ * gathers vertices + leaf faces, copies them to the host, builds Compadre neighbourhoods on a kd-tree and evaluates a
+ * GMLS surface Laplacian every RK stage (src/lpm_swe_rk2_impl.hpp:56-77,134-154,233-252).
+ * ------------------------------------------------------------------------------------------ */
+
+/* GatherMeshData<Seed> (src/mesh/lpm_gather_mesh_data.hpp:24-117, functors _impl.hpp:14-66): rows [0, n_verts) of
+ * `gathered` are the vertex rows, row n_verts + leaf_idx(f) is leaf face f (faces.leaf_idx = exclusive scan of
+ * !mask); divided faces are dropped.  n_comp = 1 (scalar fields) or 2 / 3 (coordinates, vector fields); all three
+ * arrays share `layout`.  Call with gathered == NULL to obtain *n_gathered = n_verts + n_leaves only. */
+int lpmx_gather_mesh_data(lpmx_handle_t h, int n_comp, int layout, int n_verts, const double* vert_data, long vert_ld,
+                          int n_faces, const double* face_data, long face_ld, const unsigned char* face_mask,
+                          double* gathered, long gathered_ld, int* n_gathered);
+/* ScatterMeshData<Seed>::scatter_fields (src/mesh/lpm_scatter_mesh_data_impl.hpp): the inverse; rows of divided
+ * faces in face_data are left as they are. */
+int lpmx_scatter_mesh_data(lpmx_handle_t h, int n_comp, int layout, const double* gathered, long gathered_ld, int n_verts,
+                           double* vert_data, long vert_ld, int n_faces, double* face_data, long face_ld,
+                           const unsigned char* face_mask);
+
+/* gmls::Params (src/lpm_compadre.hpp:23-60), same members and defaults */
+typedef struct lpmx_gmls_params_s {
+  double eps_multiplier;      /* window radius = eps_multiplier x distance to the min_neighbors-th nearest point */
+  int samples_order;          /* Taylor order of the data reconstruction, 2..4 */
+  int manifold_order;         /* Taylor order of the manifold (height) reconstruction, 1..4 */
+  double samples_weight_pwr;  /* p of the Power weight (1 - r/eps)^p */
+  double manifold_weight_pwr; /* must equal samples_weight_pwr (both are 2 in every gmls::Params constructor) */
+  int ambient_dim;            /* 3 */
+  int topo_dim;               /* 2 */
+  int min_neighbors;          /* Compadre::GMLS::getNP(samples_order, topo_dim) = (order+1)(order+2)/2 by default */
+} lpmx_gmls_params_t;
+/* gmls::Params(order, 3) */
+int lpmx_gmls_params_init(lpmx_gmls_params_t* params, int order);
+
+/* Surface Laplacian (Laplace-Beltrami) of the samples f at n collocated source/target points on a sphere:
+ * gmls::Neighborhoods(crds, params) + gmls::sphere_scalar_gmls(crds, crds, neighbors, params,
+ * {LaplacianOfScalarPointEvaluation}) + Evaluator::applyAlphasToDataAllComponentsAllTargetSites
+ * (src/lpm_swe_rk2_impl.hpp:66-75).  Compadre 1.6.2 is not part of the reference tree: this is its published algorithm
+ * (lpm_b200/csrc/lpmx_gmls_core.h), validated analytically, NOT pinned value-for-value.
+ * Optional outputs: the window radius and the neighbour count of every point (Neighborhoods::neighborhood_radii,
+ * neighbor_lists(i, 0)).  A point whose least-squares system is rank deficient gets NaN.  Host or device pointers. */
+int lpmx_gmls_sphere_laplacian(lpmx_handle_t h, const lpmx_gmls_params_t* params, int n, const double* xyz, int layout,
+                               long ld, const double* f, double* laplacian, double* window_radius, int* n_neighbors);
+
+/* Built-in surface-Laplacian provider for lpmx_swe_rk2_step / lpmx_swe_solver_advance: pass
+ * `lpmx_gmls_swe_laplacian` as the lpmx_swe_laplacian_fn and a lpmx_gmls_provider_t* as `user`.  It performs the
+ * reference's gather -> neighbourhoods -> GMLS -> scatter sequence without leaving the device. */
+typedef struct lpmx_gmls_provider_s {
+  lpmx_handle_t handle;
+  lpmx_gmls_params_t params;
+} lpmx_gmls_provider_t;
+int lpmx_gmls_swe_laplacian(void* user, int stage, void* cuda_stream, int n_passive, const double* passive_xyz,
+                            const double* passive_surf, double* passive_laps, int n_active, const double* active_xyz,
+                            const double* active_surf, const unsigned char* active_mask, double* active_laps, long xyz_ld);
+
+/* ------------------------------------------------------------------------------------------
  * Planar problems (PlaneGeometry): Real*[2] views.  LPMX_LAYOUT_RIGHT is x[i*2+k], LPMX_LAYOUT_LEFT is x[k*ld+i].
  * Coriolis is CoriolisBetaPlane(f0, beta) (src/lpm_coriolis.hpp:93-148): f = f0 + beta y.
  * ------------------------------------------------------------------------------------------ */

@@ -61,6 +61,18 @@ SWE_LAPLACIAN_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long)
 
 
+class GmlsParams(ctypes.Structure):
+    """lpmx_gmls_params_t == gmls::Params (src/lpm_compadre.hpp:23-60)"""
+    _fields_ = [("eps_multiplier", ctypes.c_double), ("samples_order", ctypes.c_int), ("manifold_order", ctypes.c_int),
+                ("samples_weight_pwr", ctypes.c_double), ("manifold_weight_pwr", ctypes.c_double),
+                ("ambient_dim", ctypes.c_int), ("topo_dim", ctypes.c_int), ("min_neighbors", ctypes.c_int)]
+
+
+class GmlsProvider(ctypes.Structure):
+    """lpmx_gmls_provider_t"""
+    _fields_ = [("handle", ctypes.c_void_p), ("params", GmlsParams)]
+
+
 class LpmxError(RuntimeError):
     def __init__(self, code, where, detail=""):
         self.code = code
@@ -136,6 +148,11 @@ def _declare(L):
         "lpmx_ic2d_totals": [vp, i, vp, vp, i, l, vp, vp, c_double_p, c_double_p, c_double_p],
         "lpmx_ic2d_solver_totals": [vp, c_double_p, c_double_p, c_double_p],
         "lpmx_err_norms": [vp, i, i, vp, vp, i, l, vp, c_double_p, c_double_p, c_double_p],
+        "lpmx_gather_mesh_data": [vp, i, i, i, vp, l, i, vp, l, vp, vp, l, c_int_p],
+        "lpmx_scatter_mesh_data": [vp, i, i, vp, l, i, vp, l, i, vp, l, vp],
+        "lpmx_gmls_params_init": [ctypes.POINTER(GmlsParams), i],
+        "lpmx_gmls_sphere_laplacian": [vp, ctypes.POINTER(GmlsParams), i, vp, i, l, vp, vp, vp, vp],
+        "lpmx_gmls_swe_laplacian": [vp, i, vp, i, vp, vp, vp, i, vp, vp, vp, vp, l],
         "lpmx_ftle": [vp, i, i, vp, vp, i, l, i, vp, vp, l, vp, i, vp, vp, c_double_p],
         "lpmx_swe_rk2_step": [vp, d, d, d, d, i, ctypes.POINTER(SwePassive), i, ctypes.POINTER(SweActive), i, l, l,
                               SWE_LAPLACIAN_FN, vp, i],

@@ -128,6 +128,32 @@ def _empty_like_scalar(ref, n):
     return np.empty(n, dtype=np.float64)
 
 
+def gmls_params(order_or_params=3, **overrides):
+    """gmls::Params(order) (src/lpm_compadre.hpp:49-60) as a GmlsParams struct; keyword overrides set members."""
+    if isinstance(order_or_params, _lib.GmlsParams):
+        p = order_or_params
+    else:
+        p = _lib.GmlsParams()
+        rc = _lib.lib().lpmx_gmls_params_init(ctypes.byref(p), int(order_or_params))
+        if rc:
+            raise LpmxError(rc, "lpmx_gmls_params_init")
+    for k, v in overrides.items():
+        setattr(p, k, v)
+    return p
+
+
+class GmlsLaplacian:
+    """The built-in surface-Laplacian provider (lpmx_gmls_swe_laplacian + lpmx_gmls_provider_t): pass an instance as
+    `laplacian=` to SWESolver.advance / swe_rk2_step; the reference's gather -> Compadre -> scatter stays on the device."""
+
+    def __init__(self, engine, params=None):
+        self.provider = _lib.GmlsProvider()
+        self.provider.handle = engine._h
+        self.provider.params = gmls_params(params if params is not None else 3)
+        self.fn = ctypes.cast(engine._L.lpmx_gmls_swe_laplacian, _lib.SWE_LAPLACIAN_FN)
+        self.user = ctypes.cast(ctypes.pointer(self.provider), ctypes.c_void_p)
+
+
 class Engine:
     """One engine handle per process and GPU (lpmx_create)."""
 
@@ -327,6 +353,51 @@ class Engine:
                                       ctypes.byref(mx)), "lpmx_ftle")
         return ftle, mx.value
 
+    # ---- gather / scatter and the GMLS surface Laplacian (the steps either side of the SWE sums) ----
+    def gather_mesh_data(self, vert_data, face_data, face_mask):
+        """GatherMeshData: vertices then leaf faces (row n_verts + leaf_idx(f)); 1-D or (n, k) arrays, LayoutRight."""
+        vert_data, face_data = _f64(vert_data), _f64(face_data)
+        ncomp = 1 if face_data.ndim == 1 else face_data.shape[1]
+        nv, nf = vert_data.shape[0], face_data.shape[0]
+        mask = _u8(face_mask)
+        n = ctypes.c_int()
+        self._check(self._L.lpmx_gather_mesh_data(self._h, ncomp, LAYOUT_RIGHT, nv, _ptr(vert_data), nv, nf, _ptr(face_data), nf,
+                                                  _ptr(mask), None, 0, ctypes.byref(n)), "lpmx_gather_mesh_data")
+        out = np.empty((n.value,) if face_data.ndim == 1 else (n.value, ncomp))
+        self._check(self._L.lpmx_gather_mesh_data(self._h, ncomp, LAYOUT_RIGHT, nv, _ptr(vert_data), nv, nf, _ptr(face_data), nf,
+                                                  _ptr(mask), _ptr(out), n.value, ctypes.byref(n)), "lpmx_gather_mesh_data")
+        return out
+
+    def scatter_mesh_data(self, gathered, vert_out, face_out, face_mask):
+        """ScatterMeshData::scatter_fields into vert_out / face_out (float64, C-contiguous; divided faces untouched)."""
+        gathered = _f64(gathered)
+        ncomp = 1 if gathered.ndim == 1 else gathered.shape[1]
+        nv, nf = vert_out.shape[0], face_out.shape[0]
+        self._check(self._L.lpmx_scatter_mesh_data(self._h, ncomp, LAYOUT_RIGHT, _ptr(gathered), gathered.shape[0], nv,
+                                                   _ptr(vert_out), nv, nf, _ptr(face_out), nf, _ptr(_u8(face_mask))),
+                    "lpmx_scatter_mesh_data")
+
+    def gmls_sphere_laplacian(self, xyz, f, params=None, layout=LAYOUT_RIGHT, diagnostics=False):
+        """Surface Laplacian of the samples f at the points xyz (lpmx_gmls_sphere_laplacian); params: GmlsParams or an
+        int order (gmls::Params(order)).  Returns lap, or (lap, window_radius, n_neighbors) with diagnostics=True."""
+        params = gmls_params(params if params is not None else 3)
+        xyz, f = _f64(xyz), _f64(f)
+        n = f.shape[0]
+        lap = _empty_like_scalar(f, n)
+        eps = _empty_like_scalar(f, n) if diagnostics else None
+        if diagnostics and hasattr(f, "data_ptr"):
+            import torch
+            nn = torch.empty(n, dtype=torch.int32, device=f.device)
+        else:
+            nn = np.empty(n, dtype=np.int32) if diagnostics else None
+        self._check(self._L.lpmx_gmls_sphere_laplacian(self._h, ctypes.byref(params), n, _ptr(xyz), layout, n, _ptr(f), _ptr(lap),
+                                                       _ptr(eps), _ptr(nn)), "lpmx_gmls_sphere_laplacian")
+        return (lap, eps, nn) if diagnostics else lap
+
+    def gmls_provider(self, params=None):
+        """(callback, user) for SWESolver.advance / swe_rk2_step: the built-in device-side surface-Laplacian provider."""
+        return GmlsLaplacian(self, params)
+
     # ---- stepper level, in place on caller arrays ----------------------------------------
     def bve_rk4_step(self, dt, Omega, vert_xyz, vert_vort, vert_vel, face_xyz, face_vort, face_vel, face_area,
                      face_mask, n_steps=1, layout=LAYOUT_RIGHT):
@@ -476,6 +547,8 @@ def _laplacian_cb(fn):
     as ints) into an lpmx_swe_laplacian_fn; None -> NULL provider."""
     if fn is None:
         return ctypes.cast(None, _lib.SWE_LAPLACIAN_FN)
+    if isinstance(fn, GmlsLaplacian):
+        return fn.fn
 
     def cb(user, stage, stream, n_p, pxyz, psurf, plaps, n_a, axyz, asurf, amask, alaps, ld):
         try:
@@ -496,7 +569,8 @@ def swe_rk2_step(engine, dt, Omega, g, eps, passive, active, mask, laplacian=Non
     P, A = _swe_structs(passive, active, mask)
     cb = _laplacian_cb(laplacian)
     engine._check(engine._L.lpmx_swe_rk2_step(engine._h, float(dt), float(Omega), float(g), float(eps), nv,
-                                              ctypes.byref(P), nf, ctypes.byref(A), layout, nv, nf, cb, None, n_steps),
+                                              ctypes.byref(P), nf, ctypes.byref(A), layout, nv, nf, cb,
+                                              getattr(laplacian, "user", None), n_steps),
                   "lpmx_swe_rk2_step")
 
 
@@ -542,7 +616,8 @@ class SWESolver:
 
     def advance(self, dt, Omega, g, laplacian=None, n_steps=1):
         cb = _laplacian_cb(laplacian)
-        self.e._check(self.e._L.lpmx_swe_solver_advance(self._s, float(dt), float(Omega), float(g), cb, None, n_steps),
+        self.e._check(self.e._L.lpmx_swe_solver_advance(self._s, float(dt), float(Omega), float(g), cb,
+                                                        getattr(laplacian, "user", None), n_steps),
                       "lpmx_swe_solver_advance")
 
 

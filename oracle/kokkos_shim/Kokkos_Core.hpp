@@ -49,6 +49,11 @@ struct Device {
   using memory_space = M;
 };
 
+template <class Space, class Mem>
+struct SpaceAccessibility {  // everything lives on the host here
+  enum : bool { accessible = true, assignable = true, deepcopy = true };
+};
+
 struct ALL_t {
   constexpr ALL_t operator()() const { return ALL_t{}; }
 };
@@ -144,6 +149,8 @@ class View {
   using value_type = typename traits::value_type;
   using non_const_value_type = typename std::remove_const<value_type>::type;
   using HostMirror = View<DataType, Props...>;
+  using execution_space = Serial;
+  using memory_space = HostSpace;
   using host_mirror_type = HostMirror;
   static constexpr int rank = traits::rank;
   static constexpr int Rank = traits::rank;

@@ -11,6 +11,7 @@
 //   lpm_incompressible2d_kernels.hpp  Incompressible2DPassiveSums / ActiveSums <SphereGeometry>
 //   lpm_swe_kernels.hpp        kzeta_sphere, ksigma_sphere, grad_kzeta, grad_ksigma, SphereVertexSums,
 //                              SphereFaceSums
+//   util/lpm_matlab_io.hpp     write_vector_matlab, write_array_matlab
 //   mesh/lpm_ftle.hpp          ComputeFTLE<CubedSphereSeed>, ComputeFTLE<QuadRectSeed>, get_max_ftle
 #include <cstdint>
 #include <vector>
@@ -24,6 +25,8 @@
 #include "lpm_swe_kernels.hpp"
 #include "lpm_surface_gallery.hpp"
 #include "mesh/lpm_ftle.hpp"
+#include "util/lpm_matlab_io.hpp"
+#include <sstream>
 
 using namespace Lpm;
 using crd = SphereGeometry::crd_view_type;
@@ -322,6 +325,23 @@ void oracle_ftle(int geom, int n_verts, const double* vert_phys, const double* v
 double oracle_max_ftle(int n_faces, const double* ftle, const uint8_t* mask) {
   Mask fm(mask, n_faces);
   return get_max_ftle(wrap1(ftle, n_faces), fm.v, n_faces);
+}
+
+// write_vector_matlab / write_array_matlab (util/lpm_matlab_io.hpp) into a caller buffer; returns the length
+static int copy_out(const std::string& s, char* buf, int cap) {
+  if ((int)s.size() + 1 <= cap) std::memcpy(buf, s.c_str(), s.size() + 1);
+  return (int)s.size();
+}
+int oracle_write_vector_matlab(const char* name, int n, const double* v, char* buf, int cap) {
+  std::ostringstream os;
+  write_vector_matlab(os, name, wrap1(v, n));
+  return copy_out(os.str(), buf, cap);
+}
+int oracle_write_array_matlab(const char* name, int nrow, int ncol, const double* a, char* buf, int cap) {
+  std::ostringstream os;
+  Kokkos::View<Real**> av(const_cast<double*>(a), nrow, ncol);
+  write_array_matlab(os, name, av);
+  return copy_out(os.str(), buf, cap);
 }
 
 }  // extern "C"
