@@ -197,6 +197,11 @@ def main():
                          "1 step, depth 4; examples/sphere_rh54.cpp:442-452) at constant Courant number")
     ap.add_argument("--cpu-sample", type=int, default=65536, help="vertex targets in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--laplacian", default="frozen", choices=["frozen", "gmls"],
+                    help="swe_rk2 only: surface Laplacian frozen at the TC2 closed form (the pair sums alone), or the "
+                         "device-side GMLS provider of order --gmls-order evaluated at both stages of every step (the whole "
+                         "reference step, src/lpm_swe_rk2_impl.hpp:134-154,233-252)")
+    ap.add_argument("--gmls-order", type=int, default=4, help="examples/sphere_swe_tc2.cpp:136 uses 4")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
@@ -258,10 +263,11 @@ def main():
         swe_solver.set_state(swe_p, swe_a, mask)
         swe_solver.init_direct_sums(True)
         swe_g = tc.g
+        swe_lap = eng.gmls_provider(args.gmls_order) if args.laplacian == "gmls" else None
 
         class _Adv:  # same advance(dt, Omega, n) surface as the other two solvers
             def advance(self, dt, Omega, n):
-                swe_solver.advance(dt, Omega, swe_g, None, n)
+                swe_solver.advance(dt, Omega, swe_g, swe_lap, n)
         solver = _Adv()
     eng.sync()
     fp64_peak = eng.fp64_peak_tflops()
@@ -374,7 +380,7 @@ def main():
             swe_solver.get_state(hp_np, ha_np)
 
             def one():
-                swe_rk2_step(eng, args.dt, Omega, swe_g, 0.0, hp_np, ha_np, h_mask.numpy(), None, n_steps=1)
+                swe_rk2_step(eng, args.dt, Omega, swe_g, 0.0, hp_np, ha_np, h_mask.numpy(), swe_lap, n_steps=1)
             h2d = sum(t.numel() * 8 for t in hp.values()) + sum(t.numel() * 8 for t in ha.values()) + mask.nbytes
             d2h = h2d - mask.nbytes
         else:
@@ -425,7 +431,9 @@ def main():
                        "evals_per_step": evals, "n_verts": nv, "n_faces": nf, "n_leaf_sources": nleaf,
                        "interactions_per_eval": i_eval, "dt": args.dt, "Omega": Omega,
                        "parallelism": f"targets sharded over {world} GPU(s), per-stage allgather of leaf source records",
-                       "l2": "flushed between timed steps (256 MiB write)"},
+                       "l2": "flushed between timed steps (256 MiB write)",
+                       **({"surface_laplacian": (f"device GMLS order {args.gmls_order}, both stages" if args.laplacian == "gmls"
+                                                 else "frozen at the TC2 closed form")} if args.stepper == "swe_rk2" else {})},
             "rk_step_ms": ms_per_step, "step_ms_each": step_ms, "wall_s_timed_region": t_wall,
             "state_check": state_check,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

@@ -105,16 +105,27 @@ __global__ void cell_start_kernel(long ncell, int n, const unsigned int* __restr
   cell_start[q] = lo;
 }
 
+template <int OM, int KMAX>
 __global__ void __launch_bounds__(128) gmls_laplacian_kernel(gmls::Cloud c, gmls::Params p, const int* __restrict__ idx,
                                                              double* __restrict__ lap, double* __restrict__ eps_out,
                                                              int* __restrict__ nn_out) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= c.n) return;
-  const gmls::TargetResult r = gmls::laplacian_at_target(c, p, (int)i);
+  const gmls::TargetResult r = gmls::laplacian_at_target<OM, KMAX>(c, p, (int)i);
   const int o = idx[i];
   lap[o] = r.lap;
   if (eps_out) eps_out[o] = r.eps;
   if (nn_out) nn_out[o] = r.n_neighbors;
+}
+
+template <int OM>
+static void launch_gmls(cudaStream_t st, const gmls::Cloud& c, const gmls::Params& p, const int* idx, double* lap, double* eps_out,
+                        int* nn_out) {
+  const unsigned blocks = (unsigned)((c.n + 127) / 128);
+  if (p.min_neighbors <= 16)
+    gmls_laplacian_kernel<OM, 16><<<blocks, 128, 0, st>>>(c, p, idx, lap, eps_out, nn_out);
+  else
+    gmls_laplacian_kernel<OM, gmls::kMaxK><<<blocks, 128, 0, st>>>(c, p, idx, lap, eps_out, nn_out);
 }
 
 static int check_params(lpmx_handle_t h, const lpmx_gmls_params_t* q, gmls::Params* p) {
@@ -173,7 +184,10 @@ static int gmls_laplacian_device(lpmx_handle_t h, const gmls::Params& p, int n, 
   cell_start_kernel<<<(unsigned)((ncell + 1 + threads - 1) / threads), threads, 0, h->stream>>>(ncell, n, (const unsigned int*)d_key2,
                                                                                                 (int*)d_cs);
   c.x = (const double*)d_xs, c.f = (const double*)d_fs, c.cell_start = (const int*)d_cs;
-  gmls_laplacian_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(c, p, (const int*)d_idx2, lap, eps_out, nn_out);
+  const int om = p.samples_order > p.manifold_order ? p.samples_order : p.manifold_order;
+  if (om <= 2) launch_gmls<2>(h->stream, c, p, (const int*)d_idx2, lap, eps_out, nn_out);
+  else if (om == 3) launch_gmls<3>(h->stream, c, p, (const int*)d_idx2, lap, eps_out, nn_out);
+  else launch_gmls<4>(h->stream, c, p, (const int*)d_idx2, lap, eps_out, nn_out);
   h->launches += 5;  // keys, sort (counted once), permute, cell table, Laplacian
   LPMX_CUDA(h, cudaGetLastError());
   return LPMX_OK;

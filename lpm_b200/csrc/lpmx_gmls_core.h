@@ -16,8 +16,8 @@
 //   2. weighted least squares in the scaled Taylor basis b_k(s/eps, t/eps) = (s/eps)^ax (t/eps)^ay / (ax! ay!),
 //      n = 0..order, ay = 0..n, weights W(r) = (1 - r/eps)^p (WeightingFunctionType::Power, p = *_weight_pwr), once
 //      for the height (manifold_order) and once for the data (samples_order).  Compadre factors sqrt(W) P with QR;
-//      here the normal equations P^T W P are accumulated on the fly (no neighbour list is stored) and solved by
-//      Cholesky -- the same minimiser; the scaled basis keeps cond(P^T W P) < 1e7 for order <= 4.
+//      here the normal equations P^T W P are accumulated on the fly as weighted moments (no neighbour list is stored)
+//      and solved by Cholesky -- the same minimiser; the scaled basis keeps cond(P^T W P) < 1e7 for order <= 4.
 //   3. Laplace-Beltrami at the target in the graph chart, metric g_ij = delta_ij + h_i h_j:
 //        lap f = g^ij ( f_ij - h_ij (grad h . grad f) / (1 + |grad h|^2) ).
 // Parity is therefore UNPINNED against Compadre; the pins are analytic: spherical harmonics
@@ -33,8 +33,10 @@
 
 #ifdef __CUDACC__
 #define LPMX_HD __host__ __device__ __forceinline__
+#define LPMX_UNROLL _Pragma("unroll")
 #else
 #define LPMX_HD inline
+#define LPMX_UNROLL
 #endif
 
 namespace lpmx {
@@ -178,18 +180,28 @@ struct TargetResult {
 };
 
 // Everything for one target: sorted index `it` of the cloud (targets and sources are collocated).
+//
+// OM = max(samples_order, manifold_order) and KMAX >= min_neighbors are compile-time so that every hot array has
+// static indices and lives in registers.  The entries of P^T W P are products of two Taylor monomials, i.e. weighted
+// MOMENTS of the neighbour set: (P^T W P)_rq = mu(ax_r + ax_q, ay_r + ay_q) / (ax_r! ay_r! ax_q! ay_q!) with
+// mu(a, b) = sum_j w_j u_j^a v_j^b.  There are only (2 OM + 1)(2 OM + 2) / 2 distinct moments (45 at order 4) against
+// 120 matrix entries, and the two right-hand sides are the data- and height-weighted moments of degree <= OM, so one
+// neighbour costs ~120 register FMAs; the matrix is assembled once per target.
+template <int OM, int KMAX>
 LPMX_HD TargetResult laplacian_at_target(const Cloud& c, const Params& p, int it) {
   TargetResult out;
   const int n = c.n;
   const double x0 = c.x[it], x1 = c.x[n + it], x2 = c.x[2 * n + it];
   const int ci = cell_coord(c, x0), cj = cell_coord(c, x1), ck = cell_coord(c, x2);
-  const int K = p.min_neighbors < kMaxK ? p.min_neighbors : kMaxK;
+  const int K = p.min_neighbors < KMAX ? p.min_neighbors : KMAX;
 
   // ---- pass 1: distance to the K-th nearest point (the target counts, at distance 0) ----
-  double best[kMaxK];
-  double rK2 = 0.0;
+  double best[KMAX];  // ascending; static indices only
+  double rK2 = 1e300;
   for (int ring = 1;; ++ring) {
-    for (int q = 0; q < K; ++q) best[q] = 1e300;
+LPMX_UNROLL
+    for (int q = 0; q < KMAX; ++q) best[q] = 1e300;
+    rK2 = 1e300;
     const int i0 = ci - ring < 0 ? 0 : ci - ring, i1 = ci + ring >= c.G ? c.G - 1 : ci + ring;
     const int j0 = cj - ring < 0 ? 0 : cj - ring, j1 = cj + ring >= c.G ? c.G - 1 : cj + ring;
     const int k0 = ck - ring < 0 ? 0 : ck - ring, k1 = ck + ring >= c.G ? c.G - 1 : ck + ring;
@@ -200,18 +212,21 @@ LPMX_HD TargetResult laplacian_at_target(const Cloud& c, const Params& p, int it
         const int first = c.cell_start[base + k0], hi = c.cell_start[base + k1 + 1];
         for (int j = first; j < hi; ++j) {
           const double d0 = c.x[j] - x0, d1 = c.x[n + j] - x1, d2 = c.x[2 * n + j] - x2;
-          const double d = d0 * d0 + d1 * d1 + d2 * d2;
-          if (d < best[K - 1]) {  // insertion into the ascending list
-            int q = K - 1;
-            while (q > 0 && best[q - 1] > d) {
-              best[q] = best[q - 1];
-              --q;
+          double d = d0 * d0 + d1 * d1 + d2 * d2;
+          if (d < rK2) {  // sift d into the ascending list (the displaced maximum falls off the end)
+LPMX_UNROLL
+            for (int q = 0; q < KMAX; ++q) {
+              const double lo = d < best[q] ? d : best[q];
+              d = d < best[q] ? best[q] : d;
+              best[q] = lo;
             }
-            best[q] = d;
+            rK2 = 1e300;
+LPMX_UNROLL
+            for (int q = 0; q < KMAX; ++q)
+              if (q == K - 1) rK2 = best[q];
           }
         }
       }
-    rK2 = best[K - 1];
     const double reach = ring * c.cell;  // every point closer than this has been seen
     const bool whole_grid = i0 == 0 && j0 == 0 && k0 == 0 && i1 == c.G - 1 && j1 == c.G - 1 && k1 == c.G - 1;
     if ((rK2 < 1e299 && rK2 <= reach * reach) || whole_grid) break;
@@ -224,18 +239,24 @@ LPMX_HD TargetResult laplacian_at_target(const Cloud& c, const Params& p, int it
   const double eps = (rK2 > 0.0 ? sqrt(rK2) : 1e-14) * p.eps_multiplier;
   const double eps2 = eps * eps, ieps = 1.0 / eps;
 
-  // ---- pass 2: accumulate the normal equations over every point with |y - x| < eps ----
+  // ---- pass 2: weighted moments over every point with |y - x| < eps ----
   double nrm[3] = {x0, x1, x2};
   const double inv = 1.0 / sqrt(x0 * x0 + x1 * x1 + x2 * x2);
   nrm[0] *= inv, nrm[1] *= inv, nrm[2] *= inv;
   double t1[3], t2[3];
   tangent_frame(nrm, t1, t2);
-  const int of = p.samples_order, oh = p.manifold_order;
-  const int om = of > oh ? of : oh;
-  const int npm = np_of(om), npf = np_of(of), nph = np_of(oh);
-  double M[kMaxNP * (kMaxNP + 1) / 2], rf[kMaxNP], rh[kMaxNP], bas[kMaxNP];
-  for (int q = 0; q < npm * (npm + 1) / 2; ++q) M[q] = 0.0;
-  for (int q = 0; q < npm; ++q) rf[q] = 0.0, rh[q] = 0.0;
+  constexpr int D = 2 * OM;
+  double mu[D + 1][D + 1];    // mu[a][b], a + b <= 2 OM
+  double mf[OM + 1][OM + 1];  // data-weighted, a + b <= OM
+  double mh[OM + 1][OM + 1];  // height-weighted
+LPMX_UNROLL
+  for (int a = 0; a <= D; ++a)
+LPMX_UNROLL
+    for (int b = 0; b <= D; ++b) mu[a][b] = 0.0;
+LPMX_UNROLL
+  for (int a = 0; a <= OM; ++a)
+LPMX_UNROLL
+    for (int b = 0; b <= OM; ++b) mf[a][b] = 0.0, mh[a][b] = 0.0;
   int count = 0;
   {
     int ring = (int)ceil(eps * c.inv_cell);
@@ -252,26 +273,63 @@ LPMX_HD TargetResult laplacian_at_target(const Cloud& c, const Params& p, int it
           const double d = d0 * d0 + d1 * d1 + d2 * d2;
           if (!(d < eps2)) continue;  // strictly inside the window (nanoflann radius search)
           ++count;
-          const double s = d0 * t1[0] + d1 * t1[1] + d2 * t1[2];
-          const double t = d0 * t2[0] + d1 * t2[1] + d2 * t2[2];
+          const double u = (d0 * t1[0] + d1 * t1[1] + d2 * t1[2]) * ieps;
+          const double v = (d0 * t2[0] + d1 * t2[1] + d2 * t2[2]) * ieps;
           const double hgt = d0 * nrm[0] + d1 * nrm[1] + d2 * nrm[2];
-          const double w = power_weight(sqrt(s * s + t * t) * ieps, p.weight_pwr);
-          taylor_basis(om, s * ieps, t * ieps, bas);
-          const double fv = c.f[j];
-          for (int r = 0; r < npm; ++r) {
-            const double wb = w * bas[r];
-            for (int q = 0; q <= r; ++q) M[tri(r, q)] += wb * bas[q];
-            rf[r] += wb * fv;
-            rh[r] += wb * hgt;
-          }
+          const double w = power_weight(sqrt(u * u + v * v), p.weight_pwr);
+          const double wf = w * c.f[j], wh = w * hgt;
+          double pu[D + 1], pv[D + 1];
+          pu[0] = 1.0, pv[0] = 1.0;
+LPMX_UNROLL
+          for (int q = 1; q <= D; ++q) pu[q] = pu[q - 1] * u, pv[q] = pv[q - 1] * v;
+LPMX_UNROLL
+          for (int qa = 0; qa <= D; ++qa)
+LPMX_UNROLL
+            for (int qb = 0; qb <= D - qa; ++qb) {
+              const double m = pu[qa] * pv[qb];
+              mu[qa][qb] += w * m;
+              if (qa + qb <= OM) {
+                mf[qa][qb] += wf * m;
+                mh[qa][qb] += wh * m;
+              }
+            }
         }
       }
   }
   out.eps = eps;
   out.n_neighbors = count;
+
+  // ---- assemble P^T W P and the right-hand sides in Compadre's basis order (n = 0..order, ay = 0..n) ----
+  constexpr int NPM = (OM + 1) * (OM + 2) / 2;
+  double M[NPM * (NPM + 1) / 2], rf[NPM], rh[NPM];
+  {
+    constexpr double ifact[9] = {1.0, 1.0, 0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0, 1.0 / 40320.0};
+    int r = 0;
+LPMX_UNROLL
+    for (int nr = 0; nr <= OM; ++nr)
+LPMX_UNROLL
+      for (int ayr = 0; ayr <= nr; ++ayr) {
+        const int axr = nr - ayr;
+        const double sr = ifact[axr] * ifact[ayr];
+        rf[r] = mf[axr][ayr] * sr;
+        rh[r] = mh[axr][ayr] * sr;
+        int q = 0;
+LPMX_UNROLL
+        for (int nq = 0; nq <= OM; ++nq)
+LPMX_UNROLL
+          for (int ayq = 0; ayq <= nq; ++ayq) {
+            const int axq = nq - ayq;
+            if (q <= r) M[tri(r, q)] = mu[axr + axq][ayr + ayq] * (sr * (ifact[axq] * ifact[ayq]));
+            ++q;
+          }
+        ++r;
+      }
+  }
+  const int of = p.samples_order, oh = p.manifold_order;
+  const int npf = np_of(of), nph = np_of(oh);
   // The leading np x np block of P^T W P is the lower-order system (total-degree ordering), and the Cholesky factor of
   // a leading block is the leading block of the factor: one factorisation serves both orders.
-  if (!cholesky_factor(npm, M)) {
+  if (!cholesky_factor(NPM, M)) {
     out.lap = NAN;
     return out;
   }
@@ -280,6 +338,15 @@ LPMX_HD TargetResult laplacian_at_target(const Cloud& c, const Params& p, int it
   cholesky_solve(nph, M, rh);
   out.lap = of >= 2 ? laplace_beltrami(rf, of, rh, oh, eps) : 0.0;
   return out;
+}
+
+// run-time (orders, min_neighbors) -> compile-time instance
+LPMX_HD TargetResult laplacian_at_target_dispatch(const Cloud& c, const Params& p, int it) {
+  const int om = p.samples_order > p.manifold_order ? p.samples_order : p.manifold_order;
+  const bool small = p.min_neighbors <= 16;
+  if (om <= 2) return small ? laplacian_at_target<2, 16>(c, p, it) : laplacian_at_target<2, kMaxK>(c, p, it);
+  if (om == 3) return small ? laplacian_at_target<3, 16>(c, p, it) : laplacian_at_target<3, kMaxK>(c, p, it);
+  return small ? laplacian_at_target<4, 16>(c, p, it) : laplacian_at_target<4, kMaxK>(c, p, it);
 }
 
 }  // namespace gmls

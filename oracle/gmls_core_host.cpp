@@ -37,7 +37,7 @@ extern "C" int gmls_core_host_laplacian(int n, const double* xyz /* n x 3 row-ma
   c.x = xs.data(), c.f = fs.data(), c.cell_start = start.data();
 #pragma omp parallel for schedule(dynamic, 64)
   for (int i = 0; i < n; ++i) {
-    const TargetResult r = laplacian_at_target(c, p, i);
+    const TargetResult r = laplacian_at_target_dispatch(c, p, i);
     lap[perm[i]] = r.lap;
     if (eps_out) eps_out[perm[i]] = r.eps;
     if (nn_out) nn_out[perm[i]] = r.n_neighbors;
