@@ -44,7 +44,25 @@ int run_ic2d(const char* example, const Options& opt, Vorticity& vorticity, cons
   auto solver = std::make_unique<Incompressible2DRK2<seed_type>>(dt, *sphere);
   Timer loop;
   Real max_ftle = 0;
+  // examples/sphere_rh54.cpp:190-198,255-300: rebuild the particle set every remesh_interval steps (uniform meshes)
+  const Int remesh_interval = opt.get_int("-rm", nsteps + 1);
+  const bool remesh_direct = opt.get_str("-rs", "indirect") == "direct";
+  const gmls::Params gmls_params(opt.get_int("-ro", 4));
+  Int rm_counter = 0;
   for (Int t_idx = 0; t_idx < nsteps; ++t_idx) {
+    if ((t_idx + 1) % remesh_interval == 0) {
+      ++rm_counter;
+      auto new_sphere = std::make_unique<Incompressible2D<seed_type>>(mesh_params, coriolis, eps);
+      new_sphere->t = sphere->t;
+      new_sphere->allocate_tracer(lat0);
+      auto remesh = compadre_remesh(*new_sphere, *sphere, gmls_params);
+      if (remesh_direct)
+        remesh.uniform_direct_remesh();
+      else
+        remesh.uniform_indirect_remesh(vorticity, coriolis, lat0);
+      sphere = std::move(new_sphere);
+      solver.reset(new Incompressible2DRK2<seed_type>(dt, *sphere, solver->t_idx));
+    }
     sphere->advance_timestep(*solver);
     if constexpr (std::is_same<typename seed_type::faceKind, QuadFace>::value) {
       // examples/sphere_rh54.cpp:308-318 (the reference's FTLE is a static_assert for triangular panels)
@@ -58,7 +76,7 @@ int run_ic2d(const char* example, const Options& opt, Vorticity& vorticity, cons
     }
     per_step(*sphere, vorticity);
   }
-  std::printf("max_ftle = %.12e\n", max_ftle);
+  std::printf("max_ftle = %.12e; remeshes: %d\n", max_ftle, rm_counter);
   const double loop_s = loop.seconds();
   const Real vort1 = sphere->total_vorticity(), ke1 = sphere->total_kinetic_energy(), ens1 = sphere->total_enstrophy();
   const Index nv = sphere->mesh.n_vertices_host(), nf = sphere->mesh.n_faces_host(), nl = sphere->mesh.faces.n_leaves_host();

@@ -2,6 +2,7 @@
 #ifndef LPM_SHIM_HPP
 #define LPM_SHIM_HPP
 #include "lpm_bve_sphere.hpp"
+#include "lpm_compadre_remesh.hpp"
 #include "lpm_config.hpp"
 #include "lpm_coords.hpp"
 #include "lpm_coriolis.hpp"

@@ -6,6 +6,7 @@
 #ifndef LPM_SHIM_INCOMPRESSIBLE2D_HPP
 #define LPM_SHIM_INCOMPRESSIBLE2D_HPP
 
+#include "lpm_compadre_remesh.hpp"
 #include "lpm_coriolis.hpp"
 #include "lpm_polymesh2d.hpp"
 
@@ -136,6 +137,36 @@ class Incompressible2D {
     return ss.str();
   }
 };
+
+/// compadre_remesh(new_ic2d, old_ic2d, gmls_params) (src/lpm_incompressible2d_impl.hpp:389-456): the same field maps --
+/// relative/absolute vorticity, stream function, every tracer; velocity as the vector field -- and t_ref / ref_crds reset.
+template <typename SeedType>
+CompadreRemesh<SeedType> compadre_remesh(Incompressible2D<SeedType>& new_ic2d, const Incompressible2D<SeedType>& old_ic2d,
+                                         const gmls::Params& gmls_params) {
+  typename CompadreRemesh<SeedType>::vert_scalar_field_map ps_old, ps_new;
+  typename CompadreRemesh<SeedType>::face_scalar_field_map as_old, as_new;
+  typename CompadreRemesh<SeedType>::vert_vector_field_map pv_old, pv_new;
+  typename CompadreRemesh<SeedType>::face_vector_field_map av_old, av_new;
+  for (Index i = 0; i < new_ic2d.mesh.n_vertices_host(); ++i)
+    for (int k = 0; k < 3; ++k) new_ic2d.ref_crds_passive.view(i, k) = new_ic2d.mesh.vertices.phys_crds.view(i, k);
+  for (Index i = 0; i < new_ic2d.mesh.n_faces_host(); ++i)
+    for (int k = 0; k < 3; ++k) new_ic2d.ref_crds_active.view(i, k) = new_ic2d.mesh.faces.phys_crds.view(i, k);
+  new_ic2d.t_ref = old_ic2d.t;
+  ps_old.emplace("relative_vorticity", old_ic2d.rel_vort_passive), ps_new.emplace("relative_vorticity", new_ic2d.rel_vort_passive);
+  ps_old.emplace("absolute_vorticity", old_ic2d.abs_vort_passive), ps_new.emplace("absolute_vorticity", new_ic2d.abs_vort_passive);
+  ps_old.emplace("stream_function", old_ic2d.stream_fn_passive), ps_new.emplace("stream_function", new_ic2d.stream_fn_passive);
+  as_old.emplace("relative_vorticity", old_ic2d.rel_vort_active), as_new.emplace("relative_vorticity", new_ic2d.rel_vort_active);
+  as_old.emplace("absolute_vorticity", old_ic2d.abs_vort_active), as_new.emplace("absolute_vorticity", new_ic2d.abs_vort_active);
+  as_old.emplace("stream_function", old_ic2d.stream_fn_active), as_new.emplace("stream_function", new_ic2d.stream_fn_active);
+  for (const auto& t : old_ic2d.tracer_passive) ps_old.emplace(t.first, t.second);
+  for (const auto& t : new_ic2d.tracer_passive) ps_new.emplace(t.first, t.second);
+  for (const auto& t : old_ic2d.tracer_active) as_old.emplace(t.first, t.second);
+  for (const auto& t : new_ic2d.tracer_active) as_new.emplace(t.first, t.second);
+  pv_old.emplace("velocity", old_ic2d.velocity_passive), pv_new.emplace("velocity", new_ic2d.velocity_passive);
+  av_old.emplace("velocity", old_ic2d.velocity_active), av_new.emplace("velocity", new_ic2d.velocity_active);
+  return CompadreRemesh<SeedType>(new_ic2d.mesh, ps_new, as_new, pv_new, av_new, old_ic2d.mesh, ps_old, as_old, pv_old, av_old,
+                                  gmls_params);
+}
 
 template <typename SeedType>
 class Incompressible2DRK2 {

@@ -393,6 +393,16 @@ int lpmx_gmls_params_init(lpmx_gmls_params_t* params, int order);
 int lpmx_gmls_sphere_laplacian(lpmx_handle_t h, const lpmx_gmls_params_t* params, int n, const double* xyz, int layout,
                                long ld, const double* f, double* laplacian, double* window_radius, int* n_neighbors);
 
+/* Scalar point evaluation of n_fields source fields at n_tgt target points on the sphere: gmls::Neighborhoods(src, tgt,
+ * params) + ScalarPointEvaluation / PointSample, the interpolation step of CompadreRemesh (interpolate_lag_crds and
+ * uniform_direct_remesh, src/mesh/lpm_compadre_remesh_impl.hpp:136-210; driven from examples/sphere_rh54.cpp:257-300).
+ * src_fields / tgt_fields are arrays of n_fields pointers (each n_src / n_tgt doubles; host or device, also the pointer
+ * arrays themselves live on the host).  samples_order 1..4; the manifold reconstruction does not enter a point
+ * evaluation.  Same status as the Laplacian: Compadre's published algorithm, validated analytically. */
+int lpmx_gmls_sphere_interpolate(lpmx_handle_t h, const lpmx_gmls_params_t* params, int n_src, const double* src_xyz,
+                                 int src_layout, long src_ld, int n_fields, const double* const* src_fields, int n_tgt,
+                                 const double* tgt_xyz, int tgt_layout, long tgt_ld, double* const* tgt_fields);
+
 /* Built-in surface-Laplacian provider for lpmx_swe_rk2_step / lpmx_swe_solver_advance: pass
  * `lpmx_gmls_swe_laplacian` as the lpmx_swe_laplacian_fn and a lpmx_gmls_provider_t* as `user`.  It performs the
  * reference's gather -> neighbourhoods -> GMLS -> scatter sequence without leaving the device. */

@@ -152,6 +152,7 @@ def _declare(L):
         "lpmx_scatter_mesh_data": [vp, i, i, vp, l, i, vp, l, i, vp, l, vp],
         "lpmx_gmls_params_init": [ctypes.POINTER(GmlsParams), i],
         "lpmx_gmls_sphere_laplacian": [vp, ctypes.POINTER(GmlsParams), i, vp, i, l, vp, vp, vp, vp],
+        "lpmx_gmls_sphere_interpolate": [vp, ctypes.POINTER(GmlsParams), i, vp, i, l, i, vp, i, vp, i, l, vp],
         "lpmx_gmls_swe_laplacian": [vp, i, vp, i, vp, vp, vp, i, vp, vp, vp, vp, l],
         "lpmx_ftle": [vp, i, i, vp, vp, i, l, i, vp, vp, l, vp, i, vp, vp, c_double_p],
         "lpmx_swe_rk2_step": [vp, d, d, d, d, i, ctypes.POINTER(SwePassive), i, ctypes.POINTER(SweActive), i, l, l,

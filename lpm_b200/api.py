@@ -394,6 +394,21 @@ class Engine:
                                                        _ptr(eps), _ptr(nn)), "lpmx_gmls_sphere_laplacian")
         return (lap, eps, nn) if diagnostics else lap
 
+    def gmls_sphere_interpolate(self, src_xyz, src_fields, tgt_xyz, params=None):
+        """Scalar GMLS point evaluation (remeshing): src_fields is a list of n_src arrays (or an (n_fields, n_src)
+        array); returns an (n_fields, n_tgt) array -- lpmx_gmls_sphere_interpolate.  numpy in, numpy out."""
+        params = gmls_params(params if params is not None else 3)
+        src_xyz, tgt_xyz = _f64(src_xyz), _f64(tgt_xyz)
+        F = [np.ascontiguousarray(f, dtype=np.float64) for f in src_fields]
+        nf, ns, nt = len(F), src_xyz.shape[0], tgt_xyz.shape[0]
+        out = np.empty((nf, nt))
+        pin = (ctypes.c_void_p * nf)(*[f.ctypes.data for f in F])
+        pout = (ctypes.c_void_p * nf)(*[out[k].ctypes.data for k in range(nf)])
+        self._check(self._L.lpmx_gmls_sphere_interpolate(self._h, ctypes.byref(params), ns, _ptr(src_xyz), LAYOUT_RIGHT, ns, nf,
+                                                         pin, nt, _ptr(tgt_xyz), LAYOUT_RIGHT, nt, pout),
+                    "lpmx_gmls_sphere_interpolate")
+        return out
+
     def gmls_provider(self, params=None):
         """(callback, user) for SWESolver.advance / swe_rk2_step: the built-in device-side surface-Laplacian provider."""
         return GmlsLaplacian(self, params)

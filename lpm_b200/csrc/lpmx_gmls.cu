@@ -81,15 +81,17 @@ __global__ void cell_key_kernel(int n, FieldView x, gmls::Cloud c, unsigned int*
   idx[i] = (int)i;
 }
 
-__global__ void permute_kernel(int n, const int* __restrict__ idx, FieldView x, const double* __restrict__ f,
-                               double* __restrict__ xs, double* __restrict__ fs) {
+__global__ void permute_xyz_kernel(int n, const int* __restrict__ idx, FieldView x, double* __restrict__ xs) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int j = idx[i];
   xs[i] = x(j, 0);
   xs[(long)n + i] = x(j, 1);
   xs[2L * n + i] = x(j, 2);
-  fs[i] = f[j];
+}
+__global__ void permute_scalar_kernel(int n, const int* __restrict__ idx, const double* __restrict__ f, double* __restrict__ fs) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i < n) fs[i] = f[idx[i]];
 }
 
 // cell_start[q] = first sorted position whose key is >= q (q = 0..ncell)
@@ -118,6 +120,21 @@ __global__ void __launch_bounds__(128) gmls_laplacian_kernel(gmls::Cloud c, gmls
   if (nn_out) nn_out[o] = r.n_neighbors;
 }
 
+struct InterpOut {
+  double* p[gmls::kInterpFields];
+};
+template <int OM, int KMAX>
+__global__ void __launch_bounds__(128) gmls_interpolate_kernel(gmls::Cloud c, gmls::Fields fl, gmls::Params p, int n_tgt, FieldView xt,
+                                                               InterpOut out) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= n_tgt) return;
+  double v[gmls::kInterpFields];
+  gmls::interpolate_at_point<OM, KMAX>(c, fl, p, xt(i, 0), xt(i, 1), xt(i, 2), v);
+#pragma unroll
+  for (int q = 0; q < gmls::kInterpFields; ++q)
+    if (out.p[q]) out.p[q][i] = v[q];
+}
+
 template <int OM>
 static void launch_gmls(cudaStream_t st, const gmls::Cloud& c, const gmls::Params& p, const int* idx, double* lap, double* eps_out,
                         int* nn_out) {
@@ -143,12 +160,10 @@ static int check_params(lpmx_handle_t h, const lpmx_gmls_params_t* q, gmls::Para
   return LPMX_OK;
 }
 
-// x: n x 3 device view; f, lap: device arrays of n; eps_out / nn_out optional device arrays
-static int gmls_laplacian_device(lpmx_handle_t h, const gmls::Params& p, int n, FieldView x, const double* f, double* lap,
-                                 double* eps_out, int* nn_out) {
-  if (n <= 0) return LPMX_OK;
+// Sort the cloud by grid cell: fills c (sorted coordinates, cell table; c.f is left null) and returns the sorted -> original
+// index map.  One 8-byte read back (the bounding radius sizes the grid on the host).
+static int build_cloud(lpmx_handle_t h, const gmls::Params& p, int n, FieldView x, gmls::Cloud* cloud, const int** perm) {
   const int threads = 256, blocks = (n + threads - 1) / threads;
-  // bounding radius of the cloud (one 8-byte read back; the grid is sized on the host)
   void* d_r = nullptr;
   LPMX_TRY(dev_buffer(h, "gmls_radius", 8, &d_r));
   LPMX_CUDA(h, cudaMemsetAsync(d_r, 0, 8, h->stream));
@@ -162,14 +177,12 @@ static int gmls_laplacian_device(lpmx_handle_t h, const gmls::Params& p, int n, 
   gmls::Cloud c;
   c.n = n, c.G = gd.G, c.box = gd.box, c.cell = gd.cell, c.inv_cell = 1.0 / gd.cell;
   const long ncell = (long)c.G * c.G * c.G;
-  void *d_key = nullptr, *d_key2 = nullptr, *d_idx = nullptr, *d_idx2 = nullptr, *d_xs = nullptr, *d_fs = nullptr, *d_cs = nullptr,
-       *d_tmp = nullptr;
+  void *d_key = nullptr, *d_key2 = nullptr, *d_idx = nullptr, *d_idx2 = nullptr, *d_xs = nullptr, *d_cs = nullptr, *d_tmp = nullptr;
   LPMX_TRY(dev_buffer(h, "gmls_key", 4 * (size_t)n, &d_key));
   LPMX_TRY(dev_buffer(h, "gmls_key2", 4 * (size_t)n, &d_key2));
   LPMX_TRY(dev_buffer(h, "gmls_idx", 4 * (size_t)n, &d_idx));
   LPMX_TRY(dev_buffer(h, "gmls_idx2", 4 * (size_t)n, &d_idx2));
   LPMX_TRY(dev_buffer(h, "gmls_xs", 8 * 3 * (size_t)n, &d_xs));
-  LPMX_TRY(dev_buffer(h, "gmls_fs", 8 * (size_t)n, &d_fs));
   LPMX_TRY(dev_buffer(h, "gmls_cell_start", 4 * (size_t)(ncell + 1), &d_cs));
   cell_key_kernel<<<blocks, threads, 0, h->stream>>>(n, x, c, (unsigned int*)d_key, (int*)d_idx);
   int bits = 1;
@@ -180,16 +193,77 @@ static int gmls_laplacian_device(lpmx_handle_t h, const gmls::Params& p, int n, 
   LPMX_TRY(dev_buffer(h, "gmls_sort_tmp", tmp_bytes + 16, &d_tmp));
   LPMX_CUDA(h, cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, (const unsigned int*)d_key, (unsigned int*)d_key2,
                                                (const int*)d_idx, (int*)d_idx2, n, 0, bits, h->stream));
-  permute_kernel<<<blocks, threads, 0, h->stream>>>(n, (const int*)d_idx2, x, f, (double*)d_xs, (double*)d_fs);
+  permute_xyz_kernel<<<blocks, threads, 0, h->stream>>>(n, (const int*)d_idx2, x, (double*)d_xs);
   cell_start_kernel<<<(unsigned)((ncell + 1 + threads - 1) / threads), threads, 0, h->stream>>>(ncell, n, (const unsigned int*)d_key2,
                                                                                                 (int*)d_cs);
-  c.x = (const double*)d_xs, c.f = (const double*)d_fs, c.cell_start = (const int*)d_cs;
-  const int om = p.samples_order > p.manifold_order ? p.samples_order : p.manifold_order;
-  if (om <= 2) launch_gmls<2>(h->stream, c, p, (const int*)d_idx2, lap, eps_out, nn_out);
-  else if (om == 3) launch_gmls<3>(h->stream, c, p, (const int*)d_idx2, lap, eps_out, nn_out);
-  else launch_gmls<4>(h->stream, c, p, (const int*)d_idx2, lap, eps_out, nn_out);
-  h->launches += 5;  // keys, sort (counted once), permute, cell table, Laplacian
+  h->launches += 4;  // keys, sort (counted once), permute, cell table
   LPMX_CUDA(h, cudaGetLastError());
+  c.x = (const double*)d_xs, c.f = nullptr, c.cell_start = (const int*)d_cs;
+  *cloud = c;
+  *perm = (const int*)d_idx2;
+  return LPMX_OK;
+}
+
+// x: n x 3 device view; f, lap: device arrays of n; eps_out / nn_out optional device arrays
+static int gmls_laplacian_device(lpmx_handle_t h, const gmls::Params& p, int n, FieldView x, const double* f, double* lap,
+                                 double* eps_out, int* nn_out) {
+  if (n <= 0) return LPMX_OK;
+  gmls::Cloud c;
+  const int* perm;
+  LPMX_TRY(build_cloud(h, p, n, x, &c, &perm));
+  void* d_fs = nullptr;
+  LPMX_TRY(dev_buffer(h, "gmls_fs", 8 * (size_t)n, &d_fs));
+  permute_scalar_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(n, perm, f, (double*)d_fs);
+  c.f = (const double*)d_fs;
+  const int om = p.samples_order > p.manifold_order ? p.samples_order : p.manifold_order;
+  if (om <= 2) launch_gmls<2>(h->stream, c, p, perm, lap, eps_out, nn_out);
+  else if (om == 3) launch_gmls<3>(h->stream, c, p, perm, lap, eps_out, nn_out);
+  else launch_gmls<4>(h->stream, c, p, perm, lap, eps_out, nn_out);
+  h->launches += 2;
+  LPMX_CUDA(h, cudaGetLastError());
+  return LPMX_OK;
+}
+
+// scalar point evaluation of n_fields source fields (device arrays of n_src) at n_tgt target points -> out[f] (device, n_tgt)
+static int gmls_interpolate_device(lpmx_handle_t h, const gmls::Params& p, int n_src, FieldView xs, int n_fields,
+                                   const double* const* fields, int n_tgt, FieldView xt, double* const* out) {
+  if (n_tgt <= 0 || n_fields <= 0) return LPMX_OK;
+  gmls::Cloud c;
+  const int* perm;
+  LPMX_TRY(build_cloud(h, p, n_src, xs, &c, &perm));
+  void* d_fs = nullptr;
+  LPMX_TRY(dev_buffer(h, "gmls_fs4", 8 * (size_t)gmls::kInterpFields * (size_t)n_src, &d_fs));
+  const int om = p.samples_order < 2 ? 2 : p.samples_order;
+  for (int f0 = 0; f0 < n_fields; f0 += gmls::kInterpFields) {
+    gmls::Fields fl;
+    InterpOut o;
+    for (int q = 0; q < gmls::kInterpFields; ++q) {
+      const int f = f0 + q < n_fields ? f0 + q : f0;  // unused slots repeat the first field of the batch
+      double* dst = (double*)d_fs + (size_t)q * n_src;
+      if (f0 + q < n_fields || q == 0) {
+        permute_scalar_kernel<<<(n_src + 255) / 256, 256, 0, h->stream>>>(n_src, perm, fields[f], dst);
+        ++h->launches;
+        fl.f[q] = dst;
+      } else {
+        fl.f[q] = (const double*)d_fs;
+      }
+      o.p[q] = f0 + q < n_fields ? out[f0 + q] : nullptr;
+    }
+    const unsigned blocks = (unsigned)((n_tgt + 127) / 128);
+    const bool small = p.min_neighbors <= 16;
+    if (om == 2) {
+      if (small) gmls_interpolate_kernel<2, 16><<<blocks, 128, 0, h->stream>>>(c, fl, p, n_tgt, xt, o);
+      else gmls_interpolate_kernel<2, gmls::kMaxK><<<blocks, 128, 0, h->stream>>>(c, fl, p, n_tgt, xt, o);
+    } else if (om == 3) {
+      if (small) gmls_interpolate_kernel<3, 16><<<blocks, 128, 0, h->stream>>>(c, fl, p, n_tgt, xt, o);
+      else gmls_interpolate_kernel<3, gmls::kMaxK><<<blocks, 128, 0, h->stream>>>(c, fl, p, n_tgt, xt, o);
+    } else {
+      if (small) gmls_interpolate_kernel<4, 16><<<blocks, 128, 0, h->stream>>>(c, fl, p, n_tgt, xt, o);
+      else gmls_interpolate_kernel<4, gmls::kMaxK><<<blocks, 128, 0, h->stream>>>(c, fl, p, n_tgt, xt, o);
+    }
+    ++h->launches;
+    LPMX_CUDA(h, cudaGetLastError());
+  }
   return LPMX_OK;
 }
 
@@ -319,6 +393,56 @@ int lpmx_gmls_sphere_laplacian(lpmx_handle_t h, const lpmx_gmls_params_t* params
   LPMX_TRY(stage_out_end(h, n_neighbors, dn, sizeof(int) * (size_t)n));
   if (dl != (void*)laplacian || (window_radius && de != (void*)window_radius) || (n_neighbors && dn != (void*)n_neighbors))
     LPMX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return LPMX_OK;
+}
+
+int lpmx_gmls_sphere_interpolate(lpmx_handle_t h, const lpmx_gmls_params_t* params, int n_src, const double* src_xyz, int src_layout,
+                                 long src_ld, int n_fields, const double* const* src_fields, int n_tgt, const double* tgt_xyz,
+                                 int tgt_layout, long tgt_ld, double* const* tgt_fields) {
+  if (!h) return LPMX_ERR_INVALID;
+  lpmx_gmls_params_t q;
+  if (!params) return set_error(h, LPMX_ERR_INVALID, "null gmls params");
+  q = *params;
+  if (q.manifold_order < 1) q.manifold_order = 1;
+  gmls::Params p;
+  if (q.samples_order == 1) {  // a linear fit is allowed for point evaluation
+    q.samples_order = 2;
+    LPMX_TRY(check_params(h, &q, &p));
+    p.samples_order = 1;
+  } else {
+    LPMX_TRY(check_params(h, &q, &p));
+  }
+  if (n_src < 0 || n_tgt < 0 || n_fields < 0 || n_fields > 64) return set_error(h, LPMX_ERR_INVALID, "bad extent");
+  if (n_tgt == 0 || n_fields == 0) return LPMX_OK;
+  if (n_src == 0) return set_error(h, LPMX_ERR_INVALID, "no source points");
+  if (!src_xyz || !tgt_xyz || !src_fields || !tgt_fields) return set_error(h, LPMX_ERR_INVALID, "null array");
+  for (int f = 0; f < n_fields; ++f)
+    if (!src_fields[f] || !tgt_fields[f]) return set_error(h, LPMX_ERR_INVALID, "null field %d", f);
+  if ((src_layout != LPMX_LAYOUT_LEFT && src_layout != LPMX_LAYOUT_RIGHT) || (tgt_layout != LPMX_LAYOUT_LEFT && tgt_layout != LPMX_LAYOUT_RIGHT))
+    return set_error(h, LPMX_ERR_INVALID, "unknown layout");
+  if ((src_layout == LPMX_LAYOUT_LEFT && src_ld < n_src) || (tgt_layout == LPMX_LAYOUT_LEFT && tgt_ld < n_tgt))
+    return set_error(h, LPMX_ERR_INVALID, "leading dimension smaller than extent");
+  LPMX_CUDA(h, cudaSetDevice(h->device));
+  const void *dxs, *dxt;
+  LPMX_TRY(stage_in(h, "gi_xs", src_xyz, field_bytes(src_layout, src_ld, n_src, 3), &dxs));
+  LPMX_TRY(stage_in(h, "gi_xt", tgt_xyz, field_bytes(tgt_layout, tgt_ld, n_tgt, 3), &dxt));
+  std::vector<const double*> din(n_fields);
+  std::vector<double*> dout(n_fields);
+  bool any_host = false;
+  for (int f = 0; f < n_fields; ++f) {
+    const std::string ni = "gi_in" + std::to_string(f), no = "gi_out" + std::to_string(f);
+    const void* d;
+    LPMX_TRY(stage_in(h, ni.c_str(), src_fields[f], sizeof(double) * (size_t)n_src, &d));
+    din[f] = (const double*)d;
+    void* o;
+    LPMX_TRY(stage_out_begin(h, no.c_str(), tgt_fields[f], sizeof(double) * (size_t)n_tgt, &o));
+    dout[f] = (double*)o;
+    any_host = any_host || (o != (void*)tgt_fields[f]);
+  }
+  LPMX_TRY(gmls_interpolate_device(h, p, n_src, field_view(dxs, src_layout, src_ld, 3), n_fields, din.data(), n_tgt,
+                                   field_view(dxt, tgt_layout, tgt_ld, 3), dout.data()));
+  for (int f = 0; f < n_fields; ++f) LPMX_TRY(stage_out_end(h, tgt_fields[f], dout[f], sizeof(double) * (size_t)n_tgt));
+  if (any_host) LPMX_CUDA(h, cudaStreamSynchronize(h->stream));
   return LPMX_OK;
 }
 

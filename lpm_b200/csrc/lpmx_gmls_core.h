@@ -340,6 +340,162 @@ LPMX_UNROLL
   return out;
 }
 
+// ---- scalar point evaluation at targets that are NOT cloud points (remeshing) ------------------------------------------------
+// gmls::Neighborhoods(src, tgt, params) + ScalarPointEvaluation / PointSample of CompadreRemesh
+// (src/mesh/lpm_compadre_remesh_impl.hpp:136-210): the value of the weighted least-squares Taylor fit at the chart
+// origin, i.e. coefficient 0.  The manifold reconstruction does not enter a point evaluation (the chart origin is the
+// target), so only the data fits are solved: NF fields share one moment matrix and one Cholesky factorisation.
+constexpr int kInterpFields = 4;
+struct Fields {
+  const double* f[kInterpFields];  // sorted like the cloud
+};
+
+template <int OM, int KMAX>
+LPMX_HD TargetResult interpolate_at_point(const Cloud& c, const Fields& fl, const Params& p, double x0, double x1, double x2,
+                                          double* value /* kInterpFields */) {
+  TargetResult out;
+  const int n = c.n;
+  const int ci = cell_coord(c, x0), cj = cell_coord(c, x1), ck = cell_coord(c, x2);
+  const int K = p.min_neighbors < KMAX ? p.min_neighbors : KMAX;
+  double best[KMAX];
+  double rK2 = 1e300;
+  for (int ring = 1;; ++ring) {
+LPMX_UNROLL
+    for (int q = 0; q < KMAX; ++q) best[q] = 1e300;
+    rK2 = 1e300;
+    const int i0 = ci - ring < 0 ? 0 : ci - ring, i1 = ci + ring >= c.G ? c.G - 1 : ci + ring;
+    const int j0 = cj - ring < 0 ? 0 : cj - ring, j1 = cj + ring >= c.G ? c.G - 1 : cj + ring;
+    const int k0 = ck - ring < 0 ? 0 : ck - ring, k1 = ck + ring >= c.G ? c.G - 1 : ck + ring;
+    for (int a = i0; a <= i1; ++a)
+      for (int b = j0; b <= j1; ++b) {
+        const long base = ((long)a * c.G + b) * c.G;
+        const int first = c.cell_start[base + k0], hi = c.cell_start[base + k1 + 1];
+        for (int j = first; j < hi; ++j) {
+          const double d0 = c.x[j] - x0, d1 = c.x[n + j] - x1, d2 = c.x[2 * n + j] - x2;
+          double d = d0 * d0 + d1 * d1 + d2 * d2;
+          if (d < rK2) {
+LPMX_UNROLL
+            for (int q = 0; q < KMAX; ++q) {
+              const double lo = d < best[q] ? d : best[q];
+              d = d < best[q] ? best[q] : d;
+              best[q] = lo;
+            }
+            rK2 = 1e300;
+LPMX_UNROLL
+            for (int q = 0; q < KMAX; ++q)
+              if (q == K - 1) rK2 = best[q];
+          }
+        }
+      }
+    const double reach = ring * c.cell;
+    const bool whole_grid = i0 == 0 && j0 == 0 && k0 == 0 && i1 == c.G - 1 && j1 == c.G - 1 && k1 == c.G - 1;
+    if ((rK2 < 1e299 && rK2 <= reach * reach) || whole_grid) break;
+  }
+  if (!(rK2 < 1e299)) {
+    for (int q = 0; q < kInterpFields; ++q) value[q] = NAN;
+    out.lap = NAN, out.eps = 0.0, out.n_neighbors = 0;
+    return out;
+  }
+  const double eps = (rK2 > 0.0 ? sqrt(rK2) : 1e-14) * p.eps_multiplier;
+  const double eps2 = eps * eps, ieps = 1.0 / eps;
+  double nrm[3] = {x0, x1, x2};
+  const double inv = 1.0 / sqrt(x0 * x0 + x1 * x1 + x2 * x2);
+  nrm[0] *= inv, nrm[1] *= inv, nrm[2] *= inv;
+  double t1[3], t2[3];
+  tangent_frame(nrm, t1, t2);
+  constexpr int D = 2 * OM;
+  double mu[D + 1][D + 1];
+  double mf[kInterpFields][OM + 1][OM + 1];
+LPMX_UNROLL
+  for (int a = 0; a <= D; ++a)
+LPMX_UNROLL
+    for (int b = 0; b <= D; ++b) mu[a][b] = 0.0;
+LPMX_UNROLL
+  for (int q = 0; q < kInterpFields; ++q)
+LPMX_UNROLL
+    for (int a = 0; a <= OM; ++a)
+LPMX_UNROLL
+      for (int b = 0; b <= OM; ++b) mf[q][a][b] = 0.0;
+  int count = 0;
+  {
+    int ring = (int)ceil(eps * c.inv_cell);
+    if (ring < 1) ring = 1;
+    const int i0 = ci - ring < 0 ? 0 : ci - ring, i1 = ci + ring >= c.G ? c.G - 1 : ci + ring;
+    const int j0 = cj - ring < 0 ? 0 : cj - ring, j1 = cj + ring >= c.G ? c.G - 1 : cj + ring;
+    const int k0 = ck - ring < 0 ? 0 : ck - ring, k1 = ck + ring >= c.G ? c.G - 1 : ck + ring;
+    for (int a = i0; a <= i1; ++a)
+      for (int b = j0; b <= j1; ++b) {
+        const long base = ((long)a * c.G + b) * c.G;
+        const int first = c.cell_start[base + k0], hi = c.cell_start[base + k1 + 1];
+        for (int j = first; j < hi; ++j) {
+          const double d0 = c.x[j] - x0, d1 = c.x[n + j] - x1, d2 = c.x[2 * n + j] - x2;
+          const double d = d0 * d0 + d1 * d1 + d2 * d2;
+          if (!(d < eps2)) continue;
+          ++count;
+          const double u = (d0 * t1[0] + d1 * t1[1] + d2 * t1[2]) * ieps;
+          const double v = (d0 * t2[0] + d1 * t2[1] + d2 * t2[2]) * ieps;
+          const double w = power_weight(sqrt(u * u + v * v), p.weight_pwr);
+          double wf[kInterpFields];
+LPMX_UNROLL
+          for (int q = 0; q < kInterpFields; ++q) wf[q] = w * fl.f[q][j];
+          double pu[D + 1], pv[D + 1];
+          pu[0] = 1.0, pv[0] = 1.0;
+LPMX_UNROLL
+          for (int q = 1; q <= D; ++q) pu[q] = pu[q - 1] * u, pv[q] = pv[q - 1] * v;
+LPMX_UNROLL
+          for (int qa = 0; qa <= D; ++qa)
+LPMX_UNROLL
+            for (int qb = 0; qb <= D - qa; ++qb) {
+              const double m = pu[qa] * pv[qb];
+              mu[qa][qb] += w * m;
+              if (qa + qb <= OM) {
+LPMX_UNROLL
+                for (int q = 0; q < kInterpFields; ++q) mf[q][qa][qb] += wf[q] * m;
+              }
+            }
+        }
+      }
+  }
+  out.eps = eps;
+  out.n_neighbors = count;
+  out.lap = 0.0;
+  constexpr int NPM = (OM + 1) * (OM + 2) / 2;
+  double M[NPM * (NPM + 1) / 2], rf[kInterpFields][NPM];
+  {
+    constexpr double ifact[9] = {1.0, 1.0, 0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0, 1.0 / 40320.0};
+    int r = 0;
+LPMX_UNROLL
+    for (int nr = 0; nr <= OM; ++nr)
+LPMX_UNROLL
+      for (int ayr = 0; ayr <= nr; ++ayr) {
+        const int axr = nr - ayr;
+        const double sr = ifact[axr] * ifact[ayr];
+LPMX_UNROLL
+        for (int q = 0; q < kInterpFields; ++q) rf[q][r] = mf[q][axr][ayr] * sr;
+        int q2 = 0;
+LPMX_UNROLL
+        for (int nq = 0; nq <= OM; ++nq)
+LPMX_UNROLL
+          for (int ayq = 0; ayq <= nq; ++ayq) {
+            const int axq = nq - ayq;
+            if (q2 <= r) M[tri(r, q2)] = mu[axr + axq][ayr + ayq] * (sr * (ifact[axq] * ifact[ayq]));
+            ++q2;
+          }
+        ++r;
+      }
+  }
+  const int npf = np_of(p.samples_order);
+  if (!cholesky_factor(npf, M)) {
+    for (int q = 0; q < kInterpFields; ++q) value[q] = NAN;
+    return out;
+  }
+  for (int q = 0; q < kInterpFields; ++q) {
+    cholesky_solve(npf, M, rf[q]);
+    value[q] = rf[q][0];
+  }
+  return out;
+}
+
 // run-time (orders, min_neighbors) -> compile-time instance
 LPMX_HD TargetResult laplacian_at_target_dispatch(const Cloud& c, const Params& p, int it) {
   const int om = p.samples_order > p.manifold_order ? p.samples_order : p.manifold_order;

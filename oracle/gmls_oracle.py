@@ -91,3 +91,31 @@ def sphere_laplacian(xyz, f, p, targets=None):
                       [d2(af, 4) - d2(ah, 4) * q, d2(af, 5) - d2(ah, 5) * q]])
         lap[i] = float((ginv * H).sum())
     return lap, eps, np.array([len(l) for l in lists])
+
+
+def sphere_interpolate(src_xyz, src_fields, tgt_xyz, p):
+    """ScalarPointEvaluation of CompadreRemesh (src/mesh/lpm_compadre_remesh_impl.hpp:136-210) with
+    gmls::Neighborhoods(src, tgt, params): value at each target of the weighted least-squares Taylor fit of every field
+    (rows of src_fields) over the source points inside the target's window."""
+    from scipy.spatial import cKDTree
+    src_xyz, tgt_xyz = np.asarray(src_xyz, dtype=np.float64), np.asarray(tgt_xyz, dtype=np.float64)
+    F = np.atleast_2d(np.asarray(src_fields, dtype=np.float64))
+    tree = cKDTree(src_xyz)
+    dk, _ = tree.query(tgt_xyz, k=p["min_neighbors"])
+    eps = np.where(dk[:, -1] > 0, dk[:, -1], 1e-14) * p["eps_multiplier"]
+    out = np.full((F.shape[0], tgt_xyz.shape[0]), np.nan)
+    for i, x in enumerate(tgt_xyz):
+        nb = np.array([j for j in tree.query_ball_point(x, eps[i]) if np.sum((src_xyz[j] - x) ** 2) < eps[i] ** 2])
+        nrm = x / np.linalg.norm(x)
+        a = np.eye(3)[np.argmin(np.abs(nrm))]
+        t1 = np.cross(nrm, a)
+        t1 /= np.linalg.norm(t1)
+        t2 = np.cross(nrm, t1)
+        d = src_xyz[nb] - x
+        s, t = d @ t1, d @ t2
+        e = eps[i]
+        sw = np.sqrt(np.maximum(1 - np.sqrt(s * s + t * t) / e, 0.0) ** p["weight_pwr"])
+        P = _basis(p["samples_order"], s / e, t / e) * sw[:, None]
+        coef = np.linalg.lstsq(P, (F[:, nb] * sw).T, rcond=None)[0]
+        out[:, i] = coef[0]
+    return out

@@ -80,3 +80,24 @@ def test_swe_tc2_example(built, seed):
     out, log = _run(built, "sphere_swe_tc2", "-s", seed, "-d", "3", "-tf", "0.02", "-n", "4")
     assert out["steps"] == 4 and out["gpu_launches"] > 0
     assert out["depth_l2"] < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("strategy", ["direct", "indirect"])
+def test_ic2d_example_with_remeshing(built, strategy):
+    """examples/sphere_rh54.cpp:255-300: rebuild the particle set every remesh_interval steps (CompadreRemesh uniform_*);
+    the RH54 wave is steady in shape, so energy and enstrophy must survive two remeshes."""
+    ref, _ = _run(built, "sphere_rh54", "-d", "4", "-tf", "0.06", "-n", "6")
+    out, log = _run(built, "sphere_rh54", "-d", "4", "-tf", "0.06", "-n", "6", "-rm", "3", "-rs", strategy)
+    assert "remeshes: 2" in log
+    assert out["ke_drift"] < 5e-3 and out["enstrophy_drift"] < 5e-3
+    assert abs(out["ke_drift"] - ref["ke_drift"]) < 5e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lap", ["gmls", "exact"])
+def test_swe_tc2_example_surface_laplacians(built, lap):
+    """sphere_swe_tc2 with the reference's configuration (GMLS of order 4, examples/sphere_swe_tc2.cpp:136-139), evaluated
+    on the device, and with the closed-form Laplacian: both keep the steady state."""
+    out, log = _run(built, "sphere_swe_tc2", "-d", "4", "-tf", "0.02", "-n", "4", "-lap", lap)
+    assert out["steps"] == 4 and out["depth_l2"] < 1e-3 and out["zeta_l2"] < 1e-2

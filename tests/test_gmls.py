@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from conftest import field_rel_err
-from gmls_util import core_host_laplacian, harmonic_field
+from gmls_util import core_host_interpolate, core_host_laplacian, harmonic_field, remesh_case
 from lpm_b200 import gallery
 from lpm_b200.api import PolyMesh2d
 from oracle import gmls_oracle as GO
@@ -93,7 +93,37 @@ def test_gather_scatter_restatement_round_trip():
     assert np.array_equal(v2, vd) and np.array_equal(f2[leaf], fd[leaf]) and (f2[~leaf] == -1.0).all()
 
 
+def test_interpolation_core_matches_numpy_and_converges():
+    """Remesh interpolation (ScalarPointEvaluation at new particles): host build of the product arithmetic against the
+    numpy restatement, five fields at once (two batches of kInterpFields = 4), and convergence to the exact values."""
+    src, F, tgt, exact = remesh_case(3)
+    for order in (1, 2, 4):
+        p = GO.params(order)
+        got = core_host_interpolate(src, F, tgt, p)
+        assert np.abs(got - GO.sphere_interpolate(src, F, tgt, p)).max() < 1e-12, order
+    e = {}
+    for depth in (3, 4):
+        src, F, tgt, exact = remesh_case(depth)
+        for order in (2, 4):
+            e[(depth, order)] = np.abs(core_host_interpolate(src, F, tgt, GO.params(order)) - exact).max()
+    assert e[(4, 2)] < 5e-4 and e[(4, 4)] < 1e-5
+    assert np.log2(e[(3, 2)] / e[(4, 2)]) > 2.5 and np.log2(e[(3, 4)] / e[(4, 4)]) > 4.5  # O(h^(m+1))
+
+
 # ------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("depth,order", [(3, 1), (3, 3), (4, 4), (5, 4)])
+def test_gpu_interpolation_matches_host_arithmetic(engine, depth, order):
+    src, F, tgt, exact = remesh_case(depth)
+    p = GO.params(order)
+    got = engine.gmls_sphere_interpolate(src, list(F), tgt, order)
+    assert np.abs(got - core_host_interpolate(src, F, tgt, p)).max() < 1e-11
+    if order == 4:
+        assert np.abs(got - exact).max() < (1e-5 if depth == 4 else 5e-7)
+    if depth == 3:
+        assert np.abs(got - GO.sphere_interpolate(src, F, tgt, p)).max() < 1e-11
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed,depth,order", [("cubed", 3, 2), ("icos", 3, 3), ("cubed", 4, 4), ("icos", 5, 4)])
 def test_gpu_laplacian_matches_host_arithmetic_and_numpy(engine, seed, depth, order):
