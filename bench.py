@@ -208,6 +208,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly ONE JSON line: anything a library prints there while we run (NCCL's version banner
+    # under NCCL_DEBUG=VERSION, for one) is sent to stderr; the line itself goes to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     from lpm_b200.api import BVESolver, Engine, IC2DSolver, SWESolver
     from lpm_b200.dist import env_rank_world, init_engine_comm
@@ -438,7 +444,8 @@ def main():
             "state_check": state_check,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
