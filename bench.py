@@ -354,7 +354,7 @@ def main():
         "traffic": None,
     }
     prof = os.path.join(ROOT, "profiles", "r1_pair_sum_dram.json")
-    if os.path.exists(prof):
+    if os.path.exists(prof) and args.workload == "rh54_cubed7" and args.stepper == "bve_rk4":  # captured on that launch shape
         try:
             roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:
