@@ -107,6 +107,25 @@ int lpmx_mesh_sizes(lpmx_mesh_t mesh, int* n_verts, int* n_edges, int* n_faces, 
  * element count; *is_real = 1 for double arrays, 0 for int arrays, 2 for unsigned char. */
 int lpmx_mesh_array(lpmx_mesh_t mesh, int array_id, const void** data, long* count, int* is_real);
 
+/* Overwrite one of the four coordinate arrays (LPMX_MESH_VERT_XYZ, _VERT_LAG_XYZ, _FACE_XYZ, _FACE_LAG_XYZ) with the
+ * caller's current values (`count` doubles, LayoutRight) -- the particles move between mesh construction and an adaptive
+ * refinement, and the reference divides faces from the coordinates as they are then. */
+int lpmx_mesh_update_array(lpmx_mesh_t mesh, int array_id, const double* data, long count);
+
+/* outcomes of lpmx_mesh_divide_flagged_faces */
+#define LPMX_AMR_DIVIDED_ALL 0   /* every flagged face was divided                                                   */
+#define LPMX_AMR_NO_SPACE 1      /* nothing divided: flag count > (max_faces - n_faces) / 4 (the reference warns and returns) */
+#define LPMX_AMR_LIMIT_REACHED 2 /* flagged faces with level > max_level were left alone                              */
+
+/* PolyMesh2d<Seed>::divide_flagged_faces (src/mesh/lpm_polymesh2d_impl.hpp:124-173): divide, in index order, every face
+ * i < n_faces_host() with flags[i] != 0 whose level is <= max_level (the reference passes init_depth + amr_limit; root
+ * faces have level 1 here, see LPMX_MESH_FACE_LEVEL), then rescan the leaves (Faces::scan_leaves).  max_faces is
+ * PolyMeshParameters::nmaxfaces (src/mesh/lpm_polymesh2d.hpp:68-71, allocations for depth + amr_buffer).  flags has
+ * n_flags >= n_faces entries (only the first n_faces are read).  A flagged face that is already divided is an error
+ * (LPMX_ERR_INVALID; the reference asserts).  Pointers obtained from lpmx_mesh_array are invalidated. */
+int lpmx_mesh_divide_flagged_faces(lpmx_mesh_t mesh, const unsigned char* flags, int n_flags, int max_faces,
+                                   int max_level, int* n_divided, int* outcome);
+
 /* ------------------------------------------------------------------------------------------
  * Engine handle: one per process and GPU.
  * ------------------------------------------------------------------------------------------ */
@@ -413,6 +432,43 @@ typedef struct lpmx_gmls_provider_s {
 int lpmx_gmls_swe_laplacian(void* user, int stage, void* cuda_stream, int n_passive, const double* passive_xyz,
                             const double* passive_surf, double* passive_laps, int n_active, const double* active_xyz,
                             const double* active_surf, const unsigned char* active_mask, double* active_laps, long xyz_ld);
+
+/* ------------------------------------------------------------------------------------------
+ * Adaptive refinement flags (src/mesh/lpm_refinement_flags.hpp, src/mesh/lpm_refinement.hpp): O(N) streaming kernels
+ * over the faces.  A flag functor turns flags[i] on where its criterion holds on an undivided face and never turns a
+ * flag off; Refinement<Seed>::iterate (lpm_refinement.hpp:28-41) clears the flags, runs the functor over
+ * [start, end) and counts.  NeighborsFlag (:30-53, marked "likely won't work on device", used by no driver) is not provided.
+ * ------------------------------------------------------------------------------------------ */
+#define LPMX_FLAG_SCALAR_MAX 0         /* ScalarMaxFlag (:132-183):        |f_i| > tol                                  */
+#define LPMX_FLAG_SCALAR_INTEGRAL 1    /* ScalarIntegralFlag (:185-229):   |f_i| A_i > tol                              */
+#define LPMX_FLAG_SCALAR_VARIATION 2   /* ScalarVariationFlag (:231-310):  max - min over {f_i, f at the face's vertices} > tol */
+#define LPMX_FLAG_FLOW_MAP_VARIATION 3 /* FlowMapVariationFlag (:55-130):  sum_k (max - min over the face's vertices of lag_k) > tol */
+
+typedef struct lpmx_flag_desc_s {
+  int kind;                  /* LPMX_FLAG_*                                                                      */
+  int n_faces, n_verts;      /* mesh.n_faces_host(), mesh.n_vertices_host()                                      */
+  int n_face_verts;          /* 3 or 4                                                                           */
+  const double* face_vals;   /* [n_faces]  kinds 0-2                                                             */
+  const double* area;        /* [n_faces]  kind 1                                                                */
+  const double* vert_vals;   /* [n_verts]  kind 2                                                                */
+  const int* face_verts;     /* [n_faces][n_face_verts] row-major, kinds 2-3                                     */
+  const double* vert_lag;    /* Real*[ndim] vertex Lagrangian coordinates, kind 3                                */
+  int ndim, layout;          /* 3 (sphere) or 2 (plane); LPMX_LAYOUT_* of vert_lag                               */
+  long ld;
+  const unsigned char* mask; /* [n_faces]  faces.mask                                                            */
+  double tol;                /* absolute tolerance used by lpmx_refine_flag                                      */
+} lpmx_flag_desc_t;
+
+/* The reduction of <Flag>::set_tol_from_relative_value(): the maximum the relative tolerance multiplies (kind 0:
+ * max |f_i| over ALL faces; 1: max |f_i| A_i over all faces; 2, 3: the variation over undivided faces).  As in the
+ * reference the caller then sets tol = relative_tol * max_value.  Host or device pointers. */
+int lpmx_refine_flag_max(lpmx_handle_t h, const lpmx_flag_desc_t* flag, double* max_value);
+
+/* Run the flag functor over faces [start, end): flags[i] |= criterion(i) for undivided faces.  flags: n_faces bytes,
+ * in/out (host or device); clear_first != 0 zeroes all n_faces entries first (Refinement::iterate).  *count = number of
+ * non-zero flags in [start, end) afterwards (nullable). */
+int lpmx_refine_flag(lpmx_handle_t h, const lpmx_flag_desc_t* flag, int start, int end, int clear_first,
+                     unsigned char* flags, int* count);
 
 /* ------------------------------------------------------------------------------------------
  * Planar problems (PlaneGeometry): Real*[2] views.  LPMX_LAYOUT_RIGHT is x[i*2+k], LPMX_LAYOUT_LEFT is x[k*ld+i].

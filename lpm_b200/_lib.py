@@ -68,6 +68,14 @@ class GmlsParams(ctypes.Structure):
                 ("ambient_dim", ctypes.c_int), ("topo_dim", ctypes.c_int), ("min_neighbors", ctypes.c_int)]
 
 
+class FlagDesc(ctypes.Structure):
+    """lpmx_flag_desc_t: one refinement-flag functor of src/mesh/lpm_refinement_flags.hpp"""
+    _fields_ = [("kind", ctypes.c_int), ("n_faces", ctypes.c_int), ("n_verts", ctypes.c_int), ("n_face_verts", ctypes.c_int),
+                ("face_vals", ctypes.c_void_p), ("area", ctypes.c_void_p), ("vert_vals", ctypes.c_void_p),
+                ("face_verts", ctypes.c_void_p), ("vert_lag", ctypes.c_void_p), ("ndim", ctypes.c_int),
+                ("layout", ctypes.c_int), ("ld", ctypes.c_long), ("mask", ctypes.c_void_p), ("tol", ctypes.c_double)]
+
+
 class GmlsProvider(ctypes.Structure):
     """lpmx_gmls_provider_t"""
     _fields_ = [("handle", ctypes.c_void_p), ("params", GmlsParams)]
@@ -113,6 +121,10 @@ def _declare(L):
         "lpmx_mesh_destroy": [vp],
         "lpmx_mesh_sizes": [vp, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p],
         "lpmx_mesh_array": [vp, i, ctypes.POINTER(vp), c_long_p, c_int_p],
+        "lpmx_mesh_update_array": [vp, i, vp, l],
+        "lpmx_mesh_divide_flagged_faces": [vp, vp, i, i, i, c_int_p, c_int_p],
+        "lpmx_refine_flag_max": [vp, ctypes.POINTER(FlagDesc), ctypes.POINTER(ctypes.c_double)],
+        "lpmx_refine_flag": [vp, ctypes.POINTER(FlagDesc), i, i, i, vp, c_int_p],
         "lpmx_create": [ctypes.POINTER(vp), i],
         "lpmx_destroy": [vp],
         "lpmx_sync": [vp],

@@ -46,37 +46,73 @@ def max_allocations(seed, depth):
 
 
 class PolyMesh2d:
-    """Uniform tree mesh on the sphere: PolyMesh2d<Seed>::tree_init (host; no GPU needed)."""
+    """Tree mesh on the sphere: PolyMesh2d<Seed>::tree_init, and divide_flagged_faces for adaptive refinement
+    (host; no GPU needed).  amr_buffer / amr_limit as in PolyMeshParameters (src/mesh/lpm_polymesh2d.hpp:32-72):
+    nmaxfaces is sized for depth + amr_buffer, a face may be refined amr_limit times beyond `depth`."""
 
-    def __init__(self, seed, depth, radius=1.0):
+    AMR_DIVIDED_ALL, AMR_NO_SPACE, AMR_LIMIT_REACHED = 0, 1, 2
+
+    def __init__(self, seed, depth, radius=1.0, amr_buffer=0, amr_limit=0):
         L = _lib.lib()
         self.seed = _seed_id(seed)
         self.depth = depth
+        self.amr_buffer, self.amr_limit = amr_buffer, amr_limit
+        self.nmaxverts, self.nmaxedges, self.nmaxfaces = max_allocations(seed, depth + amr_buffer)
         m = ctypes.c_void_p()
         rc = L.lpmx_mesh_create(self.seed, depth, float(radius), ctypes.byref(m))
         if rc:
             raise LpmxError(rc, "lpmx_mesh_create")
-        try:
-            s = [ctypes.c_int() for _ in range(6)]
-            L.lpmx_mesh_sizes(m, *s)
-            (self.n_verts, self.n_edges, self.n_faces, self.n_face_leaves, self.n_edge_leaves,
-             self.n_face_verts) = [x.value for x in s]
-            for name, (aid, width) in _MESH_ARRAYS.items():
-                p, n, kind = ctypes.c_void_p(), ctypes.c_long(), ctypes.c_int()
-                rc = L.lpmx_mesh_array(m, aid, ctypes.byref(p), ctypes.byref(n), ctypes.byref(kind))
+        self._m = m
+        self._fetch()
+
+    def __del__(self):
+        m, self._m = getattr(self, "_m", None), None
+        if m:
+            try:
+                _lib.lib().lpmx_mesh_destroy(m)
+            except Exception:
+                pass
+
+    def _fetch(self):
+        L, m = _lib.lib(), self._m
+        s = [ctypes.c_int() for _ in range(6)]
+        L.lpmx_mesh_sizes(m, *s)
+        (self.n_verts, self.n_edges, self.n_faces, self.n_face_leaves, self.n_edge_leaves,
+         self.n_face_verts) = [x.value for x in s]
+        for name, (aid, width) in _MESH_ARRAYS.items():
+            p, n, kind = ctypes.c_void_p(), ctypes.c_long(), ctypes.c_int()
+            rc = L.lpmx_mesh_array(m, aid, ctypes.byref(p), ctypes.byref(n), ctypes.byref(kind))
+            if rc:
+                raise LpmxError(rc, "lpmx_mesh_array")
+            ctype = {0: ctypes.c_int, 1: ctypes.c_double, 2: ctypes.c_ubyte}[kind.value]
+            if n.value == 0:
+                arr = np.zeros(0, dtype=np.dtype(ctype))
+            else:
+                arr = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctype)), shape=(n.value,)).copy()
+            w = self.n_face_verts if width == -1 else width
+            if w > 1:
+                arr = arr.reshape(-1, w)
+            setattr(self, name, arr)
+
+    def divide_flagged_faces(self, flags, push_coordinates=True):
+        """PolyMesh2d::divide_flagged_faces (src/mesh/lpm_polymesh2d_impl.hpp:124-173).  The coordinate arrays of this object
+        (which the caller may have advected) are handed to the generator first, the arrays are re-read afterwards.
+        Returns (n_divided, outcome) with outcome one of AMR_DIVIDED_ALL / AMR_NO_SPACE / AMR_LIMIT_REACHED."""
+        L = _lib.lib()
+        if push_coordinates:
+            for name in ("vert_xyz", "vert_lag_xyz", "face_xyz", "face_lag_xyz"):
+                a = np.ascontiguousarray(getattr(self, name), dtype=np.float64)
+                rc = L.lpmx_mesh_update_array(self._m, _MESH_ARRAYS[name][0], a.ctypes.data, a.size)
                 if rc:
-                    raise LpmxError(rc, "lpmx_mesh_array")
-                ctype = {0: ctypes.c_int, 1: ctypes.c_double, 2: ctypes.c_ubyte}[kind.value]
-                if n.value == 0:
-                    arr = np.zeros(0, dtype=np.dtype(ctype))
-                else:
-                    arr = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctype)), shape=(n.value,)).copy()
-                w = self.n_face_verts if width == -1 else width
-                if w > 1:
-                    arr = arr.reshape(-1, w)
-                setattr(self, name, arr)
-        finally:
-            L.lpmx_mesh_destroy(m)
+                    raise LpmxError(rc, "lpmx_mesh_update_array")
+        f = np.ascontiguousarray(flags, dtype=np.uint8)
+        nd, oc = ctypes.c_int(), ctypes.c_int()
+        rc = L.lpmx_mesh_divide_flagged_faces(self._m, f.ctypes.data, f.size, self.nmaxfaces, self.depth + self.amr_limit,
+                                              ctypes.byref(nd), ctypes.byref(oc))
+        if rc:
+            raise LpmxError(rc, "lpmx_mesh_divide_flagged_faces")
+        self._fetch()
+        return nd.value, oc.value
 
     # names used by the reference's examples
     def n_vertices_host(self):
@@ -352,6 +388,60 @@ class Engine:
                                       _ptr(face_ref), nf, _ptr(fv), verts_layout, _ptr(_u8(face_mask)), _ptr(ftle),
                                       ctypes.byref(mx)), "lpmx_ftle")
         return ftle, mx.value
+
+    # ---- adaptive-refinement flags (src/mesh/lpm_refinement_flags.hpp, lpm_refinement.hpp) ----
+    FLAG_KINDS = {"scalar_max": 0, "scalar_integral": 1, "scalar_variation": 2, "flow_map_variation": 3}
+
+    def _flag_desc(self, kind, face_mask, face_vals=None, area=None, vert_vals=None, face_verts=None, vert_lag=None, tol=0.0):
+        keep = []  # arrays must outlive the call
+        d = _lib.FlagDesc()
+        d.kind = self.FLAG_KINDS[kind] if isinstance(kind, str) else int(kind)
+        mask = _u8(face_mask)
+        keep.append(mask)
+        d.n_faces = mask.shape[0]
+        d.mask = _ptr(mask).value if d.n_faces else None
+
+        def put(field, a):
+            if a is not None:
+                keep.append(a)
+                setattr(d, field, _ptr(a).value if a.shape[0] else None)
+        put("face_vals", _f64(face_vals))
+        put("area", _f64(area))
+        vv = _f64(vert_vals)
+        put("vert_vals", vv)
+        if face_verts is not None:
+            fv = face_verts if hasattr(face_verts, "data_ptr") else np.ascontiguousarray(face_verts, dtype=np.int32)
+            d.n_face_verts = fv.shape[1]
+            put("face_verts", fv)
+        vl = _f64(vert_lag)
+        if vl is not None:
+            d.ndim, d.layout, d.ld = vl.shape[1], LAYOUT_RIGHT, vl.shape[0]
+            put("vert_lag", vl)
+        d.n_verts = vv.shape[0] if vv is not None else (vl.shape[0] if vl is not None else 0)
+        d.tol = float(tol)
+        return d, keep
+
+    def refine_flag_max(self, kind, face_mask, **arrays):
+        """The reduction of <Flag>::set_tol_from_relative_value(): tol = relative_tol * refine_flag_max(...)."""
+        d, keep = self._flag_desc(kind, face_mask, **arrays)
+        mx = ctypes.c_double()
+        self._check(self._L.lpmx_refine_flag_max(self._h, ctypes.byref(d), ctypes.byref(mx)), "lpmx_refine_flag_max")
+        return mx.value
+
+    def refine_flag(self, kind, face_mask, tol, start=0, end=None, flags=None, **arrays):
+        """Refinement::iterate with one flag functor over faces [start, end): returns (flags, count).  With flags=None
+        the flags start cleared; an existing uint8 array is updated in place (flags are only ever switched on)."""
+        d, keep = self._flag_desc(kind, face_mask, tol=tol, **arrays)
+        end = d.n_faces if end is None else end
+        clear = flags is None
+        if flags is None:
+            flags = np.zeros(d.n_faces, dtype=np.uint8)
+        elif isinstance(flags, np.ndarray) and (flags.dtype != np.uint8 or not flags.flags.c_contiguous):
+            raise ValueError("flags is an in/out argument: pass a C-contiguous uint8 array")
+        ct = ctypes.c_int()
+        self._check(self._L.lpmx_refine_flag(self._h, ctypes.byref(d), start, end, 1 if clear else 0, _ptr(flags),
+                                             ctypes.byref(ct)), "lpmx_refine_flag")
+        return flags, ct.value
 
     # ---- gather / scatter and the GMLS surface Laplacian (the steps either side of the SWE sums) ----
     def gather_mesh_data(self, vert_data, face_data, face_mask):

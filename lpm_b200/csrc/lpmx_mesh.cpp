@@ -15,6 +15,7 @@
 // is what fixes every integer array); nothing here is Kokkos-shaped.  Floating-point expressions
 // are evaluated exactly as written, and this file is compiled with -ffp-contract=off so the
 // coordinates do not depend on the compiler's FMA contraction choices.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -181,6 +182,15 @@ struct lpmx_mesh_s {
 
   void divide_tri(int f);
   void divide_quad(int f);
+  // Faces::scan_leaves: exclusive scan of !has_kids
+  void scan_leaves() {
+    fleaf.resize(nf());
+    int psum = 0;
+    for (int i = 0; i < nf(); ++i) {
+      fleaf[i] = psum;
+      psum += face_has_kids(i) ? 0 : 1;
+    }
+  }
   void finish_parent(int f, int first_kid) {
     for (int i = 0; i < 4; ++i) fkids[4 * f + i] = first_kid + i;
     farea[f] = 0.0;
@@ -434,13 +444,7 @@ int lpmx_mesh_create(int seed, int depth, double radius, lpmx_mesh_t* out) {
       }
       start = stop - 1;
     }
-    // Faces::scan_leaves: exclusive scan of !has_kids
-    m->fleaf.resize(m->nf());
-    int psum = 0;
-    for (int i = 0; i < m->nf(); ++i) {
-      m->fleaf[i] = psum;
-      psum += m->face_has_kids(i) ? 0 : 1;
-    }
+    m->scan_leaves();
   } catch (const std::bad_alloc&) {
     delete m;
     return LPMX_ERR_NOMEM;
@@ -463,6 +467,64 @@ int lpmx_mesh_sizes(lpmx_mesh_t m, int* n_verts, int* n_edges, int* n_faces, int
   if (n_face_leaves) *n_face_leaves = m->face_leaves;
   if (n_edge_leaves) *n_edge_leaves = m->edge_leaves;
   if (n_face_verts) *n_face_verts = m->nfv;
+  return LPMX_OK;
+}
+
+int lpmx_mesh_update_array(lpmx_mesh_t m, int id, const double* data, long count) {
+  if (!m || !data) return LPMX_ERR_INVALID;
+  std::vector<double>* dst = nullptr;
+  switch (id) {
+    case LPMX_MESH_VERT_XYZ: dst = &m->vx; break;
+    case LPMX_MESH_VERT_LAG_XYZ: dst = &m->vlag; break;
+    case LPMX_MESH_FACE_XYZ: dst = &m->fx; break;
+    case LPMX_MESH_FACE_LAG_XYZ: dst = &m->flag; break;
+    default: return LPMX_ERR_INVALID;
+  }
+  if (count != (long)dst->size()) return LPMX_ERR_INVALID;
+  std::copy(data, data + count, dst->begin());
+  return LPMX_OK;
+}
+
+// PolyMesh2d::divide_flagged_faces (lpm_polymesh2d_impl.hpp:124-173)
+int lpmx_mesh_divide_flagged_faces(lpmx_mesh_t m, const unsigned char* flags, int n_flags, int max_faces, int max_level,
+                                   int* n_divided, int* outcome) {
+  if (!m || (!flags && n_flags > 0) || n_flags < 0) return LPMX_ERR_INVALID;
+  const int n_in = m->nf();
+  if (n_flags < n_in) return LPMX_ERR_INVALID;
+  int flag_count = 0;
+  for (int i = 0; i < n_in; ++i) {
+    if (flags[i]) {
+      if (m->face_has_kids(i)) return LPMX_ERR_INVALID;
+      ++flag_count;
+    }
+  }
+  if (n_divided) *n_divided = 0;
+  const int space_left = max_faces - n_in;
+  if (flag_count > space_left / 4) {  // "not enough memory": warn and return, nothing divided (:138-144)
+    if (outcome) *outcome = LPMX_AMR_NO_SPACE;
+    return LPMX_OK;
+  }
+  int refine_count = 0;
+  bool limit_reached = false;
+  try {
+    for (int i = 0; i < n_in; ++i) {
+      if (!flags[i]) continue;
+      if (m->flevel[i] <= max_level) {
+        if (m->nfv == 3)
+          m->divide_tri(i);
+        else
+          m->divide_quad(i);
+        ++refine_count;
+      } else {
+        limit_reached = true;
+      }
+    }
+    m->scan_leaves();
+  } catch (const std::bad_alloc&) {
+    return LPMX_ERR_NOMEM;
+  }
+  if (n_divided) *n_divided = refine_count;
+  if (outcome) *outcome = limit_reached ? LPMX_AMR_LIMIT_REACHED : LPMX_AMR_DIVIDED_ALL;
   return LPMX_OK;
 }
 

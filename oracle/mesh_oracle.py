@@ -1,8 +1,9 @@
-"""Independent restatement (pure Python, small depths only) of the reference's uniform tree refinement.
+"""Independent restatement (pure Python, small depths only) of the reference's tree refinement, uniform and adaptive.
 
 TEST INFRASTRUCTURE ONLY.  It replays, in the reference's own insertion order,
   MeshSeed::read_file            /root/reference/src/mesh/lpm_mesh_seed.cpp:20-206  (the .dat parser)
   PolyMesh2d::tree_init          src/mesh/lpm_polymesh2d_impl.hpp:25-42
+  PolyMesh2d::divide_flagged_faces  src/mesh/lpm_polymesh2d_impl.hpp:124-173 (+ Faces::scan_leaves)
   Edges::divide                  src/mesh/lpm_edges.cpp:58-96
   FaceDivider<.., TriFace>       src/mesh/lpm_faces_impl.hpp:284-431
   FaceDivider<.., QuadFace>      src/mesh/lpm_faces_impl.hpp:433-574
@@ -131,11 +132,34 @@ class TreeMesh:
                 if not self.fkids[j][0] > 0:
                     self._divide(j)
             start = stop - 1
+        self.init_depth = depth
+        self.scan_leaves()
+
+    def scan_leaves(self):
         self.leaf_idx = []
         acc = 0
         for k in self.fkids:
             self.leaf_idx.append(acc)
             acc += 0 if k[0] > 0 else 1
+
+    def divide_flagged_faces(self, flags, nmaxfaces, amr_limit):
+        """Returns (refine_count, outcome): outcome 0 all divided, 1 not enough memory (nothing divided), 2 level limit
+        reached for some flagged faces."""
+        n_in = len(self.fx)
+        flag_count = sum(1 for i in range(n_in) if flags[i])
+        space_left = nmaxfaces - n_in
+        if flag_count > space_left // 4:
+            return 0, 1
+        refine_count, limit_reached = 0, False
+        for i in range(n_in):
+            if flags[i]:
+                if self.flevel[i] <= self.init_depth + amr_limit:
+                    self._divide(i)
+                    refine_count += 1
+                else:
+                    limit_reached = True
+        self.scan_leaves()
+        return refine_count, (2 if limit_reached else 0)
 
     def _add_face(self, ctr, lctr, verts, edges, parent, area):
         self.fx.append(ctr)
