@@ -11,7 +11,9 @@
 #include "lpm_gallery.hpp"
 #include "lpm_geometry.hpp"
 #include "lpm_incompressible2d.hpp"
+#include "lpm_logger.hpp"
 #include "lpm_polymesh2d.hpp"
+#include "lpm_refinement.hpp"
 #include "lpm_swe.hpp"
 #include "lpm_views.hpp"
 #endif

@@ -8,7 +8,9 @@
 // gather/scatter are lpmx_gather_mesh_data / lpmx_scatter_mesh_data.  Deviation, flagged: the reference reconstructs
 // vector fields with Compadre's ManifoldVectorPointSample basis; here the Cartesian components are interpolated as
 // scalars and the result is projected onto the tangent plane of the target (same order of accuracy, not the same
-// numbers -- and Compadre is unpinned anyway).  adaptive_* (AMR) is out of scope.
+// numbers -- and Compadre is unpinned anyway).
+//   adaptive_direct_remesh / adaptive_indirect_remesh   the uniform remesh, then amr_limit passes of {flag the faces the
+//                            previous pass added, divide_flagged_faces, interpolate everything again}   _impl.hpp:212-314,354-661
 #ifndef LPM_SHIM_COMPADRE_REMESH_HPP
 #define LPM_SHIM_COMPADRE_REMESH_HPP
 
@@ -18,6 +20,7 @@
 
 #include "lpm_coriolis.hpp"
 #include "lpm_polymesh2d.hpp"
+#include "lpm_refinement.hpp"
 #include "lpm_swe.hpp"  // gmls::Params
 
 namespace Lpm {
@@ -32,6 +35,7 @@ struct CompadreRemesh {
   using CoriolisType = CoriolisSphere;
 
   gmls::Params gmls_params;
+  Logger logger{"CompadreRemesh", Log::warn};
   PolyMesh2d<SeedType>& new_mesh;
   vert_scalar_field_map new_vert_scalars;
   face_scalar_field_map new_face_scalars;
@@ -84,8 +88,52 @@ struct CompadreRemesh {
     });
   }
 
+  /// uniform_direct_remesh, then new_mesh.params.amr_limit refinement passes, each followed by a fresh interpolation of
+  /// the Lagrangian coordinates and every field onto the refined particle set (_impl.hpp:212-314)
+  template <typename FlagType>
+  void adaptive_direct_remesh(Refinement<SeedType>& refiner, const FlagType& flag) {
+    uniform_direct_remesh();
+    adaptive_passes(refiner, flag, true, nullptr);
+  }
+  template <typename FlagType, typename VorticityFunctor>
+  void adaptive_indirect_remesh(Refinement<SeedType>& refiner, const FlagType& flag, const VorticityFunctor& vorticity,
+                                const CoriolisType& coriolis) {
+    uniform_indirect_remesh(vorticity, coriolis);
+    adaptive_passes(refiner, flag, false, last_point_fn_);
+  }
+  template <typename FlagType, typename VorticityFunctor, typename Tracer1>
+  void adaptive_indirect_remesh(Refinement<SeedType>& refiner, const FlagType& flag, const VorticityFunctor& vorticity,
+                                const CoriolisType& coriolis, const Tracer1& tracer1) {
+    uniform_indirect_remesh(vorticity, coriolis, tracer1);
+    adaptive_passes(refiner, flag, false, last_point_fn_);
+  }
+  template <typename FlagType, typename VorticityFunctor, typename Tracer1, typename Tracer2>
+  void adaptive_indirect_remesh(Refinement<SeedType>& refiner, const FlagType& flag, const VorticityFunctor& vorticity,
+                                const CoriolisType& coriolis, const Tracer1& tracer1, const Tracer2& tracer2) {
+    uniform_indirect_remesh(vorticity, coriolis, tracer1, tracer2);
+    adaptive_passes(refiner, flag, false, last_point_fn_);
+  }
+
  private:
   typedef std::function<void(const Real* lag, const Real* phys, std::map<std::string, Real>&)> PointFn;
+  PointFn last_point_fn_;  // the indirect definition of the fields, kept for the adaptive passes
+
+  template <typename FlagType>
+  void adaptive_passes(Refinement<SeedType>& refiner, const FlagType& flag, const bool direct, const PointFn& point_fn) {
+    Index face_start_idx = 0;
+    for (int i = 0; i < new_mesh.params.amr_limit; ++i) {
+      const Index face_end_idx = new_mesh.n_faces_host();
+      refiner.iterate(face_start_idx, face_end_idx, flag);
+      new_mesh.divide_flagged_faces(refiner.flags, logger);
+      do_remesh(direct, point_fn);
+      face_start_idx = face_end_idx;
+    }
+  }
+
+  void remesh(const bool direct, const PointFn& point_fn) {
+    last_point_fn_ = point_fn;
+    do_remesh(direct, point_fn);
+  }
 
   // gathered copy (vertices then leaves) of an n x ncomp vertex/face pair of host arrays
   static std::vector<Real> gather(const PolyMesh2d<SeedType>& m, int ncomp, const Real* vdata, const Real* fdata) {
@@ -105,7 +153,7 @@ struct CompadreRemesh {
                   "ScatterMeshData");
   }
 
-  void remesh(const bool direct, const PointFn& point_fn) {
+  void do_remesh(const bool direct, const PointFn& point_fn) {
     // sources: the old particles where they are now; targets: the new mesh's particles
     const std::vector<Real> src = gather(old_mesh, 3, old_mesh.vertices.phys_crds.view.data(), old_mesh.faces.phys_crds.view.data());
     const std::vector<Real> tgt = gather(new_mesh, 3, new_mesh.vertices.phys_crds.view.data(), new_mesh.faces.phys_crds.view.data());

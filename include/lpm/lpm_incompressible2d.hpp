@@ -1,8 +1,9 @@
 // lpm/lpm_incompressible2d.hpp -- Incompressible2D<Seed> and Incompressible2DRK2<Seed> on the sphere.
 //   Incompressible2D<Seed>             src/lpm_incompressible2d.hpp:17-108, src/lpm_incompressible2d_impl.hpp
 //   Incompressible2DRK2<Seed>          src/lpm_incompressible2d_rk2.hpp:15-63, _rk2_impl.hpp:75-172
-// Remeshing and AMR are outside the direct-sum hot path and are not provided; the FTLE field is
-// filled by ComputeFTLE (lpm_ftle.hpp), as in the reference's drivers.
+// compadre_remesh(new, old, params) returns the CompadreRemesh hand-off (lpm_compadre_remesh.hpp); adaptive refinement goes
+// through mesh.divide_flagged_faces + Refinement (lpm_refinement.hpp); the FTLE field is filled by ComputeFTLE (lpm_ftle.hpp),
+// as in the reference's drivers.
 #ifndef LPM_SHIM_INCOMPRESSIBLE2D_HPP
 #define LPM_SHIM_INCOMPRESSIBLE2D_HPP
 
@@ -71,8 +72,8 @@ class Incompressible2D {
   }
 
   void allocate_tracer(const std::string& name) {
-    tracer_passive.emplace(name, ScalarField<VertexField>(name, mesh.n_vertices_host()));
-    tracer_active.emplace(name, ScalarField<FaceField>(name, mesh.n_faces_host()));
+    tracer_passive.emplace(name, ScalarField<VertexField>(name, mesh.params.nmaxverts));
+    tracer_active.emplace(name, ScalarField<FaceField>(name, mesh.params.nmaxfaces));
   }
   template <typename TracerType>
   void allocate_tracer(const TracerType& tracer, const std::string& tname = std::string()) {

@@ -5,12 +5,17 @@
 //   PolyMeshParameters                                 src/mesh/lpm_polymesh2d.hpp:32-72
 //   PolyMesh2d::tree_init / n_*_host / appx_mesh_size  src/mesh/lpm_polymesh2d.hpp:152-159,861; _impl.hpp:25-42
 //   Vertices / Edges / Faces public views              src/mesh/lpm_vertices.hpp, lpm_edges.hpp, lpm_faces.hpp
-// Uniform refinement only: AMR (divide_flagged_faces), point location and remeshing are outside the hot path and
-// refuse with LPM_REQUIRE.
+//   PolyMesh2d::divide_flagged_faces                   src/mesh/lpm_polymesh2d_impl.hpp:124-173 (via lpmx_mesh_divide_flagged_faces)
+// As in the reference every mesh view is allocated once at its maximum extent (nmaxverts / nmaxedges / nmaxfaces, sized
+// for init_depth + amr_buffer) and n_*_host() counts the entries in use, so shallow copies held by flag functors and
+// solvers stay valid across an adaptive refinement.  Point location (locate_face_containing_pt) is not provided.
 #ifndef LPM_SHIM_POLYMESH2D_HPP
 #define LPM_SHIM_POLYMESH2D_HPP
 
+#include <memory>
+
 #include "lpm_coords.hpp"
+#include "lpm_logger.hpp"
 
 namespace Lpm {
 
@@ -55,6 +60,7 @@ struct PolyMeshParameters {
   Index nmaxverts, nmaxedges, nmaxfaces;
   Int init_depth, amr_buffer, amr_limit;
   MeshSeed<SeedType> seed;
+  PolyMeshParameters() : nmaxverts(0), nmaxedges(0), nmaxfaces(0), init_depth(0), amr_buffer(0), amr_limit(0), seed() {}
   PolyMeshParameters(const Int depth, const Real r = 1, const Int amr_buff = 0, const Int amr_lim = 0)
       : init_depth(depth), amr_buffer(amr_buff), amr_limit(amr_lim), seed(r) {
     seed.set_max_allocations(nmaxverts, nmaxedges, nmaxfaces, depth + amr_buff);
@@ -115,13 +121,17 @@ class PolyMesh2d {
   Real radius = 1;
   Int base_tree_depth = 0;
 
+  PolyMeshParameters<SeedType> params;  ///< init_depth / amr_buffer / amr_limit / nmax* (src/mesh/lpm_polymesh2d.hpp:137)
+
   /// allocates; tree_init() fills (reference: PolyMesh2d(nmaxverts, nmaxedges, nmaxfaces))
   PolyMesh2d(const Index nmaxverts, const Index nmaxedges, const Index nmaxfaces)
-      : nmaxverts_(nmaxverts), nmaxedges_(nmaxedges), nmaxfaces_(nmaxfaces) {}
+      : nmaxverts_(nmaxverts), nmaxedges_(nmaxedges), nmaxfaces_(nmaxfaces) {
+    params.nmaxverts = nmaxverts, params.nmaxedges = nmaxedges, params.nmaxfaces = nmaxfaces;
+  }
 
   /// allocates and builds the uniform tree (reference: PolyMesh2d(const PolyMeshParameters&), lpm_polymesh2d.hpp:152-159)
-  explicit PolyMesh2d(const PolyMeshParameters<SeedType>& params)
-      : nmaxverts_(params.nmaxverts), nmaxedges_(params.nmaxedges), nmaxfaces_(params.nmaxfaces) {
+  explicit PolyMesh2d(const PolyMeshParameters<SeedType>& params_in)
+      : params(params_in), nmaxverts_(params_in.nmaxverts), nmaxedges_(params_in.nmaxedges), nmaxfaces_(params_in.nmaxfaces) {
     tree_init(params.init_depth, params.seed);
   }
   virtual ~PolyMesh2d() = default;
@@ -130,24 +140,95 @@ class PolyMesh2d {
   void tree_init(const Int initDepth, const MeshSeed<SeedType>& seed) {
     lpmx_mesh_t m = nullptr;
     LPM_REQUIRE_MSG(lpmx_mesh_create(SeedType::lpmx_id, initDepth, seed.radius, &m) == LPMX_OK, "lpmx_mesh_create");
-    int nv, ne, nf, nfl, nel, nfv;
-    lpmx_mesh_sizes(m, &nv, &ne, &nf, &nfl, &nel, &nfv);
+    handle_ = std::shared_ptr<lpmx_mesh_s>(m, [](lpmx_mesh_s* p) { lpmx_mesh_destroy(p); });
+    int nv, ne, nf;
+    lpmx_mesh_sizes(m, &nv, &ne, &nf, nullptr, nullptr, nullptr);
     LPM_REQUIRE_MSG(nv <= nmaxverts_ && ne <= nmaxedges_ && nf <= nmaxfaces_, "mesh exceeds the allocated sizes");
     radius = seed.radius;
     base_tree_depth = initDepth;
+    params.init_depth = initDepth;
+    const Index mv = nmaxverts_, me = nmaxedges_, mf = nmaxfaces_;
+    vertices.phys_crds = Coords<Geo>(mv), vertices.lag_crds = Coords<Geo>(mv);
+    faces.phys_crds = Coords<Geo>(mf), faces.lag_crds = Coords<Geo>(mf);
+    vertices.crd_inds = index_view_type("vert_crd_inds", mv);
+    edges.origs = index_view_type("origs", me), edges.dests = index_view_type("dests", me);
+    edges.lefts = index_view_type("lefts", me), edges.rights = index_view_type("rights", me);
+    edges.parent = index_view_type("edge_parent", me), edges.kids = View2<Index, 2>("edge_kids", me);
+    faces.area = scalar_view_type("area", mf), faces.mask = mask_view_type("mask", mf);
+    faces.verts = View2<Index, FaceType::nverts>("face_verts", mf), faces.edges = View2<Index, FaceType::nverts>("face_edges", mf);
+    faces.kids = View2<Index, 4>("face_kids", mf);
+    faces.crd_inds = index_view_type("face_crd_inds", mf), faces.parent = index_view_type("face_parent", mf);
+    faces.level = index_view_type("face_level", mf), faces.leaf_idx = index_view_type("leaf_idx", mf);
+    refetch();
+  }
+
+  /// PolyMesh2d::divide_flagged_faces (src/mesh/lpm_polymesh2d_impl.hpp:124-173).  The particles may have moved since the
+  /// mesh was built: the current coordinates are handed to the generator first (the reference divides from the
+  /// coordinates as they are), every view is refilled in place afterwards.
+  template <typename LoggerType>
+  void divide_flagged_faces(const mask_view_type& flags, LoggerType& logger) {
+    LPM_REQUIRE_MSG(handle_, "divide_flagged_faces before tree_init");
+    LPM_REQUIRE((Index)flags.extent(0) >= n_faces_host());
+    Index flag_count = 0;
+    for (Index i = 0; i < n_faces_host(); ++i) flag_count += (flags(i) ? 1 : 0);
+    logger.debug("dividing {} flagged faces...", flag_count);
+    push(LPMX_MESH_VERT_XYZ, vertices.phys_crds.view.data(), 3L * n_vertices_host());
+    push(LPMX_MESH_VERT_LAG_XYZ, vertices.lag_crds.view.data(), 3L * n_vertices_host());
+    push(LPMX_MESH_FACE_XYZ, faces.phys_crds.view.data(), 3L * n_faces_host());
+    push(LPMX_MESH_FACE_LAG_XYZ, faces.lag_crds.view.data(), 3L * n_faces_host());
+    int refine_count = 0, outcome = 0;
+    const int rc = lpmx_mesh_divide_flagged_faces(handle_.get(), flags.data(), (int)flags.extent(0), nmaxfaces_,
+                                                  params.init_depth + params.amr_limit, &refine_count, &outcome);
+    LPM_REQUIRE_MSG(rc == LPMX_OK, std::string("lpmx_mesh_divide_flagged_faces: ") + lpmx_error_name(rc));
+    if (outcome == LPMX_AMR_NO_SPACE) {
+      logger.warn("divide_flagged_faces: not enough memory (flag count = {}, nfaces = {}, nmaxfaces = {})", flag_count,
+                  n_faces_host(), nmaxfaces_);
+      return;
+    }
+    refetch();
+    if (outcome == LPMX_AMR_LIMIT_REACHED)
+      logger.warn("divide_flagged_faces: local refinement limit reached; divided {} of {} flagged faces.", refine_count,
+                  flag_count);
+    else
+      logger.info("divide_flagged_faces: {} faces divided.", refine_count);
+  }
+
+  Index n_vertices_host() const { return vertices.nh(); }
+  Index n_edges_host() const { return edges.nh(); }
+  Index n_faces_host() const { return faces.nh(); }
+  Real appx_mesh_size() const { return faces.appx_mesh_size(); }
+  Real surface_area_host() const { return faces.surface_area_host(); }
+  virtual void update_device() const {}
+  virtual void update_host() const {}
+
+  virtual std::string info_string(const std::string& label = "", const int tab_level = 0, const bool = false) const {
+    std::ostringstream ss;
+    const std::string tabs(tab_level, '\t');
+    ss << tabs << "PolyMesh2d<" << SeedType::id_string() << "> " << label << ": depth " << base_tree_depth << ", "
+       << n_vertices_host() << " vertices, " << n_edges_host() << " edges (" << edges.n_leaves_host() << " leaves), "
+       << n_faces_host() << " faces (" << faces.n_leaves_host() << " leaves); surface area " << surface_area_host()
+       << ", appx mesh size " << appx_mesh_size() << "\n";
+    return ss.str();
+  }
+
+ protected:
+  Index nmaxverts_, nmaxedges_, nmaxfaces_;
+
+ private:
+  std::shared_ptr<lpmx_mesh_s> handle_;  // the host generator's tree (kept for divide_flagged_faces)
+
+  void push(const int id, const Real* src, const long count) {
+    LPM_REQUIRE(lpmx_mesh_update_array(handle_.get(), id, src, count) == LPMX_OK);
+  }
+
+  // counts + every array, into the nmax-sized views
+  void refetch() {
+    lpmx_mesh_t m = handle_.get();
+    int nv, ne, nf, nfl, nel, nfv;
+    lpmx_mesh_sizes(m, &nv, &ne, &nf, &nfl, &nel, &nfv);
+    LPM_REQUIRE_MSG(nv <= nmaxverts_ && ne <= nmaxedges_ && nf <= nmaxfaces_, "mesh exceeds the allocated sizes");
     vertices.n_ = nv, edges.n_ = ne, edges.n_leaves_ = nel, faces.n_ = nf, faces.n_leaves_ = nfl;
-    vertices.phys_crds = Coords<Geo>(nv), vertices.lag_crds = Coords<Geo>(nv);
-    faces.phys_crds = Coords<Geo>(nf), faces.lag_crds = Coords<Geo>(nf);
     vertices.phys_crds.set_nh(nv), vertices.lag_crds.set_nh(nv), faces.phys_crds.set_nh(nf), faces.lag_crds.set_nh(nf);
-    vertices.crd_inds = index_view_type("vert_crd_inds", nv);
-    edges.origs = index_view_type("origs", ne), edges.dests = index_view_type("dests", ne);
-    edges.lefts = index_view_type("lefts", ne), edges.rights = index_view_type("rights", ne);
-    edges.parent = index_view_type("edge_parent", ne), edges.kids = View2<Index, 2>("edge_kids", ne);
-    faces.area = scalar_view_type("area", nf), faces.mask = mask_view_type("mask", nf);
-    faces.verts = View2<Index, FaceType::nverts>("face_verts", nf), faces.edges = View2<Index, FaceType::nverts>("face_edges", nf);
-    faces.kids = View2<Index, 4>("face_kids", nf);
-    faces.crd_inds = index_view_type("face_crd_inds", nf), faces.parent = index_view_type("face_parent", nf);
-    faces.level = index_view_type("face_level", nf), faces.leaf_idx = index_view_type("leaf_idx", nf);
     fetch(m, LPMX_MESH_VERT_XYZ, vertices.phys_crds.view.data());
     fetch(m, LPMX_MESH_VERT_LAG_XYZ, vertices.lag_crds.view.data());
     fetch(m, LPMX_MESH_VERT_CRD_INDS, vertices.crd_inds.data());
@@ -168,36 +249,8 @@ class PolyMesh2d {
     fetch(m, LPMX_MESH_FACE_KIDS, faces.kids.data());
     fetch(m, LPMX_MESH_FACE_LEVEL, faces.level.data());
     fetch(m, LPMX_MESH_FACE_LEAF_IDX, faces.leaf_idx.data());
-    lpmx_mesh_destroy(m);
   }
 
-  Index n_vertices_host() const { return vertices.nh(); }
-  Index n_edges_host() const { return edges.nh(); }
-  Index n_faces_host() const { return faces.nh(); }
-  Real appx_mesh_size() const { return faces.appx_mesh_size(); }
-  Real surface_area_host() const { return faces.surface_area_host(); }
-  virtual void update_device() const {}
-  virtual void update_host() const {}
-
-  template <typename Flags, typename LoggerType>
-  void divide_flagged_faces(const Flags&, LoggerType&) {
-    LPM_REQUIRE_MSG(false, "adaptive refinement is outside the direct-sum hot path (SURVEY.md section 2, row 19)");
-  }
-
-  virtual std::string info_string(const std::string& label = "", const int tab_level = 0, const bool = false) const {
-    std::ostringstream ss;
-    const std::string tabs(tab_level, '\t');
-    ss << tabs << "PolyMesh2d<" << SeedType::id_string() << "> " << label << ": depth " << base_tree_depth << ", "
-       << n_vertices_host() << " vertices, " << n_edges_host() << " edges (" << edges.n_leaves_host() << " leaves), "
-       << n_faces_host() << " faces (" << faces.n_leaves_host() << " leaves); surface area " << surface_area_host()
-       << ", appx mesh size " << appx_mesh_size() << "\n";
-    return ss.str();
-  }
-
- protected:
-  Index nmaxverts_, nmaxedges_, nmaxfaces_;
-
- private:
   template <typename T>
   static void fetch(lpmx_mesh_t m, const int id, T* dst) {
     const void* src = nullptr;

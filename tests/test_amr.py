@@ -83,6 +83,46 @@ def test_flagging_a_divided_face_is_rejected_and_short_flag_arrays_too():
     assert m.divide_flagged_faces(np.zeros(m.n_faces, dtype=np.uint8)) == (0, PolyMesh2d.AMR_DIVIDED_ALL)
 
 
+def _fnv(arrays):
+    h = 1469598103934665603
+    for a in arrays:
+        for b in np.ascontiguousarray(a).tobytes():
+            h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+@pytest.mark.parametrize("seed,depth,amr,passes", [("icos", 2, 2, 3), ("cubed", 2, 1, 3)])
+def test_cpp_shim_divide_flagged_faces_equals_the_binding(seed, depth, amr, passes):
+    """include/lpm/lpm_polymesh2d.hpp (PolyMesh2d<Seed>::divide_flagged_faces: nmax-sized views refilled in place, coordinates
+    pushed first, Logger warnings) against the ctypes binding on the same flag rule; host-only program, no engine."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    from lpm_b200 import build
+    build.build()
+    exe = os.path.join(root, "tests", "cpp", "_build", "amr_mesh_check")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(root, "include"), "-o", exe,
+                    os.path.join(root, "tests", "cpp", "amr_mesh_check.cpp"), "-L" + os.path.join(root, "lpm_b200"), "-llpmx",
+                    "-Wl,-rpath," + os.path.join(root, "lpm_b200")], check=True)
+    p = subprocess.run([exe, seed, str(depth), str(amr), str(passes)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    counts, digest = p.stdout.split("\n")[:2]
+    m = PolyMesh2d(seed, depth, amr_buffer=amr, amr_limit=amr)
+    warnings = 0
+    for _ in range(passes):
+        flags = np.zeros(m.nmaxfaces, dtype=np.uint8)
+        leaves = np.nonzero(m.face_mask == 0)[0]
+        flags[leaves[::3]] = 1
+        _, oc = m.divide_flagged_faces(flags)
+        warnings += oc != PolyMesh2d.AMR_DIVIDED_ALL
+    assert [int(x) for x in counts.split()] == [m.n_verts, m.n_edges, m.n_faces, m.n_face_leaves, m.n_edge_leaves, warnings]
+    assert warnings >= 1  # the last pass runs into the level limit / the memory check
+    arrays = [m.vert_xyz, m.vert_lag_xyz, m.face_xyz, m.face_lag_xyz, m.face_area, m.face_mask, m.face_verts, m.face_edges,
+              m.face_kids, m.face_parent, m.face_level, m.face_leaf_idx, m.edge_origs, m.edge_dests, m.edge_lefts,
+              m.edge_rights, m.edge_parents, m.edge_kids]
+    assert int(digest, 16) == _fnv(arrays)
+
+
 @pytest.mark.parametrize("seed", ["icos", "cubed"])
 def test_adaptive_mesh_invariants(seed):
     g = np.load(os.path.join(GOLDEN, f"mesh_amr_{seed}_1_random.npz"))

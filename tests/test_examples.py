@@ -101,3 +101,33 @@ def test_swe_tc2_example_surface_laplacians(built, lap):
     on the device, and with the closed-form Laplacian: both keep the steady state."""
     out, log = _run(built, "sphere_swe_tc2", "-d", "4", "-tf", "0.02", "-n", "4", "-lap", lap)
     assert out["steps"] == 4 and out["depth_l2"] < 1e-3 and out["zeta_l2"] < 1e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["sphere_gaussian_vortex", "sphere_rh54"])
+def test_ic2d_examples_with_adaptive_refinement(built, name):
+    """examples/sphere_gaussian_vortex.cpp:89-118 / sphere_rh54.cpp:118-147: -amr 2 refines where |zeta| A exceeds a fraction
+    of its maximum on the uniform mesh (flags on the device, division on the host), then steps on the mixed-level mesh."""
+    uni, _ = _run(built, name, "-d", "3", "-tf", "0.03", "-n", "3")
+    out, log = _run(built, name, "-d", "3", "-tf", "0.03", "-n", "3", "-amr", "2", "-c", "0.25")
+    assert "amr is enabled with limit 2" in log and "faces divided" in log
+    assert out["n_leaves"] > uni["n_leaves"] and out["max_level"] == 3 + 2 + 1
+    assert out["steps"] == 3 and out["ke_drift"] < 1e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("strategy", ["direct", "indirect"])
+def test_gaussian_vortex_adaptive_remesh(built, strategy):
+    """examples/sphere_gaussian_vortex.cpp:205-245: with AMR on, every remesh builds a fresh uniform mesh, interpolates, then
+    refines it adaptively (CompadreRemesh::adaptive_direct_remesh / adaptive_indirect_remesh)."""
+    out, log = _run(built, "sphere_gaussian_vortex", "-d", "3", "-tf", "0.04", "-n", "4", "-amr", "1", "-c", "0.25", "-rm", "2",
+                    "-rs", strategy)
+    assert "remeshes: 2" in log
+    assert out["max_level"] == 3 + 1 + 1 and out["ke_drift"] < 2e-2
+
+
+@pytest.mark.gpu
+def test_rh54_remesh_triggered_by_ftle(built):
+    """examples/sphere_rh54.cpp:247-258: -rt ftle remeshes when the maximum FTLE exceeds -ftle."""
+    out, log = _run(built, "sphere_rh54", "-d", "3", "-tf", "0.2", "-n", "8", "-rt", "ftle", "-ftle", "0.05")
+    assert "triggered by ftle" in log and "remeshes: 0" not in log
