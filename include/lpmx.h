@@ -50,6 +50,8 @@ extern "C" {
 /* mesh seeds (reference: src/mesh/lpm_mesh_seed.hpp:111-147) */
 #define LPMX_SEED_ICOS_TRI_SPHERE 0
 #define LPMX_SEED_CUBED_SPHERE 1
+#define LPMX_SEED_QUAD_RECT 2 /* QuadRectSeed (:46-62): planar quadrilaterals on [-r, r]^2, free boundary; Real*[2] coordinates */
+#define LPMX_SEED_TRI_HEX 3   /* TriHexSeed (:64-82): planar triangles on a hexagon of circumradius r, free boundary          */
 
 typedef struct lpmx_handle_s* lpmx_handle_t;
 typedef struct lpmx_mesh_s* lpmx_mesh_t;
@@ -66,13 +68,16 @@ const char* lpmx_error_name(int code);
  * Replaces PolyMesh2d<Seed>::tree_init (src/mesh/lpm_polymesh2d_impl.hpp:25-42) with
  * MeshSeed<Seed> (src/mesh/lpm_mesh_seed.cpp:10-18,20-206), FaceDivider<..>::divide
  * (src/mesh/lpm_faces_impl.hpp:284-431 tri, :433-574 quad) and Edges::divide
- * (src/mesh/lpm_edges.cpp:58-96) for uniform refinement of the two spherical seeds.
+ * (src/mesh/lpm_edges.cpp:58-96) for the two spherical seeds and the two planar seeds (the dividers are generic in the
+ * geometry: SphereGeometry / PlaneGeometry midpoint, barycenter, polygon_area, src/lpm_geometry.hpp:69-160,516-642).
+ * Coordinate rows have ndim entries: 3 on the sphere, 2 in the plane.  Boundary edges of the planar seeds have right = -1.
  * ------------------------------------------------------------------------------------------ */
 
 /* MeshSeed<Seed>::set_max_allocations (src/mesh/lpm_mesh_seed.cpp:266-279) */
 int lpmx_mesh_max_allocations(int seed, int depth, int* n_verts, int* n_edges, int* n_faces);
 
-/* Build the tree mesh of `depth` uniform refinements on a sphere of `radius`. */
+/* Build the tree mesh of `depth` uniform refinements; seed coordinates are multiplied by `radius` (sphere radius; half
+ * width of the square; circumradius of the hexagon). */
 int lpmx_mesh_create(int seed, int depth, double radius, lpmx_mesh_t* mesh);
 int lpmx_mesh_destroy(lpmx_mesh_t mesh);
 
@@ -82,7 +87,7 @@ int lpmx_mesh_sizes(lpmx_mesh_t mesh, int* n_verts, int* n_edges, int* n_faces, 
                     int* n_edge_leaves, int* n_face_verts);
 
 /* array ids for lpmx_mesh_array: element type and extent in the comment */
-#define LPMX_MESH_VERT_XYZ 0       /* double[n_verts][3]  vertices.phys_crds (LayoutRight)        */
+#define LPMX_MESH_VERT_XYZ 0       /* double[n_verts][ndim]  vertices.phys_crds (LayoutRight); ndim = 3 sphere, 2 plane (also ids 1, 9, 10) */
 #define LPMX_MESH_VERT_LAG_XYZ 1   /* double[n_verts][3]  vertices.lag_crds                      */
 #define LPMX_MESH_VERT_CRD_INDS 2  /* int[n_verts]        vertices.crd_inds                      */
 #define LPMX_MESH_EDGE_ORIGS 3     /* int[n_edges]        edges.origs                            */

@@ -19,7 +19,7 @@ vp = ctypes.c_void_p
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_NO_DEVICE, ERR_COMM, ERR_UNSUPPORTED, ERR_STATE = -1, -2, -3, -4, -5, -6, -7
 LAYOUT_RIGHT, LAYOUT_LEFT = 0, 1
-SEED_ICOS_TRI_SPHERE, SEED_CUBED_SPHERE = 0, 1
+SEED_ICOS_TRI_SPHERE, SEED_CUBED_SPHERE, SEED_QUAD_RECT, SEED_TRI_HEX = 0, 1, 2, 3
 
 
 class SwePassive(ctypes.Structure):

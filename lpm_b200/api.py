@@ -14,19 +14,22 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import LAYOUT_LEFT, LAYOUT_RIGHT, SEED_CUBED_SPHERE, SEED_ICOS_TRI_SPHERE, LpmxError  # noqa: F401
+from ._lib import (LAYOUT_LEFT, LAYOUT_RIGHT, SEED_CUBED_SPHERE, SEED_ICOS_TRI_SPHERE, SEED_QUAD_RECT, SEED_TRI_HEX,  # noqa: F401
+                   LpmxError)
 
 _MESH_ARRAYS = {
-    "vert_xyz": (0, 3), "vert_lag_xyz": (1, 3), "vert_crd_inds": (2, 1),
+    # width -1: vertices per face; -2: Geo::ndim (3 on the sphere, 2 in the plane; the planar arrays keep the names *_xyz)
+    "vert_xyz": (0, -2), "vert_lag_xyz": (1, -2), "vert_crd_inds": (2, 1),
     "edge_origs": (3, 1), "edge_dests": (4, 1), "edge_lefts": (5, 1), "edge_rights": (6, 1),
     "edge_parents": (7, 1), "edge_kids": (8, 2),
-    "face_xyz": (9, 3), "face_lag_xyz": (10, 3), "face_area": (11, 1), "face_mask": (12, 1),
+    "face_xyz": (9, -2), "face_lag_xyz": (10, -2), "face_area": (11, 1), "face_mask": (12, 1),
     "face_verts": (13, -1), "face_edges": (14, -1), "face_crd_inds": (15, 1), "face_parent": (16, 1),
     "face_kids": (17, 4), "face_level": (18, 1), "face_leaf_idx": (19, 1),
 }
 
 SEEDS = {"icos": SEED_ICOS_TRI_SPHERE, "icostri_sphere": SEED_ICOS_TRI_SPHERE,
-         "cubed": SEED_CUBED_SPHERE, "cubed_sphere": SEED_CUBED_SPHERE}
+         "cubed": SEED_CUBED_SPHERE, "cubed_sphere": SEED_CUBED_SPHERE,
+         "quad_rect": SEED_QUAD_RECT, "tri_hex": SEED_TRI_HEX}
 
 
 def _seed_id(seed):
@@ -55,6 +58,7 @@ class PolyMesh2d:
     def __init__(self, seed, depth, radius=1.0, amr_buffer=0, amr_limit=0):
         L = _lib.lib()
         self.seed = _seed_id(seed)
+        self.ndim = 2 if self.seed in (SEED_QUAD_RECT, SEED_TRI_HEX) else 3
         self.depth = depth
         self.amr_buffer, self.amr_limit = amr_buffer, amr_limit
         self.nmaxverts, self.nmaxedges, self.nmaxfaces = max_allocations(seed, depth + amr_buffer)
@@ -89,7 +93,7 @@ class PolyMesh2d:
                 arr = np.zeros(0, dtype=np.dtype(ctype))
             else:
                 arr = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctype)), shape=(n.value,)).copy()
-            w = self.n_face_verts if width == -1 else width
+            w = self.n_face_verts if width == -1 else (self.ndim if width == -2 else width)
             if w > 1:
                 arr = arr.reshape(-1, w)
             setattr(self, name, arr)

@@ -1,4 +1,5 @@
-// lpmx_mesh.cpp -- host-side quad-tree particle/panel mesh generator for the two spherical seeds.
+// lpmx_mesh.cpp -- host-side quad-tree particle/panel mesh generator for the two spherical seeds and the two planar seeds
+// with free boundaries (QuadRectSeed, TriHexSeed; PlaneGeometry, Real*[2] coordinates).
 //
 // What it reproduces (reference files under /root/reference/src):
 //   MeshSeed<Seed>                          mesh/lpm_mesh_seed.cpp:10-18 (radius), :266-279 (allocations)
@@ -9,6 +10,7 @@
 //   FaceDivider<Sphere,TriFace>::divide     mesh/lpm_faces_impl.hpp:284-431
 //   FaceDivider<Sphere,QuadFace>::divide    mesh/lpm_faces_impl.hpp:433-574
 //   SphereGeometry midpoint/barycenter/tri_area/polygon_area   lpm_geometry.hpp:516-642
+//   PlaneGeometry  midpoint/barycenter/tri_area/polygon_area   lpm_geometry.hpp:69-160
 //   Faces::scan_leaves                      mesh/lpm_faces_impl.hpp:100-124
 //
 // The design is a flat structure-of-arrays builder with the reference's insertion order (that order
@@ -90,6 +92,34 @@ inline void midpoint(double* out, const double* a, const double* b) {
   normalize3(out);
 }
 
+// ---- PlaneGeometry (lpm_geometry.hpp:69-160); the third component of the local arrays is carried as 0 and never read ----
+inline double plane_tri_area(const double* a, const double* b, const double* c) {
+  const double bma0 = b[0] - a[0], bma1 = b[1] - a[1];
+  const double cma0 = c[0] - a[0], cma1 = c[1] - a[1];
+  const double ar = bma0 * cma1 - bma1 * cma0;
+  return 0.5 * std::fabs(ar);
+}
+inline double plane_polygon_area(const double* ctr, const double (*verts)[3], int n) {
+  double ar = 0.0;
+  for (int i = 0; i < n; ++i) ar += plane_tri_area(ctr, verts[i], verts[(i + 1) % n]);
+  return ar;
+}
+inline void plane_barycenter(double* out, const double (*verts)[3], int n) {
+  out[0] = out[1] = out[2] = 0.0;
+  for (int i = 0; i < n; ++i) {
+    out[0] += verts[i][0];
+    out[1] += verts[i][1];
+  }
+  const double s = 1.0 / n;
+  out[0] *= s;
+  out[1] *= s;
+}
+inline void plane_midpoint(double* out, const double* a, const double* b) {
+  out[0] = 0.5 * (a[0] + b[0]);
+  out[1] = 0.5 * (a[1] + b[1]);
+  out[2] = 0.0;
+}
+
 long ipow4(int lev) {
   long r = 1;
   for (int i = 0; i < lev; ++i) r *= 4;
@@ -101,15 +131,16 @@ long ipow4(int lev) {
 struct lpmx_mesh_s {
   int seed = 0;
   int nfv = 3;  // vertices per face
+  int nd = 3;   // Geo::ndim: 3 on the sphere, 2 in the plane (row length of every coordinate array)
   int depth = 0;
   // vertices
-  std::vector<double> vx, vlag;  // [nv][3]
+  std::vector<double> vx, vlag;  // [nv][nd]
   std::vector<int> v_crd;
   // edges
   std::vector<int> eo, ed, el, er, ep, ek;  // ek: [ne][2]
   int edge_leaves = 0;
   // faces
-  std::vector<double> fx, flag, farea;  // fx/flag: [nf][3]
+  std::vector<double> fx, flag, farea;  // fx/flag: [nf][nd]
   std::vector<unsigned char> fmask;
   std::vector<int> fverts, fedges;  // [nf][nfv]
   std::vector<int> f_crd, fparent, fkids, flevel, fleaf;  // fkids: [nf][4]
@@ -121,8 +152,8 @@ struct lpmx_mesh_s {
 
   int insert_vertex(const double* p, const double* l) {
     const int idx = nv();
-    vx.insert(vx.end(), p, p + 3);
-    vlag.insert(vlag.end(), l, l + 3);
+    vx.insert(vx.end(), p, p + nd);
+    vlag.insert(vlag.end(), l, l + nd);
     v_crd.push_back(idx);  // crd index == insertion index (lpm_vertices.hpp:158-163)
     return idx;
   }
@@ -142,8 +173,8 @@ struct lpmx_mesh_s {
   bool face_has_kids(int f) const { return fkids[4 * f] > 0; }  // lpm_faces.hpp:270-273
   int insert_face(const double* p, const double* l, const int* verts, const int* edges, int prt, double ar) {
     const int idx = nf();
-    fx.insert(fx.end(), p, p + 3);
-    flag.insert(flag.end(), l, l + 3);
+    fx.insert(fx.end(), p, p + nd);
+    flag.insert(flag.end(), l, l + nd);
     fverts.insert(fverts.end(), verts, verts + nfv);
     fedges.insert(fedges.end(), edges, edges + nfv);
     for (int i = 0; i < 4; ++i) fkids.push_back(kNull);
@@ -158,18 +189,37 @@ struct lpmx_mesh_s {
     return idx;
   }
 
+  // Geo::midpoint / barycenter / polygon_area on 3-wide local rows
+  void geo_midpoint(double* out, const double* a, const double* b) const {
+    if (nd == 3) midpoint(out, a, b);
+    else plane_midpoint(out, a, b);
+  }
+  void geo_barycenter(double* out, const double (*verts)[3], int n) const {
+    if (nd == 3) barycenter(out, verts, n);
+    else plane_barycenter(out, verts, n);
+  }
+  double geo_polygon_area(const double* ctr, const double (*verts)[3], int n) const {
+    return nd == 3 ? polygon_area(ctr, verts, n) : plane_polygon_area(ctr, verts, n);
+  }
+  // row `idx` of a coordinate array as a 3-wide local (z = 0 in the plane)
+  void load_row(double* out, const std::vector<double>& a, int idx) const {
+    out[2] = 0.0;
+    for (int k = 0; k < nd; ++k) out[k] = a[(size_t)nd * idx + k];
+  }
+
   // Edges::divide (lpm_edges.cpp:58-96); returns index of first child
   int divide_edge(int e) {
     const int vins = nv();
     const int eins = ne();
-    const double* a = &vx[3 * v_crd[eo[e]]];
-    const double* b = &vx[3 * v_crd[ed[e]]];
+    double a[3], b[3], la[3], lb[3];
+    load_row(a, vx, v_crd[eo[e]]);
+    load_row(b, vx, v_crd[ed[e]]);
     // lag_endpts(1,:) is filled from phys_crds in the reference (:81); identical at build time.
-    const double* la = &vlag[3 * v_crd[eo[e]]];
-    const double* lb = &vx[3 * v_crd[ed[e]]];
+    load_row(la, vlag, v_crd[eo[e]]);
+    load_row(lb, vx, v_crd[ed[e]]);
     double mid[3], lmid[3];
-    midpoint(mid, a, b);
-    midpoint(lmid, la, lb);
+    geo_midpoint(mid, a, b);
+    geo_midpoint(lmid, la, lb);
     insert_vertex(mid, lmid);
     const int o = eo[e], d = ed[e], l = el[e], r = er[e];
     insert_edge(o, vins, l, r, e);
@@ -258,14 +308,13 @@ void lpmx_mesh_s::divide_tri(int f) {
   double ctr[4][3], lctr[4][3], area[4];
   for (int i = 0; i < 4; ++i) {
     double vc[3][3], vl[3][3];
-    for (int j = 0; j < 3; ++j)
-      for (int k = 0; k < 3; ++k) {
-        vc[j][k] = vx[3 * v_crd[nfvx[i][j]] + k];
-        vl[j][k] = vlag[3 * v_crd[nfvx[i][j]] + k];
-      }
-    barycenter(ctr[i], vc, 3);
-    barycenter(lctr[i], vl, 3);
-    area[i] = polygon_area(ctr[i], vc, 3);
+    for (int j = 0; j < 3; ++j) {
+      load_row(vc[j], vx, v_crd[nfvx[i][j]]);
+      load_row(vl[j], vlag, v_crd[nfvx[i][j]]);
+    }
+    geo_barycenter(ctr[i], vc, 3);
+    geo_barycenter(lctr[i], vl, 3);
+    area[i] = geo_polygon_area(ctr[i], vc, 3);
   }
   for (int i = 0; i < 4; ++i) insert_face(ctr[i], lctr[i], nfvx[i], nfe[i], f, area[i]);
   finish_parent(f, kid0);
@@ -311,7 +360,10 @@ void lpmx_mesh_s::divide_quad(int f) {
   }
   // the parent's centre becomes a vertex, appended after the edge midpoints (:506-517)
   const int pc = f_crd[f];
-  const int cv = insert_vertex(&fx[3 * pc], &flag[3 * pc]);
+  double pcx[3], pcl[3];
+  load_row(pcx, fx, pc);
+  load_row(pcl, flag, pc);
+  const int cv = insert_vertex(pcx, pcl);
   for (int i = 0; i < 4; ++i) nfvx[i][(i + 2) % 4] = cv;
   // four interior edges (:520-536)
   const int e0 = ne();
@@ -330,15 +382,14 @@ void lpmx_mesh_s::divide_quad(int f) {
   double ctr[4][3], lctr[4][3], area[4];
   for (int i = 0; i < 4; ++i) {
     double vc[4][3], vl[4][3];
-    for (int j = 0; j < 4; ++j)
-      for (int k = 0; k < 3; ++k) {
-        // the quad divider indexes coordinates by vertex id directly (:548-552)
-        vc[j][k] = vx[3 * nfvx[i][j] + k];
-        vl[j][k] = vlag[3 * nfvx[i][j] + k];
-      }
-    barycenter(ctr[i], vc, 4);
-    barycenter(lctr[i], vl, 4);
-    area[i] = polygon_area(ctr[i], vc, 4);
+    for (int j = 0; j < 4; ++j) {
+      // the quad divider indexes coordinates by vertex id directly (:548-552)
+      load_row(vc[j], vx, nfvx[i][j]);
+      load_row(vl[j], vlag, nfvx[i][j]);
+    }
+    geo_barycenter(ctr[i], vc, 4);
+    geo_barycenter(lctr[i], vl, 4);
+    area[i] = geo_polygon_area(ctr[i], vc, 4);
   }
   for (int i = 0; i < 4; ++i) insert_face(ctr[i], lctr[i], nfvx[i], nfe[i], f, area[i]);
   finish_parent(f, kid0);
@@ -347,7 +398,7 @@ void lpmx_mesh_s::divide_quad(int f) {
 namespace {
 
 struct SeedDesc {
-  int nverts, nedges, nfaces, nfv;
+  int nverts, nedges, nfaces, nfv, nd;
   const double (*crds)[3];
   const int (*edges)[4];
   const int* fverts;
@@ -356,20 +407,48 @@ struct SeedDesc {
 
 bool seed_desc(int seed, SeedDesc* d) {
   if (seed == LPMX_SEED_ICOS_TRI_SPHERE) {
-    *d = {12, 30, 20, 3, kIcosTri_crds, kIcosTri_edges, &kIcosTri_face_verts[0][0], &kIcosTri_face_edges[0][0]};
+    *d = {12, 30, 20, 3, 3, kIcosTri_crds, kIcosTri_edges, &kIcosTri_face_verts[0][0], &kIcosTri_face_edges[0][0]};
     return true;
   }
   if (seed == LPMX_SEED_CUBED_SPHERE) {
-    *d = {8, 12, 6, 4, kCubedSphere_crds, kCubedSphere_edges, &kCubedSphere_face_verts[0][0],
+    *d = {8, 12, 6, 4, 3, kCubedSphere_crds, kCubedSphere_edges, &kCubedSphere_face_verts[0][0],
           &kCubedSphere_face_edges[0][0]};
+    return true;
+  }
+  if (seed == LPMX_SEED_QUAD_RECT) {
+    *d = {9, 12, 4, 4, 2, kQuadRect_crds, kQuadRect_edges, &kQuadRect_face_verts[0][0], &kQuadRect_face_edges[0][0]};
+    return true;
+  }
+  if (seed == LPMX_SEED_TRI_HEX) {
+    *d = {7, 12, 6, 3, 2, kTriHex_crds, kTriHex_edges, &kTriHex_face_verts[0][0], &kTriHex_face_edges[0][0]};
     return true;
   }
   return false;
 }
 
-// Seed::n_vertices_at_tree_level etc. (lpm_mesh_seed.cpp:353-375)
-long nverts_at(int seed, int lev) { return 2 + (seed == LPMX_SEED_ICOS_TRI_SPHERE ? 10 : 6) * ipow4(lev); }
-long nfaces_at(int seed, int lev) { return (seed == LPMX_SEED_ICOS_TRI_SPHERE ? 20 : 6) * ipow4(lev); }
+// Seed::n_vertices_at_tree_level / n_faces_at_tree_level / n_edges_at_tree_level (lpm_mesh_seed.cpp:306-375)
+long nverts_at(int seed, int lev) {
+  if (seed == LPMX_SEED_QUAD_RECT) {  // (3 + 2 + 4 + ... + 2^lev)^2
+    long r = 3;
+    for (int i = 1; i <= lev; ++i) r += 1L << i;
+    return r * r;
+  }
+  if (seed == LPMX_SEED_TRI_HEX) {  // 2 * sum_{i = 2^lev + 1}^{2^(lev+1)} i + 2^(lev+1) + 1
+    long r = 0;
+    for (long i = (1L << lev) + 1; i <= (1L << (lev + 1)); ++i) r += i;
+    return 2 * r + (1L << (lev + 1)) + 1;
+  }
+  return 2 + (seed == LPMX_SEED_ICOS_TRI_SPHERE ? 10 : 6) * ipow4(lev);
+}
+long nfaces_at(int seed, int lev) {
+  const int n0 = seed == LPMX_SEED_ICOS_TRI_SPHERE ? 20 : seed == LPMX_SEED_QUAD_RECT ? 4 : 6;
+  return n0 * ipow4(lev);
+}
+// Euler: V - E + F = 2 on the sphere, 1 for the planar seeds (free boundary)
+long nedges_at(int seed, int lev) {
+  const bool planar = seed == LPMX_SEED_QUAD_RECT || seed == LPMX_SEED_TRI_HEX;
+  return nverts_at(seed, lev) + nfaces_at(seed, lev) - (planar ? 1 : 2);
+}
 
 }  // namespace
 
@@ -381,7 +460,7 @@ int lpmx_mesh_max_allocations(int seed, int depth, int* n_verts, int* n_edges, i
   long nv = nverts_at(seed, depth), ne = 0, nf = 0;
   for (int i = 0; i <= depth; ++i) {
     nf += nfaces_at(seed, i);
-    ne += nverts_at(seed, i) + nfaces_at(seed, i) - 2;
+    ne += nedges_at(seed, i);
   }
   if (nf > 2000000000L || ne > 2000000000L) return LPMX_ERR_UNSUPPORTED;  // Index is int in the reference
   *n_verts = (int)nv;
@@ -401,14 +480,15 @@ int lpmx_mesh_create(int seed, int depth, double radius, lpmx_mesh_t* out) {
   try {
     m->seed = seed;
     m->nfv = d.nfv;
+    m->nd = d.nd;
     m->depth = depth;
-    m->vx.reserve(3L * nvmax);
-    m->vlag.reserve(3L * nvmax);
+    m->vx.reserve((long)d.nd * nvmax);
+    m->vlag.reserve((long)d.nd * nvmax);
     m->v_crd.reserve(nvmax);
     for (auto* v : {&m->eo, &m->ed, &m->el, &m->er, &m->ep}) v->reserve(nemax);
     m->ek.reserve(2L * nemax);
-    m->fx.reserve(3L * nfmax);
-    m->flag.reserve(3L * nfmax);
+    m->fx.reserve((long)d.nd * nfmax);
+    m->flag.reserve((long)d.nd * nfmax);
     m->farea.reserve(nfmax);
     m->fmask.reserve(nfmax);
     m->fverts.reserve((long)d.nfv * nfmax);
@@ -427,7 +507,7 @@ int lpmx_mesh_create(int seed, int depth, double radius, lpmx_mesh_t* out) {
       double vc[4][3];
       for (int j = 0; j < d.nfv; ++j)
         for (int k = 0; k < 3; ++k) vc[j][k] = sc[d.fverts[i * d.nfv + j]].v[k];
-      const double ar = polygon_area(sc[d.nverts + i].v, vc, d.nfv);  // MeshSeed::face_area (:281-294)
+      const double ar = m->geo_polygon_area(sc[d.nverts + i].v, vc, d.nfv);  // MeshSeed::face_area (:281-294)
       m->insert_face(sc[d.nverts + i].v, sc[d.nverts + i].v, &d.fverts[i * d.nfv], &d.fedges[i * d.nfv], kNull, ar);
     }
     // tree_init (lpm_polymesh2d_impl.hpp:25-42), including startInd = stopInd - 1

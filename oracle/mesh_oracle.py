@@ -21,7 +21,7 @@ NULL = -1
 ZERO_TOL = 2.220446049250313e-16
 
 
-def read_seed(path, nverts, nfaces, nedges, nfv):
+def read_seed(path, nverts, nfaces, nedges, nfv, ndim=3):
     """Parse a mesh seed .dat file the way MeshSeed::read_file does (line-number driven)."""
     crds, edges, fverts, fedges = [], [], [], []
     edge_hdr = fv_hdr = fe_hdr = None
@@ -36,7 +36,7 @@ def read_seed(path, nverts, nfaces, nedges, nfv):
                 fe_hdr = lineno
             tok = line.split()
             if 1 < lineno < ncrds + 2:
-                crds.append([float(t) for t in tok[:3]])
+                crds.append([float(t) for t in tok[:ndim]])
             elif edge_hdr and edge_hdr < lineno < edge_hdr + nedges + 1:
                 edges.append([int(t) for t in tok[:4]])
             elif fv_hdr and fv_hdr < lineno < fv_hdr + nfaces + 1:
@@ -50,7 +50,37 @@ def read_seed(path, nverts, nfaces, nedges, nfv):
 SEEDS = {
     "icos": dict(file="icosTriSphereSeed.dat", nverts=12, nfaces=20, nedges=30, nfv=3),
     "cubed": dict(file="cubedSphereSeed.dat", nverts=8, nfaces=6, nedges=12, nfv=4),
+    "quad_rect": dict(file="quadRectSeed.dat", nverts=9, nfaces=4, nedges=12, nfv=4, ndim=2),
+    "tri_hex": dict(file="triHexSeed.dat", nverts=7, nfaces=6, nedges=12, nfv=3, ndim=2),
 }
+
+
+# ---- PlaneGeometry (src/lpm_geometry.hpp:69-160) ----
+def _plane_tri_area(a, b, c):
+    ar = (b[0] - a[0]) * (c[1] - a[1]) - (b[1] - a[1]) * (c[0] - a[0])
+    return 0.5 * abs(ar)
+
+
+def _plane_poly_area(ctr, vs):
+    n = len(vs)
+    ar = 0.0
+    for i in range(n):
+        ar += _plane_tri_area(ctr, vs[i], vs[(i + 1) % n])
+    return ar
+
+
+def _plane_barycenter(vs):
+    n = len(vs)
+    v = [0.0, 0.0]
+    for p in vs:
+        v[0] += p[0]
+        v[1] += p[1]
+    s = 1.0 / n
+    return [v[0] * s, v[1] * s]
+
+
+def _plane_midpoint(a, b):
+    return [0.5 * (a[0] + b[0]), 0.5 * (a[1] + b[1])]
 
 
 def _dot(a, b):
@@ -104,12 +134,18 @@ def _midpoint(a, b):
 
 
 class TreeMesh:
-    def __init__(self, seed, depth, seed_dir="/root/reference/mesh_seeds"):
+    def __init__(self, seed, depth, seed_dir="/root/reference/mesh_seeds", radius=1.0):
         import os
         d = SEEDS[seed]
         self.nfv = nfv = d["nfv"]
+        self.ndim = d.get("ndim", 3)
+        if self.ndim == 2:
+            self._midpoint, self._barycenter, self._poly_area = _plane_midpoint, _plane_barycenter, _plane_poly_area
+        else:
+            self._midpoint, self._barycenter, self._poly_area = _midpoint, _barycenter, _poly_area
         crds, edges, fverts, fedges = read_seed(os.path.join(seed_dir, d["file"]), d["nverts"], d["nfaces"],
-                                                d["nedges"], nfv)
+                                                d["nedges"], nfv, self.ndim)
+        crds = [[c * radius for c in row] for row in crds]  # MeshSeed(maxr) (lpm_mesh_seed.cpp:10-18)
         nv = d["nverts"]
         self.vx = [list(c) for c in crds[:nv]]
         self.vlag = [list(c) for c in crds[:nv]]
@@ -124,7 +160,7 @@ class TreeMesh:
         for i in range(d["nfaces"]):
             ctr = list(crds[nv + i])
             vs = [self.vx[v] for v in fverts[i]]
-            self._add_face(ctr, list(ctr), list(fverts[i]), list(fedges[i]), NULL, _poly_area(ctr, vs))
+            self._add_face(ctr, list(ctr), list(fverts[i]), list(fedges[i]), NULL, self._poly_area(ctr, vs))
         start = 0
         for _ in range(depth):
             stop = len(self.fx)
@@ -183,9 +219,9 @@ class TreeMesh:
 
     def _split_edge(self, e):
         mid_v = len(self.vx)
-        self.vx.append(_midpoint(self.vx[self.eo[e]], self.vx[self.ed[e]]))
+        self.vx.append(self._midpoint(self.vx[self.eo[e]], self.vx[self.ed[e]]))
         # the reference takes the Lagrangian destination from the PHYSICAL array (lpm_edges.cpp:81)
-        self.vlag.append(_midpoint(self.vlag[self.eo[e]], self.vx[self.ed[e]]))
+        self.vlag.append(self._midpoint(self.vlag[self.eo[e]], self.vx[self.ed[e]]))
         k0 = self._add_edge(self.eo[e], mid_v, self.el[e], self.er[e], e)
         k1 = self._add_edge(mid_v, self.ed[e], self.el[e], self.er[e], e)
         self.ek[e] = [k0, k1]
@@ -256,8 +292,8 @@ class TreeMesh:
         for i in range(4):
             vs = [self.vx[v] for v in kv[i]]
             ls = [self.vlag[v] for v in kv[i]]
-            ctr = _barycenter(vs)
-            kids.append((ctr, _barycenter(ls), _poly_area(ctr, vs)))
+            ctr = self._barycenter(vs)
+            kids.append((ctr, self._barycenter(ls), self._poly_area(ctr, vs)))
         for i in range(4):
             self._add_face(kids[i][0], kids[i][1], kv[i], ke[i], f, kids[i][2])
         self.fkids[f] = [kid0 + i for i in range(4)]

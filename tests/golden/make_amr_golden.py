@@ -24,7 +24,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def nmaxfaces(seed, lev):
-    n0 = 20 if seed == "icos" else 6
+    n0 = {"icos": 20, "cubed": 6, "quad_rect": 4, "tri_hex": 6}[seed]
     return sum(n0 * 4 ** k for k in range(lev + 1))  # MeshSeed::set_max_allocations (lpm_mesh_seed.cpp:266-279)
 
 
@@ -61,7 +61,8 @@ def run_case(seed, depth, kind, amr_buffer, amr_limit, passes):
     return out
 
 
-CASES = [("icos", 2, "circ", 2, 2, 2), ("cubed", 2, "circ", 2, 2, 2), ("icos", 1, "random", 2, 2, 4), ("cubed", 1, "random", 2, 2, 4)]
+CASES = [("icos", 2, "circ", 2, 2, 2), ("cubed", 2, "circ", 2, 2, 2), ("icos", 1, "random", 2, 2, 4), ("cubed", 1, "random", 2, 2, 4),
+         ("quad_rect", 1, "random", 2, 2, 4), ("tri_hex", 1, "random", 2, 2, 4)]
 
 if __name__ == "__main__":
     for seed, depth, kind, buf, lim, passes in CASES:

@@ -20,7 +20,8 @@ from lpm_b200.api import PolyMesh2d
 from conftest import field_rel_err
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-AMR_CASES = [("icos", 2, "circ"), ("cubed", 2, "circ"), ("icos", 1, "random"), ("cubed", 1, "random")]
+AMR_CASES = [("icos", 2, "circ"), ("cubed", 2, "circ"), ("icos", 1, "random"), ("cubed", 1, "random"),
+             ("quad_rect", 1, "random"), ("tri_hex", 1, "random")]
 INT_ARRAYS = ["edge_origs", "edge_dests", "edge_lefts", "edge_rights", "edge_parents", "edge_kids", "face_verts",
               "face_edges", "face_parent", "face_kids", "face_level", "face_leaf_idx", "face_mask"]
 REAL_ARRAYS = ["vert_xyz", "vert_lag_xyz", "face_xyz", "face_lag_xyz", "face_area"]

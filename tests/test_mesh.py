@@ -93,3 +93,72 @@ def test_tree_invariants(seed, depth):
     v = m.vert_xyz[m.face_verts[leaf]]
     n = np.cross(v[:, 1] - v[:, 0], v[:, 2] - v[:, 1])
     assert ((n * m.face_xyz[leaf]).sum(axis=1) > 0).all()
+
+
+# ---- planar seeds (QuadRectSeed, TriHexSeed; PlaneGeometry) -----------------------------------------------------------------
+PLANE_CASES = [("quad_rect", 0, 1.0), ("quad_rect", 2, 1.0), ("quad_rect", 3, 4.0), ("quad_rect", 4, 6.0),
+               ("tri_hex", 0, 1.0), ("tri_hex", 2, 1.0), ("tri_hex", 3, 6.0)]
+
+
+@pytest.mark.parametrize("seed,depth,radius", PLANE_CASES)
+def test_planar_mesh_matches_golden_bit_exact(seed, depth, radius):
+    g = np.load(os.path.join(GOLDEN, f"mesh_{seed}_{depth}_r{radius:g}.npz"))
+    m = PolyMesh2d(seed, depth, radius=radius)
+    assert m.ndim == 2 and m.vert_xyz.shape[1] == 2 and m.face_xyz.shape[1] == 2
+    for k in INT_ARRAYS:
+        assert np.array_equal(g[k], getattr(m, k)), k
+    for k in REAL_ARRAYS:
+        assert np.array_equal(g[k].view(np.int64), getattr(m, k).view(np.int64)), k
+
+
+def test_embedded_planar_seed_tables_equal_reference_dat_files():
+    t = np.load(os.path.join(GOLDEN, "seed_tables.npz"))
+    for seed, nv in (("quad_rect", 9), ("tri_hex", 7)):
+        m = PolyMesh2d(seed, 0)
+        assert np.array_equal(t[f"{seed}_crds"][:nv], m.vert_xyz)
+        assert np.array_equal(t[f"{seed}_crds"][nv:], m.face_xyz)
+        assert np.array_equal(t[f"{seed}_edges"], np.stack([m.edge_origs, m.edge_dests, m.edge_lefts, m.edge_rights], axis=1))
+        assert np.array_equal(t[f"{seed}_face_verts"], m.face_verts)
+        assert np.array_equal(t[f"{seed}_face_edges"], m.face_edges)
+
+
+@pytest.mark.parametrize("seed,depth,radius,area", [("tri_hex", 3, 1.0, 1.5 * np.sqrt(3.0)), ("quad_rect", 3, 4.0, 64.0),
+                                                      ("quad_rect", 5, 6.0, 144.0)])
+def test_planar_counts_equal_max_allocations_and_area(seed, depth, radius, area):
+    """tests/lpm_polymesh_tests.cpp:30-67: nh == nmax for all three element kinds; the hexagon has area 3 sqrt(3)/2 r^2,
+    the square (2 r)^2 (FloatingPoint::equiv, i.e. within zero_tol scaled -- here 1e-13 relative)."""
+    m = PolyMesh2d(seed, depth, radius=radius)
+    assert (m.n_verts, m.n_edges, m.n_faces) == max_allocations(seed, depth)
+    total = 0.0
+    for a in m.face_area:
+        total += a
+    assert abs(total - area) < 1e-13 * area
+    assert m.n_face_leaves == (4 if seed == "quad_rect" else 6) * 4 ** depth
+
+
+@pytest.mark.parametrize("seed", ["quad_rect", "tri_hex"])
+def test_planar_tree_invariants(seed):
+    depth, radius = 4, 2.0
+    m = PolyMesh2d(seed, depth, radius=radius)
+    leaf = m.face_mask == 0
+    assert np.array_equal(~leaf, m.face_kids[:, 0] > 0)
+    assert (m.face_area[~leaf] == 0).all() and (m.face_area[leaf] > 0).all()
+    assert (m.face_level[leaf] == depth + 1).all()
+    # free boundary: boundary edges have no right face; interior leaf edges separate two leaves
+    eleaf = m.edge_kids[:, 0] <= 0
+    boundary = m.edge_rights < 0
+    assert leaf[m.edge_lefts[eleaf]].all() and leaf[m.edge_rights[eleaf & ~boundary]].all()
+    n_b = (eleaf & boundary).sum()
+    assert n_b == (8 if seed == "quad_rect" else 6) * 2 ** depth
+    # Euler characteristic of a disc: V - E + F = 1
+    assert m.n_verts - eleaf.sum() + leaf.sum() == 1
+    # boundary vertices sit on the square / inside the circumscribed circle; faces are counter-clockwise
+    if seed == "quad_rect":
+        assert np.abs(m.vert_xyz).max() == radius
+    else:
+        assert np.linalg.norm(m.vert_xyz, axis=1).max() <= radius * (1 + 1e-15)
+    v = m.vert_xyz[m.face_verts[leaf]]
+    cr = (v[:, 1, 0] - v[:, 0, 0]) * (v[:, 2, 1] - v[:, 1, 1]) - (v[:, 1, 1] - v[:, 0, 1]) * (v[:, 2, 0] - v[:, 1, 0])
+    assert (cr > 0).all()
+    # Lagrangian == physical at build time
+    assert np.array_equal(m.vert_xyz, m.vert_lag_xyz) and np.array_equal(m.face_xyz, m.face_lag_xyz)
