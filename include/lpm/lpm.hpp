@@ -12,6 +12,7 @@
 #include "lpm_geometry.hpp"
 #include "lpm_incompressible2d.hpp"
 #include "lpm_logger.hpp"
+#include "lpm_plane.hpp"
 #include "lpm_polymesh2d.hpp"
 #include "lpm_refinement.hpp"
 #include "lpm_swe.hpp"

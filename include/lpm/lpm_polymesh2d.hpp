@@ -1,5 +1,5 @@
-// lpm/lpm_polymesh2d.hpp -- MeshSeed<Seed>, PolyMeshParameters<Seed> and PolyMesh2d<Seed> for the two spherical
-// seeds, backed by the C ABI's host mesh generator (lpmx_mesh_*).
+// lpm/lpm_polymesh2d.hpp -- MeshSeed<Seed>, PolyMeshParameters<Seed> and PolyMesh2d<Seed>, backed by the C ABI's host mesh
+// generator (lpmx_mesh_*); the two spherical seeds are defined here, the planar ones in lpm_plane.hpp.
 //   MeshSeed / IcosTriSphereSeed / CubedSphereSeed     src/mesh/lpm_mesh_seed.hpp:111-147,150-230
 //   MeshSeed::set_max_allocations                      src/mesh/lpm_mesh_seed.cpp:266-279
 //   PolyMeshParameters                                 src/mesh/lpm_polymesh2d.hpp:32-72
@@ -12,6 +12,7 @@
 #ifndef LPM_SHIM_POLYMESH2D_HPP
 #define LPM_SHIM_POLYMESH2D_HPP
 
+#include <limits>
 #include <memory>
 
 #include "lpm_coords.hpp"
@@ -100,6 +101,13 @@ struct Faces {
       if (!mask(i)) s += area(i);
     return std::sqrt(s / n_leaves_);
   }
+  /// sqrt(smallest leaf area) (src/mesh/lpm_faces_impl.hpp:228-240; Kokkos::Min identity = largest double)
+  Real appx_min_mesh_size() const {
+    Real result = std::numeric_limits<Real>::max();
+    for (Index i = 0; i < n_; ++i)
+      if (!mask(i)) result = (area(i) < result ? area(i) : result);
+    return std::sqrt(result);
+  }
   Real surface_area_host() const {
     Real s = 0;
     for (Index i = 0; i < n_; ++i) s += area(i);
@@ -172,10 +180,11 @@ class PolyMesh2d {
     Index flag_count = 0;
     for (Index i = 0; i < n_faces_host(); ++i) flag_count += (flags(i) ? 1 : 0);
     logger.debug("dividing {} flagged faces...", flag_count);
-    push(LPMX_MESH_VERT_XYZ, vertices.phys_crds.view.data(), 3L * n_vertices_host());
-    push(LPMX_MESH_VERT_LAG_XYZ, vertices.lag_crds.view.data(), 3L * n_vertices_host());
-    push(LPMX_MESH_FACE_XYZ, faces.phys_crds.view.data(), 3L * n_faces_host());
-    push(LPMX_MESH_FACE_LAG_XYZ, faces.lag_crds.view.data(), 3L * n_faces_host());
+    const long nd = Geo::ndim;
+    push(LPMX_MESH_VERT_XYZ, vertices.phys_crds.view.data(), nd * n_vertices_host());
+    push(LPMX_MESH_VERT_LAG_XYZ, vertices.lag_crds.view.data(), nd * n_vertices_host());
+    push(LPMX_MESH_FACE_XYZ, faces.phys_crds.view.data(), nd * n_faces_host());
+    push(LPMX_MESH_FACE_LAG_XYZ, faces.lag_crds.view.data(), nd * n_faces_host());
     int refine_count = 0, outcome = 0;
     const int rc = lpmx_mesh_divide_flagged_faces(handle_.get(), flags.data(), (int)flags.extent(0), nmaxfaces_,
                                                   params.init_depth + params.amr_limit, &refine_count, &outcome);
@@ -197,6 +206,7 @@ class PolyMesh2d {
   Index n_edges_host() const { return edges.nh(); }
   Index n_faces_host() const { return faces.nh(); }
   Real appx_mesh_size() const { return faces.appx_mesh_size(); }
+  Real appx_min_mesh_size() const { return faces.appx_min_mesh_size(); }
   Real surface_area_host() const { return faces.surface_area_host(); }
   virtual void update_device() const {}
   virtual void update_host() const {}

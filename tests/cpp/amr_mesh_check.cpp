@@ -7,7 +7,7 @@
 #include <cstring>
 #include <string>
 
-#include "lpm/lpm_polymesh2d.hpp"
+#include "lpm/lpm.hpp"
 
 using namespace Lpm;
 
@@ -19,7 +19,7 @@ static uint64_t fnv(const void* p, size_t bytes, uint64_t h = 146959810393466560
 
 template <typename Seed>
 int run(int depth, int amr, int passes) {
-  PolyMeshParameters<Seed> params(depth, 1.0, amr, amr);
+  PolyMeshParameters<Seed> params(depth, Seed::geo::ndim == 2 ? 3.0 : 1.0, amr, amr);  // planar meshes: radius 3
   PolyMesh2d<Seed> mesh(params);
   Logger logger("amr_mesh_check", Log::none);
   mask_view_type flags("flags", mesh.faces.area.extent(0));
@@ -34,10 +34,11 @@ int run(int depth, int amr, int passes) {
   if (area_alias.data() != mesh.faces.area.data()) return 3;
   const Index nv = mesh.n_vertices_host(), ne = mesh.n_edges_host(), nf = mesh.n_faces_host();
   std::printf("%d %d %d %d %d %d\n", nv, ne, nf, mesh.faces.n_leaves_host(), mesh.edges.n_leaves_host(), logger.count(Log::warn));
-  uint64_t h = fnv(mesh.vertices.phys_crds.view.data(), sizeof(Real) * 3 * nv);
-  h = fnv(mesh.vertices.lag_crds.view.data(), sizeof(Real) * 3 * nv, h);
-  h = fnv(mesh.faces.phys_crds.view.data(), sizeof(Real) * 3 * nf, h);
-  h = fnv(mesh.faces.lag_crds.view.data(), sizeof(Real) * 3 * nf, h);
+  constexpr int nd = Seed::geo::ndim;
+  uint64_t h = fnv(mesh.vertices.phys_crds.view.data(), sizeof(Real) * nd * nv);
+  h = fnv(mesh.vertices.lag_crds.view.data(), sizeof(Real) * nd * nv, h);
+  h = fnv(mesh.faces.phys_crds.view.data(), sizeof(Real) * nd * nf, h);
+  h = fnv(mesh.faces.lag_crds.view.data(), sizeof(Real) * nd * nf, h);
   h = fnv(mesh.faces.area.data(), sizeof(Real) * nf, h);
   h = fnv(mesh.faces.mask.data(), nf, h);
   h = fnv(mesh.faces.verts.data(), sizeof(Index) * Seed::faceKind::nverts * nf, h);
@@ -60,7 +61,10 @@ int main(int argc, char** argv) {
   if (argc < 5) return 2;
   const int depth = std::atoi(argv[2]), amr = std::atoi(argv[3]), passes = std::atoi(argv[4]);
   try {
-    if (std::string(argv[1]) == "icos") return run<IcosTriSphereSeed>(depth, amr, passes);
+    const std::string seed(argv[1]);
+    if (seed == "icos") return run<IcosTriSphereSeed>(depth, amr, passes);
+    if (seed == "quad_rect") return run<QuadRectSeed>(depth, amr, passes);
+    if (seed == "tri_hex") return run<TriHexSeed>(depth, amr, passes);
     return run<CubedSphereSeed>(depth, amr, passes);
   } catch (const std::exception& e) {
     std::fprintf(stderr, "%s\n", e.what());

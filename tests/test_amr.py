@@ -92,7 +92,7 @@ def _fnv(arrays):
     return h
 
 
-@pytest.mark.parametrize("seed,depth,amr,passes", [("icos", 2, 2, 3), ("cubed", 2, 1, 3)])
+@pytest.mark.parametrize("seed,depth,amr,passes", [("icos", 2, 2, 3), ("cubed", 2, 1, 3), ("quad_rect", 2, 1, 3), ("tri_hex", 1, 2, 3)])
 def test_cpp_shim_divide_flagged_faces_equals_the_binding(seed, depth, amr, passes):
     """include/lpm/lpm_polymesh2d.hpp (PolyMesh2d<Seed>::divide_flagged_faces: nmax-sized views refilled in place, coordinates
     pushed first, Logger warnings) against the ctypes binding on the same flag rule; host-only program, no engine."""
@@ -108,7 +108,7 @@ def test_cpp_shim_divide_flagged_faces_equals_the_binding(seed, depth, amr, pass
     p = subprocess.run([exe, seed, str(depth), str(amr), str(passes)], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
     counts, digest = p.stdout.split("\n")[:2]
-    m = PolyMesh2d(seed, depth, amr_buffer=amr, amr_limit=amr)
+    m = PolyMesh2d(seed, depth, radius=3.0 if seed in ("quad_rect", "tri_hex") else 1.0, amr_buffer=amr, amr_limit=amr)
     warnings = 0
     for _ in range(passes):
         flags = np.zeros(m.nmaxfaces, dtype=np.uint8)

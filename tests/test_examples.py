@@ -10,7 +10,8 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "examples", "_build")
-EXAMPLES = ["bve_rotation", "sphere_rh54", "sphere_gaussian_vortex", "sphere_swe_tc2"]
+EXAMPLES = ["bve_rotation", "sphere_rh54", "sphere_gaussian_vortex", "sphere_swe_tc2", "plane_gravity_wave",
+            "plane_colliding_dipoles"]
 
 
 @pytest.fixture(scope="module")
@@ -131,3 +132,27 @@ def test_rh54_remesh_triggered_by_ftle(built):
     """examples/sphere_rh54.cpp:247-258: -rt ftle remeshes when the maximum FTLE exceeds -ftle."""
     out, log = _run(built, "sphere_rh54", "-d", "3", "-tf", "0.2", "-n", "8", "-rt", "ftle", "-ftle", "0.05")
     assert "triggered by ftle" in log and "remeshes: 0" not in log
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", ["quad", "tri"])
+def test_plane_gravity_wave_example(built, seed):
+    """examples/plane_gravity_wave.cpp with its defaults scaled down (depth 4 -> 3): SWE<QuadRectSeed> + SWERK4 over a Gaussian
+    mountain.  The wave spreads: the crest drops, the depth stays positive, mass (a Lagrangian invariant) is conserved."""
+    out, log = _run(built, "plane_gravity_wave", "-s", seed, "-d", "3", "-tf", "0.25", "-n", "5")
+    assert out["steps"] == 5 and out["gpu_launches"] > 0
+    assert out["mass_drift"] < 1e-14
+    assert out["surf_max"] < out["surf_max0"] and out["min_depth"] > 0.1 and 0 < out["max_speed"] < 1.0
+    assert "SWERK4: dt = 0.05" in log and "PlanarGaussianMountain" in log
+
+
+@pytest.mark.gpu
+def test_plane_colliding_dipoles_example(built):
+    """examples/plane_colliding_dipoles.cpp: uniform mesh, then with two adaptive levels driven by the circulation and
+    vorticity-variation flags; the total vorticity of the two opposite dipoles is zero."""
+    uni, _ = _run(built, "plane_colliding_dipoles", "-d", "4", "-tf", "0.1", "-n", "4")
+    assert uni["steps"] == 4 and abs(uni["total_vorticity"]) < 1e-12 and uni["ke_drift"] < 1e-2
+    out, log = _run(built, "plane_colliding_dipoles", "-d", "4", "-tf", "0.1", "-n", "4", "-amr", "2", "-c", "0.2", "-zv", "0.3")
+    assert "amr is enabled with limit 2" in log and "vorticity variation refinement count" in log
+    assert out["n_leaves"] > uni["n_leaves"] and out["max_level"] == 4 + 2 + 1
+    assert out["ke_drift"] < 1e-2

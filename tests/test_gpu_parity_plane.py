@@ -243,3 +243,35 @@ def test_plane_sums_large_subset(engine, OP):
         assert field_rel_err(fz[k] + fs[k], full[k]) < 1e-13, k
     assert np.abs(fz["phi"]).max() == 0.0 and np.abs(fs["psi"]).max() == 0.0
     assert np.array_equal(fz["laps"], full["laps"])  # the PSE term does not depend on the strengths
+
+
+@pytest.mark.parametrize("seed", ["quad_rect", "tri_hex"])
+def test_swe_plane_rk4_on_the_generated_planar_meshes(engine, OP, seed):
+    """examples/plane_gravity_wave.cpp end to end at depth 3, radius 6: the mesh from the product's generator (PolyMesh2d of
+    QuadRectSeed / TriHexSeed, divided parents included as targets), the example's surface and mountain, SWE::init_direct_sums
+    and 3 SWERK4 steps on the device against the oracle stepper.  Tolerance: STEP_TOL field-relative."""
+    from lpm_b200.api import PolyMesh2d
+    m = PolyMesh2d(seed, 3, radius=6.0)
+    nv, nf = m.n_verts, m.n_faces
+    vb, fb = plane_cases.gaussian_mountain(m.vert_xyz), plane_cases.gaussian_mountain(m.face_xyz)
+    vs, fs = plane_cases.surface_perturbation(m.vert_xyz), plane_cases.surface_perturbation(m.face_xyz)
+    P = {"xy": m.vert_xyz, "vort": np.zeros(nv), "div": np.zeros(nv), "depth": vs - vb, "surf": vs, "bottom": vb}
+    A = {"xy": m.face_xyz, "vort": np.zeros(nf), "div": np.zeros(nf), "area": m.face_area, "mass": (fs - fb) * m.face_area,
+         "depth": fs - fb, "surf": fs, "bottom": fb}
+    st = OP.PlaneSWEState(P, A, m.face_mask)
+    leaf = m.face_mask == 0
+    pse = plane_cases.pse_eps_of(np.sqrt(m.face_area[leaf].sum() / leaf.sum()))  # mesh.appx_mesh_size()
+    OP.swe_plane_init_direct_sums(st, 0.0, pse)
+    # the engine's own init_direct_sums on the same raw fields
+    sums_p = api.swe_plane_sums(engine, st.p["xy"], st.p["surf"], st.a["xy"], st.a["vort"], st.a["div"], st.a["area"], st.mask,
+                                st.a["surf"], 0.0, pse, targets_are_sources=False)
+    assert field_rel_err(sums_p["laps"], st.p["laps"]) < SUM_TOL  # the fluid starts at rest: only the PSE Laplacian is non-zero
+    assert np.abs(sums_p["vel"]).max() == 0.0 and np.abs(st.p["vel"]).max() == 0.0
+    gp = {k: st.p[k].copy() for k in api.PLANE_PASSIVE_FIELDS}
+    ga = {k: st.a[k].copy() for k in api.PLANE_ACTIVE_FIELDS}
+    OP.swe_plane_rk4_step(0.05, 0.0, 0.0, 1.0, 0.0, pse, 1, st, n_steps=3)
+    api.swe_plane_rk4_step(engine, 0.05, 0.0, 0.0, 1.0, 0.0, pse, 1, gp, ga, st.mask, n_steps=3)
+    errs = {"p_" + k: field_rel_err(gp[k], st.p[k]) for k in api.PLANE_PASSIVE_FIELDS}
+    errs.update({"a_" + k: field_rel_err(ga[k], st.a[k]) for k in api.PLANE_ACTIVE_FIELDS})
+    assert max(errs.values()) < STEP_TOL, errs
+    assert np.array_equal(ga["mass"], st.a["mass"])  # mass is carried, never recomputed
