@@ -1,5 +1,5 @@
 """Run under torchrun (one rank per GPU): sharded BVERK4 / IC2D RK2 / SWERK2 steps must equal the CPU oracle on every rank.
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py
 Used by tests/test_gpu_multi.py; exits non-zero on any mismatch."""
 import os
 import sys

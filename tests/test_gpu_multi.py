@@ -23,7 +23,7 @@ def test_sharded_steppers_equal_oracle(world):
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
-           "127.0.0.1", "--master-port", str(29500 + 7 * world), os.path.join(ROOT, "tools", "multi_gpu_check.py")]
+           "127.0.0.1", "--master-port", str(29500 + 7 * world), os.path.join(ROOT, "tests", "multi_gpu_check.py")]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert p.stdout.count("swe_rk2 cubed-3: ok") == world
