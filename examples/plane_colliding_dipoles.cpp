@@ -80,6 +80,11 @@ int main(int argc, char** argv) {
     auto solver = std::make_unique<Incompressible2DRK2<seed_type>>(dt, *plane);
     Real max_ftle = 0;
     const Real tref = 0;
+    const std::string vtk_root =
+        opt.has("-o") ? opt.get_str("-o", "") + "_" + seed_type::id_string() + std::to_string(mesh_params.init_depth) + "_" : "";
+    const int write_frequency = opt.get_int("-of", 1);
+    int frame_counter = 0;
+    if (!vtk_root.empty()) vtk_mesh_interface(*plane).write(vtk_frame_name(vtk_root, frame_counter));
     Timer loop;
     for (int t_idx = 0; t_idx < nsteps; ++t_idx) {
       plane->advance_timestep(*solver);
@@ -88,6 +93,8 @@ int main(int argc, char** argv) {
                                   plane->mesh.faces.mask, plane->t - tref);
       ftle.apply(plane->mesh.n_faces_host());
       max_ftle = get_max_ftle(plane->ftle.view, plane->mesh.faces.mask, plane->mesh.n_faces_host());
+      if (!vtk_root.empty() && (t_idx + 1) % write_frequency == 0)
+        vtk_mesh_interface(*plane).write(vtk_frame_name(vtk_root, ++frame_counter));
     }
     const double loop_s = loop.seconds();
     const Real vort1 = plane->total_vorticity(), ke1 = plane->total_kinetic_energy(), ens1 = plane->total_enstrophy();

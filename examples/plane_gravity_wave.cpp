@@ -35,8 +35,18 @@ int run(const Options& opt) {
   const auto s0 = plane->surf_active.range(plane->mesh.n_faces_host());
   auto solver = std::make_unique<SWERK4<seed_type, topography_type>>(dt, *plane, topo);
   std::printf("%s", solver->info_string().c_str());
+  // -o <root> [-of n]: .vtp frames at t = 0 and after every n-th step (:139-150,160-170)
+  const std::string vtk_root =
+      opt.has("-o") ? opt.get_str("-o", "") + "_" + seed_type::id_string() + std::to_string(mesh_params.init_depth) + "_" : "";
+  const int write_frequency = opt.get_int("-of", 1);
+  int frame_counter = 0;
+  if (!vtk_root.empty()) vtk_mesh_interface(*plane).write(vtk_frame_name(vtk_root, frame_counter));
   Timer loop;
-  for (int t_idx = 0; t_idx < nsteps; ++t_idx) plane->advance_timestep(*solver);
+  for (int t_idx = 0; t_idx < nsteps; ++t_idx) {
+    plane->advance_timestep(*solver);
+    if (!vtk_root.empty() && (t_idx + 1) % write_frequency == 0)
+      vtk_mesh_interface(*plane).write(vtk_frame_name(vtk_root, ++frame_counter));
+  }
   const double loop_s = loop.seconds();
   const Real mass1 = plane->total_mass();
   const Index nv = plane->mesh.n_vertices_host(), nf = plane->mesh.n_faces_host(), nl = plane->mesh.faces.n_leaves_host();

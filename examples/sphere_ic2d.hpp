@@ -1,7 +1,7 @@
 // sphere_ic2d.hpp -- the driver shared by sphere_rh54 and sphere_gaussian_vortex: Incompressible2D +
 // Incompressible2DRK2 on the sphere (reference: examples/sphere_rh54.cpp:56-380, examples/sphere_gaussian_vortex.cpp:36-300):
 // adaptive refinement at start-up (-ab / -al / -amr, -c), remeshing on an interval or on the FTLE (-rm, -rs, -ro, -rt, -ftle),
-// uniform or adaptive.  Per-step VTK output is left to the caller (lpm_vtk_io.hpp).
+// uniform or adaptive; -o <root> -of <n> writes .vtp frames of the model (vtk_mesh_interface).
 #ifndef LPMX_EXAMPLE_SPHERE_IC2D_HPP
 #define LPMX_EXAMPLE_SPHERE_IC2D_HPP
 #include <limits>
@@ -74,6 +74,11 @@ int run_ic2d(const char* example, const Options& opt, Vorticity& vorticity, cons
               vel_range.second, cr);
   const Real vort0 = sphere->total_vorticity(), ke0 = sphere->total_kinetic_energy(), ens0 = sphere->total_enstrophy();
   auto solver = std::make_unique<Incompressible2DRK2<seed_type>>(dt, *sphere);
+  // -o <root> [-of n]: a .vtp frame of the whole model at t = 0 and after every n-th step (reference: LPM_USE_VTK blocks)
+  const std::string vtk_root = opt.has("-o") ? opt.get_str("-o", "") + "_" + seed_type::id_string() + std::to_string(depth) + "_" : "";
+  const Int write_frequency = opt.get_int("-of", 1);
+  int frame_counter = 0;
+  if (!vtk_root.empty()) vtk_mesh_interface(*sphere).write(vtk_frame_name(vtk_root, frame_counter));
   Timer loop;
   Real max_ftle = 0;
   // examples/sphere_rh54.cpp:190-198,255-300: rebuild the particle set every remesh_interval steps (uniform meshes)
@@ -127,6 +132,8 @@ int run_ic2d(const char* example, const Options& opt, Vorticity& vorticity, cons
         throw std::runtime_error("device and host max_ftle disagree");
     }
     per_step(*sphere, vorticity);
+    if (!vtk_root.empty() && (t_idx + 1) % write_frequency == 0)
+      vtk_mesh_interface(*sphere).write(vtk_frame_name(vtk_root, ++frame_counter));
   }
   std::printf("max_ftle = %.12e; remeshes: %d\n", max_ftle, rm_counter);
   const double loop_s = loop.seconds();

@@ -55,8 +55,17 @@ int run(const Options& opt) {
   scalar_view_type depth0("depth0", nv), zeta0("zeta0", nf);
   for (Index i = 0; i < nv; ++i) depth0(i) = sphere->depth_passive.view(i);
   for (Index i = 0; i < nf; ++i) zeta0(i) = sphere->rel_vort_active.view(i);
+  // -o <root> [-of n]: .vtp frames of the model at t = 0 and after every n-th step (examples/sphere_swe_tc2.cpp:157-168,199-210)
+  const std::string vtk_root = opt.has("-o") ? opt.get_str("-o", "") + "_" + seed_type::id_string() + "_" : "";
+  const int write_frequency = opt.get_int("-of", 1);
+  int frame_counter = 0;
+  if (!vtk_root.empty()) vtk_mesh_interface(*sphere).write(vtk_frame_name(vtk_root, frame_counter));
   Timer loop;
-  for (int t_idx = 0; t_idx < nsteps; ++t_idx) sphere->advance_timestep(*solver);
+  for (int t_idx = 0; t_idx < nsteps; ++t_idx) {
+    sphere->advance_timestep(*solver);
+    if (!vtk_root.empty() && (t_idx + 1) % write_frequency == 0)
+      vtk_mesh_interface(*sphere).write(vtk_frame_name(vtk_root, ++frame_counter));
+  }
   const double loop_s = loop.seconds();
 
   // TC2 is steady: report how far the fields drifted (the reference writes these as VTK error fields)

@@ -17,4 +17,5 @@
 #include "lpm_refinement.hpp"
 #include "lpm_swe.hpp"
 #include "lpm_views.hpp"
+#include "lpm_vtk_interfaces.hpp"
 #endif

@@ -327,6 +327,8 @@ class PlaneSWE {
   VectorField<geo, FaceField> velocity_active;
   PolyMesh2d<SeedType> mesh;
   Coriolis coriolis;
+  std::map<std::string, ScalarField<VertexField>> tracer_passive;
+  std::map<std::string, ScalarField<FaceField>> tracer_active;
   Real g, t, eps, pse_eps;
 
   PlaneSWE(const PolyMeshParameters<SeedType>& mp, const Coriolis& coriolis)

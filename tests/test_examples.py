@@ -156,3 +156,24 @@ def test_plane_colliding_dipoles_example(built):
     assert "amr is enabled with limit 2" in log and "vorticity variation refinement count" in log
     assert out["n_leaves"] > uni["n_leaves"] and out["max_level"] == 4 + 2 + 1
     assert out["ke_drift"] < 1e-2
+
+
+@pytest.mark.gpu
+def test_drivers_write_vtp_frames(built, tmp_path):
+    """-o <root> -of <n>: a .vtp frame of the whole model at t = 0 and after every n-th step, as the reference's LPM_USE_VTK
+    blocks do (vtk_mesh_interface + VtkPolymeshInterface::write)."""
+    import xml.etree.ElementTree as ET
+    root = str(tmp_path / "gw")
+    out, _ = _run(built, "plane_gravity_wave", "-d", "3", "-tf", "0.2", "-n", "4", "-o", root, "-of", "2")
+    frames = sorted(f for f in os.listdir(tmp_path) if f.startswith("gw_quad_rect3_"))
+    assert frames == ["gw_quad_rect3_0000.vtp", "gw_quad_rect3_0001.vtp", "gw_quad_rect3_0002.vtp"]
+    piece = ET.parse(os.path.join(tmp_path, frames[-1])).getroot().find("PolyData/Piece")
+    assert int(piece.get("NumberOfPoints")) == out["n_verts"] and int(piece.get("NumberOfPolys")) == out["n_leaves"]
+    names = [da.get("Name") for da in piece.find("CellData").findall("DataArray")]
+    assert "surface_height" in names and "du1dx1" in names and "mass" in names
+    surf = [da for da in piece.find("CellData").findall("DataArray") if da.get("Name") == "surface_height"][0]
+    vals = [float(t) for t in surf.text.split()]
+    assert abs(max(vals) - out["surf_max"]) < 1e-8 and abs(min(vals) - out["surf_min"]) < 1e-8
+    root2 = str(tmp_path / "rh")
+    _run(built, "sphere_rh54", "-d", "3", "-tf", "0.02", "-n", "2", "-o", root2)
+    assert sorted(f for f in os.listdir(tmp_path) if f.startswith("rh_")) == [f"rh_cubed_sphere3_000{k}.vtp" for k in range(3)]

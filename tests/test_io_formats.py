@@ -84,3 +84,42 @@ def test_matlab_text_matches_the_reference_writer(driver, tmp_path):
     else:
         assert lines[1].startswith("area = [") and lines[1].endswith("];\n") and lines[1].count(",") == m.n_faces - 1
         assert lines[2].startswith("xyz = [") and lines[2].count(";") == m.n_verts  # n-1 row breaks + the final "];"
+
+
+def test_vtk_mesh_interface_of_the_models(tmp_path):
+    """vtk_mesh_interface(SWE<QuadRectSeed>) and vtk_mesh_interface(Incompressible2D<CubedSphereSeed>)
+    (src/lpm_swe_impl.hpp:489-530, src/lpm_incompressible2d_impl.hpp:298-317): array order and names as in the reference,
+    values as the init functors left them, planar points with z = 0."""
+    exe = str(tmp_path / "vtk_models_test")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "vtk_models_test.cpp"),
+                    "-o", exe, "-L" + os.path.join(ROOT, "lpm_b200"), "-llpmx", "-Wl,-rpath," + os.path.join(ROOT, "lpm_b200")],
+                   check=True, capture_output=True)
+    swe_vtp, ic2d_root = str(tmp_path / "swe.vtp"), str(tmp_path / "ic2d")
+    subprocess.run([exe, swe_vtp, ic2d_root], check=True)
+    # planar SWE
+    m = PolyMesh2d("quad_rect", 2, radius=6.0)
+    leaf = m.face_mask == 0
+    piece = ET.parse(swe_vtp).getroot().find("PolyData/Piece")
+    pts = _arrays(piece.find("Points"))["Points"]
+    assert np.array_equal(pts[:, :2], m.vert_xyz) and not pts[:, 2].any()
+    pd, cd = _arrays(piece.find("PointData")), _arrays(piece.find("CellData"))
+    assert list(pd) == ["lag_crds", "relative_vorticity", "potential_vorticity", "divergence", "surface_height",
+                        "surface_laplacian", "depth", "double_dot", "du1dx1", "du1dx2", "du2dx1", "du2dx2", "bottom_height",
+                        "stream_function", "potential", "velocity"]
+    assert list(cd) == ["area", "lag_crds", "relative_vorticity", "potential_vorticity", "divergence", "surface_height", "depth",
+                        "surface_laplacian", "double_dot", "du1dx1", "du1dx2", "du2dx1", "du2dx2", "bottom_height", "velocity",
+                        "mass", "stream_function", "potential"]
+    bot = 0.8 * np.exp(-5.0 * (m.face_xyz ** 2).sum(axis=1))
+    surf = 1.0 + 0.1 * np.exp(-(20 * (m.face_xyz[:, 0] + 1.125) ** 2 + 5 * m.face_xyz[:, 1] ** 2))
+    assert np.allclose(cd["bottom_height"], bot[leaf], rtol=1e-15, atol=0) and np.allclose(cd["surface_height"], surf[leaf], rtol=1e-15)
+    assert np.allclose(cd["mass"], ((surf - bot) * m.face_area)[leaf], rtol=1e-15)
+    assert pd["velocity"].shape == (m.n_verts, 2) and cd["lag_crds"].shape == (m.n_face_leaves, 2)
+    # spherical Incompressible2D, frame 7 of root "ic2d_"
+    ms = PolyMesh2d("cubed", 2)
+    piece = ET.parse(ic2d_root + "_0007.vtp").getroot().find("PolyData/Piece")
+    pd, cd = _arrays(piece.find("PointData")), _arrays(piece.find("CellData"))
+    assert list(pd) == ["lag_crds", "relative_vorticity", "stream_function", "velocity", "crds", "lat0"]
+    assert list(cd) == ["area", "lag_crds", "relative_vorticity", "stream_function", "velocity", "crds", "ftle", "lat0"]
+    assert np.array_equal(pd["crds"], ms.vert_xyz)  # ref_crds start as the physical coordinates
+    lat = np.arctan2(ms.vert_xyz[:, 2], np.sqrt(ms.vert_xyz[:, 0] ** 2 + ms.vert_xyz[:, 1] ** 2))
+    assert np.allclose(pd["lat0"], lat, rtol=0, atol=1e-15)
