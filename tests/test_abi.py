@@ -77,3 +77,39 @@ def test_mesh_radius_scales_coordinates():
     b = PolyMesh2d("cubed", 1, radius=2.0)
     assert np.allclose(np.linalg.norm(b.vert_xyz, axis=1), 2.0 * np.linalg.norm(a.vert_xyz, axis=1)) is not None
     assert np.array_equal(a.face_verts, b.face_verts)
+
+
+def test_header_is_plain_c99_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/lpmx.h compiles as C99 (-pedantic) and a C program links against liblpmx.so, builds a
+    mesh and refines it adaptively without any C++ or Python in between."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi_c.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <stdlib.h>
+#include "lpmx.h"
+int main(void) {
+  lpmx_mesh_t m = NULL;
+  int nv, ne, nf, nl, nel, nfv, divided = -1, outcome = -1, nmaxv, nmaxe, nmaxf;
+  const void* p; long n; int kind;
+  if (lpmx_mesh_create(LPMX_SEED_QUAD_RECT, 2, 3.0, &m) != LPMX_OK) return 1;
+  if (lpmx_mesh_max_allocations(LPMX_SEED_QUAD_RECT, 3, &nmaxv, &nmaxe, &nmaxf) != LPMX_OK) return 2;
+  lpmx_mesh_sizes(m, &nv, &ne, &nf, &nl, &nel, &nfv);
+  unsigned char* flags = (unsigned char*)calloc((size_t)nf, 1);
+  flags[nf - 1] = 1;
+  if (lpmx_mesh_divide_flagged_faces(m, flags, nf, nmaxf, 2 + 1, &divided, &outcome) != LPMX_OK) return 3;
+  lpmx_mesh_sizes(m, &nv, &ne, &nf, &nl, &nel, &nfv);
+  if (lpmx_mesh_array(m, LPMX_MESH_FACE_AREA, &p, &n, &kind) != LPMX_OK) return 4;
+  double area = 0; for (long i = 0; i < n; ++i) area += ((const double*)p)[i];
+  printf("%d %d %d %d %ld %d %.1f %s\n", divided, outcome, nf, nl, n, kind, area, lpmx_error_name(LPMX_ERR_NO_DEVICE));
+  free(flags);
+  return lpmx_mesh_destroy(m);
+}
+""")
+    exe = tmp_path / "abi_c"
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I" + os.path.join(root, "include"), str(src), "-o", str(exe),
+                    "-L" + os.path.join(root, "lpm_b200"), "-llpmx", "-Wl,-rpath," + os.path.join(root, "lpm_b200")], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out == ["1", "0", "88", "67", "88", "1", "36.0", "LPMX_ERR_NO_DEVICE"]
