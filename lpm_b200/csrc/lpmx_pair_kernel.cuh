@@ -4,6 +4,7 @@
 #ifndef LPMX_PAIR_KERNEL_CUH
 #define LPMX_PAIR_KERNEL_CUH
 
+#include "lpmx_fast_log.h"
 #include "lpmx_internal.h"
 
 namespace lpmx {
@@ -50,37 +51,24 @@ __device__ __forceinline__ double rcp_seed(double d) {
   return r;
 }
 // ------------------------------------------------------------------------------------------------
-// log(d) for the stream-function kinds.  d = kappa - x.y is a positive normal double (0 < d <= ~2), so the
-// general-purpose libdevice log (special cases, denormals, ~45 FP64-pipe instructions) is replaced by a
-// table-driven one: d = 2^k m, m in [1,2); c_i ~ 1/m from the top 7 mantissa bits, t = m c_i - 1 (one FMA,
-// |t| <= 2^-8), log d = k ln2 - log c_i + log1p(t), log1p by a degree-7 Taylor polynomial (|t|^8/8 < 2^-67).
-// 11 FP64-pipe instructions; absolute error < 3e-16 on (0, 4), checked in tests/test_gpu_parity_bve.py;
-// non-finite for d <= 0 like std::log.
-// The 2 KB table {c_i, -log c_i} sits in shared memory behind the source ring (divergent LDS.128).
+// log(d) for the stream-function kinds: lpmx_fast_log.h (two shared-memory tables behind the source ring, 8 FP64-pipe
+// instructions).  The mantissa table {c_i, -log c_i} comes from global memory, the exponent table is built per CTA.
 // ------------------------------------------------------------------------------------------------
-__device__ const double2 kLogTable[128] = {
+__device__ const double2 kLogTable[kLogMEntries] = {
 #include "log_table.inc"
 };
 
 __host__ __device__ constexpr bool kind_has_log(int k) { return k == kVelPsi || k == kPsi || k == kPlaneVelPsi || k == kPlaneSwe; }
 
-__device__ __forceinline__ double fast_log(double d, const double2* __restrict__ tbl) {
-  const int hi = __double2hiint(d);
-  const int k = (hi >> 20) - 1023;
-  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(d));
-  const double2 cl = tbl[(hi >> 13) & 127];
-  const double t = fma(m, cl.x, -1.0);
-  double q = fma(t, 1.0 / 7.0, -1.0 / 6.0);
-  q = fma(q, t, 0.2);
-  q = fma(q, t, -0.25);
-  q = fma(q, t, 1.0 / 3.0);
-  q = fma(q, t, -0.5);
-  const double l1p = fma(q, t * t, t);
-  // d <= 0 (a target sitting exactly on a source, e.g. a divided icosahedral panel on its child at eps = 0):
-  // the reference's std::log returns -inf / NaN there; stay non-finite (integer compare + select, off the FP64 pipe)
-  const double kd = hi > 0 ? (double)k : __longlong_as_double(0x7ff8000000000000LL);
-  return fma(kd, 0.693147180559945309417232121458, cl.y) + l1p;
+// the two tables of one CTA: mtab (16-byte aligned) then ktab
+struct LogTables {
+  const double2* m;
+  const double* k;
+};
+__host__ __device__ constexpr size_t log_tables_bytes() {
+  return kLogMEntries * sizeof(double2) + ((kLogKEntries * sizeof(double) + 15) / 16) * 16;
 }
+__device__ __forceinline__ double fast_log(double d, const LogTables& t) { return fast_log(d, t.m, t.k); }
 
 // exp(-x) for x >= 0 (the PSE kernel, lpm_pse.hpp:66-73): k = rint(-x log2 e) by the magic-number add, r = -x - k ln2
 // in two FMAs (hi/lo split of ln2), |r| <= ln2/2, degree-12 Taylor polynomial (|r|^13/13! < 2e-16), scale by 2^k
@@ -128,7 +116,7 @@ struct SumArgs {
 // dynamic shared memory of one CTA: source ring + full/empty barriers (+ the log table)
 __host__ __device__ constexpr size_t pair_smem_bytes(int kind) {
   return (size_t)kStages * kChunk * kind_rec(kind) * sizeof(double) + 2 * kStages * sizeof(uint64_t) +
-         (kind_has_log(kind) ? 128 * sizeof(double2) : 0);
+         (kind_has_log(kind) ? log_tables_bytes() : 0);
 }
 
 __host__ __device__ __forceinline__ int cta_of_item(long item, int grid, long n_items) {
@@ -146,7 +134,7 @@ template <bool CHECK>
 struct Pair<kVel, CHECK> {
   static constexpr int NLOAD = 6;  // doubles of the record this kind reads
   __device__ __forceinline__ static void apply(const double* x, const double* /*kx*/, double kappa, double /*aux*/, const double* s,
-                                               int j, int self, double* acc, const double2* /*tbl*/) {
+                                               int j, int self, double* acc, const LogTables& /*tbl*/) {
     const double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
     const double r0 = rcp_seed(d);
     const double e = fma(-d, r0, 1.0);
@@ -163,7 +151,7 @@ template <bool CHECK>
 struct Pair<kVelPsi, CHECK> {
   static constexpr int NLOAD = 8;
   __device__ __forceinline__ static void apply(const double* x, const double*, double kappa, double, const double* s, int j,
-                                               int self, double* acc, const double2* tbl) {
+                                               int self, double* acc, const LogTables& tbl) {
     double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
     double gam = s[6];
     if (CHECK) {
@@ -187,7 +175,7 @@ template <bool CHECK>
 struct Pair<kPsi, CHECK> {
   static constexpr int NLOAD = 8;
   __device__ __forceinline__ static void apply(const double* x, const double*, double kappa, double, const double* s, int j,
-                                               int self, double* acc, const double2* tbl) {
+                                               int self, double* acc, const LogTables& tbl) {
     double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
     double gam = s[6];
     if (CHECK) {
@@ -207,7 +195,7 @@ template <bool CHECK>
 struct Pair<kSwe, CHECK> {
   static constexpr int NLOAD = 6;
   __device__ __forceinline__ static void apply(const double* x, const double* kx, double kappa, double, const double* s,
-                                               int j, int self, double* acc, const double2* /*tbl*/) {
+                                               int j, int self, double* acc, const LogTables& /*tbl*/) {
     double d = fma(-x[0], s[0], fma(-x[1], s[1], fma(-x[2], s[2], kappa)));
     double gz = s[3], gs = s[4];
     if (CHECK) {
@@ -262,7 +250,7 @@ template <bool CHECK>
 struct Pair<kPlaneVelPsi, CHECK> {
   static constexpr int NLOAD = 4;
   __device__ __forceinline__ static void apply(const double* x, const double*, double kappa, double, const double* s,
-                                               int j, int self, double* acc, const double2* tbl) {
+                                               int j, int self, double* acc, const LogTables& tbl) {
     const double dx = x[0] - s[0], dy = x[1] - s[1];
     double a = fma(dx, dx, fma(dy, dy, kappa));
     double g = s[2];
@@ -295,7 +283,7 @@ template <bool CHECK>
 struct Pair<kPlaneSwe, CHECK> {
   static constexpr int NLOAD = 6;
   __device__ __forceinline__ static void apply(const double* x, const double*, double kappa, double inv_pe2,
-                                               const double* s, int j, int self, double* acc, const double2* tbl) {
+                                               const double* s, int j, int self, double* acc, const LogTables& tbl) {
     const double dx = x[0] - s[0], dy = x[1] - s[1];
     const double a2 = dx * dx, c2 = dy * dy, b2 = dx * dy;
     const double rsq = a2 + c2;
@@ -340,7 +328,7 @@ struct Pair<kPlaneSwe, CHECK> {
 template <int KIND, int T, int UNROLL, bool CHECK>
 __device__ __forceinline__ void chunk_loop(const double (*x)[3], const double (*kx)[3], double kappa, double aux,
                                            const double* __restrict__ sp, int j0, const int* self,
-                                           double (*acc)[kind_nacc(KIND)], const double2* tbl) {
+                                           double (*acc)[kind_nacc(KIND)], const LogTables& tbl) {
   constexpr int REC = kind_rec(KIND);
   static_assert(kChunk % UNROLL == 0, "source-loop unroll must divide the chunk");
 #pragma unroll 1
@@ -388,9 +376,14 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) pair_sum_kernel(const Sum
   double* stage = reinterpret_cast<double*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kStageBytes);
   uint64_t* empty = full + kStages;
-  double2* tbl = reinterpret_cast<double2*>(empty + kStages);  // 16-byte aligned: 2 * kStages * 8 bytes after the ring
-  if (kind_has_log(KIND))
-    for (int i = threadIdx.x; i < 128; i += C::THREADS) tbl[i] = kLogTable[i];
+  // log tables, 16-byte aligned: 2 * kStages * 8 bytes after the ring
+  double2* mtab = reinterpret_cast<double2*>(empty + kStages);
+  double* ktab = reinterpret_cast<double*>(mtab + kLogMEntries);
+  const LogTables tbl{mtab, ktab};
+  if (kind_has_log(KIND)) {
+    for (int i = threadIdx.x; i < kLogMEntries; i += C::THREADS) mtab[i] = kLogTable[i];
+    for (int i = threadIdx.x; i < kLogKEntries; i += C::THREADS) ktab[i] = fast_log_ktab_entry(i);
+  }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
