@@ -51,11 +51,17 @@ __device__ __forceinline__ double rcp_seed(double d) {
   return r;
 }
 // ------------------------------------------------------------------------------------------------
-// log(d) for the stream-function kinds: lpmx_fast_log.h (two shared-memory tables behind the source ring, 8 FP64-pipe
-// instructions).  The mantissa table {c_i, -log c_i} comes from global memory, the exponent table is built per CTA.
+// log(d) for the stream-function kinds: lpmx_fast_log.h (a 256-entry shared-memory table behind the source ring and a
+// degree-5 polynomial, 9 FP64-pipe instructions).  The table {c_i, -log c_i} is copied from global memory by every CTA.
 // ------------------------------------------------------------------------------------------------
 __device__ const double2 kLogTable[kLogMEntries] = {
-#include "log_table.inc"
+#if LPMX_LOG_MBITS == 10
+#include "log_table_10.inc"
+#elif LPMX_LOG_MBITS == 8
+#include "log_table_8.inc"
+#else
+#include "log_table_7.inc"
+#endif
 };
 
 __host__ __device__ constexpr bool kind_has_log(int k) { return k == kVelPsi || k == kPsi || k == kPlaneVelPsi || k == kPlaneSwe; }

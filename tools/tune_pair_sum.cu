@@ -302,6 +302,26 @@ int main(int argc, char** argv) {
 
 #define RUNK(K, T, NW, MINB, UNR) run<PairCfg<K, T, NW, MINB, UNR>>(#K " T" #T " NW" #NW " B" #MINB " U" #UNR)
 #define RUN(T, NW, MINB, UNR) run<PairCfg<kVel, T, NW, MINB, UNR>>("vel T" #T " NW" #NW " B" #MINB " U" #UNR)
+  if (argc > 5) {  // stream-function kinds only: more warps per SM against the two divergent table lookups per pair
+    RUNK(kVelPsi, 4, 8, 1, 2);
+    RUNK(kVelPsi, 4, 12, 1, 2);
+    RUNK(kVelPsi, 4, 16, 1, 2);
+    RUNK(kVelPsi, 3, 12, 1, 2);
+    RUNK(kVelPsi, 3, 16, 1, 2);
+    RUNK(kVelPsi, 2, 16, 1, 2);
+    RUNK(kVelPsi, 2, 24, 1, 2);
+    RUNK(kVelPsi, 2, 8, 2, 2);
+    RUNK(kVelPsi, 2, 12, 2, 2);
+    RUNK(kVelPsi, 2, 8, 3, 2);
+    RUNK(kVelPsi, 4, 8, 1, 4);
+    RUNK(kPsi, 8, 8, 1, 2);
+    RUNK(kPsi, 6, 12, 1, 2);
+    RUNK(kPsi, 4, 16, 1, 2);
+    RUNK(kPsi, 4, 24, 1, 2);
+    RUNK(kPsi, 4, 12, 2, 2);
+    RUNK(kPsi, 2, 16, 2, 2);
+    return 0;
+  }
   if (argc > 3) goto probes;
   RUN(4, 8, 2, 2);
   RUN(4, 8, 2, 1);
