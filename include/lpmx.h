@@ -260,7 +260,8 @@ int lpmx_bve_solver_interactions_per_eval(lpmx_bve_solver_t s, double* local, do
  * Omega is CoriolisSphere::Omega (src/lpm_coriolis.hpp:154-195).  On entry the velocities must
  * hold the current state's velocity (Incompressible2D::init_direct_sums,
  * src/lpm_incompressible2d_impl.hpp:235-254); on exit velocity and stream function are those
- * of the new state. */
+ * of the new state.  With n_steps > 1 the stream function is evaluated for the last step only: the reference overwrites it
+ * at every step, so the intermediate values are never observable from a multi-step call. */
 int lpmx_ic2d_rk2_step(lpmx_handle_t h, double dt, double Omega, double eps, int n_passive,
                        double* passive_xyz, double* passive_vort, double* passive_vel,
                        double* passive_psi, int n_active, double* active_xyz, double* active_vort,
