@@ -27,9 +27,11 @@ enum PairKind : int {
   kSwe = 3,     // Mz, Ms, G[9]                                   (spherical SWE 12-tuple)
   kPlaneVelPsi = 4,  // u0, u1, sum G log a                       (planar IC2D velocity + stream function)
   kPlaneSwe = 5,     // u0, u1, du[4], lap, sum Gz log a, sum Gs log a   (planar SWE 9-tuple with the PSE Laplacian)
+  kPlaneSweNoPot = 6,  // u0, u1, du[4], lap: the same without the two potentials (inner SWERK4 evaluations, where the
+                       // reference computes psi and phi only to overwrite them before anyone can read them)
 };
 constexpr int kind_nacc(int k) {
-  return k == kVel ? 3 : k == kVelPsi ? 4 : k == kPsi ? 1 : k == kSwe ? 15 : k == kPlaneVelPsi ? 3 : 9;
+  return k == kVel ? 3 : k == kVelPsi ? 4 : k == kPsi ? 1 : k == kSwe ? 15 : k == kPlaneVelPsi ? 3 : k == kPlaneSweNoPot ? 7 : 9;
 }
 // doubles per packed source record:
 //   BVE / IC2D kinds  {y0, y1, y2, G*y0, G*y1, G*y2, G, 0}   (G = -zeta*A/(4 pi); 64 bytes)
@@ -39,8 +41,10 @@ constexpr int kind_nacc(int k) {
 constexpr int kBveRec = 8;
 constexpr int kPlaneIc2dRec = 4;
 constexpr int kPlaneSweRec = 6;
-constexpr int kind_rec(int k) { return k == kSwe ? 6 : k == kPlaneVelPsi ? kPlaneIc2dRec : k == kPlaneSwe ? kPlaneSweRec : kBveRec; }
-constexpr bool kind_is_plane(int k) { return k == kPlaneVelPsi || k == kPlaneSwe; }
+constexpr int kind_rec(int k) {
+  return k == kSwe ? 6 : k == kPlaneVelPsi ? kPlaneIc2dRec : (k == kPlaneSwe || k == kPlaneSweNoPot) ? kPlaneSweRec : kBveRec;
+}
+constexpr bool kind_is_plane(int k) { return k == kPlaneVelPsi || k == kPlaneSwe || k == kPlaneSweNoPot; }
 
 // strided accessor for Real*[3] views: element (i,k) at p[i*si + k*sk]
 struct Vec3View {

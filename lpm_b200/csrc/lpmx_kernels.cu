@@ -74,6 +74,7 @@ static const Shape kShapes[] = {
     LPMX_SHAPE(kSwe, 2, 8, 1, 2),     LPMX_SHAPE(kSwe, 1, 8, 1, 2),
     LPMX_SHAPE(kPlaneVelPsi, 4, 8, 1, 2), LPMX_SHAPE(kPlaneVelPsi, 2, 8, 2, 2), LPMX_SHAPE(kPlaneVelPsi, 1, 8, 2, 2),
     LPMX_SHAPE(kPlaneSwe, 2, 8, 1, 2),    LPMX_SHAPE(kPlaneSwe, 1, 8, 2, 2),
+    LPMX_SHAPE(kPlaneSweNoPot, 2, 8, 1, 2), LPMX_SHAPE(kPlaneSweNoPot, 1, 8, 2, 2),
 };
 constexpr int kNumShapes = sizeof(kShapes) / sizeof(kShapes[0]);
 

@@ -285,49 +285,67 @@ struct Pair<kPlaneVelPsi, CHECK> {
 //   lap    = (s_j - s_i) Ap (40 (1 - q) + 10 q^2 - 2 q^3 / 3) exp(-q),  q = |x-y|^2 / pse_eps^2  (lpm_pse.hpp:66-73)
 //   psi, phi accumulate G log a; the finalize kernel applies the factor -1/2.
 // acc = {u0, u1, du1dx1, du1dx2, du2dx1, du2dx2, lap, sum Gz log a, sum Gs log a}.
+// POT = false drops the two potentials (kPlaneSweNoPot: 7 accumulators, no log).
+template <bool CHECK, bool POT>
+__device__ __forceinline__ void plane_swe_pair(const double* x, double kappa, double inv_pe2, const double* s, int j, int self,
+                                               double* acc, const LogTables& tbl) {
+  const double dx = x[0] - s[0], dy = x[1] - s[1];
+  const double a2 = dx * dx, c2 = dy * dy, b2 = dx * dy;
+  const double rsq = a2 + c2;
+  double a = rsq + kappa;
+  double gz = s[2], gs = s[3], ap = s[5];
+  if (CHECK) {
+    const bool me = (j == self);
+    a = me ? 1.0 : a;
+    gz = me ? 0.0 : gz;
+    gs = me ? 0.0 : gs;
+    ap = me ? 0.0 : ap;
+  }
+  const double r0 = rcp_seed(a);
+  const double e = fma(-a, r0, 1.0);
+  const double pp = fma(e, e, e);
+  const double r = fma(r0, pp, r0);
+  const double wz = gz * r, ws = gs * r;
+  acc[0] = fma(-dy, wz, acc[0]);
+  acc[0] = fma(dx, ws, acc[0]);
+  acc[1] = fma(dx, wz, acc[1]);
+  acc[1] = fma(dy, ws, acc[1]);
+  const double r2 = r + r;
+  const double pA = fma(-r2, a2, 1.0), pC = fma(-r2, c2, 1.0), pB = r2 * b2;
+  acc[2] = fma(wz, pB, acc[2]);
+  acc[2] = fma(ws, pA, acc[2]);
+  acc[3] = fma(-wz, pC, acc[3]);
+  acc[3] = fma(-ws, pB, acc[3]);
+  acc[4] = fma(wz, pA, acc[4]);
+  acc[4] = fma(-ws, pB, acc[4]);
+  acc[5] = fma(-wz, pB, acc[5]);
+  acc[5] = fma(ws, pC, acc[5]);
+  if (POT) {
+    const double lg = fast_log(a, tbl);
+    acc[7] = fma(gz, lg, acc[7]);
+    acc[8] = fma(gs, lg, acc[8]);
+  }
+  const double q = rsq * inv_pe2;
+  const double pre = fma(q, fma(q, fma(q, -2.0 / 3.0, 10.0), -40.0), 40.0);
+  const double t = (s[4] - x[2]) * ap;
+  acc[6] = fma(t * pre, fast_exp_neg(q), acc[6]);
+}
+
 template <bool CHECK>
 struct Pair<kPlaneSwe, CHECK> {
   static constexpr int NLOAD = 6;
   __device__ __forceinline__ static void apply(const double* x, const double*, double kappa, double inv_pe2,
                                                const double* s, int j, int self, double* acc, const LogTables& tbl) {
-    const double dx = x[0] - s[0], dy = x[1] - s[1];
-    const double a2 = dx * dx, c2 = dy * dy, b2 = dx * dy;
-    const double rsq = a2 + c2;
-    double a = rsq + kappa;
-    double gz = s[2], gs = s[3], ap = s[5];
-    if (CHECK) {
-      const bool me = (j == self);
-      a = me ? 1.0 : a;
-      gz = me ? 0.0 : gz;
-      gs = me ? 0.0 : gs;
-      ap = me ? 0.0 : ap;
-    }
-    const double r0 = rcp_seed(a);
-    const double e = fma(-a, r0, 1.0);
-    const double pp = fma(e, e, e);
-    const double r = fma(r0, pp, r0);
-    const double wz = gz * r, ws = gs * r;
-    acc[0] = fma(-dy, wz, acc[0]);
-    acc[0] = fma(dx, ws, acc[0]);
-    acc[1] = fma(dx, wz, acc[1]);
-    acc[1] = fma(dy, ws, acc[1]);
-    const double r2 = r + r;
-    const double pA = fma(-r2, a2, 1.0), pC = fma(-r2, c2, 1.0), pB = r2 * b2;
-    acc[2] = fma(wz, pB, acc[2]);
-    acc[2] = fma(ws, pA, acc[2]);
-    acc[3] = fma(-wz, pC, acc[3]);
-    acc[3] = fma(-ws, pB, acc[3]);
-    acc[4] = fma(wz, pA, acc[4]);
-    acc[4] = fma(-ws, pB, acc[4]);
-    acc[5] = fma(-wz, pB, acc[5]);
-    acc[5] = fma(ws, pC, acc[5]);
-    const double lg = fast_log(a, tbl);
-    acc[7] = fma(gz, lg, acc[7]);
-    acc[8] = fma(gs, lg, acc[8]);
-    const double q = rsq * inv_pe2;
-    const double pre = fma(q, fma(q, fma(q, -2.0 / 3.0, 10.0), -40.0), 40.0);
-    const double t = (s[4] - x[2]) * ap;
-    acc[6] = fma(t * pre, fast_exp_neg(q), acc[6]);
+    plane_swe_pair<CHECK, true>(x, kappa, inv_pe2, s, j, self, acc, tbl);
+  }
+};
+
+template <bool CHECK>
+struct Pair<kPlaneSweNoPot, CHECK> {
+  static constexpr int NLOAD = 6;
+  __device__ __forceinline__ static void apply(const double* x, const double*, double kappa, double inv_pe2,
+                                               const double* s, int j, int self, double* acc, const LogTables& tbl) {
+    plane_swe_pair<CHECK, false>(x, kappa, inv_pe2, s, j, self, acc, tbl);
   }
 };
 

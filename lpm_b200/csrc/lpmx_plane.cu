@@ -65,6 +65,7 @@ struct PlaneState {
 struct PlaneArgs {
   PartView pv;
   int t0, n_local, nv, stage, mode, topo, do_velocity;
+  int with_pot;  // the evaluation carried the two potentials (kPlaneSwe) or not (kPlaneSweNoPot)
   long nt;
   double dt, f0, beta, g, ap_scale;
   double *X, *Xw, *U, *Z, *S, *T, *Zw, *Sw, *Tw, *K0, *K1, *K2;
@@ -131,17 +132,19 @@ __device__ __forceinline__ void plane_swe_tend(const PlaneArgs& a, bool is_face,
 struct PlaneSweSums {
   double u0, u1, g11, g12, g21, g22, dd, lap, psi, phi;
 };
-// PlanarSWEVertexSums::operator() unpacking (:693-715) on the accumulators of Pair<kPlaneSwe>
+// PlanarSWEVertexSums::operator() unpacking (:693-715) on the accumulators of Pair<kPlaneSwe> (POT) / Pair<kPlaneSweNoPot>
+template <bool POT>
 __device__ __forceinline__ PlaneSweSums plane_swe_finalize(const double* acc) {
   PlaneSweSums r;
   r.u0 = acc[0], r.u1 = acc[1];
   r.g11 = acc[2], r.g12 = acc[3], r.g21 = acc[4], r.g22 = acc[5];
   r.dd = r.g11 * r.g11 + 2 * r.g12 * r.g21 + r.g22 * r.g22;
   r.lap = acc[6];
-  r.psi = -0.5 * acc[7];
-  r.phi = -0.5 * acc[8];
+  r.psi = POT ? -0.5 * acc[7] : 0.0;
+  r.phi = POT ? -0.5 * acc[8] : 0.0;
   return r;
 }
+template <bool POT>
 __device__ __forceinline__ void plane_swe_store(const PlaneArgs& a, long g, const PlaneSweSums& r, bool with_vel) {
   if (with_vel) {
     a.U[g] = r.u0;
@@ -150,13 +153,19 @@ __device__ __forceinline__ void plane_swe_store(const PlaneArgs& a, long g, cons
   a.DD[g] = r.dd;
   a.G11[g] = r.g11, a.G12[g] = r.g12, a.G21[g] = r.g21, a.G22[g] = r.g22;
   a.LAPS[g] = r.lap;
-  a.PSI[g] = r.psi;
-  a.PHI[g] = r.phi;
+  if (POT) {  // without the potentials the stored ones stay: a later evaluation of the same call overwrites them
+    a.PSI[g] = r.psi;
+    a.PHI[g] = r.phi;
+  }
 }
 
 // SWERK4 stages.  stage 0: k1 from the current state, work state 2.  stage 1/2: sums at the work state -> k2/k3 ->
 // work state 3/4.  stage 3: sums at work state 4 -> k4 -> final update, new surfaces, new source records.
 // stage 4: sums of the new state (also SWE::init_direct_sums).
+// The stream function and the velocity potential are outputs of stage 4 only (the reference's stages 1-3 compute them into
+// views that stage 4 overwrites, src/lpm_swe_rk4_impl.hpp:268-275,319-326,371-378,428-441), and inside a multi-step call only
+// the last step's are observable: every other evaluation runs the 7-accumulator kernel without the log (POT = false).
+template <bool POT>
 __global__ void plane_swe_rk4_stage_kernel(const PlaneArgs a) {
   const long li = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (li >= a.n_local) return;
@@ -179,11 +188,12 @@ __global__ void plane_swe_rk4_stage_kernel(const PlaneArgs a) {
     plane_pack(a, g, xw0, xw1, zw, sw, tw, surf);
     return;
   }
-  double acc[9];
-  reduce_slots<9>(a.pv, li, acc);
-  const PlaneSweSums r = plane_swe_finalize(acc);
+  constexpr int NACC = POT ? 9 : 7;
+  double acc[NACC];
+  reduce_slots<NACC>(a.pv, li, acc);
+  const PlaneSweSums r = plane_swe_finalize<POT>(acc);
   if (a.stage == 4) {  // (:416-441), SWE::init_direct_sums
-    plane_swe_store(a, g, r, a.do_velocity != 0);
+    plane_swe_store<POT>(a, g, r, a.do_velocity != 0);
     return;
   }
   const double xw1 = a.Xw[nt + g];
@@ -359,6 +369,7 @@ static PlaneArgs plane_args(PlaneState* s, const SumPlan* plan, const double* pa
   a.pv = plan ? part_view(*plan, partials) : PartView{nullptr, 0, 0, 0, 1, 1};
   a.t0 = t_lo, a.n_local = t_hi - t_lo, a.nv = s->nv, a.stage = stage, a.mode = s->mode, a.topo = s->topo;
   a.do_velocity = do_velocity;
+  a.with_pot = 1;
   a.nt = s->nt;
   a.dt = dt, a.f0 = f0, a.beta = beta, a.g = g;
   a.ap_scale = 1.0 / (LPMX_PI * s->pse_eps * s->pse_eps);
@@ -603,8 +614,10 @@ static int plane_launch_stage(PlaneState* s, const PlaneArgs& a) {
   lpmx_handle_t h = s->h;
   if (a.n_local <= 0) return LPMX_OK;
   const int threads = 128, blocks = (a.n_local + threads - 1) / threads;
-  if (s->mode == kModeSwe)
-    plane_swe_rk4_stage_kernel<<<blocks, threads, 0, h->stream>>>(a);
+  if (s->mode == kModeSwe && a.with_pot)
+    plane_swe_rk4_stage_kernel<true><<<blocks, threads, 0, h->stream>>>(a);
+  else if (s->mode == kModeSwe)
+    plane_swe_rk4_stage_kernel<false><<<blocks, threads, 0, h->stream>>>(a);
   else
     plane_ic2d_rk2_stage_kernel<<<blocks, threads, 0, h->stream>>>(a);
   ++h->launches;
@@ -613,9 +626,9 @@ static int plane_launch_stage(PlaneState* s, const PlaneArgs& a) {
 
 // pair sums of targets [lo, hi) (global indices of the concatenated list) at the coordinates in `tgt_base`
 // (3 rows of nt) against the current source records
-static int plane_pair_sum(PlaneState* s, double* tgt_base, int lo, int hi, SumPlan* plan, double** partials) {
+static int plane_pair_sum(PlaneState* s, double* tgt_base, int lo, int hi, int kind, SumPlan* plan, double** partials) {
   lpmx_handle_t h = s->h;
-  LPMX_TRY(make_plan(h, s->kind(), hi - lo, s->n_leaf, plan));
+  LPMX_TRY(make_plan(h, kind, hi - lo, s->n_leaf, plan));
   void* part = nullptr;
   LPMX_TRY(dev_buffer(h, "plane_partials", plan_partials_bytes(*plan) + 256, &part));
   *partials = (double*)part;
@@ -645,7 +658,7 @@ static int plane_eval_state(PlaneState* s, int lo, int hi, int do_velocity) {
   if (hi <= lo) return LPMX_OK;
   SumPlan plan;
   double* part = nullptr;
-  LPMX_TRY(plane_pair_sum(s, s->X, lo, hi, &plan, &part));
+  LPMX_TRY(plane_pair_sum(s, s->X, lo, hi, s->kind(), &plan, &part));
   const int final_stage = s->mode == kModeSwe ? 4 : 2;
   return plane_launch_stage(s, plane_args(s, &plan, part, lo, hi, final_stage, 0, 0, 0, 0, nullptr, do_velocity));
 }
@@ -666,9 +679,12 @@ static int plane_advance(PlaneState* s, double dt, double f0, double beta, doubl
       s->cur ^= 1;
       LPMX_TRY(plane_exchange_packed(s, s->packed[s->cur]));
       const bool last = e == n_eval;  // the last evaluation is at the new state
-      LPMX_TRY(plane_pair_sum(s, last ? s->X : s->Xw, s->t0, s->t1, &plan, &part));
-      LPMX_TRY(plane_launch_stage(s, plane_args(s, &plan, part, s->t0, s->t1, e, dt, f0, beta, g,
-                                                last ? nullptr : s->packed[s->cur ^ 1], 1)));
+      // SWE: psi and phi are wanted from the new-state evaluation of the call's last step only
+      const bool with_pot = s->mode != kModeSwe || (last && step + 1 == n_steps);
+      LPMX_TRY(plane_pair_sum(s, last ? s->X : s->Xw, s->t0, s->t1, with_pot ? s->kind() : kPlaneSweNoPot, &plan, &part));
+      PlaneArgs a = plane_args(s, &plan, part, s->t0, s->t1, e, dt, f0, beta, g, last ? nullptr : s->packed[s->cur ^ 1], 1);
+      a.with_pot = with_pot ? 1 : 0;
+      LPMX_TRY(plane_launch_stage(s, a));
     }
   }
   return LPMX_OK;
