@@ -62,9 +62,10 @@ def test_outcomes_cover_limit_and_no_space():
 def test_live_python_replay_of_divide_flagged_faces():
     from oracle import mesh_oracle
     rng = np.random.default_rng(7)
-    for seed in ("icos", "cubed"):
-        ref = mesh_oracle.TreeMesh(seed, 1)
-        m = PolyMesh2d(seed, 1, amr_buffer=3, amr_limit=3)
+    for seed in ("icos", "cubed", "quad_rect", "tri_hex"):
+        radius = 2.5 if seed in ("quad_rect", "tri_hex") else 1.0
+        ref = mesh_oracle.TreeMesh(seed, 1, radius=radius)
+        m = PolyMesh2d(seed, 1, radius=radius, amr_buffer=3, amr_limit=3)
         for _ in range(3):
             flags = ((rng.random(m.n_faces) < 0.3) & (m.face_mask == 0)).astype(np.uint8)
             assert ref.divide_flagged_faces(flags, m.nmaxfaces, 3) == m.divide_flagged_faces(flags)

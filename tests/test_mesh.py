@@ -45,7 +45,7 @@ def test_embedded_seed_tables_equal_reference_dat_files():
 @pytest.mark.skipif(not os.path.isdir("/root/reference/mesh_seeds"), reason="reference not mounted")
 def test_live_python_restatement_from_reference_seed_files():
     from oracle import mesh_oracle
-    for seed, depth in (("icos", 2), ("cubed", 3)):
+    for seed, depth in (("icos", 2), ("cubed", 3), ("quad_rect", 3), ("tri_hex", 2)):
         ref = mesh_oracle.TreeMesh(seed, depth).arrays()
         m = PolyMesh2d(seed, depth)
         for k, v in ref.items():
