@@ -352,7 +352,7 @@ def main():
                        "nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2)",
         "flops_per_interaction": flops_per, "launches": n_k, "avg_launch_ms": (k_ms / n_k) if n_k else None,
         "kernel_share_of_step": (k_ms / (sum(step_ms))) if step_ms else None,
-        "fp64_pipe_instr_per_interaction": {"bve_rk4": 9, "ic2d_rk2": 15.5, "swe_rk2": 53}[args.stepper],
+        "fp64_pipe_instr_per_interaction": {"bve_rk4": 9, "ic2d_rk2": 13.5, "swe_rk2": 53}[args.stepper],  # ic2d: (9 + 18) / 2
         "traffic": None,
     }
     prof = os.path.join(ROOT, "profiles", "r1_pair_sum_dram.json")
