@@ -389,6 +389,11 @@ class PlaneSWE {
     }
   }
 
+  void allocate_scalar_tracer(const std::string& name) {
+    tracer_passive.emplace(name, ScalarField<VertexField>(name, mesh.params.nmaxverts));
+    tracer_active.emplace(name, ScalarField<FaceField>(name, mesh.params.nmaxfaces));
+  }
+
   /// PlanarSWEVertexSums / PlanarSWEFaceSums at the current state (src/lpm_swe_impl.hpp:406-426)
   void init_direct_sums(const bool do_velocity = true) {
     lpmx_handle_t h = Engine::get();

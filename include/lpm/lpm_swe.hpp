@@ -109,8 +109,8 @@ class SWE {
   }
 
   void allocate_scalar_tracer(const std::string& name) {
-    tracer_passive.emplace(name, ScalarField<VertexField>(name, mesh.n_vertices_host()));
-    tracer_active.emplace(name, ScalarField<FaceField>(name, mesh.n_faces_host()));
+    tracer_passive.emplace(name, ScalarField<VertexField>(name, mesh.params.nmaxverts));
+    tracer_active.emplace(name, ScalarField<FaceField>(name, mesh.params.nmaxfaces));
   }
 
   /// SphereVertexSums / SphereFaceSums on the LAGRANGIAN coordinates (src/lpm_swe_impl.hpp:428-443, quirk C-iv)
