@@ -430,6 +430,10 @@ def main():
                "sample": f"{min(args.cpu_sample, nv)} vertex targets x all {nf} faces ({nleaf} leaf sources), one "
                          f"velocity evaluation, best of 2, {secs:.1f} s each"}
 
+    peer_on, peer_slabs = eng.comm_peer_exchange_enabled()
+    exchange = ("none (one GPU)" if world == 1 else
+                "one kernel storing each rank's records into the peers' slabs over NVLink (LPMX_PEER_EXCHANGE=1)"
+                if peer_on and peer_slabs else "grouped ncclBroadcast (default)")
     if rank == 0:
         line = {
             "metric": "fp64_pair_interactions_per_s", "value": value, "unit": "interactions/s", "n_gpus": world,
@@ -439,6 +443,7 @@ def main():
                        "evals_per_step": evals, "n_verts": nv, "n_faces": nf, "n_leaf_sources": nleaf,
                        "interactions_per_eval": i_eval, "dt": args.dt, "Omega": Omega,
                        "parallelism": f"targets sharded over {world} GPU(s), per-stage allgather of leaf source records",
+                       "exchange": exchange,
                        "l2": "flushed between timed steps (256 MiB write)",
                        **({"surface_laplacian": (f"device GMLS order {args.gmls_order}, both stages" if args.laplacian == "gmls"
                                                  else "frozen at the TC2 closed form")} if args.stepper == "swe_rk2" else {})},

@@ -264,6 +264,19 @@ class Engine:
         buf = ctypes.create_string_buffer(bytes(unique_id), 128)
         self._check(self._L.lpmx_comm_init(self._h, buf, rank, world), "lpmx_comm_init")
 
+    def comm_enable_peer_exchange(self, enable=True):
+        """Collective, after comm_init and before any solver exists: exchange the packed source records with one
+        kernel that stores into the peers' slabs over NVLink instead of the NCCL broadcasts (include/lpmx.h).
+        Raises LpmxError(LPMX_ERR_UNSUPPORTED) when the GPUs cannot map each other's memory."""
+        self._check(self._L.lpmx_comm_enable_peer_exchange(self._h, 1 if enable else 0), "lpmx_comm_enable_peer_exchange")
+
+    def comm_peer_exchange_enabled(self):
+        """(enabled, number of solver slabs currently mapped into the peers)."""
+        en, nr = ctypes.c_int(0), ctypes.c_int(0)
+        self._check(self._L.lpmx_comm_peer_exchange_enabled(self._h, ctypes.byref(en), ctypes.byref(nr)),
+                    "lpmx_comm_peer_exchange_enabled")
+        return bool(en.value), nr.value
+
     # ---- operator level -----------------------------------------------------------------
     @staticmethod
     def _vec_args(x, layout, ld):

@@ -2,6 +2,7 @@
 #include <dlfcn.h>
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "lpmx_internal.h"
@@ -99,6 +100,7 @@ int stage_out_end(lpmx_handle_t h, void* user, const void* dev, size_t bytes) {
 int comm_allgatherv(lpmx_handle_t h, double* base, const long* offsets) {
   if (h->world == 1) return LPMX_OK;
   if (!h->nccl_comm || !h->nccl_lib) return set_error(h, LPMX_ERR_COMM, "world > 1 but lpmx_comm_init was not called");
+  if (peer_can_exchange(h, base)) return peer_allgatherv(h, base, offsets);  // one kernel over NVLink peer memory
   typedef int (*group_t)(void);
   typedef int (*bcast_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
   static group_t gstart = nullptr, gend = nullptr;
@@ -182,6 +184,7 @@ int lpmx_destroy(lpmx_handle_t h) {
   if (h->cached_ic2d) lpmx_ic2d_solver_destroy(h->cached_ic2d);
   if (h->cached_swe) lpmx_swe_solver_destroy(h->cached_swe);
   if (h->cached_plane) lpmx_plane_swe_solver_destroy(h->cached_plane);
+  peer_teardown(h);  // before the NCCL communicator goes: closes the IPC mappings, then frees what was exported
   for (auto& kv : h->bufs)
     if (kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : h->pinned)
@@ -204,7 +207,7 @@ int lpmx_destroy(lpmx_handle_t h) {
 int lpmx_sync(lpmx_handle_t h) {
   if (!h) return LPMX_ERR_INVALID;
   LPMX_CUDA(h, cudaStreamSynchronize(h->stream));
-  return LPMX_OK;
+  return peer_check_error(h);
 }
 
 const char* lpmx_last_error_string(lpmx_handle_t h) { return h ? h->err.c_str() : "null handle"; }
@@ -302,6 +305,12 @@ int lpmx_comm_init(lpmx_handle_t h, const void* id128, int rank, int world) {
   h->nccl_comm = comm;
   h->rank = rank;
   h->world = world;
+  // LPMX_PEER_EXCHANGE=1 turns the peer-memory exchange on without a code change in the caller; when the GPUs
+  // cannot map each other's memory the NCCL exchange stays and the call still succeeds.
+  const char* e = getenv("LPMX_PEER_EXCHANGE");
+  if (e && atoi(e) != 0 && world > 1 && world <= kMaxPeers) {
+    if (peer_enable(h, 1) != LPMX_OK) fprintf(stderr, "lpmx: %s; keeping the NCCL exchange\n", h->err.c_str());
+  }
   return LPMX_OK;
 }
 

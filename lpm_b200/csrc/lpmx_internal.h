@@ -87,6 +87,25 @@ struct DevBuf {
   size_t cap = 0;
 };
 
+// ---- peer exchange (lpmx_peer.cu): slabs mapped into every rank of the box with CUDA IPC ----
+constexpr int kMaxPeers = 8;
+struct PeerRegion {
+  void* local = nullptr;  // base of this rank's allocation
+  size_t bytes = 0;
+  void* peer[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // rank q's allocation, mapped here
+};
+struct PeerState {
+  bool enabled = false;
+  unsigned long long epoch = 0;       // exchanges issued so far (identical on every rank)
+  unsigned long long timeout_ns = 0;  // deadline of every spin in the exchange kernel
+  unsigned long long* flags_local = nullptr;
+  unsigned long long* flags_peer[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int* host_err = nullptr;      // host-mapped: 1 + rank the kernel gave up waiting for, 0 = fine
+  int* host_err_dev = nullptr;  // device alias of host_err
+  std::vector<PeerRegion> regions;
+  std::vector<void*> graveyard;  // exported allocations whose release waits for lpmx_destroy
+};
+
 }  // namespace lpmx
 
 struct lpmx_handle_s {
@@ -99,6 +118,7 @@ struct lpmx_handle_s {
   int rank = 0, world = 1;
   void* nccl_comm = nullptr;  // ncclComm_t when lpmx_comm_init succeeded
   void* nccl_lib = nullptr;   // dlopen handle
+  lpmx::PeerState* peer = nullptr;  // lpmx_comm_enable_peer_exchange
   std::map<std::string, lpmx::DevBuf> bufs;  // named scratch buffers
   std::map<std::string, lpmx::DevBuf> pinned;  // named pinned host staging buffers
   // optional per-launch timing of the pair-sum kernel (lpmx_profile_enable)
@@ -163,6 +183,16 @@ int ic2d_totals_device(lpmx_handle_t h, int n, const double* zeta, Vec3View u, c
 // [offsets[r], offsets[r+1]) of `base`; after the call every rank holds all of them.
 // No-op for world == 1.  (lpmx_core.cu; NCCL broadcasts grouped into one launch.)
 int comm_allgatherv(lpmx_handle_t h, double* base, const long* offsets);
+
+// Solver slabs.  Without the peer exchange these are cudaMalloc / cudaFree; with it the slab is also mapped
+// into every rank (collective call) so that comm_allgatherv can store into the peers directly.  (lpmx_peer.cu)
+int slab_alloc(lpmx_handle_t h, void** out, size_t bytes);
+void slab_free(lpmx_handle_t h, void* p);
+int peer_enable(lpmx_handle_t h, int enable);
+bool peer_can_exchange(lpmx_handle_t h, const double* base);
+int peer_allgatherv(lpmx_handle_t h, double* base, const long* offsets);
+int peer_check_error(lpmx_handle_t h);
+void peer_teardown(lpmx_handle_t h);
 
 }  // namespace lpmx
 

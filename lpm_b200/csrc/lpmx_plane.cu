@@ -392,7 +392,7 @@ static int plane_alloc(PlaneState* s, lpmx_handle_t h, int mode, int nv, int nf,
   s->packed_doubles = (size_t)s->rec() * (size_t)(round_up_chunk(nf) + kChunk);
   const size_t dbl = 3 * nt + 3 * nt + 2 * nt + 6 * nt + 15 * nt + 11 * nt + 2 * s->packed_doubles + 64;
   const size_t bytes = dbl * sizeof(double) + sizeof(int) * (size_t)(nf + 1 + nt + 1) + (size_t)nf + 512;
-  LPMX_CUDA(h, cudaMalloc(&s->slab, bytes));
+  LPMX_TRY(slab_alloc(h, &s->slab, bytes));
   LPMX_CUDA(h, cudaMemsetAsync(s->slab, 0, bytes, h->stream));
   double* p = (double*)s->slab;
   s->X = p, p += 3 * nt;
@@ -716,7 +716,7 @@ static void plane_free(lpmx_plane_solver_s* s) {
   if (s->st.slab) {
     cudaSetDevice(s->st.h->device);
     cudaStreamSynchronize(s->st.h->stream);
-    cudaFree(s->st.slab);
+    slab_free(s->st.h, s->st.slab);
   }
   delete s;
 }

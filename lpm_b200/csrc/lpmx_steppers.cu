@@ -71,7 +71,7 @@ static int solver_alloc(SolverState* s, lpmx_handle_t h, int nv, int nf, int n_k
   // one slab: X U Xw (3nt each) Z Zw Psi (nt each) K (n_k * 4nt) area packed[2] | ints | mask
   size_t dbl = 9 * nt + 3 * nt + (size_t)n_k * 4 * nt + nf + 2 * kBveRec * (size_t)(s->n_src_pad + kChunk);
   size_t bytes = dbl * sizeof(double) + sizeof(int) * (size_t)(nf + 1 + nt + 1) + (size_t)nf + 64 + 256;
-  LPMX_CUDA(h, cudaMalloc(&s->slab, bytes));
+  LPMX_TRY(slab_alloc(h, &s->slab, bytes));
   LPMX_CUDA(h, cudaMemsetAsync(s->slab, 0, bytes, h->stream));  // Kokkos views start at zero
   double* p = (double*)s->slab;
   s->X = p, p += 3 * nt;
@@ -101,7 +101,7 @@ static void solver_free(SolverState* s) {
   if (s->slab) {
     cudaSetDevice(s->h->device);
     cudaStreamSynchronize(s->h->stream);
-    cudaFree(s->slab);
+    slab_free(s->h, s->slab);
     s->slab = nullptr;
   }
 }

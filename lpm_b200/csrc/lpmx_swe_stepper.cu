@@ -265,7 +265,7 @@ static int swe_alloc(SweState* s, lpmx_handle_t h, int nv, int nf, double eps) {
   const size_t pk = kSweRec * (size_t)(round_up_chunk(nf) + kChunk);
   const size_t dbl = 12 * nt + 15 * nt + 2 * pk + 32;
   const size_t bytes = dbl * sizeof(double) + sizeof(int) * (size_t)(nf + 1 + nt + 1) + (size_t)nf + 512;
-  LPMX_CUDA(h, cudaMalloc(&s->slab, bytes));
+  LPMX_TRY(slab_alloc(h, &s->slab, bytes));
   LPMX_CUDA(h, cudaMemsetAsync(s->slab, 0, bytes, h->stream));
   double* p = (double*)s->slab;
   s->X = p, p += 3 * nt;
@@ -516,7 +516,7 @@ int lpmx_swe_solver_destroy(lpmx_swe_solver_t s) {
   if (s->st.slab) {
     cudaSetDevice(s->st.h->device);
     cudaStreamSynchronize(s->st.h->stream);
-    cudaFree(s->st.slab);
+    slab_free(s->st.h, s->st.slab);
   }
   delete s;
   return LPMX_OK;
