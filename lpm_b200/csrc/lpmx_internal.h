@@ -102,6 +102,7 @@ struct PeerState {
   unsigned long long* flags_peer[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int* host_err = nullptr;      // host-mapped: 1 + rank the kernel gave up waiting for, 0 = fine
   int* host_err_dev = nullptr;  // device alias of host_err
+  int dead_peer = 0;            // sticky copy of *host_err: once a wait expired every later exchange fails fast
   std::vector<PeerRegion> regions;
   std::vector<void*> graveyard;  // exported allocations whose release waits for lpmx_destroy
 };

@@ -39,7 +39,8 @@ constexpr int kDone = kMaxPeers;                     // done[q]
 constexpr int kBye = 2 * kMaxPeers;                  // bye[q]  (teardown)
 constexpr int kTicket = 3 * kMaxPeers;               // CTA ticket counter of the running launch
 constexpr int kMagic = 3 * kMaxPeers + 1;            // mapping validation word
-constexpr size_t kFlagWords = (size_t)(3 * kMaxPeers + 2) * kFlagStride;
+constexpr int kFail = 3 * kMaxPeers + 2;             // set (and never cleared) when a wait of this rank expired
+constexpr size_t kFlagWords = (size_t)(3 * kMaxPeers + 3) * kFlagStride;
 constexpr size_t kMinIpcBytes = (size_t)2 << 20;     // allocations below this may share a block with others
 constexpr unsigned long long kMagicBase = 0x6c706d785f706565ull;  // "lpmx_pee"
 
@@ -95,7 +96,10 @@ __global__ void __launch_bounds__(256) peer_push_kernel(const PushArgs a) {
     const int p = (a.rank + 1 + (k + bid) % np) % a.world;
     if (tid == 0) {
       s_ok = wait_flag(a.flags_local + (kReady + p) * kFlagStride, a.epoch, deadline) ? 1 : 0;
-      if (!s_ok) *a.host_err = 1 + p;
+      if (!s_ok) {
+        *a.host_err = 1 + p;
+        a.flags_local[kFail * kFlagStride] = 1;
+      }
     }
     __syncthreads();
     const bool ok = s_ok != 0;
@@ -121,9 +125,15 @@ __global__ void __launch_bounds__(256) peer_push_kernel(const PushArgs a) {
   if (!s_last) return;
   if (tid == 0) a.flags_local[kTicket * kFlagStride] = 0;  // next launch on this stream starts from zero
   __threadfence_system();
+  // a rank that could not deliver says nothing, so that its peers run into their own deadline instead of
+  // computing on records that never arrived (the fail word was written before its CTA's ticket)
+  if (*(volatile unsigned long long*)(a.flags_local + kFail * kFlagStride) != 0) return;
   if (tid < a.world && tid != a.rank) {
     st_release_sys(a.flags_peer[tid] + (kDone + a.rank) * kFlagStride, a.epoch);
-    if (!wait_flag(a.flags_local + (kDone + tid) * kFlagStride, a.epoch, deadline)) *a.host_err = 1 + tid;
+    if (!wait_flag(a.flags_local + (kDone + tid) * kFlagStride, a.epoch, deadline)) {
+      *a.host_err = 1 + tid;
+      a.flags_local[kFail * kFlagStride] = 1;
+    }
   }
 }
 
@@ -228,10 +238,15 @@ const PeerRegion* find_region(const PeerState* ps, const void* p) {
 
 int peer_check_error(lpmx_handle_t h) {
   PeerState* ps = h->peer;
-  if (!ps || !ps->host_err || *ps->host_err == 0) return LPMX_OK;
-  const int who = *ps->host_err - 1;
-  *ps->host_err = 0;
-  return set_error(h, LPMX_ERR_COMM, "peer exchange timed out waiting for rank %d (epoch %llu)", who, ps->epoch);
+  if (!ps || !ps->host_err) return LPMX_OK;
+  if (*ps->host_err != 0) {
+    ps->dead_peer = *ps->host_err;
+    *ps->host_err = 0;
+  }
+  if (ps->dead_peer == 0) return LPMX_OK;
+  // fatal for this handle's exchanges: the ranks no longer agree on what has been delivered
+  return set_error(h, LPMX_ERR_COMM, "peer exchange timed out waiting for rank %d (at or before exchange %llu); destroy the handle",
+                   ps->dead_peer - 1, ps->epoch);
 }
 
 int slab_alloc(lpmx_handle_t h, void** out, size_t bytes) {
