@@ -28,19 +28,15 @@
 #include <cstring>
 
 #include "lpmx_internal.h"
+#include "lpmx_peer_protocol.h"
 
 namespace lpmx {
 
 namespace {
 
-constexpr int kFlagStride = 16;                      // 128 bytes between flags
-constexpr int kReady = 0;                            // ready[q] at (kReady + q) * kFlagStride
-constexpr int kDone = kMaxPeers;                     // done[q]
-constexpr int kBye = 2 * kMaxPeers;                  // bye[q]  (teardown)
-constexpr int kTicket = 3 * kMaxPeers;               // CTA ticket counter of the running launch
-constexpr int kMagic = 3 * kMaxPeers + 1;            // mapping validation word
-constexpr int kFail = 3 * kMaxPeers + 2;             // set (and never cleared) when a wait of this rank expired
-constexpr size_t kFlagWords = (size_t)(3 * kMaxPeers + 3) * kFlagStride;
+using namespace lpmx::peer;
+static_assert(kMaxRanks == kMaxPeers, "lpmx_internal.h and lpmx_peer_protocol.h disagree on the rank limit");
+constexpr size_t kFlagWords = (size_t)kFlagSlots * kFlagStride;
 constexpr size_t kMinIpcBytes = (size_t)2 << 20;     // allocations below this may share a block with others
 constexpr unsigned long long kMagicBase = 0x6c706d785f706565ull;  // "lpmx_pee"
 
@@ -51,101 +47,49 @@ struct Blob {  // what the ranks all-gather when a buffer is registered
   int pid;
 };
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-// spin until *p >= want or the deadline passes; false on timeout
-__device__ __forceinline__ bool wait_flag(const unsigned long long* p, unsigned long long want, unsigned long long deadline) {
-  while (ld_acquire_sys(p) < want) {
-    if (global_ns() > deadline) return false;
-    __nanosleep(200);
+// the protocol's platform on the GPU (lpmx_peer_protocol.h)
+struct DevicePlatform {
+  int* sh;  // two shared words of the CTA
+  __device__ __forceinline__ int tid() const { return threadIdx.x; }
+  __device__ __forceinline__ int bid() const { return blockIdx.x; }
+  __device__ __forceinline__ int n_threads() const { return blockDim.x; }
+  __device__ __forceinline__ int n_blocks() const { return gridDim.x; }
+  __device__ __forceinline__ unsigned long long now_ns() const {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
   }
-  return true;
-}
-
-struct PushArgs {
-  int rank, world;
-  unsigned long long epoch;
-  unsigned long long timeout_ns;
-  const double* src;  // this rank's segment in its own slab
-  long n;             // doubles in the segment
-  double* dst[kMaxPeers];               // the same segment in peer p's slab (dst[rank] unused)
-  unsigned long long* flags_local;
-  unsigned long long* flags_peer[kMaxPeers];
-  int* host_err;
+  __device__ __forceinline__ void backoff() const { __nanosleep(200); }
+  __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) const {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) const {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  }
+  __device__ __forceinline__ void fence_system() const { __threadfence_system(); }
+  __device__ __forceinline__ void sync_threads() const { __syncthreads(); }
+  __device__ __forceinline__ unsigned long long atomic_add(unsigned long long* p, unsigned long long v) const { return atomicAdd(p, v); }
+  __device__ __forceinline__ void report(int* host_err, int v) const { *(volatile int*)host_err = v; }
+  __device__ __forceinline__ int& s_ok() const { return sh[0]; }
+  __device__ __forceinline__ int& s_last() const { return sh[1]; }
 };
 
 template <int VEC>
 __global__ void __launch_bounds__(256) peer_push_kernel(const PushArgs a) {
-  __shared__ int s_ok, s_last;
-  const int tid = threadIdx.x, bid = blockIdx.x;
-  const unsigned long long deadline = global_ns() + a.timeout_ns;
-  if (bid == 0 && tid < a.world && tid != a.rank) st_release_sys(a.flags_peer[tid] + (kReady + a.rank) * kFlagStride, a.epoch);
-  const int np = a.world - 1;
-  for (int k = 0; k < np; ++k) {
-    const int p = (a.rank + 1 + (k + bid) % np) % a.world;
-    if (tid == 0) {
-      s_ok = wait_flag(a.flags_local + (kReady + p) * kFlagStride, a.epoch, deadline) ? 1 : 0;
-      if (!s_ok) {
-        *a.host_err = 1 + p;
-        a.flags_local[kFail * kFlagStride] = 1;
-      }
-    }
-    __syncthreads();
-    const bool ok = s_ok != 0;
-    __syncthreads();
-    if (!ok) continue;
-    const long stride = (long)gridDim.x * blockDim.x;
-    if (VEC == 2) {
-      const double2* s2 = reinterpret_cast<const double2*>(a.src);
-      double2* d2 = reinterpret_cast<double2*>(a.dst[p]);
-      for (long i = (long)bid * blockDim.x + tid; i < a.n / 2; i += stride) d2[i] = s2[i];
-    } else {
-      for (long i = (long)bid * blockDim.x + tid; i < a.n; i += stride) a.dst[p][i] = a.src[i];
-    }
-  }
-  // every store of this CTA is ordered before its ticket, every ticket before the last CTA's flags
-  __threadfence_system();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned long long t = atomicAdd(a.flags_local + kTicket * kFlagStride, 1ull);
-    s_last = (t == (unsigned long long)gridDim.x - 1) ? 1 : 0;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  if (tid == 0) a.flags_local[kTicket * kFlagStride] = 0;  // next launch on this stream starts from zero
-  __threadfence_system();
-  // a rank that could not deliver says nothing, so that its peers run into their own deadline instead of
-  // computing on records that never arrived (the fail word was written before its CTA's ticket)
-  if (*(volatile unsigned long long*)(a.flags_local + kFail * kFlagStride) != 0) return;
-  if (tid < a.world && tid != a.rank) {
-    st_release_sys(a.flags_peer[tid] + (kDone + a.rank) * kFlagStride, a.epoch);
-    if (!wait_flag(a.flags_local + (kDone + tid) * kFlagStride, a.epoch, deadline)) {
-      *a.host_err = 1 + tid;
-      a.flags_local[kFail * kFlagStride] = 1;
-    }
-  }
+  __shared__ int sh[2];
+  DevicePlatform pf{sh};
+  push_body<VEC>(pf, a);
 }
 
-// teardown barrier: bye[rank] := 1 on every peer, wait (briefly) for theirs
-__global__ void peer_bye_kernel(int rank, int world, unsigned long long timeout_ns, unsigned long long* flags_local,
-                                PushArgs a) {
-  const int tid = threadIdx.x;
-  const unsigned long long deadline = global_ns() + timeout_ns;
-  if (tid < world && tid != rank) {
-    st_release_sys(a.flags_peer[tid] + (kBye + rank) * kFlagStride, 1ull);
-    wait_flag(flags_local + (kBye + tid) * kFlagStride, 1ull, deadline);
-  }
+struct ByeArgs {
+  unsigned long long* flags_peer[kMaxRanks];
+};
+__global__ void peer_bye_kernel(int rank, int world, unsigned long long timeout_ns, unsigned long long* flags_local, ByeArgs b) {
+  __shared__ int sh[2];
+  DevicePlatform pf{sh};
+  bye_body(pf, rank, world, timeout_ns, flags_local, b.flags_peer);
 }
 
 typedef int (*nccl_allgather_t)(const void*, void*, size_t, int, void*, cudaStream_t);
@@ -339,10 +283,10 @@ void peer_teardown(lpmx_handle_t h) {
   ps->regions.clear();
   if (ps->flags_local) {
     // nobody frees exported memory before every rank has closed its mappings (or 2 s have passed)
-    PushArgs a;
-    memset(&a, 0, sizeof(a));
-    for (int q = 0; q < h->world; ++q) a.flags_peer[q] = q == h->rank ? nullptr : ps->flags_peer[q];
-    peer_bye_kernel<<<1, 32, 0, h->stream>>>(h->rank, h->world, 2000000000ull, ps->flags_local, a);
+    ByeArgs b;
+    memset(&b, 0, sizeof(b));
+    for (int q = 0; q < h->world; ++q) b.flags_peer[q] = q == h->rank ? nullptr : ps->flags_peer[q];
+    peer_bye_kernel<<<1, 32, 0, h->stream>>>(h->rank, h->world, 2000000000ull, ps->flags_local, b);
     cudaStreamSynchronize(h->stream);
     for (int q = 0; q < h->world; ++q)
       if (q != h->rank && ps->flags_peer[q]) cudaIpcCloseMemHandle(ps->flags_peer[q]);
