@@ -355,6 +355,12 @@ def main():
         "fp64_pipe_instr_per_interaction": {"bve_rk4": 9, "ic2d_rk2": 13.5, "swe_rk2": 53}[args.stepper],  # ic2d: (9 + 18) / 2
         "traffic": None,
     }
+    # what the FP64 pipe actually issued (2 flop per DFMA) against the same measured peak: the number that corresponds to
+    # ncu's sm__pipe_fp64_cycles_active, and the reason `frac` can exceed 1 (9 DFMAs do the work of the 24-flop reference pair)
+    if achieved_tf:
+        instr = roofline["fp64_pipe_instr_per_interaction"]
+        roofline["issued_tflops"] = achieved_tf * (2.0 * instr) / flops_per
+        roofline["issued_frac"] = roofline["issued_tflops"] / fp64_peak if fp64_peak else None
     prof = os.path.join(ROOT, "profiles", "r1_pair_sum_dram.json")
     if os.path.exists(prof) and args.workload == "rh54_cubed7" and args.stepper == "bve_rk4":  # captured on that launch shape
         try:
