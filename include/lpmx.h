@@ -175,6 +175,16 @@ int lpmx_comm_enable_peer_exchange(lpmx_handle_t h, int enable);
 /* enabled: 1 when exchanges of mapped slabs take the peer path; n_regions: slabs currently mapped. */
 int lpmx_comm_peer_exchange_enabled(lpmx_handle_t h, int* enabled, int* n_regions);
 
+/* Velocity pair sums with the source records streamed through the constant bank (opt-in, kVel launches with >= ~2e5
+ * targets per rank; lpm_b200/csrc/lpmx_const_stream.cu).  mode 0: off, 1: bank copies overlapped
+ * with the launches, 2: copies on the compute stream, -1: take LPMX_CONST_STREAM from the environment (default).  Affects
+ * the plans made AFTER the call (solvers created / states set afterwards).  One user per device and process: the bank is
+ * a single __constant__ array.  Same per-pair arithmetic as the default kernel; per-target sums differ by round-off. */
+int lpmx_pair_sum_const_stream(lpmx_handle_t h, int mode);
+/* The launch shape that path would use for n_tgt targets on a GPU with num_sms SMs (host-only planning query): T targets
+ * per thread, n_warps warps per CTA, grid CTAs per launch (one CTA per SM and wave). */
+int lpmx_const_stream_shape(int num_sms, int n_tgt, int* T, int* n_warps, int* grid);
+
 /* Measured FP64 FMA throughput of this GPU in TFLOP/s (dependent-free DFMA loop on all SMs);
  * the roofline denominator that MEASURED_PEAKS.json lacks. */
 int lpmx_fp64_peak_tflops(lpmx_handle_t h, double* tflops, double* ms);

@@ -264,6 +264,10 @@ class Engine:
         buf = ctypes.create_string_buffer(bytes(unique_id), 128)
         self._check(self._L.lpmx_comm_init(self._h, buf, rank, world), "lpmx_comm_init")
 
+    def pair_sum_const_stream(self, mode):
+        """0 off, 1 overlapped, 2 serial, -1 environment: velocity pair sums through the constant bank (include/lpmx.h)."""
+        self._check(self._L.lpmx_pair_sum_const_stream(self._h, int(mode)), "lpmx_pair_sum_const_stream")
+
     def comm_enable_peer_exchange(self, enable=True):
         """Collective, after comm_init and before any solver exists: exchange the packed source records with one
         kernel that stores into the peers' slabs over NVLink instead of the NCCL broadcasts (include/lpmx.h).

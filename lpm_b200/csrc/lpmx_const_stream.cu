@@ -1,0 +1,290 @@
+// lpmx_const_stream.cu -- the velocity pair sum with the source records streamed through the CONSTANT bank, so that
+// they reach the DFMAs as uniform-register operands (SASS: LDCU.64 + DFMA R, R, UR, R).  Opt-in, unmeasured in the
+// product: LPMX_CONST_STREAM=1 (copies overlapped with the kernels) or =2 (copies on the compute stream), or
+// lpmx_pair_sum_const_stream().  DESIGN.md section 8, lead 1.
+//
+// Why: pair_sum_kernel (lpmx_pair_kernel.cuh) is bound by FP64 issue and reaches 81 % of the pipe because 5 of its 9
+// DFMAs per pair read a third distinct register operand (profiles/README.md, "Why 81 %").  A source record is the same
+// for every thread; read from c[3][..] it costs no register-file port.  tools/const_probe.cu measured the body below at
+// 1.82e12 pairs/s per fully loaded B200 against 1.65e12 for the shared-memory ring (profiles/r1j_const_bank_probe.txt).
+//
+// How: the 64 KB bank holds two halves of 640 records x 48 B {y0, y1, y2, G*y0, G*y1, G*y2}.  One launch sums ONE half
+// into every target of this rank (accumulators live in slot 0 of the partials buffer between launches, 24 B per target
+// per launch -- three orders of magnitude below the FP64 time), while a device-to-device copy on the handle's copy
+// stream fills the other half for the next launch.  All CTAs of a launch read the same sources, so the work cannot be
+// split over sources the way the stream-K kernel does; the chip is balanced by the launch shape instead: one CTA per SM,
+// and (T targets per thread) x (NW warps) chosen so that waves x 148 x 32 x T x NW covers the targets with the least
+// excess.  That needs >= ~2e5 targets per rank; smaller launches keep the ring kernel.
+//
+// Same arithmetic per pair as Pair<kVel> (bit-identical terms); per target the terms are added in source order, so the
+// sums differ from the stream-K kernel's by round-off only (the tolerance of every parity test covers both).
+#include <cstdlib>
+
+#include "lpmx_internal.h"
+
+namespace lpmx {
+
+namespace {
+
+constexpr int kCsHalf = 640;  // records per half of the bank
+constexpr int kCsRec = 6;     // doubles per record
+constexpr int kCsMaxThreads = 384;
+__constant__ double c_src[2 * kCsHalf * kCsRec];  // 61 440 B of the 64 KB bank
+
+__device__ __forceinline__ double cs_rcp_seed(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  return r;
+}
+
+struct CsArgs {
+  Vec3View tgt;         // this launch's targets, indexed from 0
+  const int* self_idx;  // compact source index of each target's own particle, or -1 (may be null)
+  double* acc;          // [3][n_tgt_pad]
+  long n_tgt_pad;
+  int n_tgt;
+  int half;   // which half of the bank this launch reads
+  int j0;     // compact index of the half's first record
+  int first;  // start from zero instead of the stored accumulators
+  double kappa;
+};
+
+template <int T, bool CHECK>
+__device__ __forceinline__ void cs_loop(const double (&x)[T][3], const int (&self)[T], double (&acc)[T][3], int base, int j0,
+                                        double kappa) {
+#pragma unroll 2
+  for (int j = 0; j < kCsHalf; ++j) {
+    const double s0 = c_src[base + kCsRec * j], s1 = c_src[base + kCsRec * j + 1], s2 = c_src[base + kCsRec * j + 2];
+    const double s3 = c_src[base + kCsRec * j + 3], s4 = c_src[base + kCsRec * j + 4], s5 = c_src[base + kCsRec * j + 5];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const double d = fma(-x[t][0], s0, fma(-x[t][1], s1, fma(-x[t][2], s2, kappa)));
+      const double r0 = cs_rcp_seed(d);
+      const double e = fma(-d, r0, 1.0);
+      const double p = fma(e, e, e);
+      double r = fma(r0, p, r0);
+      if (CHECK) r = (j0 + j == self[t]) ? 0.0 : r;
+      acc[t][0] = fma(r, s3, acc[t][0]);
+      acc[t][1] = fma(r, s4, acc[t][1]);
+      acc[t][2] = fma(r, s5, acc[t][2]);
+    }
+  }
+}
+
+template <int T>
+__global__ void __launch_bounds__(kCsMaxThreads, 1) pair_sum_const_kernel(const CsArgs a) {
+  const int lanes = blockDim.x;
+  const long base_t = (long)blockIdx.x * ((long)T * lanes) + threadIdx.x;
+  double x[T][3], acc[T][3];
+  int self[T];
+  bool hit = false;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const long tg = base_t + (long)t * lanes;  // < n_tgt_pad by construction of the grid
+    const bool valid = tg < a.n_tgt;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      x[t][k] = valid ? a.tgt(tg, k) : 0.0;  // a zero target sees d = kappa: finite, never stored anywhere that is read
+      acc[t][k] = a.first ? 0.0 : a.acc[(long)k * a.n_tgt_pad + tg];
+    }
+    self[t] = (valid && a.self_idx) ? a.self_idx[tg] : -1;
+    hit |= (unsigned)(self[t] - a.j0) < (unsigned)kCsHalf;
+  }
+  const int base = a.half * (kCsHalf * kCsRec);
+  if (__any_sync(0xffffffffu, hit))
+    cs_loop<T, true>(x, self, acc, base, a.j0, a.kappa);
+  else
+    cs_loop<T, false>(x, self, acc, base, a.j0, a.kappa);
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const long tg = base_t + (long)t * lanes;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a.acc[(long)k * a.n_tgt_pad + tg] = acc[t][k];
+  }
+}
+
+// packed 64-byte records -> 48-byte records, zero-padded to whole halves
+__global__ void cs_repack_kernel(const double* __restrict__ packed, int n_src_pad, double* __restrict__ out, long n_out) {
+  const long j = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (j >= n_out) return;
+  double v[kCsRec] = {0, 0, 0, 0, 0, 0};
+  if (j < n_src_pad) {
+    const double2* r = reinterpret_cast<const double2*>(packed + (size_t)kBveRec * j);
+    const double2 a = r[0], b = r[1], c = r[2];
+    v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y, v[4] = c.x, v[5] = c.y;
+  }
+#pragma unroll
+  for (int k = 0; k < kCsRec; ++k) out[(size_t)kCsRec * j + k] = v[k];
+}
+
+typedef void (*cs_kernel_t)(const CsArgs);
+cs_kernel_t cs_kernel_for(int T) {
+  switch (T) {
+    case 4: return pair_sum_const_kernel<4>;
+    case 5: return pair_sum_const_kernel<5>;
+    case 6: return pair_sum_const_kernel<6>;
+    case 7: return pair_sum_const_kernel<7>;
+    case 8: return pair_sum_const_kernel<8>;
+    default: return nullptr;
+  }
+}
+
+}  // namespace
+
+int const_stream_mode(lpmx_handle_t h) {
+  if (h->const_stream >= 0) return h->const_stream;
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("LPMX_CONST_STREAM");
+    env = e ? atoi(e) : 0;
+    if (env < 0 || env > 2) env = 0;
+  }
+  return env;
+}
+
+// One CTA per SM; a launch takes ~ waves x T x NW while the FP64 pipe is the limit (>= 8 warps).  Least excess wins,
+// ties go to T = 6 (the measured shape), then to more warps.  LPMX_CONST_SHAPE="T,NW" overrides (tuning).
+void pick_const_shape(int num_sms, int n_tgt, int* T_out, int* nw_out, int* grid_out) {
+  int bt = 6, bnw = 8;
+  long best = -1;
+  static int ft = 0, fnw = 0;
+  static bool parsed = false;
+  if (!parsed) {
+    parsed = true;
+    const char* e = getenv("LPMX_CONST_SHAPE");
+    if (e && sscanf(e, "%d,%d", &ft, &fnw) == 2 && cs_kernel_for(ft) && fnw >= 1 && fnw * 32 <= kCsMaxThreads) {
+    } else {
+      ft = fnw = 0;
+    }
+  }
+  if (ft) {
+    bt = ft, bnw = fnw;
+  } else {
+    const int order[3] = {6, 7, 5};
+    for (int oi = 0; oi < 3; ++oi) {
+      const int T = order[oi];
+      for (int nw = 12; nw >= 8; --nw) {
+        const long tb = (long)T * nw * 32;
+        const long ctas = (n_tgt + tb - 1) / tb;
+        const long waves = (ctas + num_sms - 1) / num_sms;
+        const long cost = waves * T * nw;
+        if (best < 0 || cost < best) best = cost, bt = T, bnw = nw;
+      }
+    }
+  }
+  const long tb = (long)bt * bnw * 32;
+  *T_out = bt;
+  *nw_out = bnw;
+  *grid_out = (int)((n_tgt + tb - 1) / tb);
+}
+
+bool make_const_plan(lpmx_handle_t h, int n_tgt, int n_src, SumPlan* p) {
+  if (const_stream_mode(h) == 0) return false;
+  // below these sizes the launches cannot fill the chip (one CTA per SM, >= 8 warps, >= 5 targets per thread) or are
+  // too short against their own launch overhead
+  long min_tgt = (long)h->num_sms * 32 * 8 * 5;
+  if (const char* e = getenv("LPMX_CONST_MIN_TARGETS")) min_tgt = atol(e);  // parity tests on small meshes
+  if ((long)n_tgt < min_tgt || n_tgt < 1 || n_src < 4 * kCsHalf) return false;
+  int T, nw, grid;
+  pick_const_shape(h->num_sms, n_tgt, &T, &nw, &grid);
+  p->kind = kVel;
+  p->shape = kShapeConstStream;
+  p->T = T;
+  p->tb = T * nw * 32;
+  p->n_tgt = n_tgt;
+  p->n_tb = grid;  // CTAs of one launch
+  p->n_src_pad = round_up_chunk(n_src);
+  p->n_sc = p->n_src_pad / kChunk;
+  p->grid = 1;  // what the finalize kernels see: every target block was summed by "CTA 0", i.e. slot 0 only
+  p->max_slots = 1;
+  p->n_tgt_pad = (long)p->n_tb * p->tb;
+  p->smem_bytes = 0;
+  return true;
+}
+
+int launch_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* self_idx, const double* packed, double kappa,
+                        double* partials) {
+  const int mode = const_stream_mode(h) == 2 ? 2 : 1;
+  const long n_batches = ((long)p.n_src_pad + kCsHalf - 1) / kCsHalf;
+  const long n_out = n_batches * kCsHalf;
+  void* stage_v = nullptr;
+  LPMX_TRY(dev_buffer(h, "const_stage", sizeof(double) * kCsRec * (size_t)n_out, &stage_v));
+  const double* stage = (const double*)stage_v;
+  cs_repack_kernel<<<(int)((n_out + 255) / 256), 256, 0, h->stream>>>(packed, p.n_src_pad, (double*)stage_v, n_out);
+  ++h->launches;
+  LPMX_CUDA(h, cudaGetLastError());
+  if (!h->cs_events[0]) {
+    for (int i = 0; i < 5; ++i) LPMX_CUDA(h, cudaEventCreateWithFlags(&h->cs_events[i], cudaEventDisableTiming));
+  }
+  cudaEvent_t ev_repack = h->cs_events[0];
+  cudaEvent_t* ev_copied = &h->cs_events[1];  // [half]
+  cudaEvent_t* ev_summed = &h->cs_events[3];  // [half]
+  const size_t half_bytes = sizeof(double) * kCsRec * kCsHalf;
+  cs_kernel_t kern = cs_kernel_for(p.T);
+  if (!kern) return set_error(h, LPMX_ERR_STATE, "no constant-bank kernel for T = %d", p.T);
+  const int threads = p.tb / p.T;
+  cudaStream_t cps = mode == 1 ? h->copy_stream : h->stream;
+  // copy of batch b into half b & 1; in the overlapped mode it waits for the launch that last read that half
+  auto copy_batch = [&](long b) -> int {
+    const int half = (int)(b & 1);
+    if (mode == 1 && b >= 2) LPMX_CUDA(h, cudaStreamWaitEvent(cps, ev_summed[half], 0));
+    LPMX_CUDA(h, cudaMemcpyToSymbolAsync(c_src, stage + (size_t)b * kCsHalf * kCsRec, half_bytes, (size_t)half * half_bytes,
+                                         cudaMemcpyDeviceToDevice, cps));
+    if (mode == 1) LPMX_CUDA(h, cudaEventRecord(ev_copied[half], cps));
+    return LPMX_OK;
+  };
+  if (mode == 1) {
+    // everything queued so far on the compute stream (the repack, and any earlier launch still reading the bank)
+    LPMX_CUDA(h, cudaEventRecord(ev_repack, h->stream));
+    LPMX_CUDA(h, cudaStreamWaitEvent(cps, ev_repack, 0));
+    LPMX_TRY(copy_batch(0));
+    if (n_batches > 1) LPMX_TRY(copy_batch(1));
+  }
+  CsArgs a;
+  a.tgt = tgt;
+  a.self_idx = self_idx;
+  a.acc = partials;
+  a.n_tgt_pad = p.n_tgt_pad;
+  a.n_tgt = p.n_tgt;
+  a.kappa = kappa;
+  for (long b = 0; b < n_batches; ++b) {
+    const int half = (int)(b & 1);
+    if (mode == 1)
+      LPMX_CUDA(h, cudaStreamWaitEvent(h->stream, ev_copied[half], 0));
+    else
+      LPMX_TRY(copy_batch(b));
+    a.half = half;
+    a.j0 = (int)(b * kCsHalf);
+    a.first = b == 0 ? 1 : 0;
+    kern<<<p.n_tb, threads, 0, h->stream>>>(a);
+    ++h->launches;
+    LPMX_CUDA(h, cudaGetLastError());
+    if (mode == 1) {
+      LPMX_CUDA(h, cudaEventRecord(ev_summed[half], h->stream));
+      if (b + 2 < n_batches) LPMX_TRY(copy_batch(b + 2));
+    }
+  }
+  return LPMX_OK;
+}
+
+void const_stream_teardown(lpmx_handle_t h) {
+  for (int i = 0; i < 5; ++i)
+    if (h->cs_events[i]) {
+      cudaEventDestroy(h->cs_events[i]);
+      h->cs_events[i] = nullptr;
+    }
+}
+
+}  // namespace lpmx
+
+extern "C" int lpmx_const_stream_shape(int num_sms, int n_tgt, int* T, int* n_warps, int* grid) {
+  if (num_sms < 1 || n_tgt < 1 || !T || !n_warps || !grid) return LPMX_ERR_INVALID;
+  lpmx::pick_const_shape(num_sms, n_tgt, T, n_warps, grid);
+  return LPMX_OK;
+}
+
+extern "C" int lpmx_pair_sum_const_stream(lpmx_handle_t h, int mode) {
+  if (!h || mode < -1 || mode > 2) return LPMX_ERR_INVALID;
+  h->const_stream = mode;
+  return LPMX_OK;
+}

@@ -184,6 +184,7 @@ int lpmx_destroy(lpmx_handle_t h) {
   if (h->cached_ic2d) lpmx_ic2d_solver_destroy(h->cached_ic2d);
   if (h->cached_swe) lpmx_swe_solver_destroy(h->cached_swe);
   if (h->cached_plane) lpmx_plane_swe_solver_destroy(h->cached_plane);
+  const_stream_teardown(h);
   peer_teardown(h);  // before the NCCL communicator goes: closes the IPC mappings, then frees what was exported
   for (auto& kv : h->bufs)
     if (kv.second.p) cudaFree(kv.second.p);

@@ -120,6 +120,8 @@ struct lpmx_handle_s {
   void* nccl_comm = nullptr;  // ncclComm_t when lpmx_comm_init succeeded
   void* nccl_lib = nullptr;   // dlopen handle
   lpmx::PeerState* peer = nullptr;  // lpmx_comm_enable_peer_exchange
+  int const_stream = -1;            // lpmx_pair_sum_const_stream: -1 = LPMX_CONST_STREAM from the environment
+  cudaEvent_t cs_events[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // lpmx_const_stream.cu
   std::map<std::string, lpmx::DevBuf> bufs;  // named scratch buffers
   std::map<std::string, lpmx::DevBuf> pinned;  // named pinned host staging buffers
   // optional per-launch timing of the pair-sum kernel (lpmx_profile_enable)
@@ -170,6 +172,16 @@ size_t plan_partials_bytes(const SumPlan& p);
 // Planar kinds read target rows (x0, x1, surface height) through the same 3-row view.
 int launch_pair_sum(lpmx_handle_t h, const SumPlan& plan, Vec3View tgt, const int* self_idx, const double* packed,
                     double kappa, double* partials, double aux = 0.0);
+
+// ---- velocity pair sum through the constant bank (lpmx_const_stream.cu; opt-in) ----
+constexpr int kShapeConstStream = 1000;  // SumPlan::shape of a launch that takes this path
+// fills *p and returns true when the path is switched on and the launch is large enough for it (kVel only)
+bool make_const_plan(lpmx_handle_t h, int n_tgt, int n_src, SumPlan* p);
+int launch_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* self_idx, const double* packed, double kappa,
+                        double* partials);
+void pick_const_shape(int num_sms, int n_tgt, int* T_out, int* nw_out, int* grid_out);
+int const_stream_mode(lpmx_handle_t h);
+void const_stream_teardown(lpmx_handle_t h);
 
 // exclusive scan of !mask -> leaf_idx, returns number of unmasked sources (host sync)
 int scan_leaves(lpmx_handle_t h, const unsigned char* mask_dev, int n, int* leaf_idx_dev, int* n_leaves);

@@ -93,6 +93,7 @@ static int pick_shape(int kind, int num_sms, int n_tgt, int n_sc) {
 
 int make_plan(lpmx_handle_t h, int kind, int n_tgt, int n_src, SumPlan* p) {
   if (n_tgt < 0 || n_src < 0) return set_error(h, LPMX_ERR_INVALID, "negative size");
+  if (kind == kVel && make_const_plan(h, n_tgt, n_src, p)) return LPMX_OK;  // opt-in: sources through the constant bank
   p->kind = kind;
   p->n_tgt = n_tgt;
   p->n_src_pad = round_up_chunk(n_src);
@@ -146,7 +147,8 @@ int launch_pair_sum(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* 
   a.n_tgt_pad = p.n_tgt_pad;
   a.kappa = kappa;
   a.aux = aux;
-  if (!h->profile) return kShapes[p.shape].launch(h, p, a);
+  const bool cs = p.shape == kShapeConstStream;
+  if (!h->profile) return cs ? launch_const_stream(h, p, tgt, self_idx, packed, kappa, partials) : kShapes[p.shape].launch(h, p, a);
   if (h->prof_used == h->prof_events.size()) {
     cudaEvent_t e0, e1;
     LPMX_CUDA(h, cudaEventCreate(&e0));
@@ -155,7 +157,7 @@ int launch_pair_sum(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* 
   }
   auto& ev = h->prof_events[h->prof_used++];
   LPMX_CUDA(h, cudaEventRecord(ev.first, h->stream));
-  const int rc = kShapes[p.shape].launch(h, p, a);
+  const int rc = cs ? launch_const_stream(h, p, tgt, self_idx, packed, kappa, partials) : kShapes[p.shape].launch(h, p, a);
   LPMX_CUDA(h, cudaEventRecord(ev.second, h->stream));
   h->prof_pairs += (double)p.n_tgt * (double)p.n_src_pad;
   return rc;

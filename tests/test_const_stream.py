@@ -1,0 +1,79 @@
+"""Velocity pair sums through the constant bank (lpm_b200/csrc/lpmx_const_stream.cu; opt-in).
+CPU: the launch-shape planner.  GPU (only when LPMX_TEST_CONST=1: the path was written after the round's GPU budget was spent
+and has not run yet): parity with the oracle and with the default stream-K kernel."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from lpm_b200 import _lib
+
+SMS = 148
+
+
+def _shape(n_tgt, sms=SMS):
+    T, nw, grid = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = _lib.lib().lpmx_const_stream_shape(sms, n_tgt, ctypes.byref(T), ctypes.byref(nw), ctypes.byref(grid))
+    assert rc == 0
+    return T.value, nw.value, grid.value
+
+
+@pytest.mark.parametrize("n_tgt", [229376, 9382, 600742, 2402982, 9611942, 300000, 1201491, 189440, 1, 12345])
+def test_shape_covers_the_targets_and_fits_a_cta(n_tgt):
+    T, nw, grid = _shape(n_tgt)
+    assert T in (5, 6, 7) and 8 <= nw <= 12 and nw * 32 <= 384
+    tb = T * nw * 32
+    assert grid * tb >= n_tgt > (grid - 1) * tb
+
+
+@pytest.mark.parametrize("n_tgt,least", [(229376, 0.95), (600742, 0.93), (2402982, 0.95), (9611942, 0.98), (1201491, 0.95)])
+def test_shape_wastes_little_of_the_chip(n_tgt, least):
+    """cubed-7, icos-7, icos-8, icos-9 on one GPU and icos-8 on two: fraction of (waves x SMs x targets per CTA) that is work."""
+    T, nw, grid = _shape(n_tgt)
+    waves = -(-grid // SMS)
+    assert n_tgt / (waves * SMS * T * nw * 32) >= least
+
+
+def test_shape_rejects_bad_arguments():
+    T = ctypes.c_int()
+    assert _lib.lib().lpmx_const_stream_shape(0, 10, ctypes.byref(T), ctypes.byref(T), ctypes.byref(T)) != 0
+    assert _lib.lib().lpmx_const_stream_shape(148, 0, ctypes.byref(T), ctypes.byref(T), ctypes.byref(T)) != 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("seed,depth", [("icos", 4), ("cubed", 5)])
+def test_gpu_const_stream_velocity_matches_oracle_and_default_kernel(oracle, mode, seed, depth, monkeypatch):
+    if os.environ.get("LPMX_TEST_CONST") != "1":
+        pytest.skip("set LPMX_TEST_CONST=1 to run the constant-bank path (not yet measured on a GPU)")
+    from lpm_b200 import gallery
+    from lpm_b200.api import Engine, PolyMesh2d
+    from conftest import field_rel_err
+    monkeypatch.setenv("LPMX_CONST_MIN_TARGETS", "1")
+    m = PolyMesh2d(seed, depth)
+    f = gallery.RossbyHaurwitz54()
+    f.set_stationary_wave_speed()
+    fz = f(m.face_xyz)
+    ref_v = oracle.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask)
+    ref_f = oracle.bve_velocity(None, m.face_xyz, fz, m.face_area, m.face_mask, collocated=True)
+    e0, e1 = Engine(0), Engine(0)
+    try:
+        e0.pair_sum_const_stream(0)
+        e1.pair_sum_const_stream(mode)
+        got0_v = e0.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask)
+        got1_v = e1.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask)
+        got1_f = e1.bve_velocity(None, m.face_xyz, fz, m.face_area, m.face_mask, collocated=True)
+        assert field_rel_err(got1_v, ref_v) <= 1e-12
+        assert field_rel_err(got1_f, ref_f) <= 1e-12   # collocated: the self pair is removed by index
+        assert field_rel_err(got1_v, got0_v) <= 1e-13
+        # and through a stepper: two RK4 steps
+        st0 = [m.vert_xyz.copy(), f(m.vert_xyz), got0_v.copy(), m.face_xyz.copy(), fz.copy(), got1_f.copy()]
+        st1 = [a.copy() for a in st0]
+        e0.bve_rk4_step(0.01, 2 * np.pi, *st0, m.face_area, m.face_mask, n_steps=2)
+        e1.bve_rk4_step(0.01, 2 * np.pi, *st1, m.face_area, m.face_mask, n_steps=2)
+        leaf = m.face_mask == 0
+        assert max(field_rel_err(st1[0], st0[0]), field_rel_err(st1[1], st0[1]), field_rel_err(st1[3], st0[3], leaf)) <= 1e-12
+    finally:
+        e0.close()
+        e1.close()
