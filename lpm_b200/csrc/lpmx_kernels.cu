@@ -48,10 +48,14 @@ struct Shape {
 template <class C>
 static int launch_cfg(lpmx_handle_t h, const SumPlan& p, const SumArgs& a) {
   auto kern = pair_sum_kernel<C>;
-  static bool attr_set = false;  // per template instance
-  if (!attr_set) {
+  // per template instance AND per device: the attribute belongs to the function in the device's context, and one process
+  // may hold handles on several GPUs (lpmx_create(device_id))
+  constexpr int kMaxDev = 64;
+  static bool attr_set[kMaxDev] = {};
+  const int dev = h->device;
+  if (dev < 0 || dev >= kMaxDev || !attr_set[dev]) {
     LPMX_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-    attr_set = true;
+    if (dev >= 0 && dev < kMaxDev) attr_set[dev] = true;
   }
   kern<<<p.grid, C::THREADS, p.smem_bytes, h->stream>>>(a);
   ++h->launches;
