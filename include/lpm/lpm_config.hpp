@@ -10,6 +10,9 @@
 #ifndef LPM_SHIM_CONFIG_HPP
 #define LPM_SHIM_CONFIG_HPP
 
+#define LPM_NULL_IDX (-1)      /* LpmConfig.h.in:20 */
+#define LPM_MAX_AMR_LIMIT 6     /* LpmConfig.h.in:19 */
+
 #include <cmath>
 #include <cstdlib>
 #include <sstream>
@@ -27,6 +30,7 @@ typedef int Int;
 namespace constants {
 static constexpr Real PI = 3.1415926535897932384626433832795027975;
 static constexpr Real ZERO_TOL = 2.220446049250313e-16;  // FloatingPoint<Real>::zero_tol, lpm_floating_point.hpp:22
+static constexpr int NULL_IND = -1;                       // lpm_constants.hpp:31
 }  // namespace constants
 
 template <typename T>

@@ -8,7 +8,8 @@
 //   PolyMesh2d::divide_flagged_faces                   src/mesh/lpm_polymesh2d_impl.hpp:124-173 (via lpmx_mesh_divide_flagged_faces)
 // As in the reference every mesh view is allocated once at its maximum extent (nmaxverts / nmaxedges / nmaxfaces, sized
 // for init_depth + amr_buffer) and n_*_host() counts the entries in use, so shallow copies held by flag functors and
-// solvers stay valid across an adaptive refinement.  Point location (locate_face_containing_pt) is not provided.
+// solvers stay valid across an adaptive refinement.  The mesh queries (ccw_adjacent_faces, locate_face_containing_pt, ...) forward to
+// the host generator (lpmx_mesh_*), which is where the mesh lives.
 #ifndef LPM_SHIM_POLYMESH2D_HPP
 #define LPM_SHIM_POLYMESH2D_HPP
 
@@ -202,6 +203,53 @@ class PolyMesh2d {
       logger.info("divide_flagged_faces: {} faces divided.", refine_count);
   }
 
+  // ---- mesh queries (src/mesh/lpm_polymesh2d.hpp:262-552; host code here as the mesh is) ----
+  /// PolyMesh2d::get_leaf_edges_from_parent (:277-308)
+  template <typename EdgeList = Index*>
+  void get_leaf_edges_from_parent(EdgeList& edge_list, Int& n_leaves, const Index parent_edge_idx) const {
+    query(&lpmx_mesh_leaf_edges_from_parent, parent_edge_idx, edge_list, n_leaves, "get_leaf_edges_from_parent");
+  }
+  /// PolyMesh2d::ccw_edges_around_face (:316-340)
+  template <typename EdgeList = Index*>
+  void ccw_edges_around_face(EdgeList& face_leaf_edges, Int& n_leaf_edges, const Index face_idx) const {
+    query(&lpmx_mesh_ccw_edges_around_face, face_idx, face_leaf_edges, n_leaf_edges, "ccw_edges_around_face");
+  }
+  /// PolyMesh2d::ccw_adjacent_faces (:348-366); LPM_NULL_IDX across a free boundary
+  template <typename FaceList = Index*>
+  void ccw_adjacent_faces(FaceList& adj_faces, Int& n_adj, const Index face_idx) const {
+    query(&lpmx_mesh_ccw_adjacent_faces, face_idx, adj_faces, n_adj, "ccw_adjacent_faces");
+  }
+  /// NeighborsFlag::operator() over faces [start, end) (src/mesh/lpm_refinement_flags.hpp:30-52)
+  void neighbors_flag(const mask_view_type& flags, const Index start, const Index end) const {
+    LPM_REQUIRE((Index)flags.extent(0) >= end);
+    LPM_REQUIRE(lpmx_mesh_neighbors_flag(handle_.get(), flags.data(), (int)start, (int)end, nullptr) == LPMX_OK);
+  }
+  /// The generator answers point-location queries from ITS coordinates: hand it the views' current values first.
+  void push_coordinates() const {
+    const long nd = Geo::ndim;
+    lpmx_mesh_t m = handle_.get();
+    LPM_REQUIRE(lpmx_mesh_update_array(m, LPMX_MESH_VERT_XYZ, vertices.phys_crds.view.data(), nd * n_vertices_host()) == LPMX_OK);
+    LPM_REQUIRE(lpmx_mesh_update_array(m, LPMX_MESH_FACE_XYZ, faces.phys_crds.view.data(), nd * n_faces_host()) == LPMX_OK);
+  }
+  /// PolyMesh2d::locate_face_containing_pt (:541-552), locate_pt_walk_search (:377-413), locate_pt_tree_search (:446-473),
+  /// nearest_root_face (:421-434).  Call push_coordinates() after the particles have moved.
+  template <typename Point>
+  Index locate_face_containing_pt(const Point& query_pt) const {
+    return locate(LPMX_LOCATE_CONTAINING, query_pt, 0);
+  }
+  template <typename Point>
+  Index locate_pt_walk_search(const Point& query_pt, const Index face_start_idx) const {
+    return locate(LPMX_LOCATE_WALK, query_pt, face_start_idx);
+  }
+  template <typename Point>
+  Index locate_pt_tree_search(const Point& query_pt, const Index root_face) const {
+    return locate(LPMX_LOCATE_TREE, query_pt, root_face);
+  }
+  template <typename Point>
+  Index nearest_root_face(const Point& query_pt) const {
+    return locate(LPMX_LOCATE_NEAREST_ROOT, query_pt, 0);
+  }
+
   Index n_vertices_host() const { return vertices.nh(); }
   Index n_edges_host() const { return edges.nh(); }
   Index n_faces_host() const { return faces.nh(); }
@@ -226,6 +274,25 @@ class PolyMesh2d {
 
  private:
   std::shared_ptr<lpmx_mesh_s> handle_;  // the host generator's tree (kept for divide_flagged_faces)
+
+  template <typename List>
+  void query(int (*fn)(lpmx_mesh_t, int, int*, int, int*), const Index idx, List& list, Int& n, const char* what) const {
+    int tmp[8 * 6 * 4];  // nfaceverts * LPM_MAX_AMR_LIMIT entries in the reference's callers; generous
+    int nn = 0;
+    LPM_REQUIRE_MSG(fn(handle_.get(), (int)idx, tmp, (int)(sizeof(tmp) / sizeof(tmp[0])), &nn) == LPMX_OK, what);
+    LPM_REQUIRE_MSG(nn <= (int)(sizeof(tmp) / sizeof(tmp[0])), what);
+    for (int i = 0; i < nn; ++i) list[i] = tmp[i];
+    n = nn;
+  }
+  template <typename Point>
+  Index locate(const int mode, const Point& pt, const Index start) const {
+    Real q[3] = {0, 0, 0};
+    for (int k = 0; k < Geo::ndim; ++k) q[k] = pt[k];
+    const int st = (int)start;
+    int out = -1;
+    LPM_REQUIRE(lpmx_mesh_locate(handle_.get(), mode, q, 1, &st, &out) == LPMX_OK);
+    return out;
+  }
 
   void push(const int id, const Real* src, const long count) {
     LPM_REQUIRE(lpmx_mesh_update_array(handle_.get(), id, src, count) == LPMX_OK);

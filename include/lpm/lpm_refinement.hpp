@@ -6,7 +6,7 @@
 // Same constructor arguments, public members (relative_tol, tol, nfaces, flags), set_tol_from_relative_value(),
 // description() and info_string().  Where the reference passes the functor to Kokkos::parallel_for over [start, end), here
 // Refinement::iterate calls its apply(start, end): one kernel launch that switches flags on in that range and returns the
-// number of flags set there.  NeighborsFlag (:30-53; unused by the drivers) is not provided.
+// number of flags set there.  NeighborsFlag (:30-53; unused by the drivers) runs on the host, where the edge tree lives.
 #ifndef LPM_SHIM_REFINEMENT_HPP
 #define LPM_SHIM_REFINEMENT_HPP
 
@@ -154,6 +154,26 @@ struct FlowMapVariationFlag {
     d.face_verts = face_vertex_view.data(), d.vert_lag = vertex_lag_crds.data(), d.ndim = MeshSeedType::geo::ndim;
     d.layout = LPMX_LAYOUT_RIGHT, d.ld = d.n_verts, d.mask = facemask.data(), d.tol = tol;
     return d;
+  }
+};
+
+/// NeighborsFlag (src/mesh/lpm_refinement_flags.hpp:30-52): a face whose neighbour is more than one level finer is flagged
+/// too (2:1 balance).  Host code: it walks the edge tree, which lives in the host generator.
+template <typename MeshSeedType>
+struct NeighborsFlag {
+  flag_view flags;
+  const PolyMesh2d<MeshSeedType>& mesh;
+
+  NeighborsFlag(flag_view f, const PolyMesh2d<MeshSeedType>& mesh) : flags(f), mesh(mesh) {}
+
+  std::string description() const { return "NeighborsFlag"; }
+
+  /// flags on in [start, end) after this functor (the convention of the other flags' apply)
+  Index apply(const Index start, const Index end) {
+    mesh.neighbors_flag(flags, start, end);
+    Index n = 0;
+    for (Index i = start; i < end; ++i) n += flags(i) ? 1 : 0;
+    return n;
   }
 };
 

@@ -131,6 +131,27 @@ int lpmx_mesh_update_array(lpmx_mesh_t mesh, int array_id, const double* data, l
 int lpmx_mesh_divide_flagged_faces(lpmx_mesh_t mesh, const unsigned char* flags, int n_flags, int max_faces,
                                    int max_level, int* n_divided, int* outcome);
 
+/* Mesh queries on the (possibly adaptively refined) tree, host code like the mesh itself; all restated as coded.
+ * PolyMesh2d::get_leaf_edges_from_parent / ccw_edges_around_face / ccw_adjacent_faces (src/mesh/lpm_polymesh2d.hpp:277-308,
+ * :316-340, :348-366): *n receives the length of the list, the first min(*n, cap) entries are written.  Neighbours across a free
+ * boundary of a planar mesh are -1.  The reference's own known answers (tests/lpm_polymesh2d_function_tests.cpp:96-104,213-238)
+ * are asserted in tests/test_mesh_queries.py. */
+int lpmx_mesh_leaf_edges_from_parent(lpmx_mesh_t mesh, int parent_edge, int* list, int cap, int* n);
+int lpmx_mesh_ccw_edges_around_face(lpmx_mesh_t mesh, int face, int* list, int cap, int* n);
+int lpmx_mesh_ccw_adjacent_faces(lpmx_mesh_t mesh, int face, int* list, int cap, int* n);
+/* NeighborsFlag (src/mesh/lpm_refinement_flags.hpp:30-52): flags[i] |= (some neighbour of face i is more than one level
+ * finer), for i in [start, end) -- what keeps an adaptive mesh 2:1 balanced.  *n_flagged counts the newly set flags. */
+int lpmx_mesh_neighbors_flag(lpmx_mesh_t mesh, unsigned char* flags, int start, int end, int* n_flagged);
+/* Point location at the mesh's current coordinates (push them with lpmx_mesh_update_array first when the particles have moved).
+ * pts: n_pts rows of ndim doubles; out: face indices.  Modes: locate_face_containing_pt (:541-552; -1 when a planar point lies
+ * outside the mesh, pt_is_outside_mesh :484-535), locate_pt_walk_search from the leaf start[i] (:377-413), locate_pt_tree_search
+ * from the face start[i] (:446-473), nearest_root_face (:421-434). */
+#define LPMX_LOCATE_CONTAINING 0
+#define LPMX_LOCATE_WALK 1
+#define LPMX_LOCATE_TREE 2
+#define LPMX_LOCATE_NEAREST_ROOT 3
+int lpmx_mesh_locate(lpmx_mesh_t mesh, int mode, const double* pts, int n_pts, const int* start, int* out);
+
 /* ------------------------------------------------------------------------------------------
  * Engine handle: one per process and GPU.
  * ------------------------------------------------------------------------------------------ */

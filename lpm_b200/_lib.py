@@ -123,6 +123,11 @@ def _declare(L):
         "lpmx_mesh_array": [vp, i, ctypes.POINTER(vp), c_long_p, c_int_p],
         "lpmx_mesh_update_array": [vp, i, vp, l],
         "lpmx_mesh_divide_flagged_faces": [vp, vp, i, i, i, c_int_p, c_int_p],
+        "lpmx_mesh_leaf_edges_from_parent": [vp, i, vp, i, c_int_p],
+        "lpmx_mesh_ccw_edges_around_face": [vp, i, vp, i, c_int_p],
+        "lpmx_mesh_ccw_adjacent_faces": [vp, i, vp, i, c_int_p],
+        "lpmx_mesh_neighbors_flag": [vp, vp, i, i, c_int_p],
+        "lpmx_mesh_locate": [vp, i, vp, i, vp, vp],
         "lpmx_refine_flag_max": [vp, ctypes.POINTER(FlagDesc), ctypes.POINTER(ctypes.c_double)],
         "lpmx_refine_flag": [vp, ctypes.POINTER(FlagDesc), i, i, i, vp, c_int_p],
         "lpmx_create": [ctypes.POINTER(vp), i],

@@ -98,17 +98,22 @@ class PolyMesh2d:
                 arr = arr.reshape(-1, w)
             setattr(self, name, arr)
 
+    def _push_coordinates(self):
+        """Hand this object's coordinate arrays (which the caller may have advected) to the generator."""
+        L = _lib.lib()
+        for name in ("vert_xyz", "vert_lag_xyz", "face_xyz", "face_lag_xyz"):
+            a = np.ascontiguousarray(getattr(self, name), dtype=np.float64)
+            rc = L.lpmx_mesh_update_array(self._m, _MESH_ARRAYS[name][0], a.ctypes.data, a.size)
+            if rc:
+                raise LpmxError(rc, "lpmx_mesh_update_array")
+
     def divide_flagged_faces(self, flags, push_coordinates=True):
         """PolyMesh2d::divide_flagged_faces (src/mesh/lpm_polymesh2d_impl.hpp:124-173).  The coordinate arrays of this object
         (which the caller may have advected) are handed to the generator first, the arrays are re-read afterwards.
         Returns (n_divided, outcome) with outcome one of AMR_DIVIDED_ALL / AMR_NO_SPACE / AMR_LIMIT_REACHED."""
         L = _lib.lib()
         if push_coordinates:
-            for name in ("vert_xyz", "vert_lag_xyz", "face_xyz", "face_lag_xyz"):
-                a = np.ascontiguousarray(getattr(self, name), dtype=np.float64)
-                rc = L.lpmx_mesh_update_array(self._m, _MESH_ARRAYS[name][0], a.ctypes.data, a.size)
-                if rc:
-                    raise LpmxError(rc, "lpmx_mesh_update_array")
+            self._push_coordinates()
         f = np.ascontiguousarray(flags, dtype=np.uint8)
         nd, oc = ctypes.c_int(), ctypes.c_int()
         rc = L.lpmx_mesh_divide_flagged_faces(self._m, f.ctypes.data, f.size, self.nmaxfaces, self.depth + self.amr_limit,
@@ -117,6 +122,66 @@ class PolyMesh2d:
             raise LpmxError(rc, "lpmx_mesh_divide_flagged_faces")
         self._fetch()
         return nd.value, oc.value
+
+    # ---- mesh queries (src/mesh/lpm_polymesh2d.hpp:262-552), host code like the mesh ----
+    def _index_list(self, fn, idx, name):
+        cap = 64
+        while True:
+            buf = np.empty(cap, dtype=np.int32)
+            n = ctypes.c_int()
+            rc = fn(self._m, int(idx), buf.ctypes.data, cap, ctypes.byref(n))
+            if rc:
+                raise LpmxError(rc, name)
+            if n.value <= cap:
+                return buf[:n.value].copy()
+            cap = n.value
+
+    def get_leaf_edges_from_parent(self, parent_edge):
+        return self._index_list(_lib.lib().lpmx_mesh_leaf_edges_from_parent, parent_edge, "lpmx_mesh_leaf_edges_from_parent")
+
+    def ccw_edges_around_face(self, face):
+        return self._index_list(_lib.lib().lpmx_mesh_ccw_edges_around_face, face, "lpmx_mesh_ccw_edges_around_face")
+
+    def ccw_adjacent_faces(self, face):
+        return self._index_list(_lib.lib().lpmx_mesh_ccw_adjacent_faces, face, "lpmx_mesh_ccw_adjacent_faces")
+
+    def neighbors_flag(self, flags, start=0, end=None):
+        """NeighborsFlag over faces [start, end): flags |= a neighbour is more than one level finer.  In place; returns the
+        number of newly set flags."""
+        f = np.ascontiguousarray(flags, dtype=np.uint8)
+        if f is not flags:
+            raise ValueError("flags must be a C-contiguous uint8 array (updated in place)")
+        n = ctypes.c_int()
+        rc = _lib.lib().lpmx_mesh_neighbors_flag(self._m, f.ctypes.data, int(start), int(self.n_faces if end is None else end),
+                                                 ctypes.byref(n))
+        if rc:
+            raise LpmxError(rc, "lpmx_mesh_neighbors_flag")
+        return n.value
+
+    def _locate(self, mode, pts, start=None):
+        self._push_coordinates()
+        p = np.ascontiguousarray(np.atleast_2d(np.asarray(pts, dtype=np.float64)))
+        if p.shape[1] != self.ndim:
+            raise ValueError(f"points must have {self.ndim} columns")
+        out = np.empty(p.shape[0], dtype=np.int32)
+        st = None if start is None else np.ascontiguousarray(np.broadcast_to(np.asarray(start, dtype=np.int32), (p.shape[0],)))
+        rc = _lib.lib().lpmx_mesh_locate(self._m, mode, p.ctypes.data, p.shape[0], None if st is None else st.ctypes.data,
+                                         out.ctypes.data)
+        if rc:
+            raise LpmxError(rc, "lpmx_mesh_locate")
+        return out
+
+    def locate_face_containing_pt(self, pts):
+        return self._locate(0, pts)
+
+    def locate_pt_walk_search(self, pts, face_start_idx):
+        return self._locate(1, pts, face_start_idx)
+
+    def locate_pt_tree_search(self, pts, root_face):
+        return self._locate(2, pts, root_face)
+
+    def nearest_root_face(self, pts):
+        return self._locate(3, pts)
 
     # names used by the reference's examples
     def n_vertices_host(self):

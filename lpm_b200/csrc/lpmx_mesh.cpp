@@ -450,9 +450,246 @@ long nedges_at(int seed, int lev) {
   return nverts_at(seed, lev) + nfaces_at(seed, lev) - (planar ? 1 : 2);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Mesh queries (src/mesh/lpm_polymesh2d.hpp:262-552), restated as coded.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxAmrLimit = 6;  // LPM_MAX_AMR_LIMIT (LpmConfig.h.in:19): bounds the reference's fixed-size index lists
+
+// PolyMesh2d::get_leaf_edges_from_parent (:277-308).  The reference makes room for the second kid with an ASCENDING copy
+// (edge_list[j + 1] = edge_list[j], j = i + 1 ...), which smears edge_list[i + 1] over every later entry when more than one
+// entry follows the divided edge (an edge refined three levels deeper on one side): replicated, the list is the contract.
+// The reference's list has 2 * LPM_MAX_AMR_LIMIT slots and no bounds check; this one grows instead of overflowing.
+void leaf_edges_from_parent(const lpmx_mesh_s& m, int parent, std::vector<int>& list) {
+  list.assign(1, parent);
+  int n_leaves = 1;
+  bool keep_going = m.edge_has_kids(parent);
+  while (keep_going) {
+    int n_new = 0;
+    keep_going = false;
+    for (int i = 0; i < n_leaves; ++i) {
+      if ((size_t)(n_leaves + 2) > list.size()) list.resize(n_leaves + 2, kNull);
+      if (m.edge_has_kids(list[i])) {
+        const int kid0 = m.ek[2 * list[i]], kid1 = m.ek[2 * list[i] + 1];
+        for (int j = i + 1; j < n_leaves; ++j) list[j + 1] = list[j];
+        list[i] = kid0;
+        list[i + 1] = kid1;
+        if (m.edge_has_kids(kid0) || m.edge_has_kids(kid1)) keep_going = true;
+        ++n_new;
+      }
+    }
+    n_leaves += n_new;
+  }
+  list.resize(n_leaves);
+}
+
+// PolyMesh2d::edge_is_positive (:262-265)
+inline bool edge_is_positive(const lpmx_mesh_s& m, int e, int f) { return f == m.el[e]; }
+
+// PolyMesh2d::ccw_edges_around_face (:316-340)
+void ccw_edges_around_face(const lpmx_mesh_s& m, int f, std::vector<int>& out) {
+  out.clear();
+  std::vector<int> leaves;
+  for (int i = 0; i < m.nfv; ++i) {
+    const int e = m.fedges[(size_t)m.nfv * f + i];
+    leaf_edges_from_parent(m, e, leaves);
+    if (edge_is_positive(m, e, f))
+      out.insert(out.end(), leaves.begin(), leaves.end());
+    else
+      out.insert(out.end(), leaves.rbegin(), leaves.rend());
+  }
+}
+
+// PolyMesh2d::ccw_adjacent_faces (:348-366); NULL_IND (-1) across a free boundary
+void ccw_adjacent_faces(const lpmx_mesh_s& m, int f, std::vector<int>& out) {
+  std::vector<int> le;
+  ccw_edges_around_face(m, f, le);
+  out.clear();
+  for (int e : le) out.push_back(edge_is_positive(m, e, f) ? m.er[e] : m.el[e]);
+}
+
+// Geo::distance: great-circle angle (lpm_geometry.hpp:470-475) / Euclidean (:62-67)
+inline double geo_distance(const lpmx_mesh_s& m, const double* a, const double* b) {
+  if (m.nd == 3) return sph_dist(a, b);
+  const double d0 = b[0] - a[0], d1 = b[1] - a[1];
+  return std::sqrt(d0 * d0 + d1 * d1);
+}
+
+// Geo::barycenter of a face's vertices at their current coordinates
+void face_vertex_barycenter(const lpmx_mesh_s& m, int f, double* out) {
+  double vs[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int k = 0; k < m.nfv; ++k) {
+    const int v = m.fverts[(size_t)m.nfv * f + k];
+    for (int c = 0; c < m.nd; ++c) vs[k][c] = m.vx[(size_t)m.nd * v + c];
+  }
+  m.geo_barycenter(out, vs, m.nfv);
+}
+
+// PolyMesh2d::nearest_root_face (:421-434): strict '<', first root face wins ties
+int nearest_root_face(const lpmx_mesh_s& m, const double* q, int n_roots) {
+  int result = 0;
+  double dist = geo_distance(m, q, &m.fx[0]);
+  for (int i = 1; i < n_roots; ++i) {
+    const double t = geo_distance(m, &m.fx[(size_t)m.nd * i], q);
+    if (t < dist) dist = t, result = i;
+  }
+  return result;
+}
+
+// PolyMesh2d::locate_pt_tree_search (:446-473): descend to the kid whose centre is closest
+int locate_pt_tree_search(const lpmx_mesh_s& m, const double* q, int root) {
+  int cur = root;
+  while (m.face_has_kids(cur)) {
+    int next = m.fkids[4 * (size_t)cur];
+    double dist = geo_distance(m, &m.fx[(size_t)m.nd * next], q);
+    for (int k = 1; k < 4; ++k) {
+      const int kid = m.fkids[4 * (size_t)cur + k];
+      const double t = geo_distance(m, q, &m.fx[(size_t)m.nd * kid]);
+      if (t < dist) next = kid, dist = t;
+    }
+    cur = next;
+  }
+  return cur;
+}
+
+// PolyMesh2d::pt_is_outside_mesh (:484-535), planar meshes only: closer to the mirror image of the face centroid across one
+// of the face's boundary edges than to the centroid itself
+bool pt_is_outside_mesh(const lpmx_mesh_s& m, const double* q, int f) {
+  if (m.nd != 2) return false;
+  std::vector<int> le;
+  ccw_edges_around_face(m, f, le);
+  bool any = false;
+  for (int e : le) any = any || m.el[e] == kNull || m.er[e] == kNull;
+  if (!any) return false;
+  double ctr[3];
+  face_vertex_barycenter(m, f, ctr);
+  const double intr = geo_distance(m, q, ctr);
+  bool result = false;
+  for (int e : le) {
+    if (!(m.el[e] == kNull || m.er[e] == kNull)) continue;
+    const double* o = &m.vx[2 * (size_t)m.eo[e]];
+    const double* d = &m.vx[2 * (size_t)m.ed[e]];
+    double qv[2] = {d[0] - o[0], d[1] - o[1]};
+    const double* v0 = o;
+    if (!edge_is_positive(m, e, f)) {
+      qv[0] = -qv[0], qv[1] = -qv[1];
+      v0 = d;
+    }
+    const double len = std::sqrt(qv[0] * qv[0] + qv[1] * qv[1]);  // PlaneGeometry::normalize (:45-50): scale by 1 / |v|
+    qv[0] *= 1.0 / len, qv[1] *= 1.0 / len;
+    const double pv[2] = {ctr[0] - v0[0], ctr[1] - v0[1]};
+    const double dotp = pv[0] * qv[0] + pv[1] * qv[1];
+    const double refl[3] = {ctr[0] - 2 * (pv[0] - dotp * qv[0]), ctr[1] - 2 * (pv[1] - dotp * qv[1]), 0.0};
+    if (geo_distance(m, q, refl) < intr) result = true;
+  }
+  return result;
+}
+
+// PolyMesh2d::locate_pt_walk_search (:377-413): the starting distance is to the face's stored centre, the neighbours are
+// judged by the barycentre of their vertices
+int locate_pt_walk_search(const lpmx_mesh_s& m, const double* q, int start) {
+  int result = start, cur = start;
+  double dist = geo_distance(m, q, &m.fx[(size_t)m.nd * cur]);
+  std::vector<int> adj;
+  bool keep_going = true;
+  while (keep_going) {
+    result = cur;
+    ccw_adjacent_faces(m, cur, adj);
+    for (int a : adj) {
+      if (a == kNull) continue;
+      double ctr[3];
+      face_vertex_barycenter(m, a, ctr);
+      const double t = geo_distance(m, ctr, q);
+      if (t < dist) dist = t, cur = a;
+    }
+    keep_going = cur != result;
+  }
+  return result;
+}
+
 }  // namespace
 
 extern "C" {
+
+int lpmx_mesh_leaf_edges_from_parent(lpmx_mesh_t m, int parent_edge, int* list, int cap, int* n) {
+  if (!m || !n || parent_edge < 0 || parent_edge >= m->ne() || cap < 0 || (cap > 0 && !list)) return LPMX_ERR_INVALID;
+  std::vector<int> v;
+  leaf_edges_from_parent(*m, parent_edge, v);
+  *n = (int)v.size();
+  for (int i = 0; i < *n && i < cap; ++i) list[i] = v[i];
+  return LPMX_OK;
+}
+
+int lpmx_mesh_ccw_edges_around_face(lpmx_mesh_t m, int face, int* list, int cap, int* n) {
+  if (!m || !n || face < 0 || face >= m->nf() || cap < 0 || (cap > 0 && !list)) return LPMX_ERR_INVALID;
+  std::vector<int> v;
+  ccw_edges_around_face(*m, face, v);
+  *n = (int)v.size();
+  for (int i = 0; i < *n && i < cap; ++i) list[i] = v[i];
+  return LPMX_OK;
+}
+
+int lpmx_mesh_ccw_adjacent_faces(lpmx_mesh_t m, int face, int* list, int cap, int* n) {
+  if (!m || !n || face < 0 || face >= m->nf() || cap < 0 || (cap > 0 && !list)) return LPMX_ERR_INVALID;
+  std::vector<int> v;
+  ccw_adjacent_faces(*m, face, v);
+  *n = (int)v.size();
+  for (int i = 0; i < *n && i < cap; ++i) list[i] = v[i];
+  return LPMX_OK;
+}
+
+// NeighborsFlag::operator() (src/mesh/lpm_refinement_flags.hpp:30-52) over faces [start, end)
+int lpmx_mesh_neighbors_flag(lpmx_mesh_t m, unsigned char* flags, int start, int end, int* n_flagged) {
+  if (!m || !flags || start < 0 || end < start || end > m->nf()) return LPMX_ERR_INVALID;
+  std::vector<int> adj;
+  int count = 0;
+  for (int i = start; i < end; ++i) {
+    ccw_adjacent_faces(*m, i, adj);
+    const int lev = m->flevel[i];
+    bool refine = false;
+    for (int a : adj) {
+      // across a free boundary the reference reads faces.level(-1) (out of bounds); no neighbour, no level here
+      if (a != kNull && m->flevel[a] > lev + 1) {
+        refine = true;
+        break;
+      }
+    }
+    if (refine && !flags[i]) ++count;
+    flags[i] = (flags[i] || refine) ? 1 : 0;
+  }
+  if (n_flagged) *n_flagged = count;
+  return LPMX_OK;
+}
+
+int lpmx_mesh_locate(lpmx_mesh_t m, int mode, const double* pts, int n_pts, const int* start, int* out) {
+  if (!m || n_pts < 0 || (n_pts > 0 && (!pts || !out)) || m->nf() == 0) return LPMX_ERR_INVALID;
+  if ((mode == LPMX_LOCATE_WALK || mode == LPMX_LOCATE_TREE) && n_pts > 0 && !start) return LPMX_ERR_INVALID;
+  SeedDesc d;
+  if (!seed_desc(m->seed, &d)) return LPMX_ERR_INVALID;
+  for (int i = 0; i < n_pts; ++i) {
+    const double* q = pts + (size_t)m->nd * i;
+    switch (mode) {
+      case LPMX_LOCATE_CONTAINING: {  // PolyMesh2d::locate_face_containing_pt (:541-552)
+        const int leaf = locate_pt_tree_search(*m, q, nearest_root_face(*m, q, d.nfaces));
+        out[i] = pt_is_outside_mesh(*m, q, leaf) ? kNull : locate_pt_walk_search(*m, q, leaf);
+        break;
+      }
+      case LPMX_LOCATE_WALK:
+        if (start[i] < 0 || start[i] >= m->nf() || m->face_has_kids(start[i])) return LPMX_ERR_INVALID;  // leaf-only (:382)
+        out[i] = locate_pt_walk_search(*m, q, start[i]);
+        break;
+      case LPMX_LOCATE_TREE:
+        if (start[i] < 0 || start[i] >= m->nf()) return LPMX_ERR_INVALID;
+        out[i] = locate_pt_tree_search(*m, q, start[i]);
+        break;
+      case LPMX_LOCATE_NEAREST_ROOT:
+        out[i] = nearest_root_face(*m, q, d.nfaces);
+        break;
+      default:
+        return LPMX_ERR_INVALID;
+    }
+  }
+  return LPMX_OK;
+}
 
 int lpmx_mesh_max_allocations(int seed, int depth, int* n_verts, int* n_edges, int* n_faces) {
   SeedDesc d;
