@@ -93,6 +93,40 @@ def test_gather_scatter_restatement_round_trip():
     assert np.array_equal(v2, vd) and np.array_equal(f2[leaf], fd[leaf]) and (f2[~leaf] == -1.0).all()
 
 
+def _reference_gather_scatter_scenario(gather, scatter, m):
+    """tests/lpm_gather_scatter_mesh_tests.cpp:38-125: every vertex and face carries 2, the gathered copy is set to 3 and
+    scattered back -> every vertex and every LEAF holds 3, every divided face still 2; the gathered points are
+    n_vertices + n_leaves and no two of them coincide."""
+    vert, face = np.full(m.n_verts, 2.0), np.full(m.n_faces, 2.0)
+    g = gather(vert, face, m.face_mask)
+    assert g.shape[0] == m.n_verts + m.n_face_leaves                       # :61
+    x = gather(m.vert_xyz, m.face_xyz, m.face_mask)
+    d2 = ((x[:, None, :] - x[None, :, :]) ** 2).sum(axis=2) + np.eye(x.shape[0])
+    assert (d2 > 0).all()                                                  # :63-89 n_duplicates == 0
+    vert, face = scatter(np.full_like(g, 3.0), vert, face, m.face_mask)
+    assert (vert == 3.0).sum() == m.n_verts                                # :103
+    assert (face == 3.0).sum() == m.n_face_leaves                          # :124
+    assert (face == 2.0).sum() == m.n_faces - m.n_face_leaves              # :125
+
+
+@pytest.mark.parametrize("seed", ["cubed", "icos", "quad_rect"])
+def test_reference_gather_scatter_scenario_on_the_restatement(seed):
+    m = PolyMesh2d(seed, 2)
+    _reference_gather_scatter_scenario(GO.gather, lambda g, v, f, mask: GO.scatter(g, v.shape[0], mask, f.copy()), m)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", ["cubed", "icos"])
+def test_gpu_reference_gather_scatter_scenario(engine, seed):
+    m = PolyMesh2d(seed, 2)
+
+    def scatter(g, v, f, mask):
+        vo, fo = v.copy(), f.copy()
+        engine.scatter_mesh_data(g, vo, fo, mask)
+        return vo, fo
+    _reference_gather_scatter_scenario(engine.gather_mesh_data, scatter, m)
+
+
 def test_interpolation_core_matches_numpy_and_converges():
     """Remesh interpolation (ScalarPointEvaluation at new particles): host build of the product arithmetic against the
     numpy restatement, five fields at once (two batches of kInterpFields = 4), and convergence to the exact values."""

@@ -191,3 +191,10 @@ def test_ic2d_totals_and_err_norms_match_host_formulas(engine, meshes):
     assert np.isclose(ens1, 0.5 * (az ** 2 * a)[leaf].sum(), rtol=1e-13)
     assert abs(ke1 - ke0) / ke0 < 1e-2 and abs(ens1 - ens0) / ens0 < 1e-3  # near-conservation over 3 steps
     s.close()
+
+
+def test_reference_error_norm_known_answer(engine):
+    """tests/lpm_error_unit_tests.cpp:21-33: 300 points, exact = 1, approximation = 1.001, unit weights -> every norm 0.001."""
+    exact, appx = np.ones(300), np.full(300, 1.001)
+    l1, l2, linf = engine.err_norms(appx - exact, exact, np.ones(300))
+    assert l1 == pytest.approx(0.001) and l2 == pytest.approx(0.001) and linf == pytest.approx(0.001)
