@@ -20,87 +20,37 @@
 // sums differ from the stream-K kernel's by round-off only (the tolerance of every parity test covers both).
 #include <cstdlib>
 
+#include "lpmx_const_stream_body.h"
 #include "lpmx_internal.h"
 
 namespace lpmx {
 
 namespace {
 
-constexpr int kCsHalf = 640;  // records per half of the bank
-constexpr int kCsRec = 6;     // doubles per record
+using cs::CsArgs;
+constexpr int kCsHalf = cs::kHalf;  // records per half of the bank
+constexpr int kCsRec = cs::kRec;    // doubles per record
 constexpr int kCsMaxThreads = 384;
 __constant__ double c_src[2 * kCsHalf * kCsRec];  // 61 440 B of the 64 KB bank
 
-__device__ __forceinline__ double cs_rcp_seed(double d) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-  return r;
-}
-
-struct CsArgs {
-  Vec3View tgt;         // this launch's targets, indexed from 0
-  const int* self_idx;  // compact source index of each target's own particle, or -1 (may be null)
-  double* acc;          // [3][n_tgt_pad]
-  long n_tgt_pad;
-  int n_tgt;
-  int half;   // which half of the bank this launch reads
-  int j0;     // compact index of the half's first record
-  int first;  // start from zero instead of the stored accumulators
-  double kappa;
-};
-
-template <int T, bool CHECK>
-__device__ __forceinline__ void cs_loop(const double (&x)[T][3], const int (&self)[T], double (&acc)[T][3], int base, int j0,
-                                        double kappa) {
-#pragma unroll 2
-  for (int j = 0; j < kCsHalf; ++j) {
-    const double s0 = c_src[base + kCsRec * j], s1 = c_src[base + kCsRec * j + 1], s2 = c_src[base + kCsRec * j + 2];
-    const double s3 = c_src[base + kCsRec * j + 3], s4 = c_src[base + kCsRec * j + 4], s5 = c_src[base + kCsRec * j + 5];
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-      const double d = fma(-x[t][0], s0, fma(-x[t][1], s1, fma(-x[t][2], s2, kappa)));
-      const double r0 = cs_rcp_seed(d);
-      const double e = fma(-d, r0, 1.0);
-      const double p = fma(e, e, e);
-      double r = fma(r0, p, r0);
-      if (CHECK) r = (j0 + j == self[t]) ? 0.0 : r;
-      acc[t][0] = fma(r, s3, acc[t][0]);
-      acc[t][1] = fma(r, s4, acc[t][1]);
-      acc[t][2] = fma(r, s5, acc[t][2]);
-    }
+// the kernel body's platform on the GPU (lpmx_const_stream_body.h)
+struct CsDevice {
+  __device__ __forceinline__ int tid() const { return threadIdx.x; }
+  __device__ __forceinline__ int bid() const { return blockIdx.x; }
+  __device__ __forceinline__ int n_threads() const { return blockDim.x; }
+  __device__ __forceinline__ bool any_sync(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
+  __device__ __forceinline__ double src(int i) const { return c_src[i]; }  // warp-uniform index: LDCU, uniform-register operand
+  __device__ __forceinline__ double rcp_seed(double d) const {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    return r;
   }
-}
+};
 
 template <int T>
 __global__ void __launch_bounds__(kCsMaxThreads, 1) pair_sum_const_kernel(const CsArgs a) {
-  const int lanes = blockDim.x;
-  const long base_t = (long)blockIdx.x * ((long)T * lanes) + threadIdx.x;
-  double x[T][3], acc[T][3];
-  int self[T];
-  bool hit = false;
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    const long tg = base_t + (long)t * lanes;  // < n_tgt_pad by construction of the grid
-    const bool valid = tg < a.n_tgt;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      x[t][k] = valid ? a.tgt(tg, k) : 0.0;  // a zero target sees d = kappa: finite, never stored anywhere that is read
-      acc[t][k] = a.first ? 0.0 : a.acc[(long)k * a.n_tgt_pad + tg];
-    }
-    self[t] = (valid && a.self_idx) ? a.self_idx[tg] : -1;
-    hit |= (unsigned)(self[t] - a.j0) < (unsigned)kCsHalf;
-  }
-  const int base = a.half * (kCsHalf * kCsRec);
-  if (__any_sync(0xffffffffu, hit))
-    cs_loop<T, true>(x, self, acc, base, a.j0, a.kappa);
-  else
-    cs_loop<T, false>(x, self, acc, base, a.j0, a.kappa);
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    const long tg = base_t + (long)t * lanes;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) a.acc[(long)k * a.n_tgt_pad + tg] = acc[t][k];
-  }
+  CsDevice pf;
+  cs::body<T>(pf, a);
 }
 
 // packed 64-byte records -> 48-byte records, zero-padded to whole halves
@@ -241,7 +191,9 @@ int launch_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const i
     if (n_batches > 1) LPMX_TRY(copy_batch(1));
   }
   CsArgs a;
-  a.tgt = tgt;
+  a.tgt = tgt.p;
+  a.tgt_si = tgt.si;
+  a.tgt_sk = tgt.sk;
   a.self_idx = self_idx;
   a.acc = partials;
   a.n_tgt_pad = p.n_tgt_pad;

@@ -41,6 +41,19 @@ def test_shape_rejects_bad_arguments():
     assert _lib.lib().lpmx_const_stream_shape(148, 0, ctypes.byref(T), ctypes.byref(T), ctypes.byref(T)) != 0
 
 
+def test_kernel_body_host_model(tmp_path):
+    """The body of pair_sum_const_kernel (lpmx_const_stream_body.h) run on the host, one loop iteration per CUDA thread, around
+    a restatement of the launch sequence (640-record batches, alternating halves, zero padding, `first`): T = 4..8, ragged
+    target counts, both target layouts, collocated self-pair exclusion -- equal to a direct double loop."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "const_stream_model")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I", os.path.join(root, "lpm_b200", "csrc"),
+                    os.path.join(root, "tests", "cpp", "const_stream_model.cpp"), "-o", exe], check=True)
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.count(" ok") == 6 and "FAILED" not in p.stdout, p.stdout + p.stderr
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("seed,depth", [("icos", 4), ("cubed", 5)])
