@@ -162,3 +162,44 @@ def test_planar_tree_invariants(seed):
     assert (cr > 0).all()
     # Lagrangian == physical at build time
     assert np.array_equal(m.vert_xyz, m.vert_lag_xyz) and np.array_equal(m.face_xyz, m.face_lag_xyz)
+
+
+_REF_GEO = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "liblpm_ref_geometry.so")
+
+
+@pytest.mark.skipif(not os.path.exists(_REF_GEO), reason="oracle/_ref/liblpm_ref_geometry.so not built (needs /root/reference)")
+@pytest.mark.parametrize("seed,depth", [("cubed", 0), ("icos", 0), ("cubed", 3), ("icos", 3), ("quad_rect", 2), ("tri_hex", 2)])
+def test_generator_geometry_equals_reference_functions_compiled_in_place(seed, depth):
+    """The reference's own Geo::polygon_area / barycenter / midpoint (src/lpm_geometry.hpp, compiled in place without FMA
+    contraction: oracle/ref_geometry_driver.cpp) evaluated on the generator's vertices: every leaf area, every face centre
+    created by a division and every edge midpoint equal the generator's values BIT FOR BIT.  (The seed faces' centres are
+    read from the seed file, not computed.)"""
+    import ctypes
+    L = ctypes.CDLL(_REF_GEO)
+    d, dp = ctypes.c_double, ctypes.POINTER(ctypes.c_double)
+    L.ref_sphere_polygon_area.restype = d
+    L.ref_plane_polygon_area.restype = d
+
+    def P(a):
+        return np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(dp)
+    m = PolyMesh2d(seed, depth)
+    sph = m.ndim == 3
+    area_fn = L.ref_sphere_polygon_area if sph else L.ref_plane_polygon_area
+    ctr_fn = L.ref_sphere_barycenter if sph else L.ref_plane_barycenter
+    mid_fn = L.ref_sphere_midpoint if sph else L.ref_plane_midpoint
+    n_checked = 0
+    for f in np.nonzero(m.face_mask == 0)[0]:
+        vs = np.ascontiguousarray(m.vert_xyz[m.face_verts[f]])
+        ctr = np.ascontiguousarray(m.face_xyz[f])
+        assert area_fn(P(ctr), P(vs), len(vs)) == m.face_area[f]
+        if m.face_parent[f] >= 0:
+            out = np.zeros(m.ndim)
+            ctr_fn(P(out), P(vs), len(vs))
+            assert np.array_equal(out, ctr)
+            n_checked += 1
+    for e in np.nonzero(m.edge_kids[:, 0] > 0)[0]:
+        out = np.zeros(m.ndim)
+        mid_fn(P(out), P(m.vert_xyz[m.edge_origs[e]]), P(m.vert_xyz[m.edge_dests[e]]))
+        assert np.array_equal(out, m.vert_xyz[m.edge_dests[m.edge_kids[e][0]]])
+        n_checked += 1
+    assert n_checked > 0 or depth == 0
