@@ -198,15 +198,20 @@ int scan_leaves(lpmx_handle_t h, const unsigned char* mask_dev, int n, int* leaf
 }
 
 // ------------------------------------------------------------------------------------------------
-// FP64 peak probe: 8 independent DFMA chains per thread, no memory traffic
+// FP64 peak probe: 8 independent DFMA chains per thread, no memory traffic.  v = fma(v, a, v) with `a` a kernel
+// parameter: SASS `DFMA R, R, c[0x0][..], R` -- ONE distinct register operand per instruction, the multiplier from the
+// constant bank (profiles/r1b_fp64_pipe_probe.txt: 98 % of 64 lanes/clk/SM; operands served by the register reuse cache
+// already cost ~8 %, which is what the round-1 probe `fma(v, a, b)` with a, b in registers measured: 34.2 TFLOP/s).  The
+// trip loop is unrolled 16 times (3 loop instructions per 128 DFMAs).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dfma_probe_kernel(double* out, int iters, double a, double b) {
+__global__ void __launch_bounds__(256) dfma_probe_kernel(double* out, int iters, double a) {
   double v[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) v[k] = 1.0 + 1e-9 * (threadIdx.x + k);
+#pragma unroll 16
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = fma(v[k], a, b);
+    for (int k = 0; k < 8; ++k) v[k] = fma(v[k], a, v[k]);
   }
   double s = 0;
 #pragma unroll
@@ -224,7 +229,7 @@ int fp64_probe(lpmx_handle_t h, double* tflops, double* ms_out) {
   double best = 1e30;
   for (int rep = 0; rep < 12; ++rep) {  // the first launches also ramp the SM clock up from idle
     LPMX_CUDA(h, cudaEventRecord(e0, h->stream));
-    dfma_probe_kernel<<<blocks, threads, 0, h->stream>>>((double*)d, iters, 0.999999, 1e-7);
+    dfma_probe_kernel<<<blocks, threads, 0, h->stream>>>((double*)d, iters, 0x1p-60);
     ++h->launches;
     LPMX_CUDA(h, cudaEventRecord(e1, h->stream));
     LPMX_CUDA(h, cudaEventSynchronize(e1));

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <initializer_list>
 #include <limits>
 #include <string>
 #include <type_traits>
@@ -142,6 +143,9 @@ struct StaticExt<T[N]> {
 };
 }  // namespace Impl
 
+template <class T>
+struct Slice1;
+
 template <class DataType, class... Props>
 class View {
  public:
@@ -181,6 +185,23 @@ class View {
     }
     own_ = o.owner();
     ptr_ = const_cast<non_const_value_type*>(o.data());
+    strides();
+  }
+
+  // rows [r.first, r.second) of another view: View(v, pair) / View(v, pair, ALL) as Kokkos' subview constructor
+  template <class OT, class... OP, class I>
+  View(const View<OT, OP...>& o, std::pair<I, I> r) : View(o) {
+    ptr_ += (std::size_t)r.first * s0_;
+    ext_[0] = (std::size_t)(r.second - r.first);
+  }
+  template <class OT, class... OP, class I>
+  View(const View<OT, OP...>& o, std::pair<I, I> r, ALL_t) : View(o, r) {}
+  // a row of a rank-2 view, as an unmanaged rank-1 view
+  template <class ST>
+  View(const Slice1<ST>& sl) {
+    init_static();
+    ext_[0] = sl.n;
+    ptr_ = const_cast<non_const_value_type*>(sl.p);
     strides();
   }
 
@@ -260,22 +281,30 @@ KOKKOS_INLINE_FUNCTION Slice1<typename View<D, P...>::value_type> subview(const 
   return {v.data() + (std::size_t)i * v.extent(1), v.extent(1)};
 }
 template <class D, class... P, class I>
-KOKKOS_INLINE_FUNCTION View<D, P...> subview(const View<D, P...>& v, std::pair<I, I>, ALL_t) {
-  return v;  // full-range subviews only (the reference passes (0, n))
+KOKKOS_INLINE_FUNCTION View<D, P...> subview(const View<D, P...>& v, std::pair<I, I> r, ALL_t) {
+  return View<D, P...>(v, r);
 }
 template <class D, class... P, class I>
-KOKKOS_INLINE_FUNCTION View<D, P...> subview(const View<D, P...>& v, std::pair<I, I>) {
-  return v;
+KOKKOS_INLINE_FUNCTION View<D, P...> subview(const View<D, P...>& v, std::pair<I, I> r) {
+  return View<D, P...>(v, r);
 }
 
 template <class V>
 typename V::HostMirror create_mirror_view(const V& v) {
   return v;
 }
-template <class A, class B>
+template <class A, class B, typename std::enable_if<!std::is_arithmetic<B>::value, int>::type = 0>
 void deep_copy(const A& dst, const B& src) {
   if ((const void*)dst.data() != (const void*)src.data())
     std::memcpy((void*)dst.data(), (const void*)src.data(), dst.size() * sizeof(typename A::value_type));
+}
+template <class A, class B, typename std::enable_if<std::is_arithmetic<B>::value, int>::type = 0>
+void deep_copy(const A& dst, const B& value) {
+  for (std::size_t k = 0; k < dst.size(); ++k) dst.data()[k] = (typename A::value_type)value;
+}
+template <class V>
+typename V::HostMirror create_mirror(const V& v) {
+  return v;
 }
 
 // ---- policies ----------------------------------------------------------------------------------
@@ -387,6 +416,101 @@ void parallel_reduce(I n, const F& f, Max<T> red) {
   T acc = std::numeric_limits<T>::lowest();
   for (long j = 0; j < (long)n; ++j) f((int)j, acc);
   red.ref = acc;
+}
+
+template <class I, class F, class T, typename std::enable_if<std::is_integral<I>::value, int>::type = 0>
+void parallel_reduce(const std::string&, I n, const F& f, Max<T> red) {
+  parallel_reduce(n, f, red);
+}
+template <class T>
+struct Min {
+  T& ref;
+  explicit Min(T& r) : ref(r) {}
+};
+template <class I, class F, class T, typename std::enable_if<std::is_integral<I>::value, int>::type = 0>
+void parallel_reduce(I n, const F& f, Min<T> red) {
+  T acc = std::numeric_limits<T>::max();
+  for (long j = 0; j < (long)n; ++j) f((int)j, acc);
+  red.ref = acc;
+}
+template <class I, class F, class T, typename std::enable_if<std::is_integral<I>::value, int>::type = 0>
+void parallel_reduce(const std::string&, I n, const F& f, Min<T> red) {
+  parallel_reduce(n, f, red);
+}
+template <class T>
+struct MinMaxScalar {
+  T min_val, max_val;
+};
+template <class T>
+struct MinMax {
+  using value_type = MinMaxScalar<T>;
+  value_type& ref;
+  explicit MinMax(value_type& r) : ref(r) {}
+};
+template <class I, class F, class T, typename std::enable_if<std::is_integral<I>::value, int>::type = 0>
+void parallel_reduce(I n, const F& f, MinMax<T> red) {
+  MinMaxScalar<T> acc{std::numeric_limits<T>::max(), std::numeric_limits<T>::lowest()};
+  for (long j = 0; j < (long)n; ++j) f((int)j, acc);
+  red.ref = acc;
+}
+template <class I, class F, class T, typename std::enable_if<std::is_integral<I>::value, int>::type = 0>
+void parallel_reduce(const std::string&, I n, const F& f, MinMax<T> red) {
+  parallel_reduce(n, f, red);
+}
+
+// MDRangePolicy<Rank<2>>({b0, b1}, {e0, e1}) with a sum reduction (host diagnostics: nan counts), row-major, sequential
+template <int N>
+struct Rank {
+  static constexpr int rank = N;
+};
+template <class R>
+struct MDRangePolicy {
+  long b[3], e[3];
+  MDRangePolicy(std::initializer_list<long> lo, std::initializer_list<long> hi) {
+    int k = 0;
+    for (long v : lo) b[k++] = v;
+    k = 0;
+    for (long v : hi) e[k++] = v;
+  }
+};
+template <class R, class F, class V>
+void parallel_reduce(const MDRangePolicy<R>& pol, const F& f, V& result) {
+  V acc = V();
+  for (long i = pol.b[0]; i < pol.e[0]; ++i)
+    for (long j = pol.b[1]; j < pol.e[1]; ++j) f((int)i, (int)j, acc);
+  result = acc;
+}
+template <class R, class F, class V>
+void parallel_reduce(const std::string&, const MDRangePolicy<R>& pol, const F& f, V& result) {
+  parallel_reduce(pol, f, result);
+}
+template <class R, class F>
+void parallel_for(const MDRangePolicy<R>& pol, const F& f) {
+  for (long i = pol.b[0]; i < pol.e[0]; ++i)
+    for (long j = pol.b[1]; j < pol.e[1]; ++j) f((int)i, (int)j);
+}
+template <class R, class F>
+void parallel_for(const std::string&, const MDRangePolicy<R>& pol, const F& f) {
+  parallel_for(pol, f);
+}
+
+// exclusive/inclusive scan protocol of Kokkos: f(i, partial, is_final), sequential here
+template <class I, class F, class V, typename std::enable_if<std::is_integral<I>::value, int>::type = 0>
+void parallel_scan(const std::string&, I n, const F& f, V& result) {
+  V acc = V();
+  for (long j = 0; j < (long)n; ++j) f((int)j, acc, true);
+  result = acc;
+}
+template <class I, class F, typename std::enable_if<std::is_integral<I>::value, int>::type = 0>
+void parallel_scan(const std::string&, I n, const F& f) {
+  long long acc = 0;
+  (void)acc;
+  int a = 0;
+  for (long j = 0; j < (long)n; ++j) f((int)j, a, true);
+}
+template <class I, class F, class V, typename std::enable_if<std::is_integral<I>::value, int>::type = 0>
+void parallel_scan(I n, const F& f, V& result) {
+  parallel_scan(std::string(), n, f, result);
 }
 
 inline void initialize(int&, char**) {}

@@ -120,6 +120,42 @@ void oracle_bve_velocity_ld(int n_tgt, const double* tx, int n_src, const double
   }
 }
 
+/* BVEFaceVelocity (collocated) for a SUBSET of the targets: row k of vel is the velocity at particle idx[k], summed over all
+ * unmasked sources j != idx[k].  Lets the synthetic N = 1e6 configuration meet the reference arithmetic on a sample. */
+void oracle_bve_velocity_subset(int n_idx, const int* idx, int n_src, const double* sx, const double* zeta, const double* area,
+                                const uint8_t* mask, double* vel) {
+#pragma omp parallel for schedule(static)
+  for (int k = 0; k < n_idx; ++k) {
+    const int i = idx[k];
+    double acc[3] = {0, 0, 0};
+    for (int j = 0; j < n_src; ++j) {
+      double u[3] = {0, 0, 0};
+      if (!mask[j] && i != j) biot_savart(u, sx + 3 * i, sx + 3 * j, zeta[j], area[j]);
+      for (int c = 0; c < 3; ++c) acc[c] += u[c];
+    }
+    for (int c = 0; c < 3; ++c) vel[3 * k + c] = acc[c];
+  }
+}
+void oracle_bve_velocity_subset_ld(int n_idx, const int* idx, int n_src, const double* sx, const double* zeta,
+                                   const double* area, const uint8_t* mask, double* vel) {
+  const long double four_pi = 4 * 3.14159265358979323846264338327950288L;
+#pragma omp parallel for schedule(static)
+  for (int k = 0; k < n_idx; ++k) {
+    const int i = idx[k];
+    long double acc[3] = {0, 0, 0};
+    const long double x0 = sx[3 * i], x1 = sx[3 * i + 1], x2 = sx[3 * i + 2];
+    for (int j = 0; j < n_src; ++j) {
+      if (mask[j] || i == j) continue;
+      const long double y0 = sx[3 * j], y1 = sx[3 * j + 1], y2 = sx[3 * j + 2];
+      const long double s = -(long double)zeta[j] * area[j] / (four_pi * (1 - (x0 * y0 + x1 * y1 + x2 * y2)));
+      acc[0] += (x1 * y2 - x2 * y1) * s;
+      acc[1] += (x2 * y0 - x0 * y2) * s;
+      acc[2] += (x0 * y1 - x1 * y0) * s;
+    }
+    for (int c = 0; c < 3; ++c) vel[3 * k + c] = (double)acc[c];
+  }
+}
+
 /* KokkosBlas::scal(r, a, x): r = a*x ; KokkosBlas::update(alpha, x, beta, y, gamma, z):
  * z = gamma*z + alpha*x + beta*y  (KokkosKernels 4.7 semantics; call sites cited below). */
 static void blas_scal(long n, double* r, double a, const double* x) {

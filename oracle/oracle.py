@@ -68,6 +68,19 @@ def bve_velocity(tgt_xyz, src_xyz, vort, area, mask, collocated=False, long_doub
     return out
 
 
+def bve_velocity_subset(idx, xyz, vort, area, mask, long_double=False, L=None):
+    """Collocated velocity (BVEFaceVelocity) at the particles idx only: all unmasked sources j != idx[k]."""
+    L = L or lib()
+    xyz, vort, area = _d(xyz), _d(vort), _d(area)
+    mask, mp = _m(mask)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    out = np.zeros((idx.shape[0], 3))
+    f = L.oracle_bve_velocity_subset_ld if long_double else L.oracle_bve_velocity_subset
+    f(ctypes.c_int(idx.shape[0]), idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), ctypes.c_int(xyz.shape[0]), _p(xyz),
+      _p(vort), _p(area), mp, _p(out))
+    return out
+
+
 def bve_streamfn(tgt_xyz, src_xyz, vort, area, mask, collocated=False, L=None):
     L = L or lib()
     src_xyz, vort, area = _d(src_xyz), _d(vort), _d(area)

@@ -71,6 +71,21 @@ void oracle_bve_velocity(int n_tgt, const double* tx, int n_src, const double* s
   }
 }
 
+// BVEFaceVelocity (the collocated functor, lpm_bve_sphere_kernels.hpp:365-394) run for a subset of its league: the functor is
+// the reference's, only the set of league ranks it is called with is chosen here.  Row k of vel = velocity at particle idx[k].
+void oracle_bve_velocity_subset(int n_idx, const int* idx, int n_src, const double* sx, const double* zeta, const double* area,
+                                const uint8_t* mask, double* vel) {
+  Mask fm(mask, n_src);
+  crd fx = wrap3(sx, n_src);
+  scalar_view_type fz = wrap1(zeta, n_src), fa = wrap1(area, n_src);
+  vec u("subset velocity", n_src);
+  BVEFaceVelocity f(u, fx, fz, fa, fm.v, n_src);
+#pragma omp parallel for schedule(static)
+  for (int k = 0; k < n_idx; ++k) f(Kokkos::TeamMember{idx[k]});
+  for (int k = 0; k < n_idx; ++k)
+    for (int c = 0; c < 3; ++c) vel[3 * k + c] = u(idx[k], c);
+}
+
 void oracle_bve_streamfn(int n_tgt, const double* tx, int n_src, const double* sx, const double* zeta,
                          const double* area, const uint8_t* mask, int collocated, double* psi) {
   Mask fm(mask, n_src);

@@ -70,3 +70,15 @@ def field_rel_err(a, b, sel=None):
     if den == 0.0:
         return 0.0 if num == 0.0 else np.inf
     return num / den
+
+
+def check_err(name, err, tol):
+    """assert err <= tol, and append the observed error to $LPMX_PARITY_LOG (one JSON object per line) when that variable is
+    set: the GPU visits collect the table of measured parity errors this way (profiles/r2*_parity_errors.jsonl)."""
+    path = os.environ.get("LPMX_PARITY_LOG")
+    if path:
+        import json
+        test = os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0]
+        with open(path, "a") as f:
+            f.write(json.dumps({"test": test, "quantity": name, "err": float(err), "tol": float(tol)}) + "\n")
+    assert err <= tol, (name, err, tol)

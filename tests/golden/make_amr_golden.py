@@ -1,6 +1,9 @@
-"""Regenerate tests/golden/mesh_amr_*.npz: adaptively refined meshes from the independent Python replay of
-PolyMesh2d::divide_flagged_faces (oracle/mesh_oracle.py), driven by the reference's seed files.  Run in the build container:
+"""Regenerate tests/golden/mesh_amr_*.npz: adaptively refined meshes from the REFERENCE ITSELF --
+PolyMesh2d<Seed>::divide_flagged_faces of /root/reference/src/mesh compiled in place (oracle/ref_mesh_driver.cpp ->
+oracle/_ref/liblpm_ref_mesh.so, binding oracle/ref_mesh.py).  Run in the build container:
     python tests/golden/make_amr_golden.py
+(Round 1 used the Python replay oracle/mesh_oracle.py; the compiled reference reproduces every array and every
+(refine_count, outcome) of those files bit for bit, so the files did not change.)
 Each file holds the flag arrays of every refinement pass (so a test can replay them through the product's generator), the
 (refine_count, outcome) of every pass and all mesh arrays after the last pass.
 
@@ -18,7 +21,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from oracle import mesh_oracle, refinement_oracle  # noqa: E402
+from oracle import ref_mesh, refinement_oracle  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -37,8 +40,9 @@ def gaussian_vortex(xyz):
 
 
 def run_case(seed, depth, kind, amr_buffer, amr_limit, passes):
-    m = mesh_oracle.TreeMesh(seed, depth)
+    m = ref_mesh.RefMesh(seed, depth, 1.0, amr_buffer, amr_limit)
     nmax = nmaxfaces(seed, depth + amr_buffer)
+    assert m.counts()["nmaxfaces"] == nmax
     out = {"seed": seed, "depth": depth, "amr_buffer": amr_buffer, "amr_limit": amr_limit, "nmaxfaces": nmax}
     rng = np.random.default_rng(20261017)
     start, tol = 0, None
@@ -54,10 +58,13 @@ def run_case(seed, depth, kind, amr_buffer, amr_limit, passes):
         else:
             flags = ((rng.random(n) < (0.35 if it < 2 else 0.9)) & (a["face_mask"] == 0)).astype(np.uint8)
         out[f"flags_{it}"] = flags
-        results.append(m.divide_flagged_faces(flags, nmax, amr_limit))
+        results.append(m.divide_flagged_faces(flags))
         start = n
     out["results"] = np.array(results, dtype=np.int32)
-    out.update(m.arrays())
+    a = m.arrays()
+    a.pop("face_crd_idx")
+    out.update(a)
+    m.close()
     return out
 
 

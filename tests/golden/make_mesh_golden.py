@@ -1,8 +1,12 @@
-"""Regenerate tests/golden/mesh_*.npz from the reference's seed files with the independent Python mesh
-restatement (oracle/mesh_oracle.py).  Run in the build container (needs /root/reference/mesh_seeds):
+"""Regenerate tests/golden/mesh_*.npz from the REFERENCE ITSELF: PolyMesh2d<Seed>(PolyMeshParameters(depth, radius))
+of /root/reference/src/mesh compiled in place (oracle/ref_mesh_driver.cpp -> oracle/_ref/liblpm_ref_mesh.so, `make -C oracle
+ref`; binding oracle/ref_mesh.py).  Run in the build container (needs /root/reference):
     python tests/golden/make_mesh_golden.py
-Also writes tests/golden/seed_tables.npz (the parsed .dat files) so the embedded seed tables can be checked
-without the reference mount."""
+Round 1 generated these files with the Python replay oracle/mesh_oracle.py; the compiled reference reproduces every array
+of every file bit for bit (integers and coordinates), so the files did not change when the generator did -- the replay is
+now just a second witness (tests/test_mesh.py compares all three).
+Also writes tests/golden/seed_tables.npz (the reference's mesh_seeds/*.dat as its own MeshSeed parsed them: the depth-0 mesh)
+so the embedded seed tables can be checked without the reference mount."""
 import os
 import sys
 
@@ -10,7 +14,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from oracle import mesh_oracle  # noqa: E402
+from oracle import ref_mesh  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CASES = [("icos", 0), ("icos", 1), ("icos", 2), ("icos", 3), ("cubed", 0), ("cubed", 1), ("cubed", 2), ("cubed", 3),
@@ -19,22 +23,32 @@ CASES = [("icos", 0), ("icos", 1), ("icos", 2), ("icos", 3), ("cubed", 0), ("cub
 # radius 6 the default of examples/plane_gravity_wave.cpp
 PLANE_CASES = [("quad_rect", 0, 1.0), ("quad_rect", 2, 1.0), ("quad_rect", 3, 4.0), ("quad_rect", 4, 6.0),
                ("tri_hex", 0, 1.0), ("tri_hex", 2, 1.0), ("tri_hex", 3, 6.0)]
+KEYS = ["vert_xyz", "vert_lag_xyz", "edge_origs", "edge_dests", "edge_lefts", "edge_rights", "edge_parents", "edge_kids",
+        "face_xyz", "face_lag_xyz", "face_area", "face_mask", "face_verts", "face_edges", "face_parent", "face_kids",
+        "face_level", "face_leaf_idx"]
+
+
+def mesh_arrays(seed, depth, radius=1.0):
+    m = ref_mesh.RefMesh(seed, depth, radius)
+    a = m.arrays()
+    m.close()
+    return {k: a[k] for k in KEYS}
+
 
 if __name__ == "__main__":
     for seed, depth in CASES:
-        m = mesh_oracle.TreeMesh(seed, depth)
-        np.savez_compressed(os.path.join(HERE, f"mesh_{seed}_{depth}.npz"), **m.arrays())
-        print(seed, depth, len(m.vx), len(m.eo), len(m.fx))
+        a = mesh_arrays(seed, depth)
+        np.savez_compressed(os.path.join(HERE, f"mesh_{seed}_{depth}.npz"), **a)
+        print(seed, depth, len(a["vert_xyz"]), len(a["edge_origs"]), len(a["face_xyz"]))
     for seed, depth, radius in PLANE_CASES:
-        m = mesh_oracle.TreeMesh(seed, depth, radius=radius)
-        np.savez_compressed(os.path.join(HERE, f"mesh_{seed}_{depth}_r{radius:g}.npz"), **m.arrays())
-        print(seed, depth, radius, len(m.vx), len(m.eo), len(m.fx))
+        a = mesh_arrays(seed, depth, radius)
+        np.savez_compressed(os.path.join(HERE, f"mesh_{seed}_{depth}_r{radius:g}.npz"), **a)
+        print(seed, depth, radius, len(a["vert_xyz"]), len(a["edge_origs"]), len(a["face_xyz"]))
     tabs = {}
-    for seed, d in mesh_oracle.SEEDS.items():
-        crds, edges, fv, fe = mesh_oracle.read_seed(os.path.join("/root/reference/mesh_seeds", d["file"]), d["nverts"],
-                                                    d["nfaces"], d["nedges"], d["nfv"], d.get("ndim", 3))
-        tabs[f"{seed}_crds"] = np.array(crds)
-        tabs[f"{seed}_edges"] = np.array(edges, dtype=np.int32)
-        tabs[f"{seed}_face_verts"] = np.array(fv, dtype=np.int32)
-        tabs[f"{seed}_face_edges"] = np.array(fe, dtype=np.int32)
+    for seed in ref_mesh.SEED_ID:
+        a = mesh_arrays(seed, 0)  # the seed as MeshSeed<Seed>::read_file parsed it (radius 1)
+        tabs[f"{seed}_crds"] = np.concatenate([a["vert_xyz"], a["face_xyz"]])
+        tabs[f"{seed}_edges"] = np.stack([a["edge_origs"], a["edge_dests"], a["edge_lefts"], a["edge_rights"]], axis=1).astype(np.int32)
+        tabs[f"{seed}_face_verts"] = a["face_verts"].astype(np.int32)
+        tabs[f"{seed}_face_edges"] = a["face_edges"].astype(np.int32)
     np.savez_compressed(os.path.join(HERE, "seed_tables.npz"), **tabs)

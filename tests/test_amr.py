@@ -73,6 +73,36 @@ def test_live_python_replay_of_divide_flagged_faces():
             assert np.array_equal(v, getattr(m, k)), k
 
 
+def test_live_reference_divide_flagged_faces_every_array_bit_exact():
+    """PolyMesh2d<Seed>::divide_flagged_faces of the reference compiled in place (src/mesh/lpm_polymesh2d_impl.hpp:124-173,
+    oracle/_ref/liblpm_ref_mesh.so) against the product's generator on fresh pseudo-random flags: three passes per seed, deep
+    enough to meet neighbours two levels apart, the level limit and the "not enough memory" return; every outcome, index array,
+    coordinate and area."""
+    from oracle import ref_mesh
+    if not ref_mesh.available():
+        pytest.skip("oracle/_ref/liblpm_ref_mesh.so or /root/reference not present (build container only)")
+    rng = np.random.default_rng(11)
+    seen = set()
+    for seed in ("icos", "cubed", "quad_rect", "tri_hex"):
+        radius = 2.5 if seed in ("quad_rect", "tri_hex") else 1.0
+        for depth, buf, lim, p in ((1, 3, 3, 0.3), (2, 1, 1, 0.5)):
+            ref = ref_mesh.RefMesh(seed, depth, radius, buf, lim)
+            m = PolyMesh2d(seed, depth, radius=radius, amr_buffer=buf, amr_limit=lim)
+            assert ref.counts()["nmaxfaces"] == m.nmaxfaces
+            for _ in range(4):
+                flags = ((rng.random(m.n_faces) < p) & (m.face_mask == 0)).astype(np.uint8)
+                got, want = m.divide_flagged_faces(flags), ref.divide_flagged_faces(flags)
+                assert got == want, (seed, depth, got, want)
+                seen.add(got[1])
+            a = ref.arrays()
+            ref.close()
+            for k in INT_ARRAYS:
+                assert np.array_equal(a[k], getattr(m, k)), (seed, k)
+            for k in REAL_ARRAYS:
+                assert np.array_equal(a[k].view(np.int64), getattr(m, k).view(np.int64)), (seed, k)
+    assert seen == {PolyMesh2d.AMR_DIVIDED_ALL, PolyMesh2d.AMR_LIMIT_REACHED, PolyMesh2d.AMR_NO_SPACE}
+
+
 def test_flagging_a_divided_face_is_rejected_and_short_flag_arrays_too():
     from lpm_b200.api import LpmxError
     m = PolyMesh2d("icos", 1, amr_buffer=1, amr_limit=1)

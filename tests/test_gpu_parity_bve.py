@@ -10,7 +10,7 @@ pins that); on the cubed sphere they are regular and are compared as well.
 import numpy as np
 import pytest
 
-from conftest import field_rel_err
+from conftest import check_err, field_rel_err
 from lpm_b200 import gallery
 from lpm_b200.api import LAYOUT_LEFT, LAYOUT_RIGHT, BVESolver
 
@@ -141,12 +141,12 @@ def test_rk4_steps_in_place(engine, oracle, meshes, seed, depth, ic, nsteps, Ome
     engine.bve_rk4_step(dt, Omega, *got, m.face_area, m.face_mask, n_steps=nsteps)
     leaf = m.face_mask == 0
     sel = leaf if seed == "icos" else None
-    assert field_rel_err(got[0], ref[0]) <= VEL_TOL      # vertex positions
-    assert field_rel_err(got[3], ref[3], sel) <= VEL_TOL  # face positions
-    assert field_rel_err(got[1], ref[1]) <= VORT_TOL      # vertex vorticity
-    assert field_rel_err(got[4], ref[4], sel) <= VORT_TOL  # face vorticity
-    assert field_rel_err(got[2], ref[2]) <= 10 * VEL_TOL
-    assert field_rel_err(got[5], ref[5], sel) <= 10 * VEL_TOL
+    check_err("vert_xyz", field_rel_err(got[0], ref[0]), VEL_TOL)
+    check_err("face_xyz", field_rel_err(got[3], ref[3], sel), VEL_TOL)
+    check_err("vert_zeta", field_rel_err(got[1], ref[1]), VORT_TOL)
+    check_err("face_zeta", field_rel_err(got[4], ref[4], sel), VORT_TOL)
+    check_err("vert_vel", field_rel_err(got[2], ref[2]), VEL_TOL)
+    check_err("face_vel", field_rel_err(got[5], ref[5], sel), VEL_TOL)
 
 
 def test_rk4_face_vorticity_quirk_is_replicated(engine, oracle, meshes):
@@ -254,3 +254,93 @@ def test_full_size_rk4_step_properties(engine, oracle):
     idx = rng.choice(m.n_verts, 1024, replace=False)
     ov = oracle.bve_velocity(out[0][idx], out[3], out[4], m.face_area, m.face_mask)
     assert field_rel_err(out[2][idx], ov) <= VEL_TOL
+
+
+# ---- against the REFERENCE's own stepper compiled in place (tests/golden/ref_bve_rk4.npz) ---------------------------------------
+@pytest.mark.parametrize("name", ["icos3_rh54", "cubed3_rh54", "icos4_rot_3", "icos4_rot_100"])
+def test_resident_solver_matches_compiled_reference_bve_rk4(engine, name):
+    """set_state -> init_velocity -> advance(n) -> get_state [-> stream function] against BVESphere::init_velocity + n x
+    BVERK4::advance_timestep [+ init_stream_fn] of the reference itself (oracle/ref_mesh_driver.cpp; fixtures made by
+    tests/golden/make_ref_stepper_golden.py): 3 and 100 steps at icos-4, RH54 with Omega = 2 pi at icos-3 /
+    cubed-3.  north_star: <= 1e-12 on velocity, <= 1e-10 on stepped quantities."""
+    from test_oracle_golden import ref_rk4_case
+    from lpm_b200.api import PolyMesh2d
+    seed, depth, omega, dt, n_steps, g = ref_rk4_case(name)
+    m = PolyMesh2d(seed, depth)
+    area, mask = np.ascontiguousarray(m.face_area), np.ascontiguousarray(m.face_mask)
+    s = BVESolver(engine, m.n_verts, m.n_faces)
+    s.set_state(m.vert_xyz, g["vert_zeta0"], None, m.face_xyz, g["face_zeta0"], None, area, mask)
+    s.init_velocity()
+    s.advance(dt, omega, n_steps)
+    out = [np.empty((m.n_verts, 3)), np.empty(m.n_verts), np.empty((m.n_verts, 3)), np.empty((m.n_faces, 3)),
+           np.empty(m.n_faces), np.empty((m.n_faces, 3))]
+    s.get_state(*out)
+    s.close()
+    leaf = mask == 0
+    step_tol = VEL_TOL if n_steps <= 3 else VORT_TOL
+    check_err("vert_xyz", field_rel_err(out[0], g["vert_xyz"]), step_tol)
+    check_err("face_xyz", field_rel_err(out[3], g["face_xyz"], leaf), step_tol)
+    check_err("vert_zeta", field_rel_err(out[1], g["vert_zeta"]), VORT_TOL)
+    check_err("face_zeta", field_rel_err(out[4], g["face_zeta"], leaf), VORT_TOL)
+    if "vert_vel" in g:
+        check_err("vert_vel", field_rel_err(out[2], g["vert_vel"]), VEL_TOL)
+        check_err("face_vel", field_rel_err(out[5], g["face_vel"], leaf), VEL_TOL)
+        pv = engine.bve_streamfn(out[0], out[3], out[4], area, mask)
+        pf = engine.bve_streamfn(None, out[3], out[4], area, mask, collocated=True)
+        check_err("vert_psi", field_rel_err(pv, g["vert_psi"]), VEL_TOL)
+        check_err("face_psi", field_rel_err(pf, g["face_psi"], leaf), VEL_TOL)
+
+
+def test_rk4_step_at_cubed6_every_target_against_the_oracle(engine, oracle):
+    """One BVERK4 step (RH54, Omega = 2 pi) at cubed-sphere depth 6: 57 344 targets x 24 576 leaf sources is the smallest
+    mesh on which every velocity launch takes the LARGE kernel shape (T = 6 targets per thread, the shape of BASELINE
+    configs[1..3]) -- and the largest the CPU oracle steps in a few seconds -- so all targets of the production shape meet the
+    oracle, not a sample."""
+    from lpm_b200.api import PolyMesh2d
+    m = PolyMesh2d("cubed", 6)
+    dt = 0.025 * m.appx_mesh_size() / 0.09045016
+    ref = _rk4_case(m, "rh54", oracle)
+    got = [a.copy() for a in ref]
+    oracle.bve_rk4_step(dt, 2 * np.pi, *ref, m.face_area, m.face_mask, n_steps=1)
+    engine.bve_rk4_step(dt, 2 * np.pi, *got, m.face_area, m.face_mask, n_steps=1)
+    for n, a, b, t in zip(["vert_xyz", "vert_zeta", "vert_vel", "face_xyz", "face_zeta", "face_vel"], got, ref,
+                          [VEL_TOL, VORT_TOL, VEL_TOL] * 2):
+        check_err(n, field_rel_err(a, b), t)
+
+
+def _sampled_rk4_step_oracle(oracle, m, vz, fz, dt, Omega, idx):
+    """One BVERK4::advance_timestep (src/lpm_bve_rk4_impl.hpp:63-167) restated in numpy around the oracle's velocity sums, with
+    the VERTEX targets restricted to `idx` (vertices are never sources, so their stages can be sampled); all faces are stepped
+    because every stage's face state is the next stage's source set.  tests/test_bve_sampled_stepper.py checks this restatement
+    against oracle_bve_rk4_step on a small mesh (CPU suite)."""
+    from sampled_stepper import bve_rk4_step_sampled
+    return bve_rk4_step_sampled(oracle, m, vz, fz, dt, Omega, idx)
+
+
+def test_rk4_step_at_cubed7_sampled_targets_against_the_oracle(engine, oracle):
+    """BASELINE configs[1] at its stated size (cubed-sphere depth 7, 229 376 targets x 98 304 leaf sources), one BVERK4 step of
+    RH54 with Omega = 2 pi through the resident solver: all 131 070 face targets and 4 096 sampled vertex targets against the
+    oracle (the oracle evaluates the three inner stages on all faces -- they are the sources -- ~1 min of host time)."""
+    from lpm_b200.api import PolyMesh2d
+    m = PolyMesh2d("cubed", 7)
+    f = gallery.RossbyHaurwitz54()
+    f.set_stationary_wave_speed()
+    vz, fz = f(m.vert_xyz), f(m.face_xyz)
+    dt, Omega = 0.025 * m.appx_mesh_size() / 0.09045016, 2 * np.pi
+    area, mask = np.ascontiguousarray(m.face_area), np.ascontiguousarray(m.face_mask)
+    s = BVESolver(engine, m.n_verts, m.n_faces)
+    s.set_state(m.vert_xyz, vz, None, m.face_xyz, fz, None, area, mask)
+    s.init_velocity()
+    s.advance(dt, Omega, 1)
+    out = [np.empty((m.n_verts, 3)), np.empty(m.n_verts), np.empty((m.n_verts, 3)), np.empty((m.n_faces, 3)),
+           np.empty(m.n_faces), np.empty((m.n_faces, 3))]
+    s.get_state(*out)
+    s.close()
+    idx = np.sort(np.random.default_rng(20261018).choice(m.n_verts, 4096, replace=False))
+    ref = _sampled_rk4_step_oracle(oracle, m, vz, fz, dt, Omega, idx)
+    check_err("vert_xyz[sample]", field_rel_err(out[0][idx], ref["vert_xyz"]), VEL_TOL)
+    check_err("vert_zeta[sample]", field_rel_err(out[1][idx], ref["vert_zeta"]), VORT_TOL)
+    check_err("vert_vel[sample]", field_rel_err(out[2][idx], ref["vert_vel"]), VEL_TOL)
+    check_err("face_xyz", field_rel_err(out[3], ref["face_xyz"]), VEL_TOL)
+    check_err("face_zeta", field_rel_err(out[4], ref["face_zeta"]), VORT_TOL)
+    check_err("face_vel", field_rel_err(out[5], ref["face_vel"]), VEL_TOL)

@@ -1,6 +1,8 @@
 """CPU: the host mesh generator (input generator of every config) against
-  * golden fixtures produced by an independent pure-Python restatement run on the reference's own seed files
-    (oracle/mesh_oracle.py, tests/golden/make_mesh_golden.py): EVERY array bit-exact;
+  * golden fixtures produced by the REFERENCE's own mesh classes compiled in place (PolyMesh2d<Seed>::tree_init of
+    /root/reference/src/mesh -> oracle/_ref/liblpm_ref_mesh.so, tests/golden/make_mesh_golden.py): EVERY array bit-exact;
+  * the compiled reference live, at depths beyond the fixtures (where oracle/_ref and /root/reference are present);
+  * an independent pure-Python replay of the dividers (oracle/mesh_oracle.py), a second witness;
   * the reference's own mesh tests: allocation counts (tests/lpm_polymesh_tests.cpp:76-123), total area 4 pi;
   * structural invariants of the quad-tree."""
 import os
@@ -50,6 +52,47 @@ def test_live_python_restatement_from_reference_seed_files():
         m = PolyMesh2d(seed, depth)
         for k, v in ref.items():
             assert np.array_equal(v, getattr(m, k)), k
+
+
+def _ref_mesh_or_skip():
+    from oracle import ref_mesh
+    if not ref_mesh.available():
+        pytest.skip("oracle/_ref/liblpm_ref_mesh.so or /root/reference not present (build container only)")
+    return ref_mesh
+
+
+@pytest.mark.parametrize("seed,depth,radius", [("icos", 4, 1.0), ("icos", 5, 1.0), ("cubed", 5, 1.0), ("cubed", 6, 1.0),
+                                               ("quad_rect", 5, 3.0), ("tri_hex", 4, 2.5)])
+def test_live_reference_mesh_classes_every_array_bit_exact(seed, depth, radius):
+    """The reference's PolyMesh2d<Seed>(PolyMeshParameters(depth, radius)) (TriFace / QuadFace dividers of
+    src/mesh/lpm_faces_impl.hpp:284-574, Edges::divide of lpm_edges.cpp:58-125, tree_init of lpm_polymesh2d_impl.hpp:25-42),
+    compiled in place, against the product's generator: insertion order, every index array, every coordinate and area."""
+    ref_mesh = _ref_mesh_or_skip()
+    r = ref_mesh.RefMesh(seed, depth, radius)
+    a = r.arrays()
+    c = r.counts()
+    r.close()
+    m = PolyMesh2d(seed, depth, radius=radius)
+    assert (m.n_verts, m.n_edges, m.n_faces, m.n_face_leaves) == (c["n_verts"], c["n_edges"], c["n_faces"], c["n_leaves"])
+    assert (c["nmaxverts"], c["nmaxedges"], c["nmaxfaces"]) == max_allocations(seed, depth)
+    for k in INT_ARRAYS:
+        assert np.array_equal(a[k], getattr(m, k)), k
+    for k in REAL_ARRAYS:
+        assert np.array_equal(a[k].view(np.int64), getattr(m, k).view(np.int64)), k
+    # Faces::crd_inds is the identity on a freshly built tree (face i owns coordinate row i)
+    assert np.array_equal(a["face_crd_idx"], np.arange(m.n_faces, dtype=np.int32))
+
+
+def test_golden_fixtures_are_what_the_compiled_reference_produces():
+    """The committed fixtures against a fresh run of the compiled reference (guards the fixtures themselves)."""
+    ref_mesh = _ref_mesh_or_skip()
+    for seed, depth in CASES:
+        g = np.load(os.path.join(GOLDEN, f"mesh_{seed}_{depth}.npz"))
+        r = ref_mesh.RefMesh(seed, depth)
+        a = r.arrays()
+        r.close()
+        for k in g.files:
+            assert np.array_equal(g[k], a[k]), (seed, depth, k)
 
 
 @pytest.mark.parametrize("seed,depth", [("icos", 3), ("cubed", 3), ("icos", 5), ("cubed", 6)])

@@ -252,3 +252,67 @@ def test_long_double_adjudicator_agrees_to_roundoff(oracle):
     a = oracle.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask)
     b = oracle.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask, long_double=True)
     assert field_rel_err(a, b) < 1e-13
+
+
+# ---- the stepper itself: BVESphere + BVERK4::advance_timestep of the reference, compiled in place -----------------------------
+REF_RK4_CASES = ["icos3_rh54", "cubed3_rh54", "icos4_rot_3", "icos4_rot_100"]
+
+
+def ref_rk4_case(name):
+    """(seed, depth, Omega, dt, n_steps, golden dict without the prefix) of tests/golden/ref_bve_rk4.npz
+    (tests/golden/make_ref_stepper_golden.py: outputs of oracle/_ref/liblpm_ref_mesh.so)."""
+    g = np.load(os.path.join(GOLDEN, "ref_bve_rk4.npz"))
+    depth, omega, dt, n_steps = g[f"{name}_params"]
+    d = {k[len(name) + 1:]: g[k] for k in g.files if k.startswith(name + "_")}
+    return name.split("_")[0][:-1], int(depth), float(omega), float(dt), int(n_steps), d
+
+
+@pytest.mark.parametrize("name", REF_RK4_CASES)
+def test_oracle_stepper_matches_compiled_reference_bve_rk4(oracle, name):
+    """oracle_bve_rk4_step (the restatement every GPU stepper test is checked against) vs the reference's own
+    BVERK4::advance_timestep (src/lpm_bve_rk4_impl.hpp:63-167: 4 x {BVEVertexVelocity, BVEFaceVelocity, BVEVorticityTendency},
+    20 KokkosBlas calls, the facevort4-twice update) after BVESphere::init_velocity, incl. 100 steps at icos-4."""
+    seed, depth, omega, dt, n_steps, g = ref_rk4_case(name)
+    m = PolyMesh2d(seed, depth)
+    vz, fz = g["vert_zeta0"], g["face_zeta0"]
+    vu = oracle.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask)
+    fu = oracle.bve_velocity(None, m.face_xyz, fz, m.face_area, m.face_mask, collocated=True)
+    st = [m.vert_xyz.copy(), vz.copy(), vu, m.face_xyz.copy(), fz.copy(), fu]
+    oracle.bve_rk4_step(dt, omega, *st, m.face_area, m.face_mask, n_steps=n_steps)
+    leaf = m.face_mask == 0
+    tol = 2e-14 if n_steps <= 3 else 2e-13  # round-off of two compilations of the same arithmetic (FMA contraction differs)
+    assert field_rel_err(st[0], g["vert_xyz"]) <= tol
+    assert field_rel_err(st[3], g["face_xyz"], leaf) <= tol
+    assert field_rel_err(st[1], g["vert_zeta"]) <= tol
+    assert field_rel_err(st[4], g["face_zeta"], leaf) <= tol
+    if "vert_vel" in g:
+        assert field_rel_err(st[2], g["vert_vel"]) <= 10 * tol
+        assert field_rel_err(st[5], g["face_vel"], leaf) <= 10 * tol
+        psi_v = oracle.bve_streamfn(st[0], st[3], st[4], m.face_area, m.face_mask)
+        psi_f = oracle.bve_streamfn(None, st[3], st[4], m.face_area, m.face_mask, collocated=True)
+        assert field_rel_err(psi_v, g["vert_psi"]) <= 10 * tol
+        assert field_rel_err(psi_f, g["face_psi"], leaf) <= 10 * tol
+
+
+def test_rows_of_divided_icos_faces_depend_on_the_reference_build_flags(oracle):
+    """Why every comparison on icosahedral meshes selects leaf rows: a divided TriFace keeps its centre, which is also the centre
+    of its middle child, so 1 - x.y of that (target, source) pair is 0 or an ulp, and the reference's value there is 0/0 = NaN,
+    or 1e16-sized, depending on whether the compiler contracted x.y into FMAs.  Shown on the reference itself: the same functor
+    (BVEFaceVelocity, src/lpm_bve_sphere_kernels.hpp:284-320) compiled with contraction (oracle/_ref/liblpm_ref.so) and without
+    (BVESphere::init_velocity in liblpm_ref_mesh.so) disagrees on WHICH rows are NaN, while all leaf rows agree to round-off.
+    These rows are targets only (masked faces are never sources), so nothing observable depends on them."""
+    from oracle import ref_mesh
+    if not (os.path.exists(oracle.REF_LIB) and ref_mesh.available()):
+        pytest.skip("oracle/_ref not built")
+    L = ctypes.CDLL(oracle.REF_LIB)
+    m = PolyMesh2d("icos", 2)
+    f = gallery.RossbyHaurwitz54()
+    f.set_stationary_wave_speed()
+    vz, fz = f(m.vert_xyz), f(m.face_xyz)
+    a = oracle.bve_velocity(None, m.face_xyz, fz, m.face_area, m.face_mask, collocated=True, L=L)  # contracted build
+    b = ref_mesh.bve_rk4_run("icos", 2, 0.01, 0.0, 0, vz, fz)["face_vel"]                          # -ffp-contract=off build
+    leaf = m.face_mask == 0
+    assert field_rel_err(a, b, leaf) <= 1e-14
+    nan_a, nan_b = np.isnan(a).any(axis=1), np.isnan(b).any(axis=1)
+    assert not nan_a[leaf].any() and not nan_b[leaf].any()
+    assert nan_a.sum() > 0 and nan_b.sum() > 0 and not np.array_equal(nan_a, nan_b)

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "lpmx_pair_kernel.cuh"
@@ -302,6 +303,20 @@ int main(int argc, char** argv) {
 
 #define RUNK(K, T, NW, MINB, UNR) run<PairCfg<K, T, NW, MINB, UNR>>(#K " T" #T " NW" #NW " B" #MINB " U" #UNR)
 #define RUN(T, NW, MINB, UNR) run<PairCfg<kVel, T, NW, MINB, UNR>>("vel T" #T " NW" #NW " B" #MINB " U" #UNR)
+  if (argc > 3 && !strcmp(argv[3], "r2")) {  // round 2: the product shapes and their neighbours (built twice: -DLPMX_RCP_HOLD=0 / 1)
+    printf("LPMX_RCP_HOLD=%d\n", LPMX_RCP_HOLD);
+    RUN(6, 8, 1, 2);
+    RUN(6, 8, 1, 4);
+    RUN(7, 8, 1, 2);
+    RUN(8, 8, 1, 2);
+    RUN(8, 8, 1, 4);
+    RUN(4, 8, 2, 2);
+    RUNK(kVelPsi, 4, 8, 1, 2);
+    RUNK(kVelPsi, 4, 8, 1, 4);
+    RUNK(kVelPsi, 6, 8, 1, 2);
+    RUNK(kPsi, 8, 8, 1, 2);
+    return 0;
+  }
   if (argc > 5) {  // stream-function kinds only: more warps per SM against the two divergent table lookups per pair
     RUNK(kVelPsi, 4, 8, 1, 2);
     RUNK(kVelPsi, 4, 12, 1, 2);
