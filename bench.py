@@ -112,29 +112,57 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def host_threads():
+    """Host threads this process may use (cgroup/affinity aware)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_lib():
-    """The reference's own functors compiled in place (oracle/_ref) when present, else the restatement."""
+    """The reference's own functors compiled in place (oracle/_ref) when present, else the restatement.  The OpenMP team size is
+    set explicitly: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which round 1's reference arm inherited."""
     import ctypes
     from oracle import oracle
+    kind, L = "port", None
     if os.path.exists(oracle.REF_LIB):
         try:
             L = ctypes.CDLL(oracle.REF_LIB)
-            L.oracle_num_threads.restype = ctypes.c_int
-            return oracle, L, "reference"
+            kind = "reference"
         except OSError:
-            pass
-    return oracle, oracle.lib(), "port"
+            L = None
+    if L is None:
+        L = oracle.lib()
+    L.oracle_num_threads.restype = ctypes.c_int
+    try:
+        L.oracle_set_num_threads(ctypes.c_int(host_threads()))
+    except AttributeError:
+        pass
+    return oracle, L, kind
+
+
+def cpu_sample_indices(m, n_sample):
+    """A bounded sample of the workload's targets in the mesh's own proportion of vertices (BVEVertexVelocity: distinct targets)
+    and faces (BVEFaceVelocity: collocated targets with the i != j branch), evenly spaced over each list."""
+    nt = m.n_verts + m.n_faces
+    n_sample = max(2, min(n_sample, nt))
+    nvs = max(1, min(m.n_verts, int(round(n_sample * m.n_verts / nt))))
+    nfs = max(1, min(m.n_faces, n_sample - nvs))
+    vi = np.unique(np.linspace(0, m.n_verts - 1, nvs).astype(np.int64))
+    fi = np.unique(np.linspace(0, m.n_faces - 1, nfs).astype(np.int32))
+    return vi, fi
 
 
 def time_cpu_sample(m, fz, n_sample, reps=1):
-    """Velocity evaluation of the first n_sample vertex targets against all faces with the reference CPU path
-    (OpenMP over targets, sequential j, per-pair divide).  Returns (interactions/s, seconds, kind, threads)."""
+    """One velocity evaluation of a bounded target sample against all sources with the reference CPU path (OpenMP over
+    targets, sequential j, per-pair divide).  Returns (interactions/s, seconds, kind, threads, n_vert_targets, n_face_targets)."""
     oracle, L, kind = cpu_reference_lib()
-    n_sample = min(n_sample, m.n_verts)
-    tx = np.ascontiguousarray(m.vert_xyz[:n_sample])
+    vi, fi = cpu_sample_indices(m, n_sample)
+    tx = np.ascontiguousarray(m.vert_xyz[vi])
     if not getattr(time_cpu_sample, "_warm", False):
         # the first few parallel regions of a process run several times slower (thread-pool start-up)
-        w = np.ascontiguousarray(m.vert_xyz[:max(64, min(n_sample // 16, 2048))])
+        w = np.ascontiguousarray(m.vert_xyz[:max(64, min(len(vi) // 16, 2048))])
         for _ in range(4):
             oracle.bve_velocity(w, m.face_xyz, fz, m.face_area, m.face_mask, collocated=False, L=L)
         time_cpu_sample._warm = True
@@ -142,43 +170,119 @@ def time_cpu_sample(m, fz, n_sample, reps=1):
     for _ in range(reps):
         t0 = time.perf_counter()
         oracle.bve_velocity(tx, m.face_xyz, fz, m.face_area, m.face_mask, collocated=False, L=L)
+        oracle.bve_velocity_subset(fi, m.face_xyz, fz, m.face_area, m.face_mask, L=L)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    inter = float(n_sample) * m.n_face_leaves
-    return inter / best, best, kind, L.oracle_num_threads()
+    inter = float(len(vi) + len(fi)) * m.n_face_leaves - float((m.face_mask[fi] == 0).sum())
+    return inter / best, best, kind, L.oracle_num_threads(), len(vi), len(fi)
+
+
+def size_cpu_sample(m, fz, seconds):
+    """Targets that take about `seconds` per evaluation on this host, from a short calibration run."""
+    rate, _, _, _, _, _ = time_cpu_sample(m, fz, 2048)
+    rate2, _, _, _, _, _ = time_cpu_sample(m, fz, 2048)
+    n = int(max(rate, rate2) * seconds / max(1, m.n_face_leaves))
+    return max(256, min(n, m.n_verts + m.n_faces))
+
+
+def time_reference_icos4_example():
+    """BASELINE.md section 4's CPU-runnable case: examples/bve_rotation-style run at icosTriSphereSeed depth 4, 3 BVERK4 steps of
+    solid-body rotation, with the REFERENCE's own BVESphere + BVERK4::advance_timestep compiled in place (oracle/_ref/
+    liblpm_ref_mesh.so) when present, else the oracle's restatement of the step.  Returns a dict or None."""
+    from lpm_b200 import gallery
+    from lpm_b200.api import PolyMesh2d
+    try:
+        m = PolyMesh2d("icos", 4)
+        f = gallery.SolidBodyRotation()
+        vz, fz = f(m.vert_xyz), f(m.face_xyz)
+        inter = 3 * 4 * (float(m.n_verts + m.n_faces) * m.n_face_leaves - m.n_face_leaves)
+        from oracle import ref_mesh
+        if ref_mesh.available():
+            import ctypes
+            ref_mesh.lib().ref_mesh_set_num_threads(ctypes.c_int(host_threads()))
+            ref_mesh.bve_rk4_run("icos", 4, 0.0025, 0.0, 0, vz, fz)  # warm-up + what is not the stepper (mesh, init_velocity)
+            t0 = time.perf_counter()
+            ref_mesh.bve_rk4_run("icos", 4, 0.0025, 0.0, 0, vz, fz)
+            t_init = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            ref_mesh.bve_rk4_run("icos", 4, 0.0025, 0.0, 3, vz, fz)
+            secs = max(time.perf_counter() - t0 - t_init, 1e-9)
+            kind, threads = "reference", ref_mesh.lib().ref_mesh_num_threads()
+            what = "BVESphere<IcosTriSphereSeed> + 3 x BVERK4::advance_timestep compiled in place (tree_init and init_velocity subtracted)"
+        else:
+            oracle, L, kind = cpu_reference_lib()
+            L = oracle.lib()
+            L.oracle_set_num_threads(host_threads())
+            vu = oracle.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask)
+            fu = oracle.bve_velocity(None, m.face_xyz, fz, m.face_area, m.face_mask, collocated=True)
+            st = [m.vert_xyz.copy(), vz.copy(), vu, m.face_xyz.copy(), fz.copy(), fu]
+            t0 = time.perf_counter()
+            oracle.bve_rk4_step(0.0025, 0.0, *st, m.face_area, m.face_mask, n_steps=3)
+            secs = time.perf_counter() - t0
+            kind, threads = "port", L.oracle_num_threads()
+            what = "oracle_bve_rk4_step x 3 (the restatement pinned against the compiled BVERK4)"
+        return {"workload": "rotation_icos4, 3 BVERK4 steps (BASELINE configs[0])", "seconds": secs, "ms_per_step": secs / 3 * 1e3,
+                "interactions_per_s": inter / secs, "kind": kind, "cores": threads, "what": what}
+    except Exception as e:  # a baseline extra must never take the bench line down
+        return {"error": repr(e)}
+
+
+def workload_config(args, m, desc, world):
+    """The `config` object, identical for both arms (the driver compares them)."""
+    evals = EVALS_PER_STEP[args.stepper]
+    i_eval = float(m.n_verts + m.n_faces) * m.n_face_leaves - m.n_face_leaves
+    cfg = {"workload": args.workload, "description": desc, "stepper": args.stepper, "evals_per_step": evals,
+           "n_verts": m.n_verts, "n_faces": m.n_faces, "n_leaf_sources": m.n_face_leaves, "interactions_per_eval": i_eval,
+           "dt": args.dt, "Omega": 2 * np.pi,
+           "parallelism": f"targets sharded over {world} GPU(s), per-stage allgather of leaf source records",
+           "l2": "flushed between timed steps (256 MiB write)"}
+    if args.stepper == "swe_rk2":
+        cfg["surface_laplacian"] = (f"device GMLS order {args.gmls_order}, both stages" if args.laplacian == "gmls"
+                                    else "frozen at the TC2 closed form")
+    return cfg
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the same step, on the host cores, each step a
-    bounded sample (a slice of the targets, all sources) of the workload."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores (oracle/_ref: its own functors compiled
+    in place), all host threads, rank 0 only.  Each step is ONE velocity evaluation of a bounded sample of the workload's targets
+    (vertices through BVEVertexVelocity, faces through BVEFaceVelocity) against all sources, sized by a calibration run to
+    --ref-seconds per step, so that the whole --steps K --warmup W run stays within a few minutes whatever the host."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    if world > 1:
+        args.gpus = world
     m, vz, fz, desc = build_case(args.workload)
+    if args.dt is None:
+        args.dt = 0.025 * m.appx_mesh_size() / 0.09045016
     evals = EVALS_PER_STEP[args.stepper]
-    n_sample = args.cpu_sample
+    n_sample = args.cpu_sample if args.cpu_sample > 0 else size_cpu_sample(m, fz, args.ref_seconds)
     for _ in range(max(args.warmup, 0)):
         time_cpu_sample(m, fz, max(n_sample // 8, 64))
     rates, secs = [], []
-    kind, threads = "port", 1
+    kind, threads, nvs, nfs = "port", 1, 0, 0
     for _ in range(args.steps):
-        r, s, kind, threads = time_cpu_sample(m, fz, n_sample)
+        r, sec, kind, threads, nvs, nfs = time_cpu_sample(m, fz, n_sample)
         rates.append(r)
-        secs.append(s)
-    value = float(np.mean(rates))
-    i_eval = float(m.n_verts + m.n_faces) * m.n_face_leaves - m.n_face_leaves
-    sample = (f"{min(n_sample, m.n_verts)} vertex targets x all {m.n_faces} faces ({m.n_face_leaves} leaf sources) per "
-              f"step, one velocity evaluation; full-step time extrapolated linearly in targets")
+        secs.append(sec)
+    value = float(np.sum(rates) / len(rates))
+    cfg = workload_config(args, m, desc, args.gpus)
+    i_eval = cfg["interactions_per_eval"]
+    sample = (f"per step ONE velocity evaluation of {nvs} vertex targets (BVEVertexVelocity) + {nfs} face targets "
+              f"(BVEFaceVelocity, i != j) x all {m.n_faces} faces ({m.n_face_leaves} leaf sources); ms_per_step is the "
+              f"timed sample, not a stepper step")
     line = {
         "impl": "reference", "metric": "fp64_pair_interactions_per_s", "value": value, "unit": "interactions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": evals * i_eval / value * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "stepper": args.stepper,
-                   "evals_per_step": evals, "interactions_per_eval": i_eval, "l2": "n/a (CPU)"},
+        "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "full_step_ms_extrapolated": evals * i_eval / value * 1e3,
         "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "native_code_note": "lpm_b200/liblpmx.so is loaded by this arm for the HOST mesh generator only (input generation; "
+                            "no kernel runs, no device is opened); the timed code is oracle/_ref",
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -195,10 +299,15 @@ def main():
     ap.add_argument("--dt", type=float, default=None,
                     help="time step; default 0.025 * h / h(cubed-4): the reference's sphere_rh54 default (tfinal 0.025, "
                          "1 step, depth 4; examples/sphere_rh54.cpp:442-452) at constant Courant number")
-    ap.add_argument("--cpu-sample", type=int, default=196608,
-                    help="vertex targets in the CPU baseline sample (capped at the mesh's vertex count: all 98306 vertices "
-                         "of the default workload, ~6 s per evaluation on 16 host cores, timed twice)")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="targets (vertices + faces, in the mesh's proportion) in the CPU sample; 0 = sized by a calibration "
+                         "run to --ref-seconds (reference arm) / --cpu-seconds (cpu_baseline leg) per evaluation")
+    ap.add_argument("--ref-seconds", type=float, default=6.0, help="reference arm: host seconds per timed step")
+    ap.add_argument("--cpu-seconds", type=float, default=8.0, help="cpu_baseline leg: host seconds per evaluation (timed twice)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra records of the N = 1 line (n1m synthetic set, ic2d_rk2 stepper, icos-4 CPU example)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-run parity block (sampled targets vs the oracle)")
     ap.add_argument("--laplacian", default="frozen", choices=["frozen", "gmls"],
                     help="swe_rk2 only: surface Laplacian frozen at the TC2 closed form (the pair sums alone), or the "
                          "device-side GMLS provider of order --gmls-order evaluated at both stages of every step (the whole "
@@ -341,6 +450,38 @@ def main():
         "steps_advanced": args.warmup + args.steps,
     }
 
+    # ---- parity of what the timed steps left behind (rank 0; the oracle is the CHECKER here, outside every timed region):
+    # the velocity the last evaluation stored, against the reference arithmetic (oracle/_ref when present) evaluated on the
+    # same advanced state, on sampled vertex targets (distinct) and sampled leaf-face targets (collocated, i != j).  With
+    # N > 1 the state was gathered from all ranks' shards, so this is the multi-GPU parity record of the SCALE runs.
+    parity = None
+    if rank == 0 and not args.no_parity:
+        try:
+            oracle, Lref, pkind = cpu_reference_lib()
+            rng = np.random.default_rng(20261018)
+            vi = np.sort(rng.choice(nv, min(1024, nv), replace=False))
+            leaf_ids = np.nonzero(leafsel)[0]
+            fi = np.sort(rng.choice(leaf_ids, min(1024, len(leaf_ids)), replace=False)).astype(np.int32)
+            if args.stepper == "swe_rk2":
+                sdiv_p, sdiv_a, sarea = np.zeros(nv), np.zeros(nf), np.zeros(nf)
+                swe_solver.get_state({"div": sdiv_p}, {"div": sdiv_a, "area": sarea})
+                ov, _, _ = oracle.swe_sphere_sums(chk[0][vi], chk[3], chk[4], sdiv_a, sarea, mask, eps=0.0, L=Lref)
+                of, gf = None, None
+            else:
+                ov = oracle.bve_velocity(chk[0][vi], chk[3], chk[4], area, mask, L=Lref)
+                of = oracle.bve_velocity_subset(fi, chk[3], chk[4], area, mask, L=Lref)
+            scale = float(np.linalg.norm(ov, axis=1).max())
+            ev = float(np.linalg.norm(chk[2][vi] - ov, axis=1).max() / scale)
+            ef = float(np.linalg.norm(chk[5][fi] - of, axis=1).max() / scale) if of is not None else None
+            parity = {"quantity": "velocity stored by the last evaluation of the timed steps vs the reference arithmetic on the "
+                                  "same advanced state (field-relative max-norm)",
+                      "max_rel_err": max(ev, ef) if ef is not None else ev, "vertex_targets": {"n": int(len(vi)), "rel_err": ev},
+                      "leaf_face_targets": ({"n": int(len(fi)), "rel_err": ef} if ef is not None else None),
+                      "tolerance": 1e-12, "checker": "oracle/_ref (reference functors compiled in place)" if pkind == "reference"
+                      else "oracle/ (C restatement)", "n_gpus_that_produced_the_state": world}
+        except Exception as e:
+            parity = {"error": repr(e)}
+
     # ---- roofline of the dominant kernel (rank-local): algorithmic flops / CUDA-event launch time ----
     local_inter = evals * args.steps * (float(solver_local_targets(nv + nf, rank, world)) * nleaf)
     flops_per = FLOPS_PER_INTERACTION[args.stepper]
@@ -348,8 +489,8 @@ def main():
     roofline = {
         "bound": "fp64", "kernel": "lpmx::pair_sum_kernel", "achieved": achieved_tf, "peak": fp64_peak,
         "unit": "TFLOP/s", "frac": (achieved_tf / fp64_peak) if achieved_tf else None,
-        "peak_source": "measured live: lpmx_fp64_peak_tflops DFMA probe (MEASURED_PEAKS.json has no FP64 entry; "
-                       "nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2)",
+        "peak_source": "measured live: lpmx_fp64_peak_tflops, DFMA R, R, c[0][..], R probe, loop unrolled x16 (MEASURED_PEAKS.json "
+                       "has no FP64 entry; nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2)",
         "flops_per_interaction": flops_per, "launches": n_k, "avg_launch_ms": (k_ms / n_k) if n_k else None,
         "kernel_share_of_step": (k_ms / (sum(step_ms))) if step_ms else None,
         "fp64_pipe_instr_per_interaction": {"bve_rk4": 9, "ic2d_rk2": 13.5, "swe_rk2": 53}[args.stepper],  # ic2d: (9 + 18) / 2
@@ -365,6 +506,8 @@ def main():
     if os.path.exists(prof) and args.workload == "rh54_cubed7" and args.stepper == "bve_rk4":  # captured on that launch shape
         try:
             roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            roofline["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch of this shape from the ncu --set "
+                                          "full capture committed as profiles/r1_pair_sum_dram.json; NOT measured in this run")
         except Exception:
             pass
 
@@ -428,13 +571,24 @@ def main():
                "api": {"bve_rk4": "lpmx_bve_rk4_step", "ic2d_rk2": "lpmx_ic2d_rk2_step", "swe_rk2": "lpmx_swe_rk2_step"}[args.stepper],
                "host_buffers": "pinned"}
 
+    # ---- extras of the N = 1 line: the synthetic N = 1e6 set (north_star's ">= 1M particles"), and the stepper the reference's
+    # sphere_rh54 / sphere_gaussian_vortex drivers actually use (Incompressible2DRK2) on the same mesh ----
+    extras = {}
+    if world == 1 and not args.no_extras and args.stepper == "bve_rk4":
+        extras["n1m"] = bench_synthetic_n1m(eng, stream, torch, fp64_peak)
+    if not args.no_extras and args.stepper == "bve_rk4":
+        extras["ic2d_rk2"] = bench_ic2d_extra(eng, stream, torch, dist, m, vz, fz, area, mask, args.dt, Omega, i_eval, flush_buf)
+
     # ---- CPU baseline on the host cores (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, secs, kind, threads = time_cpu_sample(m, fz, args.cpu_sample, reps=2)
+        n_sample = args.cpu_sample if args.cpu_sample > 0 else size_cpu_sample(m, fz, args.cpu_seconds)
+        rate, secs, kind, threads, nvs, nfs = time_cpu_sample(m, fz, n_sample, reps=2)
         cpu = {"value": rate, "unit": "interactions/s", "cores": threads, "kind": kind,
-               "sample": f"{min(args.cpu_sample, nv)} vertex targets x all {nf} faces ({nleaf} leaf sources), one "
-                         f"velocity evaluation, best of 2, {secs:.1f} s each"}
+               "sample": f"{nvs} vertex targets (BVEVertexVelocity) + {nfs} face targets (BVEFaceVelocity, i != j) x all {nf} faces "
+                         f"({nleaf} leaf sources), one velocity evaluation, best of 2, {secs:.1f} s each"}
+        if not args.no_extras:
+            cpu["icos4_3steps"] = time_reference_icos4_example()
 
     peer_on, peer_slabs = eng.comm_peer_exchange_enabled()
     exchange = ("none (one GPU)" if world == 1 else
@@ -445,17 +599,11 @@ def main():
             "metric": "fp64_pair_interactions_per_s", "value": value, "unit": "interactions/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "stepper": args.stepper,
-                       "evals_per_step": evals, "n_verts": nv, "n_faces": nf, "n_leaf_sources": nleaf,
-                       "interactions_per_eval": i_eval, "dt": args.dt, "Omega": Omega,
-                       "parallelism": f"targets sharded over {world} GPU(s), per-stage allgather of leaf source records",
-                       "exchange": exchange,
-                       "l2": "flushed between timed steps (256 MiB write)",
-                       **({"surface_laplacian": (f"device GMLS order {args.gmls_order}, both stages" if args.laplacian == "gmls"
-                                                 else "frozen at the TC2 closed form")} if args.stepper == "swe_rk2" else {})},
+            "config": workload_config(args, m, desc, world), "exchange": exchange,
             "rk_step_ms": ms_per_step, "step_ms_each": step_ms, "wall_s_timed_region": t_wall,
             "state_check": state_check,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "parity": parity, **extras,
         }
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
@@ -463,6 +611,71 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def bench_synthetic_n1m(eng, stream, torch, fp64_peak, n=1_000_000, steps=3):
+    """BASELINE configs[4] at N = 1e6 (tools/synthetic_sweep.py's particle set): `steps` BVERK4 steps of N collocated i.i.d.
+    particles, device-resident, CUDA events on the engine's stream.  north_star's ">= 70 % of FP64 peak at N >= 1M"."""
+    from lpm_b200.api import BVESolver
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        from synthetic_sweep import particles
+        x, zeta, area = particles(n)
+        mask = np.zeros(n, dtype=np.uint8)
+        s = BVESolver(eng, 0, n)
+        s.set_state(None, None, None, x, zeta, None, area, mask)
+        s.init_velocity()
+        s.advance(1e-4, 2 * np.pi, 1)  # warm-up step
+        eng.sync()
+        with torch.cuda.stream(stream):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            s.advance(1e-4, 2 * np.pi, steps)
+            e1.record(stream)
+        eng.sync()
+        ms = e0.elapsed_time(e1) / steps
+        s.close()
+        rate = 4.0 * n * (n - 1.0) / (ms * 1e-3)
+        return {"workload": "synthetic_collocated (Philox key 20261017, RH54 vorticity formula)", "n_particles": n, "steps": steps,
+                "rk4_step_ms": ms, "interactions_per_s": rate, "alg_tflops": rate * 24e-12,
+                "frac_of_measured_fp64_peak": rate * 24e-12 / fp64_peak if fp64_peak else None,
+                "issued_frac": rate * 18e-12 / fp64_peak if fp64_peak else None, "inputs": "larger than L2 (64 MB of records per pass)"}
+    except Exception as e:
+        return {"error": repr(e)}
+
+
+def bench_ic2d_extra(eng, stream, torch, dist, m, vz, fz, area, mask, dt, Omega, i_eval, flush_buf, steps=3):
+    """Incompressible2DRK2 (src/lpm_incompressible2d_rk2_impl.hpp:75-172; 2 evaluations per step, psi with the second) on the
+    bench's mesh, one step per call as the reference's drivers call it, device-resident; max over ranks."""
+    from lpm_b200.api import IC2DSolver
+    try:
+        s = IC2DSolver(eng, m.n_verts, m.n_faces, eps=0.0)
+        s.set_state(m.vert_xyz, vz, None, m.face_xyz, fz, None, area, mask)
+        s.init_direct_sums()
+        s.advance(dt, Omega, 1)
+        eng.sync()
+        if dist is not None:
+            dist.barrier()
+        total = 0.0
+        for _ in range(steps):
+            with torch.cuda.stream(stream):
+                flush_buf.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                s.advance(dt, Omega, 1)
+                e1.record(stream)
+            eng.sync()
+            total += e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([total], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = float(t.item())
+        s.close()
+        ms = total / steps
+        return {"stepper": "Incompressible2DRK2, one step per call", "steps": steps, "ms_per_step": ms,
+                "interactions_per_s": 2 * i_eval / (ms * 1e-3), "evals_per_step": 2}
+    except Exception as e:
+        return {"error": repr(e)}
 
 
 def solver_local_targets(nt, rank, world):

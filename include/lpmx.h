@@ -196,11 +196,13 @@ int lpmx_comm_enable_peer_exchange(lpmx_handle_t h, int enable);
 /* enabled: 1 when exchanges of mapped slabs take the peer path; n_regions: slabs currently mapped. */
 int lpmx_comm_peer_exchange_enabled(lpmx_handle_t h, int* enabled, int* n_regions);
 
-/* Velocity pair sums with the source records streamed through the constant bank (opt-in, kVel launches with >= ~2e5
- * targets per rank; lpm_b200/csrc/lpmx_const_stream.cu).  mode 0: off, 1: bank copies overlapped
- * with the launches, 2: copies on the compute stream, -1: take LPMX_CONST_STREAM from the environment (default).  Affects
- * the plans made AFTER the call (solvers created / states set afterwards).  One user per device and process: the bank is
- * a single __constant__ array.  Same per-pair arithmetic as the default kernel; per-target sums differ by round-off. */
+/* Velocity pair sums with the source records streamed through the constant bank (lpm_b200/csrc/lpmx_const_stream.cu,
+ * DESIGN.md section 4.1b): sources reach the DFMAs as uniform-register operands, +8.5 % at icos-8, slower below ~1e6 targets.
+ * mode -1 (default): LPMX_CONST_STREAM from the environment, else AUTO = used for kVel launches with >= 1e6 targets per rank;
+ * 0: off; 1: forced, bank copies overlapped with the launches; 2: forced, copies on the compute stream.  Affects the plans
+ * made AFTER the call (solvers created / states set afterwards).  The bank is a single __constant__ array per device: the
+ * first handle of a process that takes the path on a device owns it until lpmx_destroy (or mode 0); other handles on that
+ * device keep the default kernel.  Same per-pair arithmetic as the default kernel; per-target sums differ by round-off. */
 int lpmx_pair_sum_const_stream(lpmx_handle_t h, int mode);
 /* The launch shape that path would use for n_tgt targets on a GPU with num_sms SMs (host-only planning query): T targets
  * per thread, n_warps warps per CTA, grid CTAs per launch (one CTA per SM and wave). */

@@ -1,7 +1,11 @@
 // lpmx_const_stream.cu -- the velocity pair sum with the source records streamed through the CONSTANT bank, so that
-// they reach the DFMAs as uniform-register operands (SASS: LDCU.64 + DFMA R, R, UR, R).  Opt-in, unmeasured in the
-// product: LPMX_CONST_STREAM=1 (copies overlapped with the kernels) or =2 (copies on the compute stream), or
-// lpmx_pair_sum_const_stream().  DESIGN.md section 8, lead 1.
+// they reach the DFMAs as uniform-register operands (SASS: LDCU.64 + DFMA R, R, UR, R).
+// Measured (profiles/r2b_*): icos-8 (2.40 M targets x 1.31 M sources) 7.604 -> 7.008 s per BVERK4 step, 1.657e12 -> 1.798e12
+// interactions/s (+8.5 %); cubed-7 (229 376 targets) 54.9 -> 66.4 ms (-21 %: one launch per 640 sources is ~80 us of work
+// there, all CTAs of a launch share the sources so a single wave is either quantised or unbalanced over the 4 schedulers).
+// Hence the default (mode -1 "auto"): used for velocity launches with >= 1e6 targets per rank (LPMX_CONST_MIN_TARGETS), the
+// stream-K ring kernel everywhere else.  LPMX_CONST_STREAM=0 turns it off, =1 forces overlapped copies, =2 copies on the
+// compute stream; lpmx_pair_sum_const_stream() sets the same per handle.
 //
 // Why: pair_sum_kernel (lpmx_pair_kernel.cuh) is bound by FP64 issue and reaches 81 % of the pipe because 5 of its 9
 // DFMAs per pair read a third distinct register operand (profiles/README.md, "Why 81 %").  A source record is the same
@@ -13,12 +17,13 @@
 // per launch -- three orders of magnitude below the FP64 time), while a device-to-device copy on the handle's copy
 // stream fills the other half for the next launch.  All CTAs of a launch read the same sources, so the work cannot be
 // split over sources the way the stream-K kernel does; the chip is balanced by the launch shape instead: one CTA per SM,
-// and (T targets per thread) x (NW warps) chosen so that waves x 148 x 32 x T x NW covers the targets with the least
+// and (T = 4..8 targets per thread) x (NW = 8 or 12 warps) chosen so that waves x 148 x 32 x T x NW covers the targets with the least
 // excess.  That needs >= ~2e5 targets per rank; smaller launches keep the ring kernel.
 //
 // Same arithmetic per pair as Pair<kVel> (bit-identical terms); per target the terms are added in source order, so the
 // sums differ from the stream-K kernel's by round-off only (the tolerance of every parity test covers both).
 #include <cstdlib>
+#include <mutex>
 
 #include "lpmx_const_stream_body.h"
 #include "lpmx_internal.h"
@@ -81,15 +86,32 @@ cs_kernel_t cs_kernel_for(int T) {
 
 }  // namespace
 
+// -1 auto (overlapped copies, large launches only), 0 off, 1 overlapped copies, 2 copies on the compute stream
 int const_stream_mode(lpmx_handle_t h) {
   if (h->const_stream >= 0) return h->const_stream;
-  static int env = -1;
-  if (env < 0) {
+  static const int env = [] {
     const char* e = getenv("LPMX_CONST_STREAM");
-    env = e ? atoi(e) : 0;
-    if (env < 0 || env > 2) env = 0;
-  }
+    const int v = e ? atoi(e) : -1;
+    return (v < -1 || v > 2) ? -1 : v;
+  }();
   return env;
+}
+
+// The bank is ONE __constant__ array per device (module scope), ordered only by the using handle's streams and events: two
+// handles on the same device must not stream through it at once.  The first handle to take the path on a device owns the
+// bank until lpmx_destroy; any other handle on that device keeps the ring kernel.
+static std::mutex g_bank_mutex;
+static lpmx_handle_t g_bank_owner[64] = {};
+static bool claim_bank(lpmx_handle_t h) {
+  if (h->device < 0 || h->device >= 64) return false;
+  std::lock_guard<std::mutex> lk(g_bank_mutex);
+  if (!g_bank_owner[h->device]) g_bank_owner[h->device] = h;
+  return g_bank_owner[h->device] == h;
+}
+static void release_bank(lpmx_handle_t h) {
+  if (h->device < 0 || h->device >= 64) return;
+  std::lock_guard<std::mutex> lk(g_bank_mutex);
+  if (g_bank_owner[h->device] == h) g_bank_owner[h->device] = nullptr;
 }
 
 // One CTA per SM; a launch takes ~ waves x T x NW while the FP64 pipe is the limit (>= 8 warps).  Least excess wins,
@@ -110,10 +132,12 @@ void pick_const_shape(int num_sms, int n_tgt, int* T_out, int* nw_out, int* grid
   if (ft) {
     bt = ft, bnw = fnw;
   } else {
-    const int order[3] = {6, 7, 5};
-    for (int oi = 0; oi < 3; ++oi) {
+    // warps per CTA in multiples of 4: with 9-11 warps two of the SM's four schedulers carry one warp more and the CTA waits
+    // for them (measured: T = 5 with 10 warps 66.4 ms where 8 balanced warps would take 54; profiles/r2b_shape_sweep.txt)
+    const int order[5] = {6, 7, 5, 8, 4};
+    for (int oi = 0; oi < 5; ++oi) {
       const int T = order[oi];
-      for (int nw = 12; nw >= 8; --nw) {
+      for (int nw = 12; nw >= 8; nw -= 4) {
         const long tb = (long)T * nw * 32;
         const long ctas = (n_tgt + tb - 1) / tb;
         const long waves = (ctas + num_sms - 1) / num_sms;
@@ -129,12 +153,15 @@ void pick_const_shape(int num_sms, int n_tgt, int* T_out, int* nw_out, int* grid
 }
 
 bool make_const_plan(lpmx_handle_t h, int n_tgt, int n_src, SumPlan* p) {
-  if (const_stream_mode(h) == 0) return false;
-  // below these sizes the launches cannot fill the chip (one CTA per SM, >= 8 warps, >= 5 targets per thread) or are
-  // too short against their own launch overhead
-  long min_tgt = (long)h->num_sms * 32 * 8 * 5;
+  const int mode = const_stream_mode(h);
+  if (mode == 0) return false;
+  // auto: only where a launch (640 sources x all targets of the rank) is long against its fixed costs -- launch gap, target
+  // loads, the read-modify-write of the accumulators, wave quantisation: measured break-even ~1e6 targets (file header).
+  // forced (1 / 2): wherever one launch can fill the chip at all.
+  long min_tgt = mode < 0 ? 1000000L : (long)h->num_sms * 32 * 8 * 5;
   if (const char* e = getenv("LPMX_CONST_MIN_TARGETS")) min_tgt = atol(e);  // parity tests on small meshes
   if ((long)n_tgt < min_tgt || n_tgt < 1 || n_src < 4 * kCsHalf) return false;
+  if (!claim_bank(h)) return false;
   int T, nw, grid;
   pick_const_shape(h->num_sms, n_tgt, &T, &nw, &grid);
   p->kind = kVel;
@@ -220,6 +247,7 @@ int launch_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const i
 }
 
 void const_stream_teardown(lpmx_handle_t h) {
+  release_bank(h);
   for (int i = 0; i < 5; ++i)
     if (h->cs_events[i]) {
       cudaEventDestroy(h->cs_events[i]);
@@ -238,5 +266,6 @@ extern "C" int lpmx_const_stream_shape(int num_sms, int n_tgt, int* T, int* n_wa
 extern "C" int lpmx_pair_sum_const_stream(lpmx_handle_t h, int mode) {
   if (!h || mode < -1 || mode > 2) return LPMX_ERR_INVALID;
   h->const_stream = mode;
+  if (mode == 0) lpmx::release_bank(h);
   return LPMX_OK;
 }

@@ -30,6 +30,15 @@
 #define ORACLE_PI 3.1415926535897932384626433832795027975 /* lpm_constants.hpp:11 */
 #define ORACLE_ZERO_TOL 2.220446049250313e-16             /* lpm_floating_point.hpp:22 */
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the timed CPU legs set the team size explicitly */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
@@ -434,6 +443,51 @@ void oracle_swe_sphere_sums(int n_tgt, const double* tx, int n_src, const double
     ddot[i] = dd;
     if (grad9)
       for (int k = 0; k < 9; ++k) grad9[9L * i + k] = s[3 + k];
+  }
+}
+
+/* Higher-precision adjudicator of the family C sums (long double pair arithmetic and accumulation, the same formulas as
+ * oracle_swe_velocity_sums): the 1/d^2 gradient terms are O(N) each and cancel to O(1), so two correct double-precision
+ * summations differ by ~N * 2^-53 and ddot by more; this settles which side of a comparison carries the error.  Not a
+ * restatement of anything in the reference.  Sequential j, as the reference. */
+void oracle_swe_sphere_sums_ld(int n_tgt, const double* tx, int n_src, const double* sx, const double* zeta,
+                               const double* sigma, const double* area, const uint8_t* mask, double eps,
+                               int targets_are_sources, double* vel, double* ddot, double* grad9) {
+  if (targets_are_sources) tx = sx;
+  const int collocated = targets_are_sources && (fabs(eps) < ORACLE_ZERO_TOL);
+  const long double four_pi = 4 * 3.14159265358979323846264338327950288L;
+  const long double kappa = 1 + (long double)eps * eps;
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n_tgt; ++i) {
+    long double s[12];
+    for (int k = 0; k < 12; ++k) s[k] = 0;
+    const long double x[3] = {tx[3 * i], tx[3 * i + 1], tx[3 * i + 2]};
+    for (int j = 0; j < n_src; ++j) {
+      if (mask[j] || (collocated && i == j)) continue;
+      const long double y[3] = {sx[3 * j], sx[3 * j + 1], sx[3 * j + 2]};
+      const long double xy = x[0] * y[0] + x[1] * y[1] + x[2] * y[2];
+      const long double d = kappa - xy;
+      const long double rot = -(long double)zeta[j] * area[j], pot = -(long double)sigma[j] * area[j];
+      const long double c[3] = {x[1] * y[2] - x[2] * y[1], x[2] * y[0] - x[0] * y[2], x[0] * y[1] - x[1] * y[0]};
+      const long double q[3] = {kappa * x[0] - y[0], kappa * x[1] - y[1], kappa * x[2] - y[2]};
+      const long double p[3] = {y[0] - xy * x[0], y[1] - xy * x[1], y[2] - xy * x[2]};
+      const long double yx[9] = {0, -y[2], y[1], y[2], 0, -y[0], -y[1], y[0], 0};
+      const long double inv1 = 1 / (four_pi * d), inv2 = 1 / (four_pi * d * d);
+      for (int a = 0; a < 3; ++a) {
+        s[a] += c[a] * rot * inv1 + p[a] * pot * inv1; /* kzeta + ksigma (P_x y = y - (x.y) x) */
+        for (int b = 0; b < 3; ++b) {
+          const long double P = (a == b ? 1.0L : 0.0L) - x[a] * x[b];
+          s[3 + 3 * a + b] += (d * yx[3 * a + b] + c[a] * q[b]) * inv2 * rot - (d * xy * P + q[a] * p[b]) * inv2 * pot;
+        }
+      }
+    }
+    for (int k = 0; k < 3; ++k) vel[3 * i + k] = (double)s[k];
+    long double dd = 0;
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) dd += s[3 + 3 * a + b] * s[3 + 3 * b + a];
+    ddot[i] = (double)dd;
+    if (grad9)
+      for (int k = 0; k < 9; ++k) grad9[9L * i + k] = (double)s[3 + k];
   }
 }
 

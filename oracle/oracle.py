@@ -153,6 +153,20 @@ def swe_sphere_sums(tgt_xyz, src_xyz, vort, div, area, mask, eps=0.0, targets_ar
     return vel, ddot, grad
 
 
+def swe_sphere_sums_ld(tgt_xyz, src_xyz, vort, div, area, mask, eps=0.0, targets_are_sources=False, L=None):
+    """Long-double adjudicator of swe_sphere_sums (oracle_swe_sphere_sums_ld): (vel, ddot, grad9) rounded to double."""
+    L = L or lib()
+    src_xyz, vort, div, area = _d(src_xyz), _d(vort), _d(div), _d(area)
+    mask, mp = _m(mask)
+    tx = src_xyz if targets_are_sources else _d(tgt_xyz)
+    n = tx.shape[0]
+    vel, ddot, grad = np.zeros((n, 3)), np.zeros(n), np.zeros((n, 9))
+    L.oracle_swe_sphere_sums_ld(ctypes.c_int(n), _p(tx), ctypes.c_int(src_xyz.shape[0]), _p(src_xyz), _p(vort), _p(div),
+                                _p(area), mp, ctypes.c_double(eps), ctypes.c_int(int(targets_are_sources)), _p(vel), _p(ddot),
+                                _p(grad))
+    return vel, ddot, grad
+
+
 # ---- SWE RK2 (family C stepper) ---------------------------------------------------------------------
 LAPS_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _dp, _dp, _dp, ctypes.c_int, _dp, _dp,
                            _up, _dp)

@@ -47,6 +47,15 @@ inline scalar_view_type wrap1(const double* p, int n) { return scalar_view_type(
 
 extern "C" {
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the timed CPU legs set the team size explicitly */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -2,9 +2,10 @@
 divide_flagged_faces) and BVESphere + BVERK4::advance_timestep, compiled in place from /root/reference/src against
 oracle/kokkos_shim (oracle/ref_mesh_driver.cpp, `make -C oracle ref`).  TEST INFRASTRUCTURE ONLY: imported by the golden
 generators under tests/golden/ and by the live comparisons in tests/ (skipped where the library is not built).  The library
-travels to the GPU box with the snapshot; /root/reference itself is needed only to build it (and at run time for the
-mesh_seeds/*.dat files the reference's MeshSeed reads: the mesh entry points therefore work in the build container only,
-`available()` says which)."""
+travels to the GPU box with the snapshot; /root/reference itself is needed only to build it.  The reference's MeshSeed reads
+mesh_seeds/*.dat at run time: where /root/reference is not mounted (the GPU box) the four files are rewritten from
+tests/golden/seed_tables.npz (the same numbers, as the reference's parser read them; repr() round-trips doubles) into a temporary
+directory that $LPM_ORACLE_SEED_DIR points the library at (oracle/kokkos_shim/LpmConfig.h)."""
 import ctypes
 import os
 
@@ -14,17 +15,50 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(_HERE, "_ref", "liblpm_ref_mesh.so")
 SEED_DIR = "/root/reference/mesh_seeds"  # LPM_MESH_SEED_DIR of oracle/kokkos_shim/LpmConfig.h
 SEED_ID = {"icos": 0, "cubed": 1, "quad_rect": 2, "tri_hex": 3}
+SEED_FILE = {"icos": "icosTriSphereSeed.dat", "cubed": "cubedSphereSeed.dat", "quad_rect": "quadRectSeed.dat",
+             "tri_hex": "triHexSeed.dat"}
+SEED_TABLES = os.path.join(os.path.dirname(_HERE), "tests", "golden", "seed_tables.npz")
 
 _lib = None
 
 
 def available():
-    return os.path.exists(LIB) and os.path.isdir(SEED_DIR)
+    return os.path.exists(LIB) and (os.path.isdir(SEED_DIR) or os.path.exists(SEED_TABLES))
+
+
+def write_seed_files(dirname):
+    """The four seed files in the layout MeshSeed<Seed>::read_file parses (src/mesh/lpm_mesh_seed.cpp:20-206): a header line,
+    nverts + nfaces coordinate lines, then the blocks edgeO / faceverts / faceedges / vertEdges, each `n` lines after its keyword."""
+    t = np.load(SEED_TABLES)
+    for seed, fname in SEED_FILE.items():
+        crds, edges = t[f"{seed}_crds"], t[f"{seed}_edges"]
+        out = ["x   y" + ("   z" if crds.shape[1] == 3 else "")]
+        out += ["  ".join(repr(float(v)) for v in row) for row in crds]
+        out.append("edgeO      edgeD       edgeLeft        edgeRight")
+        out += ["  ".join(str(int(v)) for v in row) for row in edges]
+        out.append("faceverts")
+        out += [" ".join(str(int(v)) for v in row) for row in t[f"{seed}_face_verts"]]
+        out.append("faceedges")
+        out += [" ".join(str(int(v)) for v in row) for row in t[f"{seed}_face_edges"]]
+        out.append("vertEdges")
+        out += [" ".join(str(int(v)) for v in row) for row in t[f"{seed}_vert_edges"]]
+        with open(os.path.join(dirname, fname), "w") as f:
+            f.write("\n".join(out) + "\n")
+
+
+def _seed_dir():
+    if os.path.isdir(SEED_DIR) and not os.environ.get("LPM_ORACLE_FORCE_REWRITTEN_SEEDS"):
+        return SEED_DIR
+    import tempfile
+    d = tempfile.mkdtemp(prefix="lpm_seed_files_")
+    write_seed_files(d)
+    return d
 
 
 def lib():
     global _lib
     if _lib is None:
+        os.environ["LPM_ORACLE_SEED_DIR"] = _seed_dir()
         L = ctypes.CDLL(LIB)
         L.ref_mesh_create.restype = ctypes.c_void_p
         L.ref_mesh_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int]

@@ -51,4 +51,11 @@ if __name__ == "__main__":
         tabs[f"{seed}_edges"] = np.stack([a["edge_origs"], a["edge_dests"], a["edge_lefts"], a["edge_rights"]], axis=1).astype(np.int32)
         tabs[f"{seed}_face_verts"] = a["face_verts"].astype(np.int32)
         tabs[f"{seed}_face_edges"] = a["face_edges"].astype(np.int32)
+    # the vertEdges block of each file (read by MeshSeed::read_file, not exposed by the mesh classes) straight from the .dat,
+    # so that oracle/ref_mesh.write_seed_files can rewrite complete seed files where /root/reference is not mounted
+    for seed, fname in ref_mesh.SEED_FILE.items():
+        lines = open(os.path.join(ref_mesh.SEED_DIR, fname)).read().splitlines()
+        k = next(i for i, ln in enumerate(lines) if "vertEdges" in ln)
+        nv = len(tabs[f"{seed}_crds"]) - len(tabs[f"{seed}_face_verts"])
+        tabs[f"{seed}_vert_edges"] = np.array([[int(t) for t in ln.split()] for ln in lines[k + 1:k + 1 + nv]], dtype=np.int32)
     np.savez_compressed(os.path.join(HERE, "seed_tables.npz"), **tabs)

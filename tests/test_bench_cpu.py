@@ -23,8 +23,29 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["gpu_launches"] == 0
     assert d["config"]["workload"] == "rh54_cubed5" and d["config"]["stepper"] == "bve_rk4"
     cb = d["cpu_baseline"]
-    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "512 vertex targets" in cb["sample"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"]
+    assert "vertex targets (BVEVertexVelocity)" in cb["sample"] and "face targets (BVEFaceVelocity" in cb["sample"]
+    # the same config keys as the product arm prints (the driver compares the two objects)
+    assert set(d["config"]) == {"workload", "description", "stepper", "evals_per_step", "n_verts", "n_faces", "n_leaf_sources",
+                                "interactions_per_eval", "dt", "Omega", "parallelism", "l2"}
+    assert "full_step_ms_extrapolated" in d and d["ms_per_step"] < d["full_step_ms_extrapolated"]
     assert d["e2e"] == {"value": d["value"], "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_uses_all_host_threads_under_torchrun_and_is_bounded():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to its workers (round 1: the 32-core arm ran on one thread and timed out at
+    N = 2, 4, 8).  The arm sets the team size itself and sizes its sample by a calibration run (--ref-seconds per step)."""
+    import time
+    env = dict(os.environ, RANK="0", LOCAL_RANK="0", WORLD_SIZE="4", OMP_NUM_THREADS="1")
+    t0 = time.time()
+    p = subprocess.run([sys.executable, BENCH, "--impl", "reference", "--workload", "rh54_cubed5", "--steps", "2", "--warmup", "1",
+                        "--gpus", "4", "--ref-seconds", "0.5"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = json.loads(p.stdout.strip().splitlines()[-1])
+    want = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    assert d["cpu_baseline"]["cores"] == want and d["n_gpus"] == 4
+    assert "over 4 GPU(s)" in d["config"]["parallelism"]
+    assert time.time() - t0 < 120
 
 
 def test_reference_arm_runs_on_rank_zero_only():

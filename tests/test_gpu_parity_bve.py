@@ -341,6 +341,12 @@ def test_rk4_step_at_cubed7_sampled_targets_against_the_oracle(engine, oracle):
     check_err("vert_xyz[sample]", field_rel_err(out[0][idx], ref["vert_xyz"]), VEL_TOL)
     check_err("vert_zeta[sample]", field_rel_err(out[1][idx], ref["vert_zeta"]), VORT_TOL)
     check_err("vert_vel[sample]", field_rel_err(out[2][idx], ref["vert_vel"]), VEL_TOL)
+    # whose round-off is it?  98 304 terms added one after the other (the reference's nested reduce) against the engine's
+    # chunked sums, both against a long-double sum at the engine's own final state
+    ld = oracle.bve_velocity(out[0][idx], out[3], out[4], area, mask, long_double=True)
+    fp = oracle.bve_velocity(out[0][idx], out[3], out[4], area, mask)
+    check_err("reference FP64 velocity vs long double [sample]", field_rel_err(fp, ld), VEL_TOL)
+    check_err("engine velocity vs long double [sample]", field_rel_err(out[2][idx], ld), VEL_TOL)
     check_err("face_xyz", field_rel_err(out[3], ref["face_xyz"]), VEL_TOL)
     check_err("face_zeta", field_rel_err(out[4], ref["face_zeta"]), VORT_TOL)
     check_err("face_vel", field_rel_err(out[5], ref["face_vel"]), VEL_TOL)

@@ -74,12 +74,33 @@ def device_laplacian(stage, stream, n_p, pxyz, psurf, plaps, n_a, axyz, asurf, a
     ck(rt.cudaMemcpy(alaps, al.ctypes.data, 8 * n_a, K.cudaMemcpyHostToDevice))
 
 
-def compare(got, ref, mask, tol_state=1e-10, tol_sums=1e-12):
+def ddot_tolerance(oracle, got, eps, n_sample=512):
+    """ddot = sum_ab G_ab G_ba of the accumulated velocity gradient.  The gradient kernels are 1/d^2: single terms are O(N)
+    and cancel to O(1), so ANY double-precision summation carries ~N 2^-53 (measured for the reference arithmetic against a
+    long-double evaluation of the same formulas, oracle_swe_sphere_sums_ld: 3e-13 at cubed-4, 1.4e-12 at cubed-5, 4.6e-12 at
+    cubed-6, x4 per level).  The contract is therefore stated against the extended-precision value, on a sample of the passive
+    particles at the ENGINE's own final state: the engine may be no farther from it than 2 x the reference arithmetic is
+    (floor 1e-12), and the engine-vs-oracle tolerance for ddot is 8 x the reference arithmetic's own error (floor 1e-12)."""
+    n = got.p["xyz"].shape[0]
+    idx = np.arange(0, n, max(1, n // n_sample))
+    src = (got.a["xyz"], got.a["vort"], got.a["div"], got.a["area"], got.mask)
+    _, dd_ref, _ = oracle.swe_sphere_sums(got.p["xyz"][idx], *src, eps=eps)
+    _, dd_ld, _ = oracle.swe_sphere_sums_ld(got.p["xyz"][idx], *src, eps=eps)
+    scale = np.abs(dd_ld).max()
+    if scale == 0:
+        return 1e-12
+    e_ref = np.abs(dd_ref - dd_ld).max() / scale
+    e_gpu = np.abs(got.p["ddot"][idx] - dd_ld).max() / scale
+    check_err("reference FP64 ddot vs long double (sample)", e_ref, 1e-9)
+    check_err("engine ddot vs long double (sample)", e_gpu, max(1e-12, 2 * e_ref))
+    return max(1e-12, 8 * e_ref)
+
+
+def compare(got, ref, mask, tol_state=1e-10, tol_sums=1e-12, tol_ddot=1e-12):
     """After n steps every field is a function of the advected state: <= 1e-10 (north_star's bound for stepped
-    quantities); the velocity sums additionally hold 1e-12.  ddot = sum_ab G_ab G_ba cancels (|ddot| << |G|^2), so
-    its rounding error relative to max|ddot| is a few 1e-12: it is held to 1e-11."""
+    quantities); the velocity sums additionally hold 1e-12; ddot holds tol_ddot (see ddot_tolerance)."""
     leaf = mask == 0
-    tol_of = {"vel": tol_sums, "ddot": tol_sums}
+    tol_of = {"vel": tol_sums, "ddot": tol_ddot}
     for k in PASSIVE_FIELDS:
         tol = tol_of.get(k, tol_state)
         if np.abs(ref.p[k]).max() == 0:
@@ -105,7 +126,7 @@ def test_swe_rk2_in_place_frozen_laplacian(engine, oracle, meshes, seed, depth, 
     ref = oracle.swe_rk2_step(0.01, OMEGA, G, eps, st0.copy(), None, n_steps=nsteps)
     got = st0.copy()
     swe_rk2_step(engine, 0.01, OMEGA, G, eps, got.p, got.a, got.mask, None, n_steps=nsteps)
-    compare(got, ref, m.face_mask)
+    compare(got, ref, m.face_mask, tol_ddot=ddot_tolerance(oracle, got, eps))
 
 
 def test_swe_rk2_step_at_cubed6_every_target_against_the_oracle(engine, oracle):
@@ -119,7 +140,7 @@ def test_swe_rk2_step_at_cubed6_every_target_against_the_oracle(engine, oracle):
     ref = oracle.swe_rk2_step(dt, OMEGA, G, 0.0, st0.copy(), None, n_steps=1)
     got = st0.copy()
     swe_rk2_step(engine, dt, OMEGA, G, 0.0, got.p, got.a, got.mask, None, n_steps=1)
-    compare(got, ref, m.face_mask)
+    compare(got, ref, m.face_mask, tol_ddot=ddot_tolerance(oracle, got, 0.0, n_sample=2048))
 
 
 def test_swe_rk2_with_laplacian_provider(engine, oracle, meshes):

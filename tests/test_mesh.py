@@ -246,3 +246,27 @@ def test_generator_geometry_equals_reference_functions_compiled_in_place(seed, d
         assert np.array_equal(out, m.vert_xyz[m.edge_dests[m.edge_kids[e][0]]])
         n_checked += 1
     assert n_checked > 0 or depth == 0
+
+
+def test_compiled_reference_reads_the_rewritten_seed_files_identically():
+    """Where /root/reference is not mounted (the GPU box) oracle/ref_mesh.py rewrites the four mesh_seeds/*.dat files from
+    tests/golden/seed_tables.npz for the reference's own parser (MeshSeed<Seed>::read_file).  In a fresh process that is forced
+    onto the rewritten files, the compiled reference must build the committed fixtures bit for bit."""
+    import subprocess
+    import sys
+    ref_mesh = _ref_mesh_or_skip()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import numpy as np, os, sys\n"
+            "sys.path.insert(0, %r)\n"
+            "from oracle import ref_mesh\n"
+            "for seed, depth, r in (('icos', 2, 1.0), ('cubed', 3, 1.0), ('quad_rect', 2, 1.0), ('tri_hex', 2, 1.0)):\n"
+            "    f = 'mesh_%%s_%%d%%s.npz' %% (seed, depth, '' if seed in ('icos', 'cubed') else '_r1')\n"
+            "    g = np.load(os.path.join(%r, f))\n"
+            "    m = ref_mesh.RefMesh(seed, depth, r)\n"
+            "    a = m.arrays()\n"
+            "    assert all(np.array_equal(g[k], a[k]) for k in g.files), (seed, depth)\n"
+            "assert os.environ['LPM_ORACLE_SEED_DIR'] != ref_mesh.SEED_DIR\n"
+            "print('ok')\n") % (root, GOLDEN)
+    env = dict(os.environ, LPM_ORACLE_FORCE_REWRITTEN_SEEDS="1")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert p.returncode == 0 and "ok" in p.stdout, p.stdout + p.stderr
