@@ -237,6 +237,16 @@ int lpmx_bve_streamfn(lpmx_handle_t h, const double* tgt_xyz, int tgt_layout, lo
                       const double* src_area, const unsigned char* src_mask, int n_src,
                       int collocated, double* out_psi);
 
+/* BVEVertexSolve (collocated=0, src/lpm_bve_sphere_kernels.hpp:90-132) / BVEFaceSolve (collocated=1, :284-320): stream function
+ * AND velocity of the same targets, which the reference computes as two nested reductions per team
+ * (StreamReduce* then VelocityReduce*).  Here: ONE pass of the fused (u, psi) pair kernel, i.e. the reciprocal and the
+ * logarithm of the same d = 1 - x.y per pair.  Values equal lpmx_bve_streamfn + lpmx_bve_velocity up to summation order.
+ * out_psi: Real[n_tgt], out_vel: Real*[3].  (No caller inside the reference; provided for completeness of the functor set.) */
+int lpmx_bve_solve(lpmx_handle_t h, const double* tgt_xyz, int tgt_layout, long tgt_ld, int n_tgt,
+                   const double* src_xyz, int src_layout, long src_ld, const double* src_vort,
+                   const double* src_area, const unsigned char* src_mask, int n_src,
+                   int collocated, double* out_psi, double* out_vel);
+
 /* Incompressible2DPassiveSums<SphereGeometry> (collocated_targets=0,
  * src/lpm_incompressible2d_kernels.hpp:144-193) and Incompressible2DActiveSums (collocated
  * targets, :201-246; the self term is skipped only when |eps| < DBL_EPSILON, :235), with
@@ -328,7 +338,16 @@ int lpmx_ic2d_solver_get_state(lpmx_ic2d_solver_t s, double* passive_xyz, double
                                int layout, long passive_ld, long active_ld);
 /* Incompressible2D::init_direct_sums on the resident state */
 int lpmx_ic2d_solver_init_direct_sums(lpmx_ic2d_solver_t s);
+/* n_steps x Incompressible2DRK2::advance_timestep_impl on the resident state.  The stream function of the new state is an
+ * output of a step that no later step reads (the predictor's psi is overwritten by the corrector's, and the corrector's by the
+ * next step's: src/lpm_incompressible2d_rk2_impl.hpp:113-124,157-170), and evaluating it costs more than the velocity.  It is
+ * therefore LAZY: advance() fuses psi into its last evaluation only if psi was read (get_state with a psi pointer) since the
+ * previous advance; otherwise it runs velocity-only evaluations and the next reader of psi triggers one psi-only pass over the
+ * retained state.  Values are the same sums either way (round-off of the summation order aside).  All ranks of a sharded
+ * solver must make the same get_state calls (they already must: get_state gathers). */
 int lpmx_ic2d_solver_advance(lpmx_ic2d_solver_t s, double dt, double Omega, int n_steps);
+/* Override the laziness for the next advance: demand_next != 0 fuses psi into its final evaluation, 0 leaves it stale. */
+int lpmx_ic2d_solver_lazy_stream_fn(lpmx_ic2d_solver_t s, int demand_next);
 
 /* ------------------------------------------------------------------------------------------
  * Per-step diagnostics of the callers (the O(N) tail of every example's time loop).

@@ -148,6 +148,7 @@ def _declare(L):
         "lpmx_fp64_peak_tflops": [vp, c_double_p, c_double_p],
         "lpmx_bve_velocity": [vp, vp, i, l, i, vp, i, l, vp, vp, vp, i, i, vp],
         "lpmx_bve_streamfn": [vp, vp, i, l, i, vp, i, l, vp, vp, vp, i, i, vp],
+        "lpmx_bve_solve": [vp, vp, i, l, i, vp, i, l, vp, vp, vp, i, i, vp, vp],
         "lpmx_ic2d_sums": [vp, vp, i, l, i, vp, i, l, vp, vp, vp, i, d, i, vp, vp],
         "lpmx_swe_sphere_sums": [vp, vp, i, l, i, vp, i, l, vp, vp, vp, vp, i, d, i, i, vp, vp, vp],
         "lpmx_bve_rk4_step": [vp, d, d, i, vp, vp, vp, i, vp, vp, vp, vp, vp, i, l, l, i],
@@ -166,6 +167,7 @@ def _declare(L):
         "lpmx_ic2d_solver_get_state": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, l, l],
         "lpmx_ic2d_solver_init_direct_sums": [vp],
         "lpmx_ic2d_solver_advance": [vp, d, d, i],
+        "lpmx_ic2d_solver_lazy_stream_fn": [vp, i],
         "lpmx_ic2d_totals": [vp, i, vp, vp, i, l, vp, vp, c_double_p, c_double_p, c_double_p],
         "lpmx_ic2d_solver_totals": [vp, c_double_p, c_double_p, c_double_p],
         "lpmx_err_norms": [vp, i, i, vp, vp, i, l, vp, c_double_p, c_double_p, c_double_p],

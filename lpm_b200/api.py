@@ -399,6 +399,19 @@ class Engine:
                                               int(bool(collocated)), _ptr(out)), "lpmx_bve_streamfn")
         return out
 
+    def bve_solve(self, tgt_xyz, src_xyz, src_vort, src_area, src_mask, collocated=False, layout=LAYOUT_RIGHT,
+                  n_tgt=None, n_src=None, tgt_ld=0, src_ld=0):
+        """BVEVertexSolve / BVEFaceSolve: (psi, velocity) of the targets in one pass of the fused pair kernel."""
+        tgt_xyz, src_xyz, n_tgt, n_src, tgt_ld, src_ld = self._sums_common(
+            None if collocated else tgt_xyz, src_xyz, layout, n_tgt, n_src, tgt_ld, src_ld)
+        src_vort, src_area, src_mask = _f64(src_vort), _f64(src_area), _u8(src_mask)
+        vel = _empty_like_vec(src_xyz, n_tgt, layout, tgt_ld)
+        psi = _empty_like_scalar(src_xyz, n_tgt)
+        self._check(self._L.lpmx_bve_solve(self._h, _ptr(tgt_xyz), layout, tgt_ld, n_tgt, _ptr(src_xyz), layout, src_ld,
+                                           _ptr(src_vort), _ptr(src_area), _ptr(src_mask), n_src, int(bool(collocated)),
+                                           _ptr(psi), _ptr(vel)), "lpmx_bve_solve")
+        return psi, vel
+
     def ic2d_sums(self, tgt_xyz, src_xyz, src_vort, src_area, src_mask, eps=0.0, targets_are_sources=False,
                   with_psi=True, layout=LAYOUT_RIGHT, n_tgt=None, n_src=None, tgt_ld=0, src_ld=0):
         """Incompressible2DPassiveSums (targets_are_sources=False) / ActiveSums (True)."""
@@ -709,6 +722,10 @@ class IC2DSolver:
         self.e._check(self.e._L.lpmx_ic2d_solver_totals(self._s, ctypes.byref(v), ctypes.byref(k), ctypes.byref(e)),
                       "lpmx_ic2d_solver_totals")
         return v.value, k.value, e.value
+
+    def lazy_stream_fn(self, demand_next):
+        """Override the lazy-psi heuristic for the next advance (True: fuse psi into its final evaluation)."""
+        self.e._check(self.e._L.lpmx_ic2d_solver_lazy_stream_fn(self._s, int(bool(demand_next))), "lpmx_ic2d_solver_lazy_stream_fn")
 
     def advance(self, dt, Omega, n_steps=1):
         self.e._check(self.e._L.lpmx_ic2d_solver_advance(self._s, float(dt), float(Omega), n_steps),

@@ -17,7 +17,7 @@
 // per launch -- three orders of magnitude below the FP64 time), while a device-to-device copy on the handle's copy
 // stream fills the other half for the next launch.  All CTAs of a launch read the same sources, so the work cannot be
 // split over sources the way the stream-K kernel does; the chip is balanced by the launch shape instead: one CTA per SM,
-// and (T = 4..8 targets per thread) x (NW = 8 or 12 warps) chosen so that waves x 148 x 32 x T x NW covers the targets with the least
+// and (T = 5..7 targets per thread) x 8 warps chosen so that waves x 148 x 32 x T x NW covers the targets with the least
 // excess.  That needs >= ~2e5 targets per rank; smaller launches keep the ring kernel.
 //
 // Same arithmetic per pair as Pair<kVel> (bit-identical terms); per target the terms are added in source order, so the
@@ -134,10 +134,12 @@ void pick_const_shape(int num_sms, int n_tgt, int* T_out, int* nw_out, int* grid
   } else {
     // warps per CTA in multiples of 4: with 9-11 warps two of the SM's four schedulers carry one warp more and the CTA waits
     // for them (measured: T = 5 with 10 warps 66.4 ms where 8 balanced warps would take 54; profiles/r2b_shape_sweep.txt)
-    const int order[5] = {6, 7, 5, 8, 4};
-    for (int oi = 0; oi < 5; ++oi) {
+    // measured at icos-8 (profiles/r2e_icos8_const_shapes.txt): T = 5 / 8 warps 1.797e12, T = 6 / 8 warps 1.776e12 interactions/s,
+    // but T = 8 / 8 warps 1.649e12 and T = 6 / 12 warps 1.588e12 (below the ring kernel's 1.657e12): 8 warps, T <= 7
+    const int order[3] = {5, 6, 7};
+    for (int oi = 0; oi < 3; ++oi) {
       const int T = order[oi];
-      for (int nw = 12; nw >= 8; nw -= 4) {
+      for (int nw = 8; nw >= 8; nw -= 4) {
         const long tb = (long)T * nw * 32;
         const long ctas = (n_tgt + tb - 1) / tb;
         const long waves = (ctas + num_sms - 1) / num_sms;
@@ -161,9 +163,16 @@ bool make_const_plan(lpmx_handle_t h, int n_tgt, int n_src, SumPlan* p) {
   long min_tgt = mode < 0 ? 1000000L : (long)h->num_sms * 32 * 8 * 5;
   if (const char* e = getenv("LPMX_CONST_MIN_TARGETS")) min_tgt = atol(e);  // parity tests on small meshes
   if ((long)n_tgt < min_tgt || n_tgt < 1 || n_src < 4 * kCsHalf) return false;
-  if (!claim_bank(h)) return false;
   int T, nw, grid;
   pick_const_shape(h->num_sms, n_tgt, &T, &nw, &grid);
+  if (mode < 0) {
+    // auto: the path is worth +8.5 % of a launch that fills its waves; a rank whose targets leave the last wave mostly empty
+    // (1.2e6 targets: 7 waves at 90.6 %) is better served by the stream-K kernel, which has no wave quantisation
+    const long tb = (long)T * nw * 32;
+    const long waves = (grid + h->num_sms - 1) / h->num_sms;
+    if ((double)n_tgt < 0.95 * (double)(waves * h->num_sms * tb)) return false;
+  }
+  if (!claim_bank(h)) return false;
   p->kind = kVel;
   p->shape = kShapeConstStream;
   p->T = T;

@@ -70,7 +70,7 @@ LPMX_CS_HD void body(P& pf, const CsArgs& a) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       x[t][k] = valid ? a.tgt[tg * a.tgt_si + k * a.tgt_sk] : 0.0;  // a zero target sees d = kappa: finite, never read back
-      acc[t][k] = a.first ? 0.0 : a.acc[(long)k * a.n_tgt_pad + tg];
+      acc[t][k] = 0.0;  // two-level summation: this launch's 640 terms start from zero (see the store below)
     }
     self[t] = (valid && a.self_idx) ? a.self_idx[tg] : -1;
     hit |= (unsigned)(self[t] - a.j0) < (unsigned)kHalf;
@@ -83,8 +83,13 @@ LPMX_CS_HD void body(P& pf, const CsArgs& a) {
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const long tg = base_t + (long)t * lanes;
+    // the launch's partial sum is added to the running total once: the accumulated rounding of the factored sum scales with
+    // sqrt(640) + sqrt(N / 640) instead of sqrt(N) (lpmx_pair_kernel.cuh, "two-level summation")
 #pragma unroll
-    for (int k = 0; k < 3; ++k) a.acc[(long)k * a.n_tgt_pad + tg] = acc[t][k];
+    for (int k = 0; k < 3; ++k) {
+      double* p = a.acc + (long)k * a.n_tgt_pad + tg;
+      *p = a.first ? acc[t][k] : (*p + acc[t][k]);
+    }
   }
 }
 

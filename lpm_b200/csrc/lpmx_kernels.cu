@@ -26,6 +26,7 @@
 //     order (deterministic) and fuse all per-target algebra of the RK stage.
 #include <cub/device/device_scan.cuh>
 
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 
@@ -50,12 +51,13 @@ static int launch_cfg(lpmx_handle_t h, const SumPlan& p, const SumArgs& a) {
   auto kern = pair_sum_kernel<C>;
   // per template instance AND per device: the attribute belongs to the function in the device's context, and one process
   // may hold handles on several GPUs (lpmx_create(device_id))
-  constexpr int kMaxDev = 64;
-  static bool attr_set[kMaxDev] = {};
+  // one bit per device, atomic: handles may be driven from several host threads; setting the attribute twice is harmless
+  static std::atomic<unsigned long long> attr_set{0ull};
   const int dev = h->device;
-  if (dev < 0 || dev >= kMaxDev || !attr_set[dev]) {
+  const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
+  if (!bit || !(attr_set.load(std::memory_order_acquire) & bit)) {
     LPMX_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-    if (dev >= 0 && dev < kMaxDev) attr_set[dev] = true;
+    if (bit) attr_set.fetch_or(bit, std::memory_order_release);
   }
   kern<<<p.grid, C::THREADS, p.smem_bytes, h->stream>>>(a);
   ++h->launches;

@@ -23,18 +23,42 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+// Wait for a phase of a ring barrier.  Steady state: the first try_wait succeeds or suspends for the hardware's time limit.
+// A wait that keeps failing backs off (nanosleep after 1024 tries) and has a deadline: a bulk copy that faulted or a ring
+// protocol error would otherwise spin forever and take the GPU with it; after kMbarDeadlineNs the CTA traps, the launch
+// fails with a sticky CUDA error and the next lpmx_* call reports it.  A legitimate wait is microseconds (one 256-record
+// chunk of another warp's work).
+constexpr unsigned long long kMbarDeadlineNs = 4000000000ull;
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (uint32_t spins = 1;; ++spins) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((spins & 1023u) == 0) {
+      __nanosleep(256);
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > kMbarDeadlineNs) asm volatile("trap;");
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 // global -> shared bulk copy (TMA, SASS UBLKCP); bytes % 16 == 0, both addresses 16-byte aligned
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
@@ -64,6 +88,8 @@ __device__ const double2 kLogTable[kLogMEntries] = {
 #endif
 };
 
+// kinds whose chunk sums are formed from zero and added to the running total once per chunk (see pair_sum_kernel)
+__host__ __device__ constexpr bool kind_two_level(int k) { return k == kVel || k == kVelPsi || k == kPsi; }
 __host__ __device__ constexpr bool kind_has_log(int k) { return k == kVelPsi || k == kPsi || k == kPlaneVelPsi || k == kPlaneSwe; }
 
 // the two tables of one CTA: mtab (16-byte aligned) then ktab
@@ -479,7 +505,28 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) pair_sum_kernel(const Sum
       bool hit = false;
 #pragma unroll
       for (int t = 0; t < T; ++t) hit |= (unsigned)(self[t] - j0) < (unsigned)kChunk;
-      if (__any_sync(0xffffffffu, hit))
+      if (kind_two_level(KIND)) {
+        // two-level summation: the 256 terms of a chunk are added into accumulators that start from zero, and the chunk's
+        // sum is added to the running total once.  The factored velocity sum u = x cross sum(G y / d) carries a component
+        // of M along x that the cross product cancels (|M| / |u| ~ 2..50), so the rounding of a single running sum over N
+        // sources shows up amplified in u: measured 4.3e-13 of max|u| at cubed-7 and 1.2e-12 at icos-8 against a long-double
+        // sum where the reference's own sequential sum has 1.8e-13.  With chunk partials the accumulated rounding scales
+        // with sqrt(256) + sqrt(N / 256) instead of sqrt(N) (emulated at icos-7: 1.3e-12 -> 7e-14).  Cost: 3 DADD per target
+        // per 256 pairs.
+        double cacc[T][NACC];
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+#pragma unroll
+          for (int q = 0; q < NACC; ++q) cacc[t][q] = 0.0;
+        if (__any_sync(0xffffffffu, hit))
+          chunk_loop<KIND, T, C::UNROLL, true>(x, kx, a.kappa, a.aux, sp, j0, self, cacc, tbl);
+        else
+          chunk_loop<KIND, T, C::UNROLL, false>(x, kx, a.kappa, a.aux, sp, j0, self, cacc, tbl);
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+#pragma unroll
+          for (int q = 0; q < NACC; ++q) acc[t][q] += cacc[t][q];
+      } else if (__any_sync(0xffffffffu, hit))
         chunk_loop<KIND, T, C::UNROLL, true>(x, kx, a.kappa, a.aux, sp, j0, self, acc, tbl);
       else
         chunk_loop<KIND, T, C::UNROLL, false>(x, kx, a.kappa, a.aux, sp, j0, self, acc, tbl);

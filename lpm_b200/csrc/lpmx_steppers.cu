@@ -524,8 +524,15 @@ struct lpmx_bve_solver_s {
 };
 struct lpmx_ic2d_solver_s {
   SolverState st;
-  SumPlan plan_vel, plan_velpsi;
+  SumPlan plan_vel, plan_velpsi, plan_psi;
   double eps = 0;
+  // Lazy stream function.  psi of the new state is an OUTPUT of a step that no later step reads (quirk B-i), and the fused
+  // velocity + psi evaluation costs 2.4 x the velocity one.  advance() therefore ends with the velocity-only kernel and marks
+  // psi stale unless somebody read psi since the previous advance (psi_demanded: then the next advance fuses it again, which
+  // is cheaper than a separate pass); a reader of a stale psi (get_state with a psi pointer) triggers ONE psi-only pass over
+  // the retained state.  Same per-pair arithmetic either way; the sums differ by summation order only.
+  bool psi_stale = false;
+  bool psi_demanded = true;
 };
 
 extern "C" {
@@ -714,24 +721,56 @@ int lpmx_ic2d_solver_set_state(lpmx_ic2d_solver_t s, const double* px, const dou
   LPMX_TRY(solver_set_state(&s->st, px, pz, pu, ax, az, au, aa, am, layout, pld, ald, skip));
   LPMX_TRY(make_plan(s->st.h, kVel, s->st.t1 - s->st.t0, s->st.n_leaf, &s->plan_vel));
   LPMX_TRY(make_plan(s->st.h, kVelPsi, s->st.t1 - s->st.t0, s->st.n_leaf, &s->plan_velpsi));
+  LPMX_TRY(make_plan(s->st.h, kPsi, s->st.t1 - s->st.t0, s->st.n_leaf, &s->plan_psi));
+  s->psi_stale = false;
+  return LPMX_OK;
+}
+
+// one psi-only pass (kPsi) over the retained state: what the last evaluation of advance() left out
+static int ic2d_refresh_psi(lpmx_ic2d_solver_s* s) {
+  SolverState& st = s->st;
+  lpmx_handle_t h = st.h;
+  LPMX_CUDA(h, cudaSetDevice(h->device));
+  LPMX_TRY(pack_resident(&st));
+  LPMX_TRY(ensure_partials(&st, s->plan_psi));
+  LPMX_TRY(launch_pair_sum(h, s->plan_psi, st.local_view(st.X), st.self_idx + st.t0, st.packed[st.cur], 1.0 + s->eps * s->eps,
+                           st.partials));
+  const int n_local = st.t1 - st.t0;
+  if (n_local > 0) {
+    const int threads = 128, blocks = (n_local + threads - 1) / threads;
+    psi_out_kernel<<<blocks, threads, 0, h->stream>>>(part_view(s->plan_psi, st.partials), st.t0, n_local, st.Psi);
+    ++h->launches;
+    LPMX_CUDA(h, cudaGetLastError());
+  }
+  s->psi_stale = false;
   return LPMX_OK;
 }
 
 int lpmx_ic2d_solver_get_state(lpmx_ic2d_solver_t s, double* px, double* pz, double* pu, double* ppsi, double* ax,
                                double* az, double* au, double* apsi, int layout, long pld, long ald) {
   if (!s) return LPMX_ERR_INVALID;
+  if (ppsi || apsi) {
+    s->psi_demanded = true;
+    if (s->psi_stale) LPMX_TRY(ic2d_refresh_psi(s));
+  }
   return solver_get_state(&s->st, px, pz, pu, ppsi, ax, az, au, apsi, layout, pld, ald);
+}
+
+int lpmx_ic2d_solver_lazy_stream_fn(lpmx_ic2d_solver_t s, int demand_next) {
+  if (!s) return LPMX_ERR_INVALID;
+  s->psi_demanded = demand_next != 0;
+  return LPMX_OK;
 }
 
 // one evaluation: stage 1 = predictor (velocity only; its psi is overwritten by the corrector in
 // the reference, quirk B-i), stage 2 = velocity + stream function at the new state.  The same argument runs across
 // steps: inside a multi-step call the psi of every step but the last is overwritten by the next step before anyone can
 // read it, so only the final evaluation of the call uses the (2.4 x dearer) velocity + psi kernel.
-static int ic2d_eval(lpmx_ic2d_solver_s* s, int stage, int more, double dt, double Omega) {
+static int ic2d_eval(lpmx_ic2d_solver_s* s, int stage, int more, double dt, double Omega, bool want_psi = true) {
   SolverState& st = s->st;
   lpmx_handle_t h = st.h;
   const int n_local = st.t1 - st.t0;
-  const bool with_psi = (stage == 2) && !more;
+  const bool with_psi = (stage == 2) && !more && want_psi;
   const SumPlan& plan = with_psi ? s->plan_velpsi : s->plan_vel;
   const double kappa = 1.0 + s->eps * s->eps;
   LPMX_TRY(ensure_partials(&st, plan));
@@ -783,11 +822,14 @@ int lpmx_ic2d_solver_advance(lpmx_ic2d_solver_t s, double dt, double Omega, int 
     LPMX_CUDA(h, cudaGetLastError());
   }
   LPMX_TRY(exchange_packed(&st, st.packed[st.cur]));
+  const bool eager_psi = s->psi_demanded;  // somebody read psi since the last advance: fuse it into the final evaluation
   for (int step = 0; step < n_steps; ++step) {
     const int more = step + 1 < n_steps;
     LPMX_TRY(ic2d_eval(s, 1, more, dt, Omega));
-    LPMX_TRY(ic2d_eval(s, 2, more, dt, Omega));
+    LPMX_TRY(ic2d_eval(s, 2, more, dt, Omega, eager_psi));
   }
+  s->psi_stale = !eager_psi;
+  s->psi_demanded = false;
   return LPMX_OK;
 }
 
@@ -826,6 +868,7 @@ int lpmx_ic2d_rk2_step(lpmx_handle_t h, double dt, double Omega, double eps, int
     h->cached_ic2d = s;
   }
   LPMX_TRY(lpmx_ic2d_solver_set_state(s, px, pz, pu, ax, az, au, aa, am, layout, pld, ald));
+  s->psi_demanded = (ppsi != nullptr) || (apsi != nullptr);  // the caller's psi views are outputs of this very call
   LPMX_TRY(lpmx_ic2d_solver_advance(s, dt, Omega, n_steps));
   return lpmx_ic2d_solver_get_state(s, px, pz, pu, ppsi, ax, az, au, apsi, layout, pld, ald);
 }

@@ -249,6 +249,17 @@ int lpmx_bve_streamfn(lpmx_handle_t h, const double* tgt_xyz, int tgt_layout, lo
   return run_sum(h, c);
 }
 
+int lpmx_bve_solve(lpmx_handle_t h, const double* tgt_xyz, int tgt_layout, long tgt_ld, int n_tgt, const double* src_xyz,
+                   int src_layout, long src_ld, const double* src_vort, const double* src_area,
+                   const unsigned char* src_mask, int n_src, int collocated, double* out_psi, double* out_vel) {
+  if (!h) return LPMX_ERR_INVALID;
+  if ((!out_vel || !out_psi) && n_tgt > 0) return set_error(h, LPMX_ERR_INVALID, "null output");
+  SumCall c{kVelPsi, tgt_xyz,  tgt_layout, tgt_ld, n_tgt, src_xyz,         src_layout,      src_ld, src_vort,
+            nullptr, src_area, src_mask,   n_src,  0.0,   collocated != 0, collocated != 0, 1,      out_vel,
+            out_psi, nullptr};
+  return run_sum(h, c);
+}
+
 int lpmx_ic2d_sums(lpmx_handle_t h, const double* tgt_xyz, int tgt_layout, long tgt_ld, int n_tgt,
                    const double* src_xyz, int src_layout, long src_ld, const double* src_vort,
                    const double* src_area, const unsigned char* src_mask, int n_src, double eps,

@@ -473,6 +473,12 @@ static int swe_launch_stage(SweState* s, const SweStageArgs& a) {
 
 static int swe_pair_sum(SweState* s, double* tgt_base) {
   const double kappa = 1.0 + s->eps * s->eps;
+  // the partials live in a handle-wide grow-only buffer: another SWE solver on this handle with a larger plan may have
+  // reallocated it since set_state, so the pointer is fetched again for every evaluation (as ensure_partials does for BVE/IC2D);
+  // the stage kernel that follows reads it through s->partials
+  void* part = nullptr;
+  LPMX_TRY(dev_buffer(s->h, "swe_partials", plan_partials_bytes(s->plan) + 256, &part));
+  s->partials = (double*)part;
   return launch_pair_sum(s->h, s->plan, s->local_view(tgt_base), s->self_idx + s->t0, s->packed[s->cur], kappa, s->partials);
 }
 
@@ -563,6 +569,7 @@ int lpmx_swe_solver_init_direct_sums(lpmx_swe_solver_t sv, int do_velocity) {
   }
   LPMX_TRY(swe_exchange_packed(s, s->packed[s->cur]));
   LPMX_TRY(swe_pair_sum(s, s->X));
+  a = swe_args(s, 0, 0, 0, 0, s->packed[s->cur], true);  // swe_pair_sum re-fetched the partials buffer
   if (a.n_local > 0) {
     const int threads = 128, blocks = (a.n_local + threads - 1) / threads;
     swe_init_sums_kernel<<<blocks, threads, 0, h->stream>>>(a, do_velocity);

@@ -22,12 +22,12 @@ def _shape(n_tgt, sms=SMS):
 @pytest.mark.parametrize("n_tgt", [229376, 9382, 600742, 2402982, 9611942, 300000, 1201491, 189440, 1, 12345])
 def test_shape_covers_the_targets_and_fits_a_cta(n_tgt):
     T, nw, grid = _shape(n_tgt)
-    assert T in (4, 5, 6, 7, 8) and nw in (8, 12) and nw * 32 <= 384  # warps in multiples of the 4 schedulers
+    assert T in (5, 6, 7) and nw == 8  # 8 warps = 2 per scheduler; the measured shapes (profiles/r2e_icos8_const_shapes.txt)
     tb = T * nw * 32
     assert grid * tb >= n_tgt > (grid - 1) * tb
 
 
-@pytest.mark.parametrize("n_tgt,least", [(1000000, 0.97), (2402982, 0.97), (9611942, 0.99), (1201491, 0.98)])
+@pytest.mark.parametrize("n_tgt,least", [(1000000, 0.94), (2402982, 0.97), (9611942, 0.98), (1201491, 0.90)])
 def test_shape_wastes_little_of_the_chip(n_tgt, least):
     """The sizes the automatic mode takes (>= 1e6 targets per rank): the threshold itself, icos-8 and icos-9 on one GPU, icos-8 on
     two = icos-9 on eight: fraction of (waves x SMs x targets per CTA) that is work."""

@@ -81,6 +81,23 @@ def test_streamfn(engine, oracle, meshes, seed, depth):
     assert field_rel_err(pf, of, leaf if seed == "icos" else None) <= VEL_TOL
 
 
+@pytest.mark.parametrize("seed,depth", [("icos", 3), ("cubed", 5)])
+def test_bve_solve_vertices_and_faces(engine, oracle, meshes, seed, depth):
+    """lpmx_bve_solve == BVEVertexSolve / BVEFaceSolve (src/lpm_bve_sphere_kernels.hpp:90-132, 284-320): the stream function and
+    the velocity of the same targets, against the oracle's two reductions."""
+    m = meshes(seed, depth)
+    _, fz = _ic(m, "rh54")
+    sel_f = (m.face_mask == 0) if seed == "icos" else None
+    pv, uv = engine.bve_solve(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask)
+    pf, uf = engine.bve_solve(None, m.face_xyz, fz, m.face_area, m.face_mask, collocated=True)
+    check_err("vert_vel", field_rel_err(uv, oracle.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask)), VEL_TOL)
+    check_err("vert_psi", field_rel_err(pv, oracle.bve_streamfn(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask)), VEL_TOL)
+    check_err("face_vel", field_rel_err(uf, oracle.bve_velocity(None, m.face_xyz, fz, m.face_area, m.face_mask, collocated=True),
+                                        sel_f), VEL_TOL)
+    check_err("face_psi", field_rel_err(pf, oracle.bve_streamfn(None, m.face_xyz, fz, m.face_area, m.face_mask, collocated=True),
+                                        sel_f), VEL_TOL)
+
+
 def test_edge_cases_empty_and_all_masked(engine):
     x = np.array([[0.0, 0.0, 1.0], [1.0, 0.0, 0.0]])
     # no sources
