@@ -472,12 +472,18 @@ def main():
                 of = oracle.bve_velocity_subset(fi, chk[3], chk[4], area, mask, L=Lref)
             scale = float(np.linalg.norm(ov, axis=1).max())
             ev = float(np.linalg.norm(chk[2][vi] - ov, axis=1).max() / scale)
+            adjud = None
+            if args.stepper != "swe_rk2":
+                # whose round-off is it: both against a long-double sum of the same formula on the same state (vertex sample)
+                old = oracle.bve_velocity(chk[0][vi], chk[3], chk[4], area, mask, long_double=True)
+                adjud = {"engine_vs_long_double": float(np.linalg.norm(chk[2][vi] - old, axis=1).max() / scale),
+                         "reference_fp64_vs_long_double": float(np.linalg.norm(ov - old, axis=1).max() / scale)}
             ef = float(np.linalg.norm(chk[5][fi] - of, axis=1).max() / scale) if of is not None else None
             parity = {"quantity": "velocity stored by the last evaluation of the timed steps vs the reference arithmetic on the "
                                   "same advanced state (field-relative max-norm)",
                       "max_rel_err": max(ev, ef) if ef is not None else ev, "vertex_targets": {"n": int(len(vi)), "rel_err": ev},
                       "leaf_face_targets": ({"n": int(len(fi)), "rel_err": ef} if ef is not None else None),
-                      "tolerance": 1e-12, "checker": "oracle/_ref (reference functors compiled in place)" if pkind == "reference"
+                      "adjudication_vertex_sample": adjud, "tolerance": 1e-12, "checker": "oracle/_ref (reference functors compiled in place)" if pkind == "reference"
                       else "oracle/ (C restatement)", "n_gpus_that_produced_the_state": world}
         except Exception as e:
             parity = {"error": repr(e)}

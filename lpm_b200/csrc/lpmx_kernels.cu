@@ -126,7 +126,7 @@ int make_plan(lpmx_handle_t h, int kind, int n_tgt, int n_src, SumPlan* p) {
     }
   }
   p->max_slots = ms;
-  p->smem_bytes = pair_smem_bytes(kind);
+  p->smem_bytes = pair_smem_bytes(kind, sh.T, sh.nw * 32);
   return LPMX_OK;
 }
 

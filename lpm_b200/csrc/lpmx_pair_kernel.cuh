@@ -145,10 +145,12 @@ struct SumArgs {
   double aux;    // 1 / pse_eps^2 (kPlaneSwe)
 };
 
-// dynamic shared memory of one CTA: source ring + full/empty barriers (+ the log table)
-__host__ __device__ constexpr size_t pair_smem_bytes(int kind) {
+// dynamic shared memory of one CTA: source ring + full/empty barriers (+ the log table) (+ the running totals of the two-level
+// summation: T * NACC doubles per compute thread, see pair_sum_kernel)
+__host__ __device__ constexpr size_t pair_smem_bytes(int kind, int T, int lanes) {
   return (size_t)kStages * kChunk * kind_rec(kind) * sizeof(double) + 2 * kStages * sizeof(uint64_t) +
-         (kind_has_log(kind) ? log_tables_bytes() : 0);
+         (kind_has_log(kind) ? log_tables_bytes() : 0) +
+         (kind_two_level(kind) ? (size_t)T * kind_nacc(kind) * lanes * sizeof(double) : 0);
 }
 
 __host__ __device__ __forceinline__ int cta_of_item(long item, int grid, long n_items) {
@@ -430,6 +432,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) pair_sum_kernel(const Sum
   double2* mtab = reinterpret_cast<double2*>(empty + kStages);
   double* ktab = reinterpret_cast<double*>(mtab + kLogMEntries);
   const LogTables tbl{mtab, ktab};
+  // running totals of the two-level summation, [t * NACC + q][compute thread] (conflict-free), behind the tables / barriers
+  double* tot = reinterpret_cast<double*>(smem_raw + (size_t)kStages * kStageBytes + 2 * kStages * sizeof(uint64_t) +
+                                          (kind_has_log(KIND) ? log_tables_bytes() : 0));
   if (kind_has_log(KIND)) {
     for (int i = threadIdx.x; i < kLogMEntries; i += C::THREADS) mtab[i] = kLogTable[i];
     for (int i = threadIdx.x; i < kLogKEntries; i += C::THREADS) ktab[i] = fast_log_ktab_entry(i);
@@ -498,6 +503,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) pair_sum_kernel(const Sum
       for (int q = 0; q < NACC; ++q) acc[t][q] = 0.0;
     }
 
+    bool first_chunk = true;
     for (; it < it_end; ++it, ++sc) {
       mbar_wait(full + s, ph);
       const double* sp = stage + (size_t)s * kChunk * REC;
@@ -505,31 +511,29 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) pair_sum_kernel(const Sum
       bool hit = false;
 #pragma unroll
       for (int t = 0; t < T; ++t) hit |= (unsigned)(self[t] - j0) < (unsigned)kChunk;
-      if (kind_two_level(KIND)) {
-        // two-level summation: the 256 terms of a chunk are added into accumulators that start from zero, and the chunk's
-        // sum is added to the running total once.  The factored velocity sum u = x cross sum(G y / d) carries a component
-        // of M along x that the cross product cancels (|M| / |u| ~ 2..50), so the rounding of a single running sum over N
-        // sources shows up amplified in u: measured 4.3e-13 of max|u| at cubed-7 and 1.2e-12 at icos-8 against a long-double
-        // sum where the reference's own sequential sum has 1.8e-13.  With chunk partials the accumulated rounding scales
-        // with sqrt(256) + sqrt(N / 256) instead of sqrt(N) (emulated at icos-7: 1.3e-12 -> 7e-14).  Cost: 3 DADD per target
-        // per 256 pairs.
-        double cacc[T][NACC];
-#pragma unroll
-        for (int t = 0; t < T; ++t)
-#pragma unroll
-          for (int q = 0; q < NACC; ++q) cacc[t][q] = 0.0;
-        if (__any_sync(0xffffffffu, hit))
-          chunk_loop<KIND, T, C::UNROLL, true>(x, kx, a.kappa, a.aux, sp, j0, self, cacc, tbl);
-        else
-          chunk_loop<KIND, T, C::UNROLL, false>(x, kx, a.kappa, a.aux, sp, j0, self, cacc, tbl);
-#pragma unroll
-        for (int t = 0; t < T; ++t)
-#pragma unroll
-          for (int q = 0; q < NACC; ++q) acc[t][q] += cacc[t][q];
-      } else if (__any_sync(0xffffffffu, hit))
+      if (__any_sync(0xffffffffu, hit))
         chunk_loop<KIND, T, C::UNROLL, true>(x, kx, a.kappa, a.aux, sp, j0, self, acc, tbl);
       else
         chunk_loop<KIND, T, C::UNROLL, false>(x, kx, a.kappa, a.aux, sp, j0, self, acc, tbl);
+      if (kind_two_level(KIND)) {
+        // two-level summation: the register accumulators hold ONE chunk's 256 terms (they restart from zero) and are added
+        // to this thread's running totals in shared memory once per chunk.  The factored velocity sum u = x cross sum(G y / d)
+        // carries a component of M along x that the cross product cancels (|M| / |u| ~ 2..50), so the rounding of a single
+        // running sum over N sources shows up amplified in u: 4.3e-13 of max|u| at cubed-7 and 1.2e-12 at icos-8 against a
+        // long-double sum, where the reference's own sequential sum has 1.8e-13 (profiles/r2e_parity_errors.jsonl).  With
+        // chunk partials the accumulated rounding scales with sqrt(256) + sqrt(N / 256) instead of sqrt(N): 3.0e-13 at icos-8
+        // (r2f).  Keeping the totals in shared memory leaves the inner loop's registers as they were: holding them in
+        // registers cost 12 % of the kernel's speed (r2f: 54.9 -> 62.5 ms per BVERK4 step at cubed-7).
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+#pragma unroll
+          for (int q = 0; q < NACC; ++q) {
+            double* p = tot + (size_t)(t * NACC + q) * kLanesPerCta + tid;
+            *p = first_chunk ? acc[t][q] : (*p + acc[t][q]);
+            acc[t][q] = 0.0;
+          }
+        first_chunk = false;
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);
       if (++s == kStages) {
@@ -544,7 +548,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) pair_sum_kernel(const Sum
     for (int t = 0; t < T; ++t) {
       const long tg = (long)tb * TB + t * kLanesPerCta + tid;
 #pragma unroll
-      for (int q = 0; q < NACC; ++q) a.part[((long)slot * NACC + q) * a.n_tgt_pad + tg] = acc[t][q];
+      for (int q = 0; q < NACC; ++q)
+        a.part[((long)slot * NACC + q) * a.n_tgt_pad + tg] =
+            kind_two_level(KIND) ? tot[(size_t)(t * NACC + q) * kLanesPerCta + tid] : acc[t][q];
     }
   }
 }

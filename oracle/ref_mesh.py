@@ -1,5 +1,5 @@
 """ctypes binding of oracle/_ref/liblpm_ref_mesh.so: the REFERENCE's own mesh classes (PolyMesh2d<Seed>::tree_init,
-divide_flagged_faces) and BVESphere + BVERK4::advance_timestep, compiled in place from /root/reference/src against
+divide_flagged_faces), BVESphere + BVERK4::advance_timestep and Incompressible2D + Incompressible2DRK2, compiled in place from /root/reference/src against
 oracle/kokkos_shim (oracle/ref_mesh_driver.cpp, `make -C oracle ref`).  TEST INFRASTRUCTURE ONLY: imported by the golden
 generators under tests/golden/ and by the live comparisons in tests/ (skipped where the library is not built).  The library
 travels to the GPU box with the snapshot; /root/reference itself is needed only to build it.  The reference's MeshSeed reads
@@ -138,4 +138,27 @@ def bve_rk4_run(seed, depth, dt, omega, n_steps, vert_zeta, face_zeta, with_psi=
            p(out["vert_psi"]), p(out["face_xyz"]), p(out["face_zeta"]), p(out["face_vel"]), p(out["face_psi"]), int(with_psi))
     if rc != 0:
         raise RuntimeError("ref_bve_rk4_run failed")
+    return out
+
+
+def ic2d_rk2_run(seed, depth, dt, omega, eps, n_steps, vert_zeta, face_zeta):
+    """Incompressible2D<Seed>(depth, CoriolisSphere(omega), eps) with the given relative vorticity -> init_direct_sums() ->
+    n_steps x advance_timestep(Incompressible2DRK2), all the reference's code (oracle/ref_ic2d_driver.cpp).  Returns
+    dict(vert_xyz, vert_zeta, vert_vel, vert_psi, face_...)."""
+    m = RefMesh(seed, depth)
+    c = m.counts()
+    m.close()
+    nv, nf = c["n_verts"], c["n_faces"]
+    vz = np.ascontiguousarray(vert_zeta, dtype=np.float64)
+    fz = np.ascontiguousarray(face_zeta, dtype=np.float64)
+    assert vz.shape == (nv,) and fz.shape == (nf,)
+    out = dict(vert_xyz=np.zeros((nv, 3)), vert_zeta=np.zeros(nv), vert_vel=np.zeros((nv, 3)), vert_psi=np.zeros(nv),
+               face_xyz=np.zeros((nf, 3)), face_zeta=np.zeros(nf), face_vel=np.zeros((nf, 3)), face_psi=np.zeros(nf))
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    f = lib().ref_ic2d_rk2_run
+    f.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int] + [ctypes.c_void_p] * 10
+    rc = f(SEED_ID[seed], depth, dt, omega, eps, n_steps, p(vz), p(fz), p(out["vert_xyz"]), p(out["vert_zeta"]), p(out["vert_vel"]),
+           p(out["vert_psi"]), p(out["face_xyz"]), p(out["face_zeta"]), p(out["face_vel"]), p(out["face_psi"]))
+    if rc != 0:
+        raise RuntimeError("ref_ic2d_rk2_run failed")
     return out

@@ -76,16 +76,17 @@ def test_gpu_const_stream_velocity_matches_oracle_and_default_kernel(oracle, mod
         got0_v = e0.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask)
         got1_v = e1.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask)
         got1_f = e1.bve_velocity(None, m.face_xyz, fz, m.face_area, m.face_mask, collocated=True)
+        leaf = m.face_mask == 0  # divided icosahedral faces sit on their centre child: 0/0 in the reference too
         assert field_rel_err(got1_v, ref_v) <= 1e-12
-        assert field_rel_err(got1_f, ref_f) <= 1e-12   # collocated: the self pair is removed by index
+        assert field_rel_err(got1_f, ref_f, leaf) <= 1e-12   # collocated: the self pair is removed by index
         # two summation orders of the same terms, each within 1e-12 of the oracle (4e-15 .. 1.1e-13 measured, r2b)
         assert field_rel_err(got1_v, got0_v) <= 5e-13
         # and through a stepper: two RK4 steps
+        got1_f[~leaf] = 0.0
         st0 = [m.vert_xyz.copy(), f(m.vert_xyz), got0_v.copy(), m.face_xyz.copy(), fz.copy(), got1_f.copy()]
         st1 = [a.copy() for a in st0]
         e0.bve_rk4_step(0.01, 2 * np.pi, *st0, m.face_area, m.face_mask, n_steps=2)
         e1.bve_rk4_step(0.01, 2 * np.pi, *st1, m.face_area, m.face_mask, n_steps=2)
-        leaf = m.face_mask == 0
         assert max(field_rel_err(st1[0], st0[0]), field_rel_err(st1[1], st0[1]), field_rel_err(st1[3], st0[3], leaf)) <= 1e-12
     finally:
         e0.close()

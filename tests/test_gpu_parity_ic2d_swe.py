@@ -90,6 +90,29 @@ def test_ic2d_rk2_step_at_cubed6_every_target_against_the_oracle(engine, oracle)
         check_err(n, field_rel_err(a, b), t)
 
 
+@pytest.mark.parametrize("name", ["cubed3_rh54", "icos3_rh54", "cubed4_gauss"])
+def test_ic2d_resident_solver_matches_compiled_reference_ic2d_rk2(engine, name):
+    """set_state -> init_direct_sums -> advance(n) -> get_state against the reference's own Incompressible2D::init_direct_sums +
+    n x Incompressible2DRK2::advance_timestep_impl compiled in place (tests/golden/ref_ic2d_rk2.npz), eps = 0 and eps > 0."""
+    from test_oracle_golden import ref_ic2d_case
+    from lpm_b200.api import PolyMesh2d
+    seed, depth, omega, dt, n_steps, eps, g = ref_ic2d_case(name)
+    m = PolyMesh2d(seed, depth)
+    area, mask = np.ascontiguousarray(m.face_area), np.ascontiguousarray(m.face_mask)
+    s = IC2DSolver(engine, m.n_verts, m.n_faces, eps=eps)
+    s.set_state(m.vert_xyz, g["vert_zeta0"], None, m.face_xyz, g["face_zeta0"], None, area, mask)
+    s.init_direct_sums()
+    s.advance(dt, omega, n_steps)
+    out = [np.empty((m.n_verts, 3)), np.empty(m.n_verts), np.empty((m.n_verts, 3)), np.empty(m.n_verts),
+           np.empty((m.n_faces, 3)), np.empty(m.n_faces), np.empty((m.n_faces, 3)), np.empty(m.n_faces)]
+    s.get_state(*out)
+    s.close()
+    leaf = mask == 0
+    keys = ["vert_xyz", "vert_zeta", "vert_vel", "vert_psi", "face_xyz", "face_zeta", "face_vel", "face_psi"]
+    for k, a, t in zip(keys, out, [VEL_TOL, VORT_TOL, VEL_TOL, VEL_TOL] * 2):
+        check_err(k, field_rel_err(a, g[k], leaf if k.startswith("face") else None), t)
+
+
 def test_ic2d_resident_solver_lazy_stream_function(engine, oracle, meshes):
     """The resident solver leaves psi stale when nobody read it since the previous advance (velocity-only evaluations) and
     recomputes it from the retained state on demand; a reader in between switches the next advance back to the fused

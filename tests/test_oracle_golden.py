@@ -316,3 +316,35 @@ def test_rows_of_divided_icos_faces_depend_on_the_reference_build_flags(oracle):
     nan_a, nan_b = np.isnan(a).any(axis=1), np.isnan(b).any(axis=1)
     assert not nan_a[leaf].any() and not nan_b[leaf].any()
     assert nan_a.sum() > 0 and nan_b.sum() > 0 and not np.array_equal(nan_a, nan_b)
+
+
+# ---- Incompressible2D + Incompressible2DRK2 of the reference, compiled in place ------------------------------------------------
+REF_IC2D_CASES = ["cubed3_rh54", "icos3_rh54", "cubed4_gauss"]
+
+
+def ref_ic2d_case(name):
+    """(seed, depth, Omega, dt, n_steps, eps, golden dict) of tests/golden/ref_ic2d_rk2.npz (make_ref_stepper_golden.py: outputs of
+    oracle/_ref/liblpm_ref_mesh.so, i.e. the reference's Incompressible2D<Seed>::init_direct_sums + n x advance_timestep)."""
+    g = np.load(os.path.join(GOLDEN, "ref_ic2d_rk2.npz"))
+    depth, omega, dt, n_steps, eps = g[f"{name}_params"]
+    d = {k[len(name) + 1:]: g[k] for k in g.files if k.startswith(name + "_")}
+    return name.split("_")[0][:-1], int(depth), float(omega), float(dt), int(n_steps), float(eps), d
+
+
+@pytest.mark.parametrize("name", REF_IC2D_CASES)
+def test_oracle_stepper_matches_compiled_reference_ic2d_rk2(oracle, name):
+    """oracle_ic2d_rk2_step vs the reference's own Incompressible2DRK2::advance_timestep_impl
+    (src/lpm_incompressible2d_rk2_impl.hpp:75-172: PassiveSums/ActiveSums x 2, Incompressible2DTendencies without dt, 12 KokkosBlas
+    calls) after Incompressible2D::init_direct_sums, eps = 0 (self term skipped) and eps > 0 (kept)."""
+    seed, depth, omega, dt, n_steps, eps, g = ref_ic2d_case(name)
+    m = PolyMesh2d(seed, depth)
+    vz, fz = g["vert_zeta0"], g["face_zeta0"]
+    pu, pp = oracle.ic2d_sums(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask, eps=eps)
+    au, ap = oracle.ic2d_sums(None, m.face_xyz, fz, m.face_area, m.face_mask, eps=eps, targets_are_sources=True)
+    st = [m.vert_xyz.copy(), vz.copy(), pu, pp, m.face_xyz.copy(), fz.copy(), au, ap]
+    oracle.ic2d_rk2_step(dt, omega, eps, *st, m.face_area, m.face_mask, n_steps=n_steps)
+    leaf = m.face_mask == 0
+    keys = ["vert_xyz", "vert_zeta", "vert_vel", "vert_psi", "face_xyz", "face_zeta", "face_vel", "face_psi"]
+    for k, a in zip(keys, st):
+        sel = leaf if k.startswith("face") else None
+        assert field_rel_err(a, g[k], sel) <= (2e-13 if k.endswith(("vel", "psi")) else 2e-14), k

@@ -75,7 +75,7 @@ static void run(const char* label) {
   a.n_tgt_pad = n_tgt_pad;
   a.kappa = 1.0;
   a.aux = 0.0;
-  const size_t smem = pair_smem_bytes(C::KIND);
+  const size_t smem = pair_smem_bytes(C::KIND, C::T, C::LANES);
   auto kern = pair_sum_kernel<C>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaFuncAttributes fa;
