@@ -519,7 +519,14 @@ def main():
 
     # ---- e2e: in-place C-ABI call on pinned host buffers (H2D + step + D2H inside the timed region) ----
     e2e = None
-    if True:  # every rank passes the full state; the engine shards the targets and gathers the result
+    if True:
+        # N = 1: the full state goes up and comes back every step.  N > 1: sharded host I/O (lpmx_set_io_sharded) -- each rank's
+        # host arrays carry its own target rows, as in any distributed-memory program: it uploads those rows (+ area and mask
+        # of all faces) and downloads those rows; nothing is replicated through the host.
+        sharded_io = world > 1 and args.stepper in ("bve_rk4", "ic2d_rk2")
+        (lv0, lv1), (lf0, lf1) = eng.local_rows(nv, nf)
+        n_own = (lv1 - lv0) + (lf1 - lf0)
+
         def pin(a):
             t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
             return t
@@ -534,6 +541,8 @@ def main():
                 eng.bve_rk4_step(args.dt, Omega, *args_np, h_area.numpy(), h_mask.numpy(), n_steps=1)
             h2d = sum(t.numel() * 8 for t in host) + area.nbytes + mask.nbytes
             d2h = sum(t.numel() * 8 for t in host)
+            if sharded_io:
+                h2d, d2h = n_own * 7 * 8 + area.nbytes + mask.nbytes, n_own * 7 * 8
         elif args.stepper == "swe_rk2":
             from lpm_b200.api import ACTIVE_FIELDS, PASSIVE_FIELDS, swe_rk2_step
             hp = {k: pin(np.zeros((nv, 3)) if k in ("xyz", "vel") else np.zeros(nv)) for k in PASSIVE_FIELDS}
@@ -558,6 +567,10 @@ def main():
                 eng.ic2d_rk2_step(args.dt, Omega, 0.0, *args_np, h_area.numpy(), h_mask.numpy(), n_steps=1)
             h2d = sum(t.numel() * 8 for t in host) - 8 * (nv + nf) + area.nbytes + mask.nbytes
             d2h = sum(t.numel() * 8 for t in host)
+            if sharded_io:
+                h2d, d2h = n_own * 7 * 8 + area.nbytes + mask.nbytes, n_own * 8 * 8
+        if sharded_io:
+            eng.set_io_sharded(True)
         one()  # warm-up: allocates the cached solver and the staging buffers
         torch.cuda.synchronize()
         t_calls = 0.0
@@ -575,7 +588,11 @@ def main():
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": t_calls / args.steps * 1e3,
                "api": {"bve_rk4": "lpmx_bve_rk4_step", "ic2d_rk2": "lpmx_ic2d_rk2_step", "swe_rk2": "lpmx_swe_rk2_step"}[args.stepper],
-               "host_buffers": "pinned"}
+               "host_buffers": "pinned",
+               "host_io": ("sharded: each rank moves its own target rows (lpmx_set_io_sharded); bytes are per rank" if sharded_io
+                           else "full state per rank")}
+        if sharded_io:
+            eng.set_io_sharded(False)
 
     # ---- extras of the N = 1 line: the synthetic N = 1e6 set (north_star's ">= 1M particles"), and the stepper the reference's
     # sphere_rh54 / sphere_gaussian_vortex drivers actually use (Incompressible2DRK2) on the same mesh ----

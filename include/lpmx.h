@@ -180,6 +180,16 @@ int lpmx_copy(lpmx_handle_t h, void* dst, const void* src, long bytes);
  * section 6).  The concatenated target list (vertices then faces) is split into `world`
  * contiguous index ranges; this handle evaluates range `rank`.  Default: rank 0 of 1. */
 int lpmx_set_partition(lpmx_handle_t h, int rank, int world);
+/* The rows of the two target lists (n_first vertices / passive particles, then n_second faces / active particles) that this
+ * handle's rank owns under lpmx_set_partition: [first0, first1) and [second0, second1). */
+int lpmx_local_rows(lpmx_handle_t h, int n_first, int n_second, int* first0, int* first1, int* second0, int* second1);
+/* Sharded host I/O for world > 1 (BVE and Incompressible2D solvers and their in-place steppers).  Off (default): every rank
+ * passes the full state and gets the full state back (replicated, as if it were alone).  On: of the HOST arrays passed to
+ * set_state / *_rk?_step only the rows of lpmx_local_rows are read (area and mask are always read in full), and get_state / the
+ * in-place steppers write back only those rows, without gathering the other ranks' -- each rank's host memory then holds its
+ * own shard, as in any distributed-memory program.  Cuts the per-step host traffic of an 8-GPU run from 14 + 13 MB to
+ * 2.9 + 1.6 MB per rank at cubed-7.  Device-pointer arguments are unaffected.  No counterpart in the reference. */
+int lpmx_set_io_sharded(lpmx_handle_t h, int on);
 /* NCCL bootstrap: rank 0 calls lpmx_comm_unique_id, the host program ships the 128 bytes to
  * all ranks (torch.distributed / MPI / a file), then every rank calls lpmx_comm_init. */
 int lpmx_comm_unique_id(void* id128);

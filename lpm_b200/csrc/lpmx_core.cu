@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <algorithm>
+
 #include "lpmx_internal.h"
 
 namespace lpmx {
@@ -261,6 +263,23 @@ int lpmx_set_partition(lpmx_handle_t h, int rank, int world) {
   if (!h || world < 1 || rank < 0 || rank >= world) return LPMX_ERR_INVALID;
   h->rank = rank;
   h->world = world;
+  return LPMX_OK;
+}
+
+int lpmx_set_io_sharded(lpmx_handle_t h, int on) {
+  if (!h) return LPMX_ERR_INVALID;
+  h->io_sharded = on != 0;
+  return LPMX_OK;
+}
+
+int lpmx_local_rows(lpmx_handle_t h, int n_first, int n_second, int* first0, int* first1, int* second0, int* second1) {
+  if (!h || n_first < 0 || n_second < 0) return LPMX_ERR_INVALID;
+  const long nt = (long)n_first + n_second;
+  const long t0 = ((long)h->rank * nt) / h->world, t1 = ((long)(h->rank + 1) * nt) / h->world;
+  if (first0) *first0 = (int)std::min<long>(t0, n_first);
+  if (first1) *first1 = (int)std::min<long>(t1, n_first);
+  if (second0) *second0 = (int)std::max<long>(t0 - n_first, 0);
+  if (second1) *second1 = (int)std::max<long>(t1 - n_first, 0);
   return LPMX_OK;
 }
 

@@ -117,6 +117,7 @@ struct lpmx_handle_s {
   std::string err;
   long launches = 0;
   int rank = 0, world = 1;
+  bool io_sharded = false;    // lpmx_set_io_sharded: host arrays carry only this rank's target rows
   void* nccl_comm = nullptr;  // ncclComm_t when lpmx_comm_init succeeded
   void* nccl_lib = nullptr;   // dlopen handle
   lpmx::PeerState* peer = nullptr;  // lpmx_comm_enable_peer_exchange

@@ -403,6 +403,21 @@ __device__ __forceinline__ void chunk_loop(const double (*x)[3], const double (*
   }
 }
 
+// blocks of the two-level summation: 4 chunks = 1024 terms (sqrt(b) + sqrt(N / b) is flat around b = sqrt(N): 313 .. 2290 for
+// the BASELINE meshes)
+constexpr int kFlushChunks = 4;
+template <int T, int NACC>
+__device__ __forceinline__ void flush_block(double (*acc)[NACC], double* tot, int lanes, int tid, bool first) {
+#pragma unroll
+  for (int t = 0; t < T; ++t)
+#pragma unroll
+    for (int q = 0; q < NACC; ++q) {
+      double* p = tot + (size_t)(t * NACC + q) * lanes + tid;
+      *p = first ? acc[t][q] : (*p + acc[t][q]);
+      acc[t][q] = 0.0;
+    }
+}
+
 // Compile-time shape of one kernel instance.
 //   KIND    pair body (PairKind)          T      targets per thread (register blocking)
 //   NW      compute warps per CTA (+1 producer warp)     MINB   CTAs per SM the register budget allows
@@ -503,7 +518,16 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) pair_sum_kernel(const Sum
       for (int q = 0; q < NACC; ++q) acc[t][q] = 0.0;
     }
 
-    bool first_chunk = true;
+    // two-level summation (kind_two_level): the register accumulators hold one BLOCK of kFlushChunks * 256 terms (they restart
+    // from zero) and are added to this thread's running totals in shared memory once per block.  The factored velocity sum
+    // u = x cross sum(G y / d) carries a component of M along x that the cross product cancels (|M| / |u| ~ 2..50), so the
+    // rounding of a single running sum over N sources shows up amplified in u: 4.3e-13 of max|u| at cubed-7 and 1.2e-12 at
+    // icos-8 against a long-double sum, where the reference's own sequential sum has 1.8e-13 (profiles/r2e_parity_errors.jsonl).
+    // With block partials the accumulated rounding scales with sqrt(b) + sqrt(N / b) instead of sqrt(N): 3.0e-13 at icos-8
+    // (r2f).  The totals live in shared memory so that the inner loop keeps its registers: holding them in registers cost 12 %
+    // of the kernel's speed (r2f: 54.9 -> 62.5 ms per BVERK4 step at cubed-7); a flush per 256-term chunk cost 2 % (r2g).
+    bool first_block = true;
+    int since_flush = 0;
     for (; it < it_end; ++it, ++sc) {
       mbar_wait(full + s, ph);
       const double* sp = stage + (size_t)s * kChunk * REC;
@@ -515,24 +539,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) pair_sum_kernel(const Sum
         chunk_loop<KIND, T, C::UNROLL, true>(x, kx, a.kappa, a.aux, sp, j0, self, acc, tbl);
       else
         chunk_loop<KIND, T, C::UNROLL, false>(x, kx, a.kappa, a.aux, sp, j0, self, acc, tbl);
-      if (kind_two_level(KIND)) {
-        // two-level summation: the register accumulators hold ONE chunk's 256 terms (they restart from zero) and are added
-        // to this thread's running totals in shared memory once per chunk.  The factored velocity sum u = x cross sum(G y / d)
-        // carries a component of M along x that the cross product cancels (|M| / |u| ~ 2..50), so the rounding of a single
-        // running sum over N sources shows up amplified in u: 4.3e-13 of max|u| at cubed-7 and 1.2e-12 at icos-8 against a
-        // long-double sum, where the reference's own sequential sum has 1.8e-13 (profiles/r2e_parity_errors.jsonl).  With
-        // chunk partials the accumulated rounding scales with sqrt(256) + sqrt(N / 256) instead of sqrt(N): 3.0e-13 at icos-8
-        // (r2f).  Keeping the totals in shared memory leaves the inner loop's registers as they were: holding them in
-        // registers cost 12 % of the kernel's speed (r2f: 54.9 -> 62.5 ms per BVERK4 step at cubed-7).
-#pragma unroll
-        for (int t = 0; t < T; ++t)
-#pragma unroll
-          for (int q = 0; q < NACC; ++q) {
-            double* p = tot + (size_t)(t * NACC + q) * kLanesPerCta + tid;
-            *p = first_chunk ? acc[t][q] : (*p + acc[t][q]);
-            acc[t][q] = 0.0;
-          }
-        first_chunk = false;
+      if (kind_two_level(KIND) && ++since_flush == kFlushChunks) {
+        flush_block<T, NACC>(acc, tot, kLanesPerCta, tid, first_block);
+        first_block = false;
+        since_flush = 0;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);
@@ -542,6 +552,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) pair_sum_kernel(const Sum
       }
     }
 
+    if (kind_two_level(KIND) && (since_flush > 0 || first_block)) flush_block<T, NACC>(acc, tot, kLanesPerCta, tid, first_block);
     // flush this CTA's contribution to target block tb into its slot
     const int slot = blockIdx.x - cta_of_item((long)tb * a.n_sc, grid, n_items);
 #pragma unroll

@@ -352,6 +352,32 @@ static int exchange_rows(SolverState* s, double* base, int n_rows) {
   return LPMX_OK;
 }
 
+// Rows [r0, r1) of a Real*[3] (ncomp = 3) or Real* (ncomp = 1) array between a host array and its full-size device staging
+// copy (same offsets on both sides): the sharded host I/O of lpmx_set_io_sharded.
+static int copy_rows(lpmx_handle_t h, void* dev, const void* user, int layout, long ld, long r0, long r1, int ncomp,
+                     bool to_device) {
+  if (r1 <= r0 || !dev || !user) return LPMX_OK;
+  const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+  auto run = [&](long off, long len) -> int {
+    char* d = (char*)dev + sizeof(double) * off;
+    char* u = (char*)const_cast<void*>(user) + sizeof(double) * off;
+    LPMX_CUDA(h, cudaMemcpyAsync(to_device ? (void*)d : (void*)u, to_device ? (const void*)u : (const void*)d,
+                                 sizeof(double) * len, kind, h->stream));
+    return LPMX_OK;
+  };
+  if (ncomp == 1) return run(r0, r1 - r0);
+  if (layout == LPMX_LAYOUT_RIGHT) return run(3 * r0, 3 * (r1 - r0));
+  for (int k = 0; k < 3; ++k) LPMX_TRY(run(k * ld + r0, r1 - r0));
+  return LPMX_OK;
+}
+
+// this rank's rows of the vertex list and of the face list
+static void local_rows(const SolverState* s, int rank, int world, long* v0, long* v1, long* f0, long* f1) {
+  const long t0 = ((long)rank * s->nt) / world, t1 = ((long)(rank + 1) * s->nt) / world;
+  *v0 = std::min<long>(t0, s->nv), *v1 = std::min<long>(t1, s->nv);
+  *f0 = std::max<long>(t0 - s->nv, 0), *f1 = std::max<long>(t1 - s->nv, 0);
+}
+
 static int solver_set_state(SolverState* s, const double* vx, const double* vz, const double* vu, const double* fx,
                             const double* fz, const double* fu, const double* fa, const unsigned char* fm, int layout,
                             long vld, long fld, int skip_self) {
@@ -366,12 +392,27 @@ static int solver_set_state(SolverState* s, const double* vx, const double* vz, 
     return (layout == LPMX_LAYOUT_LEFT ? (size_t)(2 * ld + n) : (size_t)3 * n) * sizeof(double);
   };
   const void *dvx, *dvz, *dvu, *dfx, *dfz, *dfu, *dfa, *dfm;
-  LPMX_TRY(stage_in(h, "st_vx", vx, vb(vld, s->nv), &dvx));
-  LPMX_TRY(stage_in(h, "st_vz", vz, sizeof(double) * s->nv, &dvz));
-  LPMX_TRY(stage_in(h, "st_vu", vu, vb(vld, s->nv), &dvu));
-  LPMX_TRY(stage_in(h, "st_fx", fx, vb(fld, s->nf), &dfx));
-  LPMX_TRY(stage_in(h, "st_fz", fz, sizeof(double) * s->nf, &dfz));
-  LPMX_TRY(stage_in(h, "st_fu", fu, vb(fld, s->nf), &dfu));
+  // sharded host I/O (lpmx_set_io_sharded, world > 1): only this rank's target rows are read from the host arrays -- they are
+  // all it needs, since every rank packs the source records of its OWN leaf faces and the exchange distributes them.  The
+  // other rows of the device-side state are left as they are and never read.  Area and mask are read in full (the leaf scan
+  // and the conserved totals run over all faces).
+  const bool shard_in = h->io_sharded && h->world > 1;
+  auto in_rows = [&](const char* name, const double* user, size_t bytes, long ld, long r0, long r1, int ncomp,
+                     const void** dev) -> int {
+    if (!shard_in || !user || is_device_pointer(user)) return stage_in(h, name, user, bytes, dev);
+    void* d = nullptr;
+    LPMX_TRY(dev_buffer(h, name, bytes, &d));
+    *dev = d;
+    return copy_rows(h, d, user, layout, ld, r0, r1, ncomp, true);
+  };
+  long v0, v1, f0, f1;
+  local_rows(s, h->rank, h->world, &v0, &v1, &f0, &f1);
+  LPMX_TRY(in_rows("st_vx", vx, vb(vld, s->nv), vld, v0, v1, 3, &dvx));
+  LPMX_TRY(in_rows("st_vz", vz, sizeof(double) * s->nv, 0, v0, v1, 1, &dvz));
+  LPMX_TRY(in_rows("st_vu", vu, vb(vld, s->nv), vld, v0, v1, 3, &dvu));
+  LPMX_TRY(in_rows("st_fx", fx, vb(fld, s->nf), fld, f0, f1, 3, &dfx));
+  LPMX_TRY(in_rows("st_fz", fz, sizeof(double) * s->nf, 0, f0, f1, 1, &dfz));
+  LPMX_TRY(in_rows("st_fu", fu, vb(fld, s->nf), fld, f0, f1, 3, &dfu));
   LPMX_TRY(stage_in(h, "st_fa", fa, sizeof(double) * s->nf, &dfa));
   LPMX_TRY(stage_in(h, "st_fm", fm, (size_t)s->nf, &dfm));
   if (s->nf > 0) {
@@ -431,11 +472,16 @@ static int solver_get_state(SolverState* s, double* vx, double* vz, double* vu, 
   if (!s->has_state) return set_error(h, LPMX_ERR_STATE, "get_state before set_state");
   if (layout != LPMX_LAYOUT_LEFT && layout != LPMX_LAYOUT_RIGHT) return set_error(h, LPMX_ERR_INVALID, "unknown layout");
   LPMX_CUDA(h, cudaSetDevice(h->device));
-  // every rank returns the full state
-  LPMX_TRY(exchange_rows(s, s->X, 3));
-  LPMX_TRY(exchange_rows(s, s->U, 3));
-  LPMX_TRY(exchange_rows(s, s->Z, 1));
-  if (vpsi || fpsi) LPMX_TRY(exchange_rows(s, s->Psi, 1));
+  // every rank returns the full state -- unless the host I/O is sharded: then each rank writes back its own target rows only
+  const bool shard_out = h->io_sharded && h->world > 1;
+  if (!shard_out) {
+    LPMX_TRY(exchange_rows(s, s->X, 3));
+    LPMX_TRY(exchange_rows(s, s->U, 3));
+    LPMX_TRY(exchange_rows(s, s->Z, 1));
+    if (vpsi || fpsi) LPMX_TRY(exchange_rows(s, s->Psi, 1));
+  }
+  long v0, v1, f0, f1;
+  local_rows(s, h->rank, h->world, &v0, &v1, &f0, &f1);
   auto vb = [&](long ld, int n) {
     return (layout == LPMX_LAYOUT_LEFT ? (size_t)(2 * ld + n) : (size_t)3 * n) * sizeof(double);
   };
@@ -460,18 +506,19 @@ static int solver_get_state(SolverState* s, double* vx, double* vz, double* vu, 
     LPMX_CUDA(h, cudaGetLastError());
   }
   bool any_host = false;
-  auto out = [&](void* user, void* dev, size_t bytes) -> int {
+  auto out = [&](void* user, void* dev, size_t bytes, long ld, long r0, long r1, int ncomp) -> int {
     if (user && user != dev) any_host = true;
+    if (shard_out && user && user != dev) return copy_rows(h, dev, user, layout, ld, r0, r1, ncomp, false);
     return stage_out_end(h, user, dev, bytes);
   };
-  LPMX_TRY(out(vx, dvx, vb(vld, s->nv)));
-  LPMX_TRY(out(vz, dvz, sizeof(double) * s->nv));
-  LPMX_TRY(out(vu, dvu, vb(vld, s->nv)));
-  LPMX_TRY(out(vpsi, dvp, sizeof(double) * s->nv));
-  LPMX_TRY(out(fx, dfx, vb(fld, s->nf)));
-  LPMX_TRY(out(fz, dfz, sizeof(double) * s->nf));
-  LPMX_TRY(out(fu, dfu, vb(fld, s->nf)));
-  LPMX_TRY(out(fpsi, dfp, sizeof(double) * s->nf));
+  LPMX_TRY(out(vx, dvx, vb(vld, s->nv), vld, v0, v1, 3));
+  LPMX_TRY(out(vz, dvz, sizeof(double) * s->nv, 0, v0, v1, 1));
+  LPMX_TRY(out(vu, dvu, vb(vld, s->nv), vld, v0, v1, 3));
+  LPMX_TRY(out(vpsi, dvp, sizeof(double) * s->nv, 0, v0, v1, 1));
+  LPMX_TRY(out(fx, dfx, vb(fld, s->nf), fld, f0, f1, 3));
+  LPMX_TRY(out(fz, dfz, sizeof(double) * s->nf, 0, f0, f1, 1));
+  LPMX_TRY(out(fu, dfu, vb(fld, s->nf), fld, f0, f1, 3));
+  LPMX_TRY(out(fpsi, dfp, sizeof(double) * s->nf, 0, f0, f1, 1));
   if (any_host) LPMX_CUDA(h, cudaStreamSynchronize(h->stream));
   return LPMX_OK;
 }

@@ -55,6 +55,36 @@ def main():
         errs = [field_rel_err(got[i], ref[i]) for i in (0, 1, 2, 3)] + [field_rel_err(got[i], ref[i], leaf) for i in (4, 5, 6, 7)]
         worst = max(worst, max(errs))
         print(f"[rank {rank}/{world}] ic2d_rk2 {seed}-{depth}: max field-rel err {max(errs):.3e}", flush=True)
+    # sharded host I/O (lpmx_set_io_sharded): every rank passes arrays whose rows of OTHER ranks are poisoned; after two steps its
+    # own rows equal the oracle's and the others are still untouched
+    m = PolyMesh2d("cubed", 4)
+    leaf = m.face_mask == 0
+    f = gallery.RossbyHaurwitz54()
+    f.set_stationary_wave_speed()
+    vz, fz = f(m.vert_xyz), f(m.face_xyz)
+    a = (m.face_xyz, fz, m.face_area, m.face_mask)
+    ref = [m.vert_xyz.copy(), vz.copy(), oracle.bve_velocity(m.vert_xyz, *a), m.face_xyz.copy(), fz.copy(),
+           oracle.bve_velocity(None, *a, collocated=True)]
+    got = [x.copy() for x in ref]
+    (v0, v1), (f0, f1) = e.local_rows(m.n_verts, m.n_faces)
+    own = [np.zeros(m.n_verts, bool), np.zeros(m.n_faces, bool)]
+    own[0][v0:v1], own[1][f0:f1] = True, True
+    for k, arr in enumerate(got):
+        arr[~own[k // 3]] = np.nan
+    e.set_io_sharded(True)
+    e.bve_rk4_step(0.01, 2 * np.pi, *got, m.face_area, m.face_mask, n_steps=2)
+    e.set_io_sharded(False)
+    oracle.bve_rk4_step(0.01, 2 * np.pi, *ref, m.face_area, m.face_mask, n_steps=2)
+    ok = True
+    for k, (g, r) in enumerate(zip(got, ref)):
+        o = own[k // 3]
+        ok &= bool(np.isnan(g[~o]).all())
+        if o.any():
+            ok &= field_rel_err(g[o], r[o]) <= 1e-10 * max(1.0, np.abs(r).max() / max(np.abs(r[o]).max(), 1e-300))
+    print(f"[rank {rank}/{world}] sharded host I/O (rows {v0}:{v1} of the vertices, {f0}:{f1} of the faces): {'ok' if ok else 'FAILED'}",
+          flush=True)
+    if not ok:
+        worst = np.inf
     # SWE RK2 with the Laplacian provider (the provider sees the gathered arrays on every rank)
     m = PolyMesh2d("cubed", 3)
     st0 = T.tc2_state(oracle, m, eps=0.0, div_amp=0.02)

@@ -303,8 +303,8 @@ int main(int argc, char** argv) {
 
 #define RUNK(K, T, NW, MINB, UNR) run<PairCfg<K, T, NW, MINB, UNR>>(#K " T" #T " NW" #NW " B" #MINB " U" #UNR)
 #define RUN(T, NW, MINB, UNR) run<PairCfg<kVel, T, NW, MINB, UNR>>("vel T" #T " NW" #NW " B" #MINB " U" #UNR)
-  if (argc > 3 && !strcmp(argv[3], "r2")) {  // round 2: the product shapes and their neighbours (built twice: -DLPMX_RCP_HOLD=0 / 1)
-    printf("LPMX_RCP_HOLD=%d\n", LPMX_RCP_HOLD);
+  if (argc > 3 && !strcmp(argv[3], "r2")) {  // round 2: the product shapes and their neighbours 
+
     RUN(6, 8, 1, 2);
     RUN(6, 8, 1, 4);
     RUN(7, 8, 1, 2);
