@@ -72,7 +72,7 @@ static int launch_cfg(lpmx_handle_t h, const SumPlan& p, const SumArgs& a) {
 // operands (3 distinct: 3 cycles), so the winner is the shape with the most operand reuse across the T
 // targets of a thread that still leaves 8 warps per SM to cover MUFU/LDS latency.
 static const Shape kShapes[] = {
-    LPMX_SHAPE(kVel, 6, 8, 1, 2),     LPMX_SHAPE(kVel, 4, 8, 2, 2),    LPMX_SHAPE(kVel, 2, 8, 2, 2),
+    LPMX_SHAPE(kVel, 6, 8, 1, 4),     LPMX_SHAPE(kVel, 4, 8, 2, 2),    LPMX_SHAPE(kVel, 2, 8, 2, 2),
     LPMX_SHAPE(kVel, 1, 8, 2, 2),
     LPMX_SHAPE(kVelPsi, 4, 8, 1, 2),  LPMX_SHAPE(kVelPsi, 2, 8, 2, 2), LPMX_SHAPE(kVelPsi, 1, 8, 2, 2),
     LPMX_SHAPE(kPsi, 8, 8, 1, 2),     LPMX_SHAPE(kPsi, 4, 8, 2, 2),    LPMX_SHAPE(kPsi, 2, 8, 2, 2),

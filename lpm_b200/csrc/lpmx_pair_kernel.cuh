@@ -527,32 +527,32 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) pair_sum_kernel(const Sum
     // (r2f).  The totals live in shared memory so that the inner loop keeps its registers: holding them in registers cost 12 %
     // of the kernel's speed (r2f: 54.9 -> 62.5 ms per BVERK4 step at cubed-7); a flush per 256-term chunk cost 2 % (r2g).
     bool first_block = true;
-    int since_flush = 0;
-    for (; it < it_end; ++it, ++sc) {
-      mbar_wait(full + s, ph);
-      const double* sp = stage + (size_t)s * kChunk * REC;
-      const int j0 = sc * kChunk;
-      bool hit = false;
+    while (it < it_end) {
+      const long blk_end = kind_two_level(KIND) ? min(it_end, it + (long)kFlushChunks) : it_end;
+      for (; it < blk_end; ++it, ++sc) {
+        mbar_wait(full + s, ph);
+        const double* sp = stage + (size_t)s * kChunk * REC;
+        const int j0 = sc * kChunk;
+        bool hit = false;
 #pragma unroll
-      for (int t = 0; t < T; ++t) hit |= (unsigned)(self[t] - j0) < (unsigned)kChunk;
-      if (__any_sync(0xffffffffu, hit))
-        chunk_loop<KIND, T, C::UNROLL, true>(x, kx, a.kappa, a.aux, sp, j0, self, acc, tbl);
-      else
-        chunk_loop<KIND, T, C::UNROLL, false>(x, kx, a.kappa, a.aux, sp, j0, self, acc, tbl);
-      if (kind_two_level(KIND) && ++since_flush == kFlushChunks) {
+        for (int t = 0; t < T; ++t) hit |= (unsigned)(self[t] - j0) < (unsigned)kChunk;
+        if (__any_sync(0xffffffffu, hit))
+          chunk_loop<KIND, T, C::UNROLL, true>(x, kx, a.kappa, a.aux, sp, j0, self, acc, tbl);
+        else
+          chunk_loop<KIND, T, C::UNROLL, false>(x, kx, a.kappa, a.aux, sp, j0, self, acc, tbl);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+        if (++s == kStages) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+      if (kind_two_level(KIND)) {  // after the ring slot has been handed back
         flush_block<T, NACC>(acc, tot, kLanesPerCta, tid, first_block);
         first_block = false;
-        since_flush = 0;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty + s);
-      if (++s == kStages) {
-        s = 0;
-        ph ^= 1u;
       }
     }
 
-    if (kind_two_level(KIND) && (since_flush > 0 || first_block)) flush_block<T, NACC>(acc, tot, kLanesPerCta, tid, first_block);
     // flush this CTA's contribution to target block tb into its slot
     const int slot = blockIdx.x - cta_of_item((long)tb * a.n_sc, grid, n_items);
 #pragma unroll
