@@ -489,7 +489,11 @@ def main():
             parity = {"error": repr(e)}
 
     # ---- roofline of the dominant kernel (rank-local): algorithmic flops / CUDA-event launch time ----
-    local_inter = evals * args.steps * (float(solver_local_targets(nv + nf, rank, world)) * nleaf)
+    if args.stepper == "swe_rk2":  # the SWE solver shards the concatenated list; BVE / IC2D shard vertices and faces separately
+        n_local_targets = solver_local_targets(nv + nf, rank, world)
+    else:
+        n_local_targets = solver_local_targets(nv, rank, world) + solver_local_targets(nf, rank, world)
+    local_inter = evals * args.steps * (float(n_local_targets) * nleaf)
     flops_per = FLOPS_PER_INTERACTION[args.stepper]
     achieved_tf = local_inter * flops_per / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else None
     roofline = {

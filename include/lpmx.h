@@ -176,12 +176,14 @@ int lpmx_profile_read(lpmx_handle_t h, long* n_launches, double* total_ms, doubl
  * the CUDA headers. */
 int lpmx_copy(lpmx_handle_t h, void* dst, const void* src, long bytes);
 
-/* Target sharding over the GPUs of one box (the reference has no multi-device path; DESIGN.md
- * section 6).  The concatenated target list (vertices then faces) is split into `world`
- * contiguous index ranges; this handle evaluates range `rank`.  Default: rank 0 of 1. */
+/* Target sharding over the GPUs of one box (the reference has no multi-device path).  This handle
+ * evaluates the targets of rank `rank` of `world`: for the BVE / Incompressible2D solvers 1/world of the vertex rows and
+ * 1/world of the face rows (lpmx_local_rows), for the SWE and planar solvers a contiguous range of the concatenated list
+ * (vertices then faces).  Default: rank 0 of 1. */
 int lpmx_set_partition(lpmx_handle_t h, int rank, int world);
-/* The rows of the two target lists (n_first vertices / passive particles, then n_second faces / active particles) that this
- * handle's rank owns under lpmx_set_partition: [first0, first1) and [second0, second1). */
+/* The rows of the two target lists (n_first vertices / passive particles, n_second faces / active particles) that this
+ * handle's rank owns in the BVE / Incompressible2D solvers: [first0, first1) = [r n_first / W, (r+1) n_first / W) and
+ * [second0, second1) likewise. */
 int lpmx_local_rows(lpmx_handle_t h, int n_first, int n_second, int* first0, int* first1, int* second0, int* second1);
 /* Sharded host I/O for world > 1 (BVE and Incompressible2D solvers and their in-place steppers).  Off (default): every rank
  * passes the full state and gets the full state back (replicated, as if it were alone).  On: of the HOST arrays passed to

@@ -99,10 +99,11 @@ int stage_out_end(lpmx_handle_t h, void* user, const void* dev, size_t bytes) {
   return LPMX_OK;
 }
 
-int comm_allgatherv(lpmx_handle_t h, double* base, const long* offsets) {
+int comm_allgatherv(lpmx_handle_t h, double* base, const long* offsets, cudaStream_t stream) {
   if (h->world == 1) return LPMX_OK;
+  if (!stream) stream = h->stream;
   if (!h->nccl_comm || !h->nccl_lib) return set_error(h, LPMX_ERR_COMM, "world > 1 but lpmx_comm_init was not called");
-  if (peer_can_exchange(h, base)) return peer_allgatherv(h, base, offsets);  // one kernel over NVLink peer memory
+  if (peer_can_exchange(h, base)) return peer_allgatherv(h, base, offsets, stream);  // one kernel over NVLink peer memory
   typedef int (*group_t)(void);
   typedef int (*bcast_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
   static group_t gstart = nullptr, gend = nullptr;
@@ -119,7 +120,7 @@ int comm_allgatherv(lpmx_handle_t h, double* base, const long* offsets) {
     const long n = offsets[r + 1] - offsets[r];
     if (n <= 0) continue;
     double* seg = base + offsets[r];
-    rc = bcast(seg, seg, (size_t)n, kNcclFloat64, r, h->nccl_comm, h->stream);
+    rc = bcast(seg, seg, (size_t)n, kNcclFloat64, r, h->nccl_comm, stream);
   }
   const int rc2 = gend();
   if (rc != 0 || rc2 != 0) return set_error(h, LPMX_ERR_COMM, "ncclBroadcast group failed (%d/%d)", rc, rc2);
@@ -192,6 +193,8 @@ int lpmx_destroy(lpmx_handle_t h) {
     if (kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : h->pinned)
     if (kv.second.p) cudaFreeHost(kv.second.p);
+  for (int i = 0; i < 2; ++i)
+    if (h->xchg_ev[i]) cudaEventDestroy(h->xchg_ev[i]);
   for (auto& ev : h->prof_events) {
     cudaEventDestroy(ev.first);
     cudaEventDestroy(ev.second);
@@ -274,12 +277,11 @@ int lpmx_set_io_sharded(lpmx_handle_t h, int on) {
 
 int lpmx_local_rows(lpmx_handle_t h, int n_first, int n_second, int* first0, int* first1, int* second0, int* second1) {
   if (!h || n_first < 0 || n_second < 0) return LPMX_ERR_INVALID;
-  const long nt = (long)n_first + n_second;
-  const long t0 = ((long)h->rank * nt) / h->world, t1 = ((long)(h->rank + 1) * nt) / h->world;
-  if (first0) *first0 = (int)std::min<long>(t0, n_first);
-  if (first1) *first1 = (int)std::min<long>(t1, n_first);
-  if (second0) *second0 = (int)std::max<long>(t0 - n_first, 0);
-  if (second1) *second1 = (int)std::max<long>(t1 - n_first, 0);
+  const long r = h->rank, w = h->world;
+  if (first0) *first0 = (int)((r * n_first) / w);
+  if (first1) *first1 = (int)(((r + 1) * n_first) / w);
+  if (second0) *second0 = (int)((r * n_second) / w);
+  if (second1) *second1 = (int)(((r + 1) * n_second) / w);
   return LPMX_OK;
 }
 

@@ -118,6 +118,7 @@ struct lpmx_handle_s {
   long launches = 0;
   int rank = 0, world = 1;
   bool io_sharded = false;    // lpmx_set_io_sharded: host arrays carry only this rank's target rows
+  cudaEvent_t xchg_ev[2] = {nullptr, nullptr};  // overlapped exchange of the sharded steppers (compute -> copy stream -> compute)
   void* nccl_comm = nullptr;  // ncclComm_t when lpmx_comm_init succeeded
   void* nccl_lib = nullptr;   // dlopen handle
   lpmx::PeerState* peer = nullptr;  // lpmx_comm_enable_peer_exchange
@@ -164,15 +165,16 @@ int stage_out_begin(lpmx_handle_t h, const char* name, void* user, size_t bytes,
 int stage_out_end(lpmx_handle_t h, void* user, const void* dev, size_t bytes);
 
 // ---- pair-sum engine (lpmx_kernels.cu) ----
-int make_plan(lpmx_handle_t h, int kind, int n_tgt, int n_src, SumPlan* plan);
+int make_plan(lpmx_handle_t h, int kind, int n_tgt, int n_src, SumPlan* plan, bool allow_const_stream = true);
 size_t plan_partials_bytes(const SumPlan& p);
 // tgt: target coordinates of the n_tgt targets of this launch (view indexed from 0);
 // self_idx: compact source index of each target's own particle or -1 (may be nullptr);
 // packed: n_src_pad records of kind_rec(kind) doubles; partials: plan_partials_bytes.
 // kappa: 1 + eps^2 on the sphere, eps^2 in the plane; aux: 1 / pse_eps^2 for kPlaneSwe (unused otherwise).
 // Planar kinds read target rows (x0, x1, surface height) through the same 3-row view.
+// tgt_map (optional): the launch's targets are the elements tgt_map[0 .. plan.n_tgt) of `tgt` / `self_idx`
 int launch_pair_sum(lpmx_handle_t h, const SumPlan& plan, Vec3View tgt, const int* self_idx, const double* packed,
-                    double kappa, double* partials, double aux = 0.0);
+                    double kappa, double* partials, double aux = 0.0, const int* tgt_map = nullptr);
 
 // ---- velocity pair sum through the constant bank (lpmx_const_stream.cu; opt-in) ----
 constexpr int kShapeConstStream = 1000;  // SumPlan::shape of a launch that takes this path
@@ -196,7 +198,7 @@ int ic2d_totals_device(lpmx_handle_t h, int n, const double* zeta, Vec3View u, c
 // In-place allgatherv of doubles on the handle's stream: rank r owns elements
 // [offsets[r], offsets[r+1]) of `base`; after the call every rank holds all of them.
 // No-op for world == 1.  (lpmx_core.cu; NCCL broadcasts grouped into one launch.)
-int comm_allgatherv(lpmx_handle_t h, double* base, const long* offsets);
+int comm_allgatherv(lpmx_handle_t h, double* base, const long* offsets, cudaStream_t stream = nullptr);  // null: h->stream
 
 // Solver slabs.  Without the peer exchange these are cudaMalloc / cudaFree; with it the slab is also mapped
 // into every rank (collective call) so that comm_allgatherv can store into the peers directly.  (lpmx_peer.cu)
@@ -204,7 +206,7 @@ int slab_alloc(lpmx_handle_t h, void** out, size_t bytes);
 void slab_free(lpmx_handle_t h, void* p);
 int peer_enable(lpmx_handle_t h, int enable);
 bool peer_can_exchange(lpmx_handle_t h, const double* base);
-int peer_allgatherv(lpmx_handle_t h, double* base, const long* offsets);
+int peer_allgatherv(lpmx_handle_t h, double* base, const long* offsets, cudaStream_t stream = nullptr);
 int peer_check_error(lpmx_handle_t h);
 void peer_teardown(lpmx_handle_t h);
 

@@ -97,9 +97,9 @@ static int pick_shape(int kind, int num_sms, int n_tgt, int n_sc) {
   return last;
 }
 
-int make_plan(lpmx_handle_t h, int kind, int n_tgt, int n_src, SumPlan* p) {
+int make_plan(lpmx_handle_t h, int kind, int n_tgt, int n_src, SumPlan* p, bool allow_const_stream) {
   if (n_tgt < 0 || n_src < 0) return set_error(h, LPMX_ERR_INVALID, "negative size");
-  if (kind == kVel && make_const_plan(h, n_tgt, n_src, p)) return LPMX_OK;  // opt-in: sources through the constant bank
+  if (kind == kVel && allow_const_stream && make_const_plan(h, n_tgt, n_src, p)) return LPMX_OK;  // opt-in: sources through the constant bank
   p->kind = kind;
   p->n_tgt = n_tgt;
   p->n_src_pad = round_up_chunk(n_src);
@@ -135,15 +135,18 @@ size_t plan_partials_bytes(const SumPlan& p) {
 }
 
 int launch_pair_sum(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* self_idx, const double* packed,
-                    double kappa, double* partials, double aux) {
+                    double kappa, double* partials, double aux, const int* tgt_map) {
   if (p.n_tgt == 0) return LPMX_OK;
   if (p.n_sc == 0) {
     // no sources: every partial sum is zero
     LPMX_CUDA(h, cudaMemsetAsync(partials, 0, plan_partials_bytes(p), h->stream));
     return LPMX_OK;
   }
+  if (tgt_map && p.shape == kShapeConstStream)
+    return set_error(h, LPMX_ERR_STATE, "the constant-bank path takes no target index list (plan made with allow_const_stream)");
   SumArgs a;
   a.tgt = tgt;
+  a.tgt_map = tgt_map;
   a.self_idx = self_idx;
   a.packed = packed;
   a.part = partials;

@@ -134,6 +134,8 @@ __device__ __forceinline__ double fast_exp_neg(double x) {
 // ------------------------------------------------------------------------------------------------
 struct SumArgs {
   Vec3View tgt;
+  const int* tgt_map;  // optional: target tg of this launch is element tgt_map[tg] of `tgt` / `self_idx` (an index list of a
+                       // sharded solver: its leaf faces, or its vertices and divided faces); null: element tg itself
   const int* self_idx;
   const double* packed;
   double* part;
@@ -508,12 +510,13 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) pair_sum_kernel(const Sum
     for (int t = 0; t < T; ++t) {
       const long tg = (long)tb * TB + t * kLanesPerCta + tid;
       const bool valid = tg < a.n_tgt;
+      const long ge = (valid && a.tgt_map) ? (long)a.tgt_map[tg] : tg;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        x[t][k] = valid ? a.tgt(tg, k) : 0.0;
+        x[t][k] = valid ? a.tgt(ge, k) : 0.0;
         kx[t][k] = a.kappa * x[t][k];
       }
-      self[t] = (valid && a.self_idx) ? a.self_idx[tg] : -1;
+      self[t] = (valid && a.self_idx) ? a.self_idx[ge] : -1;
 #pragma unroll
       for (int q = 0; q < NACC; ++q) acc[t][q] = 0.0;
     }

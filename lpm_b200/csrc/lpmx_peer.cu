@@ -235,7 +235,8 @@ bool peer_can_exchange(lpmx_handle_t h, const double* base) {
   return ps && ps->enabled && h->world > 1 && find_region(ps, base) != nullptr;
 }
 
-int peer_allgatherv(lpmx_handle_t h, double* base, const long* offsets) {
+int peer_allgatherv(lpmx_handle_t h, double* base, const long* offsets, cudaStream_t stream) {
+  if (!stream) stream = h->stream;
   PeerState* ps = h->peer;
   const PeerRegion* r = find_region(ps, base);
   if (!r) return set_error(h, LPMX_ERR_STATE, "peer exchange on an unregistered buffer");
@@ -262,9 +263,9 @@ int peer_allgatherv(lpmx_handle_t h, double* base, const long* offsets) {
   int grid = (int)(out_bytes / 32768);
   grid = grid < 1 ? 1 : grid > 64 ? 64 : grid;
   if (vec2)
-    peer_push_kernel<2><<<grid, 256, 0, h->stream>>>(a);
+    peer_push_kernel<2><<<grid, 256, 0, stream>>>(a);
   else
-    peer_push_kernel<1><<<grid, 256, 0, h->stream>>>(a);
+    peer_push_kernel<1><<<grid, 256, 0, stream>>>(a);
   ++h->launches;
   LPMX_CUDA(h, cudaGetLastError());
   return LPMX_OK;

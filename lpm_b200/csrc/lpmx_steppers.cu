@@ -11,11 +11,14 @@
 // kernel adds the partial moments, applies u = x cross M, forms the stage increments, the next
 // stage's input state AND its packed source records (ping-pong buffers), so the reference's
 // KokkosBlas scal/update calls and tendency/update functors never run as separate passes.
-// Targets (vertices then faces) are stored structure-of-arrays; with world > 1 each rank
-// evaluates a contiguous range of that list and the packed source records of its leaves are
-// exchanged after every stage (in-place allgatherv over NCCL).
+// Targets (vertices then faces) are stored structure-of-arrays.  With world > 1 each rank owns a contiguous range of the
+// vertices and a contiguous range of the faces (1/world of each) and evaluates them as two index lists per stage: list A = its
+// leaf faces (the sources it contributes), list B = its vertices and divided faces (never sources).  A goes first; the packed
+// records its stage kernel writes are exchanged (one kernel over NVLink peer memory on the copy stream when the peer path is on,
+// else the NCCL all-gather in line) WHILE the pair sum of list B runs, so the exchange is off the critical path.
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <new>
 
 #include "lpmx_finalize.cuh"
@@ -29,7 +32,14 @@ namespace lpmx {
 struct SolverState {
   lpmx_handle_t h = nullptr;
   int nv = 0, nf = 0, nt = 0, n_leaf = 0;
-  int t0 = 0, t1 = 0;  // this rank's targets
+  // this rank's targets: vertex rows [v0, v1) and face rows [f0, f1).  world == 1: one "list" B = everything (gid[1] null: the
+  // identity), list A empty.  world > 1: gid[0] = own leaf faces, gid[1] = own vertices + own divided faces (global indices
+  // into the concatenated SoA arrays).
+  int v0 = 0, v1 = 0, f0 = 0, f1 = 0;
+  bool split = false;
+  int* gid[2] = {nullptr, nullptr};
+  int n_part[2] = {0, 0};
+  int* gid_store = nullptr;  // nt ints in the slab
   bool has_state = false;
   void* slab = nullptr;
   double *X = nullptr, *U = nullptr, *Xw = nullptr, *Z = nullptr, *Zw = nullptr, *Psi = nullptr;
@@ -41,20 +51,15 @@ struct SolverState {
   double* packed[2] = {nullptr, nullptr};
   int cur = 0;
   int n_src_pad = 0;
-  double* partials = nullptr;
-  size_t partials_bytes = 0;
-  std::vector<long> tgt_off;     // world+1 target offsets
-  std::vector<long> packed_off;  // world+1 offsets into packed (in doubles)
+  double* partials[2] = {nullptr, nullptr};  // per list
+  std::vector<long> v_off, f_off;  // world+1 row offsets of the vertex / face ranges (f_off relative to the face list)
+  std::vector<long> packed_off;    // world+1 offsets into packed (in doubles)
+  int n_local() const { return n_part[0] + n_part[1]; }
   Vec3View view(double* base) const {
     Vec3View v;
     v.p = base;
     v.si = 1;
     v.sk = nt;
-    return v;
-  }
-  Vec3View local_view(double* base) const {
-    Vec3View v = view(base);
-    v.p = base + t0;
     return v;
   }
 };
@@ -70,7 +75,7 @@ static int solver_alloc(SolverState* s, lpmx_handle_t h, int nv, int nf, int n_k
   s->n_src_pad = round_up_chunk(nf);  // upper bound: every face a leaf
   // one slab: X U Xw (3nt each) Z Zw Psi (nt each) K (n_k * 4nt) area packed[2] | ints | mask
   size_t dbl = 9 * nt + 3 * nt + (size_t)n_k * 4 * nt + nf + 2 * kBveRec * (size_t)(s->n_src_pad + kChunk);
-  size_t bytes = dbl * sizeof(double) + sizeof(int) * (size_t)(nf + 1 + nt + 1) + (size_t)nf + 64 + 256;
+  size_t bytes = dbl * sizeof(double) + sizeof(int) * (size_t)(nf + 1 + nt + 1 + nt + 1) + (size_t)nf + 64 + 256;
   LPMX_TRY(slab_alloc(h, &s->slab, bytes));
   LPMX_CUDA(h, cudaMemsetAsync(s->slab, 0, bytes, h->stream));  // Kokkos views start at zero
   double* p = (double*)s->slab;
@@ -91,9 +96,8 @@ static int solver_alloc(SolverState* s, lpmx_handle_t h, int nv, int nf, int n_k
   int* ip = (int*)p;
   s->leaf_idx = ip, ip += nf + 1;
   s->self_idx = ip, ip += nt + 1;
+  s->gid_store = ip, ip += nt + 1;
   s->mask = (unsigned char*)ip;
-  s->t0 = (int)(((long)h->rank * nt) / h->world);
-  s->t1 = (int)(((long)(h->rank + 1) * nt) / h->world);
   return LPMX_OK;
 }
 
@@ -166,18 +170,19 @@ __device__ __forceinline__ void pack_target(long g, int nv, const unsigned char*
 }
 
 // pack the current state (X, Z) [or work state] of this rank's targets
-__global__ void pack_state_kernel(int t0, int n_local, int nv, long nt, const double* X, const double* Z,
+__global__ void pack_state_kernel(const int* gid, int n_local, int nv, long nt, const double* X, const double* Z,
                                   const unsigned char* mask, const int* leaf_idx, const double* area, double* packed) {
   const long li = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (li >= n_local) return;
-  const long g = t0 + li;
+  const long g = gid ? gid[li] : li;
   const double x[3] = {X[g], X[nt + g], X[2 * nt + g]};
   pack_target(g, nv, mask, leaf_idx, area, x, Z[g], packed);
 }
 
 struct StageArgs {
   PartView pv;
-  int t0, n_local, nv;
+  const int* gid;  // index list of this launch's targets (null: the identity)
+  int n_local, nv;
   long nt;
   int stage;  // which evaluation just finished (1-based); 0 = prologue from U
   int more;   // another step follows (fuse its stage 1)
@@ -210,7 +215,7 @@ __device__ __forceinline__ void bve_stage1(const StageArgs& a, long g, const dou
 __global__ void bve_rk4_stage_kernel(const StageArgs a) {
   const long li = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (li >= a.n_local) return;
-  const long g = a.t0 + li;
+  const long g = a.gid ? a.gid[li] : li;
   const long nt = a.nt;
   double u[3], xw[3], zw;
   if (a.stage == 0) {
@@ -280,7 +285,7 @@ template <bool WITH_PSI>
 __global__ void ic2d_rk2_stage_kernel(const StageArgs a) {
   const long li = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (li >= a.n_local) return;
-  const long g = a.t0 + li;
+  const long g = a.gid ? a.gid[li] : li;
   const long nt = a.nt;
   double u[3], xw[3], zw;
   if (a.stage == 0) {
@@ -319,20 +324,20 @@ __global__ void ic2d_rk2_stage_kernel(const StageArgs a) {
 }
 
 // psi-only finalize on the resident state (BVESphere::init_stream_fn)
-__global__ void psi_out_kernel(PartView pv, int t0, int n_local, double* Psi) {
+__global__ void psi_out_kernel(PartView pv, const int* gid, int n_local, double* Psi) {
   const long li = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (li >= n_local) return;
   double p[1];
   reduce_slots<1>(pv, li, p);
-  Psi[t0 + li] = p[0];
+  Psi[gid ? gid[li] : li] = p[0];
 }
 
-static int ensure_partials(SolverState* s, const SumPlan& plan) {
+// the handle-wide grow-only partials buffer of one list (re-fetched per evaluation: another solver on the handle may have grown it)
+static int ensure_partials(SolverState* s, int part, const SumPlan& plan) {
   const size_t need = plan_partials_bytes(plan) + 256;
   void* p = nullptr;
-  LPMX_TRY(dev_buffer(s->h, "solver_partials", need, &p));
-  s->partials = (double*)p;
-  s->partials_bytes = need;
+  LPMX_TRY(dev_buffer(s->h, part == 0 ? "solver_partials_a" : "solver_partials_b", need, &p));
+  s->partials[part] = (double*)p;
   return LPMX_OK;
 }
 
@@ -341,13 +346,40 @@ static int exchange_packed(SolverState* s, double* packed) {
   return comm_allgatherv(s->h, packed, s->packed_off.data());
 }
 
-// gather full-length SoA rows (n_rows rows of length nt) so every rank holds every target
+// The overlapped exchange of a split evaluation.  begin(): called after the stage kernel of list A (this rank's leaf faces) has
+// written its records; with the peer path the all-gather runs as ONE small kernel on the copy stream, ordered after that stage
+// kernel by an event, while the compute stream goes on with the pair sum of list B; without it (NCCL) the all-gather is
+// issued in line on the compute stream -- NCCL's kernels do not fit beside the persistent pair-sum CTAs, they would only run
+// after them.  end(): the compute stream waits for the exchange before the next evaluation reads the records.
+static int exchange_packed_begin(SolverState* s, double* packed, bool* async) {
+  lpmx_handle_t h = s->h;
+  *async = false;
+  if (h->world == 1) return LPMX_OK;
+  if (!peer_can_exchange(h, packed)) return comm_allgatherv(h, packed, s->packed_off.data());
+  for (int i = 0; i < 2; ++i)
+    if (!h->xchg_ev[i]) LPMX_CUDA(h, cudaEventCreateWithFlags(&h->xchg_ev[i], cudaEventDisableTiming));
+  LPMX_CUDA(h, cudaEventRecord(h->xchg_ev[0], h->stream));
+  LPMX_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->xchg_ev[0], 0));
+  LPMX_TRY(comm_allgatherv(h, packed, s->packed_off.data(), h->copy_stream));
+  LPMX_CUDA(h, cudaEventRecord(h->xchg_ev[1], h->copy_stream));
+  *async = true;
+  return LPMX_OK;
+}
+static int exchange_packed_end(SolverState* s, bool async) {
+  if (async) LPMX_CUDA(s->h, cudaStreamWaitEvent(s->h->stream, s->h->xchg_ev[1], 0));
+  return LPMX_OK;
+}
+
+// gather full-length SoA rows (n_rows rows of length nt) so every rank holds every target: the vertex ranges, then the face ranges
 static int exchange_rows(SolverState* s, double* base, int n_rows) {
   if (s->h->world == 1) return LPMX_OK;
   std::vector<long> off(s->h->world + 1);
   for (int r = 0; r < n_rows; ++r) {
-    for (int q = 0; q <= s->h->world; ++q) off[q] = s->tgt_off[q];
-    LPMX_TRY(comm_allgatherv(s->h, base + (long)r * s->nt, off.data()));
+    if (s->nv > 0) LPMX_TRY(comm_allgatherv(s->h, base + (long)r * s->nt, s->v_off.data()));
+    if (s->nf > 0) {
+      for (int q = 0; q <= s->h->world; ++q) off[q] = s->nv + s->f_off[q];
+      LPMX_TRY(comm_allgatherv(s->h, base + (long)r * s->nt, off.data()));
+    }
   }
   return LPMX_OK;
 }
@@ -373,9 +405,8 @@ static int copy_rows(lpmx_handle_t h, void* dev, const void* user, int layout, l
 
 // this rank's rows of the vertex list and of the face list
 static void local_rows(const SolverState* s, int rank, int world, long* v0, long* v1, long* f0, long* f1) {
-  const long t0 = ((long)rank * s->nt) / world, t1 = ((long)(rank + 1) * s->nt) / world;
-  *v0 = std::min<long>(t0, s->nv), *v1 = std::min<long>(t1, s->nv);
-  *f0 = std::max<long>(t0 - s->nv, 0), *f1 = std::max<long>(t1 - s->nv, 0);
+  *v0 = ((long)rank * s->nv) / world, *v1 = ((long)(rank + 1) * s->nv) / world;
+  *f0 = ((long)rank * s->nf) / world, *f1 = ((long)(rank + 1) * s->nf) / world;
 }
 
 static int solver_set_state(SolverState* s, const double* vx, const double* vz, const double* vu, const double* fx,
@@ -440,27 +471,51 @@ static int solver_set_state(SolverState* s, const double* vx, const double* vz, 
   const size_t pk_bytes = sizeof(double) * kBveRec * (size_t)(round_up_chunk(s->nf) + kChunk);
   LPMX_CUDA(h, cudaMemsetAsync(s->packed[0], 0, pk_bytes, h->stream));
   LPMX_CUDA(h, cudaMemsetAsync(s->packed[1], 0, pk_bytes, h->stream));
-  // shard offsets (targets, and each rank's leaf range in the packed array)
+  // shard offsets: each rank owns rows [v_off[r], v_off[r+1]) of the vertices and [f_off[r], f_off[r+1]) of the faces, and with
+  // them the leaf range [leaf_idx[f_off[r]], leaf_idx[f_off[r+1]]) of the packed array
   const int W = h->world;
-  s->tgt_off.assign(W + 1, 0);
+  s->v_off.assign(W + 1, 0);
+  s->f_off.assign(W + 1, 0);
   s->packed_off.assign(W + 1, 0);
+  // LPMX_FORCE_SPLIT=1: evaluate the two index lists on a single GPU as well (test hook: the list path of the kernels and the
+  // A-then-B evaluation can then be checked on a one-GPU box; there is nothing to exchange)
+  const char* fs = getenv("LPMX_FORCE_SPLIT");
+  const bool want_split = W > 1 || (fs && fs[0] == '1');
   std::vector<int> leaf_host;
-  if (W > 1 && s->nf > 0) {
+  if (want_split && s->nf > 0) {
     leaf_host.resize(s->nf);
     LPMX_CUDA(h, cudaMemcpyAsync(leaf_host.data(), s->leaf_idx, sizeof(int) * s->nf, cudaMemcpyDeviceToHost, h->stream));
     LPMX_CUDA(h, cudaStreamSynchronize(h->stream));
   }
+  auto leaf_at = [&](long f) -> long { return f >= s->nf ? s->n_leaf : (want_split ? leaf_host[f] : 0); };
   for (int r = 0; r <= W; ++r) {
-    const long t = ((long)r * s->nt) / W;
-    s->tgt_off[r] = t;
-    long f = t - s->nv;
-    if (f < 0) f = 0;
-    long l = (f >= s->nf) ? s->n_leaf : (W > 1 ? leaf_host[f] : 0);
-    if (r == W) l = s->n_leaf;
-    s->packed_off[r] = kBveRec * l;
+    s->v_off[r] = ((long)r * s->nv) / W;
+    s->f_off[r] = ((long)r * s->nf) / W;
+    s->packed_off[r] = kBveRec * (r == W ? (long)s->n_leaf : leaf_at(s->f_off[r]));
   }
-  s->t0 = (int)s->tgt_off[h->rank];
-  s->t1 = (int)s->tgt_off[h->rank + 1];
+  s->v0 = (int)s->v_off[h->rank], s->v1 = (int)s->v_off[h->rank + 1];
+  s->f0 = (int)s->f_off[h->rank], s->f1 = (int)s->f_off[h->rank + 1];
+  s->split = want_split;
+  if (!s->split) {
+    s->gid[0] = s->gid[1] = nullptr;
+    s->n_part[0] = 0, s->n_part[1] = s->nt;
+  } else {
+    // list A: own leaf faces; list B: own vertices, then own divided faces
+    std::vector<int> la, lb;
+    la.reserve(s->f1 - s->f0), lb.reserve((s->v1 - s->v0) + (s->f1 - s->f0));
+    for (int v = s->v0; v < s->v1; ++v) lb.push_back(v);
+    for (long f = s->f0; f < s->f1; ++f) {
+      const bool leaf = leaf_at(f + 1) > leaf_at(f);
+      (leaf ? la : lb).push_back(s->nv + (int)f);
+    }
+    s->n_part[0] = (int)la.size(), s->n_part[1] = (int)lb.size();
+    s->gid[0] = s->gid_store, s->gid[1] = s->gid_store + la.size();
+    if (!la.empty())
+      LPMX_CUDA(h, cudaMemcpyAsync(s->gid[0], la.data(), sizeof(int) * la.size(), cudaMemcpyHostToDevice, h->stream));
+    if (!lb.empty())
+      LPMX_CUDA(h, cudaMemcpyAsync(s->gid[1], lb.data(), sizeof(int) * lb.size(), cudaMemcpyHostToDevice, h->stream));
+    LPMX_CUDA(h, cudaStreamSynchronize(h->stream));  // la / lb go out of scope
+  }
   s->has_state = true;
   if (!is_device_pointer(vx) || !is_device_pointer(fx)) LPMX_CUDA(h, cudaStreamSynchronize(h->stream));
   return LPMX_OK;
@@ -523,15 +578,15 @@ static int solver_get_state(SolverState* s, double* vx, double* vz, double* vu, 
   return LPMX_OK;
 }
 
-static StageArgs stage_args(SolverState* s, const SumPlan* plan, int stage, int more, double dt, double Omega,
+static StageArgs stage_args(SolverState* s, int part, const SumPlan* plan, int stage, int more, double dt, double Omega,
                             double* packed_next) {
   StageArgs a;
   if (plan)
-    a.pv = part_view(*plan, s->partials);
+    a.pv = part_view(*plan, s->partials[part]);
   else
     a.pv = PartView{nullptr, 0, 0, 0, 1, 1};
-  a.t0 = s->t0;
-  a.n_local = s->t1 - s->t0;
+  a.gid = s->gid[part];
+  a.n_local = s->n_part[part];
   a.nv = s->nv;
   a.nt = s->nt;
   a.stage = stage;
@@ -552,26 +607,63 @@ static StageArgs stage_args(SolverState* s, const SumPlan* plan, int stage, int 
 // pack (X,Z) of the resident state into packed[cur] and exchange
 static int pack_resident(SolverState* s) {
   lpmx_handle_t h = s->h;
-  const int n_local = s->t1 - s->t0;
+  const int part = s->split ? 0 : 1;  // only leaf faces have records: list A when the lists are split
+  const int n_local = s->n_part[part];
   if (n_local > 0) {
     const int threads = 256, blocks = (n_local + threads - 1) / threads;
-    pack_state_kernel<<<blocks, threads, 0, h->stream>>>(s->t0, n_local, s->nv, s->nt, s->X, s->Z, s->mask, s->leaf_idx,
-                                                         s->area, s->packed[s->cur]);
+    pack_state_kernel<<<blocks, threads, 0, h->stream>>>(s->gid[part], n_local, s->nv, s->nt, s->X, s->Z, s->mask,
+                                                         s->leaf_idx, s->area, s->packed[s->cur]);
     ++h->launches;
     LPMX_CUDA(h, cudaGetLastError());
   }
   return exchange_packed(s, s->packed[s->cur]);
 }
 
+// One evaluation over this rank's targets: per list, pair sum -> stage kernel (`stage_fn(part)` launches it); the records the
+// stage kernel of list A wrote into `next` are exchanged while list B is summed (see exchange_packed_begin).
+template <class StageFn>
+static int eval_lists(SolverState* st, const SumPlan* plans, double* tgt_base, double kappa, double* next, StageFn stage_fn) {
+  lpmx_handle_t h = st->h;
+  bool async = false;
+  for (int part = 0; part < 2; ++part) {
+    if (st->n_part[part] > 0) {
+      LPMX_TRY(ensure_partials(st, part, plans[part]));
+      LPMX_TRY(launch_pair_sum(h, plans[part], st->view(tgt_base), st->self_idx, st->packed[st->cur], kappa, st->partials[part],
+                               0.0, st->gid[part]));
+      LPMX_TRY(stage_fn(part));
+    }
+    if (part == 0 && st->split && next) LPMX_TRY(exchange_packed_begin(st, next, &async));
+  }
+  if (next) {
+    LPMX_TRY(exchange_packed_end(st, async));
+    st->cur ^= 1;
+  }
+  return LPMX_OK;
+}
+
+// "stage 1 of the first step from the resident velocity" for both lists, then the exchange of the records it wrote
+template <class Launch>
+static int prologue_lists(SolverState* st, Launch launch) {
+  for (int part = 0; part < 2; ++part)
+    if (st->n_part[part] > 0) LPMX_TRY(launch(part));
+  return exchange_packed(st, st->packed[st->cur]);
+}
+
+static int make_list_plans(SolverState* st, int kind, SumPlan* plans) {
+  for (int part = 0; part < 2; ++part)
+    LPMX_TRY(make_plan(st->h, kind, st->n_part[part], st->n_leaf, &plans[part], /*allow_const_stream=*/st->gid[part] == nullptr));
+  return LPMX_OK;
+}
+
 }  // namespace lpmx
 
 struct lpmx_bve_solver_s {
   SolverState st;
-  SumPlan plan_vel, plan_psi;
+  SumPlan plan_vel[2], plan_psi[2];  // per target list
 };
 struct lpmx_ic2d_solver_s {
   SolverState st;
-  SumPlan plan_vel, plan_velpsi, plan_psi;
+  SumPlan plan_vel[2], plan_velpsi[2], plan_psi[2];  // per target list
   double eps = 0;
   // Lazy stream function.  psi of the new state is an OUTPUT of a step that no later step reads (quirk B-i), and the fused
   // velocity + psi evaluation costs 2.4 x the velocity one.  advance() therefore ends with the velocity-only kernel and marks
@@ -613,8 +705,8 @@ int lpmx_bve_solver_set_state(lpmx_bve_solver_t s, const double* vx, const doubl
                               const unsigned char* fm, int layout, long vld, long fld) {
   if (!s) return LPMX_ERR_INVALID;
   LPMX_TRY(solver_set_state(&s->st, vx, vz, vu, fx, fz, fu, fa, fm, layout, vld, fld, /*skip_self=*/1));
-  LPMX_TRY(make_plan(s->st.h, kVel, s->st.t1 - s->st.t0, s->st.n_leaf, &s->plan_vel));
-  LPMX_TRY(make_plan(s->st.h, kPsi, s->st.t1 - s->st.t0, s->st.n_leaf, &s->plan_psi));
+  LPMX_TRY(make_list_plans(&s->st, kVel, s->plan_vel));
+  LPMX_TRY(make_list_plans(&s->st, kPsi, s->plan_psi));
   return LPMX_OK;
 }
 
@@ -633,31 +725,33 @@ int lpmx_bve_solver_interactions_per_eval(lpmx_bve_solver_t s, double* local, do
   if (local) {
     // leaves among this rank's face targets
     const long l0 = st.packed_off[st.h->rank] / kBveRec, l1 = st.packed_off[st.h->rank + 1] / kBveRec;
-    *local = (double)(st.t1 - st.t0) * nl - (double)(st.h->world > 1 ? (l1 - l0) : st.n_leaf);
+    *local = (double)st.n_local() * nl - (double)(st.h->world > 1 ? (l1 - l0) : st.n_leaf);
   }
   return LPMX_OK;
+}
+
+// a psi-only pass over the lists (BVESphere::init_stream_fn, the lazy psi of the IC2D solver): no records are written
+static int psi_pass(SolverState* st, const SumPlan* plans, double kappa) {
+  return eval_lists(st, plans, st->X, kappa, nullptr, [&](int part) -> int {
+    const int n = st->n_part[part], threads = 128, blocks = (n + threads - 1) / threads;
+    psi_out_kernel<<<blocks, threads, 0, st->h->stream>>>(part_view(plans[part], st->partials[part]), st->gid[part], n, st->Psi);
+    ++st->h->launches;
+    return check_cuda(st->h, cudaGetLastError(), "psi_out_kernel launch");
+  });
 }
 
 static int bve_eval(lpmx_bve_solver_s* s, int stage, int more, double dt, double Omega) {
   SolverState& st = s->st;
   lpmx_handle_t h = st.h;
-  const int n_local = st.t1 - st.t0;
-  LPMX_TRY(ensure_partials(&st, s->plan_vel));
-  LPMX_TRY(launch_pair_sum(h, s->plan_vel, st.local_view(st.Xw), st.self_idx + st.t0, st.packed[st.cur], 1.0, st.partials));
   const bool writes_next = !(stage == 4 && !more);
   double* next = writes_next ? st.packed[st.cur ^ 1] : nullptr;
-  if (n_local > 0) {
-    const StageArgs a = stage_args(&st, &s->plan_vel, stage, more, dt, Omega, next);
-    const int threads = 128, blocks = (n_local + threads - 1) / threads;
+  return eval_lists(&st, s->plan_vel, st.Xw, 1.0, next, [&](int part) -> int {
+    const StageArgs a = stage_args(&st, part, &s->plan_vel[part], stage, more, dt, Omega, next);
+    const int threads = 128, blocks = (a.n_local + threads - 1) / threads;
     bve_rk4_stage_kernel<<<blocks, threads, 0, h->stream>>>(a);
     ++h->launches;
-    LPMX_CUDA(h, cudaGetLastError());
-  }
-  if (writes_next) {
-    LPMX_TRY(exchange_packed(&st, next));
-    st.cur ^= 1;
-  }
-  return LPMX_OK;
+    return check_cuda(h, cudaGetLastError(), "bve_rk4_stage_kernel launch");
+  });
 }
 
 int lpmx_bve_solver_init_velocity(lpmx_bve_solver_t s) {
@@ -679,15 +773,7 @@ int lpmx_bve_solver_stream_fn(lpmx_bve_solver_t s, double* vert_psi, double* fac
   if (!st.has_state) return set_error(h, LPMX_ERR_STATE, "stream_fn before set_state");
   LPMX_CUDA(h, cudaSetDevice(h->device));
   LPMX_TRY(pack_resident(&st));
-  LPMX_TRY(ensure_partials(&st, s->plan_psi));
-  LPMX_TRY(launch_pair_sum(h, s->plan_psi, st.local_view(st.X), st.self_idx + st.t0, st.packed[st.cur], 1.0, st.partials));
-  const int n_local = st.t1 - st.t0;
-  if (n_local > 0) {
-    const int threads = 128, blocks = (n_local + threads - 1) / threads;
-    psi_out_kernel<<<blocks, threads, 0, h->stream>>>(part_view(s->plan_psi, st.partials), st.t0, n_local, st.Psi);
-    ++h->launches;
-    LPMX_CUDA(h, cudaGetLastError());
-  }
+  LPMX_TRY(psi_pass(&st, s->plan_psi, 1.0));
   return solver_get_state(&st, nullptr, nullptr, nullptr, vert_psi, nullptr, nullptr, nullptr, face_psi,
                           LPMX_LAYOUT_RIGHT, 0, 0);
 }
@@ -700,16 +786,14 @@ int lpmx_bve_solver_advance(lpmx_bve_solver_t s, double dt, double Omega, int n_
   if (n_steps < 0) return set_error(h, LPMX_ERR_INVALID, "negative step count");
   if (n_steps == 0 || st.nt == 0) return LPMX_OK;
   LPMX_CUDA(h, cudaSetDevice(h->device));
-  const int n_local = st.t1 - st.t0;
   // prologue: stage 1 of the first step from the resident velocity
-  if (n_local > 0) {
-    const StageArgs a = stage_args(&st, nullptr, 0, 1, dt, Omega, st.packed[st.cur]);
-    const int threads = 128, blocks = (n_local + threads - 1) / threads;
+  LPMX_TRY(prologue_lists(&st, [&](int part) -> int {
+    const StageArgs a = stage_args(&st, part, nullptr, 0, 1, dt, Omega, st.packed[st.cur]);
+    const int threads = 128, blocks = (a.n_local + threads - 1) / threads;
     bve_rk4_stage_kernel<<<blocks, threads, 0, h->stream>>>(a);
     ++h->launches;
-    LPMX_CUDA(h, cudaGetLastError());
-  }
-  LPMX_TRY(exchange_packed(&st, st.packed[st.cur]));
+    return check_cuda(h, cudaGetLastError(), "bve_rk4_stage_kernel launch");
+  }));
   for (int step = 0; step < n_steps; ++step) {
     const int more = step + 1 < n_steps;
     for (int stage = 1; stage <= 4; ++stage) LPMX_TRY(bve_eval(s, stage, more, dt, Omega));
@@ -766,9 +850,9 @@ int lpmx_ic2d_solver_set_state(lpmx_ic2d_solver_t s, const double* px, const dou
   // Incompressible2DActiveSums skips the self term only when |eps| < DBL_EPSILON (:235)
   const int skip = std::fabs(s->eps) < DBL_EPSILON;
   LPMX_TRY(solver_set_state(&s->st, px, pz, pu, ax, az, au, aa, am, layout, pld, ald, skip));
-  LPMX_TRY(make_plan(s->st.h, kVel, s->st.t1 - s->st.t0, s->st.n_leaf, &s->plan_vel));
-  LPMX_TRY(make_plan(s->st.h, kVelPsi, s->st.t1 - s->st.t0, s->st.n_leaf, &s->plan_velpsi));
-  LPMX_TRY(make_plan(s->st.h, kPsi, s->st.t1 - s->st.t0, s->st.n_leaf, &s->plan_psi));
+  LPMX_TRY(make_list_plans(&s->st, kVel, s->plan_vel));
+  LPMX_TRY(make_list_plans(&s->st, kVelPsi, s->plan_velpsi));
+  LPMX_TRY(make_list_plans(&s->st, kPsi, s->plan_psi));
   s->psi_stale = false;
   return LPMX_OK;
 }
@@ -779,16 +863,7 @@ static int ic2d_refresh_psi(lpmx_ic2d_solver_s* s) {
   lpmx_handle_t h = st.h;
   LPMX_CUDA(h, cudaSetDevice(h->device));
   LPMX_TRY(pack_resident(&st));
-  LPMX_TRY(ensure_partials(&st, s->plan_psi));
-  LPMX_TRY(launch_pair_sum(h, s->plan_psi, st.local_view(st.X), st.self_idx + st.t0, st.packed[st.cur], 1.0 + s->eps * s->eps,
-                           st.partials));
-  const int n_local = st.t1 - st.t0;
-  if (n_local > 0) {
-    const int threads = 128, blocks = (n_local + threads - 1) / threads;
-    psi_out_kernel<<<blocks, threads, 0, h->stream>>>(part_view(s->plan_psi, st.partials), st.t0, n_local, st.Psi);
-    ++h->launches;
-    LPMX_CUDA(h, cudaGetLastError());
-  }
+  LPMX_TRY(psi_pass(&st, s->plan_psi, 1.0 + s->eps * s->eps));
   s->psi_stale = false;
   return LPMX_OK;
 }
@@ -816,29 +891,21 @@ int lpmx_ic2d_solver_lazy_stream_fn(lpmx_ic2d_solver_t s, int demand_next) {
 static int ic2d_eval(lpmx_ic2d_solver_s* s, int stage, int more, double dt, double Omega, bool want_psi = true) {
   SolverState& st = s->st;
   lpmx_handle_t h = st.h;
-  const int n_local = st.t1 - st.t0;
   const bool with_psi = (stage == 2) && !more && want_psi;
-  const SumPlan& plan = with_psi ? s->plan_velpsi : s->plan_vel;
+  const SumPlan* plans = with_psi ? s->plan_velpsi : s->plan_vel;
   const double kappa = 1.0 + s->eps * s->eps;
-  LPMX_TRY(ensure_partials(&st, plan));
-  LPMX_TRY(launch_pair_sum(h, plan, st.local_view(st.Xw), st.self_idx + st.t0, st.packed[st.cur], kappa, st.partials));
   const bool writes_next = !(stage == 2 && !more);
   double* next = writes_next ? st.packed[st.cur ^ 1] : nullptr;
-  if (n_local > 0) {
-    const StageArgs a = stage_args(&st, &plan, stage, more, dt, Omega, next);
-    const int threads = 128, blocks = (n_local + threads - 1) / threads;
+  return eval_lists(&st, plans, st.Xw, kappa, next, [&](int part) -> int {
+    const StageArgs a = stage_args(&st, part, &plans[part], stage, more, dt, Omega, next);
+    const int threads = 128, blocks = (a.n_local + threads - 1) / threads;
     if (with_psi)
       ic2d_rk2_stage_kernel<true><<<blocks, threads, 0, h->stream>>>(a);
     else
       ic2d_rk2_stage_kernel<false><<<blocks, threads, 0, h->stream>>>(a);
     ++h->launches;
-    LPMX_CUDA(h, cudaGetLastError());
-  }
-  if (writes_next) {
-    LPMX_TRY(exchange_packed(&st, next));
-    st.cur ^= 1;
-  }
-  return LPMX_OK;
+    return check_cuda(h, cudaGetLastError(), "ic2d_rk2_stage_kernel launch");
+  });
 }
 
 int lpmx_ic2d_solver_init_direct_sums(lpmx_ic2d_solver_t s) {
@@ -860,15 +927,13 @@ int lpmx_ic2d_solver_advance(lpmx_ic2d_solver_t s, double dt, double Omega, int 
   if (n_steps < 0) return set_error(h, LPMX_ERR_INVALID, "negative step count");
   if (n_steps == 0 || st.nt == 0) return LPMX_OK;
   LPMX_CUDA(h, cudaSetDevice(h->device));
-  const int n_local = st.t1 - st.t0;
-  if (n_local > 0) {
-    const StageArgs a = stage_args(&st, nullptr, 0, 1, dt, Omega, st.packed[st.cur]);
-    const int threads = 128, blocks = (n_local + threads - 1) / threads;
+  LPMX_TRY(prologue_lists(&st, [&](int part) -> int {
+    const StageArgs a = stage_args(&st, part, nullptr, 0, 1, dt, Omega, st.packed[st.cur]);
+    const int threads = 128, blocks = (a.n_local + threads - 1) / threads;
     ic2d_rk2_stage_kernel<false><<<blocks, threads, 0, h->stream>>>(a);
     ++h->launches;
-    LPMX_CUDA(h, cudaGetLastError());
-  }
-  LPMX_TRY(exchange_packed(&st, st.packed[st.cur]));
+    return check_cuda(h, cudaGetLastError(), "ic2d_rk2_stage_kernel launch");
+  }));
   const bool eager_psi = s->psi_demanded;  // somebody read psi since the last advance: fuse it into the final evaluation
   for (int step = 0; step < n_steps; ++step) {
     const int more = step + 1 < n_steps;

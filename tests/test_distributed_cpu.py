@@ -1,8 +1,9 @@
 """CPU, world_size 2 over gloo: the host-side logic of the target-sharded evaluation.
 
-Each rank evaluates its contiguous range of the concatenated target list against ALL leaf sources (with the
-oracle standing in for the GPU kernel), the shards are all-gathered, and the result must equal the unsharded
-evaluation bit for bit -- the property the multi-GPU stepper relies on.  Also checks the partition helpers
+Each rank evaluates its two target lists (A: own leaf faces, B: own vertices and divided faces -- lpm_b200/partition.py, the
+mirror of solver_set_state) against ALL leaf sources (with the oracle standing in for the GPU kernel), the vertex and the face
+row ranges are all-gathered, and the result must equal the unsharded evaluation bit for bit -- the property the multi-GPU
+stepper relies on.  Also checks the partition helpers
 and that the NCCL-unique-id hand-off reaches every rank identically."""
 import os
 import socket
@@ -20,15 +21,21 @@ def test_offsets_cover_without_overlap():
         assert max(b - a for a, b in zip(off, off[1:])) - min(b - a for a, b in zip(off, off[1:])) <= 1
 
 
-def test_leaf_offsets_follow_face_ranges(meshes):
+def test_leaf_offsets_and_target_lists_follow_the_row_ranges(meshes):
     m = meshes("icos", 3)
     for w in (1, 2, 3, 8):
-        t = partition.target_offsets(m.n_verts + m.n_faces, w)
-        l = partition.leaf_offsets(m.n_verts, m.face_mask, w)
+        l = partition.leaf_offsets(m.face_mask, w)
         assert l[0] == 0 and l[-1] == m.n_face_leaves
+        seen = []
         for r in range(w):
-            f0, f1 = max(t[r] - m.n_verts, 0), max(t[r + 1] - m.n_verts, 0)
+            (v0, v1), (f0, f1) = partition.local_rows(m.n_verts, m.n_faces, r, w)
             assert l[r + 1] - l[r] == int((m.face_mask[f0:f1] == 0).sum())
+            a, b = partition.target_lists(m.n_verts, m.face_mask, r, w)
+            assert len(a) == l[r + 1] - l[r] and len(a) + len(b) == (v1 - v0) + (f1 - f0)
+            assert (m.face_mask[a - m.n_verts] == 0).all()                       # A: leaf faces only (the sources)
+            assert ((b < m.n_verts) | (m.face_mask[np.maximum(b - m.n_verts, 0)] == 1)).all()  # B: never sources
+            seen += [a, b]
+        assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(m.n_verts + m.n_faces))  # a partition of all targets
     assert partition.interactions_per_eval(2562, 6820, 5120) == (2562 + 6820) * 5120 - 5120
 
 
@@ -53,29 +60,29 @@ def _worker(rank, world, port, q):
         m = PolyMesh2d("cubed", 3)
         fz = gallery.SolidBodyRotation()(m.face_xyz)
         nv, nf = m.n_verts, m.n_faces
-        off = partition.target_offsets(nv + nf, world)
-        t0, t1 = off[rank], off[rank + 1]
-        # this rank's targets: a slice of [vertices | faces]; faces need the collocated (skip-self) rule
+        (v0, v1), (f0, f1) = partition.local_rows(nv, nf, rank, world)
+        la, lb = partition.target_lists(nv, m.face_mask, rank, world)
+        # this rank's targets: list A then list B; faces need the collocated (skip-self) rule
         full_v = oracle.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask)
         full_f = oracle.bve_velocity(None, m.face_xyz, fz, m.face_area, m.face_mask, collocated=True)
         full = np.concatenate([full_v, full_f])
         xyz = np.concatenate([m.vert_xyz, m.face_xyz])
-        local = np.zeros((t1 - t0, 3))
-        for i, g in enumerate(range(t0, t1)):
+        gathered = torch.zeros((nv + nf, 3), dtype=torch.float64)
+        for g in np.concatenate([la, lb]):
             mask = m.face_mask.copy()
             if g >= nv:
                 mask[g - nv] = 1  # skip the self pair by index
-            local[i] = oracle.bve_velocity(xyz[g:g + 1], m.face_xyz, fz, m.face_area, mask)[0]
-        # in-place allgatherv: every rank broadcasts its segment
-        gathered = torch.zeros((nv + nf, 3), dtype=torch.float64)
-        gathered[t0:t1] = torch.from_numpy(local)
+            gathered[g] = torch.from_numpy(oracle.bve_velocity(xyz[g:g + 1], m.face_xyz, fz, m.face_area, mask)[0])
+        # in-place allgatherv of the vertex rows, then of the face rows: every rank broadcasts its segments
+        voff, foff = partition.target_offsets(nv, world), partition.target_offsets(nf, world)
         for r in range(world):
-            seg = gathered[off[r]:off[r + 1]].contiguous()
-            dist.broadcast(seg, src=r)
-            gathered[off[r]:off[r + 1]] = seg
+            for lo_, hi_ in ((voff[r], voff[r + 1]), (nv + foff[r], nv + foff[r + 1])):
+                seg = gathered[lo_:hi_].contiguous()
+                dist.broadcast(seg, src=r)
+                gathered[lo_:hi_] = seg
         ok_sum = bool(np.array_equal(gathered.numpy(), full))
         # leaf ranges: the packed records this rank would own
-        lo = partition.leaf_offsets(nv, m.face_mask, world)
+        lo = partition.leaf_offsets(m.face_mask, world)
         uid = broadcast_unique_id(lambda: bytes(range(128)), rank)
         q.put((rank, ok_sum, lo, uid == bytes(range(128))))
     finally:

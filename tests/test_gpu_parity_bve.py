@@ -367,3 +367,57 @@ def test_rk4_step_at_cubed7_sampled_targets_against_the_oracle(engine, oracle):
     check_err("face_xyz", field_rel_err(out[3], ref["face_xyz"]), VEL_TOL)
     check_err("face_zeta", field_rel_err(out[4], ref["face_zeta"]), VORT_TOL)
     check_err("face_vel", field_rel_err(out[5], ref["face_vel"]), VEL_TOL)
+
+
+def test_split_target_lists_on_one_gpu(oracle, meshes, monkeypatch):
+    """What every rank of a multi-GPU run does per evaluation -- list A (its leaf faces) through the pair kernel's index-list
+    path, their stage kernel, then list B (vertices and divided faces) -- forced onto one GPU (LPMX_FORCE_SPLIT=1: all targets
+    are "own", nothing is exchanged): BVERK4 steps, the stream function and the Incompressible2DRK2 stepper with its lazy psi
+    against the oracle, on an icosahedral mesh (divided faces in list B) and a cubed-sphere one."""
+    from lpm_b200.api import Engine, IC2DSolver
+    monkeypatch.setenv("LPMX_FORCE_SPLIT", "1")
+    e = Engine(0)
+    try:
+        for seed, depth in (("icos", 3), ("cubed", 4)):
+            m = meshes(seed, depth)
+            leaf = m.face_mask == 0
+            sel = leaf if seed == "icos" else None
+            ref = _rk4_case(m, "rh54", oracle)
+            if seed == "icos":
+                ref[5][~leaf] = 0.0
+            got = [a.copy() for a in ref]
+            l0 = e.launch_count()
+            oracle.bve_rk4_step(0.01, 2 * np.pi, *ref, m.face_area, m.face_mask, n_steps=2)
+            e.bve_rk4_step(0.01, 2 * np.pi, *got, m.face_area, m.face_mask, n_steps=2)
+            assert e.launch_count() - l0 >= 2 * 4 * 4  # two pair sums + two stage kernels per evaluation
+            for n, k, t in (("vert_xyz", 0, VEL_TOL), ("vert_zeta", 1, VORT_TOL), ("vert_vel", 2, VEL_TOL)):
+                check_err(n, field_rel_err(got[k], ref[k]), t)
+            for n, k, t in (("face_xyz", 3, VEL_TOL), ("face_zeta", 4, VORT_TOL), ("face_vel", 5, VEL_TOL)):
+                check_err(n, field_rel_err(got[k], ref[k], sel), t)
+            area, mask = np.ascontiguousarray(m.face_area), np.ascontiguousarray(m.face_mask)
+            s = BVESolver(e, m.n_verts, m.n_faces)
+            s.set_state(*got, area, mask)
+            pv, pf = np.empty(m.n_verts), np.empty(m.n_faces)
+            s.stream_fn(pv, pf)
+            s.close()
+            check_err("vert_psi", field_rel_err(pv, oracle.bve_streamfn(got[0], got[3], got[4], area, mask)), VEL_TOL)
+            check_err("face_psi", field_rel_err(pf, oracle.bve_streamfn(None, got[3], got[4], area, mask, collocated=True), sel), VEL_TOL)
+            # Incompressible2DRK2 through the resident solver (lazy psi: the second advance leaves it stale, get_state refreshes)
+            fz = got[4]
+            pu, pp = oracle.ic2d_sums(got[0], got[3], fz, area, mask, eps=0.0)
+            au, ap = oracle.ic2d_sums(None, got[3], fz, area, mask, eps=0.0, targets_are_sources=True)
+            if seed == "icos":
+                au[~leaf], ap[~leaf] = 0.0, 0.0
+            r2 = [got[0].copy(), got[1].copy(), pu, pp, got[3].copy(), fz.copy(), au, ap]
+            s2 = IC2DSolver(e, m.n_verts, m.n_faces, eps=0.0)
+            s2.set_state(r2[0], r2[1], r2[2], r2[4], r2[5], r2[6], area, mask)
+            s2.advance(0.01, 2 * np.pi, 1)
+            s2.advance(0.01, 2 * np.pi, 1)
+            out = [np.empty_like(a) for a in r2]
+            s2.get_state(*out)
+            s2.close()
+            oracle.ic2d_rk2_step(0.01, 2 * np.pi, 0.0, *r2, area, mask, n_steps=2)
+            for n, a, b, t in zip(["px", "pz", "pu", "ppsi", "ax", "az", "au", "apsi"], out, r2, [VEL_TOL, VORT_TOL, VEL_TOL, VEL_TOL] * 2):
+                check_err(n, field_rel_err(a, b, sel if n.startswith("a") else None), t)
+    finally:
+        e.close()

@@ -67,6 +67,7 @@ static void run(const char* label) {
   a.tgt.si = 1;
   a.tgt.sk = n_tgt;
   a.self_idx = nullptr;
+  a.tgt_map = nullptr;
   a.packed = d_src;
   a.part = d_part;
   a.n_tgt = n_tgt;
