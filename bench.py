@@ -489,10 +489,10 @@ def main():
             parity = {"error": repr(e)}
 
     # ---- roofline of the dominant kernel (rank-local): algorithmic flops / CUDA-event launch time ----
-    if args.stepper == "swe_rk2":  # the SWE solver shards the concatenated list; BVE / IC2D shard vertices and faces separately
+    if args.stepper == "swe_rk2":  # the SWE solver shards the concatenated list; BVE / IC2D shard leaves and non-sources separately
         n_local_targets = solver_local_targets(nv + nf, rank, world)
     else:
-        n_local_targets = solver_local_targets(nv, rank, world) + solver_local_targets(nf, rank, world)
+        n_local_targets = solver_local_targets(nleaf, rank, world) + solver_local_targets(nv + nf - nleaf, rank, world)
     local_inter = evals * args.steps * (float(n_local_targets) * nleaf)
     flops_per = FLOPS_PER_INTERACTION[args.stepper]
     achieved_tf = local_inter * flops_per / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else None
@@ -528,8 +528,8 @@ def main():
         # host arrays carry its own target rows, as in any distributed-memory program: it uploads those rows (+ area and mask
         # of all faces) and downloads those rows; nothing is replicated through the host.
         sharded_io = world > 1 and args.stepper in ("bve_rk4", "ic2d_rk2")
-        (lv0, lv1), (lf0, lf1) = eng.local_rows(nv, nf)
-        n_own = (lv1 - lv0) + (lf1 - lf0)
+        own_a, own_b = eng.local_targets(nv, nf, mask)
+        n_own = len(own_a) + len(own_b)
 
         def pin(a):
             t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()

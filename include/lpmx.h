@@ -177,17 +177,19 @@ int lpmx_profile_read(lpmx_handle_t h, long* n_launches, double* total_ms, doubl
 int lpmx_copy(lpmx_handle_t h, void* dst, const void* src, long bytes);
 
 /* Target sharding over the GPUs of one box (the reference has no multi-device path).  This handle
- * evaluates the targets of rank `rank` of `world`: for the BVE / Incompressible2D solvers 1/world of the vertex rows and
- * 1/world of the face rows (lpmx_local_rows), for the SWE and planar solvers a contiguous range of the concatenated list
+ * evaluates the targets of rank `rank` of `world`: for the BVE / Incompressible2D solvers 1/world of the leaf faces and 1/world
+ * of the other targets (lpmx_local_targets), for the SWE and planar solvers a contiguous range of the concatenated list
  * (vertices then faces).  Default: rank 0 of 1. */
 int lpmx_set_partition(lpmx_handle_t h, int rank, int world);
-/* The rows of the two target lists (n_first vertices / passive particles, n_second faces / active particles) that this
- * handle's rank owns in the BVE / Incompressible2D solvers: [first0, first1) = [r n_first / W, (r+1) n_first / W) and
- * [second0, second1) likewise. */
-int lpmx_local_rows(lpmx_handle_t h, int n_first, int n_second, int* first0, int* first1, int* second0, int* second1);
+/* The targets this handle's rank owns in the BVE / Incompressible2D solvers, as indices into the concatenated list (n_first
+ * vertices / passive particles, then n_second faces / active particles): first its n_sources leaf faces (slice `rank` of the
+ * leaves in index order), then its n_other non-sources (slice `rank` of [vertices, divided faces in index order]).
+ * mask_second: HOST array of the faces' mask bytes.  idx: room for n_first + n_second entries. */
+int lpmx_local_targets(lpmx_handle_t h, int n_first, int n_second, const unsigned char* mask_second, int* idx, int* n_sources,
+                       int* n_other);
 /* Sharded host I/O for world > 1 (BVE and Incompressible2D solvers and their in-place steppers).  Off (default): every rank
  * passes the full state and gets the full state back (replicated, as if it were alone).  On: of the HOST arrays passed to
- * set_state / *_rk?_step only the rows of lpmx_local_rows are read (area and mask are always read in full), and get_state / the
+ * set_state / *_rk?_step only the rows of lpmx_local_targets are read (area and mask are always read in full), and get_state / the
  * in-place steppers write back only those rows, without gathering the other ranks' -- each rank's host memory then holds its
  * own shard, as in any distributed-memory program.  Cuts the per-step host traffic of an 8-GPU run from 14 + 13 MB to
  * 2.9 + 1.6 MB per rank at cubed-7.  Device-pointer arguments are unaffected.  No counterpart in the reference. */

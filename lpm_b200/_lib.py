@@ -149,7 +149,7 @@ def _declare(L):
         "lpmx_bve_velocity": [vp, vp, i, l, i, vp, i, l, vp, vp, vp, i, i, vp],
         "lpmx_bve_streamfn": [vp, vp, i, l, i, vp, i, l, vp, vp, vp, i, i, vp],
         "lpmx_set_io_sharded": [vp, i],
-        "lpmx_local_rows": [vp, i, i, vp, vp, vp, vp],
+        "lpmx_local_targets": [vp, i, i, vp, vp, vp, vp],
         "lpmx_bve_solve": [vp, vp, i, l, i, vp, i, l, vp, vp, vp, i, i, vp, vp],
         "lpmx_ic2d_sums": [vp, vp, i, l, i, vp, i, l, vp, vp, vp, i, d, i, vp, vp],
         "lpmx_swe_sphere_sums": [vp, vp, i, l, i, vp, i, l, vp, vp, vp, vp, i, d, i, i, vp, vp, vp],

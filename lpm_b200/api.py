@@ -403,11 +403,14 @@ class Engine:
         """Host arrays of the BVE / IC2D solvers and in-place steppers carry only this rank's rows (lpmx_set_io_sharded)."""
         self._check(self._L.lpmx_set_io_sharded(self._h, int(bool(on))), "lpmx_set_io_sharded")
 
-    def local_rows(self, n_first, n_second):
-        """((first0, first1), (second0, second1)): the vertex and face rows this rank owns."""
-        a = [ctypes.c_int() for _ in range(4)]
-        self._check(self._L.lpmx_local_rows(self._h, n_first, n_second, *[ctypes.byref(x) for x in a]), "lpmx_local_rows")
-        return (a[0].value, a[1].value), (a[2].value, a[3].value)
+    def local_targets(self, n_first, n_second, mask_second):
+        """(A, B): this rank's leaf faces and its non-source targets, as indices into [vertices | faces] (lpmx_local_targets)."""
+        mask = np.ascontiguousarray(mask_second, dtype=np.uint8)
+        idx = np.zeros(n_first + n_second, dtype=np.int32)
+        na, nb = ctypes.c_int(), ctypes.c_int()
+        self._check(self._L.lpmx_local_targets(self._h, n_first, n_second, _ptr(mask), _ptr(idx), ctypes.byref(na),
+                                               ctypes.byref(nb)), "lpmx_local_targets")
+        return idx[:na.value].copy(), idx[na.value:na.value + nb.value].copy()
 
     def bve_solve(self, tgt_xyz, src_xyz, src_vort, src_area, src_mask, collocated=False, layout=LAYOUT_RIGHT,
                   n_tgt=None, n_src=None, tgt_ld=0, src_ld=0):

@@ -6,6 +6,8 @@
 #include <cstring>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "lpmx_internal.h"
 
@@ -249,10 +251,16 @@ int lpmx_profile_read(lpmx_handle_t h, long* n_launches, double* total_ms, doubl
   if (!h) return LPMX_ERR_INVALID;
   LPMX_CUDA(h, cudaStreamSynchronize(h->stream));
   double ms = 0;
+  const bool dump = getenv("LPMX_PROFILE_DUMP") != nullptr;  // per-launch durations and the gaps between them, to stderr
   for (size_t i = 0; i < h->prof_used; ++i) {
     float t = 0;
     LPMX_CUDA(h, cudaEventElapsedTime(&t, h->prof_events[i].first, h->prof_events[i].second));
     ms += t;
+    if (dump) {
+      float gap = 0;
+      if (i > 0) cudaEventElapsedTime(&gap, h->prof_events[i - 1].second, h->prof_events[i].first);
+      fprintf(stderr, "[lpmx profile] rank %d launch %zu: %.3f ms, gap before %.3f ms\n", h->rank, i, t, gap);
+    }
   }
   if (n_launches) *n_launches = (long)h->prof_used;
   if (total_ms) *total_ms = ms;
@@ -272,16 +280,6 @@ int lpmx_set_partition(lpmx_handle_t h, int rank, int world) {
 int lpmx_set_io_sharded(lpmx_handle_t h, int on) {
   if (!h) return LPMX_ERR_INVALID;
   h->io_sharded = on != 0;
-  return LPMX_OK;
-}
-
-int lpmx_local_rows(lpmx_handle_t h, int n_first, int n_second, int* first0, int* first1, int* second0, int* second1) {
-  if (!h || n_first < 0 || n_second < 0) return LPMX_ERR_INVALID;
-  const long r = h->rank, w = h->world;
-  if (first0) *first0 = (int)((r * n_first) / w);
-  if (first1) *first1 = (int)(((r + 1) * n_first) / w);
-  if (second0) *second0 = (int)((r * n_second) / w);
-  if (second1) *second1 = (int)(((r + 1) * n_second) / w);
   return LPMX_OK;
 }
 

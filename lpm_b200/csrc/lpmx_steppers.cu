@@ -16,10 +16,13 @@
 // leaf faces (the sources it contributes), list B = its vertices and divided faces (never sources).  A goes first; the packed
 // records its stage kernel writes are exchanged (one kernel over NVLink peer memory on the copy stream when the peer path is on,
 // else the NCCL all-gather in line) WHILE the pair sum of list B runs, so the exchange is off the critical path.
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
 #include <new>
+#include <utility>
+#include <vector>
 
 #include "lpmx_finalize.cuh"
 #include "lpmx_internal.h"
@@ -32,14 +35,17 @@ namespace lpmx {
 struct SolverState {
   lpmx_handle_t h = nullptr;
   int nv = 0, nf = 0, nt = 0, n_leaf = 0;
-  // this rank's targets: vertex rows [v0, v1) and face rows [f0, f1).  world == 1: one "list" B = everything (gid[1] null: the
-  // identity), list A empty.  world > 1: gid[0] = own leaf faces, gid[1] = own vertices + own divided faces (global indices
-  // into the concatenated SoA arrays).
-  int v0 = 0, v1 = 0, f0 = 0, f1 = 0;
+  // Target lists.  world == 1: one "list" B = everything (gid[1] null: the identity), list A empty.  world > 1: the leaf faces
+  // (in index order) and the non-sources (vertices, then divided faces in index order) are each cut into `world` equal
+  // slices; rank r owns slice r of both: list A = gid[0] = its leaf faces, list B = gid[1] = its non-sources (global indices
+  // into the concatenated SoA arrays).  `perm` (device, nt ints) is the concatenation [A_0, B_0, A_1, B_1, ...] of all
+  // ranks' lists, p_off[r] the start of rank r's segment in it: the row gather of get_state runs in that order.
   bool split = false;
   int* gid[2] = {nullptr, nullptr};
   int n_part[2] = {0, 0};
-  int* gid_store = nullptr;  // nt ints in the slab
+  int* perm = nullptr;  // nt ints in the slab
+  std::vector<long> p_off;
+  std::vector<std::pair<int, int>> own_v_runs, own_f_runs;  // this rank's rows as [first, last) runs (sharded host I/O)
   bool has_state = false;
   void* slab = nullptr;
   double *X = nullptr, *U = nullptr, *Xw = nullptr, *Z = nullptr, *Zw = nullptr, *Psi = nullptr;
@@ -52,8 +58,7 @@ struct SolverState {
   int cur = 0;
   int n_src_pad = 0;
   double* partials[2] = {nullptr, nullptr};  // per list
-  std::vector<long> v_off, f_off;  // world+1 row offsets of the vertex / face ranges (f_off relative to the face list)
-  std::vector<long> packed_off;    // world+1 offsets into packed (in doubles)
+  std::vector<long> packed_off;    // world+1 offsets into packed (in doubles): rank r's leaves are [r L / W, (r+1) L / W)
   int n_local() const { return n_part[0] + n_part[1]; }
   Vec3View view(double* base) const {
     Vec3View v;
@@ -96,7 +101,7 @@ static int solver_alloc(SolverState* s, lpmx_handle_t h, int nv, int nf, int n_k
   int* ip = (int*)p;
   s->leaf_idx = ip, ip += nf + 1;
   s->self_idx = ip, ip += nt + 1;
-  s->gid_store = ip, ip += nt + 1;
+  s->perm = ip, ip += nt + 1;
   s->mask = (unsigned char*)ip;
   return LPMX_OK;
 }
@@ -370,16 +375,34 @@ static int exchange_packed_end(SolverState* s, bool async) {
   return LPMX_OK;
 }
 
-// gather full-length SoA rows (n_rows rows of length nt) so every rank holds every target: the vertex ranges, then the face ranges
+// gather full-length SoA rows (n_rows rows of length nt) so every rank holds every target: each rank's rows are an index list,
+// so the rows are gathered into list order (perm), all-gathered there (contiguous per rank) and scattered back
+__global__ void perm_gather_kernel(const int* perm, long j0, long j1, const double* row, double* buf) {
+  const long j = j0 + blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (j < j1) buf[j] = row[perm[j]];
+}
+__global__ void perm_scatter_kernel(const int* perm, long n, long skip0, long skip1, const double* buf, double* row) {
+  const long j = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (j < n && (j < skip0 || j >= skip1)) row[perm[j]] = buf[j];
+}
 static int exchange_rows(SolverState* s, double* base, int n_rows) {
-  if (s->h->world == 1) return LPMX_OK;
-  std::vector<long> off(s->h->world + 1);
+  lpmx_handle_t h = s->h;
+  if (h->world == 1 || s->nt == 0) return LPMX_OK;
+  void* bufv = nullptr;
+  LPMX_TRY(dev_buffer(h, "xrows", sizeof(double) * (size_t)s->nt, &bufv));
+  double* buf = (double*)bufv;
+  const long j0 = s->p_off[h->rank], j1 = s->p_off[h->rank + 1];
+  const int threads = 256;
   for (int r = 0; r < n_rows; ++r) {
-    if (s->nv > 0) LPMX_TRY(comm_allgatherv(s->h, base + (long)r * s->nt, s->v_off.data()));
-    if (s->nf > 0) {
-      for (int q = 0; q <= s->h->world; ++q) off[q] = s->nv + s->f_off[q];
-      LPMX_TRY(comm_allgatherv(s->h, base + (long)r * s->nt, off.data()));
+    double* row = base + (long)r * s->nt;
+    if (j1 > j0) {
+      perm_gather_kernel<<<(int)((j1 - j0 + threads - 1) / threads), threads, 0, h->stream>>>(s->perm, j0, j1, row, buf);
+      ++h->launches;
     }
+    LPMX_TRY(comm_allgatherv(h, buf, s->p_off.data()));
+    perm_scatter_kernel<<<(s->nt + threads - 1) / threads, threads, 0, h->stream>>>(s->perm, s->nt, j0, j1, buf, row);
+    ++h->launches;
+    LPMX_CUDA(h, cudaGetLastError());
   }
   return LPMX_OK;
 }
@@ -403,10 +426,49 @@ static int copy_rows(lpmx_handle_t h, void* dev, const void* user, int layout, l
   return LPMX_OK;
 }
 
-// this rank's rows of the vertex list and of the face list
-static void local_rows(const SolverState* s, int rank, int world, long* v0, long* v1, long* f0, long* f1) {
-  *v0 = ((long)rank * s->nv) / world, *v1 = ((long)(rank + 1) * s->nv) / world;
-  *f0 = ((long)rank * s->nf) / world, *f1 = ((long)(rank + 1) * s->nf) / world;
+static int copy_runs(lpmx_handle_t h, void* dev, const void* user, int layout, long ld, const std::vector<std::pair<int, int>>& runs,
+                     int ncomp, bool to_device) {
+  for (const auto& r : runs) LPMX_TRY(copy_rows(h, dev, user, layout, ld, r.first, r.second, ncomp, to_device));
+  return LPMX_OK;
+}
+
+// The class-balanced target lists of every rank (see SolverState): perm = [A_0, B_0, A_1, B_1, ...], p_off, and for rank `rank`
+// the list sizes and its rows as runs.  `leaf(f)` tells whether face f is a leaf.  Mirrored by lpm_b200/partition.py.
+template <class LeafFn>
+static void build_target_lists(int nv, int nf, int n_leaf, int world, int rank, LeafFn leaf, std::vector<int>* perm,
+                               std::vector<long>* p_off, int* n_a, int* n_b, std::vector<std::pair<int, int>>* v_runs,
+                               std::vector<std::pair<int, int>>* f_runs) {
+  std::vector<int> lf, ns;  // leaf faces; non-sources (global indices)
+  lf.reserve(n_leaf), ns.reserve((size_t)nv + nf - n_leaf);
+  for (int v = 0; v < nv; ++v) ns.push_back(v);
+  for (int f = 0; f < nf; ++f) (leaf(f) ? lf : ns).push_back(nv + f);
+  perm->clear(), perm->reserve((size_t)nv + nf);
+  p_off->assign(world + 1, 0);
+  std::vector<int> own;
+  for (int r = 0; r < world; ++r) {
+    (*p_off)[r] = (long)perm->size();
+    const size_t a0 = (size_t)r * lf.size() / world, a1 = (size_t)(r + 1) * lf.size() / world;
+    const size_t b0 = (size_t)r * ns.size() / world, b1 = (size_t)(r + 1) * ns.size() / world;
+    perm->insert(perm->end(), lf.begin() + a0, lf.begin() + a1);
+    perm->insert(perm->end(), ns.begin() + b0, ns.begin() + b1);
+    if (r == rank) {
+      *n_a = (int)(a1 - a0), *n_b = (int)(b1 - b0);
+      own.assign(perm->end() - (*n_a + *n_b), perm->end());
+    }
+  }
+  (*p_off)[world] = (long)perm->size();
+  std::sort(own.begin(), own.end());
+  v_runs->clear(), f_runs->clear();
+  for (size_t i = 0; i < own.size();) {
+    size_t j = i + 1;
+    const bool vert = own[i] < nv;
+    while (j < own.size() && own[j] == own[j - 1] + 1 && (own[j] < nv) == vert) ++j;
+    if (vert)
+      v_runs->push_back({own[i], own[j - 1] + 1});
+    else
+      f_runs->push_back({own[i] - nv, own[j - 1] + 1 - nv});
+    i = j;
+  }
 }
 
 static int solver_set_state(SolverState* s, const double* vx, const double* vz, const double* vu, const double* fx,
@@ -423,33 +485,63 @@ static int solver_set_state(SolverState* s, const double* vx, const double* vz, 
     return (layout == LPMX_LAYOUT_LEFT ? (size_t)(2 * ld + n) : (size_t)3 * n) * sizeof(double);
   };
   const void *dvx, *dvz, *dvu, *dfx, *dfz, *dfu, *dfa, *dfm;
-  // sharded host I/O (lpmx_set_io_sharded, world > 1): only this rank's target rows are read from the host arrays -- they are
-  // all it needs, since every rank packs the source records of its OWN leaf faces and the exchange distributes them.  The
-  // other rows of the device-side state are left as they are and never read.  Area and mask are read in full (the leaf scan
-  // and the conserved totals run over all faces).
-  const bool shard_in = h->io_sharded && h->world > 1;
-  auto in_rows = [&](const char* name, const double* user, size_t bytes, long ld, long r0, long r1, int ncomp,
-                     const void** dev) -> int {
-    if (!shard_in || !user || is_device_pointer(user)) return stage_in(h, name, user, bytes, dev);
-    void* d = nullptr;
-    LPMX_TRY(dev_buffer(h, name, bytes, &d));
-    *dev = d;
-    return copy_rows(h, d, user, layout, ld, r0, r1, ncomp, true);
-  };
-  long v0, v1, f0, f1;
-  local_rows(s, h->rank, h->world, &v0, &v1, &f0, &f1);
-  LPMX_TRY(in_rows("st_vx", vx, vb(vld, s->nv), vld, v0, v1, 3, &dvx));
-  LPMX_TRY(in_rows("st_vz", vz, sizeof(double) * s->nv, 0, v0, v1, 1, &dvz));
-  LPMX_TRY(in_rows("st_vu", vu, vb(vld, s->nv), vld, v0, v1, 3, &dvu));
-  LPMX_TRY(in_rows("st_fx", fx, vb(fld, s->nf), fld, f0, f1, 3, &dfx));
-  LPMX_TRY(in_rows("st_fz", fz, sizeof(double) * s->nf, 0, f0, f1, 1, &dfz));
-  LPMX_TRY(in_rows("st_fu", fu, vb(fld, s->nf), fld, f0, f1, 3, &dfu));
+  // 1. area and mask (always in full: the leaf scan, the target lists and the conserved totals run over all faces)
   LPMX_TRY(stage_in(h, "st_fa", fa, sizeof(double) * s->nf, &dfa));
   LPMX_TRY(stage_in(h, "st_fm", fm, (size_t)s->nf, &dfm));
   if (s->nf > 0) {
     LPMX_CUDA(h, cudaMemcpyAsync(s->area, dfa, sizeof(double) * s->nf, cudaMemcpyDeviceToDevice, h->stream));
     LPMX_CUDA(h, cudaMemcpyAsync(s->mask, dfm, (size_t)s->nf, cudaMemcpyDeviceToDevice, h->stream));
   }
+  LPMX_TRY(scan_leaves(h, s->mask, s->nf, s->leaf_idx, &s->n_leaf));
+  s->n_src_pad = round_up_chunk(s->n_leaf);
+
+  // 2. who owns what.  LPMX_FORCE_SPLIT=1: evaluate the two index lists on a single GPU as well (test hook: the list path of
+  // the kernels and the A-then-B evaluation can then be checked on a one-GPU box; there is nothing to exchange)
+  const int W = h->world;
+  const char* fs = getenv("LPMX_FORCE_SPLIT");
+  s->split = W > 1 || (fs && fs[0] == '1');
+  s->packed_off.assign(W + 1, 0);
+  for (int r = 0; r <= W; ++r) s->packed_off[r] = kBveRec * (((long)r * s->n_leaf) / W);
+  s->own_v_runs.clear(), s->own_f_runs.clear();
+  if (!s->split) {
+    s->gid[0] = s->gid[1] = nullptr;
+    s->n_part[0] = 0, s->n_part[1] = s->nt;
+    s->p_off.assign(2, 0);
+    s->p_off[1] = s->nt;
+  } else {
+    std::vector<int> leaf_host(s->nf + 1, 0);
+    if (s->nf > 0)
+      LPMX_CUDA(h, cudaMemcpyAsync(leaf_host.data(), s->leaf_idx, sizeof(int) * s->nf, cudaMemcpyDeviceToHost, h->stream));
+    LPMX_CUDA(h, cudaStreamSynchronize(h->stream));
+    leaf_host[s->nf] = s->n_leaf;
+    std::vector<int> perm;
+    build_target_lists(s->nv, s->nf, s->n_leaf, W, h->rank, [&](int f) { return leaf_host[f + 1] > leaf_host[f]; }, &perm,
+                       &s->p_off, &s->n_part[0], &s->n_part[1], &s->own_v_runs, &s->own_f_runs);
+    if (!perm.empty())
+      LPMX_CUDA(h, cudaMemcpyAsync(s->perm, perm.data(), sizeof(int) * perm.size(), cudaMemcpyHostToDevice, h->stream));
+    LPMX_CUDA(h, cudaStreamSynchronize(h->stream));  // perm goes out of scope
+    s->gid[0] = s->perm + s->p_off[h->rank];
+    s->gid[1] = s->gid[0] + s->n_part[0];
+  }
+
+  // 3. the state rows.  Sharded host I/O (lpmx_set_io_sharded, world > 1): only this rank's rows are read from the host arrays --
+  // they are all it needs, since every rank packs the source records of its OWN leaf faces and the exchange distributes them.
+  // The other rows of the device-side state are left as they are and never read.
+  const bool shard_in = h->io_sharded && W > 1;
+  auto in_rows = [&](const char* name, const double* user, size_t bytes, long ld, const std::vector<std::pair<int, int>>& runs,
+                     int ncomp, const void** dev) -> int {
+    if (!shard_in || !user || is_device_pointer(user)) return stage_in(h, name, user, bytes, dev);
+    void* d = nullptr;
+    LPMX_TRY(dev_buffer(h, name, bytes, &d));
+    *dev = d;
+    return copy_runs(h, d, user, layout, ld, runs, ncomp, true);
+  };
+  LPMX_TRY(in_rows("st_vx", vx, vb(vld, s->nv), vld, s->own_v_runs, 3, &dvx));
+  LPMX_TRY(in_rows("st_vz", vz, sizeof(double) * s->nv, 0, s->own_v_runs, 1, &dvz));
+  LPMX_TRY(in_rows("st_vu", vu, vb(vld, s->nv), vld, s->own_v_runs, 3, &dvu));
+  LPMX_TRY(in_rows("st_fx", fx, vb(fld, s->nf), fld, s->own_f_runs, 3, &dfx));
+  LPMX_TRY(in_rows("st_fz", fz, sizeof(double) * s->nf, 0, s->own_f_runs, 1, &dfz));
+  LPMX_TRY(in_rows("st_fu", fu, vb(fld, s->nf), fld, s->own_f_runs, 3, &dfu));
   const int threads = 256;
   const int blocks = (s->nt + threads - 1) / threads;
   if (s->nt > 0) {
@@ -459,63 +551,14 @@ static int solver_set_state(SolverState* s, const double* vx, const double* vz, 
         make_view((const double*)dfu, layout, fld), s->X, s->Z, s->U);
     ++h->launches;
     LPMX_CUDA(h, cudaGetLastError());
-  }
-  LPMX_TRY(scan_leaves(h, s->mask, s->nf, s->leaf_idx, &s->n_leaf));
-  if (s->nt > 0) {
     self_idx_kernel<<<blocks, threads, 0, h->stream>>>(s->nv, s->nf, s->mask, s->leaf_idx, skip_self, s->self_idx);
     ++h->launches;
     LPMX_CUDA(h, cudaGetLastError());
   }
-  s->n_src_pad = round_up_chunk(s->n_leaf);
   // zero both packed buffers once: the padding records must stay {0,0,0,0}
   const size_t pk_bytes = sizeof(double) * kBveRec * (size_t)(round_up_chunk(s->nf) + kChunk);
   LPMX_CUDA(h, cudaMemsetAsync(s->packed[0], 0, pk_bytes, h->stream));
   LPMX_CUDA(h, cudaMemsetAsync(s->packed[1], 0, pk_bytes, h->stream));
-  // shard offsets: each rank owns rows [v_off[r], v_off[r+1]) of the vertices and [f_off[r], f_off[r+1]) of the faces, and with
-  // them the leaf range [leaf_idx[f_off[r]], leaf_idx[f_off[r+1]]) of the packed array
-  const int W = h->world;
-  s->v_off.assign(W + 1, 0);
-  s->f_off.assign(W + 1, 0);
-  s->packed_off.assign(W + 1, 0);
-  // LPMX_FORCE_SPLIT=1: evaluate the two index lists on a single GPU as well (test hook: the list path of the kernels and the
-  // A-then-B evaluation can then be checked on a one-GPU box; there is nothing to exchange)
-  const char* fs = getenv("LPMX_FORCE_SPLIT");
-  const bool want_split = W > 1 || (fs && fs[0] == '1');
-  std::vector<int> leaf_host;
-  if (want_split && s->nf > 0) {
-    leaf_host.resize(s->nf);
-    LPMX_CUDA(h, cudaMemcpyAsync(leaf_host.data(), s->leaf_idx, sizeof(int) * s->nf, cudaMemcpyDeviceToHost, h->stream));
-    LPMX_CUDA(h, cudaStreamSynchronize(h->stream));
-  }
-  auto leaf_at = [&](long f) -> long { return f >= s->nf ? s->n_leaf : (want_split ? leaf_host[f] : 0); };
-  for (int r = 0; r <= W; ++r) {
-    s->v_off[r] = ((long)r * s->nv) / W;
-    s->f_off[r] = ((long)r * s->nf) / W;
-    s->packed_off[r] = kBveRec * (r == W ? (long)s->n_leaf : leaf_at(s->f_off[r]));
-  }
-  s->v0 = (int)s->v_off[h->rank], s->v1 = (int)s->v_off[h->rank + 1];
-  s->f0 = (int)s->f_off[h->rank], s->f1 = (int)s->f_off[h->rank + 1];
-  s->split = want_split;
-  if (!s->split) {
-    s->gid[0] = s->gid[1] = nullptr;
-    s->n_part[0] = 0, s->n_part[1] = s->nt;
-  } else {
-    // list A: own leaf faces; list B: own vertices, then own divided faces
-    std::vector<int> la, lb;
-    la.reserve(s->f1 - s->f0), lb.reserve((s->v1 - s->v0) + (s->f1 - s->f0));
-    for (int v = s->v0; v < s->v1; ++v) lb.push_back(v);
-    for (long f = s->f0; f < s->f1; ++f) {
-      const bool leaf = leaf_at(f + 1) > leaf_at(f);
-      (leaf ? la : lb).push_back(s->nv + (int)f);
-    }
-    s->n_part[0] = (int)la.size(), s->n_part[1] = (int)lb.size();
-    s->gid[0] = s->gid_store, s->gid[1] = s->gid_store + la.size();
-    if (!la.empty())
-      LPMX_CUDA(h, cudaMemcpyAsync(s->gid[0], la.data(), sizeof(int) * la.size(), cudaMemcpyHostToDevice, h->stream));
-    if (!lb.empty())
-      LPMX_CUDA(h, cudaMemcpyAsync(s->gid[1], lb.data(), sizeof(int) * lb.size(), cudaMemcpyHostToDevice, h->stream));
-    LPMX_CUDA(h, cudaStreamSynchronize(h->stream));  // la / lb go out of scope
-  }
   s->has_state = true;
   if (!is_device_pointer(vx) || !is_device_pointer(fx)) LPMX_CUDA(h, cudaStreamSynchronize(h->stream));
   return LPMX_OK;
@@ -535,8 +578,6 @@ static int solver_get_state(SolverState* s, double* vx, double* vz, double* vu, 
     LPMX_TRY(exchange_rows(s, s->Z, 1));
     if (vpsi || fpsi) LPMX_TRY(exchange_rows(s, s->Psi, 1));
   }
-  long v0, v1, f0, f1;
-  local_rows(s, h->rank, h->world, &v0, &v1, &f0, &f1);
   auto vb = [&](long ld, int n) {
     return (layout == LPMX_LAYOUT_LEFT ? (size_t)(2 * ld + n) : (size_t)3 * n) * sizeof(double);
   };
@@ -561,19 +602,19 @@ static int solver_get_state(SolverState* s, double* vx, double* vz, double* vu, 
     LPMX_CUDA(h, cudaGetLastError());
   }
   bool any_host = false;
-  auto out = [&](void* user, void* dev, size_t bytes, long ld, long r0, long r1, int ncomp) -> int {
+  auto out = [&](void* user, void* dev, size_t bytes, long ld, const std::vector<std::pair<int, int>>& runs, int ncomp) -> int {
     if (user && user != dev) any_host = true;
-    if (shard_out && user && user != dev) return copy_rows(h, dev, user, layout, ld, r0, r1, ncomp, false);
+    if (shard_out && user && user != dev) return copy_runs(h, dev, user, layout, ld, runs, ncomp, false);
     return stage_out_end(h, user, dev, bytes);
   };
-  LPMX_TRY(out(vx, dvx, vb(vld, s->nv), vld, v0, v1, 3));
-  LPMX_TRY(out(vz, dvz, sizeof(double) * s->nv, 0, v0, v1, 1));
-  LPMX_TRY(out(vu, dvu, vb(vld, s->nv), vld, v0, v1, 3));
-  LPMX_TRY(out(vpsi, dvp, sizeof(double) * s->nv, 0, v0, v1, 1));
-  LPMX_TRY(out(fx, dfx, vb(fld, s->nf), fld, f0, f1, 3));
-  LPMX_TRY(out(fz, dfz, sizeof(double) * s->nf, 0, f0, f1, 1));
-  LPMX_TRY(out(fu, dfu, vb(fld, s->nf), fld, f0, f1, 3));
-  LPMX_TRY(out(fpsi, dfp, sizeof(double) * s->nf, 0, f0, f1, 1));
+  LPMX_TRY(out(vx, dvx, vb(vld, s->nv), vld, s->own_v_runs, 3));
+  LPMX_TRY(out(vz, dvz, sizeof(double) * s->nv, 0, s->own_v_runs, 1));
+  LPMX_TRY(out(vu, dvu, vb(vld, s->nv), vld, s->own_v_runs, 3));
+  LPMX_TRY(out(vpsi, dvp, sizeof(double) * s->nv, 0, s->own_v_runs, 1));
+  LPMX_TRY(out(fx, dfx, vb(fld, s->nf), fld, s->own_f_runs, 3));
+  LPMX_TRY(out(fz, dfz, sizeof(double) * s->nf, 0, s->own_f_runs, 1));
+  LPMX_TRY(out(fu, dfu, vb(fld, s->nf), fld, s->own_f_runs, 3));
+  LPMX_TRY(out(fpsi, dfp, sizeof(double) * s->nf, 0, s->own_f_runs, 1));
   if (any_host) LPMX_CUDA(h, cudaStreamSynchronize(h->stream));
   return LPMX_OK;
 }
@@ -679,6 +720,23 @@ extern "C" {
 // ------------------------------------------------------------------------------------------------
 // BVE
 // ------------------------------------------------------------------------------------------------
+int lpmx_local_targets(lpmx_handle_t h, int n_first, int n_second, const unsigned char* mask_second, int* idx, int* n_sources,
+                       int* n_other) {
+  if (!h || n_first < 0 || n_second < 0 || (n_second > 0 && !mask_second) || !idx) return LPMX_ERR_INVALID;
+  int n_leaf = 0;
+  for (int f = 0; f < n_second; ++f) n_leaf += mask_second[f] ? 0 : 1;
+  std::vector<int> perm;
+  std::vector<long> p_off;
+  std::vector<std::pair<int, int>> vr, fr;
+  int na = 0, nb = 0;
+  build_target_lists(n_first, n_second, n_leaf, h->world, h->rank, [&](int f) { return mask_second[f] == 0; }, &perm, &p_off, &na,
+                     &nb, &vr, &fr);
+  for (int k = 0; k < na + nb; ++k) idx[k] = perm[p_off[h->rank] + k];
+  if (n_sources) *n_sources = na;
+  if (n_other) *n_other = nb;
+  return LPMX_OK;
+}
+
 int lpmx_bve_solver_create(lpmx_handle_t h, int n_verts, int n_faces, lpmx_bve_solver_t* out) {
   if (!h || !out) return LPMX_ERR_INVALID;
   lpmx_bve_solver_s* s = new (std::nothrow) lpmx_bve_solver_s;

@@ -66,9 +66,10 @@ def main():
     ref = [m.vert_xyz.copy(), vz.copy(), oracle.bve_velocity(m.vert_xyz, *a), m.face_xyz.copy(), fz.copy(),
            oracle.bve_velocity(None, *a, collocated=True)]
     got = [x.copy() for x in ref]
-    (v0, v1), (f0, f1) = e.local_rows(m.n_verts, m.n_faces)
-    own = [np.zeros(m.n_verts, bool), np.zeros(m.n_faces, bool)]
-    own[0][v0:v1], own[1][f0:f1] = True, True
+    la, lb = e.local_targets(m.n_verts, m.n_faces, m.face_mask)
+    own_all = np.zeros(m.n_verts + m.n_faces, bool)
+    own_all[la], own_all[lb] = True, True
+    own = [own_all[:m.n_verts], own_all[m.n_verts:]]
     for k, arr in enumerate(got):
         arr[~own[k // 3]] = np.nan
     e.set_io_sharded(True)
@@ -81,8 +82,8 @@ def main():
         ok &= bool(np.isnan(g[~o]).all())
         if o.any():
             ok &= field_rel_err(g[o], r[o]) <= 1e-10 * max(1.0, np.abs(r).max() / max(np.abs(r[o]).max(), 1e-300))
-    print(f"[rank {rank}/{world}] sharded host I/O (rows {v0}:{v1} of the vertices, {f0}:{f1} of the faces): {'ok' if ok else 'FAILED'}",
-          flush=True)
+    print(f"[rank {rank}/{world}] sharded host I/O ({len(la)} leaf faces + {len(lb)} other targets of {m.n_verts + m.n_faces}): "
+          f"{'ok' if ok else 'FAILED'}", flush=True)
     if not ok:
         worst = np.inf
     # SWE RK2 with the Laplacian provider (the provider sees the gathered arrays on every rank)

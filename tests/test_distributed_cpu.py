@@ -21,22 +21,46 @@ def test_offsets_cover_without_overlap():
         assert max(b - a for a, b in zip(off, off[1:])) - min(b - a for a, b in zip(off, off[1:])) <= 1
 
 
-def test_leaf_offsets_and_target_lists_follow_the_row_ranges(meshes):
-    m = meshes("icos", 3)
-    for w in (1, 2, 3, 8):
-        l = partition.leaf_offsets(m.face_mask, w)
-        assert l[0] == 0 and l[-1] == m.n_face_leaves
-        seen = []
-        for r in range(w):
-            (v0, v1), (f0, f1) = partition.local_rows(m.n_verts, m.n_faces, r, w)
-            assert l[r + 1] - l[r] == int((m.face_mask[f0:f1] == 0).sum())
-            a, b = partition.target_lists(m.n_verts, m.face_mask, r, w)
-            assert len(a) == l[r + 1] - l[r] and len(a) + len(b) == (v1 - v0) + (f1 - f0)
-            assert (m.face_mask[a - m.n_verts] == 0).all()                       # A: leaf faces only (the sources)
-            assert ((b < m.n_verts) | (m.face_mask[np.maximum(b - m.n_verts, 0)] == 1)).all()  # B: never sources
-            seen += [a, b]
-        assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(m.n_verts + m.n_faces))  # a partition of all targets
+def test_target_lists_are_class_balanced_partitions(meshes):
+    from lpm_b200.api import PolyMesh2d
+    amr = PolyMesh2d("cubed", 2, amr_buffer=2, amr_limit=2)
+    rng = np.random.default_rng(3)
+    for _ in range(2):  # an adaptively refined mesh: leaves and divided faces interleave in face order
+        amr.divide_flagged_faces(((rng.random(amr.n_faces) < 0.4) & (amr.face_mask == 0)).astype(np.uint8))
+    for m in (meshes("icos", 3), meshes("cubed", 3), amr):
+        for w in (1, 2, 3, 8):
+            l = partition.leaf_offsets(m.face_mask, w)
+            assert l[0] == 0 and l[-1] == m.n_face_leaves
+            seen, na, nb = [], [], []
+            for r in range(w):
+                a, b = partition.target_lists(m.n_verts, m.face_mask, r, w)
+                assert len(a) == l[r + 1] - l[r]
+                assert (m.face_mask[a - m.n_verts] == 0).all()                       # A: leaf faces only (the sources)
+                assert ((b < m.n_verts) | (m.face_mask[np.maximum(b - m.n_verts, 0)] == 1)).all()  # B: never sources
+                seen += [a, b]
+                na.append(len(a)), nb.append(len(b))
+            assert max(na) - min(na) <= 1 and max(nb) - min(nb) <= 1                 # both classes balanced over the ranks
+            assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(m.n_verts + m.n_faces))  # a partition of all targets
     assert partition.interactions_per_eval(2562, 6820, 5120) == (2562 + 6820) * 5120 - 5120
+
+
+@pytest.mark.gpu
+def test_engine_target_lists_equal_the_mirror(meshes):
+    """lpmx_local_targets (host code of the engine, no device needed) against lpm_b200/partition.py."""
+    m = meshes("icos", 3)
+    mask = np.ascontiguousarray(m.face_mask, dtype=np.uint8)
+    from lpm_b200.api import Engine
+    e = Engine(0)
+    try:
+        for w in (1, 3, 8):
+            for r in range(w):
+                e.set_partition(r, w)
+                a, b = e.local_targets(m.n_verts, m.n_faces, mask)
+                pa, pb = partition.target_lists(m.n_verts, mask, r, w)
+                assert np.array_equal(a, pa) and np.array_equal(b, pb)
+        e.set_partition(0, 1)
+    finally:
+        e.close()
 
 
 def _free_port():
@@ -60,7 +84,6 @@ def _worker(rank, world, port, q):
         m = PolyMesh2d("cubed", 3)
         fz = gallery.SolidBodyRotation()(m.face_xyz)
         nv, nf = m.n_verts, m.n_faces
-        (v0, v1), (f0, f1) = partition.local_rows(nv, nf, rank, world)
         la, lb = partition.target_lists(nv, m.face_mask, rank, world)
         # this rank's targets: list A then list B; faces need the collocated (skip-self) rule
         full_v = oracle.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask)
@@ -73,13 +96,16 @@ def _worker(rank, world, port, q):
             if g >= nv:
                 mask[g - nv] = 1  # skip the self pair by index
             gathered[g] = torch.from_numpy(oracle.bve_velocity(xyz[g:g + 1], m.face_xyz, fz, m.face_area, mask)[0])
-        # in-place allgatherv of the vertex rows, then of the face rows: every rank broadcasts its segments
-        voff, foff = partition.target_offsets(nv, world), partition.target_offsets(nf, world)
+        # the row gather in list order: rows -> perm order, every rank broadcasts its segment, scatter back
+        lists = [np.concatenate(partition.target_lists(nv, m.face_mask, r, world)) for r in range(world)]
+        perm = np.concatenate(lists)
+        off = np.concatenate([[0], np.cumsum([len(x) for x in lists])])
+        buf = gathered[torch.from_numpy(perm)].contiguous()
         for r in range(world):
-            for lo_, hi_ in ((voff[r], voff[r + 1]), (nv + foff[r], nv + foff[r + 1])):
-                seg = gathered[lo_:hi_].contiguous()
-                dist.broadcast(seg, src=r)
-                gathered[lo_:hi_] = seg
+            seg = buf[off[r]:off[r + 1]].contiguous()
+            dist.broadcast(seg, src=r)
+            buf[off[r]:off[r + 1]] = seg
+        gathered[torch.from_numpy(perm)] = buf
         ok_sum = bool(np.array_equal(gathered.numpy(), full))
         # leaf ranges: the packed records this rank would own
         lo = partition.leaf_offsets(m.face_mask, world)
