@@ -20,6 +20,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <new>
 #include <utility>
 #include <vector>
@@ -46,6 +47,10 @@ struct SolverState {
   int* perm = nullptr;  // nt ints in the slab
   std::vector<long> p_off;
   std::vector<std::pair<int, int>> own_v_runs, own_f_runs;  // this rank's rows as [first, last) runs (sharded host I/O)
+  // the lists depend on the mask only: a set_state with the same (host) mask bytes, rank and world keeps them (the in-place
+  // steppers call set_state every step)
+  std::vector<unsigned char> list_mask;
+  int list_rank = -1, list_world = -1;
   bool has_state = false;
   void* slab = nullptr;
   double *X = nullptr, *U = nullptr, *Xw = nullptr, *Z = nullptr, *Zw = nullptr, *Psi = nullptr;
@@ -502,12 +507,15 @@ static int solver_set_state(SolverState* s, const double* vx, const double* vz, 
   s->split = W > 1 || (fs && fs[0] == '1');
   s->packed_off.assign(W + 1, 0);
   for (int r = 0; r <= W; ++r) s->packed_off[r] = kBveRec * (((long)r * s->n_leaf) / W);
-  s->own_v_runs.clear(), s->own_f_runs.clear();
   if (!s->split) {
+    s->own_v_runs.clear(), s->own_f_runs.clear();
     s->gid[0] = s->gid[1] = nullptr;
     s->n_part[0] = 0, s->n_part[1] = s->nt;
     s->p_off.assign(2, 0);
     s->p_off[1] = s->nt;
+  } else if (!is_device_pointer(fm) && s->list_rank == h->rank && s->list_world == W && (int)s->list_mask.size() == s->nf &&
+             (s->nf == 0 || memcmp(s->list_mask.data(), fm, (size_t)s->nf) == 0) && s->gid[0] != nullptr) {
+    // same mask as last time: perm, p_off, the list sizes and the runs are still valid
   } else {
     std::vector<int> leaf_host(s->nf + 1, 0);
     if (s->nf > 0)
@@ -522,6 +530,12 @@ static int solver_set_state(SolverState* s, const double* vx, const double* vz, 
     LPMX_CUDA(h, cudaStreamSynchronize(h->stream));  // perm goes out of scope
     s->gid[0] = s->perm + s->p_off[h->rank];
     s->gid[1] = s->gid[0] + s->n_part[0];
+    if (!is_device_pointer(fm)) {
+      s->list_mask.assign(fm, fm + s->nf);
+      s->list_rank = h->rank, s->list_world = W;
+    } else {
+      s->list_rank = -1;
+    }
   }
 
   // 3. the state rows.  Sharded host I/O (lpmx_set_io_sharded, world > 1): only this rank's rows are read from the host arrays --
