@@ -619,8 +619,9 @@ def main():
 
     peer_on, peer_slabs = eng.comm_peer_exchange_enabled()
     exchange = ("none (one GPU)" if world == 1 else
-                "one kernel storing each rank's records into the peers' slabs over NVLink (LPMX_PEER_EXCHANGE=1)"
-                if peer_on and peer_slabs else "grouped ncclBroadcast (default)")
+                "one kernel storing each rank's records into the peers' slabs over NVLink, on the copy stream beside the pair sum of the "
+                "rank's non-source targets (default for world <= 8)"
+                if peer_on and peer_slabs else "grouped ncclBroadcast in line (LPMX_PEER_EXCHANGE=0, or peer mapping unavailable)")
     if rank == 0:
         line = {
             "metric": "fp64_pair_interactions_per_s", "value": value, "unit": "interactions/s", "n_gpus": world,

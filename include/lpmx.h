@@ -202,9 +202,9 @@ int lpmx_comm_init(lpmx_handle_t h, const void* id128, int rank, int world);
  * process per GPU of ONE box).  Solver slabs created afterwards are mapped into every rank with CUDA IPC and the
  * per-stage all-gather of the packed source records becomes one kernel that stores each rank's segment straight
  * into its peers over NVLink (ready / done flags with system-scope release-acquire; every wait has a deadline,
- * LPMX_PEER_TIMEOUT_S, default 30 s, after which lpmx_sync returns LPMX_ERR_COMM instead of hanging).  Returns
+ * LPMX_PEER_TIMEOUT_S, default 600 s, after which lpmx_sync returns LPMX_ERR_COMM instead of hanging).  Returns
  * LPMX_ERR_UNSUPPORTED -- and leaves the NCCL exchange in place -- when the GPUs cannot map each other's memory.
- * Setting LPMX_PEER_EXCHANGE=1 in the environment makes lpmx_comm_init call this.  Results are bit-identical to the
+ * lpmx_comm_init calls this itself for world <= 8 unless LPMX_PEER_EXCHANGE=0 is set in the environment.  Results are bit-identical to the
  * NCCL exchange (the same records land in the same places).  The reference has no counterpart. */
 int lpmx_comm_enable_peer_exchange(lpmx_handle_t h, int enable);
 /* enabled: 1 when exchanges of mapped slabs take the peer path; n_regions: slabs currently mapped. */

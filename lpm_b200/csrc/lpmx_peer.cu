@@ -15,7 +15,8 @@
 //
 // The ready handshake makes the kernel as safe as the NCCL rendezvous for any call sequence (the same buffer
 // may be exchanged twice in a row); the ping-pong of the steppers is not relied upon.  Every spin has a
-// deadline (LPMX_PEER_TIMEOUT_S, default 30 s): on expiry the kernel records the peer in a host-mapped error
+// deadline (LPMX_PEER_TIMEOUT_S, default 600 s: it has to outlast any legitimate skew between ranks, e.g. one rank writing
+// output -- r2m: a 10 s deadline fired because rank 0 alone ran a host-side check between two exchanges): on expiry the kernel records the peer in a host-mapped error
 // word and returns, and the next lpmx_sync() / exchange reports LPMX_ERR_COMM -- it never hangs the GPU.
 //
 // Slabs are mapped with CUDA IPC (one process per GPU).  A mapping is validated by reading a magic word the
@@ -318,7 +319,7 @@ int peer_enable(lpmx_handle_t h, int enable) {
   h->peer = ps;
   const char* t = getenv("LPMX_PEER_TIMEOUT_S");
   const double ts = t ? atof(t) : 30.0;
-  ps->timeout_ns = (unsigned long long)((ts > 0 ? ts : 30.0) * 1e9);
+  ps->timeout_ns = (unsigned long long)((ts > 0 ? ts : 600.0) * 1e9);
   LPMX_CUDA(h, cudaHostAlloc((void**)&ps->host_err, sizeof(int), cudaHostAllocMapped));
   *ps->host_err = 0;
   LPMX_CUDA(h, cudaHostGetDevicePointer((void**)&ps->host_err_dev, ps->host_err, 0));

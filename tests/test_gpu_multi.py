@@ -36,7 +36,7 @@ def test_sharded_steppers_equal_oracle(world):
 
 @pytest.mark.gpu
 def test_peer_exchange_equals_nccl_exchange():
-    """lpmx_peer.cu (opt-in, LPMX_PEER_EXCHANGE=1): the one-kernel exchange over NVLink peer memory must leave the
+    """lpmx_peer.cu (default for world <= 8; LPMX_PEER_EXCHANGE=0 turns it off): the one-kernel exchange over NVLink peer memory must leave the
     steppers' results bit-identical to the NCCL exchange.  Needs >= 2 GPUs."""
     if _n_gpus() < 2:
         pytest.skip("needs 2 GPUs")

@@ -39,7 +39,7 @@ def main():
     rank, world, local = env_rank_world()
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    os.environ.pop("LPMX_PEER_EXCHANGE", None)  # the two engines are configured explicitly
+    os.environ["LPMX_PEER_EXCHANGE"] = "0"  # the two engines are configured explicitly (the default would turn it on for both)
     e_nccl, e_peer = Engine(local), Engine(local)
     init_engine_comm(e_nccl, rank, world)
     init_engine_comm(e_peer, rank, world)

@@ -86,6 +86,8 @@ def main():
         vel = np.zeros((n, 3))
         s.get_state(None, None, None, None, None, vel)
         err, bound = subset_check(x, zeta, area, vel) if rank == 0 else (0.0, 0.0)
+        if dist is not None:
+            dist.barrier()  # rank 0 alone ran the host-side check: do not let the others wait for it inside a kernel
         s.advance(args.dt, 2 * np.pi, 1)  # warm-up step
         eng.sync()
         if dist is not None:
