@@ -512,12 +512,12 @@ def main():
         instr = roofline["fp64_pipe_instr_per_interaction"]
         roofline["issued_tflops"] = achieved_tf * (2.0 * instr) / flops_per
         roofline["issued_frac"] = roofline["issued_tflops"] / fp64_peak if fp64_peak else None
-    prof = os.path.join(ROOT, "profiles", "r1_pair_sum_dram.json")
+    prof = os.path.join(ROOT, "profiles", "r2_pair_sum_dram.json")
     if os.path.exists(prof) and args.workload == "rh54_cubed7" and args.stepper == "bve_rk4":  # captured on that launch shape
         try:
             roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
             roofline["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch of this shape from the ncu --set "
-                                          "full capture committed as profiles/r1_pair_sum_dram.json; NOT measured in this run")
+                                          "full capture committed as profiles/r2_pair_sum_dram.json (r2o); NOT measured in this run")
         except Exception:
             pass
 
