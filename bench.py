@@ -404,6 +404,7 @@ def main():
     # ---- timed: K device-resident steps, L2 flushed between steps, events on the engine's stream ----
     sampler = ClockSampler(local_rank)
     launches0 = eng.launch_count()
+    cs_launches0 = eng.const_stream_launch_count()
     eng.profile_enable(True)
     eng.profile_read()
     barrier()
@@ -427,6 +428,7 @@ def main():
     n_k, k_ms, k_pairs = eng.profile_read()
     eng.profile_enable(False)
     launches = eng.launch_count() - launches0
+    cs_launches = eng.const_stream_launch_count() - cs_launches0
     if dist is not None:
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -506,18 +508,26 @@ def main():
         "fp64_pipe_instr_per_interaction": {"bve_rk4": 9, "ic2d_rk2": 13.5, "swe_rk2": 53}[args.stepper],  # ic2d: (9 + 18) / 2
         "traffic": None,
     }
+    if cs_launches > 0:
+        # the velocity sums of this run went through the constant banks: `launches` above counts evaluations
+        # (each = one sequence of bank launches + the ring kernel on the remainder of the targets, timed as a whole)
+        roofline["kernel"] = "lpmx::pair_sum_const_kernel (sources through the constant banks; the ring kernel takes the targets beyond whole waves)"
+        roofline["evaluations"] = n_k
+        roofline["bank_launches"] = int(cs_launches)
+        roofline["avg_bank_launch_ms"] = (k_ms / cs_launches) if cs_launches else None
     # what the FP64 pipe actually issued (2 flop per DFMA) against the same measured peak: the number that corresponds to
     # ncu's sm__pipe_fp64_cycles_active, and the reason `frac` can exceed 1 (9 DFMAs do the work of the 24-flop reference pair)
     if achieved_tf:
         instr = roofline["fp64_pipe_instr_per_interaction"]
         roofline["issued_tflops"] = achieved_tf * (2.0 * instr) / flops_per
         roofline["issued_frac"] = roofline["issued_tflops"] / fp64_peak if fp64_peak else None
-    prof = os.path.join(ROOT, "profiles", "r2_pair_sum_dram.json")
-    if os.path.exists(prof) and args.workload == "rh54_cubed7" and args.stepper == "bve_rk4":  # captured on that launch shape
+    prof = os.path.join(ROOT, "profiles", "r2_pair_sum_const_dram.json" if cs_launches > 0 else "r2_pair_sum_dram.json")
+    if os.path.exists(prof) and args.workload == "rh54_cubed7" and args.stepper == "bve_rk4" and world == 1:  # captured on that launch shape
         try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            rec = json.load(open(prof))
+            roofline["traffic"] = rec.get("dram_bytes_per_launch")
             roofline["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch of this shape from the ncu --set "
-                                          "full capture committed as profiles/r2_pair_sum_dram.json (r2o); NOT measured in this run")
+                                          f"full capture committed as profiles/{os.path.basename(prof)} ({rec.get('tag', 'r2')}); NOT measured in this run")
         except Exception:
             pass
 

@@ -211,16 +211,25 @@ int lpmx_comm_enable_peer_exchange(lpmx_handle_t h, int enable);
 int lpmx_comm_peer_exchange_enabled(lpmx_handle_t h, int* enabled, int* n_regions);
 
 /* Velocity pair sums with the source records streamed through the constant bank (lpm_b200/csrc/lpmx_const_stream.cu,
- * DESIGN.md section 4.1b): sources reach the DFMAs as uniform-register operands, +8.5 % at icos-8, slower below ~1e6 targets.
- * mode -1 (default): LPMX_CONST_STREAM from the environment, else AUTO = used for kVel launches with >= 1e6 targets per rank;
- * 0: off; 1: forced, bank copies overlapped with the launches; 2: forced, copies on the compute stream.  Affects the plans
- * made AFTER the call (solvers created / states set afterwards).  The bank is a single __constant__ array per device: the
- * first handle of a process that takes the path on a device owns it until lpmx_destroy (or mode 0); other handles on that
- * device keep the default kernel.  Same per-pair arithmetic as the default kernel; per-target sums differ by round-off. */
+ * DESIGN.md section 4.1b): sources reach the DFMAs as uniform-register operands (88 % of the FP64 pipe against 80 %).  The
+ * path takes whole waves of the chip (148 CTAs x T targets per thread x 256 threads); the targets that would leave a last wave
+ * mostly empty go through the default kernel in the same call.
+ * mode -1 (default): LPMX_CONST_STREAM from the environment, else AUTO = used for velocity launches from 189 440 targets per
+ * rank (one wave of T = 5) where the modelled time beats the default kernel's; 0: off; 1: forced, bank copies overlapped with
+ * the launches; 2: forced, copies on the compute stream.  Affects the plans made AFTER the call (solvers created / states set
+ * afterwards).  The two banks are __constant__ arrays of two modules, one pair per device: the first handle of a process that
+ * takes the path on a device owns them until lpmx_destroy (or mode 0); other handles on that device keep the default kernel.
+ * Same per-pair arithmetic as the default kernel; per-target sums differ by round-off. */
 int lpmx_pair_sum_const_stream(lpmx_handle_t h, int mode);
-/* The launch shape that path would use for n_tgt targets on a GPU with num_sms SMs (host-only planning query): T targets
- * per thread, n_warps warps per CTA, grid CTAs per launch (one CTA per SM and wave). */
-int lpmx_const_stream_shape(int num_sms, int n_tgt, int* T, int* n_warps, int* grid);
+/* How that path would split n_tgt targets x n_src sources on a GPU with num_sms SMs (host-only planning query): T targets
+ * per thread, n_warps warps per CTA, ctas CTAs per bank launch covering the first n_const targets (the other n_tgt - n_const
+ * go through the default kernel); model_seconds / ring_seconds (may be null): the modelled duration of the evaluation on
+ * that split and on the default kernel alone -- AUTO takes the path when the former is below 0.98 x the latter. */
+int lpmx_const_stream_split(int num_sms, int n_tgt, int n_src, int* T, int* n_warps, int* ctas, int* n_const,
+                            double* model_seconds, double* ring_seconds);
+/* Bank-kernel launches issued by this handle so far (0 = every pair sum went through the default kernel): lets a caller
+ * (bench.py's roofline block) name the kernel that did the work. */
+int lpmx_const_stream_launch_count(lpmx_handle_t h, long* n);
 
 /* Measured FP64 FMA throughput of this GPU in TFLOP/s (dependent-free DFMA loop on all SMs);
  * the roofline denominator that MEASURED_PEAKS.json lacks. */

@@ -144,7 +144,8 @@ def _declare(L):
         "lpmx_comm_enable_peer_exchange": [vp, i],
         "lpmx_comm_peer_exchange_enabled": [vp, c_int_p, c_int_p],
         "lpmx_pair_sum_const_stream": [vp, i],
-        "lpmx_const_stream_shape": [i, i, c_int_p, c_int_p, c_int_p],
+        "lpmx_const_stream_split": [i, i, i, c_int_p, c_int_p, c_int_p, c_int_p, c_double_p, c_double_p],
+        "lpmx_const_stream_launch_count": [vp, c_long_p],
         "lpmx_fp64_peak_tflops": [vp, c_double_p, c_double_p],
         "lpmx_bve_velocity": [vp, vp, i, l, i, vp, i, l, vp, vp, vp, i, i, vp],
         "lpmx_bve_streamfn": [vp, vp, i, l, i, vp, i, l, vp, vp, vp, i, i, vp],

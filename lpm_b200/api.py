@@ -329,6 +329,12 @@ class Engine:
         buf = ctypes.create_string_buffer(bytes(unique_id), 128)
         self._check(self._L.lpmx_comm_init(self._h, buf, rank, world), "lpmx_comm_init")
 
+    def const_stream_launch_count(self):
+        """Bank-kernel launches issued so far (0: every pair sum went through the default kernel)."""
+        n = ctypes.c_long(0)
+        self._check(self._L.lpmx_const_stream_launch_count(self._h, ctypes.byref(n)), "lpmx_const_stream_launch_count")
+        return int(n.value)
+
     def pair_sum_const_stream(self, mode):
         """0 off, 1 overlapped, 2 serial, -1 environment: velocity pair sums through the constant bank (include/lpmx.h)."""
         self._check(self._L.lpmx_pair_sum_const_stream(self._h, int(mode)), "lpmx_pair_sum_const_stream")

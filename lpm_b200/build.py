@@ -15,9 +15,9 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "liblpmx.so")
 
-CU_SOURCES = ["lpmx_core.cu", "lpmx_peer.cu", "lpmx_kernels.cu", "lpmx_const_stream.cu", "lpmx_sums.cu", "lpmx_steppers.cu", "lpmx_swe_stepper.cu", "lpmx_plane.cu", "lpmx_diagnostics.cu", "lpmx_gmls.cu", "lpmx_refinement.cu"]
+CU_SOURCES = ["lpmx_core.cu", "lpmx_peer.cu", "lpmx_kernels.cu", "lpmx_const_stream.cu", "lpmx_const_bank0.cu", "lpmx_const_bank1.cu", "lpmx_sums.cu", "lpmx_steppers.cu", "lpmx_swe_stepper.cu", "lpmx_plane.cu", "lpmx_diagnostics.cu", "lpmx_gmls.cu", "lpmx_refinement.cu"]
 CXX_SOURCES = ["lpmx_mesh.cpp"]
-HEADERS = ["lpmx_internal.h", "lpmx_finalize.cuh", "lpmx_pair_kernel.cuh", "lpmx_gmls_core.h", "lpmx_fast_log.h", "lpmx_peer_protocol.h", "lpmx_const_stream_body.h", "seed_tables.inc", "log_table_7.inc", "log_table_8.inc", "log_table_10.inc", os.path.join("..", "..", "include", "lpmx.h")]
+HEADERS = ["lpmx_internal.h", "lpmx_finalize.cuh", "lpmx_pair_kernel.cuh", "lpmx_gmls_core.h", "lpmx_fast_log.h", "lpmx_peer_protocol.h", "lpmx_const_stream_body.h", "lpmx_const_bank.cuh", "seed_tables.inc", "log_table_7.inc", "log_table_8.inc", "log_table_10.inc", os.path.join("..", "..", "include", "lpmx.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

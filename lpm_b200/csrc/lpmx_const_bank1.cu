@@ -1,0 +1,4 @@
+// lpmx_const_bank1.cu -- constant bank 1 of the constant-bank velocity path: its own translation unit = its own module = its own
+// 64 KB user constant bank (lpmx_const_bank.cuh, lpmx_const_stream.cu).
+#define LPMX_CS_BANK 1
+#include "lpmx_const_bank.cuh"

@@ -1,64 +1,59 @@
 // lpmx_const_stream.cu -- the velocity pair sum with the source records streamed through the CONSTANT bank, so that
 // they reach the DFMAs as uniform-register operands (SASS: LDCU.64 + DFMA R, R, UR, R).
-// Measured (profiles/r2b_*): icos-8 (2.40 M targets x 1.31 M sources) 7.604 -> 7.008 s per BVERK4 step, 1.657e12 -> 1.798e12
-// interactions/s (+8.5 %); cubed-7 (229 376 targets) 54.9 -> 66.4 ms (-21 %: one launch per 640 sources is ~80 us of work
-// there, all CTAs of a launch share the sources so a single wave is either quantised or unbalanced over the 4 schedulers).
-// Hence the default (mode -1 "auto"): used for velocity launches with >= 1e6 targets per rank (LPMX_CONST_MIN_TARGETS), the
-// stream-K ring kernel everywhere else.  LPMX_CONST_STREAM=0 turns it off, =1 forces overlapped copies, =2 copies on the
-// compute stream; lpmx_pair_sum_const_stream() sets the same per handle.
 //
-// Why: pair_sum_kernel (lpmx_pair_kernel.cuh) is bound by FP64 issue and reaches 81 % of the pipe because 5 of its 9
+// Why: pair_sum_kernel (lpmx_pair_kernel.cuh) is bound by FP64 issue and reaches 80 % of the pipe because 5 of its 9
 // DFMAs per pair read a third distinct register operand (profiles/README.md, "Why 81 %").  A source record is the same
-// for every thread; read from c[3][..] it costs no register-file port.  tools/const_probe.cu measured the body below at
-// 1.82e12 pairs/s per fully loaded B200 against 1.65e12 for the shared-memory ring (profiles/r1j_const_bank_probe.txt).
+// for every thread; read from c[3][..] it costs no register-file port.  Measured with one bank of two 640-record halves
+// (profiles/r2b_*, r2e_*): icos-8 (2.40 M targets x 1.31 M sources) 1.657e12 -> 1.797e12 interactions/s (+8.5 %), 88 % of the
+// FP64 pipe; but cubed-7 (229 376 targets) 54.9 -> 66.4 ms, because all CTAs of a launch share the sources (the work cannot
+// be split over sources the way the stream-K kernel does), so a launch over 229 376 targets was either two waves with the
+// second one 1 % full (T = 6, 8 warps) or unbalanced over the SM's four schedulers (10 warps).
 //
-// How: the 64 KB bank holds two halves of 640 records x 48 B {y0, y1, y2, G*y0, G*y1, G*y2}.  One launch sums ONE half
-// into every target of this rank (accumulators live in slot 0 of the partials buffer between launches, 24 B per target
-// per launch -- three orders of magnitude below the FP64 time), while a device-to-device copy on the handle's copy
-// stream fills the other half for the next launch.  All CTAs of a launch read the same sources, so the work cannot be
-// split over sources the way the stream-K kernel does; the chip is balanced by the launch shape instead: one CTA per SM,
-// and (T = 5..7 targets per thread) x 8 warps chosen so that waves x 148 x 32 x T x NW covers the targets with the least
-// excess.  That needs >= ~2e5 targets per rank; smaller launches keep the ring kernel.
+// How (round 2, second cut):
+//   * TWO banks.  lpmx_const_bank0.cu and lpmx_const_bank1.cu are separate modules, each with its own 64 KB user constant
+//     bank holding cs::kBatch = 1 280 records x 48 B {y0, y1, y2, G*y0, G*y1, G*y2}.  A launch of bank b's kernel sums that
+//     whole bank into its targets (accumulators live in slot 0 of the partials buffer between launches: 24 B per target per
+//     launch, three orders of magnitude below the FP64 time) while a device-to-device copy on the handle's copy stream
+//     refills the other bank.  Half as many launches -- and launch gaps, target loads, accumulator read-modify-writes -- as
+//     the two 640-record halves of one bank.
+//   * WHOLE WAVES ONLY.  The bank path takes the first waves x 148 x (T x 8 warps x 32) targets -- one CTA per SM, every CTA
+//     of every wave full -- and the ring kernel (stream-K, no wave quantisation) the rest, into slots behind the bank path's
+//     accumulators; cs_fold_kernel adds them into slot 0, so the stage kernels see one layout.  cubed-7: 1 wave of T = 6
+//     = 227 328 targets through the bank, 2 048 through the ring kernel.
+//   * pick_const_split chooses T in {5, 6, 7}, the number of waves and the remainder by modelled time (measured rates of
+//     both kernels, a fixed cost per launch), and the AUTO mode takes the path only where the model beats the ring kernel
+//     alone by 2 %: from one full wave of T = 5 (189 440 targets per rank) upwards.
+// LPMX_CONST_STREAM=0 turns the path off, =1 forces it wherever one wave can be filled (copies overlapped), =2 forces it
+// with the copies on the compute stream; lpmx_pair_sum_const_stream() sets the same per handle.
 //
-// Same arithmetic per pair as Pair<kVel> (bit-identical terms); per target the terms are added in source order, so the
-// sums differ from the stream-K kernel's by round-off only (the tolerance of every parity test covers both).
+// Same arithmetic per pair as Pair<kVel> (bit-identical terms); per target the terms are added in source order in blocks of
+// 1 280, so the sums differ from the stream-K kernel's by round-off only (the tolerance of every parity test covers both).
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "lpmx_const_stream_body.h"
 #include "lpmx_internal.h"
 
 namespace lpmx {
 
+// lpmx_kernels.cu
+int launch_ring_remainder(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* self_idx, const double* packed, double kappa,
+                          double* rem_partials);
+
 namespace {
 
 using cs::CsArgs;
-constexpr int kCsHalf = cs::kHalf;  // records per half of the bank
-constexpr int kCsRec = cs::kRec;    // doubles per record
-constexpr int kCsMaxThreads = 384;
-__constant__ double c_src[2 * kCsHalf * kCsRec];  // 61 440 B of the 64 KB bank
+constexpr int kCsBatch = cs::kBatch;  // records per bank
+constexpr int kCsRec = cs::kRec;      // doubles per record
 
-// the kernel body's platform on the GPU (lpmx_const_stream_body.h)
-struct CsDevice {
-  __device__ __forceinline__ int tid() const { return threadIdx.x; }
-  __device__ __forceinline__ int bid() const { return blockIdx.x; }
-  __device__ __forceinline__ int n_threads() const { return blockDim.x; }
-  __device__ __forceinline__ bool any_sync(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
-  __device__ __forceinline__ double src(int i) const { return c_src[i]; }  // warp-uniform index: LDCU, uniform-register operand
-  __device__ __forceinline__ double rcp_seed(double d) const {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    return r;
-  }
+struct Bank {
+  cudaError_t (*launch)(int, int, int, cudaStream_t, const CsArgs&);
+  cudaError_t (*fill)(const double*, cudaStream_t);
 };
+const Bank kBanks[2] = {{cs_bank_launch_0, cs_bank_fill_0}, {cs_bank_launch_1, cs_bank_fill_1}};
 
-template <int T>
-__global__ void __launch_bounds__(kCsMaxThreads, 1) pair_sum_const_kernel(const CsArgs a) {
-  CsDevice pf;
-  cs::body<T>(pf, a);
-}
-
-// packed 64-byte records -> 48-byte records, zero-padded to whole halves
+// packed 64-byte records -> 48-byte records, zero-padded to whole banks
 __global__ void cs_repack_kernel(const double* __restrict__ packed, int n_src_pad, double* __restrict__ out, long n_out) {
   const long j = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (j >= n_out) return;
@@ -72,16 +67,20 @@ __global__ void cs_repack_kernel(const double* __restrict__ packed, int n_src_pa
   for (int k = 0; k < kCsRec; ++k) out[(size_t)kCsRec * j + k] = v[k];
 }
 
-typedef void (*cs_kernel_t)(const CsArgs);
-cs_kernel_t cs_kernel_for(int T) {
-  switch (T) {
-    case 4: return pair_sum_const_kernel<4>;
-    case 5: return pair_sum_const_kernel<5>;
-    case 6: return pair_sum_const_kernel<6>;
-    case 7: return pair_sum_const_kernel<7>;
-    case 8: return pair_sum_const_kernel<8>;
-    default: return nullptr;
-  }
+// remainder targets: the ring kernel's slots (in slot order, as the stage kernels would add them) -> the bank path's layout
+__global__ void cs_fold_kernel(const double* __restrict__ rem, long rem_pad, int n_rem, int rem_tb, int rem_n_sc, int rem_grid,
+                               long rem_items, double* __restrict__ acc, long n_tgt_pad, int n_const) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rem) return;
+  const int tb = i / rem_tb;
+  const int c0 = (int)((((long)tb * rem_n_sc + 1) * (long)rem_grid - 1) / rem_items);
+  const int c1 = (int)(((((long)(tb + 1) * rem_n_sc - 1) + 1) * (long)rem_grid - 1) / rem_items);
+  double m[3] = {0.0, 0.0, 0.0};
+  for (int slot = 0; slot <= c1 - c0; ++slot)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) m[k] += rem[((long)slot * 3 + k) * rem_pad + i];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) acc[(long)k * n_tgt_pad + n_const + i] = m[k];
 }
 
 }  // namespace
@@ -97,9 +96,9 @@ int const_stream_mode(lpmx_handle_t h) {
   return env;
 }
 
-// The bank is ONE __constant__ array per device (module scope), ordered only by the using handle's streams and events: two
-// handles on the same device must not stream through it at once.  The first handle to take the path on a device owns the
-// bank until lpmx_destroy; any other handle on that device keeps the ring kernel.
+// The two banks are module-scope __constant__ arrays, one pair per device, ordered only by the using handle's streams and
+// events: two handles on the same device must not stream through them at once.  The first handle to take the path on a device
+// owns the banks until lpmx_destroy; any other handle on that device keeps the ring kernel.
 static std::mutex g_bank_mutex;
 static lpmx_handle_t g_bank_owner[64] = {};
 static bool claim_bank(lpmx_handle_t h) {
@@ -114,88 +113,117 @@ static void release_bank(lpmx_handle_t h) {
   if (g_bank_owner[h->device] == h) g_bank_owner[h->device] = nullptr;
 }
 
-// One CTA per SM; a launch takes ~ waves x T x NW while the FP64 pipe is the limit (>= 8 warps).  Least excess wins,
-// ties go to T = 6 (the measured shape), then to more warps.  LPMX_CONST_SHAPE="T,NW" overrides (tuning).
-void pick_const_shape(int num_sms, int n_tgt, int* T_out, int* nw_out, int* grid_out) {
-  int bt = 6, bnw = 8;
-  long best = -1;
-  static int ft = 0, fnw = 0;
+// Measured constants of the model (one B200): a bank launch with every CTA full runs at 88.6 % of the FP64 pipe
+// (profiles/r2e_icos8_const_shapes.txt: T = 5 and 6 within 1 %, T = 7 slightly below), i.e. 64 / 9 * 0.886 = 6.3 pairs per
+// cycle and SM; its fixed cost (launch gap, target loads, the read-modify-write of the accumulators) is ~6 us
+// (profiles/r2b_shape_sweep.txt: two waves of T = 6 per 640-record launch took 163.8 us at cubed-7).
+static double const_launch_seconds(int waves, int T, int nw) {
+  const double pairs_per_sm = (double)waves * T * nw * 32 * kCsBatch;
+  const double eff = T == 7 ? 0.80 : 0.886;  // T = 7: one CTA per SM, no second CTA to cover its stalls (r2e, r2r)
+  return pairs_per_sm * 9.0 / (64.0 * eff) / 1.965e9 + 6e-6;
+}
+
+// LPMX_CONST_SHAPE="T,NW[,PERSM]" pins the shape (tuning): T targets per thread, NW compute warps, PERSM CTAs per SM and wave
+static void forced_shape(int* ft, int* fnw, int* fps) {
+  static int t = 0, nw = 0, ps = 1;
   static bool parsed = false;
   if (!parsed) {
     parsed = true;
     const char* e = getenv("LPMX_CONST_SHAPE");
-    if (e && sscanf(e, "%d,%d", &ft, &fnw) == 2 && cs_kernel_for(ft) && fnw >= 1 && fnw * 32 <= kCsMaxThreads) {
-    } else {
-      ft = fnw = 0;
-    }
+    const int n = e ? sscanf(e, "%d,%d,%d", &t, &nw, &ps) : 0;
+    if (n < 3) ps = 1;
+    if (!(n >= 2 && t >= 3 && t <= 8 && nw >= 1 && (nw + 1) * 32 <= kCsMaxThreads && ps >= 1 && ps <= 4)) t = nw = 0, ps = 1;
   }
-  if (ft) {
-    bt = ft, bnw = fnw;
-  } else {
-    // warps per CTA in multiples of 4: with 9-11 warps two of the SM's four schedulers carry one warp more and the CTA waits
-    // for them (measured: T = 5 with 10 warps 66.4 ms where 8 balanced warps would take 54; profiles/r2b_shape_sweep.txt)
-    // measured at icos-8 (profiles/r2e_icos8_const_shapes.txt): T = 5 / 8 warps 1.797e12, T = 6 / 8 warps 1.776e12 interactions/s,
-    // but T = 8 / 8 warps 1.649e12 and T = 6 / 12 warps 1.588e12 (below the ring kernel's 1.657e12): 8 warps, T <= 7
-    const int order[3] = {5, 6, 7};
-    for (int oi = 0; oi < 3; ++oi) {
-      const int T = order[oi];
-      for (int nw = 8; nw >= 8; nw -= 4) {
-        const long tb = (long)T * nw * 32;
-        const long ctas = (n_tgt + tb - 1) / tb;
-        const long waves = (ctas + num_sms - 1) / num_sms;
-        const long cost = waves * T * nw;
-        if (best < 0 || cost < best) best = cost, bt = T, bnw = nw;
+  *ft = t, *fnw = nw, *fps = ps;
+}
+
+double pick_const_split(lpmx_handle_t h, int num_sms, int n_tgt, int n_src, int* T_out, int* nw_out, int* ctas_out, int* n_const_out,
+                        double* ring_s_out) {
+  const long n_batches = ((long)round_up_chunk(n_src) + kCsBatch - 1) / kCsBatch;
+  SumPlan ring;
+  double ring_s = 0.0;
+  if (make_plan(h, kVel, n_tgt, n_src, &ring, false) == LPMX_OK) ring_s = ring_plan_seconds(ring);
+  if (ring_s_out) *ring_s_out = ring_s;
+  int ft, fnw, fps;
+  forced_shape(&ft, &fnw, &fps);
+  double best = -1.0;
+  // 8 warps = 2 per scheduler: with 9-11 warps two of the SM's four schedulers carry one warp more and the CTA waits for them
+  // (r2b: T = 5 with 10 warps 66.4 ms at cubed-7), 12 warps and T = 8 are slower than the ring kernel (r2e)
+  for (int T = ft ? ft : 5; T <= (ft ? ft : 7); ++T) {
+    const int nw = ft ? fnw : 8;
+    const long tb = (long)T * nw * 32;
+    const long wave = (long)num_sms * (ft ? fps : 1) * tb;
+    const long full = n_tgt / wave;
+    // candidates: `full` whole waves + a ring remainder, or one more (partly empty) wave and no remainder
+    for (int extra = 0; extra < 2; ++extra) {
+      const long waves = full + extra;
+      if (waves < 1) continue;
+      const long n_const = extra ? n_tgt : full * wave;
+      const long ctas = (n_const + tb - 1) / tb;
+      double t = (double)n_batches * const_launch_seconds((int)waves, T, nw);
+      const long n_rem = n_tgt - n_const;
+      if (n_rem > 0) {
+        SumPlan r;
+        if (make_plan(h, kVel, (int)n_rem, n_src, &r, false) != LPMX_OK) continue;
+        t += ring_plan_seconds(r) + 4e-6;  // + the fold
+      }
+      if (best < 0 || t < best) {
+        best = t;
+        *T_out = T, *nw_out = nw, *ctas_out = (int)ctas, *n_const_out = (int)n_const;
       }
     }
   }
-  const long tb = (long)bt * bnw * 32;
-  *T_out = bt;
-  *nw_out = bnw;
-  *grid_out = (int)((n_tgt + tb - 1) / tb);
+  return best;
 }
 
 bool make_const_plan(lpmx_handle_t h, int n_tgt, int n_src, SumPlan* p) {
   const int mode = const_stream_mode(h);
   if (mode == 0) return false;
-  // auto: only where a launch (640 sources x all targets of the rank) is long against its fixed costs -- launch gap, target
-  // loads, the read-modify-write of the accumulators, wave quantisation: measured break-even ~1e6 targets (file header).
-  // forced (1 / 2): wherever one launch can fill the chip at all.
-  long min_tgt = mode < 0 ? 1000000L : (long)h->num_sms * 32 * 8 * 5;
-  if (const char* e = getenv("LPMX_CONST_MIN_TARGETS")) min_tgt = atol(e);  // parity tests on small meshes
-  if ((long)n_tgt < min_tgt || n_tgt < 1 || n_src < 4 * kCsHalf) return false;
-  int T, nw, grid;
-  pick_const_shape(h->num_sms, n_tgt, &T, &nw, &grid);
-  if (mode < 0) {
-    // auto: the path is worth +8.5 % of a launch that fills its waves; a rank whose targets leave the last wave mostly empty
-    // (1.2e6 targets: 7 waves at 90.6 %) is better served by the stream-K kernel, which has no wave quantisation
-    const long tb = (long)T * nw * 32;
-    const long waves = (grid + h->num_sms - 1) / h->num_sms;
-    if ((double)n_tgt < 0.95 * (double)(waves * h->num_sms * tb)) return false;
-  }
+  // auto: from one full wave of the smallest shape upwards, and only where the modelled time beats the ring kernel's;
+  // forced (1 / 2): wherever one wave can be filled at all.  LPMX_CONST_MIN_TARGETS lowers the floor (parity tests on small
+  // meshes: whatever does not fill a wave goes through an only partly filled one)
+  long min_tgt = (long)h->num_sms * 32 * 8 * 5;
+  if (const char* e = getenv("LPMX_CONST_MIN_TARGETS")) min_tgt = atol(e);
+  if ((long)n_tgt < min_tgt || n_tgt < 1 || n_src < 4 * kCsBatch) return false;
+  int T = 0, nw = 0, ctas = 0, n_const = 0;
+  double ring_s = 0.0;
+  const double t = pick_const_split(h, h->num_sms, n_tgt, n_src, &T, &nw, &ctas, &n_const, &ring_s);
+  if (t < 0) return false;
+  if (mode < 0 && !(t < 0.98 * ring_s)) return false;
   if (!claim_bank(h)) return false;
+  *p = SumPlan();
   p->kind = kVel;
   p->shape = kShapeConstStream;
   p->T = T;
   p->tb = T * nw * 32;
   p->n_tgt = n_tgt;
-  p->n_tb = grid;  // CTAs of one launch
+  p->cs_ctas = ctas;
+  p->cs_n_const = n_const;
   p->n_src_pad = round_up_chunk(n_src);
   p->n_sc = p->n_src_pad / kChunk;
   p->grid = 1;  // what the finalize kernels see: every target block was summed by "CTA 0", i.e. slot 0 only
   p->max_slots = 1;
-  p->n_tgt_pad = (long)p->n_tb * p->tb;
+  const long covered = (long)ctas * p->tb;  // >= n_const; == n_const when a remainder follows
+  p->n_tgt_pad = covered > n_tgt ? covered : (long)n_tgt;
+  p->n_tb = (int)((p->n_tgt_pad + p->tb - 1) / p->tb);
   p->smem_bytes = 0;
+  if (n_const < n_tgt) {
+    SumPlan r;
+    if (make_plan(h, kVel, n_tgt - n_const, n_src, &r, false) != LPMX_OK) return false;
+    p->rem.shape = r.shape, p->rem.T = r.T, p->rem.tb = r.tb, p->rem.n_tgt = r.n_tgt, p->rem.n_tb = r.n_tb, p->rem.grid = r.grid;
+    p->rem.max_slots = r.max_slots, p->rem.n_tgt_pad = r.n_tgt_pad, p->rem.smem_bytes = r.smem_bytes;
+  }
   return true;
 }
 
-int launch_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* self_idx, const double* packed, double kappa,
-                        double* partials) {
-  const int mode = const_stream_mode(h) == 2 ? 2 : 1;
-  const long n_batches = ((long)p.n_src_pad + kCsHalf - 1) / kCsHalf;
-  const long n_out = n_batches * kCsHalf;
-  void* stage_v = nullptr;
-  LPMX_TRY(dev_buffer(h, "const_stage", sizeof(double) * kCsRec * (size_t)n_out, &stage_v));
+// the launch sequence of one evaluation, enqueued on the handle's two streams (eagerly, or into a stream capture)
+static int enqueue_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* self_idx, const double* packed,
+                                double kappa, double* partials, int mode, int pf_stride, void* stage_v, long* n_launches,
+                                long* n_bank_launches) {
+  const long n_batches = ((long)p.n_src_pad + kCsBatch - 1) / kCsBatch;
+  const long n_out = n_batches * kCsBatch;
   const double* stage = (const double*)stage_v;
+  const long launches0 = h->launches, cs0 = h->cs_launches;
   cs_repack_kernel<<<(int)((n_out + 255) / 256), 256, 0, h->stream>>>(packed, p.n_src_pad, (double*)stage_v, n_out);
   ++h->launches;
   LPMX_CUDA(h, cudaGetLastError());
@@ -203,29 +231,35 @@ int launch_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const i
     for (int i = 0; i < 5; ++i) LPMX_CUDA(h, cudaEventCreateWithFlags(&h->cs_events[i], cudaEventDisableTiming));
   }
   cudaEvent_t ev_repack = h->cs_events[0];
-  cudaEvent_t* ev_copied = &h->cs_events[1];  // [half]
-  cudaEvent_t* ev_summed = &h->cs_events[3];  // [half]
-  const size_t half_bytes = sizeof(double) * kCsRec * kCsHalf;
-  cs_kernel_t kern = cs_kernel_for(p.T);
-  if (!kern) return set_error(h, LPMX_ERR_STATE, "no constant-bank kernel for T = %d", p.T);
-  const int threads = p.tb / p.T;
+  cudaEvent_t* ev_filled = &h->cs_events[1];  // [bank]
+  cudaEvent_t* ev_summed = &h->cs_events[3];  // [bank]
+  // the prefetch warp (lpmx_const_bank.cuh) rides along on launches of a single wave, where every CTA starts on cold constant
+  // caches; later waves of a longer launch find the bank cached, and without the extra warp two CTAs of T <= 6 fit an SM
+  // (r2p: 88.6 % of the FP64 pipe at icos-8 that way, 78 % with the extra warp in every CTA, r2q)
+  int fts, fnws, per_sm;
+  forced_shape(&fts, &fnws, &per_sm);
+  const bool single_wave = p.cs_ctas <= h->num_sms * (fts ? per_sm : 1);
+  const int pf = single_wave ? pf_stride : 0;
+  const int threads = p.tb / p.T + (pf > 0 ? 32 : 0);
   cudaStream_t cps = mode == 1 ? h->copy_stream : h->stream;
-  // copy of batch b into half b & 1; in the overlapped mode it waits for the launch that last read that half
-  auto copy_batch = [&](long b) -> int {
-    const int half = (int)(b & 1);
-    if (mode == 1 && b >= 2) LPMX_CUDA(h, cudaStreamWaitEvent(cps, ev_summed[half], 0));
-    LPMX_CUDA(h, cudaMemcpyToSymbolAsync(c_src, stage + (size_t)b * kCsHalf * kCsRec, half_bytes, (size_t)half * half_bytes,
-                                         cudaMemcpyDeviceToDevice, cps));
-    if (mode == 1) LPMX_CUDA(h, cudaEventRecord(ev_copied[half], cps));
+  // refill of bank (b & 1) with batch b; in the overlapped mode it waits for the launch that last read that bank
+  auto fill_batch = [&](long b) -> int {
+    const int bank = (int)(b & 1);
+    if (mode == 1 && b >= 2) LPMX_CUDA(h, cudaStreamWaitEvent(cps, ev_summed[bank], 0));
+    LPMX_CUDA(h, kBanks[bank].fill(stage + (size_t)b * kCsBatch * kCsRec, cps));
+    if (mode == 1) LPMX_CUDA(h, cudaEventRecord(ev_filled[bank], cps));
     return LPMX_OK;
   };
   if (mode == 1) {
-    // everything queued so far on the compute stream (the repack, and any earlier launch still reading the bank)
+    // everything queued so far on the compute stream (the repack, and any earlier launch still reading the banks)
     LPMX_CUDA(h, cudaEventRecord(ev_repack, h->stream));
     LPMX_CUDA(h, cudaStreamWaitEvent(cps, ev_repack, 0));
-    LPMX_TRY(copy_batch(0));
-    if (n_batches > 1) LPMX_TRY(copy_batch(1));
+    LPMX_TRY(fill_batch(0));
+    if (n_batches > 1) LPMX_TRY(fill_batch(1));
   }
+  // the remainder first: the ring kernel runs while the first banks are being filled
+  double* rem_partials = partials + 3 * (size_t)p.n_tgt_pad;
+  if (p.rem.n_tgt > 0) LPMX_TRY(launch_ring_remainder(h, p, tgt, self_idx, packed, kappa, rem_partials));
   CsArgs a;
   a.tgt = tgt.p;
   a.tgt_si = tgt.si;
@@ -233,30 +267,150 @@ int launch_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const i
   a.self_idx = self_idx;
   a.acc = partials;
   a.n_tgt_pad = p.n_tgt_pad;
-  a.n_tgt = p.n_tgt;
+  a.n_tgt = p.cs_n_const;
   a.kappa = kappa;
+  a.prefetch_stride = pf;
   for (long b = 0; b < n_batches; ++b) {
-    const int half = (int)(b & 1);
+    const int bank = (int)(b & 1);
     if (mode == 1)
-      LPMX_CUDA(h, cudaStreamWaitEvent(h->stream, ev_copied[half], 0));
+      LPMX_CUDA(h, cudaStreamWaitEvent(h->stream, ev_filled[bank], 0));
     else
-      LPMX_TRY(copy_batch(b));
-    a.half = half;
-    a.j0 = (int)(b * kCsHalf);
+      LPMX_TRY(fill_batch(b));
+    a.j0 = (int)(b * kCsBatch);
     a.first = b == 0 ? 1 : 0;
-    kern<<<p.n_tb, threads, 0, h->stream>>>(a);
+    const cudaError_t e = kBanks[bank].launch(p.T, p.cs_ctas, threads, h->stream, a);
+    if (e == cudaErrorInvalidValue) return set_error(h, LPMX_ERR_STATE, "no constant-bank kernel for T = %d", p.T);
     ++h->launches;
-    LPMX_CUDA(h, cudaGetLastError());
+    ++h->cs_launches;
+    LPMX_CUDA(h, e);
     if (mode == 1) {
-      LPMX_CUDA(h, cudaEventRecord(ev_summed[half], h->stream));
-      if (b + 2 < n_batches) LPMX_TRY(copy_batch(b + 2));
+      LPMX_CUDA(h, cudaEventRecord(ev_summed[bank], h->stream));
+      if (b + 2 < n_batches) LPMX_TRY(fill_batch(b + 2));
     }
   }
+  if (p.rem.n_tgt > 0) {
+    const long rem_items = (long)p.rem.n_tb * p.n_sc;
+    cs_fold_kernel<<<(p.rem.n_tgt + 255) / 256, 256, 0, h->stream>>>(rem_partials, p.rem.n_tgt_pad, p.rem.n_tgt, p.rem.tb, p.n_sc,
+                                                                      p.rem.grid, rem_items, partials, p.n_tgt_pad, p.cs_n_const);
+    ++h->launches;
+    LPMX_CUDA(h, cudaGetLastError());
+  }
+  *n_launches = h->launches - launches0;
+  *n_bank_launches = h->cs_launches - cs0;
+  return LPMX_OK;
+}
+
+// One evaluation is ~80 kernel launches, as many bank refills and twice as many event operations: enqueued one by one they
+// cost the host ~15 ms per BVERK4 step at cubed-7 (r2p: e2e 81 ms against 66 ms on the device).  The sequence depends only on
+// the plan and the pointers, and a stepper repeats the same few of them (two source buffers x the work array), so the second
+// time a sequence comes by it is captured into a CUDA graph -- both streams, the event edges, the refills as memcpy nodes --
+// and from then on it is ONE cudaGraphLaunch.  LPMX_CONST_GRAPH=0 keeps the eager sequence.
+namespace {
+struct CsGraphKey {
+  const void *tgt, *self_idx, *packed, *partials, *stage;
+  long si, sk, n_tgt_pad, rem_pad;
+  int T, tb, ctas, n_const, n_tgt, n_src_pad, rem_n, rem_shape, rem_grid, mode, pf;
+  double kappa;
+  bool operator==(const CsGraphKey& o) const {
+    return tgt == o.tgt && self_idx == o.self_idx && packed == o.packed && partials == o.partials && stage == o.stage && si == o.si &&
+           sk == o.sk && n_tgt_pad == o.n_tgt_pad && rem_pad == o.rem_pad && T == o.T && tb == o.tb && ctas == o.ctas &&
+           n_const == o.n_const && n_tgt == o.n_tgt && n_src_pad == o.n_src_pad && rem_n == o.rem_n && rem_shape == o.rem_shape &&
+           rem_grid == o.rem_grid && mode == o.mode && pf == o.pf && kappa == o.kappa;
+  }
+};
+struct CsGraph {
+  CsGraphKey key;
+  cudaGraphExec_t exec = nullptr;
+  long n_launches = 0, n_bank_launches = 0;
+  unsigned long tick = 0;
+};
+struct CsGraphCache {
+  std::vector<CsGraph> entries;
+  unsigned long tick = 0;
+  bool broken = false;  // a capture failed on this handle: stay eager
+};
+constexpr size_t kCsMaxGraphs = 16;
+}  // namespace
+
+int launch_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* self_idx, const double* packed, double kappa,
+                        double* partials) {
+  const int mode = const_stream_mode(h) == 2 ? 2 : 1;
+  // read per call (two getenv per evaluation) so that tests can switch them within one process
+  const int pf_stride = [] {  // LPMX_CONST_PREFETCH = bytes between the prefetch warp's loads (0: off); default one per 128 B (r2r: 64 B 51.9 ms, 128 B 51.4 ms per step at cubed-7)
+    const char* e = getenv("LPMX_CONST_PREFETCH");
+    const int v = e ? atoi(e) : 128;
+    return v <= 0 ? 0 : (v < 8 ? 1 : v / 8);
+  }();
+  const bool use_graphs = [] {
+    const char* e = getenv("LPMX_CONST_GRAPH");
+    return !(e && atoi(e) == 0);
+  }();
+  const long n_batches = ((long)p.n_src_pad + kCsBatch - 1) / kCsBatch;
+  void* stage_v = nullptr;
+  LPMX_TRY(dev_buffer(h, "const_stage", sizeof(double) * kCsRec * (size_t)(n_batches * kCsBatch), &stage_v));
+  long nl = 0, nb = 0;
+  if (!use_graphs) return enqueue_const_stream(h, p, tgt, self_idx, packed, kappa, partials, mode, pf_stride, stage_v, &nl, &nb);
+  if (!h->cs_graph_cache) h->cs_graph_cache = new CsGraphCache();
+  CsGraphCache* cache = (CsGraphCache*)h->cs_graph_cache;
+  if (cache->broken) return enqueue_const_stream(h, p, tgt, self_idx, packed, kappa, partials, mode, pf_stride, stage_v, &nl, &nb);
+  CsGraphKey key{tgt.p, self_idx, packed, partials, stage_v, tgt.si, tgt.sk, p.n_tgt_pad, p.rem.n_tgt_pad, p.T, p.tb, p.cs_ctas,
+                 p.cs_n_const, p.n_tgt, p.n_src_pad, p.rem.n_tgt, p.rem.shape, p.rem.grid, mode, pf_stride, kappa};
+  CsGraph* g = nullptr;
+  for (auto& e : cache->entries)
+    if (e.key == key) g = &e;
+  if (!g) {
+    // first sighting: run it eagerly (this also does the one-time work a capture must not contain: function attributes, event
+    // creation, buffer growth) and remember the key
+    if (cache->entries.size() >= kCsMaxGraphs) {
+      size_t old = 0;
+      for (size_t i = 1; i < cache->entries.size(); ++i)
+        if (cache->entries[i].tick < cache->entries[old].tick) old = i;
+      if (cache->entries[old].exec) cudaGraphExecDestroy(cache->entries[old].exec);
+      cache->entries.erase(cache->entries.begin() + old);
+    }
+    CsGraph e;
+    e.key = key;
+    e.tick = ++cache->tick;
+    cache->entries.push_back(e);
+    return enqueue_const_stream(h, p, tgt, self_idx, packed, kappa, partials, mode, pf_stride, stage_v, &nl, &nb);
+  }
+  g->tick = ++cache->tick;
+  if (!g->exec) {
+    const long launches0 = h->launches, cs0 = h->cs_launches;
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+    int rc = LPMX_OK;
+    if (ce == cudaSuccess) {
+      rc = enqueue_const_stream(h, p, tgt, self_idx, packed, kappa, partials, mode, pf_stride, stage_v, &g->n_launches, &g->n_bank_launches);
+      ce = cudaStreamEndCapture(h->stream, &graph);
+    }
+    h->launches = launches0, h->cs_launches = cs0;  // nothing has run yet
+    if (ce == cudaSuccess && rc == LPMX_OK && graph) ce = cudaGraphInstantiate(&g->exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (ce != cudaSuccess || rc != LPMX_OK || !g->exec) {
+      // not capturable here: clear the error state and stay with the eager sequence on this handle
+      cudaGetLastError();
+      h->err.clear();
+      g->exec = nullptr;
+      cache->broken = true;
+      return enqueue_const_stream(h, p, tgt, self_idx, packed, kappa, partials, mode, pf_stride, stage_v, &nl, &nb);
+    }
+  }
+  LPMX_CUDA(h, cudaGraphLaunch(g->exec, h->stream));
+  h->launches += g->n_launches;
+  h->cs_launches += g->n_bank_launches;
   return LPMX_OK;
 }
 
 void const_stream_teardown(lpmx_handle_t h) {
   release_bank(h);
+  if (h->cs_graph_cache) {
+    CsGraphCache* cache = (CsGraphCache*)h->cs_graph_cache;
+    for (auto& e : cache->entries)
+      if (e.exec) cudaGraphExecDestroy(e.exec);
+    delete cache;
+    h->cs_graph_cache = nullptr;
+  }
   for (int i = 0; i < 5; ++i)
     if (h->cs_events[i]) {
       cudaEventDestroy(h->cs_events[i]);
@@ -266,9 +420,23 @@ void const_stream_teardown(lpmx_handle_t h) {
 
 }  // namespace lpmx
 
-extern "C" int lpmx_const_stream_shape(int num_sms, int n_tgt, int* T, int* n_warps, int* grid) {
-  if (num_sms < 1 || n_tgt < 1 || !T || !n_warps || !grid) return LPMX_ERR_INVALID;
-  lpmx::pick_const_shape(num_sms, n_tgt, T, n_warps, grid);
+extern "C" int lpmx_const_stream_split(int num_sms, int n_tgt, int n_src, int* T, int* n_warps, int* ctas, int* n_const,
+                                       double* model_seconds, double* ring_seconds) {
+  if (num_sms < 1 || n_tgt < 1 || n_src < 1 || !T || !n_warps || !ctas || !n_const) return LPMX_ERR_INVALID;
+  lpmx_handle_s probe;  // planning only: the ring planner reads num_sms and nothing else
+  probe.num_sms = num_sms;
+  probe.device = -1;
+  double ring_s = 0.0;
+  const double t = lpmx::pick_const_split(&probe, num_sms, n_tgt, n_src, T, n_warps, ctas, n_const, &ring_s);
+  if (t < 0) return LPMX_ERR_STATE;
+  if (model_seconds) *model_seconds = t;
+  if (ring_seconds) *ring_seconds = ring_s;
+  return LPMX_OK;
+}
+
+extern "C" int lpmx_const_stream_launch_count(lpmx_handle_t h, long* n) {
+  if (!h || !n) return LPMX_ERR_INVALID;
+  *n = h->cs_launches;
   return LPMX_OK;
 }
 

@@ -2,8 +2,9 @@
 // CPU suite runs the kernel's own indexing (targets per thread, padding, accumulator layout, first-launch flag, self-pair
 // exclusion by compact index) with every CUDA thread a loop iteration (tests/cpp/const_stream_model.cpp).
 //
-// Platform P: int tid(), bid(), n_threads();  bool any_sync(bool);  double src(int i)  (record storage of the two halves);
-//             double rcp_seed(double)  (>= 19 correct bits).
+// Platform P: int tid(), bid(), n_threads();  bool any_sync(bool);  double src(int i)  (record storage of the launch's bank);
+//             double rcp_seed(double)  (>= 19 correct bits);  void accumulate(double* p, double v, bool first)  (*p = v or *p += v;
+//             every address belongs to one thread of one launch at a time).
 #ifndef LPMX_CONST_STREAM_BODY_H
 #define LPMX_CONST_STREAM_BODY_H
 
@@ -18,8 +19,9 @@
 namespace lpmx {
 namespace cs {
 
-constexpr int kHalf = 640;  // records per half of the constant bank
-constexpr int kRec = 6;     // doubles per record {y0, y1, y2, G*y0, G*y1, G*y2}
+constexpr int kBatch = 1280;  // records per launch = one whole constant bank (61 440 of its 65 536 bytes); two banks alternate
+constexpr int kRec = 6;       // doubles per record {y0, y1, y2, G*y0, G*y1, G*y2}
+constexpr int kBankDoubles = (kBatch + 1) * kRec;  // + one record the pipelined loop reads ahead into and never uses
 
 struct CsArgs {
   const double* tgt;    // this launch's targets, element (i, k) at tgt[i * tgt_si + k * tgt_sk], indexed from 0
@@ -28,30 +30,40 @@ struct CsArgs {
   double* acc;          // [3][n_tgt_pad]
   long n_tgt_pad;
   int n_tgt;
-  int half;   // which half of the bank this launch reads
-  int j0;     // compact index of the half's first record
+  int j0;     // compact index of the bank's first record
   int first;  // start from zero instead of the stored accumulators
+  int prefetch_stride;  // doubles between the loads of the CTA's prefetch warp (GPU only; 0: no prefetch)
   double kappa;
 };
 
 // Same arithmetic per pair as Pair<kVel>::apply (lpmx_pair_kernel.cuh): 3 (d) + 3 (1/d from the seed) + 3 (M += r * G*y).
+// The record of source j + 1 is loaded BEFORE the pairs of source j are evaluated (software pipelining: on the GPU a
+// constant load to a uniform register has a latency that two warps per scheduler do not hide when it is issued right in
+// front of its first use -- r2q: short-scoreboard stalls, 77 % of the FP64 pipe).  The last iteration loads record kBatch:
+// the bank is declared one record longer (its content is never used).
 template <int T, bool CHECK, class P>
-LPMX_CS_HD void loop(P& pf, const double (&x)[T][3], const int (&self)[T], double (&acc)[T][3], int base, int j0, double kappa) {
+LPMX_CS_HD void loop(P& pf, const double (&x)[T][3], const int (&self)[T], double (&acc)[T][3], int j0, double kappa) {
+  double s[kRec], sn[kRec];
+#pragma unroll
+  for (int k = 0; k < kRec; ++k) sn[k] = pf.src(k);
 #pragma unroll 2
-  for (int j = 0; j < kHalf; ++j) {
-    const double s0 = pf.src(base + kRec * j), s1 = pf.src(base + kRec * j + 1), s2 = pf.src(base + kRec * j + 2);
-    const double s3 = pf.src(base + kRec * j + 3), s4 = pf.src(base + kRec * j + 4), s5 = pf.src(base + kRec * j + 5);
+  for (int j = 0; j < kBatch; ++j) {
+#pragma unroll
+    for (int k = 0; k < kRec; ++k) {
+      s[k] = sn[k];
+      sn[k] = pf.src(kRec * (j + 1) + k);
+    }
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-      const double d = fma(-x[t][0], s0, fma(-x[t][1], s1, fma(-x[t][2], s2, kappa)));
+      const double d = fma(-x[t][0], s[0], fma(-x[t][1], s[1], fma(-x[t][2], s[2], kappa)));
       const double r0 = pf.rcp_seed(d);
       const double e = fma(-d, r0, 1.0);
       const double p = fma(e, e, e);
       double r = fma(r0, p, r0);
       if (CHECK) r = (j0 + j == self[t]) ? 0.0 : r;
-      acc[t][0] = fma(r, s3, acc[t][0]);
-      acc[t][1] = fma(r, s4, acc[t][1]);
-      acc[t][2] = fma(r, s5, acc[t][2]);
+      acc[t][0] = fma(r, s[3], acc[t][0]);
+      acc[t][1] = fma(r, s[4], acc[t][1]);
+      acc[t][2] = fma(r, s[5], acc[t][2]);
     }
   }
 }
@@ -70,26 +82,22 @@ LPMX_CS_HD void body(P& pf, const CsArgs& a) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       x[t][k] = valid ? a.tgt[tg * a.tgt_si + k * a.tgt_sk] : 0.0;  // a zero target sees d = kappa: finite, never read back
-      acc[t][k] = 0.0;  // two-level summation: this launch's 640 terms start from zero (see the store below)
+      acc[t][k] = 0.0;  // two-level summation: this launch's 1 280 terms start from zero (see the store below)
     }
     self[t] = (valid && a.self_idx) ? a.self_idx[tg] : -1;
-    hit |= (unsigned)(self[t] - a.j0) < (unsigned)kHalf;
+    hit |= (unsigned)(self[t] - a.j0) < (unsigned)kBatch;
   }
-  const int base = a.half * (kHalf * kRec);
   if (pf.any_sync(hit))
-    loop<T, true>(pf, x, self, acc, base, a.j0, a.kappa);
+    loop<T, true>(pf, x, self, acc, a.j0, a.kappa);
   else
-    loop<T, false>(pf, x, self, acc, base, a.j0, a.kappa);
+    loop<T, false>(pf, x, self, acc, a.j0, a.kappa);
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const long tg = base_t + (long)t * lanes;
     // the launch's partial sum is added to the running total once: the accumulated rounding of the factored sum scales with
-    // sqrt(640) + sqrt(N / 640) instead of sqrt(N) (lpmx_pair_kernel.cuh, "two-level summation")
+    // sqrt(1280) + sqrt(N / 1280) instead of sqrt(N) (lpmx_pair_kernel.cuh, "two-level summation")
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      double* p = a.acc + (long)k * a.n_tgt_pad + tg;
-      *p = a.first ? acc[t][k] : (*p + acc[t][k]);
-    }
+    for (int k = 0; k < 3; ++k) pf.accumulate(a.acc + (long)k * a.n_tgt_pad + tg, acc[t][k], a.first != 0);
   }
 }
 

@@ -79,6 +79,17 @@ struct SumPlan {
   int max_slots;    // partial-sum slots per target block
   long n_tgt_pad;   // n_tb * tb
   size_t smem_bytes;
+  // Constant-bank plans only (shape == kShapeConstStream): the first cs_n_const targets go through the bank in launches of
+  // cs_ctas CTAs (whole waves of the chip); the other rem.n_tgt targets -- what would leave a last wave mostly empty -- go through
+  // the stream-K ring kernel (plan `rem`), whose slots are folded into the bank path's accumulators before the stage kernel
+  // reads them (lpmx_const_stream.cu).
+  int cs_ctas = 0;
+  int cs_n_const = 0;
+  struct Rem {
+    int shape = 0, T = 0, tb = 0, n_tgt = 0, n_tb = 0, grid = 0, max_slots = 0;
+    long n_tgt_pad = 0;
+    size_t smem_bytes = 0;
+  } rem;
 };
 
 // grow-only device buffer
@@ -123,7 +134,9 @@ struct lpmx_handle_s {
   void* nccl_lib = nullptr;   // dlopen handle
   lpmx::PeerState* peer = nullptr;  // lpmx_comm_enable_peer_exchange
   int const_stream = -1;            // lpmx_pair_sum_const_stream: -1 = LPMX_CONST_STREAM from the environment
-  cudaEvent_t cs_events[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // lpmx_const_stream.cu
+  long cs_launches = 0;             // bank-kernel launches so far (lpmx_const_stream_launch_count)
+  void* cs_graph_cache = nullptr;   // captured launch sequences of the constant-bank path (lpmx_const_stream.cu)
+  cudaEvent_t cs_events[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // lpmx_const_stream.cu: repack, filled[2], summed[2]
   std::map<std::string, lpmx::DevBuf> bufs;  // named scratch buffers
   std::map<std::string, lpmx::DevBuf> pinned;  // named pinned host staging buffers
   // optional per-launch timing of the pair-sum kernel (lpmx_profile_enable)
@@ -167,6 +180,9 @@ int stage_out_end(lpmx_handle_t h, void* user, const void* dev, size_t bytes);
 // ---- pair-sum engine (lpmx_kernels.cu) ----
 int make_plan(lpmx_handle_t h, int kind, int n_tgt, int n_src, SumPlan* plan, bool allow_const_stream = true);
 size_t plan_partials_bytes(const SumPlan& p);
+// modelled duration [s] of the ring kernel's launch for `p` (padded work / measured rate of the shape + a fixed ramp): what
+// the constant-bank planner compares its own launches with
+double ring_plan_seconds(const SumPlan& p);
 // tgt: target coordinates of the n_tgt targets of this launch (view indexed from 0);
 // self_idx: compact source index of each target's own particle or -1 (may be nullptr);
 // packed: n_src_pad records of kind_rec(kind) doubles; partials: plan_partials_bytes.
@@ -182,7 +198,18 @@ constexpr int kShapeConstStream = 1000;  // SumPlan::shape of a launch that take
 bool make_const_plan(lpmx_handle_t h, int n_tgt, int n_src, SumPlan* p);
 int launch_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* self_idx, const double* packed, double kappa,
                         double* partials);
-void pick_const_shape(int num_sms, int n_tgt, int* T_out, int* nw_out, int* grid_out);
+constexpr int kCsMaxThreads = 544;  // 16 compute warps + the prefetch warp (T = 3); per T: cs_max_threads, lpmx_const_bank.cuh
+// the split of n_tgt targets x n_src sources between the bank path and the ring kernel with the least modelled time:
+// *T_out targets per thread x *nw_out warps, *ctas_out CTAs per bank launch covering the first *n_const_out targets;
+// returns the modelled seconds of the whole evaluation (bank launches + remainder), *ring_s_out those of the ring kernel alone
+double pick_const_split(lpmx_handle_t h, int num_sms, int n_tgt, int n_src, int* T_out, int* nw_out, int* ctas_out, int* n_const_out,
+                        double* ring_s_out);
+// the two banks (lpmx_const_bank0.cu, lpmx_const_bank1.cu)
+namespace cs { struct CsArgs; }
+cudaError_t cs_bank_launch_0(int T, int grid, int threads, cudaStream_t stream, const cs::CsArgs& a);
+cudaError_t cs_bank_launch_1(int T, int grid, int threads, cudaStream_t stream, const cs::CsArgs& a);
+cudaError_t cs_bank_fill_0(const double* records, cudaStream_t stream);
+cudaError_t cs_bank_fill_1(const double* records, cudaStream_t stream);
 int const_stream_mode(lpmx_handle_t h);
 void const_stream_teardown(lpmx_handle_t h);
 

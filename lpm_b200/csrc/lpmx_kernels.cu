@@ -99,7 +99,9 @@ static int pick_shape(int kind, int num_sms, int n_tgt, int n_sc) {
 
 int make_plan(lpmx_handle_t h, int kind, int n_tgt, int n_src, SumPlan* p, bool allow_const_stream) {
   if (n_tgt < 0 || n_src < 0) return set_error(h, LPMX_ERR_INVALID, "negative size");
-  if (kind == kVel && allow_const_stream && make_const_plan(h, n_tgt, n_src, p)) return LPMX_OK;  // opt-in: sources through the constant bank
+  *p = SumPlan();
+  if (kind == kVel && allow_const_stream && make_const_plan(h, n_tgt, n_src, p)) return LPMX_OK;  // sources through the constant bank
+  *p = SumPlan();
   p->kind = kind;
   p->n_tgt = n_tgt;
   p->n_src_pad = round_up_chunk(n_src);
@@ -130,8 +132,58 @@ int make_plan(lpmx_handle_t h, int kind, int n_tgt, int n_src, SumPlan* p, bool 
   return LPMX_OK;
 }
 
+// Modelled duration of a ring-kernel launch: padded pairs over the measured rate of the shape (velocity kind, one B200:
+// profiles/r1b_tune_shapes.txt, r1h_size_sweep.txt; T = 2 / 1 shapes from the small-mesh rows), stretched by the item
+// quantisation of the persistent grid, plus a fixed ramp (launch, first tile, flush).  Only the constant-bank planner uses it,
+// to decide which targets are better served by which kernel; it does not have to be better than ~10 %.
+double ring_plan_seconds(const SumPlan& p) {
+  if (p.n_tgt <= 0 || p.n_sc <= 0) return 0.0;
+  const double rate = p.T >= 6 ? 1.637e12 : p.T >= 4 ? 1.48e12 : p.T >= 2 ? 1.2e12 : 0.8e12;
+  const long n_items = (long)p.n_tb * p.n_sc;
+  const double per_cta = (double)n_items / p.grid;
+  const double quant = std::ceil(per_cta) / per_cta;
+  return (double)p.n_tgt_pad * (double)p.n_src_pad / rate * quant + 25e-6;
+}
+
 size_t plan_partials_bytes(const SumPlan& p) {
-  return (size_t)p.max_slots * kind_nacc(p.kind) * (size_t)p.n_tgt_pad * sizeof(double);
+  size_t b = (size_t)p.max_slots * kind_nacc(p.kind) * (size_t)p.n_tgt_pad * sizeof(double);
+  // constant-bank plan with a ring remainder: the remainder's slots live behind the bank path's accumulators
+  if (p.shape == kShapeConstStream && p.rem.n_tgt > 0)
+    b += (size_t)p.rem.max_slots * kind_nacc(p.kind) * (size_t)p.rem.n_tgt_pad * sizeof(double);
+  return b;
+}
+
+// the ring kernel on the remainder of a constant-bank plan: targets [cs_n_const, n_tgt) of the launch's views, slots behind
+// the bank path's accumulators (lpmx_const_stream.cu folds them in)
+int launch_ring_remainder(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* self_idx, const double* packed, double kappa,
+                          double* rem_partials) {
+  SumPlan r;
+  r.kind = p.kind;
+  r.shape = p.rem.shape;
+  r.T = p.rem.T;
+  r.tb = p.rem.tb;
+  r.n_tgt = p.rem.n_tgt;
+  r.n_tb = p.rem.n_tb;
+  r.n_src_pad = p.n_src_pad;
+  r.n_sc = p.n_sc;
+  r.grid = p.rem.grid;
+  r.max_slots = p.rem.max_slots;
+  r.n_tgt_pad = p.rem.n_tgt_pad;
+  r.smem_bytes = p.rem.smem_bytes;
+  SumArgs a;
+  a.tgt = tgt;
+  a.tgt.p = tgt.p + (long)p.cs_n_const * tgt.si;
+  a.tgt_map = nullptr;
+  a.self_idx = self_idx ? self_idx + p.cs_n_const : nullptr;
+  a.packed = packed;
+  a.part = rem_partials;
+  a.n_tgt = r.n_tgt;
+  a.n_tb = r.n_tb;
+  a.n_sc = r.n_sc;
+  a.n_tgt_pad = r.n_tgt_pad;
+  a.kappa = kappa;
+  a.aux = 0.0;
+  return kShapes[r.shape].launch(h, r, a);
 }
 
 int launch_pair_sum(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* self_idx, const double* packed,

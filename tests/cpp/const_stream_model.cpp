@@ -1,6 +1,6 @@
 // Host model of pair_sum_const_kernel (lpm_b200/csrc/lpmx_const_stream_body.h -- the body the CUDA kernel runs): every CUDA
-// thread is a loop iteration, the constant bank a plain array, the launch sequence of launch_const_stream (one launch per
-// 640-record batch, alternating halves, zero-padded last batch, `first` on batch 0) restated around it.  Checks the kernel's
+// thread is a loop iteration, the two constant banks plain arrays, the launch sequence of launch_const_stream (one launch per
+// 1 280-record batch, alternating banks, zero-padded last batch, `first` on batch 0) restated around it.  Checks the kernel's
 // indexing -- T targets per thread at a stride of blockDim, padded tail threads, the [3][n_tgt_pad] accumulator layout that
 // the stage kernels read as "slot 0", accumulation across launches, self-pair exclusion by compact index, both target
 // layouts -- against a direct double loop.
@@ -14,7 +14,8 @@
 
 using namespace lpmx::cs;
 
-static std::vector<double> g_bank(2 * kHalf * kRec, 0.0);
+static std::vector<double> g_banks[2] = {std::vector<double>(kBankDoubles, 1e300), std::vector<double>(kBankDoubles, 1e300)};  // the read-ahead record stays poisoned
+static int g_bank = 0;  // the bank the running launch's module sees
 
 struct HostPlatform {
   int tid_, bid_, nt_;
@@ -22,8 +23,9 @@ struct HostPlatform {
   int bid() const { return bid_; }
   int n_threads() const { return nt_; }
   bool any_sync(bool p) const { return p; }  // per-thread here: the checked loop is a superset of the unchecked one
-  double src(int i) const { return g_bank[(size_t)i]; }
+  double src(int i) const { return g_banks[g_bank][(size_t)i]; }
   double rcp_seed(double d) const { return (double)(float)(1.0 / d); }  // 24 good bits; the cubic step must do the rest
+  void accumulate(double* p, double v, bool first) const { *p = first ? v : *p + v; }
 };
 
 template <int T>
@@ -71,8 +73,8 @@ static int run_case(int n_tgt, int n_src, int threads, bool collocated, bool soa
   const int tb = T * threads, grid = (n_tgt + tb - 1) / tb;
   const long n_tgt_pad = (long)grid * tb;
   std::vector<double> acc(3 * (size_t)n_tgt_pad, 1e300);  // poisoned: `first` must overwrite
-  // launch_const_stream: batches of kHalf records, zero-padded, alternating halves
-  const int n_batches = (n_src + kHalf - 1) / kHalf;
+  // launch_const_stream: batches of kBatch records, zero-padded, alternating banks
+  const int n_batches = (n_src + kBatch - 1) / kBatch;
   CsArgs a{};
   a.tgt = tx.data();
   a.tgt_si = soa ? 1 : 3;
@@ -83,13 +85,13 @@ static int run_case(int n_tgt, int n_src, int threads, bool collocated, bool soa
   a.n_tgt = n_tgt;
   a.kappa = kappa;
   for (int b = 0; b < n_batches; ++b) {
-    const int half = b & 1;
-    for (int j = 0; j < kHalf; ++j)
+    g_bank = b & 1;
+    for (int j = 0; j < kBatch; ++j)
       for (int k = 0; k < kRec; ++k) {
-        const long js = (long)b * kHalf + j;
-        g_bank[(size_t)half * kHalf * kRec + (size_t)kRec * j + k] = js < n_src ? src[6 * (size_t)js + k] : 0.0;
+        const long js = (long)b * kBatch + j;
+        g_banks[g_bank][(size_t)kRec * j + k] = js < n_src ? src[6 * (size_t)js + k] : 0.0;
       }
-    a.half = half, a.j0 = b * kHalf, a.first = b == 0;
+    a.j0 = b * kBatch, a.first = b == 0;
     launch<T>(a, grid, threads);
   }
   // direct evaluation: d formed as the kernel forms it (for random points the closest pairs have d ~ 1/N^2, and ANY double
@@ -122,11 +124,11 @@ static int run_case(int n_tgt, int n_src, int threads, bool collocated, bool soa
 
 int main() {
   int bad = 0;
-  bad += run_case<6>(1000, 1500, 64, false, true, 1);    // 3 batches, last one padded; tail threads
-  bad += run_case<5>(1700, 1400, 96, true, true, 2);     // collocated: self pairs in batches 0..2
-  bad += run_case<7>(777, 640, 32, true, false, 3);      // exactly one batch, AoS targets
-  bad += run_case<6>(2000, 2600, 128, true, false, 4);   // 5 batches: both halves reused
-  bad += run_case<4>(129, 700, 32, false, false, 5);
-  bad += run_case<8>(300, 641, 32, true, true, 6);       // second batch holds one record
+  bad += run_case<6>(1000, 3000, 64, false, true, 1);    // 3 batches, last one padded; tail threads
+  bad += run_case<5>(3000, 2800, 96, true, true, 2);     // collocated: self pairs in batches 0..2
+  bad += run_case<7>(777, 1280, 32, true, false, 3);     // exactly one batch, AoS targets
+  bad += run_case<6>(2000, 5200, 128, true, false, 4);   // 5 batches: both banks reused
+  bad += run_case<4>(129, 1400, 32, false, false, 5);
+  bad += run_case<8>(300, 1281, 32, true, true, 6);      // second batch holds one record
   return bad ? 1 : 0;
 }

@@ -1,6 +1,7 @@
-"""Velocity pair sums through the constant bank (lpm_b200/csrc/lpmx_const_stream.cu; automatic for >= 1e6 targets per rank,
-DESIGN.md section 4.1b).  CPU: the launch-shape planner and the kernel body on the host.  GPU: parity with the oracle and with
-the default stream-K kernel, forced onto small meshes (LPMX_CONST_MIN_TARGETS) and at icos-7 on sampled targets."""
+"""Velocity pair sums through the constant banks (lpm_b200/csrc/lpmx_const_stream.cu; automatic from one full wave of the chip
+per rank).  CPU: the planner that splits the targets between the bank path (whole waves) and the ring
+kernel (the remainder), and the kernel body on the host.  GPU: parity with the oracle and with the default stream-K kernel,
+forced onto small meshes (LPMX_CONST_MIN_TARGETS), at icos-7 on sampled targets, and the automatic split at cubed-7."""
 import ctypes
 import os
 
@@ -12,39 +13,51 @@ from lpm_b200 import _lib
 SMS = 148
 
 
-def _shape(n_tgt, sms=SMS):
-    T, nw, grid = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
-    rc = _lib.lib().lpmx_const_stream_shape(sms, n_tgt, ctypes.byref(T), ctypes.byref(nw), ctypes.byref(grid))
+def _split(n_tgt, n_src, sms=SMS):
+    T, nw, ctas, n_const = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    t, tr = ctypes.c_double(), ctypes.c_double()
+    rc = _lib.lib().lpmx_const_stream_split(sms, n_tgt, n_src, ctypes.byref(T), ctypes.byref(nw), ctypes.byref(ctas),
+                                            ctypes.byref(n_const), ctypes.byref(t), ctypes.byref(tr))
     assert rc == 0
-    return T.value, nw.value, grid.value
+    return T.value, nw.value, ctas.value, n_const.value, t.value, tr.value
 
 
-@pytest.mark.parametrize("n_tgt", [229376, 9382, 600742, 2402982, 9611942, 300000, 1201491, 189440, 1, 12345])
-def test_shape_covers_the_targets_and_fits_a_cta(n_tgt):
-    T, nw, grid = _shape(n_tgt)
+@pytest.mark.parametrize("n_tgt,n_src", [(229376, 98304), (9382, 5120), (600742, 327680), (2402982, 1310720), (9611942, 5242880),
+                                         (300000, 300000), (1201491, 1310720), (189440, 98304), (1, 5120), (12345, 6000)])
+def test_split_covers_the_targets_with_whole_waves_plus_a_remainder(n_tgt, n_src):
+    T, nw, ctas, n_const, t, tr = _split(n_tgt, n_src)
     assert T in (5, 6, 7) and nw == 8  # 8 warps = 2 per scheduler; the measured shapes (profiles/r2e_icos8_const_shapes.txt)
     tb = T * nw * 32
-    assert grid * tb >= n_tgt > (grid - 1) * tb
+    assert 0 < n_const <= n_tgt and t > 0 and tr > 0
+    if n_const < n_tgt:  # a remainder follows: the bank path's CTAs are all full and come in whole waves
+        assert n_const == ctas * tb and ctas % SMS == 0
+    else:  # no remainder: the last CTA may be partly filled
+        assert ctas * tb >= n_tgt > (ctas - 1) * tb
 
 
-@pytest.mark.parametrize("n_tgt,least", [(1000000, 0.94), (2402982, 0.97), (9611942, 0.98), (1201491, 0.90)])
-def test_shape_wastes_little_of_the_chip(n_tgt, least):
-    """The sizes the automatic mode takes (>= 1e6 targets per rank): the threshold itself, icos-8 and icos-9 on one GPU, icos-8 on
-    two = icos-9 on eight: fraction of (waves x SMs x targets per CTA) that is work."""
-    T, nw, grid = _shape(n_tgt)
-    waves = -(-grid // SMS)
-    assert n_tgt / (waves * SMS * T * nw * 32) >= least
+def test_split_at_the_headline_sizes():
+    """cubed-7 (BASELINE configs[1]): one wave of T = 6 = 227 328 targets through the banks, 2 048 through the ring kernel, and
+    the model prefers that to the ring kernel alone; icos-8 on one GPU: whole waves + a remainder, also preferred; a rank's
+    share of cubed-7 on two GPUs (114 688 targets) cannot fill one wave and stays with the ring kernel in the automatic mode."""
+    T, nw, ctas, n_const, t, tr = _split(229376, 98304)
+    assert (T, nw, ctas, n_const) == (6, 8, 148, 227328) and t < 0.98 * tr
+    T, nw, ctas, n_const, t, tr = _split(2402982, 1310720)
+    assert n_const >= 0.9 * 2402982 and t < 0.98 * tr
+    T, nw, ctas, n_const, t, tr = _split(114688, 98304)
+    assert 114688 < SMS * 5 * 256  # below the automatic mode's floor (make_const_plan)
 
 
-def test_shape_rejects_bad_arguments():
+def test_split_rejects_bad_arguments():
     T = ctypes.c_int()
-    assert _lib.lib().lpmx_const_stream_shape(0, 10, ctypes.byref(T), ctypes.byref(T), ctypes.byref(T)) != 0
-    assert _lib.lib().lpmx_const_stream_shape(148, 0, ctypes.byref(T), ctypes.byref(T), ctypes.byref(T)) != 0
+    args = [ctypes.byref(T)] * 4 + [None, None]
+    assert _lib.lib().lpmx_const_stream_split(0, 10, 10, *args) != 0
+    assert _lib.lib().lpmx_const_stream_split(148, 0, 10, *args) != 0
+    assert _lib.lib().lpmx_const_stream_split(148, 10, 0, *args) != 0
 
 
 def test_kernel_body_host_model(tmp_path):
     """The body of pair_sum_const_kernel (lpmx_const_stream_body.h) run on the host, one loop iteration per CUDA thread, around
-    a restatement of the launch sequence (640-record batches, alternating halves, zero padding, `first`): T = 4..8, ragged
+    a restatement of the launch sequence (1 280-record batches, alternating banks, zero padding, `first`): T = 4..8, ragged
     target counts, both target layouts, collocated self-pair exclusion -- equal to a direct double loop."""
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -94,10 +107,91 @@ def test_gpu_const_stream_velocity_matches_oracle_and_default_kernel(oracle, mod
 
 
 @pytest.mark.gpu
+def test_gpu_const_stream_automatic_split_at_cubed7():
+    """BASELINE configs[1] as bench.py runs it, nothing forced: the 229 376 targets of the resident solver's evaluation split
+    into one wave through the banks (227 328) and 2 048 through the ring kernel.  One BVERK4 step against the same step with
+    the path switched off (two summation orders of the same terms; the remainder is the tail of the face list), and the launch
+    count shows the path was taken (77 bank launches per evaluation).  The same step against the ORACLE -- every face target,
+    so the remainder too, and 4 096 sampled vertices -- is test_rk4_step_at_cubed7_sampled_targets_against_the_oracle
+    (tests/test_gpu_parity_bve.py), which runs on the automatic mode as well."""
+    from lpm_b200 import gallery
+    from lpm_b200.api import BVESolver, Engine, PolyMesh2d
+    from conftest import field_rel_err
+    m = PolyMesh2d("cubed", 7)
+    f = gallery.RossbyHaurwitz54()
+    f.set_stationary_wave_speed()
+    vz, fz = f(m.vert_xyz), f(m.face_xyz)
+    area, mask = np.ascontiguousarray(m.face_area), np.ascontiguousarray(m.face_mask)
+    states, counts = [], []
+    for mode in (0, -1):
+        e = Engine(0)
+        try:
+            e.pair_sum_const_stream(mode)
+            s = BVESolver(e, m.n_verts, m.n_faces)
+            s.set_state(m.vert_xyz, vz, None, m.face_xyz, fz, None, area, mask)
+            s.init_velocity()
+            l0 = e.launch_count()
+            s.advance(0.003, 2 * np.pi, 1)
+            counts.append(e.launch_count() - l0)
+            out = [np.empty((m.n_verts, 3)), np.empty(m.n_verts), np.empty((m.n_verts, 3)), np.empty((m.n_faces, 3)),
+                   np.empty(m.n_faces), np.empty((m.n_faces, 3))]
+            s.get_state(*out)
+            s.close()
+            states.append(out)
+        finally:
+            e.close()
+    assert counts[0] < 20 and counts[1] >= 4 * 77, counts
+    a, b = states
+    for k, tol in ((0, 1e-13), (1, 1e-12), (2, 1e-12), (3, 1e-13), (4, 1e-12), (5, 1e-12)):
+        assert field_rel_err(b[k], a[k]) <= tol, (k, field_rel_err(b[k], a[k]))
+    tail = slice(m.n_faces - 2048, m.n_faces)  # the ring kernel's share
+    assert field_rel_err(b[5][tail], a[5][tail]) <= 1e-12 and np.abs(b[5][tail]).max() > 0
+
+
+@pytest.mark.gpu
+def test_gpu_const_stream_captured_sequence_is_bit_identical(monkeypatch):
+    """The launch sequence of an evaluation replayed from its CUDA graph (captured the second time a sequence comes by) against
+    the same sequence enqueued launch by launch (LPMX_CONST_GRAPH=0), with and without the prefetch warp: the same kernels on
+    the same data in the same order -- bit-identical states after three BVERK4 steps, and the same launch counts."""
+    from lpm_b200 import gallery
+    from lpm_b200.api import BVESolver, Engine, PolyMesh2d
+    monkeypatch.setenv("LPMX_CONST_MIN_TARGETS", "1")
+    m = PolyMesh2d("cubed", 5)
+    f = gallery.RossbyHaurwitz54()
+    f.set_stationary_wave_speed()
+    vz, fz = f(m.vert_xyz), f(m.face_xyz)
+    area, mask = np.ascontiguousarray(m.face_area), np.ascontiguousarray(m.face_mask)
+    runs = []
+    for graph, prefetch in (("0", "64"), ("1", "64"), ("1", "0")):
+        monkeypatch.setenv("LPMX_CONST_GRAPH", graph)
+        monkeypatch.setenv("LPMX_CONST_PREFETCH", prefetch)
+        e = Engine(0)
+        try:
+            e.pair_sum_const_stream(1)
+            s = BVESolver(e, m.n_verts, m.n_faces)
+            s.set_state(m.vert_xyz, vz, None, m.face_xyz, fz, None, area, mask)
+            s.init_velocity()
+            l0, c0 = e.launch_count(), e.const_stream_launch_count()
+            for _ in range(3):
+                s.advance(0.01, 2 * np.pi, 1)
+            counts = (e.launch_count() - l0, e.const_stream_launch_count() - c0)
+            out = [np.empty((m.n_verts, 3)), np.empty(m.n_verts), np.empty((m.n_verts, 3)), np.empty((m.n_faces, 3)),
+                   np.empty(m.n_faces), np.empty((m.n_faces, 3))]
+            s.get_state(*out)
+            s.close()
+            runs.append((counts, out))
+        finally:
+            e.close()
+    assert runs[0][0] == runs[1][0] == runs[2][0] and runs[0][0][1] >= 12 * 5
+    for k in range(6):
+        assert np.array_equal(runs[0][1][k], runs[1][1][k]) and np.array_equal(runs[0][1][k], runs[2][1][k]), k
+
+
+@pytest.mark.gpu
 def test_gpu_const_stream_at_icos7_sampled_targets(oracle, monkeypatch):
-    """600 742 targets x 327 680 leaf sources through the constant bank (forced: the automatic mode starts at 1e6 targets),
-    512 launches of 640 sources with the bank halves refilled behind them: 2 048 sampled vertex targets against the oracle, all
-    vertex targets against the default kernel, and a second handle on the same device keeps the default kernel (one bank)."""
+    """600 742 targets x 327 680 leaf sources through the constant banks, 256 launches of 1 280 sources with the other bank
+    refilled behind them: 2 048 sampled vertex targets against the oracle, all vertex targets against the default kernel, and a
+    second handle on the same device keeps the default kernel (one pair of banks per device)."""
     from lpm_b200 import gallery
     from lpm_b200.api import Engine, PolyMesh2d
     from conftest import field_rel_err
@@ -116,7 +210,7 @@ def test_gpu_const_stream_at_icos7_sampled_targets(oracle, monkeypatch):
         got2 = e2.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask)  # bank owned by e1: ring kernel
         n2 = e2.launch_count() - l2
         got0 = e0.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask)
-        assert n1 > 500 and n2 < 20
+        assert n1 > 250 and n2 < 20
         assert np.array_equal(got2, got0)
         idx = np.sort(np.random.default_rng(5).choice(m.n_verts, 2048, replace=False))
         ref = oracle.bve_velocity(m.vert_xyz[idx], m.face_xyz, fz, m.face_area, m.face_mask)

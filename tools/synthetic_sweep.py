@@ -60,6 +60,9 @@ def main():
     ap.add_argument("--sizes", default="1e4,3e4,1e5,3e5,1e6")
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--dt", type=float, default=1e-4)
+    ap.add_argument("--eval-only-above", type=float, default=4e6,
+                    help="sizes above this time ONE velocity evaluation (BVESphere::init_velocity on the resident state) instead of "
+                         "RK4 steps: N = 1e7 is 1e14 interactions, a minute per evaluation on one GPU")
     args = ap.parse_args()
     import torch
     from lpm_b200.api import BVESolver, Engine
@@ -81,13 +84,38 @@ def main():
         mask = np.zeros(n, dtype=np.uint8)
         s = BVESolver(eng, 0, n)
         s.set_state(None, None, None, x, zeta, None, area, mask)
-        s.init_velocity()
+        eval_only = n > args.eval_only_above
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record(stream)
+            s.init_velocity()
+            v1.record(stream)
         eng.sync()
+        eval_ms = v0.elapsed_time(v1)
         vel = np.zeros((n, 3))
         s.get_state(None, None, None, None, None, vel)
         err, bound = subset_check(x, zeta, area, vel) if rank == 0 else (0.0, 0.0)
         if dist is not None:
             dist.barrier()  # rank 0 alone ran the host-side check: do not let the others wait for it inside a kernel
+        if eval_only:
+            if dist is not None:
+                t = torch.tensor([eval_ms], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                eval_ms = float(t.item())
+            if rank == 0:
+                rate = n * (n - 1.0) / (eval_ms * 1e-3)
+                print(json.dumps({"workload": "synthetic_collocated", "n_particles": n, "n_gpus": world, "timed": "one velocity evaluation "
+                                  "(init_velocity on the resident state, first call)", "eval_ms": eval_ms,
+                                  "interactions_per_s": rate, "alg_tflops": rate * 24e-12,
+                                  "frac_of_measured_fp64_peak_per_gpu": rate * 24e-12 / (peak * world),
+                                  "fp64_peak_tflops_measured": peak, "bank_launches": eng.const_stream_launch_count(),
+                                  "velocity_rel_err_vs_float128_subset": err,
+                                  "conditioning_bound_of_1_minus_xdoty": bound}), flush=True)
+            s.close()
+            continue
         s.advance(args.dt, 2 * np.pi, 1)  # warm-up step
         eng.sync()
         if dist is not None:
