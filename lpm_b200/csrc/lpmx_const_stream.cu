@@ -39,7 +39,7 @@ namespace lpmx {
 
 // lpmx_kernels.cu
 int launch_ring_remainder(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* self_idx, const double* packed, double kappa,
-                          double* rem_partials);
+                          double* rem_partials, const int* tgt_map);
 
 namespace {
 
@@ -218,8 +218,8 @@ bool make_const_plan(lpmx_handle_t h, int n_tgt, int n_src, SumPlan* p) {
 
 // the launch sequence of one evaluation, enqueued on the handle's two streams (eagerly, or into a stream capture)
 static int enqueue_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* self_idx, const double* packed,
-                                double kappa, double* partials, int mode, int pf_stride, void* stage_v, long* n_launches,
-                                long* n_bank_launches) {
+                                double kappa, double* partials, const int* tgt_map, int mode, int pf_stride, void* stage_v,
+                                long* n_launches, long* n_bank_launches) {
   const long n_batches = ((long)p.n_src_pad + kCsBatch - 1) / kCsBatch;
   const long n_out = n_batches * kCsBatch;
   const double* stage = (const double*)stage_v;
@@ -241,7 +241,7 @@ static int enqueue_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt,
   const bool single_wave = p.cs_ctas <= h->num_sms * (fts ? per_sm : 1);
   const int pf = single_wave ? pf_stride : 0;
   const int threads = p.tb / p.T + (pf > 0 ? 32 : 0);
-  cudaStream_t cps = mode == 1 ? h->copy_stream : h->stream;
+  cudaStream_t cps = mode == 1 ? h->cs_stream : h->stream;
   // refill of bank (b & 1) with batch b; in the overlapped mode it waits for the launch that last read that bank
   auto fill_batch = [&](long b) -> int {
     const int bank = (int)(b & 1);
@@ -259,11 +259,12 @@ static int enqueue_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt,
   }
   // the remainder first: the ring kernel runs while the first banks are being filled
   double* rem_partials = partials + 3 * (size_t)p.n_tgt_pad;
-  if (p.rem.n_tgt > 0) LPMX_TRY(launch_ring_remainder(h, p, tgt, self_idx, packed, kappa, rem_partials));
+  if (p.rem.n_tgt > 0) LPMX_TRY(launch_ring_remainder(h, p, tgt, self_idx, packed, kappa, rem_partials, tgt_map));
   CsArgs a;
   a.tgt = tgt.p;
   a.tgt_si = tgt.si;
   a.tgt_sk = tgt.sk;
+  a.tgt_map = tgt_map;
   a.self_idx = self_idx;
   a.acc = partials;
   a.n_tgt_pad = p.n_tgt_pad;
@@ -307,12 +308,12 @@ static int enqueue_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt,
 // and from then on it is ONE cudaGraphLaunch.  LPMX_CONST_GRAPH=0 keeps the eager sequence.
 namespace {
 struct CsGraphKey {
-  const void *tgt, *self_idx, *packed, *partials, *stage;
+  const void *tgt, *self_idx, *packed, *partials, *stage, *tgt_map;
   long si, sk, n_tgt_pad, rem_pad;
   int T, tb, ctas, n_const, n_tgt, n_src_pad, rem_n, rem_shape, rem_grid, mode, pf;
   double kappa;
   bool operator==(const CsGraphKey& o) const {
-    return tgt == o.tgt && self_idx == o.self_idx && packed == o.packed && partials == o.partials && stage == o.stage && si == o.si &&
+    return tgt == o.tgt && self_idx == o.self_idx && packed == o.packed && partials == o.partials && stage == o.stage && tgt_map == o.tgt_map && si == o.si &&
            sk == o.sk && n_tgt_pad == o.n_tgt_pad && rem_pad == o.rem_pad && T == o.T && tb == o.tb && ctas == o.ctas &&
            n_const == o.n_const && n_tgt == o.n_tgt && n_src_pad == o.n_src_pad && rem_n == o.rem_n && rem_shape == o.rem_shape &&
            rem_grid == o.rem_grid && mode == o.mode && pf == o.pf && kappa == o.kappa;
@@ -333,8 +334,9 @@ constexpr size_t kCsMaxGraphs = 16;
 }  // namespace
 
 int launch_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* self_idx, const double* packed, double kappa,
-                        double* partials) {
+                        double* partials, const int* tgt_map) {
   const int mode = const_stream_mode(h) == 2 ? 2 : 1;
+  if (mode == 1 && !h->cs_stream) LPMX_CUDA(h, cudaStreamCreateWithFlags(&h->cs_stream, cudaStreamNonBlocking));
   // read per call (two getenv per evaluation) so that tests can switch them within one process
   const int pf_stride = [] {  // LPMX_CONST_PREFETCH = bytes between the prefetch warp's loads (0: off); default one per 128 B (r2r: 64 B 51.9 ms, 128 B 51.4 ms per step at cubed-7)
     const char* e = getenv("LPMX_CONST_PREFETCH");
@@ -349,11 +351,11 @@ int launch_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const i
   void* stage_v = nullptr;
   LPMX_TRY(dev_buffer(h, "const_stage", sizeof(double) * kCsRec * (size_t)(n_batches * kCsBatch), &stage_v));
   long nl = 0, nb = 0;
-  if (!use_graphs) return enqueue_const_stream(h, p, tgt, self_idx, packed, kappa, partials, mode, pf_stride, stage_v, &nl, &nb);
+  if (!use_graphs) return enqueue_const_stream(h, p, tgt, self_idx, packed, kappa, partials, tgt_map, mode, pf_stride, stage_v, &nl, &nb);
   if (!h->cs_graph_cache) h->cs_graph_cache = new CsGraphCache();
   CsGraphCache* cache = (CsGraphCache*)h->cs_graph_cache;
-  if (cache->broken) return enqueue_const_stream(h, p, tgt, self_idx, packed, kappa, partials, mode, pf_stride, stage_v, &nl, &nb);
-  CsGraphKey key{tgt.p, self_idx, packed, partials, stage_v, tgt.si, tgt.sk, p.n_tgt_pad, p.rem.n_tgt_pad, p.T, p.tb, p.cs_ctas,
+  if (cache->broken) return enqueue_const_stream(h, p, tgt, self_idx, packed, kappa, partials, tgt_map, mode, pf_stride, stage_v, &nl, &nb);
+  CsGraphKey key{tgt.p, self_idx, packed, partials, stage_v, tgt_map, tgt.si, tgt.sk, p.n_tgt_pad, p.rem.n_tgt_pad, p.T, p.tb, p.cs_ctas,
                  p.cs_n_const, p.n_tgt, p.n_src_pad, p.rem.n_tgt, p.rem.shape, p.rem.grid, mode, pf_stride, kappa};
   CsGraph* g = nullptr;
   for (auto& e : cache->entries)
@@ -372,7 +374,7 @@ int launch_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const i
     e.key = key;
     e.tick = ++cache->tick;
     cache->entries.push_back(e);
-    return enqueue_const_stream(h, p, tgt, self_idx, packed, kappa, partials, mode, pf_stride, stage_v, &nl, &nb);
+    return enqueue_const_stream(h, p, tgt, self_idx, packed, kappa, partials, tgt_map, mode, pf_stride, stage_v, &nl, &nb);
   }
   g->tick = ++cache->tick;
   if (!g->exec) {
@@ -381,7 +383,7 @@ int launch_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const i
     cudaError_t ce = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
     int rc = LPMX_OK;
     if (ce == cudaSuccess) {
-      rc = enqueue_const_stream(h, p, tgt, self_idx, packed, kappa, partials, mode, pf_stride, stage_v, &g->n_launches, &g->n_bank_launches);
+      rc = enqueue_const_stream(h, p, tgt, self_idx, packed, kappa, partials, tgt_map, mode, pf_stride, stage_v, &g->n_launches, &g->n_bank_launches);
       ce = cudaStreamEndCapture(h->stream, &graph);
     }
     h->launches = launches0, h->cs_launches = cs0;  // nothing has run yet
@@ -393,7 +395,7 @@ int launch_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const i
       h->err.clear();
       g->exec = nullptr;
       cache->broken = true;
-      return enqueue_const_stream(h, p, tgt, self_idx, packed, kappa, partials, mode, pf_stride, stage_v, &nl, &nb);
+      return enqueue_const_stream(h, p, tgt, self_idx, packed, kappa, partials, tgt_map, mode, pf_stride, stage_v, &nl, &nb);
     }
   }
   LPMX_CUDA(h, cudaGraphLaunch(g->exec, h->stream));
@@ -410,6 +412,10 @@ void const_stream_teardown(lpmx_handle_t h) {
       if (e.exec) cudaGraphExecDestroy(e.exec);
     delete cache;
     h->cs_graph_cache = nullptr;
+  }
+  if (h->cs_stream) {
+    cudaStreamDestroy(h->cs_stream);
+    h->cs_stream = nullptr;
   }
   for (int i = 0; i < 5; ++i)
     if (h->cs_events[i]) {

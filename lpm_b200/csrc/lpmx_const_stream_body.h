@@ -24,8 +24,10 @@ constexpr int kRec = 6;       // doubles per record {y0, y1, y2, G*y0, G*y1, G*y
 constexpr int kBankDoubles = (kBatch + 1) * kRec;  // + one record the pipelined loop reads ahead into and never uses
 
 struct CsArgs {
-  const double* tgt;    // this launch's targets, element (i, k) at tgt[i * tgt_si + k * tgt_sk], indexed from 0
+  const double* tgt;    // target coordinates, element (i, k) at tgt[i * tgt_si + k * tgt_sk], indexed from 0
   long tgt_si, tgt_sk;
+  const int* tgt_map;   // optional: target tg of this launch is element tgt_map[tg] of `tgt` / `self_idx` (a sharded solver's
+                        // index list); null: element tg itself.  The accumulators are indexed by tg either way.
   const int* self_idx;  // compact source index of each target's own particle, or -1 (may be null)
   double* acc;          // [3][n_tgt_pad]
   long n_tgt_pad;
@@ -79,12 +81,13 @@ LPMX_CS_HD void body(P& pf, const CsArgs& a) {
   for (int t = 0; t < T; ++t) {
     const long tg = base_t + (long)t * lanes;  // < n_tgt_pad by construction of the grid
     const bool valid = tg < a.n_tgt;
+    const long ge = (valid && a.tgt_map) ? (long)a.tgt_map[tg] : tg;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      x[t][k] = valid ? a.tgt[tg * a.tgt_si + k * a.tgt_sk] : 0.0;  // a zero target sees d = kappa: finite, never read back
+      x[t][k] = valid ? a.tgt[ge * a.tgt_si + k * a.tgt_sk] : 0.0;  // a zero target sees d = kappa: finite, never read back
       acc[t][k] = 0.0;  // two-level summation: this launch's 1 280 terms start from zero (see the store below)
     }
-    self[t] = (valid && a.self_idx) ? a.self_idx[tg] : -1;
+    self[t] = (valid && a.self_idx) ? a.self_idx[ge] : -1;
     hit |= (unsigned)(self[t] - a.j0) < (unsigned)kBatch;
   }
   if (pf.any_sync(hit))

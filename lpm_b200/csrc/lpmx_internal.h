@@ -125,6 +125,7 @@ struct lpmx_handle_s {
   int num_sms = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t cs_stream = nullptr;  // bank refills of the constant-bank path (the copy stream may be busy with an exchange)
   std::string err;
   long launches = 0;
   int rank = 0, world = 1;
@@ -197,7 +198,7 @@ constexpr int kShapeConstStream = 1000;  // SumPlan::shape of a launch that take
 // fills *p and returns true when the path is switched on and the launch is large enough for it (kVel only)
 bool make_const_plan(lpmx_handle_t h, int n_tgt, int n_src, SumPlan* p);
 int launch_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* self_idx, const double* packed, double kappa,
-                        double* partials);
+                        double* partials, const int* tgt_map);
 constexpr int kCsMaxThreads = 544;  // 16 compute warps + the prefetch warp (T = 3); per T: cs_max_threads, lpmx_const_bank.cuh
 // the split of n_tgt targets x n_src sources between the bank path and the ring kernel with the least modelled time:
 // *T_out targets per thread x *nw_out warps, *ctas_out CTAs per bank launch covering the first *n_const_out targets;

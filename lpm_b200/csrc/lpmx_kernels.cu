@@ -156,7 +156,7 @@ size_t plan_partials_bytes(const SumPlan& p) {
 // the ring kernel on the remainder of a constant-bank plan: targets [cs_n_const, n_tgt) of the launch's views, slots behind
 // the bank path's accumulators (lpmx_const_stream.cu folds them in)
 int launch_ring_remainder(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* self_idx, const double* packed, double kappa,
-                          double* rem_partials) {
+                          double* rem_partials, const int* tgt_map) {
   SumPlan r;
   r.kind = p.kind;
   r.shape = p.rem.shape;
@@ -172,9 +172,14 @@ int launch_ring_remainder(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const
   r.smem_bytes = p.rem.smem_bytes;
   SumArgs a;
   a.tgt = tgt;
-  a.tgt.p = tgt.p + (long)p.cs_n_const * tgt.si;
-  a.tgt_map = nullptr;
-  a.self_idx = self_idx ? self_idx + p.cs_n_const : nullptr;
+  if (tgt_map) {  // the list's tail; the views stay (the list holds indices into them)
+    a.tgt_map = tgt_map + p.cs_n_const;
+    a.self_idx = self_idx;
+  } else {
+    a.tgt.p = tgt.p + (long)p.cs_n_const * tgt.si;
+    a.tgt_map = nullptr;
+    a.self_idx = self_idx ? self_idx + p.cs_n_const : nullptr;
+  }
   a.packed = packed;
   a.part = rem_partials;
   a.n_tgt = r.n_tgt;
@@ -194,8 +199,6 @@ int launch_pair_sum(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* 
     LPMX_CUDA(h, cudaMemsetAsync(partials, 0, plan_partials_bytes(p), h->stream));
     return LPMX_OK;
   }
-  if (tgt_map && p.shape == kShapeConstStream)
-    return set_error(h, LPMX_ERR_STATE, "the constant-bank path takes no target index list (plan made with allow_const_stream)");
   SumArgs a;
   a.tgt = tgt;
   a.tgt_map = tgt_map;
@@ -209,7 +212,7 @@ int launch_pair_sum(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* 
   a.kappa = kappa;
   a.aux = aux;
   const bool cs = p.shape == kShapeConstStream;
-  if (!h->profile) return cs ? launch_const_stream(h, p, tgt, self_idx, packed, kappa, partials) : kShapes[p.shape].launch(h, p, a);
+  if (!h->profile) return cs ? launch_const_stream(h, p, tgt, self_idx, packed, kappa, partials, tgt_map) : kShapes[p.shape].launch(h, p, a);
   if (h->prof_used == h->prof_events.size()) {
     cudaEvent_t e0, e1;
     LPMX_CUDA(h, cudaEventCreate(&e0));
@@ -218,7 +221,7 @@ int launch_pair_sum(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* 
   }
   auto& ev = h->prof_events[h->prof_used++];
   LPMX_CUDA(h, cudaEventRecord(ev.first, h->stream));
-  const int rc = cs ? launch_const_stream(h, p, tgt, self_idx, packed, kappa, partials) : kShapes[p.shape].launch(h, p, a);
+  const int rc = cs ? launch_const_stream(h, p, tgt, self_idx, packed, kappa, partials, tgt_map) : kShapes[p.shape].launch(h, p, a);
   LPMX_CUDA(h, cudaEventRecord(ev.second, h->stream));
   h->prof_pairs += (double)p.n_tgt * (double)p.n_src_pad;
   return rc;

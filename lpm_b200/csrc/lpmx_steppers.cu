@@ -706,7 +706,7 @@ static int prologue_lists(SolverState* st, Launch launch) {
 
 static int make_list_plans(SolverState* st, int kind, SumPlan* plans) {
   for (int part = 0; part < 2; ++part)
-    LPMX_TRY(make_plan(st->h, kind, st->n_part[part], st->n_leaf, &plans[part], /*allow_const_stream=*/st->gid[part] == nullptr));
+    LPMX_TRY(make_plan(st->h, kind, st->n_part[part], st->n_leaf, &plans[part]));
   return LPMX_OK;
 }
 

@@ -5,6 +5,7 @@
 // the stage kernels read as "slot 0", accumulation across launches, self-pair exclusion by compact index, both target
 // layouts -- against a direct double loop.
 //   g++ -O2 -std=c++17 -ffp-contract=off -I lpm_b200/csrc tests/cpp/const_stream_model.cpp -o model && ./model
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <random>
@@ -38,7 +39,7 @@ static void launch(const CsArgs& a, int grid, int threads) {
 }
 
 template <int T>
-static int run_case(int n_tgt, int n_src, int threads, bool collocated, bool soa, unsigned seed) {
+static int run_case(int n_tgt, int n_src, int threads, bool collocated, bool soa, unsigned seed, bool mapped = false) {
   std::mt19937_64 rng(seed);
   std::normal_distribution<double> nd;
   auto unit = [&](double* p) {
@@ -69,6 +70,11 @@ static int run_case(int n_tgt, int n_src, int threads, bool collocated, bool soa
     }
     for (int k = 0; k < 3; ++k) tx[soa ? (size_t)k * n_tgt + i : 3 * (size_t)i + k] = x[k];
   }
+  // mapped: the launch's targets are an index list (a sharded solver's): target tg of the launch is element map[tg] of the
+  // views; the accumulators stay in launch order
+  std::vector<int> map(n_tgt);
+  for (int i = 0; i < n_tgt; ++i) map[i] = i;
+  if (mapped) std::shuffle(map.begin(), map.end(), rng);
   const double kappa = collocated ? 1.0 : 1.0 + 1e-4;
   const int tb = T * threads, grid = (n_tgt + tb - 1) / tb;
   const long n_tgt_pad = (long)grid * tb;
@@ -79,6 +85,7 @@ static int run_case(int n_tgt, int n_src, int threads, bool collocated, bool soa
   a.tgt = tx.data();
   a.tgt_si = soa ? 1 : 3;
   a.tgt_sk = soa ? n_tgt : 1;
+  a.tgt_map = mapped ? map.data() : nullptr;
   a.self_idx = collocated ? self.data() : nullptr;
   a.acc = acc.data();
   a.n_tgt_pad = n_tgt_pad;
@@ -98,7 +105,8 @@ static int run_case(int n_tgt, int n_src, int threads, bool collocated, bool soa
   // evaluation of 1 - x.y carries a relative error of 2^-53 / d there -- DESIGN.md section 7 -- so a long-double d would
   // measure that conditioning, not the kernel), the reciprocal exact, the terms added in source order
   double worst = 0, scale = 0;
-  for (int i = 0; i < n_tgt; ++i) {
+  for (int li = 0; li < n_tgt; ++li) {
+    const int i = map[li];
     double m[3] = {0, 0, 0};
     const double x[3] = {tx[soa ? i : 3 * (size_t)i], tx[soa ? (size_t)n_tgt + i : 3 * (size_t)i + 1],
                          tx[soa ? 2 * (size_t)n_tgt + i : 3 * (size_t)i + 2]};
@@ -110,15 +118,15 @@ static int run_case(int n_tgt, int n_src, int threads, bool collocated, bool soa
       for (int k = 0; k < 3; ++k) m[k] = std::fma(r, y[3 + k], m[k]);
     }
     for (int k = 0; k < 3; ++k) {
-      worst = std::fmax(worst, std::fabs(acc[(size_t)k * n_tgt_pad + i] - m[k]));
+      worst = std::fmax(worst, std::fabs(acc[(size_t)k * n_tgt_pad + li] - m[k]));
       scale = std::fmax(scale, std::fabs(m[k]));
     }
   }
   int bad = !(worst <= 1e-13 * scale);
   for (long i = n_tgt; i < n_tgt_pad; ++i)  // padded targets: finite, never poison
     for (int k = 0; k < 3; ++k) bad += !std::isfinite(acc[(size_t)k * n_tgt_pad + i]) || acc[(size_t)k * n_tgt_pad + i] == 1e300;
-  std::printf("T=%d n_tgt=%d n_src=%d threads=%d colloc=%d soa=%d: rel err %.2e %s\n", T, n_tgt, n_src, threads, (int)collocated,
-              (int)soa, worst / scale, bad ? "FAILED" : "ok");
+  std::printf("T=%d n_tgt=%d n_src=%d threads=%d colloc=%d soa=%d mapped=%d: rel err %.2e %s\n", T, n_tgt, n_src, threads,
+              (int)collocated, (int)soa, (int)mapped, worst / scale, bad ? "FAILED" : "ok");
   return bad;
 }
 
@@ -130,5 +138,7 @@ int main() {
   bad += run_case<6>(2000, 5200, 128, true, false, 4);   // 5 batches: both banks reused
   bad += run_case<4>(129, 1400, 32, false, false, 5);
   bad += run_case<8>(300, 1281, 32, true, true, 6);      // second batch holds one record
+  bad += run_case<6>(1500, 2700, 64, true, true, 7, true);   // an index list of targets, collocated
+  bad += run_case<5>(900, 1300, 32, false, false, 8, true);
   return bad ? 1 : 0;
 }

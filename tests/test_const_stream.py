@@ -58,14 +58,14 @@ def test_split_rejects_bad_arguments():
 def test_kernel_body_host_model(tmp_path):
     """The body of pair_sum_const_kernel (lpmx_const_stream_body.h) run on the host, one loop iteration per CUDA thread, around
     a restatement of the launch sequence (1 280-record batches, alternating banks, zero padding, `first`): T = 4..8, ragged
-    target counts, both target layouts, collocated self-pair exclusion -- equal to a direct double loop."""
+    target counts, both target layouts, index lists of targets, collocated self-pair exclusion -- equal to a direct double loop."""
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = str(tmp_path / "const_stream_model")
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I", os.path.join(root, "lpm_b200", "csrc"),
                     os.path.join(root, "tests", "cpp", "const_stream_model.cpp"), "-o", exe], check=True)
     p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
-    assert p.returncode == 0 and p.stdout.count(" ok") == 6 and "FAILED" not in p.stdout, p.stdout + p.stderr
+    assert p.returncode == 0 and p.stdout.count(" ok") == 8 and "FAILED" not in p.stdout, p.stdout + p.stderr
 
 
 @pytest.mark.gpu
@@ -146,6 +146,40 @@ def test_gpu_const_stream_automatic_split_at_cubed7():
         assert field_rel_err(b[k], a[k]) <= tol, (k, field_rel_err(b[k], a[k]))
     tail = slice(m.n_faces - 2048, m.n_faces)  # the ring kernel's share
     assert field_rel_err(b[5][tail], a[5][tail]) <= 1e-12 and np.abs(b[5][tail]).max() > 0
+
+
+@pytest.mark.gpu
+def test_gpu_const_stream_with_split_target_lists(oracle, monkeypatch):
+    """What a rank of a multi-GPU run does on a large mesh -- list A (its leaf faces) and list B (vertices and divided faces)
+    as index lists, each through the banks + the ring remainder -- forced onto one GPU and a small mesh (LPMX_FORCE_SPLIT=1,
+    LPMX_CONST_MIN_TARGETS=1): two BVERK4 steps against the oracle, and the bank launches are counted."""
+    from lpm_b200 import gallery
+    from lpm_b200.api import Engine, PolyMesh2d
+    from conftest import field_rel_err
+    monkeypatch.setenv("LPMX_FORCE_SPLIT", "1")
+    monkeypatch.setenv("LPMX_CONST_MIN_TARGETS", "1")
+    for seed, depth in (("cubed", 5), ("icos", 5)):
+        m = PolyMesh2d(seed, depth)
+        f = gallery.RossbyHaurwitz54()
+        f.set_stationary_wave_speed()
+        leaf = m.face_mask == 0
+        fz = f(m.face_xyz)
+        vu = oracle.bve_velocity(m.vert_xyz, m.face_xyz, fz, m.face_area, m.face_mask)
+        fu = oracle.bve_velocity(None, m.face_xyz, fz, m.face_area, m.face_mask, collocated=True)
+        fu[~leaf] = 0.0
+        ref = [m.vert_xyz.copy(), f(m.vert_xyz), vu, m.face_xyz.copy(), fz.copy(), fu]
+        got = [a.copy() for a in ref]
+        oracle.bve_rk4_step(0.01, 2 * np.pi, *ref, m.face_area, m.face_mask, n_steps=2)
+        e = Engine(0)
+        try:
+            e.pair_sum_const_stream(1)
+            c0 = e.const_stream_launch_count()
+            e.bve_rk4_step(0.01, 2 * np.pi, *got, m.face_area, m.face_mask, n_steps=2)
+            assert e.const_stream_launch_count() - c0 >= 2 * 4 * 2 * 4  # 2 steps x 4 evaluations x 2 lists x >= 4 banks
+        finally:
+            e.close()
+        for k, sel, tol in ((0, None, 1e-12), (1, None, 1e-10), (2, None, 1e-12), (3, leaf, 1e-12), (4, leaf, 1e-10), (5, leaf, 1e-12)):
+            assert field_rel_err(got[k], ref[k], sel) <= tol, (seed, k, field_rel_err(got[k], ref[k], sel))
 
 
 @pytest.mark.gpu
