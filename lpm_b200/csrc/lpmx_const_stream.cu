@@ -164,7 +164,7 @@ double pick_const_split(lpmx_handle_t h, int num_sms, int n_tgt, int n_src, int*
       const long n_rem = n_tgt - n_const;
       if (n_rem > 0) {
         SumPlan r;
-        if (make_plan(h, kVel, (int)n_rem, n_src, &r, false) != LPMX_OK) continue;
+        if (make_best_ring_plan(h, (int)n_rem, n_src, &r) != LPMX_OK) continue;
         t += ring_plan_seconds(r) + 4e-6;  // + the fold
       }
       if (best < 0 || t < best) {
@@ -209,7 +209,7 @@ bool make_const_plan(lpmx_handle_t h, int n_tgt, int n_src, SumPlan* p) {
   p->smem_bytes = 0;
   if (n_const < n_tgt) {
     SumPlan r;
-    if (make_plan(h, kVel, n_tgt - n_const, n_src, &r, false) != LPMX_OK) return false;
+    if (make_best_ring_plan(h, n_tgt - n_const, n_src, &r) != LPMX_OK) return false;
     p->rem.shape = r.shape, p->rem.T = r.T, p->rem.tb = r.tb, p->rem.n_tgt = r.n_tgt, p->rem.n_tb = r.n_tb, p->rem.grid = r.grid;
     p->rem.max_slots = r.max_slots, p->rem.n_tgt_pad = r.n_tgt_pad, p->rem.smem_bytes = r.smem_bytes;
   }

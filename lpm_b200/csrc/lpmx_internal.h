@@ -179,7 +179,8 @@ int stage_out_begin(lpmx_handle_t h, const char* name, void* user, size_t bytes,
 int stage_out_end(lpmx_handle_t h, void* user, const void* dev, size_t bytes);
 
 // ---- pair-sum engine (lpmx_kernels.cu) ----
-int make_plan(lpmx_handle_t h, int kind, int n_tgt, int n_src, SumPlan* plan, bool allow_const_stream = true);
+int make_plan(lpmx_handle_t h, int kind, int n_tgt, int n_src, SumPlan* plan, bool allow_const_stream = true, int force_T = 0);
+int make_best_ring_plan(lpmx_handle_t h, int n_tgt, int n_src, SumPlan* plan);  // velocity kind, least modelled time over the shapes
 size_t plan_partials_bytes(const SumPlan& p);
 // modelled duration [s] of the ring kernel's launch for `p` (padded work / measured rate of the shape + a fixed ramp): what
 // the constant-bank planner compares its own launches with

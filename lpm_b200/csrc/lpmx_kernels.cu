@@ -29,6 +29,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
+#include <initializer_list>
 
 #include "lpmx_internal.h"
 #include "lpmx_pair_kernel.cuh"
@@ -97,7 +98,7 @@ static int pick_shape(int kind, int num_sms, int n_tgt, int n_sc) {
   return last;
 }
 
-int make_plan(lpmx_handle_t h, int kind, int n_tgt, int n_src, SumPlan* p, bool allow_const_stream) {
+int make_plan(lpmx_handle_t h, int kind, int n_tgt, int n_src, SumPlan* p, bool allow_const_stream, int force_T) {
   if (n_tgt < 0 || n_src < 0) return set_error(h, LPMX_ERR_INVALID, "negative size");
   *p = SumPlan();
   if (kind == kVel && allow_const_stream && make_const_plan(h, n_tgt, n_src, p)) return LPMX_OK;  // sources through the constant bank
@@ -106,7 +107,13 @@ int make_plan(lpmx_handle_t h, int kind, int n_tgt, int n_src, SumPlan* p, bool 
   p->n_tgt = n_tgt;
   p->n_src_pad = round_up_chunk(n_src);
   p->n_sc = p->n_src_pad / kChunk;
-  p->shape = pick_shape(kind, h->num_sms, n_tgt, p->n_sc > 0 ? p->n_sc : 1);
+  p->shape = -1;
+  if (force_T > 0) {
+    for (int i = 0; i < kNumShapes; ++i)
+      if (kShapes[i].kind == kind && kShapes[i].T == force_T) p->shape = i;
+  } else {
+    p->shape = pick_shape(kind, h->num_sms, n_tgt, p->n_sc > 0 ? p->n_sc : 1);
+  }
   if (p->shape < 0) return set_error(h, LPMX_ERR_INVALID, "no kernel for kind %d", kind);
   const Shape& sh = kShapes[p->shape];
   p->T = sh.T;
@@ -132,13 +139,26 @@ int make_plan(lpmx_handle_t h, int kind, int n_tgt, int n_src, SumPlan* p, bool 
   return LPMX_OK;
 }
 
+// The velocity shape with the least modelled time for a SMALL target set (the remainder of a constant-bank plan: a few
+// thousand targets, where the general rule of pick_shape -- 8 items per resident CTA -- falls through to T = 1).
+int make_best_ring_plan(lpmx_handle_t h, int n_tgt, int n_src, SumPlan* p) {
+  double best = -1.0;
+  SumPlan q;
+  for (int T : {6, 4, 2, 1}) {
+    if (make_plan(h, kVel, n_tgt, n_src, &q, false, T) != LPMX_OK) continue;
+    const double t = ring_plan_seconds(q);
+    if (best < 0 || t < best) best = t, *p = q;
+  }
+  return best < 0 ? set_error(h, LPMX_ERR_INVALID, "no velocity kernel") : LPMX_OK;
+}
+
 // Modelled duration of a ring-kernel launch: padded pairs over the measured rate of the shape (velocity kind, one B200:
 // profiles/r1b_tune_shapes.txt, r1h_size_sweep.txt; T = 2 / 1 shapes from the small-mesh rows), stretched by the item
 // quantisation of the persistent grid, plus a fixed ramp (launch, first tile, flush).  Only the constant-bank planner uses it,
 // to decide which targets are better served by which kernel; it does not have to be better than ~10 %.
 double ring_plan_seconds(const SumPlan& p) {
   if (p.n_tgt <= 0 || p.n_sc <= 0) return 0.0;
-  const double rate = p.T >= 6 ? 1.637e12 : p.T >= 4 ? 1.48e12 : p.T >= 2 ? 1.2e12 : 0.8e12;
+  const double rate = p.T >= 6 ? 1.637e12 : p.T >= 4 ? 1.48e12 : p.T >= 2 ? 1.4e12 : 1.3e12;  // T = 1: r2s, 2 048 targets in 0.187 ms
   const long n_items = (long)p.n_tb * p.n_sc;
   const double per_cta = (double)n_items / p.grid;
   const double quant = std::ceil(per_cta) / per_cta;
