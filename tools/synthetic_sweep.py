@@ -63,6 +63,7 @@ def main():
     ap.add_argument("--eval-only-above", type=float, default=4e6,
                     help="sizes above this time ONE velocity evaluation (BVESphere::init_velocity on the resident state) instead of "
                          "RK4 steps: N = 1e7 is 1e14 interactions, a minute per evaluation on one GPU")
+    ap.add_argument("--n-check", type=int, default=64, help="targets of the long-double host check (rank 0; 64 x 1e7 takes a minute)")
     args = ap.parse_args()
     import torch
     from lpm_b200.api import BVESolver, Engine
@@ -97,7 +98,7 @@ def main():
         eval_ms = v0.elapsed_time(v1)
         vel = np.zeros((n, 3))
         s.get_state(None, None, None, None, None, vel)
-        err, bound = subset_check(x, zeta, area, vel) if rank == 0 else (0.0, 0.0)
+        err, bound = subset_check(x, zeta, area, vel, args.n_check) if rank == 0 else (0.0, 0.0)
         if dist is not None:
             dist.barrier()  # rank 0 alone ran the host-side check: do not let the others wait for it inside a kernel
         if eval_only:
