@@ -31,6 +31,11 @@ struct CsDevice {
   }
   // *p += v as a reduction that returns nothing (RED.E.ADD.F64): the CTA does not wait for the old value on its way out.  One
   // thread per address and launch, launches in stream order: the same IEEE sum as load-add-store, deterministic.
+  // Programmatic dependent launch (LPMX_CONST_PDL): the next bank launch may start while this one runs -- its CTAs load their
+  // targets and sum their bank beside ours -- and only its reduction into the accumulators waits for us (wait_prior), so the
+  // per-target order of the additions stays the launch order.  Both are no-ops in a launch without the attribute.
+  __device__ __forceinline__ void launch_dependents() const { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+  __device__ __forceinline__ void wait_prior() const { asm volatile("griddepcontrol.wait;" ::: "memory"); }
   __device__ __forceinline__ void accumulate(double* p, double v, bool first) const {
     if (first)
       *p = v;
@@ -57,8 +62,10 @@ __host__ __device__ constexpr int cs_max_threads(int T) { return T >= 5 ? 288 : 
 
 // PF: launched with one extra warp that prefetches (single-wave launches).  Without it (launches of several waves) T <= 6 is
 // held to 128 registers so that two CTAs share an SM: 16 resident warps and no gap between waves (r2p: 88.6 % of the pipe).
-template <int T, bool PF>
-__global__ void __launch_bounds__(PF ? cs_max_threads(T) : cs_max_threads(T) - 32, (!PF && T <= 6) ? 2 : 1)
+// SMALL: 4 compute warps + the prefetch warp, three CTAs per SM (the pipelined single-wave shape of LPMX_CONST_PDL: two CTAs
+// of the running launch and one of the next share an SM).
+template <int T, bool PF, bool SMALL = false>
+__global__ void __launch_bounds__(SMALL ? 160 : (PF ? cs_max_threads(T) : cs_max_threads(T) - 32), SMALL ? 3 : ((!PF && T <= 6) ? 2 : 1))
     pair_sum_const_kernel(const cs::CsArgs a) {
   if (PF && threadIdx.x >= blockDim.x - 32) {
     prefetch_bank(a.prefetch_stride, a.acc);
@@ -89,12 +96,23 @@ cs_kernel_t cs_kernel_for(int T) {
 #define LPMX_CS_CAT(a, b) LPMX_CS_CAT2(a, b)
 
 // cudaErrorInvalidValue when there is no kernel for T
-cudaError_t LPMX_CS_CAT(cs_bank_launch_, LPMX_CS_BANK)(int T, int grid, int threads, cudaStream_t stream, const cs::CsArgs& a) {
+// pdl: launch with programmatic stream serialization (may start before the preceding kernel of the stream has completed)
+cudaError_t LPMX_CS_CAT(cs_bank_launch_, LPMX_CS_BANK)(int T, int grid, int threads, cudaStream_t stream, const cs::CsArgs& a, int pdl) {
   const bool pf = a.prefetch_stride > 0;  // then `threads` includes the prefetch warp
   cs_kernel_t kern = pf ? cs_kernel_for<true>(T) : cs_kernel_for<false>(T);
+  if (pf && T == 6 && threads == 160) kern = pair_sum_const_kernel<6, true, true>;
   if (!kern || threads > cs_max_threads(T) - (pf ? 0 : 32)) return cudaErrorInvalidValue;
-  kern<<<grid, threads, 0, stream>>>(a);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
 // device-to-device refill of the whole bank from `records` (cs::kBatch records of cs::kRec doubles)

@@ -48,7 +48,7 @@ constexpr int kCsBatch = cs::kBatch;  // records per bank
 constexpr int kCsRec = cs::kRec;      // doubles per record
 
 struct Bank {
-  cudaError_t (*launch)(int, int, int, cudaStream_t, const CsArgs&);
+  cudaError_t (*launch)(int, int, int, cudaStream_t, const CsArgs&, int);
   cudaError_t (*fill)(const double*, cudaStream_t);
 };
 const Bank kBanks[2] = {{cs_bank_launch_0, cs_bank_fill_0}, {cs_bank_launch_1, cs_bank_fill_1}};
@@ -137,6 +137,12 @@ static void forced_shape(int* ft, int* fnw, int* fps) {
   *ft = t, *fnw = nw, *fps = ps;
 }
 
+// LPMX_CONST_PDL=0 switches the pipelining of the bank launches off (then: whole waves + a ring remainder, see below)
+bool const_pdl() {
+  const char* e = getenv("LPMX_CONST_PDL");
+  return !(e && atoi(e) == 0);
+}
+
 double pick_const_split(lpmx_handle_t h, int num_sms, int n_tgt, int n_src, int* T_out, int* nw_out, int* ctas_out, int* n_const_out,
                         double* ring_s_out) {
   const long n_batches = ((long)round_up_chunk(n_src) + kCsBatch - 1) / kCsBatch;
@@ -146,6 +152,18 @@ double pick_const_split(lpmx_handle_t h, int num_sms, int n_tgt, int n_src, int*
   if (ring_s_out) *ring_s_out = ring_s;
   int ft, fnw, fps;
   forced_shape(&ft, &fnw, &fps);
+  if (const_pdl()) {
+    // Pipelined launches (programmatic dependent launch): CTAs of launch b + 1 take the slots the CTAs of launch b leave, so
+    // there are no waves to fill and no remainder -- every target goes through the banks, and the time is the padded work
+    // over the chip's rate (r2v: 94 % of the FP64 pipe issued at cubed-7) plus ~1.5 us per launch.  Shape: T = 6 targets per
+    // thread, 4 compute warps + the prefetch warp, three CTAs per SM (126 registers).
+    const int T = ft ? ft : 6, nw = ft ? fnw : 4;
+    const long tb = (long)T * nw * 32;
+    const long ctas = (n_tgt + tb - 1) / tb;
+    *T_out = T, *nw_out = nw, *ctas_out = (int)ctas, *n_const_out = n_tgt;
+    const double launch_s = (double)ctas * tb * kCsBatch * 9.0 / (64.0 * 0.94 * 1.965e9 * num_sms) + 1.5e-6;
+    return (double)n_batches * launch_s;
+  }
   double best = -1.0;
   // 8 warps = 2 per scheduler: with 9-11 warps two of the SM's four schedulers carry one warp more and the CTA waits for them
   // (r2b: T = 5 with 10 warps 66.4 ms at cubed-7), 12 warps and T = 8 are slower than the ring kernel (r2e)
@@ -239,7 +257,9 @@ static int enqueue_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt,
   int fts, fnws, per_sm;
   forced_shape(&fts, &fnws, &per_sm);
   const bool single_wave = p.cs_ctas <= h->num_sms * (fts ? per_sm : 1);
-  const int pf = single_wave ? pf_stride : 0;
+  const bool pdl = const_pdl();  // bank launch b + 1 may start while launch b runs (programmatic dependent launch)
+  const bool small_cta = p.T == 6 && p.tb == 6 * 4 * 32;  // the pipelined shape: its kernel instance carries the prefetch warp
+  const int pf = (single_wave || (pdl && small_cta)) ? pf_stride : 0;
   const int threads = p.tb / p.T + (pf > 0 ? 32 : 0);
   cudaStream_t cps = mode == 1 ? h->cs_stream : h->stream;
   // refill of bank (b & 1) with batch b; in the overlapped mode it waits for the launch that last read that bank
@@ -279,7 +299,7 @@ static int enqueue_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt,
       LPMX_TRY(fill_batch(b));
     a.j0 = (int)(b * kCsBatch);
     a.first = b == 0 ? 1 : 0;
-    const cudaError_t e = kBanks[bank].launch(p.T, p.cs_ctas, threads, h->stream, a);
+    const cudaError_t e = kBanks[bank].launch(p.T, p.cs_ctas, threads, h->stream, a, (pdl && b > 0) ? 1 : 0);
     if (e == cudaErrorInvalidValue) return set_error(h, LPMX_ERR_STATE, "no constant-bank kernel for T = %d", p.T);
     ++h->launches;
     ++h->cs_launches;
@@ -310,13 +330,13 @@ namespace {
 struct CsGraphKey {
   const void *tgt, *self_idx, *packed, *partials, *stage, *tgt_map;
   long si, sk, n_tgt_pad, rem_pad;
-  int T, tb, ctas, n_const, n_tgt, n_src_pad, rem_n, rem_shape, rem_grid, mode, pf;
+  int T, tb, ctas, n_const, n_tgt, n_src_pad, rem_n, rem_shape, rem_grid, mode, pf, pdl;
   double kappa;
   bool operator==(const CsGraphKey& o) const {
     return tgt == o.tgt && self_idx == o.self_idx && packed == o.packed && partials == o.partials && stage == o.stage && tgt_map == o.tgt_map && si == o.si &&
            sk == o.sk && n_tgt_pad == o.n_tgt_pad && rem_pad == o.rem_pad && T == o.T && tb == o.tb && ctas == o.ctas &&
            n_const == o.n_const && n_tgt == o.n_tgt && n_src_pad == o.n_src_pad && rem_n == o.rem_n && rem_shape == o.rem_shape &&
-           rem_grid == o.rem_grid && mode == o.mode && pf == o.pf && kappa == o.kappa;
+           rem_grid == o.rem_grid && mode == o.mode && pf == o.pf && pdl == o.pdl && kappa == o.kappa;
   }
 };
 struct CsGraph {
@@ -356,7 +376,7 @@ int launch_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const i
   CsGraphCache* cache = (CsGraphCache*)h->cs_graph_cache;
   if (cache->broken) return enqueue_const_stream(h, p, tgt, self_idx, packed, kappa, partials, tgt_map, mode, pf_stride, stage_v, &nl, &nb);
   CsGraphKey key{tgt.p, self_idx, packed, partials, stage_v, tgt_map, tgt.si, tgt.sk, p.n_tgt_pad, p.rem.n_tgt_pad, p.T, p.tb, p.cs_ctas,
-                 p.cs_n_const, p.n_tgt, p.n_src_pad, p.rem.n_tgt, p.rem.shape, p.rem.grid, mode, pf_stride, kappa};
+                 p.cs_n_const, p.n_tgt, p.n_src_pad, p.rem.n_tgt, p.rem.shape, p.rem.grid, mode, pf_stride, const_pdl() ? 1 : 0, kappa};
   CsGraph* g = nullptr;
   for (auto& e : cache->entries)
     if (e.key == key) g = &e;

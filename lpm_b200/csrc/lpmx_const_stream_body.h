@@ -4,7 +4,8 @@
 //
 // Platform P: int tid(), bid(), n_threads();  bool any_sync(bool);  double src(int i)  (record storage of the launch's bank);
 //             double rcp_seed(double)  (>= 19 correct bits);  void accumulate(double* p, double v, bool first)  (*p = v or *p += v;
-//             every address belongs to one thread of one launch at a time).
+//             every address belongs to one thread of one launch at a time);  void launch_dependents(), wait_prior()  (programmatic
+//             dependent launch on the GPU; no-ops elsewhere).
 #ifndef LPMX_CONST_STREAM_BODY_H
 #define LPMX_CONST_STREAM_BODY_H
 
@@ -72,6 +73,7 @@ LPMX_CS_HD void loop(P& pf, const double (&x)[T][3], const int (&self)[T], doubl
 
 template <int T, class P>
 LPMX_CS_HD void body(P& pf, const CsArgs& a) {
+  pf.launch_dependents();
   const int lanes = pf.n_threads();
   const long base_t = (long)pf.bid() * ((long)T * lanes) + pf.tid();
   double x[T][3], acc[T][3];
@@ -94,6 +96,7 @@ LPMX_CS_HD void body(P& pf, const CsArgs& a) {
     loop<T, true>(pf, x, self, acc, a.j0, a.kappa);
   else
     loop<T, false>(pf, x, self, acc, a.j0, a.kappa);
+  pf.wait_prior();  // the accumulators take the launches' sums in launch order
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const long tg = base_t + (long)t * lanes;

@@ -208,8 +208,8 @@ double pick_const_split(lpmx_handle_t h, int num_sms, int n_tgt, int n_src, int*
                         double* ring_s_out);
 // the two banks (lpmx_const_bank0.cu, lpmx_const_bank1.cu)
 namespace cs { struct CsArgs; }
-cudaError_t cs_bank_launch_0(int T, int grid, int threads, cudaStream_t stream, const cs::CsArgs& a);
-cudaError_t cs_bank_launch_1(int T, int grid, int threads, cudaStream_t stream, const cs::CsArgs& a);
+cudaError_t cs_bank_launch_0(int T, int grid, int threads, cudaStream_t stream, const cs::CsArgs& a, int pdl);
+cudaError_t cs_bank_launch_1(int T, int grid, int threads, cudaStream_t stream, const cs::CsArgs& a, int pdl);
 cudaError_t cs_bank_fill_0(const double* records, cudaStream_t stream);
 cudaError_t cs_bank_fill_1(const double* records, cudaStream_t stream);
 int const_stream_mode(lpmx_handle_t h);

@@ -27,6 +27,8 @@ struct HostPlatform {
   double src(int i) const { return g_banks[g_bank][(size_t)i]; }
   double rcp_seed(double d) const { return (double)(float)(1.0 / d); }  // 24 good bits; the cubic step must do the rest
   void accumulate(double* p, double v, bool first) const { *p = first ? v : *p + v; }
+  void launch_dependents() const {}
+  void wait_prior() const {}
 };
 
 template <int T>

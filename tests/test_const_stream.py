@@ -22,9 +22,21 @@ def _split(n_tgt, n_src, sms=SMS):
     return T.value, nw.value, ctas.value, n_const.value, t.value, tr.value
 
 
+@pytest.mark.parametrize("n_tgt,n_src", [(229376, 98304), (9382, 5120), (2402982, 1310720), (9611942, 5242880), (1, 5120)])
+def test_pipelined_plan_puts_every_target_through_the_banks(n_tgt, n_src):
+    """The default: bank launches pipelined with programmatic dependent launch -- no waves to fill, no remainder; CTAs of
+    T = 6 x 4 compute warps = 768 targets, three per SM."""
+    T, nw, ctas, n_const, t, tr = _split(n_tgt, n_src)
+    assert (T, nw) == (6, 4) and n_const == n_tgt and ctas == -(-n_tgt // 768) and t > 0 and tr > 0
+    if n_tgt >= 189440:
+        assert t < 0.98 * tr  # the automatic mode takes it
+
+
 @pytest.mark.parametrize("n_tgt,n_src", [(229376, 98304), (9382, 5120), (600742, 327680), (2402982, 1310720), (9611942, 5242880),
                                          (300000, 300000), (1201491, 1310720), (189440, 98304), (1, 5120), (12345, 6000)])
-def test_split_covers_the_targets_with_whole_waves_plus_a_remainder(n_tgt, n_src):
+def test_split_covers_the_targets_with_whole_waves_plus_a_remainder(n_tgt, n_src, monkeypatch):
+    """Without the pipelining (LPMX_CONST_PDL=0) a launch has to fill whole waves of the chip."""
+    monkeypatch.setenv("LPMX_CONST_PDL", "0")
     T, nw, ctas, n_const, t, tr = _split(n_tgt, n_src)
     assert T in (5, 6, 7) and nw == 8  # 8 warps = 2 per scheduler; the measured shapes (profiles/r2e_icos8_const_shapes.txt)
     tb = T * nw * 32
@@ -35,10 +47,11 @@ def test_split_covers_the_targets_with_whole_waves_plus_a_remainder(n_tgt, n_src
         assert ctas * tb >= n_tgt > (ctas - 1) * tb
 
 
-def test_split_at_the_headline_sizes():
-    """cubed-7 (BASELINE configs[1]): one wave of T = 6 = 227 328 targets through the banks, 2 048 through the ring kernel, and
+def test_split_at_the_headline_sizes(monkeypatch):
+    """(LPMX_CONST_PDL=0) cubed-7 (BASELINE configs[1]): one wave of T = 6 = 227 328 targets through the banks, 2 048 through the ring kernel, and
     the model prefers that to the ring kernel alone; icos-8 on one GPU: whole waves + a remainder, also preferred; a rank's
     share of cubed-7 on two GPUs (114 688 targets) cannot fill one wave and stays with the ring kernel in the automatic mode."""
+    monkeypatch.setenv("LPMX_CONST_PDL", "0")
     T, nw, ctas, n_const, t, tr = _split(229376, 98304)
     assert (T, nw, ctas, n_const) == (6, 8, 148, 227328) and t < 0.98 * tr
     T, nw, ctas, n_const, t, tr = _split(2402982, 1310720)
@@ -107,16 +120,19 @@ def test_gpu_const_stream_velocity_matches_oracle_and_default_kernel(oracle, mod
 
 
 @pytest.mark.gpu
-def test_gpu_const_stream_automatic_split_at_cubed7():
-    """BASELINE configs[1] as bench.py runs it, nothing forced: the 229 376 targets of the resident solver's evaluation split
-    into one wave through the banks (227 328) and 2 048 through the ring kernel.  One BVERK4 step against the same step with
-    the path switched off (two summation orders of the same terms; the remainder is the tail of the face list), and the launch
-    count shows the path was taken (77 bank launches per evaluation).  The same step against the ORACLE -- every face target,
+@pytest.mark.parametrize("pdl", ["1", "0"])
+def test_gpu_const_stream_automatic_split_at_cubed7(pdl, monkeypatch):
+    """BASELINE configs[1] as bench.py runs it, nothing forced.  pdl = 1 (the default): all 229 376 targets of the resident
+    solver's evaluation through the banks, launches pipelined; pdl = 0: one wave through the banks (227 328) and 2 048 through
+    the ring kernel.  One BVERK4 step against the same step with the path switched off (two summation orders of the same
+    terms; the tail of the face list is the ring kernel's share when pdl = 0), and the launch count shows the path was taken
+    (77 bank launches per evaluation).  The same step against the ORACLE -- every face target,
     so the remainder too, and 4 096 sampled vertices -- is test_rk4_step_at_cubed7_sampled_targets_against_the_oracle
     (tests/test_gpu_parity_bve.py), which runs on the automatic mode as well."""
     from lpm_b200 import gallery
     from lpm_b200.api import BVESolver, Engine, PolyMesh2d
     from conftest import field_rel_err
+    monkeypatch.setenv("LPMX_CONST_PDL", pdl)
     m = PolyMesh2d("cubed", 7)
     f = gallery.RossbyHaurwitz54()
     f.set_stationary_wave_speed()
@@ -185,8 +201,9 @@ def test_gpu_const_stream_with_split_target_lists(oracle, monkeypatch):
 @pytest.mark.gpu
 def test_gpu_const_stream_captured_sequence_is_bit_identical(monkeypatch):
     """The launch sequence of an evaluation replayed from its CUDA graph (captured the second time a sequence comes by) against
-    the same sequence enqueued launch by launch (LPMX_CONST_GRAPH=0), with and without the prefetch warp: the same kernels on
-    the same data in the same order -- bit-identical states after three BVERK4 steps, and the same launch counts."""
+    the same sequence enqueued launch by launch (LPMX_CONST_GRAPH=0), with and without the prefetch warp, with and without
+    pipelined launches: the same kernels on the same data in the same order -- bit-identical states after three BVERK4 steps,
+    and the same launch counts."""
     from lpm_b200 import gallery
     from lpm_b200.api import BVESolver, Engine, PolyMesh2d
     monkeypatch.setenv("LPMX_CONST_MIN_TARGETS", "1")
@@ -196,9 +213,10 @@ def test_gpu_const_stream_captured_sequence_is_bit_identical(monkeypatch):
     vz, fz = f(m.vert_xyz), f(m.face_xyz)
     area, mask = np.ascontiguousarray(m.face_area), np.ascontiguousarray(m.face_mask)
     runs = []
-    for graph, prefetch in (("0", "64"), ("1", "64"), ("1", "0")):
+    for graph, prefetch, pdl in (("0", "64", "0"), ("1", "64", "0"), ("1", "0", "0"), ("0", "128", "1"), ("1", "128", "1")):
         monkeypatch.setenv("LPMX_CONST_GRAPH", graph)
         monkeypatch.setenv("LPMX_CONST_PREFETCH", prefetch)
+        monkeypatch.setenv("LPMX_CONST_PDL", pdl)
         e = Engine(0)
         try:
             e.pair_sum_const_stream(1)
@@ -216,9 +234,13 @@ def test_gpu_const_stream_captured_sequence_is_bit_identical(monkeypatch):
             runs.append((counts, out))
         finally:
             e.close()
-    assert runs[0][0] == runs[1][0] == runs[2][0] and runs[0][0][1] >= 12 * 5
+    # runs 0-2: whole waves (+ remainder); runs 3-4: pipelined launches, every target through the banks -- two different
+    # splits of the targets (the same per-target sums either way: a target's terms are added in the same order by whichever
+    # kernel has it only within a split, so bit-identity is asserted within each group)
+    assert runs[0][0] == runs[1][0] == runs[2][0] and runs[0][0][1] >= 12 * 5 and runs[3][0] == runs[4][0]
     for k in range(6):
         assert np.array_equal(runs[0][1][k], runs[1][1][k]) and np.array_equal(runs[0][1][k], runs[2][1][k]), k
+        assert np.array_equal(runs[3][1][k], runs[4][1][k]), k
 
 
 @pytest.mark.gpu
