@@ -15,7 +15,10 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "liblpmx.so")
 
-CU_SOURCES = ["lpmx_core.cu", "lpmx_peer.cu", "lpmx_kernels.cu", "lpmx_const_stream.cu", "lpmx_const_bank0.cu", "lpmx_const_bank1.cu", "lpmx_sums.cu", "lpmx_steppers.cu", "lpmx_swe_stepper.cu", "lpmx_plane.cu", "lpmx_diagnostics.cu", "lpmx_gmls.cu", "lpmx_refinement.cu"]
+CU_SOURCES = ["lpmx_core.cu", "lpmx_peer.cu", "lpmx_kernels.cu", "lpmx_const_stream.cu", "lpmx_sums.cu", "lpmx_steppers.cu", "lpmx_swe_stepper.cu", "lpmx_plane.cu", "lpmx_diagnostics.cu", "lpmx_gmls.cu", "lpmx_refinement.cu"]
+# lpmx_const_bank.cu is compiled once per constant bank: every object is its own module with its own 64 KB bank
+# (kCsBanks in csrc/lpmx_internal.h must equal N_CONST_BANKS)
+N_CONST_BANKS = 24
 CXX_SOURCES = ["lpmx_mesh.cpp"]
 HEADERS = ["lpmx_internal.h", "lpmx_finalize.cuh", "lpmx_pair_kernel.cuh", "lpmx_gmls_core.h", "lpmx_fast_log.h", "lpmx_peer_protocol.h", "lpmx_const_stream_body.h", "lpmx_const_bank.cuh", "seed_tables.inc", "log_table_7.inc", "log_table_8.inc", "log_table_10.inc", os.path.join("..", "..", "include", "lpmx.h")]
 
@@ -62,6 +65,12 @@ def build(force=False, verbose=False):
         obj = os.path.join(OBJ, src + ".o")
         if force or _stale(obj, [path] + hdrs):
             _run([_nvcc()] + NVCC_FLAGS + ["-c", path, "-o", obj], verbose, log)
+        objs.append(obj)
+    bank_src = os.path.join(CSRC, "lpmx_const_bank.cu")
+    for k in range(N_CONST_BANKS):
+        obj = os.path.join(OBJ, "lpmx_const_bank%d.cu.o" % k)
+        if force or _stale(obj, [bank_src] + hdrs):
+            _run([_nvcc()] + NVCC_FLAGS + ["-DLPMX_CS_BANK=%d" % k, "-c", bank_src, "-o", obj], verbose, log)
         objs.append(obj)
     for src in CXX_SOURCES:
         path = os.path.join(CSRC, src)

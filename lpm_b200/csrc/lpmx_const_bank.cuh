@@ -1,10 +1,11 @@
 // lpmx_const_bank.cuh -- ONE constant bank of the constant-bank velocity path and the kernels that read it.
-// Compiled twice (lpmx_const_bank0.cu, lpmx_const_bank1.cu define LPMX_CS_BANK = 0 / 1): without relocatable device code every
-// translation unit is its own module with its own 64 KB user constant bank, so two translation units give two banks of
-// cs::kBatch = 1 280 records.  A launch of bank b's kernel sums the whole bank into every target while the other bank is
-// refilled behind it (lpmx_const_stream.cu) -- half as many launches as two halves of one bank would need.
+// Compiled kCsBanks times (lpmx_const_bank.cu with -DLPMX_CS_BANK=0 .. kCsBanks-1, lpm_b200/build.py): without relocatable
+// device code every translation unit is its own module with its own 64 KB user constant bank, so N translation units give N
+// banks of cs::kBatch = 1 280 records.  A launch of bank b's kernel sums the whole bank into its targets while the other banks
+// are refilled behind it or read by the launches pipelined around it (lpmx_const_stream.cu).  Banks 0 and 1 carry every kernel
+// shape; the others only the pipelined small-CTA shapes, the only ones that keep more than two launches in flight.
 #ifndef LPMX_CS_BANK
-#error "include from lpmx_const_bank0.cu / lpmx_const_bank1.cu"
+#error "compile lpmx_const_bank.cu with -DLPMX_CS_BANK=<n>"
 #endif
 
 #include "lpmx_const_stream_body.h"
@@ -49,11 +50,11 @@ struct CsDevice {
 // wait for, one miss at a time (r2p: 56 % of the FP64 pipe on the first wave of a launch against 88 % on the later waves
 // of the same launch, whose lines are still cached; ~1.6 ns per byte = 96 us per 61 KB bank and SM).  The prefetch warp takes
 // those misses instead, ahead of the compute warps, and exits.  (CsArgs::prefetch_stride = 0 switches it off: LPMX_CONST_PREFETCH.)
-__device__ __forceinline__ void prefetch_bank(int stride, double* never) {  // stride in doubles: one load per cache line
+__device__ __forceinline__ void prefetch_bank(int stride, int n_rec, double* never) {  // stride in doubles: one load per cache line
   const int lane = threadIdx.x & 31;
   double sink = 0.0;
 #pragma unroll 4
-  for (int i = lane * stride; i < cs::kBatch * cs::kRec; i += 32 * stride) sink += c_src[i];  // lane-varying index: LDC
+  for (int i = lane * stride; i < n_rec * cs::kRec; i += 32 * stride) sink += c_src[i];  // lane-varying index: LDC
   if (sink == -1.2345678901234567e300) *never = sink;  // keeps the loads alive (ptxas drops loads nobody consumes)
 }
 
@@ -62,23 +63,26 @@ __host__ __device__ constexpr int cs_max_threads(int T) { return T >= 5 ? 288 : 
 
 // PF: launched with one extra warp that prefetches (single-wave launches).  Without it (launches of several waves) T <= 6 is
 // held to 128 registers so that two CTAs share an SM: 16 resident warps and no gap between waves (r2p: 88.6 % of the pipe).
-// SMALL: 4 compute warps + the prefetch warp, three CTAs per SM (the pipelined single-wave shape of LPMX_CONST_PDL: two CTAs
-// of the running launch and one of the next share an SM).
-template <int T, bool PF, bool SMALL = false>
+// SMALL: the pipelined shape -- 4 compute warps + the prefetch warp, three CTAs per SM, so that CTAs of consecutive launches
+// share an SM (programmatic dependent launch, lpmx_const_stream.cu).  (A 2-warp shape, five per SM, lost at every size: r2y.)
+// NREC: source records per launch (half a bank for small target sets: the CTAs hold their slots half as long when the
+// pipeline of an evaluation drains, r2z).
+template <int T, bool PF, bool SMALL = false, int NREC = cs::kBatch>
 __global__ void __launch_bounds__(SMALL ? 160 : (PF ? cs_max_threads(T) : cs_max_threads(T) - 32), SMALL ? 3 : ((!PF && T <= 6) ? 2 : 1))
     pair_sum_const_kernel(const cs::CsArgs a) {
   if (PF && threadIdx.x >= blockDim.x - 32) {
-    prefetch_bank(a.prefetch_stride, a.acc);
+    prefetch_bank(a.prefetch_stride, a.n_rec, a.acc);
     return;
   }
   CsDevice pf;
   pf.lanes = PF ? blockDim.x - 32 : blockDim.x;
-  cs::body<T>(pf, a);
+  cs::body<T, NREC>(pf, a);
 }
 
 typedef void (*cs_kernel_t)(const cs::CsArgs);
 template <bool PF>
 cs_kernel_t cs_kernel_for(int T) {
+#if LPMX_CS_BANK < 2
   switch (T) {
     case 3: return pair_sum_const_kernel<3, PF>;
     case 4: return pair_sum_const_kernel<4, PF>;
@@ -88,6 +92,9 @@ cs_kernel_t cs_kernel_for(int T) {
     case 8: return pair_sum_const_kernel<8, PF>;
     default: return nullptr;
   }
+#else
+  return nullptr;
+#endif
 }
 
 }  // namespace
@@ -100,7 +107,8 @@ cs_kernel_t cs_kernel_for(int T) {
 cudaError_t LPMX_CS_CAT(cs_bank_launch_, LPMX_CS_BANK)(int T, int grid, int threads, cudaStream_t stream, const cs::CsArgs& a, int pdl) {
   const bool pf = a.prefetch_stride > 0;  // then `threads` includes the prefetch warp
   cs_kernel_t kern = pf ? cs_kernel_for<true>(T) : cs_kernel_for<false>(T);
-  if (pf && T == 6 && threads == 160) kern = pair_sum_const_kernel<6, true, true>;
+  if (pf && T == 6 && threads == 160) kern = a.n_rec == cs::kBatch / 2 ? pair_sum_const_kernel<6, true, true, cs::kBatch / 2> : pair_sum_const_kernel<6, true, true>;
+  else if (a.n_rec != cs::kBatch) return cudaErrorInvalidValue;
   if (!kern || threads > cs_max_threads(T) - (pf ? 0 : 32)) return cudaErrorInvalidValue;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -115,9 +123,9 @@ cudaError_t LPMX_CS_CAT(cs_bank_launch_, LPMX_CS_BANK)(int T, int grid, int thre
   return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
-// device-to-device refill of the whole bank from `records` (cs::kBatch records of cs::kRec doubles)
-cudaError_t LPMX_CS_CAT(cs_bank_fill_, LPMX_CS_BANK)(const double* records, cudaStream_t stream) {
-  return cudaMemcpyToSymbolAsync(c_src, records, sizeof(double) * cs::kBatch * cs::kRec, 0, cudaMemcpyDeviceToDevice, stream);  // not the read-ahead record
+// device-to-device refill of the bank from `records` (n_rec <= cs::kBatch records of cs::kRec doubles)
+cudaError_t LPMX_CS_CAT(cs_bank_fill_, LPMX_CS_BANK)(const double* records, int n_rec, cudaStream_t stream) {
+  return cudaMemcpyToSymbolAsync(c_src, records, sizeof(double) * n_rec * cs::kRec, 0, cudaMemcpyDeviceToDevice, stream);  // not the read-ahead record
 }
 
 }  // namespace lpmx

@@ -49,9 +49,11 @@ constexpr int kCsRec = cs::kRec;      // doubles per record
 
 struct Bank {
   cudaError_t (*launch)(int, int, int, cudaStream_t, const CsArgs&, int);
-  cudaError_t (*fill)(const double*, cudaStream_t);
+  cudaError_t (*fill)(const double*, int, cudaStream_t);
 };
-const Bank kBanks[2] = {{cs_bank_launch_0, cs_bank_fill_0}, {cs_bank_launch_1, cs_bank_fill_1}};
+#define LPMX_CS_ENTRY(k) {cs_bank_launch_##k, cs_bank_fill_##k},
+const Bank kBanks[kCsBanks] = {LPMX_CS_BANK_LIST(LPMX_CS_ENTRY)};
+#undef LPMX_CS_ENTRY
 
 // packed 64-byte records -> 48-byte records, zero-padded to whole banks
 __global__ void cs_repack_kernel(const double* __restrict__ packed, int n_src_pad, double* __restrict__ out, long n_out) {
@@ -124,17 +126,22 @@ static double const_launch_seconds(int waves, int T, int nw) {
 }
 
 // LPMX_CONST_SHAPE="T,NW[,PERSM]" pins the shape (tuning): T targets per thread, NW compute warps, PERSM CTAs per SM and wave
-static void forced_shape(int* ft, int* fnw, int* fps) {
-  static int t = 0, nw = 0, ps = 1;
-  static bool parsed = false;
-  if (!parsed) {
-    parsed = true;
-    const char* e = getenv("LPMX_CONST_SHAPE");
-    const int n = e ? sscanf(e, "%d,%d,%d", &t, &nw, &ps) : 0;
-    if (n < 3) ps = 1;
-    if (!(n >= 2 && t >= 3 && t <= 8 && nw >= 1 && (nw + 1) * 32 <= kCsMaxThreads && ps >= 1 && ps <= 4)) t = nw = 0, ps = 1;
-  }
+static void forced_shape(int* ft, int* fnw, int* fps) {  // parsed per call: tools switch shapes within one process
+  int t = 0, nw = 0, ps = 1;
+  const char* e = getenv("LPMX_CONST_SHAPE");
+  const int n = e ? sscanf(e, "%d,%d,%d", &t, &nw, &ps) : 0;
+  if (n < 3) ps = 1;
+  if (!(n >= 2 && t >= 3 && t <= 8 && nw >= 1 && (nw + 1) * 32 <= kCsMaxThreads && ps >= 1 && ps <= 5)) t = nw = 0, ps = 1;
   *ft = t, *fnw = nw, *fps = ps;
+}
+
+// source records per bank launch: a whole bank, or half a bank for small target sets (measured, r2z: 28 672 targets 1.667 ->
+// 1.62 ms, 57 344 targets 3.18 -> 3.07 ms per evaluation; no difference from 114 688 targets up).  LPMX_CONST_BATCH overrides.
+constexpr int kCsHalfBatchBelow = 100000;
+int const_batch(int n_tgt) {
+  int b = n_tgt < kCsHalfBatchBelow ? kCsBatch / 2 : kCsBatch;
+  if (const char* e = getenv("LPMX_CONST_BATCH")) b = atoi(e) <= kCsBatch / 2 ? kCsBatch / 2 : kCsBatch;
+  return b;
 }
 
 // LPMX_CONST_PDL=0 switches the pipelining of the bank launches off (then: whole waves + a ring remainder, see below)
@@ -145,7 +152,7 @@ bool const_pdl() {
 
 double pick_const_split(lpmx_handle_t h, int num_sms, int n_tgt, int n_src, int* T_out, int* nw_out, int* ctas_out, int* n_const_out,
                         double* ring_s_out) {
-  const long n_batches = ((long)round_up_chunk(n_src) + kCsBatch - 1) / kCsBatch;
+  const long n_batches = ((long)round_up_chunk(n_src) + kCsBatch - 1) / kCsBatch;  // (the whole-wave planner below)
   SumPlan ring;
   double ring_s = 0.0;
   if (make_plan(h, kVel, n_tgt, n_src, &ring, false) == LPMX_OK) ring_s = ring_plan_seconds(ring);
@@ -154,15 +161,25 @@ double pick_const_split(lpmx_handle_t h, int num_sms, int n_tgt, int n_src, int*
   forced_shape(&ft, &fnw, &fps);
   if (const_pdl()) {
     // Pipelined launches (programmatic dependent launch): CTAs of launch b + 1 take the slots the CTAs of launch b leave, so
-    // there are no waves to fill and no remainder -- every target goes through the banks, and the time is the padded work
-    // over the chip's rate (r2v: 94 % of the FP64 pipe issued at cubed-7) plus ~1.5 us per launch.  Shape: T = 6 targets per
-    // thread, 4 compute warps + the prefetch warp, three CTAs per SM (126 registers).
+    // there are no waves to fill and no remainder -- every target goes through the banks.  Shape: T = 6 targets per thread,
+    // 4 compute warps + the prefetch warp, three CTAs per SM (126 registers).  Measured on one B200 (r2y,
+    // tools/rank_size_sweep.py: 28 672 .. 229 376 targets x 98 304 sources): t = pairs / 2.0e12 + 0.26 ms with 1 280 records
+    // per launch -- the FP64 pipe is 97 % busy while the pipeline is full, and filling and draining it costs about the time a
+    // CTA holds its slot (three CTAs share an SM: 3 x 768 x 1 280 pairs = 216 us) once per evaluation.  Enough launches have
+    // to be in flight to fill the chip's 444 CTA slots: one per bank, so small launches (a rank's share of a small mesh: 38
+    // CTAs at cubed-7 on eight GPUs) are limited by the number of banks.
     const int T = ft ? ft : 6, nw = ft ? fnw : 4;
+    const int per_sm = ft ? fps : 3;
     const long tb = (long)T * nw * 32;
     const long ctas = (n_tgt + tb - 1) / tb;
     *T_out = T, *nw_out = nw, *ctas_out = (int)ctas, *n_const_out = n_tgt;
-    const double launch_s = (double)ctas * tb * kCsBatch * 9.0 / (64.0 * 0.94 * 1.965e9 * num_sms) + 1.5e-6;
-    return (double)n_batches * launch_s;
+    const int batch = (T == 6 && nw == 4) ? const_batch(n_tgt) : kCsBatch;
+    const double slots = (double)num_sms * per_sm;
+    double fill = (double)ctas * kCsBanks / slots;
+    if (fill > 1.0) fill = 1.0;
+    const double sum_s = (double)ctas * tb * (double)round_up_chunk(n_src) / (2.0e12 * fill);
+    const double drain_s = (double)per_sm * tb * batch * 9.0 / (64.0 * 0.97 * 1.965e9);
+    return sum_s + drain_s + 30e-6;
   }
   double best = -1.0;
   // 8 warps = 2 per scheduler: with 9-11 warps two of the SM's four schedulers carry one warp more and the CTA waits for them
@@ -200,7 +217,8 @@ bool make_const_plan(lpmx_handle_t h, int n_tgt, int n_src, SumPlan* p) {
   // auto: from one full wave of the smallest shape upwards, and only where the modelled time beats the ring kernel's;
   // forced (1 / 2): wherever one wave can be filled at all.  LPMX_CONST_MIN_TARGETS lowers the floor (parity tests on small
   // meshes: whatever does not fill a wave goes through an only partly filled one)
-  long min_tgt = (long)h->num_sms * 32 * 8 * 5;
+  // pipelined launches fill the chip with the CTAs of several launches, so the floor is low and the model decides
+  long min_tgt = const_pdl() ? 16384 : (long)h->num_sms * 32 * 8 * 5;
   if (const char* e = getenv("LPMX_CONST_MIN_TARGETS")) min_tgt = atol(e);
   if ((long)n_tgt < min_tgt || n_tgt < 1 || n_src < 4 * kCsBatch) return false;
   int T = 0, nw = 0, ctas = 0, n_const = 0;
@@ -217,6 +235,7 @@ bool make_const_plan(lpmx_handle_t h, int n_tgt, int n_src, SumPlan* p) {
   p->n_tgt = n_tgt;
   p->cs_ctas = ctas;
   p->cs_n_const = n_const;
+  p->cs_batch = (const_pdl() && T == 6 && nw == 4) ? const_batch(n_tgt) : kCsBatch;
   p->n_src_pad = round_up_chunk(n_src);
   p->n_sc = p->n_src_pad / kChunk;
   p->grid = 1;  // what the finalize kernels see: every target block was summed by "CTA 0", i.e. slot 0 only
@@ -238,19 +257,21 @@ bool make_const_plan(lpmx_handle_t h, int n_tgt, int n_src, SumPlan* p) {
 static int enqueue_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const int* self_idx, const double* packed,
                                 double kappa, double* partials, const int* tgt_map, int mode, int pf_stride, void* stage_v,
                                 long* n_launches, long* n_bank_launches) {
-  const long n_batches = ((long)p.n_src_pad + kCsBatch - 1) / kCsBatch;
-  const long n_out = n_batches * kCsBatch;
+  const int batch = p.cs_batch;
+  const long n_batches = ((long)p.n_src_pad + batch - 1) / batch;
+  const long n_out = n_batches * batch;
   const double* stage = (const double*)stage_v;
   const long launches0 = h->launches, cs0 = h->cs_launches;
   cs_repack_kernel<<<(int)((n_out + 255) / 256), 256, 0, h->stream>>>(packed, p.n_src_pad, (double*)stage_v, n_out);
   ++h->launches;
   LPMX_CUDA(h, cudaGetLastError());
-  if (!h->cs_events[0]) {
-    for (int i = 0; i < 5; ++i) LPMX_CUDA(h, cudaEventCreateWithFlags(&h->cs_events[i], cudaEventDisableTiming));
+  if (h->cs_events.empty()) {
+    h->cs_events.assign(1 + 2 * kCsBanks, nullptr);
+    for (auto& e : h->cs_events) LPMX_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   cudaEvent_t ev_repack = h->cs_events[0];
-  cudaEvent_t* ev_filled = &h->cs_events[1];  // [bank]
-  cudaEvent_t* ev_summed = &h->cs_events[3];  // [bank]
+  cudaEvent_t* ev_filled = &h->cs_events[1];             // [bank]
+  cudaEvent_t* ev_summed = &h->cs_events[1 + kCsBanks];  // [bank]
   // the prefetch warp (lpmx_const_bank.cuh) rides along on launches of a single wave, where every CTA starts on cold constant
   // caches; later waves of a longer launch find the bank cached, and without the extra warp two CTAs of T <= 6 fit an SM
   // (r2p: 88.6 % of the FP64 pipe at icos-8 that way, 78 % with the extra warp in every CTA, r2q)
@@ -258,15 +279,27 @@ static int enqueue_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt,
   forced_shape(&fts, &fnws, &per_sm);
   const bool single_wave = p.cs_ctas <= h->num_sms * (fts ? per_sm : 1);
   const bool pdl = const_pdl();  // bank launch b + 1 may start while launch b runs (programmatic dependent launch)
-  const bool small_cta = p.T == 6 && p.tb == 6 * 4 * 32;  // the pipelined shape: its kernel instance carries the prefetch warp
+  // the pipelined shapes: their kernel instances carry the prefetch warp and exist in every bank
+  const bool small_cta = p.T == 6 && p.tb == 6 * 4 * 32;
   const int pf = (single_wave || (pdl && small_cta)) ? pf_stride : 0;
   const int threads = p.tb / p.T + (pf > 0 ? 32 : 0);
+  // banks in rotation: as many launches can be in flight at once.  Two for the large shapes (their launches fill the chip
+  // by themselves); for the pipelined small-CTA shapes enough of them to fill every CTA slot of the chip with the CTAs of
+  // consecutive launches (a rank's share of a small mesh is a few dozen CTAs per launch), LPMX_CONST_BANKS caps it.
+  int nb = 2;
+  if (pdl && small_cta && pf > 0 && mode == 1) {
+    const int slots = h->num_sms * 3;
+    nb = (slots + p.cs_ctas - 1) / p.cs_ctas + 2;
+    if (const char* e = getenv("LPMX_CONST_BANKS")) nb = atoi(e);
+    if (nb < 2) nb = 2;
+    if (nb > kCsBanks) nb = kCsBanks;
+  }
   cudaStream_t cps = mode == 1 ? h->cs_stream : h->stream;
-  // refill of bank (b & 1) with batch b; in the overlapped mode it waits for the launch that last read that bank
+  // refill of bank (b % nb) with batch b; in the overlapped mode it waits for the launch that last read that bank
   auto fill_batch = [&](long b) -> int {
-    const int bank = (int)(b & 1);
-    if (mode == 1 && b >= 2) LPMX_CUDA(h, cudaStreamWaitEvent(cps, ev_summed[bank], 0));
-    LPMX_CUDA(h, kBanks[bank].fill(stage + (size_t)b * kCsBatch * kCsRec, cps));
+    const int bank = (int)(b % nb);
+    if (mode == 1 && b >= nb) LPMX_CUDA(h, cudaStreamWaitEvent(cps, ev_summed[bank], 0));
+    LPMX_CUDA(h, kBanks[bank].fill(stage + (size_t)b * batch * kCsRec, batch, cps));
     if (mode == 1) LPMX_CUDA(h, cudaEventRecord(ev_filled[bank], cps));
     return LPMX_OK;
   };
@@ -274,8 +307,7 @@ static int enqueue_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt,
     // everything queued so far on the compute stream (the repack, and any earlier launch still reading the banks)
     LPMX_CUDA(h, cudaEventRecord(ev_repack, h->stream));
     LPMX_CUDA(h, cudaStreamWaitEvent(cps, ev_repack, 0));
-    LPMX_TRY(fill_batch(0));
-    if (n_batches > 1) LPMX_TRY(fill_batch(1));
+    for (long b = 0; b < nb && b < n_batches; ++b) LPMX_TRY(fill_batch(b));
   }
   // the remainder first: the ring kernel runs while the first banks are being filled
   double* rem_partials = partials + 3 * (size_t)p.n_tgt_pad;
@@ -292,12 +324,13 @@ static int enqueue_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt,
   a.kappa = kappa;
   a.prefetch_stride = pf;
   for (long b = 0; b < n_batches; ++b) {
-    const int bank = (int)(b & 1);
+    const int bank = (int)(b % nb);
     if (mode == 1)
       LPMX_CUDA(h, cudaStreamWaitEvent(h->stream, ev_filled[bank], 0));
     else
       LPMX_TRY(fill_batch(b));
-    a.j0 = (int)(b * kCsBatch);
+    a.j0 = (int)(b * batch);
+    a.n_rec = batch;
     a.first = b == 0 ? 1 : 0;
     const cudaError_t e = kBanks[bank].launch(p.T, p.cs_ctas, threads, h->stream, a, (pdl && b > 0) ? 1 : 0);
     if (e == cudaErrorInvalidValue) return set_error(h, LPMX_ERR_STATE, "no constant-bank kernel for T = %d", p.T);
@@ -306,7 +339,7 @@ static int enqueue_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt,
     LPMX_CUDA(h, e);
     if (mode == 1) {
       LPMX_CUDA(h, cudaEventRecord(ev_summed[bank], h->stream));
-      if (b + 2 < n_batches) LPMX_TRY(fill_batch(b + 2));
+      if (b + nb < n_batches) LPMX_TRY(fill_batch(b + nb));
     }
   }
   if (p.rem.n_tgt > 0) {
@@ -330,13 +363,13 @@ namespace {
 struct CsGraphKey {
   const void *tgt, *self_idx, *packed, *partials, *stage, *tgt_map;
   long si, sk, n_tgt_pad, rem_pad;
-  int T, tb, ctas, n_const, n_tgt, n_src_pad, rem_n, rem_shape, rem_grid, mode, pf, pdl;
+  int T, tb, ctas, n_const, n_tgt, n_src_pad, rem_n, rem_shape, rem_grid, mode, pf, pdl, banks, batch;
   double kappa;
   bool operator==(const CsGraphKey& o) const {
     return tgt == o.tgt && self_idx == o.self_idx && packed == o.packed && partials == o.partials && stage == o.stage && tgt_map == o.tgt_map && si == o.si &&
            sk == o.sk && n_tgt_pad == o.n_tgt_pad && rem_pad == o.rem_pad && T == o.T && tb == o.tb && ctas == o.ctas &&
            n_const == o.n_const && n_tgt == o.n_tgt && n_src_pad == o.n_src_pad && rem_n == o.rem_n && rem_shape == o.rem_shape &&
-           rem_grid == o.rem_grid && mode == o.mode && pf == o.pf && pdl == o.pdl && kappa == o.kappa;
+           rem_grid == o.rem_grid && mode == o.mode && pf == o.pf && pdl == o.pdl && banks == o.banks && batch == o.batch && kappa == o.kappa;
   }
 };
 struct CsGraph {
@@ -367,16 +400,16 @@ int launch_const_stream(lpmx_handle_t h, const SumPlan& p, Vec3View tgt, const i
     const char* e = getenv("LPMX_CONST_GRAPH");
     return !(e && atoi(e) == 0);
   }();
-  const long n_batches = ((long)p.n_src_pad + kCsBatch - 1) / kCsBatch;
+  const long n_batches = ((long)p.n_src_pad + p.cs_batch - 1) / p.cs_batch;
   void* stage_v = nullptr;
-  LPMX_TRY(dev_buffer(h, "const_stage", sizeof(double) * kCsRec * (size_t)(n_batches * kCsBatch), &stage_v));
+  LPMX_TRY(dev_buffer(h, "const_stage", sizeof(double) * kCsRec * (size_t)(n_batches * p.cs_batch), &stage_v));
   long nl = 0, nb = 0;
   if (!use_graphs) return enqueue_const_stream(h, p, tgt, self_idx, packed, kappa, partials, tgt_map, mode, pf_stride, stage_v, &nl, &nb);
   if (!h->cs_graph_cache) h->cs_graph_cache = new CsGraphCache();
   CsGraphCache* cache = (CsGraphCache*)h->cs_graph_cache;
   if (cache->broken) return enqueue_const_stream(h, p, tgt, self_idx, packed, kappa, partials, tgt_map, mode, pf_stride, stage_v, &nl, &nb);
   CsGraphKey key{tgt.p, self_idx, packed, partials, stage_v, tgt_map, tgt.si, tgt.sk, p.n_tgt_pad, p.rem.n_tgt_pad, p.T, p.tb, p.cs_ctas,
-                 p.cs_n_const, p.n_tgt, p.n_src_pad, p.rem.n_tgt, p.rem.shape, p.rem.grid, mode, pf_stride, const_pdl() ? 1 : 0, kappa};
+                 p.cs_n_const, p.n_tgt, p.n_src_pad, p.rem.n_tgt, p.rem.shape, p.rem.grid, mode, pf_stride, const_pdl() ? 1 : 0, getenv("LPMX_CONST_BANKS") ? atoi(getenv("LPMX_CONST_BANKS")) : 0, p.cs_batch, kappa};
   CsGraph* g = nullptr;
   for (auto& e : cache->entries)
     if (e.key == key) g = &e;
@@ -437,11 +470,9 @@ void const_stream_teardown(lpmx_handle_t h) {
     cudaStreamDestroy(h->cs_stream);
     h->cs_stream = nullptr;
   }
-  for (int i = 0; i < 5; ++i)
-    if (h->cs_events[i]) {
-      cudaEventDestroy(h->cs_events[i]);
-      h->cs_events[i] = nullptr;
-    }
+  for (auto& e : h->cs_events)
+    if (e) cudaEventDestroy(e);
+  h->cs_events.clear();
 }
 
 }  // namespace lpmx

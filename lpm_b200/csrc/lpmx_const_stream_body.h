@@ -34,6 +34,7 @@ struct CsArgs {
   long n_tgt_pad;
   int n_tgt;
   int j0;     // compact index of the bank's first record
+  int n_rec;  // records of the bank this launch sums: kBatch, or kBatch / 2 (the kernel instance has it as a constant)
   int first;  // start from zero instead of the stored accumulators
   int prefetch_stride;  // doubles between the loads of the CTA's prefetch warp (GPU only; 0: no prefetch)
   double kappa;
@@ -44,13 +45,14 @@ struct CsArgs {
 // constant load to a uniform register has a latency that two warps per scheduler do not hide when it is issued right in
 // front of its first use -- r2q: short-scoreboard stalls, 77 % of the FP64 pipe).  The last iteration loads record kBatch:
 // the bank is declared one record longer (its content is never used).
-template <int T, bool CHECK, class P>
+// NREC: the trip count as a compile-time constant (a run-time bound costs the pipelined loop 2 %, r2z)
+template <int T, bool CHECK, int NREC, class P>
 LPMX_CS_HD void loop(P& pf, const double (&x)[T][3], const int (&self)[T], double (&acc)[T][3], int j0, double kappa) {
   double s[kRec], sn[kRec];
 #pragma unroll
   for (int k = 0; k < kRec; ++k) sn[k] = pf.src(k);
 #pragma unroll 2
-  for (int j = 0; j < kBatch; ++j) {
+  for (int j = 0; j < NREC; ++j) {
 #pragma unroll
     for (int k = 0; k < kRec; ++k) {
       s[k] = sn[k];
@@ -71,7 +73,7 @@ LPMX_CS_HD void loop(P& pf, const double (&x)[T][3], const int (&self)[T], doubl
   }
 }
 
-template <int T, class P>
+template <int T, int NREC = kBatch, class P>
 LPMX_CS_HD void body(P& pf, const CsArgs& a) {
   pf.launch_dependents();
   const int lanes = pf.n_threads();
@@ -90,12 +92,12 @@ LPMX_CS_HD void body(P& pf, const CsArgs& a) {
       acc[t][k] = 0.0;  // two-level summation: this launch's 1 280 terms start from zero (see the store below)
     }
     self[t] = (valid && a.self_idx) ? a.self_idx[ge] : -1;
-    hit |= (unsigned)(self[t] - a.j0) < (unsigned)kBatch;
+    hit |= (unsigned)(self[t] - a.j0) < (unsigned)NREC;
   }
   if (pf.any_sync(hit))
-    loop<T, true>(pf, x, self, acc, a.j0, a.kappa);
+    loop<T, true, NREC>(pf, x, self, acc, a.j0, a.kappa);
   else
-    loop<T, false>(pf, x, self, acc, a.j0, a.kappa);
+    loop<T, false, NREC>(pf, x, self, acc, a.j0, a.kappa);
   pf.wait_prior();  // the accumulators take the launches' sums in launch order
 #pragma unroll
   for (int t = 0; t < T; ++t) {

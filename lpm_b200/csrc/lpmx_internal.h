@@ -85,6 +85,7 @@ struct SumPlan {
   // reads them (lpmx_const_stream.cu).
   int cs_ctas = 0;
   int cs_n_const = 0;
+  int cs_batch = 0;  // source records per bank launch
   struct Rem {
     int shape = 0, T = 0, tb = 0, n_tgt = 0, n_tb = 0, grid = 0, max_slots = 0;
     long n_tgt_pad = 0;
@@ -137,7 +138,7 @@ struct lpmx_handle_s {
   int const_stream = -1;            // lpmx_pair_sum_const_stream: -1 = LPMX_CONST_STREAM from the environment
   long cs_launches = 0;             // bank-kernel launches so far (lpmx_const_stream_launch_count)
   void* cs_graph_cache = nullptr;   // captured launch sequences of the constant-bank path (lpmx_const_stream.cu)
-  cudaEvent_t cs_events[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // lpmx_const_stream.cu: repack, filled[2], summed[2]
+  std::vector<cudaEvent_t> cs_events;  // lpmx_const_stream.cu: repack, filled[kCsBanks], summed[kCsBanks]
   std::map<std::string, lpmx::DevBuf> bufs;  // named scratch buffers
   std::map<std::string, lpmx::DevBuf> pinned;  // named pinned host staging buffers
   // optional per-launch timing of the pair-sum kernel (lpmx_profile_enable)
@@ -206,12 +207,16 @@ constexpr int kCsMaxThreads = 544;  // 16 compute warps + the prefetch warp (T =
 // returns the modelled seconds of the whole evaluation (bank launches + remainder), *ring_s_out those of the ring kernel alone
 double pick_const_split(lpmx_handle_t h, int num_sms, int n_tgt, int n_src, int* T_out, int* nw_out, int* ctas_out, int* n_const_out,
                         double* ring_s_out);
-// the two banks (lpmx_const_bank0.cu, lpmx_const_bank1.cu)
+// the banks (lpmx_const_bank.cu compiled kCsBanks times, lpm_b200/build.py: N_CONST_BANKS)
+constexpr int kCsBanks = 24;
+#define LPMX_CS_BANK_LIST(X) \
+  X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18) X(19) X(20) X(21) X(22) X(23)
 namespace cs { struct CsArgs; }
-cudaError_t cs_bank_launch_0(int T, int grid, int threads, cudaStream_t stream, const cs::CsArgs& a, int pdl);
-cudaError_t cs_bank_launch_1(int T, int grid, int threads, cudaStream_t stream, const cs::CsArgs& a, int pdl);
-cudaError_t cs_bank_fill_0(const double* records, cudaStream_t stream);
-cudaError_t cs_bank_fill_1(const double* records, cudaStream_t stream);
+#define LPMX_CS_DECLARE(k)                                                                                               \
+  cudaError_t cs_bank_launch_##k(int T, int grid, int threads, cudaStream_t stream, const cs::CsArgs& a, int pdl); \
+  cudaError_t cs_bank_fill_##k(const double* records, int n_rec, cudaStream_t stream);
+LPMX_CS_BANK_LIST(LPMX_CS_DECLARE)
+#undef LPMX_CS_DECLARE
 int const_stream_mode(lpmx_handle_t h);
 void const_stream_teardown(lpmx_handle_t h);
 

@@ -63,6 +63,12 @@ struct SolverState {
   int cur = 0;
   int n_src_pad = 0;
   double* partials[2] = {nullptr, nullptr};  // per list
+  // Merged evaluation (sharded solvers on small meshes): the two lists summed by ONE bank sequence over gid[0][0 .. n_A + n_B)
+  // -- the lists are adjacent in `perm` -- into one accumulator array; the stage kernels of list A and list B then read their
+  // parts of it through pv_m (set for the duration of the stage launches of such an evaluation).
+  double* partials_m = nullptr;
+  bool merged_now = false;
+  PartView pv_m[2];
   std::vector<long> packed_off;    // world+1 offsets into packed (in doubles): rank r's leaves are [r L / W, (r+1) L / W)
   int n_local() const { return n_part[0] + n_part[1]; }
   Vec3View view(double* base) const {
@@ -636,7 +642,9 @@ static int solver_get_state(SolverState* s, double* vx, double* vz, double* vu, 
 static StageArgs stage_args(SolverState* s, int part, const SumPlan* plan, int stage, int more, double dt, double Omega,
                             double* packed_next) {
   StageArgs a;
-  if (plan)
+  if (plan && s->merged_now)
+    a.pv = s->pv_m[part];
+  else if (plan)
     a.pv = part_view(*plan, s->partials[part]);
   else
     a.pv = PartView{nullptr, 0, 0, 0, 1, 1};
@@ -676,10 +684,35 @@ static int pack_resident(SolverState* s) {
 
 // One evaluation over this rank's targets: per list, pair sum -> stage kernel (`stage_fn(part)` launches it); the records the
 // stage kernel of list A wrote into `next` are exchanged while list B is summed (see exchange_packed_begin).
+// `merged` (optional): a plan over both lists at once, used instead of plans[0..1] -- see SolverState::partials_m.  The exchange
+// of list A's records then starts after the whole sum instead of beside list B's, the price of one launch sequence that fills
+// the chip where two would not (make_merged_plan).
 template <class StageFn>
-static int eval_lists(SolverState* st, const SumPlan* plans, double* tgt_base, double kappa, double* next, StageFn stage_fn) {
+static int eval_lists(SolverState* st, const SumPlan* plans, double* tgt_base, double kappa, double* next, StageFn stage_fn,
+                      const SumPlan* merged = nullptr) {
   lpmx_handle_t h = st->h;
   bool async = false;
+  if (merged) {
+    void* pm = nullptr;
+    LPMX_TRY(dev_buffer(h, "solver_partials_m", plan_partials_bytes(*merged) + 256, &pm));
+    st->partials_m = (double*)pm;
+    LPMX_TRY(launch_pair_sum(h, *merged, st->view(tgt_base), st->self_idx, st->packed[st->cur], kappa, st->partials_m, 0.0, st->gid[0]));
+    st->pv_m[0] = part_view(*merged, st->partials_m);
+    st->pv_m[1] = part_view(*merged, st->partials_m + st->n_part[0]);
+    st->merged_now = true;
+    int rc = LPMX_OK;
+    for (int part = 0; part < 2 && rc == LPMX_OK; ++part) {
+      rc = stage_fn(part);
+      if (rc == LPMX_OK && part == 0 && next) rc = exchange_packed_begin(st, next, &async);
+    }
+    st->merged_now = false;
+    LPMX_TRY(rc);
+    if (next) {
+      LPMX_TRY(exchange_packed_end(st, async));
+      st->cur ^= 1;
+    }
+    return LPMX_OK;
+  }
   for (int part = 0; part < 2; ++part) {
     if (st->n_part[part] > 0) {
       LPMX_TRY(ensure_partials(st, part, plans[part]));
@@ -710,15 +743,36 @@ static int make_list_plans(SolverState* st, int kind, SumPlan* plans) {
   return LPMX_OK;
 }
 
+// One velocity plan over both lists, where that gets the bank path and the lists by themselves do not (a rank's share of a small
+// mesh: at cubed-7 on eight GPUs 12 288 + 16 384 targets per rank; the bank path wants a few dozen CTAs per launch).  Returns
+// whether to use it.  LPMX_MERGE_LISTS=0 / 1 overrides.
+static bool make_merged_plan(SolverState* st, const SumPlan* plans, SumPlan* merged) {
+  if (!st->split || st->n_part[0] == 0 || st->n_part[1] == 0) return false;
+  const char* e = getenv("LPMX_MERGE_LISTS");
+  if (e && e[0] == '0') return false;
+  if (make_plan(st->h, kVel, st->n_part[0] + st->n_part[1], st->n_leaf, merged) != LPMX_OK) return false;
+  if (merged->shape != kShapeConstStream) return false;
+  if (e && e[0] == '1') return true;
+  // measured (r2z, one GPU, a rank's target counts x 98 304 sources): 28 672 targets merged 1.62 ms against 0.77 + 1.04 ms for the
+  // two lists through the ring kernel (neither fills the banks' pipeline); 57 344 merged 3.07 ms, 114 688 merged 5.98 ms against
+  // 3.53 / 6.91 ms.  From 150 000 targets per rank the lists fill the pipeline by themselves and keep the overlapped exchange.
+  (void)plans;
+  return st->n_part[0] + st->n_part[1] < 150000;
+}
+
 }  // namespace lpmx
 
 struct lpmx_bve_solver_s {
   SolverState st;
   SumPlan plan_vel[2], plan_psi[2];  // per target list
+  SumPlan plan_vel_m;                // both lists at once (make_merged_plan)
+  bool merged = false;
 };
 struct lpmx_ic2d_solver_s {
   SolverState st;
   SumPlan plan_vel[2], plan_velpsi[2], plan_psi[2];  // per target list
+  SumPlan plan_vel_m;                                // both lists at once (make_merged_plan)
+  bool merged = false;
   double eps = 0;
   // Lazy stream function.  psi of the new state is an OUTPUT of a step that no later step reads (quirk B-i), and the fused
   // velocity + psi evaluation costs 2.4 x the velocity one.  advance() therefore ends with the velocity-only kernel and marks
@@ -778,6 +832,7 @@ int lpmx_bve_solver_set_state(lpmx_bve_solver_t s, const double* vx, const doubl
   if (!s) return LPMX_ERR_INVALID;
   LPMX_TRY(solver_set_state(&s->st, vx, vz, vu, fx, fz, fu, fa, fm, layout, vld, fld, /*skip_self=*/1));
   LPMX_TRY(make_list_plans(&s->st, kVel, s->plan_vel));
+  s->merged = make_merged_plan(&s->st, s->plan_vel, &s->plan_vel_m);
   LPMX_TRY(make_list_plans(&s->st, kPsi, s->plan_psi));
   return LPMX_OK;
 }
@@ -823,7 +878,7 @@ static int bve_eval(lpmx_bve_solver_s* s, int stage, int more, double dt, double
     bve_rk4_stage_kernel<<<blocks, threads, 0, h->stream>>>(a);
     ++h->launches;
     return check_cuda(h, cudaGetLastError(), "bve_rk4_stage_kernel launch");
-  });
+  }, s->merged ? &s->plan_vel_m : nullptr);
 }
 
 int lpmx_bve_solver_init_velocity(lpmx_bve_solver_t s) {
@@ -923,6 +978,7 @@ int lpmx_ic2d_solver_set_state(lpmx_ic2d_solver_t s, const double* px, const dou
   const int skip = std::fabs(s->eps) < DBL_EPSILON;
   LPMX_TRY(solver_set_state(&s->st, px, pz, pu, ax, az, au, aa, am, layout, pld, ald, skip));
   LPMX_TRY(make_list_plans(&s->st, kVel, s->plan_vel));
+  s->merged = make_merged_plan(&s->st, s->plan_vel, &s->plan_vel_m);
   LPMX_TRY(make_list_plans(&s->st, kVelPsi, s->plan_velpsi));
   LPMX_TRY(make_list_plans(&s->st, kPsi, s->plan_psi));
   s->psi_stale = false;
@@ -977,7 +1033,7 @@ static int ic2d_eval(lpmx_ic2d_solver_s* s, int stage, int more, double dt, doub
       ic2d_rk2_stage_kernel<false><<<blocks, threads, 0, h->stream>>>(a);
     ++h->launches;
     return check_cuda(h, cudaGetLastError(), "ic2d_rk2_stage_kernel launch");
-  });
+  }, (!with_psi && s->merged) ? &s->plan_vel_m : nullptr);
 }
 
 int lpmx_ic2d_solver_init_direct_sums(lpmx_ic2d_solver_t s) {

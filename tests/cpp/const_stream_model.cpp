@@ -100,7 +100,7 @@ static int run_case(int n_tgt, int n_src, int threads, bool collocated, bool soa
         const long js = (long)b * kBatch + j;
         g_banks[g_bank][(size_t)kRec * j + k] = js < n_src ? src[6 * (size_t)js + k] : 0.0;
       }
-    a.j0 = b * kBatch, a.first = b == 0;
+    a.j0 = b * kBatch, a.n_rec = kBatch, a.first = b == 0;
     launch<T>(a, grid, threads);
   }
   // direct evaluation: d formed as the kernel forms it (for random points the closest pairs have d ~ 1/N^2, and ANY double

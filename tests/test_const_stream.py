@@ -165,15 +165,20 @@ def test_gpu_const_stream_automatic_split_at_cubed7(pdl, monkeypatch):
 
 
 @pytest.mark.gpu
-def test_gpu_const_stream_with_split_target_lists(oracle, monkeypatch):
-    """What a rank of a multi-GPU run does on a large mesh -- list A (its leaf faces) and list B (vertices and divided faces)
-    as index lists, each through the banks + the ring remainder -- forced onto one GPU and a small mesh (LPMX_FORCE_SPLIT=1,
-    LPMX_CONST_MIN_TARGETS=1): two BVERK4 steps against the oracle, and the bank launches are counted."""
+@pytest.mark.parametrize("merge", ["0", "1"])
+def test_gpu_const_stream_with_split_target_lists(oracle, merge, monkeypatch):
+    """What a rank of a multi-GPU run does -- list A (its leaf faces) and list B (vertices and divided faces) as index lists --
+    forced onto one GPU and a small mesh (LPMX_FORCE_SPLIT=1, LPMX_CONST_MIN_TARGETS=1).  merge = 0: each list through its own
+    bank sequence (large meshes: the exchange of list A's records runs beside list B's sum); merge = 1: both lists through ONE
+    sequence into one accumulator array that the two stage kernels read at their offsets (small meshes: LPMX_MERGE_LISTS).
+    Two BVERK4 steps and two Incompressible2DRK2 steps against the oracle, and the bank launches are counted."""
     from lpm_b200 import gallery
     from lpm_b200.api import Engine, PolyMesh2d
     from conftest import field_rel_err
     monkeypatch.setenv("LPMX_FORCE_SPLIT", "1")
     monkeypatch.setenv("LPMX_CONST_MIN_TARGETS", "1")
+    monkeypatch.setenv("LPMX_MERGE_LISTS", merge)
+    lists = 1 if merge == "1" else 2
     for seed, depth in (("cubed", 5), ("icos", 5)):
         m = PolyMesh2d(seed, depth)
         f = gallery.RossbyHaurwitz54()
@@ -191,7 +196,17 @@ def test_gpu_const_stream_with_split_target_lists(oracle, monkeypatch):
             e.pair_sum_const_stream(1)
             c0 = e.const_stream_launch_count()
             e.bve_rk4_step(0.01, 2 * np.pi, *got, m.face_area, m.face_mask, n_steps=2)
-            assert e.const_stream_launch_count() - c0 >= 2 * 4 * 2 * 4  # 2 steps x 4 evaluations x 2 lists x >= 4 banks
+            n = e.const_stream_launch_count() - c0
+            n_banks = -(-int(leaf.sum()) // 640)  # target sets below 100 000: half a bank (640 records) per launch
+            assert n == 2 * 4 * lists * n_banks, (n, lists, n_banks)  # 2 steps x 4 evaluations x sequences x bank launches
+            # Incompressible2DRK2 with eps = 0 and a lazy psi: the velocity-only evaluations take the same path
+            ic_ref = [m.vert_xyz.copy(), f(m.vert_xyz), vu.copy(), np.zeros(m.n_verts), m.face_xyz.copy(), fz.copy(), fu.copy(),
+                      np.zeros(m.n_faces)]
+            ic_got = [a.copy() for a in ic_ref]
+            oracle.ic2d_rk2_step(0.01, 2 * np.pi, 0.0, *ic_ref, m.face_area, m.face_mask, n_steps=2)
+            e.ic2d_rk2_step(0.01, 2 * np.pi, 0.0, *ic_got, m.face_area, m.face_mask, n_steps=2)
+            for k, sel, tol in ((0, None, 1e-12), (1, None, 1e-10), (2, None, 1e-12), (4, leaf, 1e-12), (5, leaf, 1e-10), (6, leaf, 1e-12)):
+                assert field_rel_err(ic_got[k], ic_ref[k], sel) <= tol, ("ic2d", seed, k, field_rel_err(ic_got[k], ic_ref[k], sel))
         finally:
             e.close()
         for k, sel, tol in ((0, None, 1e-12), (1, None, 1e-10), (2, None, 1e-12), (3, leaf, 1e-12), (4, leaf, 1e-10), (5, leaf, 1e-12)):
