@@ -210,21 +210,22 @@ int lpmx_comm_enable_peer_exchange(lpmx_handle_t h, int enable);
 /* enabled: 1 when exchanges of mapped slabs take the peer path; n_regions: slabs currently mapped. */
 int lpmx_comm_peer_exchange_enabled(lpmx_handle_t h, int* enabled, int* n_regions);
 
-/* Velocity pair sums with the source records streamed through the constant bank (lpm_b200/csrc/lpmx_const_stream.cu,
- * DESIGN.md section 4.1b): sources reach the DFMAs as uniform-register operands (88 % of the FP64 pipe against 80 %).  The
- * path takes whole waves of the chip (148 CTAs x T targets per thread x 256 threads); the targets that would leave a last wave
- * mostly empty go through the default kernel in the same call.
- * mode -1 (default): LPMX_CONST_STREAM from the environment, else AUTO = used for velocity launches from 189 440 targets per
- * rank (one wave of T = 5) where the modelled time beats the default kernel's; 0: off; 1: forced, bank copies overlapped with
- * the launches; 2: forced, copies on the compute stream.  Affects the plans made AFTER the call (solvers created / states set
- * afterwards).  The two banks are __constant__ arrays of two modules, one pair per device: the first handle of a process that
- * takes the path on a device owns them until lpmx_destroy (or mode 0); other handles on that device keep the default kernel.
- * Same per-pair arithmetic as the default kernel; per-target sums differ by round-off. */
+/* Velocity pair sums with the source records streamed through constant banks (lpm_b200/csrc/lpmx_const_stream.cu,
+ * DESIGN.md section 4.1b): sources reach the DFMAs as uniform-register operands (94-96 % of the FP64 peak issued over whole
+ * evaluations against 80 % for the default kernel).  24 banks in rotation, the launches pipelined with programmatic dependent
+ * launch, one CUDA graph launch per evaluation.
+ * mode -1 (default): LPMX_CONST_STREAM from the environment, else AUTO = used for velocity launches from 16 384 targets where the
+ * planner's modelled time beats the default kernel's by 2 % (cubed-7 on one to eight GPUs, everything larger); 0: off; 1: forced,
+ * bank refills overlapped with the launches; 2: forced, refills on the compute stream.  Affects the plans made AFTER the call
+ * (solvers created / states set afterwards).  The banks are __constant__ arrays of 24 modules, one set per device: the first
+ * handle of a process that takes the path on a device owns them until lpmx_destroy (or mode 0); other handles on that device
+ * keep the default kernel.  Same per-pair arithmetic as the default kernel; per-target sums differ by round-off. */
 int lpmx_pair_sum_const_stream(lpmx_handle_t h, int mode);
-/* How that path would split n_tgt targets x n_src sources on a GPU with num_sms SMs (host-only planning query): T targets
- * per thread, n_warps warps per CTA, ctas CTAs per bank launch covering the first n_const targets (the other n_tgt - n_const
- * go through the default kernel); model_seconds / ring_seconds (may be null): the modelled duration of the evaluation on
- * that split and on the default kernel alone -- AUTO takes the path when the former is below 0.98 x the latter. */
+/* How that path would run n_tgt targets x n_src sources on a GPU with num_sms SMs (host-only planning query): T targets per
+ * thread, n_warps compute warps per CTA, ctas CTAs per bank launch covering the first n_const targets (all of them with
+ * pipelined launches; with LPMX_CONST_PDL=0 whole waves, the other n_tgt - n_const go through the default kernel);
+ * model_seconds / ring_seconds (may be null): the modelled duration of the evaluation on that path and on the default kernel
+ * alone -- AUTO takes the path when the former is below 0.98 x the latter. */
 int lpmx_const_stream_split(int num_sms, int n_tgt, int n_src, int* T, int* n_warps, int* ctas, int* n_const,
                             double* model_seconds, double* ring_seconds);
 /* Bank-kernel launches issued by this handle so far (0 = every pair sum went through the default kernel): lets a caller

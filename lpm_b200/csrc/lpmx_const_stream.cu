@@ -1,33 +1,34 @@
-// lpmx_const_stream.cu -- the velocity pair sum with the source records streamed through the CONSTANT bank, so that
-// they reach the DFMAs as uniform-register operands (SASS: LDCU.64 + DFMA R, R, UR, R).
+// lpmx_const_stream.cu -- the velocity pair sum with the source records streamed through CONSTANT banks, so that they reach
+// the DFMAs as uniform-register operands (SASS: LDCU.64 + DFMA R, R, UR, R).  Host side: planning, the launch sequence of one
+// evaluation, its CUDA graph.  Device side: lpmx_const_bank.cuh (one bank + its kernels, compiled once per bank) and
+// lpmx_const_stream_body.h (the kernel body, shared with a host model).  DESIGN.md section 4.1b has the measurements.
 //
-// Why: pair_sum_kernel (lpmx_pair_kernel.cuh) is bound by FP64 issue and reaches 80 % of the pipe because 5 of its 9
-// DFMAs per pair read a third distinct register operand (profiles/README.md, "Why 81 %").  A source record is the same
-// for every thread; read from c[3][..] it costs no register-file port.  Measured with one bank of two 640-record halves
-// (profiles/r2b_*, r2e_*): icos-8 (2.40 M targets x 1.31 M sources) 1.657e12 -> 1.797e12 interactions/s (+8.5 %), 88 % of the
-// FP64 pipe; but cubed-7 (229 376 targets) 54.9 -> 66.4 ms, because all CTAs of a launch share the sources (the work cannot
-// be split over sources the way the stream-K kernel does), so a launch over 229 376 targets was either two waves with the
-// second one 1 % full (T = 6, 8 warps) or unbalanced over the SM's four schedulers (10 warps).
+// Why: pair_sum_kernel (lpmx_pair_kernel.cuh) is bound by FP64 issue and reaches 80 % of the pipe because 5 of its 9 DFMAs
+// per pair read a third distinct register operand (profiles/README.md, "Why 81 %").  A source record is the same for every
+// thread; read from c[3][..] it costs no register-file port: 94-96 % of the FP64 peak in issued DFMAs over whole evaluations.
 //
-// How (round 2, second cut):
-//   * TWO banks.  lpmx_const_bank0.cu and lpmx_const_bank1.cu are separate modules, each with its own 64 KB user constant
-//     bank holding cs::kBatch = 1 280 records x 48 B {y0, y1, y2, G*y0, G*y1, G*y2}.  A launch of bank b's kernel sums that
-//     whole bank into its targets (accumulators live in slot 0 of the partials buffer between launches: 24 B per target per
-//     launch, three orders of magnitude below the FP64 time) while a device-to-device copy on the handle's copy stream
-//     refills the other bank.  Half as many launches -- and launch gaps, target loads, accumulator read-modify-writes -- as
-//     the two 640-record halves of one bank.
-//   * WHOLE WAVES ONLY.  The bank path takes the first waves x 148 x (T x 8 warps x 32) targets -- one CTA per SM, every CTA
-//     of every wave full -- and the ring kernel (stream-K, no wave quantisation) the rest, into slots behind the bank path's
-//     accumulators; cs_fold_kernel adds them into slot 0, so the stage kernels see one layout.  cubed-7: 1 wave of T = 6
-//     = 227 328 targets through the bank, 2 048 through the ring kernel.
-//   * pick_const_split chooses T in {5, 6, 7}, the number of waves and the remainder by modelled time (measured rates of
-//     both kernels, a fixed cost per launch), and the AUTO mode takes the path only where the model beats the ring kernel
-//     alone by 2 %: from one full wave of T = 5 (189 440 targets per rank) upwards.
-// LPMX_CONST_STREAM=0 turns the path off, =1 forces it wherever one wave can be filled (copies overlapped), =2 forces it
-// with the copies on the compute stream; lpmx_pair_sum_const_stream() sets the same per handle.
+// How:
+//   * BANKS ARE MODULES.  lpmx_const_bank.cu is compiled kCsBanks = 24 times; every object is its own module with its own
+//     64 KB user constant bank of cs::kBatch = 1 280 records x 48 B {y0, y1, y2, G*y0, G*y1, G*y2}.  A launch of bank b's
+//     kernel sums that bank into all targets of the launch (accumulators live in slot 0 of the partials buffer between
+//     launches, added with RED.ADD.F64); device-to-device copies on the handle's cs_stream refill a bank once the launch
+//     that read it has completed.
+//   * PIPELINED LAUNCHES (programmatic dependent launch, LPMX_CONST_PDL, default on).  CTAs of launch b + 1 take the slots
+//     the CTAs of launch b leave and sum their own bank beside them; only their reduction into the accumulators waits for
+//     launch b, so the additions per target keep the launch order (bit-identical to the serial sequence).  No waves to fill,
+//     no remainder: every target goes through the banks in CTAs of 6 x 128 targets + a prefetch warp, three per SM, and as
+//     many launches are in flight as it takes to fill the chip's 444 CTA slots -- one per bank in rotation, which is why a
+//     rank's share of a small mesh (38 CTAs per launch at cubed-7 on eight GPUs) needs a dozen banks and more.
+//   * ONE GRAPH LAUNCH PER EVALUATION: the ~80 (160) launches, as many refills and their event edges are captured the second
+//     time a sequence comes by and replayed from then on (LPMX_CONST_GRAPH).
+//   * WITHOUT THE PIPELINING (LPMX_CONST_PDL=0) all CTAs of a launch start together, so the launch has to fill whole waves:
+//     pick_const_split then takes waves x 148 CTAs of 8 warps through two banks and hands the remainder to the ring kernel,
+//     whose slots cs_fold_kernel adds into slot 0 (the state of r2s; kept, and tested, as the fallback).
+// LPMX_CONST_STREAM=0 turns the path off, =1 forces it wherever a launch exists (refills overlapped), =2 forces it with the
+// refills on the compute stream; lpmx_pair_sum_const_stream() sets the same per handle.
 //
 // Same arithmetic per pair as Pair<kVel> (bit-identical terms); per target the terms are added in source order in blocks of
-// 1 280, so the sums differ from the stream-K kernel's by round-off only (the tolerance of every parity test covers both).
+// 1 280 (640), so the sums differ from the stream-K kernel's by round-off only (the tolerance of every parity test covers both).
 #include <cstdlib>
 #include <mutex>
 #include <vector>
