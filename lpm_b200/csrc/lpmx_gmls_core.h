@@ -109,12 +109,20 @@ LPMX_HD double power_weight(double r_over_eps, double p) {
 LPMX_HD int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
 // In-place Cholesky of the leading np x np block of the packed matrix M and solution of M a = r for two right-hand
-// sides.  Returns false when a pivot is not positive (too few / degenerate neighbours).
+// sides.  Returns false when a pivot is not positive (too few / degenerate neighbours) or when the pivots span more than
+// kMaxPivotRatio: the fit is then ill-conditioned (cond(P^T W P) ~ max pivot / min pivot; the scaled basis keeps it below 1e7 on
+// the quasi-uniform meshes) and its Taylor coefficients carry no digits -- the callers return NaN instead of a number that
+// looks like a Laplacian (strongly non-uniform clouds, e.g. all neighbours of a target along one line).
+constexpr double kMaxPivotRatio = 1e12;
 LPMX_HD bool cholesky_factor(int np, double* M) {
+  double dmin = 0.0, dmax = 0.0;
   for (int j = 0; j < np; ++j) {
     double d = M[tri(j, j)];
     for (int k = 0; k < j; ++k) d -= M[tri(j, k)] * M[tri(j, k)];
     if (!(d > 0.0)) return false;
+    dmin = (j == 0 || d < dmin) ? d : dmin;
+    dmax = d > dmax ? d : dmax;
+    if (!(dmin * kMaxPivotRatio > dmax)) return false;
     d = sqrt(d);
     M[tri(j, j)] = d;
     for (int i = j + 1; i < np; ++i) {

@@ -81,6 +81,23 @@ def test_points_slightly_off_the_sphere_and_other_radii():
     assert field_rel_err(lap2 * 2.5 ** 2, lap1) < 1e-9 and np.abs(eps2 / 2.5 - eps1).max() < 1e-14
 
 
+def test_ill_conditioned_fit_is_reported_as_nan():
+    """A cloud whose points all lie (to 1e-9) on one great circle: every target's neighbours are on a line in its tangent plane,
+    the moment matrix has no information across it, and the fit's coefficients carry no digits.  The Cholesky pivots then span
+    more than 1e12 and the core returns NaN -- on the quasi-uniform meshes the same check never fires (all finite)."""
+    rng = np.random.default_rng(7)
+    n = 3000
+    lam = np.sort(rng.uniform(0, 2 * np.pi, n))
+    xyz = np.stack([np.cos(lam), np.sin(lam), 1e-9 * rng.standard_normal(n)], axis=1)
+    xyz /= np.linalg.norm(xyz, axis=1)[:, None]
+    p = GO.params(4)
+    lap, _, _ = core_host_laplacian(xyz, np.cos(3 * lam), p)
+    assert np.isnan(lap).all()
+    _, x_ok = _cloud("icos", 3)
+    lap_ok, _, _ = core_host_laplacian(x_ok, harmonic_field(x_ok)[0], p)
+    assert np.isfinite(lap_ok).all()
+
+
 def test_gather_scatter_restatement_round_trip():
     m = PolyMesh2d("icos", 2)
     rng = np.random.default_rng(5)
