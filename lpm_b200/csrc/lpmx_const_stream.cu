@@ -88,7 +88,8 @@ __global__ void cs_fold_kernel(const double* __restrict__ rem, long rem_pad, int
 
 }  // namespace
 
-// -1 auto (overlapped copies, large launches only), 0 off, 1 overlapped copies, 2 copies on the compute stream
+// -1 auto (overlapped refills, where the planner's model beats the ring kernel), 0 off, 1 forced with overlapped refills,
+// 2 forced with the refills on the compute stream
 int const_stream_mode(lpmx_handle_t h) {
   if (h->const_stream >= 0) return h->const_stream;
   static const int env = [] {
@@ -99,7 +100,7 @@ int const_stream_mode(lpmx_handle_t h) {
   return env;
 }
 
-// The two banks are module-scope __constant__ arrays, one pair per device, ordered only by the using handle's streams and
+// The banks are module-scope __constant__ arrays, one set per device, ordered only by the using handle's streams and
 // events: two handles on the same device must not stream through them at once.  The first handle to take the path on a device
 // owns the banks until lpmx_destroy; any other handle on that device keeps the ring kernel.
 static std::mutex g_bank_mutex;
