@@ -53,31 +53,43 @@ def _run(cmd, verbose, log):
         sys.stdout.write(p.stdout + p.stderr)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, jobs=None):
+    """Compile what is stale (all of it with force) and link; the compile steps are independent and run `jobs` at a time
+    (default: the host's cores, at most 8)."""
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     objs = []
-    log = []
+    cmds = []
     for src in CU_SOURCES:
         path = os.path.join(CSRC, src)
         if not os.path.exists(path):
             continue
         obj = os.path.join(OBJ, src + ".o")
         if force or _stale(obj, [path] + hdrs):
-            _run([_nvcc()] + NVCC_FLAGS + ["-c", path, "-o", obj], verbose, log)
+            cmds.append([_nvcc()] + NVCC_FLAGS + ["-c", path, "-o", obj])
         objs.append(obj)
     bank_src = os.path.join(CSRC, "lpmx_const_bank.cu")
     for k in range(N_CONST_BANKS):
         obj = os.path.join(OBJ, "lpmx_const_bank%d.cu.o" % k)
         if force or _stale(obj, [bank_src] + hdrs):
-            _run([_nvcc()] + NVCC_FLAGS + ["-DLPMX_CS_BANK=%d" % k, "-c", bank_src, "-o", obj], verbose, log)
+            cmds.append([_nvcc()] + NVCC_FLAGS + ["-DLPMX_CS_BANK=%d" % k, "-c", bank_src, "-o", obj])
         objs.append(obj)
     for src in CXX_SOURCES:
         path = os.path.join(CSRC, src)
         obj = os.path.join(OBJ, src + ".o")
         if force or _stale(obj, [path] + hdrs):
-            _run(["g++"] + CXX_FLAGS + ["-c", path, "-o", obj], verbose, log)
+            cmds.append(["g++"] + CXX_FLAGS + ["-c", path, "-o", obj])
         objs.append(obj)
+    log = []
+    if cmds:
+        jobs = jobs or max(1, min(8, os.cpu_count() or 1))
+        logs = [[] for _ in cmds]
+        with ThreadPoolExecutor(max_workers=jobs) as pool:
+            for f in [pool.submit(_run, c, verbose, lg) for c, lg in zip(cmds, logs)]:
+                f.result()  # re-raises the first failure
+        for lg in logs:
+            log += lg
     if force or _stale(LIB, objs):
         _run([_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"], verbose, log)
     with open(os.path.join(OBJ, "build.log"), "a") as f:
